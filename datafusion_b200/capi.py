@@ -1,0 +1,573 @@
+"""ctypes binding of include/dfgpu.h — the only way Python reaches the CUDA path.
+
+There is NO CPU fallback here: if libdfgpu.so is missing or no CUDA device is present, every
+entry point raises.  (The CPU restatement lives in oracle/ and is test infrastructure only.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdfgpu.so")
+
+# ---- enums (mirror include/dfgpu.h) -------------------------------------------------------
+OK, END = 0, 1
+BOOL, INT8, INT16, INT32, INT64, UINT8, UINT16, UINT32, UINT64, FLOAT32, FLOAT64, DATE32, DATE64, TIMESTAMP, DECIMAL128 = range(1, 16)
+
+EXPR_COLUMN, EXPR_LITERAL, EXPR_BINARY, EXPR_NOT, EXPR_IS_NULL, EXPR_IS_NOT_NULL, EXPR_NEGATIVE, EXPR_CAST = range(1, 9)
+(OP_EQ, OP_NEQ, OP_LT, OP_LTEQ, OP_GT, OP_GTEQ, OP_PLUS, OP_MINUS, OP_MULTIPLY, OP_DIVIDE, OP_MODULO, OP_AND, OP_OR,
+ OP_IS_DISTINCT_FROM, OP_IS_NOT_DISTINCT_FROM, OP_BITAND, OP_BITOR, OP_BITXOR, OP_SHIFT_LEFT, OP_SHIFT_RIGHT) = range(1, 21)
+
+(JOIN_INNER, JOIN_LEFT, JOIN_RIGHT, JOIN_FULL, JOIN_LEFT_SEMI, JOIN_RIGHT_SEMI, JOIN_LEFT_ANTI, JOIN_RIGHT_ANTI,
+ JOIN_LEFT_MARK, JOIN_RIGHT_MARK) = range(10)
+NULL_EQUALS_NOTHING, NULL_EQUALS_NULL = 0, 1
+
+AGG_PARTIAL, AGG_FINAL, AGG_FINAL_PARTITIONED, AGG_SINGLE, AGG_SINGLE_PARTITIONED, AGG_PARTIAL_REDUCE = range(6)
+AGG_SUM, AGG_COUNT, AGG_MIN, AGG_MAX, AGG_AVG, AGG_COUNT_STAR = range(1, 7)
+
+GEN_SEQ, GEN_UNIFORM, GEN_SPLITMIX, GEN_PERM, GEN_SPARSE_OF = range(5)
+
+NP_OF_TYPE = {
+    INT8: np.int8, INT16: np.int16, INT32: np.int32, INT64: np.int64, UINT8: np.uint8, UINT16: np.uint16,
+    UINT32: np.uint32, UINT64: np.uint64, FLOAT32: np.float32, FLOAT64: np.float64, DATE32: np.int32,
+    DATE64: np.int64, TIMESTAMP: np.int64,
+}
+TYPE_OF_NP = {np.dtype(v): k for k, v in NP_OF_TYPE.items() if k not in (DATE32, DATE64, TIMESTAMP)}
+TYPE_OF_NP[np.dtype(np.bool_)] = BOOL
+WIDTH = {BOOL: 0, INT8: 1, UINT8: 1, INT16: 2, UINT16: 2, INT32: 4, UINT32: 4, FLOAT32: 4, DATE32: 4, INT64: 8,
+         UINT64: 8, FLOAT64: 8, DATE64: 8, TIMESTAMP: 8, DECIMAL128: 16}
+
+
+class DfgpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"dfgpu error {code}: {msg}")
+        self.code = code
+
+
+class Column(C.Structure):
+    _fields_ = [("type", C.c_int32), ("flags", C.c_int32), ("length", C.c_int64), ("offset", C.c_int64),
+                ("null_count", C.c_int64), ("values", C.c_void_p), ("validity", C.c_void_p)]
+
+
+class ExprNode(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("a", C.c_int32), ("type", C.c_int32), ("is_null", C.c_int32),
+                ("lit_i64", C.c_int64), ("lit_f64", C.c_double)]
+
+
+class HashJoinOptions(C.Structure):
+    _fields_ = [("join_type", C.c_int32), ("null_equality", C.c_int32), ("batch_size", C.c_int64),
+                ("perfect_hash_join_small_build_threshold", C.c_int64), ("perfect_hash_join_min_key_density", C.c_double),
+                ("force_hash_collisions", C.c_int32), ("ordered_output", C.c_int32)]
+
+
+class AggDesc(C.Structure):
+    _fields_ = [("func", C.c_int32), ("arg_col", C.c_int32), ("filter_col", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ArrowSchema(C.Structure):
+    pass
+
+
+class ArrowArray(C.Structure):
+    pass
+
+
+ArrowSchema._fields_ = [("format", C.c_char_p), ("name", C.c_char_p), ("metadata", C.c_char_p), ("flags", C.c_int64),
+                        ("n_children", C.c_int64), ("children", C.POINTER(C.POINTER(ArrowSchema))),
+                        ("dictionary", C.POINTER(ArrowSchema)), ("release", C.c_void_p), ("private_data", C.c_void_p)]
+ArrowArray._fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64), ("n_buffers", C.c_int64),
+                       ("n_children", C.c_int64), ("buffers", C.POINTER(C.c_void_p)),
+                       ("children", C.POINTER(C.POINTER(ArrowArray))), ("dictionary", C.POINTER(ArrowArray)),
+                       ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+# every symbol include/dfgpu.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "dfgpu_ctx_create", "dfgpu_ctx_destroy", "dfgpu_last_error", "dfgpu_version", "dfgpu_device_count", "dfgpu_sync",
+    "dfgpu_ctx_stream", "dfgpu_malloc", "dfgpu_free", "dfgpu_host_alloc", "dfgpu_host_free", "dfgpu_memcpy_h2d",
+    "dfgpu_memcpy_d2h", "dfgpu_memset", "dfgpu_flush_l2", "dfgpu_event_create", "dfgpu_event_record",
+    "dfgpu_event_elapsed_ms", "dfgpu_event_destroy", "dfgpu_launch_count", "dfgpu_generate_i64",
+    "dfgpu_filter_create", "dfgpu_filter_push_host", "dfgpu_filter_push_device", "dfgpu_filter_push_arrow",
+    "dfgpu_filter_finish", "dfgpu_filter_next", "dfgpu_filter_metric", "dfgpu_filter_destroy",
+    "dfgpu_expr_evaluate_device", "dfgpu_expr_evaluate_host",
+    "dfgpu_hashjoin_default_options", "dfgpu_hashjoin_create", "dfgpu_hashjoin_push_build_host",
+    "dfgpu_hashjoin_push_build_device", "dfgpu_hashjoin_push_build_arrow", "dfgpu_hashjoin_finish_build",
+    "dfgpu_hashjoin_push_probe_host", "dfgpu_hashjoin_push_probe_device", "dfgpu_hashjoin_push_probe_arrow",
+    "dfgpu_hashjoin_finish_probe", "dfgpu_hashjoin_next", "dfgpu_hashjoin_metric", "dfgpu_hashjoin_destroy",
+    "dfgpu_agg_create", "dfgpu_agg_push_host", "dfgpu_agg_push_device", "dfgpu_agg_push_arrow", "dfgpu_agg_finish",
+    "dfgpu_agg_next", "dfgpu_agg_metric", "dfgpu_agg_destroy",
+    "dfgpu_batch_num_rows", "dfgpu_batch_num_columns", "dfgpu_batch_column", "dfgpu_batch_is_host",
+    "dfgpu_batch_export_arrow", "dfgpu_batch_release", "dfgpu_hash_partition_device",
+]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen libdfgpu.so (built in-tree by __graft_entry__.build()). Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+    P = C.POINTER
+
+    def sig(name, res, args):
+        f = getattr(lib, name)
+        f.restype = res
+        f.argtypes = args
+
+    sig("dfgpu_ctx_create", C.c_int, [C.c_int, vp, P(vp)])
+    sig("dfgpu_ctx_destroy", None, [vp])
+    sig("dfgpu_last_error", C.c_char_p, [vp])
+    sig("dfgpu_version", C.c_char_p, [])
+    sig("dfgpu_device_count", C.c_int, [])
+    sig("dfgpu_sync", C.c_int, [vp])
+    sig("dfgpu_ctx_stream", vp, [vp])
+    sig("dfgpu_malloc", C.c_int, [vp, C.c_size_t, P(vp)])
+    sig("dfgpu_free", C.c_int, [vp, vp])
+    sig("dfgpu_host_alloc", C.c_int, [vp, C.c_size_t, P(vp)])
+    sig("dfgpu_host_free", C.c_int, [vp, vp])
+    sig("dfgpu_memcpy_h2d", C.c_int, [vp, vp, vp, C.c_size_t])
+    sig("dfgpu_memcpy_d2h", C.c_int, [vp, vp, vp, C.c_size_t])
+    sig("dfgpu_memset", C.c_int, [vp, vp, C.c_int, C.c_size_t])
+    sig("dfgpu_flush_l2", C.c_int, [vp])
+    sig("dfgpu_event_create", C.c_int, [vp, P(vp)])
+    sig("dfgpu_event_record", C.c_int, [vp, vp])
+    sig("dfgpu_event_elapsed_ms", C.c_int, [vp, vp, vp, P(C.c_float)])
+    sig("dfgpu_event_destroy", C.c_int, [vp, vp])
+    sig("dfgpu_launch_count", i64, [vp])
+    sig("dfgpu_generate_i64", C.c_int, [vp, C.c_int, u64, i64, i64, i64, i64, vp])
+    sig("dfgpu_filter_create", C.c_int, [vp, P(i32), i32, P(ExprNode), i32, P(i32), i32, i64, i64, P(vp)])
+    for n in ("dfgpu_filter_push_host", "dfgpu_filter_push_device", "dfgpu_hashjoin_push_build_host",
+              "dfgpu_hashjoin_push_build_device", "dfgpu_hashjoin_push_probe_host", "dfgpu_hashjoin_push_probe_device",
+              "dfgpu_agg_push_host", "dfgpu_agg_push_device"):
+        sig(n, C.c_int, [vp, P(Column), i32])
+    for n in ("dfgpu_filter_push_arrow", "dfgpu_hashjoin_push_build_arrow", "dfgpu_hashjoin_push_probe_arrow",
+              "dfgpu_agg_push_arrow"):
+        sig(n, C.c_int, [vp, vp, vp])
+    for n in ("dfgpu_filter_finish", "dfgpu_hashjoin_finish_build", "dfgpu_hashjoin_finish_probe", "dfgpu_agg_finish"):
+        sig(n, C.c_int, [vp])
+    for n in ("dfgpu_filter_next", "dfgpu_hashjoin_next", "dfgpu_agg_next"):
+        sig(n, C.c_int, [vp, C.c_int, P(vp)])
+    for n in ("dfgpu_filter_metric", "dfgpu_hashjoin_metric", "dfgpu_agg_metric"):
+        sig(n, i64, [vp, C.c_char_p])
+    for n in ("dfgpu_filter_destroy", "dfgpu_hashjoin_destroy", "dfgpu_agg_destroy", "dfgpu_batch_release"):
+        sig(n, None, [vp])
+    sig("dfgpu_expr_evaluate_device", C.c_int, [vp, P(Column), i32, i64, P(ExprNode), i32, P(vp)])
+    sig("dfgpu_expr_evaluate_host", C.c_int, [vp, P(Column), i32, i64, P(ExprNode), i32, P(vp)])
+    sig("dfgpu_hashjoin_default_options", None, [P(HashJoinOptions)])
+    sig("dfgpu_hashjoin_create", C.c_int, [vp, P(i32), i32, P(i32), i32, P(i32), P(i32), i32, P(i32), P(i32), i32,
+                                           P(HashJoinOptions), P(vp)])
+    sig("dfgpu_agg_create", C.c_int, [vp, P(i32), i32, P(i32), i32, P(AggDesc), i32, i32, i64, i64, P(vp)])
+    sig("dfgpu_batch_num_rows", i64, [vp])
+    sig("dfgpu_batch_num_columns", i32, [vp])
+    sig("dfgpu_batch_column", C.c_int, [vp, i32, P(Column)])
+    sig("dfgpu_batch_is_host", C.c_int, [vp])
+    sig("dfgpu_batch_export_arrow", C.c_int, [vp, vp, vp])
+    sig("dfgpu_hash_partition_device", C.c_int, [vp, P(Column), i32, P(i32), i32, i32, P(vp), P(i64)])
+    _lib = lib
+    return lib
+
+
+def _i32arr(xs: Sequence[int]):
+    return (C.c_int32 * max(len(xs), 1))(*xs)
+
+
+# ---- context ------------------------------------------------------------------------------
+class Context:
+    """dfgpu_ctx: one device + one CUDA stream.  stream: an existing cudaStream_t (int) or None."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.dfgpu_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != OK:
+            raise DfgpuError(rc, "cannot create a CUDA context (no GPU / driver?) — there is no CPU fallback")
+        self.h = h
+        self.device = device
+
+    def check(self, rc: int):
+        if rc < 0:
+            raise DfgpuError(rc, self.lib.dfgpu_last_error(self.h).decode())
+        return rc
+
+    def close(self):
+        if self.h:
+            self.lib.dfgpu_ctx_destroy(self.h)
+            self.h = None
+
+    def sync(self):
+        self.check(self.lib.dfgpu_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return self.lib.dfgpu_launch_count(self.h)
+
+    def flush_l2(self):
+        self.check(self.lib.dfgpu_flush_l2(self.h))
+
+    # memory
+    def malloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self.check(self.lib.dfgpu_malloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def free(self, ptr: int):
+        self.check(self.lib.dfgpu_free(self.h, C.c_void_p(ptr)))
+
+    def pinned_empty(self, n: int, dtype) -> np.ndarray:
+        """numpy array backed by pinned host memory (kept alive by the returned array's base)."""
+        dtype = np.dtype(dtype)
+        nbytes = max(int(n) * dtype.itemsize, 8)
+        p = C.c_void_p()
+        self.check(self.lib.dfgpu_host_alloc(self.h, nbytes, C.byref(p)))
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        owner = _PinnedOwner(self, p.value, buf)
+        arr = np.frombuffer(owner, dtype=dtype, count=int(n)) if n else np.empty(0, dtype)
+        return arr
+
+    def to_device(self, arr: np.ndarray) -> "DeviceBuffer":
+        arr = np.ascontiguousarray(arr)
+        d = DeviceBuffer(self, arr.nbytes)
+        self.check(self.lib.dfgpu_memcpy_h2d(self.h, C.c_void_p(d.ptr), arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+        self.sync()
+        return d
+
+    def to_host(self, ptr: int, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, np.uint8)
+        if nbytes:
+            self.check(self.lib.dfgpu_memcpy_d2h(self.h, out.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), nbytes))
+            self.sync()
+        return out
+
+    # timing
+    def event(self) -> int:
+        e = C.c_void_p()
+        self.check(self.lib.dfgpu_event_create(self.h, C.byref(e)))
+        return e.value
+
+    def record(self, ev: int):
+        self.check(self.lib.dfgpu_event_record(self.h, C.c_void_p(ev)))
+
+    def elapsed_ms(self, start: int, stop: int) -> float:
+        ms = C.c_float()
+        self.check(self.lib.dfgpu_event_elapsed_ms(self.h, C.c_void_p(start), C.c_void_p(stop), C.byref(ms)))
+        return ms.value
+
+    def generate_i64(self, kind: int, seed: int, a: int, b: int, start: int, n: int) -> "DeviceBuffer":
+        d = DeviceBuffer(self, max(n, 1) * 8)
+        self.check(self.lib.dfgpu_generate_i64(self.h, kind, seed, a, b, start, n, C.c_void_p(d.ptr)))
+        return d
+
+
+class _PinnedOwner:
+    """buffer-protocol object owning a pinned allocation"""
+
+    def __init__(self, ctx: Context, ptr: int, buf):
+        self._ctx, self._ptr, self._buf = ctx, ptr, buf
+
+    def __buffer__(self, flags):  # python 3.12 buffer protocol
+        return memoryview(self._buf)
+
+    def __del__(self):
+        try:
+            if self._ctx.h:
+                self._ctx.lib.dfgpu_host_free(self._ctx.h, C.c_void_p(self._ptr))
+        except Exception:
+            pass
+
+
+class DeviceBuffer:
+    def __init__(self, ctx: Context, nbytes: int):
+        self.ctx, self.nbytes = ctx, nbytes
+        self.ptr = ctx.malloc(max(nbytes, 8))
+
+    def free(self):
+        if self.ptr and self.ctx.h:
+            self.ctx.free(self.ptr)
+        self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def to_numpy(self, dtype, count: Optional[int] = None) -> np.ndarray:
+        raw = self.ctx.to_host(self.ptr, self.nbytes)
+        a = raw.view(dtype)
+        return a if count is None else a[:count]
+
+
+# ---- columns ------------------------------------------------------------------------------
+def pack_bits(mask: np.ndarray) -> np.ndarray:
+    """bool array -> Arrow LSB bitmap, padded to 8 bytes"""
+    b = np.packbits(np.asarray(mask, dtype=bool), bitorder="little")
+    pad = (-len(b)) % 8
+    if pad:
+        b = np.concatenate([b, np.zeros(pad, np.uint8)])
+    return b if len(b) else np.zeros(8, np.uint8)
+
+
+def unpack_bits(buf: np.ndarray, n: int, offset: int = 0) -> np.ndarray:
+    return np.unpackbits(buf, bitorder="little")[offset:offset + n].astype(bool)
+
+
+class HostColumn:
+    """values (+ optional validity mask) in host memory, with the dfgpu_column describing it"""
+
+    def __init__(self, values: np.ndarray, valid: Optional[np.ndarray] = None, type_id: Optional[int] = None):
+        values = np.asarray(values)
+        self.type = type_id if type_id is not None else TYPE_OF_NP[values.dtype]
+        self.length = len(values)
+        if self.type == BOOL:
+            self._values = pack_bits(values)
+        else:
+            self._values = np.ascontiguousarray(values.astype(NP_OF_TYPE[self.type], copy=False))
+        self._validity = None if valid is None else pack_bits(valid)
+        self.null_count = 0 if valid is None else int(self.length - np.count_nonzero(valid))
+
+    def c(self) -> Column:
+        col = Column()
+        col.type, col.flags, col.length, col.offset, col.null_count = self.type, 0, self.length, 0, self.null_count
+        col.values = self._values.ctypes.data
+        col.validity = self._validity.ctypes.data if self._validity is not None else None
+        return col
+
+
+class DeviceColumn:
+    """a column resident in HBM (buffers owned by this object)"""
+
+    def __init__(self, ctx: Context, type_id: int, length: int, values: DeviceBuffer, validity: Optional[DeviceBuffer] = None,
+                 null_count: int = 0):
+        self.ctx, self.type, self.length, self.values, self.validity, self.null_count = ctx, type_id, length, values, validity, null_count
+
+    @staticmethod
+    def from_host(ctx: Context, hc: HostColumn) -> "DeviceColumn":
+        v = ctx.to_device(hc._values)
+        val = ctx.to_device(hc._validity) if hc._validity is not None else None
+        return DeviceColumn(ctx, hc.type, hc.length, v, val, hc.null_count)
+
+    def c(self) -> Column:
+        col = Column()
+        col.type, col.flags, col.length, col.offset = self.type, 0, self.length, 0
+        col.null_count = self.null_count
+        col.values = self.values.ptr
+        col.validity = self.validity.ptr if self.validity is not None else None
+        return col
+
+
+def _cols(columns) -> "C.Array":
+    arr = (Column * max(len(columns), 1))()
+    for i, c in enumerate(columns):
+        arr[i] = c.c() if not isinstance(c, Column) else c
+    return arr
+
+
+class Batch:
+    """library-owned output batch (dfgpu_batch)"""
+
+    def __init__(self, ctx: Context, handle: int):
+        self.ctx, self.h = ctx, C.c_void_p(handle)
+        lib = ctx.lib
+        self.num_rows = lib.dfgpu_batch_num_rows(self.h)
+        self.num_columns = lib.dfgpu_batch_num_columns(self.h)
+        self.is_host = bool(lib.dfgpu_batch_is_host(self.h))
+
+    def column(self, i: int) -> Column:
+        c = Column()
+        rc = self.ctx.lib.dfgpu_batch_column(self.h, i, C.byref(c))
+        if rc != OK:
+            raise DfgpuError(rc, "bad column index")
+        return c
+
+    def column_numpy(self, i: int):
+        """(values ndarray, valid bool ndarray or None) — copies D2H when the batch is on the device"""
+        c = self.column(i)
+        n = c.length
+        if c.type == BOOL:
+            nbytes = (c.offset + n + 7) // 8
+            raw = self._read(c.values, nbytes)
+            vals = unpack_bits(raw, n, c.offset)
+        else:
+            w = WIDTH[c.type]
+            off = c.offset if (c.validity and not self.is_host) else 0
+            raw = self._read((c.values or 0) + off * w, n * w)
+            if c.type == DECIMAL128:
+                vals = raw.view(np.uint64).reshape(-1, 2)
+            else:
+                vals = raw.view(NP_OF_TYPE[c.type]).copy()
+        valid = None
+        if c.validity:
+            nbytes = (c.offset + n + 7) // 8
+            valid = unpack_bits(self._read(c.validity, nbytes), n, c.offset)
+        return vals, valid
+
+    def _read(self, ptr, nbytes) -> np.ndarray:
+        if nbytes == 0:
+            return np.zeros(0, np.uint8)
+        if self.is_host:
+            return np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(ptr)).copy()
+        return self.ctx.to_host(ptr, nbytes)
+
+    def to_arrow(self):
+        """export a HOST batch through the Arrow C Data Interface -> pyarrow.RecordBatch"""
+        import pyarrow as pa
+        assert self.is_host, "to_arrow needs a host batch (next(host=True))"
+        arr, sch = ArrowArray(), ArrowSchema()
+        rc = self.ctx.lib.dfgpu_batch_export_arrow(self.h, C.byref(arr), C.byref(sch))
+        if rc != OK:
+            raise DfgpuError(rc, "export failed")
+        return pa.RecordBatch._import_from_c(C.addressof(arr), C.addressof(sch))
+
+    def release(self):
+        if self.h:
+            self.ctx.lib.dfgpu_batch_release(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class _Operator:
+    _next_fn = ""
+    _destroy_fn = ""
+    _metric_fn = ""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+
+    def _push(self, fn: str, columns):
+        arr = _cols(columns)
+        self.ctx.check(getattr(self.ctx.lib, fn)(self.h, arr, len(columns)))
+
+    def _push_arrow(self, fn: str, record_batch):
+        import pyarrow as pa
+        sa = pa.StructArray.from_arrays(record_batch.columns, fields=list(record_batch.schema))
+        arr, sch = ArrowArray(), ArrowSchema()
+        sa._export_to_c(C.addressof(arr), C.addressof(sch))
+        try:
+            rc = getattr(self.ctx.lib, fn)(self.h, C.addressof(arr), C.addressof(sch))
+        finally:
+            for obj in (arr, sch):  # we own the exported structs: call their release callbacks
+                if obj.release:
+                    C.CFUNCTYPE(None, C.c_void_p)(obj.release)(C.addressof(obj))
+        self.ctx.check(rc)
+
+    def next(self, host: bool = True) -> Optional[Batch]:
+        out = C.c_void_p()
+        rc = self.ctx.check(getattr(self.ctx.lib, self._next_fn)(self.h, 1 if host else 0, C.byref(out)))
+        if rc == END:
+            return None
+        return Batch(self.ctx, out.value)
+
+    def drain(self, host: bool = True) -> List[Batch]:
+        res = []
+        while True:
+            b = self.next(host)
+            if b is None:
+                return res
+            res.append(b)
+
+    def metric(self, name: str) -> int:
+        return getattr(self.ctx.lib, self._metric_fn)(self.h, name.encode())
+
+    def close(self):
+        if self.h:
+            getattr(self.ctx.lib, self._destroy_fn)(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def expr_nodes(nodes: Sequence[tuple]):
+    """[(kind, a, type, is_null, lit_i64, lit_f64), ...] -> ExprNode array"""
+    arr = (ExprNode * len(nodes))()
+    for i, nd in enumerate(nodes):
+        arr[i].kind, arr[i].a, arr[i].type, arr[i].is_null, arr[i].lit_i64, arr[i].lit_f64 = nd
+    return arr
+
+
+class FilterHandle(_Operator):
+    _next_fn, _destroy_fn, _metric_fn = "dfgpu_filter_next", "dfgpu_filter_destroy", "dfgpu_filter_metric"
+
+    def __init__(self, ctx, schema_types, nodes, projection=None, batch_size=8192, fetch=-1):
+        super().__init__(ctx)
+        na = expr_nodes(nodes)
+        proj = _i32arr(projection) if projection is not None else None
+        ctx.check(ctx.lib.dfgpu_filter_create(ctx.h, _i32arr(schema_types), len(schema_types), na, len(nodes), proj,
+                                              len(projection) if projection is not None else 0, batch_size, fetch, C.byref(self.h)))
+
+    def push_host(self, cols): self._push("dfgpu_filter_push_host", cols)
+    def push_device(self, cols): self._push("dfgpu_filter_push_device", cols)
+    def push_arrow(self, rb): self._push_arrow("dfgpu_filter_push_arrow", rb)
+    def finish(self): self.ctx.check(self.ctx.lib.dfgpu_filter_finish(self.h))
+
+
+class HashJoinHandle(_Operator):
+    _next_fn, _destroy_fn, _metric_fn = "dfgpu_hashjoin_next", "dfgpu_hashjoin_destroy", "dfgpu_hashjoin_metric"
+
+    def __init__(self, ctx, build_types, probe_types, on_build, on_probe, out_side, out_index, join_type=JOIN_INNER,
+                 null_equality=NULL_EQUALS_NOTHING, batch_size=8192, phj_threshold=None, phj_density=None, force_hash_collisions=False):
+        super().__init__(ctx)
+        opt = HashJoinOptions()
+        ctx.lib.dfgpu_hashjoin_default_options(C.byref(opt))
+        opt.join_type, opt.null_equality, opt.batch_size = join_type, null_equality, batch_size
+        if phj_threshold is not None:
+            opt.perfect_hash_join_small_build_threshold = phj_threshold
+        if phj_density is not None:
+            opt.perfect_hash_join_min_key_density = phj_density
+        opt.force_hash_collisions = 1 if force_hash_collisions else 0
+        ctx.check(ctx.lib.dfgpu_hashjoin_create(ctx.h, _i32arr(build_types), len(build_types), _i32arr(probe_types), len(probe_types),
+                                                _i32arr(on_build), _i32arr(on_probe), len(on_build), _i32arr(out_side), _i32arr(out_index),
+                                                len(out_side), C.byref(opt), C.byref(self.h)))
+
+    def push_build_host(self, cols): self._push("dfgpu_hashjoin_push_build_host", cols)
+    def push_build_device(self, cols): self._push("dfgpu_hashjoin_push_build_device", cols)
+    def push_build_arrow(self, rb): self._push_arrow("dfgpu_hashjoin_push_build_arrow", rb)
+    def finish_build(self): self.ctx.check(self.ctx.lib.dfgpu_hashjoin_finish_build(self.h))
+    def push_probe_host(self, cols): self._push("dfgpu_hashjoin_push_probe_host", cols)
+    def push_probe_device(self, cols): self._push("dfgpu_hashjoin_push_probe_device", cols)
+    def push_probe_arrow(self, rb): self._push_arrow("dfgpu_hashjoin_push_probe_arrow", rb)
+    def finish_probe(self): self.ctx.check(self.ctx.lib.dfgpu_hashjoin_finish_probe(self.h))
+
+
+class AggHandle(_Operator):
+    _next_fn, _destroy_fn, _metric_fn = "dfgpu_agg_next", "dfgpu_agg_destroy", "dfgpu_agg_metric"
+
+    def __init__(self, ctx, input_types, group_cols, aggs, mode=AGG_SINGLE, batch_size=8192, capacity_hint=0):
+        """aggs: [(func, arg_col, filter_col)]"""
+        super().__init__(ctx)
+        descs = (AggDesc * max(len(aggs), 1))()
+        for i, (f, a, fc) in enumerate(aggs):
+            descs[i].func, descs[i].arg_col, descs[i].filter_col, descs[i].reserved = f, a, fc, 0
+        ctx.check(ctx.lib.dfgpu_agg_create(ctx.h, _i32arr(input_types), len(input_types), _i32arr(group_cols), len(group_cols),
+                                           descs, len(aggs), mode, batch_size, capacity_hint, C.byref(self.h)))
+
+    def push_host(self, cols): self._push("dfgpu_agg_push_host", cols)
+    def push_device(self, cols): self._push("dfgpu_agg_push_device", cols)
+    def push_arrow(self, rb): self._push_arrow("dfgpu_agg_push_arrow", rb)
+    def finish(self): self.ctx.check(self.ctx.lib.dfgpu_agg_finish(self.h))
+
+
+def hash_partition_device(ctx: Context, cols, key_cols, n_parts: int):
+    arr = _cols(cols)
+    out = C.c_void_p()
+    offs = (C.c_int64 * (n_parts + 1))()
+    ctx.check(ctx.lib.dfgpu_hash_partition_device(ctx.h, arr, len(cols), _i32arr(key_cols), len(key_cols), n_parts, C.byref(out), offs))
+    return Batch(ctx, out.value), list(offs)

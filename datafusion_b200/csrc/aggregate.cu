@@ -1,0 +1,846 @@
+// aggregate.cu — GpuAggregateExec: hash group-by with partial -> final merge.
+//
+// Reference path being replaced (SURVEY.md §8a rows a17–a25):
+//   stream selection / modes      aggregates/mod.rs:289-362, 1167-1253
+//   AggregateHashTable            aggregates/aggregate_hash_table/common.rs:169-366
+//   GroupValuesPrimitive::intern  aggregates/group_values/single_group_by/primitive.rs:138-181
+//   GroupValuesColumn (multi-col) aggregates/group_values/multi_group_by/mod.rs:455-512
+//   SUM  PrimitiveGroupsAccumulator + add_wrapping   functions-aggregate-common/.../prim_op.rs:41-195, functions-aggregate/src/sum.rs:308-321
+//   COUNT CountGroupsAccumulator  functions-aggregate/src/count.rs:631-780
+//   NullState (seen values)       functions-aggregate-common/.../accumulate.rs:114-334
+//
+// B200 design: the reference interns keys to dense group ids (hashbrown + Vec) and then scatters
+// into per-aggregate Vecs.  Here one kernel does both: every input row finds-or-claims an
+// open-addressing slot whose tag IS the (bit-packed, exact, <= 128-bit) group key, and applies its
+// aggregate updates with L2 atomics straight into struct-of-arrays accumulators indexed by slot.
+// For C3 (1M groups) tags + SUM + COUNT are 3 x 8 B x 4M slots = 96 MB: L2-resident (126 MB), so the
+// only HBM traffic is the 16 B/row input stream.  The table grows by rehash between chunks; rows
+// that cannot be placed (group budget reached) are deferred to an overflow list and replayed after
+// the grow, so every row is accumulated exactly once.
+// Partial/Final use the same table: Final consumes [group cols, state cols] and merges.
+#include "batch.cuh"
+#include "scan.cuh"
+
+namespace dfgpu {
+
+constexpr int kMaxGroupCols = 8;
+constexpr int kMaxAggs = 8;
+constexpr int kMaxProbe = 512;
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+
+struct alignas(16) Key2 { unsigned long long lo, hi; };
+
+struct GroupCols {
+  int n;
+  int kw;                 // key words: 1 (<= 64 bits) or 2 (<= 128 bits)
+  int single_null_slot;   // n == 1 and nullable: NULL keys go to the dedicated null-group slot
+  const void* ptr[kMaxGroupCols];
+  const uint8_t* valid[kMaxGroupCols];
+  int64_t voff[kMaxGroupCols];
+  int width[kMaxGroupCols];     // bytes; 0 = BOOL (1 bit)
+  int64_t boff[kMaxGroupCols];  // BOOL value bit offset
+  int shift[kMaxGroupCols];     // bit position of the value inside the 128-bit key
+  int null_bit[kMaxGroupCols];  // bit position of the null flag or -1
+  int is_float[kMaxGroupCols];  // canonicalise -0.0 -> +0.0 (primitive.rs:75-98)
+};
+
+__device__ __forceinline__ void key_or(Key2& k, uint64_t v, int shift) {
+  // v < 2^width and shift + width <= 128, so nothing is lost
+  if (shift < 64) {
+    k.lo |= v << shift;
+    if (shift > 0) k.hi |= v >> (64 - shift);
+  } else {
+    k.hi |= v << (shift - 64);
+  }
+}
+
+// returns true when the row belongs to the single-column NULL group
+__device__ __forceinline__ bool load_group_key(const GroupCols& g, int64_t row, Key2* out) {
+  Key2 k{0ull, 0ull};
+  bool null_group = false;
+#pragma unroll
+  for (int c = 0; c < kMaxGroupCols; ++c) {
+    if (c >= g.n) break;
+    bool ok = !(g.valid[c] && !bit_get(g.valid[c], g.voff[c] + row));
+    uint64_t v = 0;
+    if (ok) {
+      switch (g.width[c]) {
+        case 0: v = bit_get((const uint8_t*)g.ptr[c], g.boff[c] + row) ? 1ull : 0ull; break;
+        case 1: v = ((const uint8_t*)g.ptr[c])[row]; break;
+        case 2: v = ((const uint16_t*)g.ptr[c])[row]; break;
+        case 4: v = ((const uint32_t*)g.ptr[c])[row]; if (g.is_float[c] && (v & 0x7FFFFFFFull) == 0) v = 0; break;  // f32 -0.0 -> +0.0
+        default: v = ((const uint64_t*)g.ptr[c])[row]; if (g.is_float[c] && (v << 1) == 0) v = 0; break;     // f64 -0.0 -> +0.0
+      }
+      key_or(k, v, g.shift[c]);
+    } else {
+      if (g.single_null_slot) null_group = true;
+      else key_or(k, 1ull, g.null_bit[c]);
+    }
+  }
+  *out = k;
+  return null_group;
+}
+
+struct AggDev {
+  int func;   // dfgpu_agg_func
+  int cls;    // 0 signed int, 1 unsigned int, 2 float  (class of the accumulated value)
+  int merge;  // 1 = inputs are partial states
+  int in0_type, in1_type;
+  const void* in0; const uint8_t* in0_valid; int64_t in0_voff;  // BOOL in0: in0_voff doubles as value offset
+  const void* in1; const uint8_t* in1_valid; int64_t in1_voff;
+  const uint8_t* filt; int64_t filt_off; const uint8_t* filt_valid; int64_t filt_voff;
+  unsigned long long* acc0;  // sum / min / max / count
+  unsigned long long* acc1;  // AVG: count
+  uint8_t* seen;             // NullState::seen_values (nullptr = SeenValues::All)
+};
+struct AggSet { int n; AggDev a[kMaxAggs]; };
+
+__device__ __forceinline__ int64_t load_as_i64(const void* p, int type, int64_t i) {
+  switch (type) {
+    case DFGPU_INT8: return ((const int8_t*)p)[i];
+    case DFGPU_INT16: return ((const int16_t*)p)[i];
+    case DFGPU_INT32: case DFGPU_DATE32: return ((const int32_t*)p)[i];
+    case DFGPU_UINT8: return ((const uint8_t*)p)[i];
+    case DFGPU_UINT16: return ((const uint16_t*)p)[i];
+    case DFGPU_UINT32: return ((const uint32_t*)p)[i];
+    case DFGPU_FLOAT32: return (int64_t)((const float*)p)[i];
+    case DFGPU_FLOAT64: return (int64_t)((const double*)p)[i];
+    default: return ((const int64_t*)p)[i];
+  }
+}
+__device__ __forceinline__ double load_as_f64(const void* p, int type, int64_t i) {
+  switch (type) {
+    case DFGPU_FLOAT32: return (double)((const float*)p)[i];
+    case DFGPU_FLOAT64: return ((const double*)p)[i];
+    case DFGPU_UINT64: return (double)((const uint64_t*)p)[i];
+    default: return (double)load_as_i64(p, type, i);
+  }
+}
+// order-preserving map double -> uint64 (IEEE total order: -NaN < -inf < ... < +inf < +NaN)
+__host__ __device__ __forceinline__ uint64_t f64_to_ordered(double d) {
+  uint64_t b;
+  memcpy(&b, &d, 8);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double ordered_to_f64(uint64_t u) {
+  uint64_t b = (u & 0x8000000000000000ull) ? (u & 0x7FFFFFFFFFFFFFFFull) : ~u;
+  double d;
+  memcpy(&d, &b, 8);
+  return d;
+}
+
+__device__ __forceinline__ void apply_agg(const AggDev& a, int64_t row, uint64_t slot) {
+  // opt_filter: only rows whose filter is Some(true) contribute (accumulate.rs:373-470)
+  if (a.filt) {
+    if (a.filt_valid && !bit_get(a.filt_valid, a.filt_voff + row)) return;
+    if (!bit_get(a.filt, a.filt_off + row)) return;
+  }
+  if (a.func == DFGPU_AGG_COUNT_STAR && !a.merge) { atomicAdd(&a.acc0[slot], 1ull); return; }
+  if (a.in0_valid && !bit_get(a.in0_valid, a.in0_voff + row)) {
+    if (!(a.func == DFGPU_AGG_AVG && a.merge)) return;  // NULL input: skipped
+  }
+  switch (a.func) {
+    case DFGPU_AGG_COUNT:
+    case DFGPU_AGG_COUNT_STAR:
+      // update: +1 per non-null row (count.rs:648-672); merge: + partial count (count.rs:675-698)
+      atomicAdd(&a.acc0[slot], a.merge ? (unsigned long long)((const int64_t*)a.in0)[row] : 1ull);
+      break;
+    case DFGPU_AGG_SUM:
+      if (a.cls == 2) atomicAdd((double*)&a.acc0[slot], load_as_f64(a.in0, a.in0_type, row));
+      else if (a.in0_type == DFGPU_UINT64) atomicAdd(&a.acc0[slot], (unsigned long long)((const uint64_t*)a.in0)[row]);
+      else atomicAdd(&a.acc0[slot], (unsigned long long)load_as_i64(a.in0, a.in0_type, row));  // add_wrapping (sum.rs:316)
+      if (a.seen) a.seen[slot] = 1;
+      break;
+    case DFGPU_AGG_MIN:
+    case DFGPU_AGG_MAX: {
+      const bool is_min = a.func == DFGPU_AGG_MIN;
+      if (a.cls == 0) {
+        long long v = load_as_i64(a.in0, a.in0_type, row);
+        if (is_min) atomicMin((long long*)&a.acc0[slot], v); else atomicMax((long long*)&a.acc0[slot], v);
+      } else {
+        unsigned long long v = a.cls == 2 ? f64_to_ordered(load_as_f64(a.in0, a.in0_type, row))
+                               : (a.in0_type == DFGPU_UINT64 ? ((const uint64_t*)a.in0)[row] : (unsigned long long)load_as_i64(a.in0, a.in0_type, row));
+        if (is_min) atomicMin(&a.acc0[slot], v); else atomicMax(&a.acc0[slot], v);
+      }
+      if (a.seen) a.seen[slot] = 1;
+      break;
+    }
+    case DFGPU_AGG_AVG:
+      if (a.merge) {
+        // state = [count: UInt64, sum: Float64]
+        unsigned long long c = ((const uint64_t*)a.in0)[row];
+        atomicAdd(&a.acc1[slot], c);
+        if (!(a.in1_valid && !bit_get(a.in1_valid, a.in1_voff + row))) atomicAdd((double*)&a.acc0[slot], ((const double*)a.in1)[row]);
+      } else {
+        atomicAdd((double*)&a.acc0[slot], load_as_f64(a.in0, a.in0_type, row));
+        atomicAdd(&a.acc1[slot], 1ull);
+      }
+      break;
+  }
+}
+
+struct TableDev {
+  void* tags;                 // KW=1: uint64[cap+2]; KW=2: Key2[cap+2]
+  uint64_t cap;
+  unsigned long long* ngroups;  // claimed regular slots
+  uint64_t group_limit;         // stop claiming beyond this (load-factor guard)
+  uint32_t* special_used;       // [0]: slot cap (key == all-ones), [1]: slot cap+1 (NULL group)
+};
+
+__device__ __forceinline__ Key2 cas128(Key2* addr, Key2 cmp, Key2 val) {
+  Key2 old;
+  asm volatile("{\n\t.reg .b128 c, v, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 v, {%4, %5};\n\tatom.global.cas.b128 o, [%6], c, v;\n\tmov.b128 {%0, %1}, o;\n\t}"
+               : "=l"(old.lo), "=l"(old.hi) : "l"(cmp.lo), "l"(cmp.hi), "l"(val.lo), "l"(val.hi), "l"(addr) : "memory");
+  return old;
+}
+
+// find-or-claim; returns slot or ~0ull when the row must be deferred (table budget exhausted)
+template <int KW>
+__device__ __forceinline__ uint64_t find_or_claim(const TableDev& t, Key2 k, bool null_group, bool may_claim) {
+  if (null_group) { if (!t.special_used[1]) t.special_used[1] = 1; return t.cap + 1; }
+  if (k.lo == kEmptyKey && (KW == 1 || k.hi == kEmptyKey)) { if (!t.special_used[0]) t.special_used[0] = 1; return t.cap; }
+  uint64_t h = KW == 1 ? hash_u64(k.lo, kSeedAgg) : hash_combine(hash_u64(k.lo, kSeedAgg), k.hi);
+  uint64_t s = __umul64hi(h, t.cap);
+  for (int probe = 0; probe < kMaxProbe; ++probe) {
+    if (KW == 1) {
+      unsigned long long* tp = (unsigned long long*)t.tags + s;
+      unsigned long long cur = __ldcg(tp);
+      if (cur == k.lo) return s;
+      if (cur == kEmptyKey) {
+        if (!may_claim || __ldcg(t.ngroups) >= t.group_limit) return ~0ull;
+        unsigned long long prev = atomicCAS(tp, (unsigned long long)kEmptyKey, k.lo);
+        if (prev == kEmptyKey) { atomicAdd(t.ngroups, 1ull); return s; }
+        if (prev == k.lo) return s;
+      }
+    } else {
+      Key2* tp = (Key2*)t.tags + s;
+      uint4 raw = __ldcg((const uint4*)tp);
+      Key2 cur{(unsigned long long)raw.x | ((unsigned long long)raw.y << 32), (unsigned long long)raw.z | ((unsigned long long)raw.w << 32)};
+      if (cur.lo == k.lo && cur.hi == k.hi) return s;
+      if (cur.lo == kEmptyKey && cur.hi == kEmptyKey) {
+        if (!may_claim || __ldcg(t.ngroups) >= t.group_limit) return ~0ull;
+        Key2 prev = cas128(tp, Key2{kEmptyKey, kEmptyKey}, k);
+        if (prev.lo == kEmptyKey && prev.hi == kEmptyKey) { atomicAdd(t.ngroups, 1ull); return s; }
+        if (prev.lo == k.lo && prev.hi == k.hi) return s;
+      }
+    }
+    if (++s == t.cap) s = 0;
+  }
+  return ~0ull;
+}
+
+// the hot kernel: intern + accumulate, one row per thread iteration.
+template <int KW>
+__global__ void __launch_bounds__(256) agg_update_kernel(GroupCols g, AggSet aggs, TableDev t, int64_t row0, int64_t n,
+                                                      const uint32_t* __restrict__ row_list, uint32_t* __restrict__ overflow,
+                                                      unsigned long long* __restrict__ overflow_count) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t row = row0 + (row_list ? (int64_t)row_list[i] : i);
+    Key2 k;
+    bool ng = load_group_key(g, row, &k);
+    uint64_t slot = find_or_claim<KW>(t, k, ng, true);
+    if (slot == ~0ull) {
+      unsigned long long pos = atomicAdd(overflow_count, 1ull);
+      overflow[pos] = (uint32_t)(row - row0);
+      continue;
+    }
+#pragma unroll 1
+    for (int a = 0; a < aggs.n; ++a) apply_agg(aggs.a[a], row, slot);
+  }
+}
+
+struct AccArrays { int n; void* ptr[kMaxAggs * 3]; void* new_ptr[kMaxAggs * 3]; int elem[kMaxAggs * 3]; };
+
+// grow: re-insert every occupied slot of the old table into the new one and move its accumulators
+template <int KW>
+__global__ void __launch_bounds__(256) agg_rehash_kernel(TableDev old_t, TableDev new_t, AccArrays acc) {
+  const uint64_t total = old_t.cap + 2;
+  for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < total; s += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t ns;
+    if (s >= old_t.cap) {
+      if (!old_t.special_used[s - old_t.cap]) continue;
+      ns = new_t.cap + (s - old_t.cap);
+      new_t.special_used[s - old_t.cap] = 1;
+    } else {
+      Key2 k;
+      if (KW == 1) { k.lo = ((const unsigned long long*)old_t.tags)[s]; k.hi = 0; if (k.lo == kEmptyKey) continue; }
+      else { k = ((const Key2*)old_t.tags)[s]; if (k.lo == kEmptyKey && k.hi == kEmptyKey) continue; }
+      ns = find_or_claim<KW>(new_t, k, false, true);
+    }
+    for (int a = 0; a < acc.n; ++a) {
+      if (acc.elem[a] == 8) ((uint64_t*)acc.new_ptr[a])[ns] = ((const uint64_t*)acc.ptr[a])[s];
+      else ((uint8_t*)acc.new_ptr[a])[ns] = ((const uint8_t*)acc.ptr[a])[s];
+    }
+  }
+}
+
+template <int KW>
+__global__ void agg_occupancy_kernel(TableDev t, uint32_t* __restrict__ words) {
+  const uint64_t total = t.cap + 2;
+  const uint64_t nw = (total + 31) / 32;
+  int lane = threadIdx.x & 31;
+  for (uint64_t wi = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5; wi < nw; wi += ((uint64_t)gridDim.x * blockDim.x) >> 5) {
+    uint64_t s = wi * 32 + lane;
+    bool occ = false;
+    if (s < t.cap) {
+      if (KW == 1) occ = ((const unsigned long long*)t.tags)[s] != kEmptyKey;
+      else { Key2 k = ((const Key2*)t.tags)[s]; occ = !(k.lo == kEmptyKey && k.hi == kEmptyKey); }
+    } else if (s < total) occ = t.special_used[s - t.cap] != 0;
+    uint32_t w = __ballot_sync(0xffffffffu, occ);
+    if (lane == 0) words[wi] = w;
+  }
+}
+
+// seen[] materialisation when the first batch with NULLs / a filter arrives: every existing group
+// has seen a value (SeenValues::All -> Some, accumulate.rs:59-82)
+template <int KW>
+__global__ void agg_init_seen_kernel(TableDev t, uint8_t* __restrict__ seen) {
+  const uint64_t total = t.cap + 2;
+  for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < total; s += (uint64_t)gridDim.x * blockDim.x) {
+    bool occ;
+    if (s < t.cap) {
+      if (KW == 1) occ = ((const unsigned long long*)t.tags)[s] != kEmptyKey;
+      else { Key2 k = ((const Key2*)t.tags)[s]; occ = !(k.lo == kEmptyKey && k.hi == kEmptyKey); }
+    } else occ = t.special_used[s - t.cap] != 0;
+    seen[s] = occ ? 1 : 0;
+  }
+}
+
+// ---- emit kernels: one per output column, 32 consecutive outputs per warp ----
+enum EmitKind : int { EK_KEY = 0, EK_COPY64 = 1, EK_AVG = 2, EK_MINMAX = 3 };
+struct EmitDesc {
+  int kind;
+  int out_type;        // output column type
+  int kw;
+  const void* tags;
+  uint64_t cap;
+  int shift, width_bits, null_bit, single_null_slot;  // EK_KEY
+  const unsigned long long* acc0;
+  const unsigned long long* acc1;
+  const uint8_t* seen;
+  int cls;             // EK_MINMAX: 0 signed, 1 unsigned, 2 float
+};
+
+__device__ __forceinline__ void store_typed(void* out, int type, int64_t i, uint64_t bits) {
+  switch (type_width(type)) {
+    case 1: ((uint8_t*)out)[i] = (uint8_t)bits; break;
+    case 2: ((uint16_t*)out)[i] = (uint16_t)bits; break;
+    case 4: ((uint32_t*)out)[i] = (uint32_t)bits; break;
+    default: ((uint64_t*)out)[i] = bits; break;
+  }
+}
+
+__global__ void __launch_bounds__(256) agg_emit_kernel(EmitDesc d, const uint32_t* __restrict__ slot_idx, int64_t n, void* __restrict__ out,
+                                                    uint32_t* __restrict__ out_valid, uint32_t* __restrict__ out_boolbits) {
+  const int64_t nw = (n + 31) / 32;
+  int lane = threadIdx.x & 31;
+  for (int64_t wi = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; wi < nw; wi += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    int64_t i = wi * 32 + lane;
+    bool ok = false, bval = false;
+    if (i < n) {
+      uint64_t s = slot_idx[i];
+      ok = true;
+      uint64_t bits = 0;
+      switch (d.kind) {
+        case EK_KEY: {
+          if (s == d.cap + 1) { ok = false; break; }  // the NULL group (primitive.rs:195-249 build_primitive)
+          unsigned long long lo, hi = 0;
+          if (s == d.cap) { lo = kEmptyKey; hi = kEmptyKey; }
+          else if (d.kw == 1) lo = ((const unsigned long long*)d.tags)[s];
+          else { Key2 k = ((const Key2*)d.tags)[s]; lo = k.lo; hi = k.hi; }
+          if (d.null_bit >= 0) {
+            bool isnull = d.null_bit < 64 ? ((lo >> d.null_bit) & 1) : ((hi >> (d.null_bit - 64)) & 1);
+            if (isnull) { ok = false; break; }
+          }
+          if (d.shift < 64) {
+            bits = lo >> d.shift;
+            if (d.shift > 0 && d.shift + d.width_bits > 64) bits |= hi << (64 - d.shift);
+          } else bits = hi >> (d.shift - 64);
+          if (d.width_bits < 64) bits &= (1ull << d.width_bits) - 1ull;
+          break;
+        }
+        case EK_COPY64:
+          bits = d.acc0[s];
+          if (d.seen) ok = d.seen[s] != 0;
+          break;
+        case EK_AVG: {
+          unsigned long long c = d.acc1[s];
+          if (c == 0) { ok = false; break; }
+          double sum;
+          memcpy(&sum, &d.acc0[s], 8);
+          double r = sum / (double)c;
+          memcpy(&bits, &r, 8);
+          break;
+        }
+        case EK_MINMAX: {
+          if (d.seen) ok = d.seen[s] != 0;
+          unsigned long long v = d.acc0[s];
+          if (d.cls == 2) {
+            double dv = ordered_to_f64(v);
+            if (d.out_type == DFGPU_FLOAT32) { float f = (float)dv; uint32_t fb; memcpy(&fb, &f, 4); bits = fb; }
+            else memcpy(&bits, &dv, 8);
+          } else bits = v;
+          break;
+        }
+      }
+      if (!ok) bits = 0;
+      if (d.out_type == DFGPU_BOOL) bval = bits & 1;
+      else store_typed(out, d.out_type, i, bits);
+    }
+    uint32_t vw = __ballot_sync(0xffffffffu, ok);
+    uint32_t bw = __ballot_sync(0xffffffffu, bval);
+    if (lane == 0) {
+      if (out_valid) out_valid[wi] = vw;
+      if (out_boolbits) out_boolbits[wi] = bw;
+    }
+  }
+}
+
+__global__ void fill_u64_kernel(unsigned long long* p, uint64_t n, unsigned long long v) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace dfgpu
+
+// ==========================================================================================
+// operator state
+// ==========================================================================================
+using namespace dfgpu;
+
+struct AggState {
+  int func, cls;
+  int arg_col, filter_col;
+  int in_type;          // raw input type (raw modes) or state value type
+  int out_type;         // final value type
+  int first_state_col;  // state modes: index of this aggregate's first state column in the input
+  DevBuf acc0, acc1, seen;
+  bool track_seen = false;
+  unsigned long long init0 = 0;
+};
+
+struct dfgpu_agg {
+  dfgpu_ctx* ctx = nullptr;
+  std::vector<int> input_types, group_cols;
+  std::vector<AggState> aggs;
+  int mode = DFGPU_AGG_SINGLE;
+  bool state_input = false, state_output = false;
+  int64_t batch_size = 8192;
+  int kw = 1;
+  int key_bits = 0;
+  bool finished = false, emitted = false;
+  // key packing
+  std::vector<int> g_shift, g_width_bits, g_null_bit;
+  bool single_null_slot = false;
+  // table
+  DevBuf tags, counters /* [ngroups, overflow_count] */, special_used;
+  uint64_t cap = 0;
+  std::deque<BatchPtr> outq;
+  int64_t m_input_rows = 0, m_output_rows = 0, m_rehashes = 0, m_num_groups = 0, m_input_batches = 0;
+};
+
+namespace dfgpu {
+
+static TableDev table_dev(dfgpu_agg* a, DevBuf& tags, uint64_t cap, DevBuf& counters, DevBuf& special) {
+  TableDev t;
+  t.tags = tags.ptr;
+  t.cap = cap;
+  t.ngroups = counters.as<unsigned long long>();
+  t.group_limit = cap / 2;  // load factor <= 0.5
+  t.special_used = special.as<uint32_t>();
+  return t;
+}
+
+static void fill_u64(dfgpu_ctx* ctx, void* p, uint64_t n, unsigned long long v) {
+  if (n == 0) return;
+  if (v == 0) { DF_CUDA(cudaMemsetAsync(p, 0, n * 8, ctx->stream)); return; }
+  if (v == ~0ull) { DF_CUDA(cudaMemsetAsync(p, 0xFF, n * 8, ctx->stream)); return; }
+  fill_u64_kernel<<<grid_for((int64_t)n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>((unsigned long long*)p, n, v);
+  DF_LAUNCH_CHECK(ctx);
+}
+
+static void alloc_table(dfgpu_agg* a, uint64_t cap, DevBuf* tags, std::vector<DevBuf>* acc0, std::vector<DevBuf>* acc1, std::vector<DevBuf>* seen) {
+  dfgpu_ctx* ctx = a->ctx;
+  tags->alloc(ctx, (size_t)(cap + 2) * 8 * a->kw);
+  tags->fill(0xFF);
+  acc0->resize(a->aggs.size()); acc1->resize(a->aggs.size()); seen->resize(a->aggs.size());
+  for (size_t i = 0; i < a->aggs.size(); ++i) {
+    (*acc0)[i].alloc(ctx, (size_t)(cap + 2) * 8);
+    fill_u64(ctx, (*acc0)[i].ptr, cap + 2, a->aggs[i].init0);
+    if (a->aggs[i].func == DFGPU_AGG_AVG) { (*acc1)[i].alloc(ctx, (size_t)(cap + 2) * 8); (*acc1)[i].zero(); }
+    if (a->aggs[i].track_seen) { (*seen)[i].alloc(ctx, (size_t)(cap + 2)); (*seen)[i].zero(); }
+  }
+}
+
+static void grow_table(dfgpu_agg* a, uint64_t new_cap) {
+  dfgpu_ctx* ctx = a->ctx;
+  DevBuf ntags, ncounters(ctx, 16), nspecial(ctx, 8);
+  std::vector<DevBuf> nacc0, nacc1, nseen;
+  alloc_table(a, new_cap, &ntags, &nacc0, &nacc1, &nseen);
+  ncounters.zero();
+  nspecial.zero();
+  TableDev old_t = table_dev(a, a->tags, a->cap, a->counters, a->special_used);
+  TableDev new_t = table_dev(a, ntags, new_cap, ncounters, nspecial);
+  new_t.group_limit = new_cap;  // the rehash itself may always claim
+  AccArrays arr;
+  arr.n = 0;
+  for (size_t i = 0; i < a->aggs.size(); ++i) {
+    arr.ptr[arr.n] = a->aggs[i].acc0.ptr; arr.new_ptr[arr.n] = nacc0[i].ptr; arr.elem[arr.n++] = 8;
+    if (a->aggs[i].acc1.ptr) { arr.ptr[arr.n] = a->aggs[i].acc1.ptr; arr.new_ptr[arr.n] = nacc1[i].ptr; arr.elem[arr.n++] = 8; }
+    if (a->aggs[i].seen.ptr) { arr.ptr[arr.n] = a->aggs[i].seen.ptr; arr.new_ptr[arr.n] = nseen[i].ptr; arr.elem[arr.n++] = 1; }
+  }
+  int grid = grid_for((int64_t)a->cap + 2, 256, kNumSMs * 8);
+  if (a->kw == 1) agg_rehash_kernel<1><<<grid, 256, 0, ctx->stream>>>(old_t, new_t, arr);
+  else agg_rehash_kernel<2><<<grid, 256, 0, ctx->stream>>>(old_t, new_t, arr);
+  DF_LAUNCH_CHECK(ctx);
+  a->tags = std::move(ntags);
+  a->counters = std::move(ncounters);
+  a->special_used = std::move(nspecial);
+  for (size_t i = 0; i < a->aggs.size(); ++i) {
+    a->aggs[i].acc0 = std::move(nacc0[i]);
+    a->aggs[i].acc1 = std::move(nacc1[i]);
+    a->aggs[i].seen = std::move(nseen[i]);
+  }
+  a->cap = new_cap;
+  a->m_rehashes++;
+}
+
+static void ensure_seen(dfgpu_agg* a, AggState& s) {
+  if (s.track_seen) return;
+  if (!(s.func == DFGPU_AGG_SUM || s.func == DFGPU_AGG_MIN || s.func == DFGPU_AGG_MAX)) return;
+  dfgpu_ctx* ctx = a->ctx;
+  s.track_seen = true;
+  s.seen.alloc(ctx, (size_t)(a->cap + 2));
+  TableDev t = table_dev(a, a->tags, a->cap, a->counters, a->special_used);
+  int grid = grid_for((int64_t)a->cap + 2, 256, kNumSMs * 8);
+  if (a->kw == 1) agg_init_seen_kernel<1><<<grid, 256, 0, ctx->stream>>>(t, s.seen.as<uint8_t>());
+  else agg_init_seen_kernel<2><<<grid, 256, 0, ctx->stream>>>(t, s.seen.as<uint8_t>());
+  DF_LAUNCH_CHECK(ctx);
+}
+
+static void agg_push(dfgpu_agg* a, const std::vector<DCol>& cols) {
+  DF_CHECK(!a->finished, DFGPU_ERR_STATE, "push after finish");
+  DF_CHECK(cols.size() == a->input_types.size(), DFGPU_ERR_INVALID, "aggregate input column count mismatch");
+  dfgpu_ctx* ctx = a->ctx;
+  set_device(ctx);
+  const int64_t n = cols.empty() ? 0 : cols[0].length;
+  for (size_t c = 0; c < cols.size(); ++c) {
+    DF_CHECK(cols[c].type == a->input_types[c], DFGPU_ERR_INVALID, "aggregate input column type mismatch");
+    DF_CHECK(cols[c].length == n, DFGPU_ERR_INVALID, "aggregate input ragged columns");
+  }
+  a->m_input_rows += n;
+  a->m_input_batches++;
+  if (n == 0) return;
+  // group key columns
+  GroupCols g;
+  memset(&g, 0, sizeof(g));
+  g.n = (int)a->group_cols.size();
+  g.kw = a->kw;
+  g.single_null_slot = a->single_null_slot ? 1 : 0;
+  for (int c = 0; c < g.n; ++c) {
+    const DCol& col = cols[a->group_cols[c]];
+    g.ptr[c] = col.values; g.valid[c] = col.validity; g.voff[c] = col.offset;
+    g.width[c] = type_width(col.type); g.boff[c] = col.offset;
+    g.shift[c] = a->g_shift[c]; g.null_bit[c] = a->g_null_bit[c];
+    g.is_float[c] = type_is_float(col.type) ? 1 : 0;
+    DF_CHECK(!(col.validity && a->g_null_bit[c] < 0 && !a->single_null_slot), DFGPU_ERR_INVALID, "group column declared non-nullable has a validity bitmap");
+  }
+  // aggregates
+  AggSet set;
+  memset(&set, 0, sizeof(set));
+  set.n = (int)a->aggs.size();
+  for (int i = 0; i < set.n; ++i) {
+    AggState& s = a->aggs[i];
+    AggDev& d = set.a[i];
+    d.func = s.func; d.cls = s.cls; d.merge = a->state_input ? 1 : 0;
+    const DCol* in0 = nullptr; const DCol* in1 = nullptr; const DCol* filt = nullptr;
+    if (a->state_input) {
+      in0 = &cols[s.first_state_col];
+      if (s.func == DFGPU_AGG_AVG) in1 = &cols[s.first_state_col + 1];
+    } else {
+      if (s.func != DFGPU_AGG_COUNT_STAR) in0 = &cols[s.arg_col];
+      if (s.filter_col >= 0) filt = &cols[s.filter_col];
+    }
+    if (in0) { d.in0 = in0->values; d.in0_type = in0->type; d.in0_valid = in0->validity; d.in0_voff = in0->offset; }
+    if (in1) { d.in1 = in1->values; d.in1_type = in1->type; d.in1_valid = in1->validity; d.in1_voff = in1->offset; }
+    if (filt) { d.filt = (const uint8_t*)filt->values; d.filt_off = filt->offset; d.filt_valid = filt->validity; d.filt_voff = filt->offset; }
+    // NullState: switch to explicit seen tracking once nulls or a filter show up (accumulate.rs:164-188)
+    if ((in0 && in0->validity) || filt) ensure_seen(a, s);
+  }
+  auto refresh_ptrs = [&]() {
+    for (int i = 0; i < set.n; ++i) {
+      set.a[i].acc0 = a->aggs[i].acc0.as<unsigned long long>();
+      set.a[i].acc1 = a->aggs[i].acc1.as<unsigned long long>();
+      set.a[i].seen = a->aggs[i].seen.as<uint8_t>();
+    }
+  };
+  // chunked processing with ramp-up so an undersized table is discovered cheaply
+  int64_t done = 0;
+  int64_t chunk = std::max<int64_t>((int64_t)a->cap / 2, 1 << 20);
+  const int64_t kMaxChunk = 1ll << 28;
+  DevBuf overflow;
+  while (done < n) {
+    int64_t m = std::min<int64_t>(std::min(chunk, kMaxChunk), n - done);
+    if (overflow.bytes < (size_t)m * 4) overflow.alloc(ctx, (size_t)m * 4);
+    const uint32_t* list = nullptr;
+    int64_t work = m;
+    DevBuf replay;
+    while (true) {
+      refresh_ptrs();
+      TableDev t = table_dev(a, a->tags, a->cap, a->counters, a->special_used);
+      DF_CUDA(cudaMemsetAsync(a->counters.as<unsigned long long>() + 1, 0, 8, ctx->stream));
+      int grid = grid_for(work, 256, kNumSMs * 8);
+      if (a->kw == 1)
+        agg_update_kernel<1><<<grid, 256, 0, ctx->stream>>>(g, set, t, done, work, list, overflow.as<uint32_t>(), a->counters.as<unsigned long long>() + 1);
+      else
+        agg_update_kernel<2><<<grid, 256, 0, ctx->stream>>>(g, set, t, done, work, list, overflow.as<uint32_t>(), a->counters.as<unsigned long long>() + 1);
+      DF_LAUNCH_CHECK(ctx);
+      unsigned long long hc[2];
+      DF_CUDA(cudaMemcpyAsync(hc, a->counters.ptr, 16, cudaMemcpyDeviceToHost, ctx->stream));
+      DF_CUDA(cudaStreamSynchronize(ctx->stream));
+      a->m_num_groups = (int64_t)hc[0];
+      if (hc[1] == 0) {
+        // keep the load factor below 1/4 ahead of the next chunk so steady-state chunks never overflow
+        if (hc[0] * 4 > a->cap) grow_table(a, a->cap * 4);
+        break;
+      }
+      // deferred rows: grow, then replay just those rows
+      replay = std::move(overflow);
+      overflow.alloc(ctx, (size_t)hc[1] * 4);
+      list = replay.as<uint32_t>();
+      work = (int64_t)hc[1];
+      uint64_t want = std::max<uint64_t>(a->cap * 4, (hc[0] + hc[1]) * 2);
+      grow_table(a, want);
+    }
+    done += m;
+    chunk = std::min<int64_t>(chunk * 4, kMaxChunk);
+  }
+}
+
+static void agg_finish(dfgpu_agg* a) {
+  DF_CHECK(!a->finished, DFGPU_ERR_STATE, "finish called twice");
+  a->finished = true;
+  dfgpu_ctx* ctx = a->ctx;
+  set_device(ctx);
+  // emit = group_values.emit(EmitTo::All) ++ acc.state()/evaluate() (common.rs:247-297)
+  TableDev t = table_dev(a, a->tags, a->cap, a->counters, a->special_used);
+  const uint64_t total = a->cap + 2;
+  DevBuf occ(ctx, (size_t)((total + 31) / 32) * 4);
+  int grid = grid_for((int64_t)total, 256, kNumSMs * 8);
+  if (a->kw == 1) agg_occupancy_kernel<1><<<grid, 256, 0, ctx->stream>>>(t, occ.as<uint32_t>());
+  else agg_occupancy_kernel<2><<<grid, 256, 0, ctx->stream>>>(t, occ.as<uint32_t>());
+  DF_LAUNCH_CHECK(ctx);
+  DevBuf idx;
+  int64_t ng = compact_flag_indices(ctx, occ.as<uint32_t>(), (int64_t)total, 1, &idx);
+  a->m_num_groups = ng;
+  // a global aggregate (no GROUP BY) over empty input still yields one row in Final/Single modes; grouped: zero rows.
+  BatchPtr out(new dfgpu_batch());
+  out->ctx = ctx; out->rows = ng; out->host = false;
+  auto run_emit = [&](EmitDesc& d, int out_type, bool with_valid) -> DCol {
+    DCol col = alloc_col(ctx, out_type, ng, with_valid);
+    if (ng > 0) {
+      d.out_type = out_type; d.kw = a->kw; d.tags = a->tags.ptr; d.cap = a->cap;
+      agg_emit_kernel<<<grid_for(ng, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(
+          d, idx.as<uint32_t>(), ng, out_type == DFGPU_BOOL ? nullptr : col.own_values->ptr,
+          with_valid ? col.own_validity->as<uint32_t>() : nullptr, out_type == DFGPU_BOOL ? col.own_values->as<uint32_t>() : nullptr);
+      DF_LAUNCH_CHECK(ctx);
+    }
+    col.null_count = with_valid ? -1 : 0;
+    return col;
+  };
+  for (size_t c = 0; c < a->group_cols.size(); ++c) {
+    EmitDesc d;
+    memset(&d, 0, sizeof(d));
+    d.kind = EK_KEY; d.shift = a->g_shift[c]; d.width_bits = a->g_width_bits[c]; d.null_bit = a->g_null_bit[c];
+    d.single_null_slot = a->single_null_slot;
+    bool nullable = a->g_null_bit[c] >= 0 || a->single_null_slot;
+    out->cols.push_back(run_emit(d, a->input_types[a->group_cols[c]], nullable));
+  }
+  for (auto& s : a->aggs) {
+    EmitDesc d;
+    memset(&d, 0, sizeof(d));
+    d.acc0 = s.acc0.as<unsigned long long>(); d.acc1 = s.acc1.as<unsigned long long>(); d.seen = s.seen.as<uint8_t>(); d.cls = s.cls;
+    d.null_bit = -1;
+    switch (s.func) {
+      case DFGPU_AGG_SUM: {
+        d.kind = EK_COPY64;
+        int t2 = s.cls == 2 ? DFGPU_FLOAT64 : (s.cls == 1 ? DFGPU_UINT64 : DFGPU_INT64);  // Sum::return_type, sum.rs:232-261
+        out->cols.push_back(run_emit(d, t2, s.track_seen));
+        break;
+      }
+      case DFGPU_AGG_COUNT: case DFGPU_AGG_COUNT_STAR:
+        d.kind = EK_COPY64; d.seen = nullptr;
+        out->cols.push_back(run_emit(d, DFGPU_INT64, false));  // COUNT is never NULL (count.rs:700-708)
+        break;
+      case DFGPU_AGG_MIN: case DFGPU_AGG_MAX:
+        d.kind = EK_MINMAX;
+        out->cols.push_back(run_emit(d, s.out_type, s.track_seen));
+        break;
+      case DFGPU_AGG_AVG:
+        if (a->state_output) {
+          EmitDesc dc = d; dc.kind = EK_COPY64; dc.acc0 = s.acc1.as<unsigned long long>(); dc.seen = nullptr;
+          out->cols.push_back(run_emit(dc, DFGPU_UINT64, false));
+          EmitDesc ds = d; ds.kind = EK_COPY64; ds.seen = nullptr;
+          out->cols.push_back(run_emit(ds, DFGPU_FLOAT64, false));
+        } else {
+          d.kind = EK_AVG;
+          out->cols.push_back(run_emit(d, DFGPU_FLOAT64, true));
+        }
+        break;
+    }
+  }
+  a->m_output_rows += ng;
+  if (ng > 0 || a->group_cols.empty()) a->outq.push_back(std::move(out));
+}
+
+}  // namespace dfgpu
+
+extern "C" {
+
+int dfgpu_agg_create(dfgpu_ctx* ctx, const int32_t* input_types, int32_t n_cols, const int32_t* group_cols, int32_t n_group,
+                     const dfgpu_agg_desc* aggs, int32_t n_aggs, int32_t mode, int64_t batch_size, int64_t capacity_hint, dfgpu_agg** out) {
+  DF_API_BEGIN(ctx)
+  DF_CHECK(ctx && out, DFGPU_ERR_INVALID, "null argument");
+  DF_CHECK(n_group >= 1 && n_group <= kMaxGroupCols, DFGPU_ERR_UNSUPPORTED, "aggregate: 1..8 group columns supported (no-GROUP-BY aggregation stays on the CPU operator)");
+  DF_CHECK(n_aggs >= 0 && n_aggs <= kMaxAggs, DFGPU_ERR_UNSUPPORTED, "aggregate: at most 8 aggregate expressions");
+  set_device(ctx);
+  std::unique_ptr<dfgpu_agg> a(new dfgpu_agg());
+  a->ctx = ctx;
+  a->input_types.assign(input_types, input_types + n_cols);
+  a->group_cols.assign(group_cols, group_cols + n_group);
+  a->mode = mode;
+  a->batch_size = batch_size > 0 ? batch_size : 8192;
+  a->state_input = (mode == DFGPU_AGG_FINAL || mode == DFGPU_AGG_FINAL_PARTITIONED || mode == DFGPU_AGG_PARTIAL_REDUCE);
+  a->state_output = (mode == DFGPU_AGG_PARTIAL || mode == DFGPU_AGG_PARTIAL_REDUCE);
+  // key packing: values first, then one null flag per (multi-column) group column.  All group
+  // columns are treated as nullable: the schema-level nullability is not part of this ABI.
+  int bits = 0;
+  for (int c = 0; c < n_group; ++c) {
+    DF_CHECK(group_cols[c] >= 0 && group_cols[c] < n_cols, DFGPU_ERR_INVALID, "group column index out of range");
+    int t = input_types[group_cols[c]];
+    int w = type_width(t);
+    DF_CHECK(w >= 0 && w <= 8, DFGPU_ERR_UNSUPPORTED, "aggregate: group column type not supported");
+    int wb = (t == DFGPU_BOOL) ? 1 : 8 * w;
+    a->g_shift.push_back(bits);
+    a->g_width_bits.push_back(wb);
+    bits += wb;
+  }
+  a->single_null_slot = (n_group == 1);
+  for (int c = 0; c < n_group; ++c) {
+    if (a->single_null_slot) a->g_null_bit.push_back(-1);
+    else { a->g_null_bit.push_back(bits); bits += 1; }
+  }
+  if (!a->single_null_slot && bits > 128) {
+    // retry without null flags when the values alone fill 128 bits (e.g. TPC-H Q3: int64 + date32 + int32):
+    // NULL group keys are then rejected at push time.
+    bits -= n_group;
+    for (int c = 0; c < n_group; ++c) a->g_null_bit[c] = -1;
+  }
+  DF_CHECK(bits <= 128, DFGPU_ERR_UNSUPPORTED, "aggregate: group key wider than 128 bits is not supported yet");
+  a->key_bits = bits;
+  a->kw = bits <= 64 ? 1 : 2;
+  int next_state_col = n_group;
+  for (int i = 0; i < n_aggs; ++i) {
+    AggState s;
+    s.func = aggs[i].func; s.arg_col = aggs[i].arg_col; s.filter_col = aggs[i].filter_col;
+    s.first_state_col = next_state_col;
+    int vt;
+    if (a->state_input) {
+      DF_CHECK(next_state_col < n_cols, DFGPU_ERR_INVALID, "aggregate: state columns missing from input schema");
+      vt = input_types[s.func == DFGPU_AGG_AVG ? next_state_col + 1 : next_state_col];
+      next_state_col += (s.func == DFGPU_AGG_AVG) ? 2 : 1;
+    } else {
+      if (s.func == DFGPU_AGG_COUNT_STAR) vt = DFGPU_INT64;
+      else {
+        DF_CHECK(s.arg_col >= 0 && s.arg_col < n_cols, DFGPU_ERR_INVALID, "aggregate argument column out of range");
+        vt = input_types[s.arg_col];
+      }
+      if (s.filter_col >= 0) DF_CHECK(s.filter_col < n_cols && input_types[s.filter_col] == DFGPU_BOOL, DFGPU_ERR_INVALID, "aggregate FILTER column must be Boolean");
+    }
+    s.in_type = vt;
+    s.out_type = vt;
+    s.cls = type_is_float(vt) ? 2 : (type_is_unsigned_int(vt) ? 1 : 0);
+    switch (s.func) {
+      case DFGPU_AGG_SUM:
+        DF_CHECK(type_is_int(vt) || type_is_float(vt), DFGPU_ERR_UNSUPPORTED, "SUM: numeric argument required (Decimal128 not supported yet)");
+        s.init0 = 0; break;
+      case DFGPU_AGG_COUNT: case DFGPU_AGG_COUNT_STAR: s.init0 = 0; break;
+      case DFGPU_AGG_AVG:
+        DF_CHECK(type_is_int(vt) || type_is_float(vt), DFGPU_ERR_UNSUPPORTED, "AVG: numeric argument required");
+        s.cls = 2; s.init0 = 0; break;
+      case DFGPU_AGG_MIN:
+        DF_CHECK(type_is_int(vt) || type_is_float(vt), DFGPU_ERR_UNSUPPORTED, "MIN: numeric argument required");
+        s.init0 = s.cls == 0 ? (unsigned long long)LLONG_MAX : ~0ull; break;
+      case DFGPU_AGG_MAX:
+        DF_CHECK(type_is_int(vt) || type_is_float(vt), DFGPU_ERR_UNSUPPORTED, "MAX: numeric argument required");
+        s.init0 = s.cls == 0 ? (unsigned long long)LLONG_MIN : 0ull; break;
+      default: throw Error(DFGPU_ERR_INVALID, "unknown aggregate function");
+    }
+    a->aggs.push_back(std::move(s));
+  }
+  // table
+  uint64_t cap = 1 << 16;
+  if (capacity_hint > 0) cap = std::max<uint64_t>(cap, (uint64_t)capacity_hint * 4);
+  a->cap = cap;
+  a->counters.alloc(ctx, 16); a->counters.zero();
+  a->special_used.alloc(ctx, 8); a->special_used.zero();
+  {
+    std::vector<DevBuf> acc0, acc1, seen;
+    alloc_table(a.get(), cap, &a->tags, &acc0, &acc1, &seen);
+    for (size_t i = 0; i < a->aggs.size(); ++i) { a->aggs[i].acc0 = std::move(acc0[i]); a->aggs[i].acc1 = std::move(acc1[i]); a->aggs[i].seen = std::move(seen[i]); }
+  }
+  *out = a.release();
+  DF_API_END
+}
+
+int dfgpu_agg_push_host(dfgpu_agg* a, const dfgpu_column* cols, int32_t n_cols) {
+  DF_API_BEGIN(a ? a->ctx : nullptr)
+  set_device(a->ctx);
+  std::vector<DCol> v;
+  for (int i = 0; i < n_cols; ++i) v.push_back(upload_column(a->ctx, cols[i]));
+  agg_push(a, v);
+  DF_API_END
+}
+int dfgpu_agg_push_device(dfgpu_agg* a, const dfgpu_column* cols, int32_t n_cols) {
+  DF_API_BEGIN(a ? a->ctx : nullptr)
+  std::vector<DCol> v;
+  for (int i = 0; i < n_cols; ++i) v.push_back(device_view(cols[i]));
+  agg_push(a, v);  // fully consumed (stream-synchronised) before returning
+  DF_API_END
+}
+int dfgpu_agg_finish(dfgpu_agg* a) {
+  DF_API_BEGIN(a ? a->ctx : nullptr)
+  agg_finish(a);
+  DF_API_END
+}
+int dfgpu_agg_next(dfgpu_agg* a, int host, dfgpu_batch** out) {
+  dfgpu_ctx* _ctx = a ? a->ctx : nullptr;
+  try {
+    DF_CHECK(a && out, DFGPU_ERR_INVALID, "null argument");
+    if (a->outq.empty()) { *out = nullptr; return DFGPU_END; }
+    BatchPtr b = std::move(a->outq.front());
+    a->outq.pop_front();
+    if (host) { set_device(a->ctx); b = to_host_batch(a->ctx, *b); }
+    *out = b.release();
+    return DFGPU_OK;
+  } catch (const dfgpu::Error& e) { if (_ctx) _ctx->last_error = e.what(); return e.code; }
+  catch (const std::exception& e) { if (_ctx) _ctx->last_error = e.what(); return DFGPU_ERR_INVALID; }
+}
+int64_t dfgpu_agg_metric(dfgpu_agg* a, const char* name) {
+  if (!a || !name) return -1;
+  std::string s(name);
+  if (s == "num_groups") return a->m_num_groups;
+  if (s == "input_rows") return a->m_input_rows;
+  if (s == "input_batches") return a->m_input_batches;
+  if (s == "output_rows") return a->m_output_rows;
+  if (s == "table_capacity") return (int64_t)a->cap;
+  if (s == "rehashes") return a->m_rehashes;
+  if (s == "key_words") return a->kw;
+  return -1;
+}
+void dfgpu_agg_destroy(dfgpu_agg* a) {
+  if (!a) return;
+  cudaSetDevice(a->ctx->device);
+  delete a;
+}
+
+}  // extern "C"

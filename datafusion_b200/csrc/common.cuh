@@ -1,0 +1,259 @@
+// common.cuh — shared host/device plumbing for libdfgpu (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <memory>
+#include <stdexcept>
+#include "../../include/dfgpu.h"
+
+namespace dfgpu {
+
+// ------------------------------------------------------------------------------------------
+// errors: C++ exceptions inside, converted to status codes at the extern "C" boundary
+// ------------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define DF_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      char _buf[512];                                                                         \
+      snprintf(_buf, sizeof(_buf), "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e),        \
+               __FILE__, __LINE__, cudaGetErrorString(_e));                                   \
+      throw ::dfgpu::Error(_e == cudaErrorMemoryAllocation ? DFGPU_ERR_OOM : DFGPU_ERR_CUDA, _buf); \
+    }                                                                                         \
+  } while (0)
+
+#define DF_CHECK(cond, code, msg)                                 \
+  do {                                                            \
+    if (!(cond)) throw ::dfgpu::Error((code), std::string(msg));  \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// ------------------------------------------------------------------------------------------
+// type helpers
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline int type_width(int t) {
+  switch (t) {
+    case DFGPU_BOOL: return 0;  // bit-packed
+    case DFGPU_INT8: case DFGPU_UINT8: return 1;
+    case DFGPU_INT16: case DFGPU_UINT16: return 2;
+    case DFGPU_INT32: case DFGPU_UINT32: case DFGPU_FLOAT32: case DFGPU_DATE32: return 4;
+    case DFGPU_INT64: case DFGPU_UINT64: case DFGPU_FLOAT64: case DFGPU_DATE64: case DFGPU_TIMESTAMP: return 8;
+    case DFGPU_DECIMAL128: return 16;
+    default: return -1;
+  }
+}
+__host__ __device__ inline bool type_is_signed_int(int t) {
+  return t == DFGPU_INT8 || t == DFGPU_INT16 || t == DFGPU_INT32 || t == DFGPU_INT64 || t == DFGPU_DATE32 ||
+         t == DFGPU_DATE64 || t == DFGPU_TIMESTAMP;
+}
+__host__ __device__ inline bool type_is_unsigned_int(int t) {
+  return t == DFGPU_UINT8 || t == DFGPU_UINT16 || t == DFGPU_UINT32 || t == DFGPU_UINT64;
+}
+__host__ __device__ inline bool type_is_float(int t) { return t == DFGPU_FLOAT32 || t == DFGPU_FLOAT64; }
+__host__ __device__ inline bool type_is_int(int t) { return type_is_signed_int(t) || type_is_unsigned_int(t); }
+
+inline size_t values_bytes(int type, int64_t rows) {
+  if (type == DFGPU_BOOL) return (size_t)((rows + 7) / 8);
+  return (size_t)rows * (size_t)type_width(type);
+}
+inline size_t bitmap_bytes(int64_t rows) { return (size_t)((rows + 7) / 8); }
+// device bitmaps are allocated in whole 64-bit words so kernels may use uint64 accesses
+inline size_t bitmap_alloc_bytes(int64_t rows) { return (size_t)((rows + 63) / 64) * 8; }
+
+// ------------------------------------------------------------------------------------------
+// hashing.  Hash VALUES never reach operator output (join order follows probe
+// order + ascending build index, group ids are not exposed, the exchange only picks a
+// partition), so any 64-bit mixer is admissible; we use the splitmix64 finaliser with the
+// reference's three distinct seeds so exchange / join / aggregate hashes stay decorrelated
+// (hash_join/exec.rs:105, aggregates/mod.rs:236, repartition/mod.rs:650).
+// ------------------------------------------------------------------------------------------
+constexpr uint64_t kSeedJoin = 12210250226015887276ull;
+constexpr uint64_t kSeedAgg = 15395726432021054657ull;
+constexpr uint64_t kSeedExchange = 0x9E3779B97F4A7C15ull;  // reference uses seed 0; any fixed value decorrelated from the others
+
+__host__ __device__ inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return x;
+}
+__host__ __device__ inline uint64_t hash_u64(uint64_t v, uint64_t seed) { return mix64(v + seed); }
+// multi-column: later columns re-seed with the running hash (hash_utils.rs:306-345 does the same for primitives)
+__host__ __device__ inline uint64_t hash_combine(uint64_t running, uint64_t v) { return mix64(v ^ (running * 0x9E3779B97F4A7C15ull + 0x7F4A7C15ull)); }
+
+// counter-based generator shared with the oracle (oracle/gen.h restates it)
+__host__ __device__ inline uint64_t splitmix64_at(uint64_t seed, uint64_t i) {
+  uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+}  // namespace dfgpu
+
+struct dfgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string last_error;
+  int64_t launches = 0;
+  void* l2_scratch = nullptr;
+  size_t l2_scratch_bytes = 0;
+  // small pinned scratch for scalar readbacks
+  void* pinned_scalar = nullptr;
+};
+
+namespace dfgpu {
+
+inline void set_device(dfgpu_ctx* ctx) { DF_CUDA(cudaSetDevice(ctx->device)); }
+
+// stream-ordered device buffer (cudaMallocAsync pool: no implicit device sync on alloc/free)
+struct DevBuf {
+  dfgpu_ctx* ctx = nullptr;
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  DevBuf() {}
+  DevBuf(dfgpu_ctx* c, size_t n) { alloc(c, n); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept { *this = std::move(o); }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); ctx = o.ctx; ptr = o.ptr; bytes = o.bytes; o.ptr = nullptr; o.bytes = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(dfgpu_ctx* c, size_t n) {
+    release();
+    ctx = c;
+    bytes = n;
+    if (n == 0) { ptr = nullptr; return; }
+    DF_CUDA(cudaMallocAsync(&ptr, n, c->stream));
+  }
+  void release() {
+    if (ptr) { cudaFreeAsync(ptr, ctx->stream); ptr = nullptr; bytes = 0; }
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(ptr); }
+  void zero() { if (ptr) DF_CUDA(cudaMemsetAsync(ptr, 0, bytes, ctx->stream)); }
+  void fill(int byte) { if (ptr) DF_CUDA(cudaMemsetAsync(ptr, byte, bytes, ctx->stream)); }
+};
+
+// pinned host buffer
+struct HostBuf {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  HostBuf() {}
+  explicit HostBuf(size_t n) { alloc(n); }
+  HostBuf(const HostBuf&) = delete;
+  HostBuf& operator=(const HostBuf&) = delete;
+  HostBuf(HostBuf&& o) noexcept { ptr = o.ptr; bytes = o.bytes; o.ptr = nullptr; o.bytes = 0; }
+  HostBuf& operator=(HostBuf&& o) noexcept {
+    if (this != &o) { release(); ptr = o.ptr; bytes = o.bytes; o.ptr = nullptr; o.bytes = 0; }
+    return *this;
+  }
+  ~HostBuf() { release(); }
+  void alloc(size_t n) {
+    release();
+    bytes = n;
+    if (n == 0) return;
+    DF_CUDA(cudaMallocHost(&ptr, n));
+  }
+  void release() { if (ptr) { cudaFreeHost(ptr); ptr = nullptr; bytes = 0; } }
+};
+
+// A device-resident column: either a borrowed view or owning buffers.
+struct DCol {
+  int type = 0;
+  int64_t length = 0;
+  int64_t offset = 0;          // logical element offset into values/validity
+  const void* values = nullptr;
+  const uint8_t* validity = nullptr;  // nullptr = all valid
+  int64_t null_count = -1;
+  std::shared_ptr<DevBuf> own_values, own_validity;  // keep-alive when owning
+};
+
+inline DCol view_of(const dfgpu_column& c) {
+  DCol d;
+  d.type = c.type; d.length = c.length; d.offset = c.offset; d.values = c.values; d.validity = c.validity;
+  d.null_count = c.null_count;
+  if (c.null_count == 0) d.validity = nullptr;
+  return d;
+}
+
+inline DCol alloc_col(dfgpu_ctx* ctx, int type, int64_t rows, bool with_validity) {
+  DCol d;
+  d.type = type; d.length = rows; d.offset = 0;
+  d.own_values = std::make_shared<DevBuf>(ctx, type == DFGPU_BOOL ? bitmap_alloc_bytes(rows) : values_bytes(type, rows));
+  d.values = d.own_values->ptr;
+  if (with_validity) {
+    d.own_validity = std::make_shared<DevBuf>(ctx, bitmap_alloc_bytes(rows));
+    d.validity = d.own_validity->as<uint8_t>();
+  } else {
+    d.null_count = 0;
+  }
+  return d;
+}
+
+#define DF_LAUNCH_CHECK(ctx)            \
+  do {                                  \
+    (ctx)->launches++;                  \
+    DF_CUDA(cudaGetLastError());        \
+  } while (0)
+
+inline int grid_for(int64_t work_items, int per_block, int max_blocks = kNumSMs * 16) {
+  int64_t b = (work_items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+// read one device scalar back (stream-synchronising)
+template <class T>
+inline T read_scalar(dfgpu_ctx* ctx, const T* dptr) {
+  T* h = reinterpret_cast<T*>(ctx->pinned_scalar);
+  DF_CUDA(cudaMemcpyAsync(h, dptr, sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+  DF_CUDA(cudaStreamSynchronize(ctx->stream));
+  return *h;
+}
+
+// ------------------------------------------------------------------------------------------
+// device bit helpers (Arrow validity bitmaps are LSB-numbered)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool bit_get(const uint8_t* bm, int64_t i) { return (bm[i >> 3] >> (i & 7)) & 1; }
+
+// 128-bit streaming load (read-once data: keep it out of L1)
+__device__ __forceinline__ int4 ld_stream_16(const void* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_16(void* p, int4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ int64_t ld_stream_8(const int64_t* p) {
+  int64_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(r) : "l"(p));
+  return r;
+}
+
+}  // namespace dfgpu
+
+// extern "C" wrappers: exceptions -> status codes + ctx->last_error
+#define DF_API_BEGIN(ctxptr) dfgpu_ctx* _ctx = (ctxptr); try {
+#define DF_API_END                                                                   \
+  return DFGPU_OK; }                                                                 \
+  catch (const dfgpu::Error& e) { if (_ctx) _ctx->last_error = e.what(); return e.code; } \
+  catch (const std::exception& e) { if (_ctx) _ctx->last_error = e.what(); return DFGPU_ERR_INVALID; }

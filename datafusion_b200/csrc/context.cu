@@ -1,0 +1,310 @@
+// context.cu — ctx / memory / timing / generators / batch accessors of the C ABI (include/dfgpu.h).
+#include "batch.cuh"
+
+using namespace dfgpu;
+
+namespace dfgpu {
+
+// deterministic synthetic data: the same functions exist in oracle/gen.h so CPU and
+// GPU inputs are bit-identical without ever crossing PCIe.
+__host__ __device__ inline uint64_t perm_bijection(uint64_t i, uint64_t n, uint64_t seed) {
+  // cycle-walking Feistel permutation over [0, n)
+  int bits = 1;
+  while ((1ull << bits) < n) ++bits;
+  if (bits & 1) ++bits;
+  const int half = bits / 2;
+  const uint64_t mask = (1ull << half) - 1ull;
+  uint64_t x = i;
+  do {
+    uint64_t l = x >> half, r = x & mask;
+    for (int round = 0; round < 4; ++round) {
+      uint64_t f = mix64(r + seed * 0x9E3779B97F4A7C15ull + (uint64_t)round * 0xD1B54A32D192ED03ull) & mask;
+      uint64_t nl = r, nr = l ^ f;
+      l = nl; r = nr;
+    }
+    x = (l << half) | r;
+  } while (x >= n);
+  return x;
+}
+
+__global__ void generate_i64_kernel(int kind, uint64_t seed, int64_t a, int64_t b, int64_t start, int64_t n, int64_t* out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t idx = (uint64_t)(start + i);
+    int64_t v;
+    switch (kind) {
+      case DFGPU_GEN_SEQ: v = a + (int64_t)idx; break;
+      case DFGPU_GEN_UNIFORM: v = a + (int64_t)(splitmix64_at(seed, idx) % (uint64_t)b); break;
+      case DFGPU_GEN_SPLITMIX: v = (int64_t)splitmix64_at(seed, idx); break;
+      case DFGPU_GEN_PERM: v = a + (int64_t)perm_bijection(idx, (uint64_t)b, seed); break;
+      case DFGPU_GEN_SPARSE_OF: v = (int64_t)splitmix64_at(seed, splitmix64_at((uint64_t)a, idx) % (uint64_t)b); break;
+      default: v = 0;
+    }
+    out[i] = v;
+  }
+}
+
+__global__ void l2_flush_kernel(int4* p, size_t n16) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p[i] = make_int4((int)i, 1, 2, 3);
+}
+
+}  // namespace dfgpu
+
+extern "C" {
+
+const char* dfgpu_version(void) { return "dfgpu 0.1.0 (sm_100a)"; }
+
+int dfgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int dfgpu_ctx_create(int device, void* stream, dfgpu_ctx** out) {
+  if (!out) return DFGPU_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0 || device < 0 || device >= n) { cudaGetLastError(); return DFGPU_ERR_CUDA; }
+  std::unique_ptr<dfgpu_ctx> ctx(new dfgpu_ctx());
+  try {
+    ctx->device = device;
+    DF_CUDA(cudaSetDevice(device));
+    if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
+    else { DF_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    DF_CUDA(cudaMallocHost(&ctx->pinned_scalar, 256));
+    // keep freed blocks in the pool: operators re-allocate similar sizes every batch
+    cudaMemPool_t pool;
+    DF_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thresh = UINT64_MAX;
+    DF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  } catch (const Error&) { return DFGPU_ERR_CUDA; }
+  *out = ctx.release();
+  return DFGPU_OK;
+}
+
+void dfgpu_ctx_destroy(dfgpu_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->l2_scratch) cudaFree(ctx->l2_scratch);
+  if (ctx->pinned_scalar) cudaFreeHost(ctx->pinned_scalar);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* dfgpu_last_error(dfgpu_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null ctx"; }
+void* dfgpu_ctx_stream(dfgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int64_t dfgpu_launch_count(dfgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int dfgpu_sync(dfgpu_ctx* ctx) {
+  DF_API_BEGIN(ctx)
+  set_device(ctx);
+  DF_CUDA(cudaStreamSynchronize(ctx->stream));
+  DF_API_END
+}
+int dfgpu_malloc(dfgpu_ctx* ctx, size_t bytes, void** out) {
+  DF_API_BEGIN(ctx)
+  set_device(ctx);
+  DF_CUDA(cudaMallocAsync(out, bytes ? bytes : 8, ctx->stream));
+  DF_API_END
+}
+int dfgpu_free(dfgpu_ctx* ctx, void* p) {
+  DF_API_BEGIN(ctx)
+  set_device(ctx);
+  if (p) DF_CUDA(cudaFreeAsync(p, ctx->stream));
+  DF_API_END
+}
+int dfgpu_host_alloc(dfgpu_ctx* ctx, size_t bytes, void** out) {
+  DF_API_BEGIN(ctx)
+  set_device(ctx);
+  DF_CUDA(cudaMallocHost(out, bytes ? bytes : 8));
+  DF_API_END
+}
+int dfgpu_host_free(dfgpu_ctx* ctx, void* p) {
+  DF_API_BEGIN(ctx)
+  if (p) DF_CUDA(cudaFreeHost(p));
+  DF_API_END
+}
+int dfgpu_memcpy_h2d(dfgpu_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  DF_API_BEGIN(ctx)
+  set_device(ctx);
+  if (bytes) DF_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  DF_API_END
+}
+int dfgpu_memcpy_d2h(dfgpu_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  DF_API_BEGIN(ctx)
+  set_device(ctx);
+  if (bytes) DF_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  DF_API_END
+}
+int dfgpu_memset(dfgpu_ctx* ctx, void* dst, int value, size_t bytes) {
+  DF_API_BEGIN(ctx)
+  set_device(ctx);
+  if (bytes) DF_CUDA(cudaMemsetAsync(dst, value, bytes, ctx->stream));
+  DF_API_END
+}
+int dfgpu_flush_l2(dfgpu_ctx* ctx) {
+  DF_API_BEGIN(ctx)
+  set_device(ctx);
+  if (!ctx->l2_scratch) {
+    ctx->l2_scratch_bytes = 256ull << 20;  // 2x the 126 MB L2
+    DF_CUDA(cudaMalloc(&ctx->l2_scratch, ctx->l2_scratch_bytes));
+  }
+  l2_flush_kernel<<<kNumSMs * 8, 256, 0, ctx->stream>>>((int4*)ctx->l2_scratch, ctx->l2_scratch_bytes / 16);
+  DF_CUDA(cudaGetLastError());  // not counted in launches: bench hygiene, not product work
+  DF_API_END
+}
+
+int dfgpu_event_create(dfgpu_ctx* ctx, void** out) {
+  DF_API_BEGIN(ctx)
+  set_device(ctx);
+  cudaEvent_t ev;
+  DF_CUDA(cudaEventCreate(&ev));
+  *out = (void*)ev;
+  DF_API_END
+}
+int dfgpu_event_record(dfgpu_ctx* ctx, void* ev) {
+  DF_API_BEGIN(ctx)
+  set_device(ctx);
+  DF_CUDA(cudaEventRecord((cudaEvent_t)ev, ctx->stream));
+  DF_API_END
+}
+int dfgpu_event_elapsed_ms(dfgpu_ctx* ctx, void* start, void* stop, float* ms) {
+  DF_API_BEGIN(ctx)
+  set_device(ctx);
+  DF_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
+  DF_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  DF_API_END
+}
+int dfgpu_event_destroy(dfgpu_ctx* ctx, void* ev) {
+  DF_API_BEGIN(ctx)
+  if (ev) DF_CUDA(cudaEventDestroy((cudaEvent_t)ev));
+  DF_API_END
+}
+
+int dfgpu_generate_i64(dfgpu_ctx* ctx, int kind, uint64_t seed, int64_t a, int64_t b, int64_t start, int64_t n, int64_t* out_device) {
+  DF_API_BEGIN(ctx)
+  set_device(ctx);
+  DF_CHECK(kind >= 0 && kind <= DFGPU_GEN_SPARSE_OF, DFGPU_ERR_INVALID, "unknown generator kind");
+  if ((kind == DFGPU_GEN_UNIFORM || kind == DFGPU_GEN_PERM || kind == DFGPU_GEN_SPARSE_OF)) DF_CHECK(b > 0, DFGPU_ERR_INVALID, "generator range must be positive");
+  if (n > 0) {
+    generate_i64_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(kind, seed, a, b, start, n, out_device);
+    DF_CUDA(cudaGetLastError());
+  }
+  DF_API_END
+}
+
+// ---- output batches ----
+int64_t dfgpu_batch_num_rows(const dfgpu_batch* b) { return b ? b->rows : -1; }
+int32_t dfgpu_batch_num_columns(const dfgpu_batch* b) { return b ? (int32_t)(b->host ? b->hcols.size() : b->cols.size()) : -1; }
+int dfgpu_batch_is_host(const dfgpu_batch* b) { return b && b->host ? 1 : 0; }
+
+int dfgpu_batch_column(const dfgpu_batch* b, int32_t i, dfgpu_column* out) {
+  if (!b || !out || i < 0 || i >= dfgpu_batch_num_columns(b)) return DFGPU_ERR_INVALID;
+  memset(out, 0, sizeof(*out));
+  if (b->host) {
+    const HCol& h = b->hcols[i];
+    out->type = h.type; out->length = h.length; out->offset = 0; out->null_count = h.null_count;
+    out->values = h.values ? h.values->ptr : nullptr;
+    out->validity = h.validity ? (const uint8_t*)h.validity->ptr : nullptr;
+  } else {
+    const DCol& d = b->cols[i];
+    out->type = d.type; out->length = d.length; out->null_count = d.null_count;
+    out->values = d.values; out->validity = d.validity;
+    // DCol keeps `values` pre-advanced for fixed-width types; report offset 0 unless a bitmap needs it
+    out->offset = (d.type == DFGPU_BOOL || d.validity) ? d.offset : 0;
+    if (d.type != DFGPU_BOOL && d.validity && d.offset != 0) {
+      // express as an Arrow-style slice: step the values pointer back by the validity offset
+      out->values = (const char*)d.values - d.offset * type_width(d.type);
+    }
+  }
+  return DFGPU_OK;
+}
+
+void dfgpu_batch_release(dfgpu_batch* b) {
+  if (!b) return;
+  if (b->ctx) cudaSetDevice(b->ctx->device);
+  delete b;
+}
+
+// ---- Arrow C Data export of a host batch (struct array, one child per column) ----
+namespace {
+const char* arrow_format(int type) {
+  switch (type) {
+    case DFGPU_BOOL: return "b";
+    case DFGPU_INT8: return "c"; case DFGPU_UINT8: return "C";
+    case DFGPU_INT16: return "s"; case DFGPU_UINT16: return "S";
+    case DFGPU_INT32: return "i"; case DFGPU_UINT32: return "I";
+    case DFGPU_INT64: return "l"; case DFGPU_UINT64: return "L";
+    case DFGPU_FLOAT32: return "f"; case DFGPU_FLOAT64: return "g";
+    case DFGPU_DATE32: return "tdD"; case DFGPU_DATE64: return "tdm";
+    case DFGPU_TIMESTAMP: return "tsn:";
+    case DFGPU_DECIMAL128: return "d:38,0";
+    default: return "n";
+  }
+}
+struct ExportPrivate {
+  std::vector<HCol> cols;  // keeps the pinned buffers alive
+  std::vector<ArrowArray> child_arrays;
+  std::vector<ArrowArray*> child_ptrs;
+  std::vector<std::vector<const void*>> child_buffers;
+  const void* top_buffers[1] = {nullptr};
+};
+struct SchemaPrivate {
+  std::vector<ArrowSchema> children;
+  std::vector<ArrowSchema*> child_ptrs;
+  std::vector<std::string> names;
+};
+void release_child_array(ArrowArray* a) { a->release = nullptr; }
+void release_top_array(ArrowArray* a) {
+  if (!a || !a->release) return;
+  delete (ExportPrivate*)a->private_data;
+  a->release = nullptr;
+}
+void release_child_schema(ArrowSchema* s) { s->release = nullptr; }
+void release_top_schema(ArrowSchema* s) {
+  if (!s || !s->release) return;
+  delete (SchemaPrivate*)s->private_data;
+  s->release = nullptr;
+}
+}  // namespace
+
+int dfgpu_batch_export_arrow(dfgpu_batch* b, struct ArrowArray* out_array, struct ArrowSchema* out_schema) {
+  if (!b || !b->host || !out_array || !out_schema) return DFGPU_ERR_INVALID;
+  auto* p = new ExportPrivate();
+  p->cols = b->hcols;  // shared_ptr copies: the buffers outlive the dfgpu_batch
+  size_t n = p->cols.size();
+  p->child_arrays.resize(n); p->child_ptrs.resize(n); p->child_buffers.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    HCol& h = p->cols[i];
+    p->child_buffers[i] = {h.validity ? h.validity->ptr : nullptr, h.values ? h.values->ptr : nullptr};
+    ArrowArray& a = p->child_arrays[i];
+    memset(&a, 0, sizeof(a));
+    a.length = h.length; a.null_count = h.validity ? h.null_count : 0; a.offset = 0;
+    a.n_buffers = 2; a.buffers = p->child_buffers[i].data();
+    a.release = release_child_array;
+    p->child_ptrs[i] = &a;
+  }
+  memset(out_array, 0, sizeof(*out_array));
+  out_array->length = b->rows; out_array->null_count = 0; out_array->offset = 0;
+  out_array->n_buffers = 1; out_array->buffers = p->top_buffers;
+  out_array->n_children = (int64_t)n; out_array->children = p->child_ptrs.data();
+  out_array->release = release_top_array; out_array->private_data = p;
+
+  auto* sp = new SchemaPrivate();
+  sp->children.resize(n); sp->child_ptrs.resize(n); sp->names.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    sp->names[i] = "c" + std::to_string(i);
+    ArrowSchema& s = sp->children[i];
+    memset(&s, 0, sizeof(s));
+    s.format = arrow_format(p->cols[i].type); s.name = sp->names[i].c_str(); s.flags = ARROW_FLAG_NULLABLE;
+    s.release = release_child_schema;
+    sp->child_ptrs[i] = &s;
+  }
+  memset(out_schema, 0, sizeof(*out_schema));
+  out_schema->format = "+s"; out_schema->name = ""; out_schema->n_children = (int64_t)n;
+  out_schema->children = sp->child_ptrs.data(); out_schema->release = release_top_schema; out_schema->private_data = sp;
+  return DFGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,688 @@
+// filter.cu — PhysicalExpr::evaluate + GpuFilterExec.
+//
+// Reference path being replaced (SURVEY.md §8a rows a1–a7):
+//   FilterExecStream::poll_next       physical-plan/src/filter.rs:1364-1445
+//   filter_and_project                physical-plan/src/filter.rs:1339-1361
+//   BinaryExpr::evaluate              physical-expr/src/expressions/binary.rs:536-676
+//   apply / apply_cmp (+ float zero normalisation)   physical-expr-common/src/datum.rs:36-105
+//   and_kleene / or_kleene            physical-expr/src/expressions/binary.rs:1093-1116
+//   filter_record_batch (arrow-select 59.2.0; null mask entries count as false)  filter.rs:1412
+//   LimitedBatchCoalescer             physical-plan/src/coalesce/mod.rs:27-147
+//
+// B200 design: the reference walks the expression tree once per node per batch and allocates an
+// Arrow array for every intermediate.  Here the whole tree is a post-order program evaluated per
+// row in registers by ONE kernel (no intermediate arrays in HBM); a warp owns 32 consecutive rows
+// so Boolean results and validity leave as one ballot word per warp (Arrow's LSB bitmaps for free).
+// Selection = that bitmap -> popcount/scan -> index list -> one gather per projected column.
+#include "batch.cuh"
+#include "scan.cuh"
+
+namespace dfgpu {
+
+constexpr int kMaxNodes = 48;
+constexpr int kMaxStack = 16;
+
+struct ENode {
+  int kind, op;
+  int in_type;   // operand type (binary / unary / cast source)
+  int out_type;
+  const void* col; const uint8_t* valid; int64_t voff;  // COLUMN (BOOL: voff is also the value bit offset)
+  uint64_t lit; int lit_null;
+};
+struct EProgram { int n; ENode node[kMaxNodes]; };
+
+enum Cls : int { C_I64 = 0, C_U64 = 1, C_F64 = 2, C_BOOL = 3 };
+__host__ __device__ inline int cls_of(int t) {
+  if (t == DFGPU_BOOL) return C_BOOL;
+  if (type_is_float(t)) return C_F64;
+  if (type_is_unsigned_int(t)) return C_U64;
+  return C_I64;
+}
+
+// values travel on the evaluation stack as 64-bit payloads: ints sign/zero-extended, floats as
+// f64 bits (f32 widened exactly), bools as 0/1.
+__device__ __forceinline__ uint64_t load_col_value(const ENode& nd, int64_t row) {
+  switch (nd.out_type) {
+    case DFGPU_BOOL: return bit_get((const uint8_t*)nd.col, nd.voff + row) ? 1ull : 0ull;
+    case DFGPU_INT8: return (uint64_t)(int64_t)((const int8_t*)nd.col)[row];
+    case DFGPU_INT16: return (uint64_t)(int64_t)((const int16_t*)nd.col)[row];
+    case DFGPU_INT32: case DFGPU_DATE32: return (uint64_t)(int64_t)((const int32_t*)nd.col)[row];
+    case DFGPU_UINT8: return ((const uint8_t*)nd.col)[row];
+    case DFGPU_UINT16: return ((const uint16_t*)nd.col)[row];
+    case DFGPU_UINT32: return ((const uint32_t*)nd.col)[row];
+    case DFGPU_FLOAT32: { double d = (double)((const float*)nd.col)[row]; return (uint64_t)__double_as_longlong(d); }
+    default: return ((const uint64_t*)nd.col)[row];
+  }
+}
+
+// wrap an integer result to the width of its Arrow type (add_wrapping on Int32 wraps at 32 bits)
+__device__ __forceinline__ uint64_t wrap_to_type(uint64_t v, int t) {
+  switch (t) {
+    case DFGPU_INT8: return (uint64_t)(int64_t)(int8_t)v;
+    case DFGPU_INT16: return (uint64_t)(int64_t)(int16_t)v;
+    case DFGPU_INT32: case DFGPU_DATE32: return (uint64_t)(int64_t)(int32_t)v;
+    case DFGPU_UINT8: return v & 0xFFull;
+    case DFGPU_UINT16: return v & 0xFFFFull;
+    case DFGPU_UINT32: return v & 0xFFFFFFFFull;
+    case DFGPU_FLOAT32: { float f = (float)__longlong_as_double((long long)v); return (uint64_t)__double_as_longlong((double)f); }
+    default: return v;
+  }
+}
+
+// IEEE-754 totalOrder compare after -0.0 -> +0.0 normalisation (datum.rs:88-105)
+__device__ __forceinline__ int cmp_f64_total(double a, double b) {
+  long long x = __double_as_longlong(a), y = __double_as_longlong(b);
+  if ((x << 1) == 0) x = 0;
+  if ((y << 1) == 0) y = 0;
+  x ^= (long long)((unsigned long long)(x >> 63) >> 1);
+  y ^= (long long)((unsigned long long)(y >> 63) >> 1);
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+enum ErrBits : int { ERR_DIV_ZERO = 1, ERR_OVERFLOW = 2 };
+
+__device__ __forceinline__ void eval_binary(const ENode& nd, uint64_t a, bool av, uint64_t b, bool bv, uint64_t* r, bool* rv, int* err) {
+  const int op = nd.op;
+  const int c = cls_of(nd.in_type);
+  // ---- Kleene logic (and_kleene / or_kleene) ----
+  if (op == DFGPU_OP_AND) {
+    bool at = av && a, af = av && !a, bt = bv && b, bf = bv && !b;
+    if (af || bf) { *r = 0; *rv = true; } else if (at && bt) { *r = 1; *rv = true; } else { *r = 0; *rv = false; }
+    return;
+  }
+  if (op == DFGPU_OP_OR) {
+    bool at = av && a, af = av && !a, bt = bv && b, bf = bv && !b;
+    if (at || bt) { *r = 1; *rv = true; } else if (af && bf) { *r = 0; *rv = true; } else { *r = 0; *rv = false; }
+    return;
+  }
+  // ---- comparisons ----
+  if (op <= DFGPU_OP_GTEQ || op == DFGPU_OP_IS_DISTINCT_FROM || op == DFGPU_OP_IS_NOT_DISTINCT_FROM) {
+    int cmp;
+    if (c == C_F64) cmp = cmp_f64_total(__longlong_as_double((long long)a), __longlong_as_double((long long)b));
+    else if (c == C_U64 || c == C_BOOL) cmp = a < b ? -1 : (a > b ? 1 : 0);
+    else cmp = (long long)a < (long long)b ? -1 : ((long long)a > (long long)b ? 1 : 0);
+    if (op == DFGPU_OP_IS_DISTINCT_FROM || op == DFGPU_OP_IS_NOT_DISTINCT_FROM) {
+      bool distinct = (av != bv) || (av && bv && cmp != 0);
+      *r = (op == DFGPU_OP_IS_DISTINCT_FROM) ? distinct : !distinct;
+      *rv = true;  // never NULL (arrow-ord distinct / not_distinct)
+      return;
+    }
+    bool res;
+    switch (op) {
+      case DFGPU_OP_EQ: res = cmp == 0; break;
+      case DFGPU_OP_NEQ: res = cmp != 0; break;
+      case DFGPU_OP_LT: res = cmp < 0; break;
+      case DFGPU_OP_LTEQ: res = cmp <= 0; break;
+      case DFGPU_OP_GT: res = cmp > 0; break;
+      default: res = cmp >= 0; break;
+    }
+    *r = res; *rv = av && bv;  // result null = union of operand nulls (datum.rs:36-58)
+    return;
+  }
+  // ---- arithmetic / bitwise: null if either side is null; kernels run only on valid slots ----
+  *rv = av && bv;
+  if (!*rv) { *r = 0; return; }
+  if (c == C_F64) {
+    double x = __longlong_as_double((long long)a), y = __longlong_as_double((long long)b), z;
+    switch (op) {
+      case DFGPU_OP_PLUS: z = x + y; break;
+      case DFGPU_OP_MINUS: z = x - y; break;
+      case DFGPU_OP_MULTIPLY: z = x * y; break;
+      case DFGPU_OP_DIVIDE: z = x / y; break;
+      case DFGPU_OP_MODULO: z = fmod(x, y); break;
+      default: z = 0; break;
+    }
+    if (nd.out_type == DFGPU_FLOAT32) {
+      // f32 arithmetic happens in f32 in the reference: both inputs are exact f32 values, so round once
+      float xf = (float)x, yf = (float)y, zf;
+      switch (op) {
+        case DFGPU_OP_PLUS: zf = xf + yf; break;
+        case DFGPU_OP_MINUS: zf = xf - yf; break;
+        case DFGPU_OP_MULTIPLY: zf = xf * yf; break;
+        case DFGPU_OP_DIVIDE: zf = xf / yf; break;
+        case DFGPU_OP_MODULO: zf = fmodf(xf, yf); break;
+        default: zf = 0; break;
+      }
+      z = (double)zf;
+    }
+    *r = (uint64_t)__double_as_longlong(z);
+    return;
+  }
+  uint64_t z = 0;
+  switch (op) {
+    case DFGPU_OP_PLUS: z = a + b; break;       // add_wrapping
+    case DFGPU_OP_MINUS: z = a - b; break;      // sub_wrapping
+    case DFGPU_OP_MULTIPLY: z = a * b; break;   // mul_wrapping
+    case DFGPU_OP_DIVIDE:
+    case DFGPU_OP_MODULO:
+      if (b == 0) { *err |= ERR_DIV_ZERO; z = 0; break; }  // ArrowError::DivideByZero
+      if (c == C_I64) {
+        long long x = (long long)a, y = (long long)b;
+        // MIN / -1 overflows the type: arrow's checked `div` reports ArithmeticOverflow; `rem` yields 0
+        bool ovf = (y == -1) && (wrap_to_type((uint64_t)(-x), nd.out_type) == (uint64_t)x) && x != 0;
+        if (ovf) { if (op == DFGPU_OP_DIVIDE) *err |= ERR_OVERFLOW; z = 0; }
+        else z = (uint64_t)(op == DFGPU_OP_DIVIDE ? x / y : x % y);
+      } else z = op == DFGPU_OP_DIVIDE ? a / b : a % b;
+      break;
+    case DFGPU_OP_BITAND: z = a & b; break;
+    case DFGPU_OP_BITOR: z = a | b; break;
+    case DFGPU_OP_BITXOR: z = a ^ b; break;
+    case DFGPU_OP_SHIFT_LEFT: { int w = type_width(nd.out_type) * 8; z = (b < (uint64_t)w) ? (a << b) : 0; break; }
+    case DFGPU_OP_SHIFT_RIGHT: {
+      int w = type_width(nd.out_type) * 8;
+      if (c == C_I64) z = (b < (uint64_t)w) ? (uint64_t)((long long)a >> b) : (uint64_t)((long long)a >> 63);
+      else z = (b < (uint64_t)w) ? (a >> b) : 0;
+      break;
+    }
+  }
+  *r = wrap_to_type(z, nd.out_type);
+}
+
+__device__ __forceinline__ uint64_t cast_value(uint64_t v, int from, int to) {
+  int cf = cls_of(from), ct = cls_of(to);
+  if (ct == C_F64) {
+    double d = cf == C_F64 ? __longlong_as_double((long long)v) : (cf == C_U64 || cf == C_BOOL ? (double)v : (double)(long long)v);
+    if (to == DFGPU_FLOAT32) d = (double)(float)d;
+    return (uint64_t)__double_as_longlong(d);
+  }
+  if (ct == C_BOOL) return cf == C_F64 ? (__longlong_as_double((long long)v) != 0.0) : (v != 0);
+  uint64_t iv = cf == C_F64 ? (ct == C_U64 ? (uint64_t)__longlong_as_double((long long)v) : (uint64_t)(long long)__longlong_as_double((long long)v)) : v;
+  return wrap_to_type(iv, to);
+}
+
+// One kernel evaluates the whole expression.  Outputs: typed values (or bit-packed booleans),
+// validity words, and — for predicates — the selection words (valid AND true).
+__global__ void __launch_bounds__(256) expr_eval_kernel(EProgram p, int64_t n, void* __restrict__ out_values, uint32_t* __restrict__ out_boolwords,
+                                                     uint32_t* __restrict__ out_valid, uint32_t* __restrict__ out_select, int* __restrict__ err_flag) {
+  const int64_t nw = (n + 31) / 32;
+  const int lane = threadIdx.x & 31;
+  const int root_type = p.node[p.n - 1].out_type;
+  int err = 0;
+  for (int64_t wi = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; wi < nw; wi += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int64_t row = wi * 32 + lane;
+    uint64_t rv = 0;
+    bool rok = false;
+    if (row < n) {
+      uint64_t sv[kMaxStack];
+      bool sk[kMaxStack];
+      int sp = 0;
+#pragma unroll 1
+      for (int i = 0; i < p.n; ++i) {
+        const ENode& nd = p.node[i];
+        switch (nd.kind) {
+          case DFGPU_EXPR_COLUMN:
+            sk[sp] = !(nd.valid && !bit_get(nd.valid, nd.voff + row));
+            sv[sp] = load_col_value(nd, row);
+            ++sp;
+            break;
+          case DFGPU_EXPR_LITERAL:
+            sk[sp] = !nd.lit_null; sv[sp] = nd.lit; ++sp;
+            break;
+          case DFGPU_EXPR_BINARY: {
+            uint64_t r; bool ok;
+            eval_binary(nd, sv[sp - 2], sk[sp - 2], sv[sp - 1], sk[sp - 1], &r, &ok, &err);
+            sp -= 1; sv[sp - 1] = r; sk[sp - 1] = ok;
+            break;
+          }
+          case DFGPU_EXPR_NOT: sv[sp - 1] = sv[sp - 1] ? 0 : 1; break;  // NULL stays NULL
+          case DFGPU_EXPR_IS_NULL: sv[sp - 1] = sk[sp - 1] ? 0 : 1; sk[sp - 1] = true; break;
+          case DFGPU_EXPR_IS_NOT_NULL: sv[sp - 1] = sk[sp - 1] ? 1 : 0; sk[sp - 1] = true; break;
+          case DFGPU_EXPR_NEGATIVE:
+            if (cls_of(nd.out_type) == C_F64) sv[sp - 1] ^= 0x8000000000000000ull;
+            else sv[sp - 1] = wrap_to_type(0ull - sv[sp - 1], nd.out_type);  // neg_wrapping
+            break;
+          case DFGPU_EXPR_CAST: sv[sp - 1] = cast_value(sv[sp - 1], nd.in_type, nd.out_type); break;
+        }
+      }
+      rv = sv[0]; rok = sk[0];
+      if (!rok) rv = 0;
+      if (out_values) {
+        switch (root_type) {
+          case DFGPU_INT8: case DFGPU_UINT8: ((uint8_t*)out_values)[row] = (uint8_t)rv; break;
+          case DFGPU_INT16: case DFGPU_UINT16: ((uint16_t*)out_values)[row] = (uint16_t)rv; break;
+          case DFGPU_INT32: case DFGPU_UINT32: case DFGPU_DATE32: ((uint32_t*)out_values)[row] = (uint32_t)rv; break;
+          case DFGPU_FLOAT32: ((float*)out_values)[row] = (float)__longlong_as_double((long long)rv); break;
+          default: ((uint64_t*)out_values)[row] = rv; break;
+        }
+      }
+    }
+    uint32_t vw = __ballot_sync(0xffffffffu, rok);
+    uint32_t bw = __ballot_sync(0xffffffffu, rok && (rv & 1));
+    if (lane == 0) {
+      if (out_valid) out_valid[wi] = vw;
+      if (out_boolwords) out_boolwords[wi] = bw;  // NULL slots hold 0
+      if (out_select) out_select[wi] = bw;
+    }
+  }
+  if (err) atomicOr(err_flag, err);
+}
+
+// ---- fast path: `column <cmp> literal` on an 8-byte integer column without NULLs ------------
+// 128-bit vectorised loads, two rows per load, 8 loads in flight per thread; each warp emits whole
+// 32-bit selection words.  (C1: `x:int64 > c`.)
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {  // bit i -> bit 2i
+  x &= 0xFFFFu;
+  x = (x | (x << 8)) & 0x00FF00FFu;
+  x = (x | (x << 4)) & 0x0F0F0F0Fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
+template <int OP>
+__device__ __forceinline__ bool cmp_i64(int64_t a, int64_t lit) {
+  if (OP == DFGPU_OP_EQ) return a == lit;
+  if (OP == DFGPU_OP_NEQ) return a != lit;
+  if (OP == DFGPU_OP_LT) return a < lit;
+  if (OP == DFGPU_OP_LTEQ) return a <= lit;
+  if (OP == DFGPU_OP_GT) return a > lit;
+  return a >= lit;
+}
+// A warp owns 512 consecutive rows per iteration: 8 coalesced 512-byte wavefronts of int4 loads in
+// flight, two ballots per wavefront, bit-interleaved into two selection words.
+template <int OP>
+__global__ void __launch_bounds__(256) cmp_i64_scalar_kernel(const int64_t* __restrict__ col, int64_t n, int64_t lit, uint32_t* __restrict__ select_words) {
+  constexpr int K = 8;
+  const int lane = threadIdx.x & 31;
+  const int64_t nchunks = n / (64 * K);
+  const int64_t warp_id = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = warp_id; c < nchunks; c += nwarps) {
+    const int4* p = reinterpret_cast<const int4*>(col + c * 64 * K);
+    int4 v[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = ld_stream_16(p + k * 32 + lane);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      int64_t a = (int64_t)(((uint64_t)(uint32_t)v[k].y << 32) | (uint32_t)v[k].x);
+      int64_t b = (int64_t)(((uint64_t)(uint32_t)v[k].w << 32) | (uint32_t)v[k].z);
+      uint32_t ba = __ballot_sync(0xffffffffu, cmp_i64<OP>(a, lit));  // even rows
+      uint32_t bb = __ballot_sync(0xffffffffu, cmp_i64<OP>(b, lit));  // odd rows
+      if (lane < 2) {
+        uint32_t ha = lane ? (ba >> 16) : ba, hb = lane ? (bb >> 16) : bb;
+        select_words[c * 2 * K + k * 2 + lane] = spread16(ha) | (spread16(hb) << 1);
+      }
+    }
+  }
+  // tail (< 512 rows): one word per thread of the first block
+  if (blockIdx.x == 0) {
+    const int64_t tail0 = nchunks * 64 * K;
+    const int64_t nw = (n + 31) / 32;
+    for (int64_t w = tail0 / 32 + threadIdx.x; w < nw; w += blockDim.x) {
+      uint32_t word = 0;
+      for (int k = 0; k < 32 && w * 32 + k < n; ++k) word |= (uint32_t)cmp_i64<OP>(col[w * 32 + k], lit) << k;
+      select_words[w] = word;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: type inference + program binding
+// ------------------------------------------------------------------------------------------
+struct ExprPlan {
+  std::vector<dfgpu_expr_node> nodes;
+  std::vector<int> in_type, out_type;
+  int root_type = 0;
+};
+
+static bool is_cmp_op(int op) { return (op >= DFGPU_OP_EQ && op <= DFGPU_OP_GTEQ) || op == DFGPU_OP_IS_DISTINCT_FROM || op == DFGPU_OP_IS_NOT_DISTINCT_FROM; }
+static bool is_arith_op(int op) { return op >= DFGPU_OP_PLUS && op <= DFGPU_OP_MODULO; }
+static bool is_bit_op(int op) { return op >= DFGPU_OP_BITAND && op <= DFGPU_OP_SHIFT_RIGHT; }
+static bool expr_type_ok(int t) {
+  return t == DFGPU_BOOL || type_is_int(t) || type_is_float(t);
+}
+
+ExprPlan plan_expr(const int32_t* schema_types, int n_cols, const dfgpu_expr_node* nodes, int n_nodes) {
+  DF_CHECK(n_nodes >= 1 && n_nodes <= kMaxNodes, DFGPU_ERR_UNSUPPORTED, "expression: 1..48 nodes supported");
+  ExprPlan p;
+  p.nodes.assign(nodes, nodes + n_nodes);
+  p.in_type.assign(n_nodes, 0);
+  p.out_type.assign(n_nodes, 0);
+  std::vector<int> stack;       // node index of each stack entry
+  for (int i = 0; i < n_nodes; ++i) {
+    const dfgpu_expr_node& nd = nodes[i];
+    switch (nd.kind) {
+      case DFGPU_EXPR_COLUMN:
+        DF_CHECK(nd.a >= 0 && nd.a < n_cols, DFGPU_ERR_INVALID, "expression: column index out of range");
+        DF_CHECK(expr_type_ok(schema_types[nd.a]), DFGPU_ERR_UNSUPPORTED, "expression: column type not supported on the GPU");
+        p.out_type[i] = schema_types[nd.a];
+        stack.push_back(i);
+        break;
+      case DFGPU_EXPR_LITERAL:
+        DF_CHECK(expr_type_ok(nd.type), DFGPU_ERR_UNSUPPORTED, "expression: literal type not supported on the GPU");
+        p.out_type[i] = nd.type;
+        stack.push_back(i);
+        break;
+      case DFGPU_EXPR_BINARY: {
+        DF_CHECK(stack.size() >= 2, DFGPU_ERR_INVALID, "expression: malformed program (binary needs two operands)");
+        int r = stack.back(); stack.pop_back();
+        int l = stack.back(); stack.pop_back();
+        int lt = p.out_type[l], rt = p.out_type[r];
+        // the planner coerces both sides to one type (expr-common type_coercion); we insist on it
+        DF_CHECK(lt == rt || (cls_of(lt) == cls_of(rt) && type_width(lt) == type_width(rt)), DFGPU_ERR_INVALID,
+                 "expression: binary operands must already be coerced to a common type");
+        p.in_type[i] = lt;
+        if (nd.a == DFGPU_OP_AND || nd.a == DFGPU_OP_OR) {
+          DF_CHECK(lt == DFGPU_BOOL, DFGPU_ERR_INVALID, "expression: AND/OR need Boolean operands");
+          p.out_type[i] = DFGPU_BOOL;
+        } else if (is_cmp_op(nd.a)) p.out_type[i] = DFGPU_BOOL;
+        else if (is_arith_op(nd.a)) {
+          DF_CHECK(lt != DFGPU_BOOL, DFGPU_ERR_INVALID, "expression: arithmetic on Boolean");
+          DF_CHECK(!(lt == DFGPU_DATE32 || lt == DFGPU_DATE64 || lt == DFGPU_TIMESTAMP), DFGPU_ERR_UNSUPPORTED, "expression: temporal arithmetic stays on the CPU operator");
+          p.out_type[i] = lt;
+        } else if (is_bit_op(nd.a)) {
+          DF_CHECK(type_is_int(lt), DFGPU_ERR_INVALID, "expression: bitwise operators need integer operands");
+          p.out_type[i] = lt;
+        } else throw Error(DFGPU_ERR_UNSUPPORTED, "expression: operator not supported on the GPU");
+        stack.push_back(i);
+        break;
+      }
+      case DFGPU_EXPR_NOT:
+        DF_CHECK(!stack.empty() && p.out_type[stack.back()] == DFGPU_BOOL, DFGPU_ERR_INVALID, "expression: NOT needs a Boolean operand");
+        p.in_type[i] = DFGPU_BOOL; p.out_type[i] = DFGPU_BOOL; stack.back() = i;
+        break;
+      case DFGPU_EXPR_IS_NULL: case DFGPU_EXPR_IS_NOT_NULL:
+        DF_CHECK(!stack.empty(), DFGPU_ERR_INVALID, "expression: malformed program");
+        p.in_type[i] = p.out_type[stack.back()]; p.out_type[i] = DFGPU_BOOL; stack.back() = i;
+        break;
+      case DFGPU_EXPR_NEGATIVE:
+        DF_CHECK(!stack.empty() && p.out_type[stack.back()] != DFGPU_BOOL, DFGPU_ERR_INVALID, "expression: negative needs a numeric operand");
+        p.in_type[i] = p.out_type[stack.back()]; p.out_type[i] = p.in_type[i]; stack.back() = i;
+        break;
+      case DFGPU_EXPR_CAST:
+        DF_CHECK(!stack.empty() && expr_type_ok(nd.type), DFGPU_ERR_UNSUPPORTED, "expression: cast target not supported");
+        p.in_type[i] = p.out_type[stack.back()]; p.out_type[i] = nd.type; stack.back() = i;
+        break;
+      default: throw Error(DFGPU_ERR_INVALID, "expression: unknown node kind");
+    }
+    DF_CHECK((int)stack.size() <= kMaxStack, DFGPU_ERR_UNSUPPORTED, "expression: too deep");
+  }
+  DF_CHECK(stack.size() == 1, DFGPU_ERR_INVALID, "expression: malformed program (stack must end with one value)");
+  p.root_type = p.out_type[n_nodes - 1];
+  return p;
+}
+
+static uint64_t literal_bits(const dfgpu_expr_node& nd) {
+  if (type_is_float(nd.type)) {
+    double d = nd.lit_f64;
+    if (nd.type == DFGPU_FLOAT32) d = (double)(float)d;
+    uint64_t b; memcpy(&b, &d, 8); return b;
+  }
+  if (nd.type == DFGPU_BOOL) return nd.lit_i64 ? 1 : 0;
+  switch (nd.type) {
+    case DFGPU_INT8: return (uint64_t)(int64_t)(int8_t)nd.lit_i64;
+    case DFGPU_INT16: return (uint64_t)(int64_t)(int16_t)nd.lit_i64;
+    case DFGPU_INT32: case DFGPU_DATE32: return (uint64_t)(int64_t)(int32_t)nd.lit_i64;
+    case DFGPU_UINT8: return (uint64_t)nd.lit_i64 & 0xFFull;
+    case DFGPU_UINT16: return (uint64_t)nd.lit_i64 & 0xFFFFull;
+    case DFGPU_UINT32: return (uint64_t)nd.lit_i64 & 0xFFFFFFFFull;
+    default: return (uint64_t)nd.lit_i64;
+  }
+}
+
+// Evaluate `plan` over device columns.  want_select: also produce selection words (valid & true).
+struct EvalResult { DCol column; DevBuf select_words; };
+
+EvalResult evaluate_expr(dfgpu_ctx* ctx, const ExprPlan& plan, const std::vector<DCol>& cols, int64_t n, bool want_column, bool want_select) {
+  EvalResult res;
+  const int64_t nw = (n + 31) / 32;
+  if (want_select) res.select_words.alloc(ctx, (size_t)std::max<int64_t>(nw, 1) * 4);
+  // fast path: Column(int64-like, no nulls) cmp Literal(non-null)
+  if (want_select && !want_column && plan.nodes.size() == 3 && plan.nodes[0].kind == DFGPU_EXPR_COLUMN && plan.nodes[1].kind == DFGPU_EXPR_LITERAL &&
+      plan.nodes[2].kind == DFGPU_EXPR_BINARY && plan.nodes[2].a >= DFGPU_OP_EQ && plan.nodes[2].a <= DFGPU_OP_GTEQ && !plan.nodes[1].is_null) {
+    const DCol& c = cols[plan.nodes[0].a];
+    if (cls_of(c.type) == C_I64 && type_width(c.type) == 8 && !c.validity && ((uintptr_t)c.values % 16 == 0)) {
+      if (n > 0) {
+        const int64_t* p = (const int64_t*)c.values;
+        int64_t lit = (int64_t)literal_bits(plan.nodes[1]);
+        int grid = grid_for((n + 511) / 512 * 32, 256, kNumSMs * 8);
+        uint32_t* sw = res.select_words.as<uint32_t>();
+        switch (plan.nodes[2].a) {
+          case DFGPU_OP_EQ: cmp_i64_scalar_kernel<DFGPU_OP_EQ><<<grid, 256, 0, ctx->stream>>>(p, n, lit, sw); break;
+          case DFGPU_OP_NEQ: cmp_i64_scalar_kernel<DFGPU_OP_NEQ><<<grid, 256, 0, ctx->stream>>>(p, n, lit, sw); break;
+          case DFGPU_OP_LT: cmp_i64_scalar_kernel<DFGPU_OP_LT><<<grid, 256, 0, ctx->stream>>>(p, n, lit, sw); break;
+          case DFGPU_OP_LTEQ: cmp_i64_scalar_kernel<DFGPU_OP_LTEQ><<<grid, 256, 0, ctx->stream>>>(p, n, lit, sw); break;
+          case DFGPU_OP_GT: cmp_i64_scalar_kernel<DFGPU_OP_GT><<<grid, 256, 0, ctx->stream>>>(p, n, lit, sw); break;
+          default: cmp_i64_scalar_kernel<DFGPU_OP_GTEQ><<<grid, 256, 0, ctx->stream>>>(p, n, lit, sw); break;
+        }
+        DF_LAUNCH_CHECK(ctx);
+      }
+      return res;
+    }
+  }
+  EProgram prog;
+  memset(&prog, 0, sizeof(prog));
+  prog.n = (int)plan.nodes.size();
+  bool any_nullable = false;
+  for (int i = 0; i < prog.n; ++i) {
+    const dfgpu_expr_node& nd = plan.nodes[i];
+    ENode& e = prog.node[i];
+    e.kind = nd.kind; e.op = nd.a; e.in_type = plan.in_type[i]; e.out_type = plan.out_type[i];
+    if (nd.kind == DFGPU_EXPR_COLUMN) {
+      const DCol& c = cols[nd.a];
+      DF_CHECK(c.type == plan.out_type[i], DFGPU_ERR_INVALID, "expression: batch column type differs from the planned schema");
+      e.col = c.values; e.valid = c.validity; e.voff = c.offset;
+      any_nullable |= (c.validity != nullptr);
+    } else if (nd.kind == DFGPU_EXPR_LITERAL) {
+      e.lit = literal_bits(nd); e.lit_null = nd.is_null;
+      any_nullable |= (nd.is_null != 0);
+    }
+  }
+  const int rt = plan.root_type;
+  if (want_column) {
+    res.column = alloc_col(ctx, rt, n, true);
+  }
+  DevBuf err(ctx, 4);
+  err.zero();
+  if (n > 0) {
+    expr_eval_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(
+        prog, n, (want_column && rt != DFGPU_BOOL) ? res.column.own_values->ptr : nullptr,
+        (want_column && rt == DFGPU_BOOL) ? res.column.own_values->as<uint32_t>() : nullptr,
+        want_column ? res.column.own_validity->as<uint32_t>() : nullptr, want_select ? res.select_words.as<uint32_t>() : nullptr, err.as<int>());
+    DF_LAUNCH_CHECK(ctx);
+    int e = read_scalar<int>(ctx, err.as<int>());
+    if (e & ERR_DIV_ZERO) throw Error(DFGPU_ERR_ARITH, "Arrow error: Divide by zero error");
+    if (e & ERR_OVERFLOW) throw Error(DFGPU_ERR_ARITH, "Arrow error: Arithmetic overflow");
+  }
+  if (want_column) res.column.null_count = -1;
+  (void)any_nullable;
+  return res;
+}
+
+}  // namespace dfgpu
+
+// ==========================================================================================
+// GpuFilterExec
+// ==========================================================================================
+using namespace dfgpu;
+
+struct dfgpu_filter {
+  dfgpu_ctx* ctx = nullptr;
+  std::vector<int> schema, projection;
+  ExprPlan plan;
+  int64_t batch_size = 8192, fetch = -1;
+  bool finished = false, limit_reached = false;
+  // coalescer state: pending filtered parts (LimitedBatchCoalescer, coalesce/mod.rs:27-147)
+  std::vector<std::vector<DCol>> pending;
+  int64_t pending_rows = 0, total_rows = 0;
+  std::deque<BatchPtr> outq;
+  int64_t m_input_rows = 0, m_output_rows = 0, m_input_batches = 0, m_output_batches = 0;
+};
+
+namespace dfgpu {
+
+static void filter_flush(dfgpu_filter* f, bool final_flush) {
+  dfgpu_ctx* ctx = f->ctx;
+  if (f->pending_rows == 0) return;
+  if (!final_flush && f->batch_size > 0 && f->pending_rows < f->batch_size) return;
+  // concatenate the buffered parts, then cut batch_size-row batches (BatchCoalescer emits exactly target-size batches)
+  size_t ncols = f->projection.size();
+  std::vector<DCol> merged;
+  for (size_t c = 0; c < ncols; ++c) {
+    std::vector<DCol> parts;
+    for (auto& b : f->pending) parts.push_back(b[c]);
+    merged.push_back(concat_columns(ctx, parts, f->schema[f->projection[c]]));
+  }
+  int64_t rows = f->pending_rows;
+  f->pending.clear();
+  f->pending_rows = 0;
+  int64_t pos = 0;
+  const int64_t bs = f->batch_size > 0 ? f->batch_size : rows;
+  while (rows - pos >= bs || (final_flush && pos < rows)) {
+    int64_t len = std::min<int64_t>(bs, rows - pos);
+    BatchPtr b(new dfgpu_batch());
+    b->ctx = ctx; b->rows = len; b->host = false;
+    for (size_t c = 0; c < ncols; ++c) b->cols.push_back((pos == 0 && len == rows) ? merged[c] : slice_column(merged[c], pos, len));
+    f->m_output_rows += len;
+    f->m_output_batches++;
+    f->outq.push_back(std::move(b));
+    pos += len;
+  }
+  if (pos < rows) {
+    std::vector<DCol> rest;
+    for (size_t c = 0; c < ncols; ++c) rest.push_back(slice_column(merged[c], pos, rows - pos));
+    f->pending.push_back(std::move(rest));
+    f->pending_rows = rows - pos;
+  }
+}
+
+static void filter_push(dfgpu_filter* f, const std::vector<DCol>& cols) {
+  DF_CHECK(!f->finished, DFGPU_ERR_STATE, "push after finish");
+  DF_CHECK(cols.size() == f->schema.size(), DFGPU_ERR_INVALID, "filter input column count mismatch");
+  dfgpu_ctx* ctx = f->ctx;
+  set_device(ctx);
+  int64_t n = cols.empty() ? 0 : cols[0].length;
+  for (size_t c = 0; c < cols.size(); ++c) {
+    DF_CHECK(cols[c].type == f->schema[c], DFGPU_ERR_INVALID, "filter input column type mismatch");
+    DF_CHECK(cols[c].length == n, DFGPU_ERR_INVALID, "filter input ragged columns");
+  }
+  f->m_input_rows += n;
+  f->m_input_batches++;
+  if (n == 0 || f->limit_reached) return;
+  DF_CHECK(n < 0xFFFFFFFFll, DFGPU_ERR_UNSUPPORTED, "filter: a batch must have < 2^32-1 rows");
+  EvalResult ev = evaluate_expr(ctx, f->plan, cols, n, false, true);
+  DevBuf idx;
+  int64_t kept = compact_flag_indices(ctx, ev.select_words.as<uint32_t>(), n, 1, &idx);
+  if (kept == 0) return;
+  if (f->fetch >= 0 && f->total_rows + kept >= f->fetch) {  // LimitReached: keep only the head (coalesce/mod.rs:100-112)
+    kept = f->fetch - f->total_rows;
+    f->limit_reached = true;
+  }
+  f->total_rows += kept;
+  if (kept == 0) return;
+  std::vector<DCol> part;
+  for (int pc : f->projection) part.push_back(take_column(ctx, cols[pc], idx.as<uint32_t>(), kept, false));
+  f->pending.push_back(std::move(part));
+  f->pending_rows += kept;
+  filter_flush(f, false);
+}
+
+}  // namespace dfgpu
+
+extern "C" {
+
+int dfgpu_filter_create(dfgpu_ctx* ctx, const int32_t* schema_types, int32_t n_cols, const dfgpu_expr_node* predicate, int32_t n_nodes,
+                        const int32_t* projection, int32_t n_projection, int64_t batch_size, int64_t fetch, dfgpu_filter** out) {
+  DF_API_BEGIN(ctx)
+  DF_CHECK(ctx && out && schema_types && predicate, DFGPU_ERR_INVALID, "null argument");
+  std::unique_ptr<dfgpu_filter> f(new dfgpu_filter());
+  f->ctx = ctx;
+  f->schema.assign(schema_types, schema_types + n_cols);
+  f->plan = plan_expr(schema_types, n_cols, predicate, n_nodes);
+  DF_CHECK(f->plan.root_type == DFGPU_BOOL, DFGPU_ERR_INVALID, "Cannot create filter_array from non-boolean predicates");  // filter.rs:1355-1359
+  if (projection) {
+    for (int i = 0; i < n_projection; ++i) {
+      DF_CHECK(projection[i] >= 0 && projection[i] < n_cols, DFGPU_ERR_INVALID, "projection index out of range");
+      f->projection.push_back(projection[i]);
+    }
+  } else for (int i = 0; i < n_cols; ++i) f->projection.push_back(i);
+  for (int pc : f->projection) DF_CHECK(type_width(f->schema[pc]) >= 0, DFGPU_ERR_UNSUPPORTED, "filter: column type not supported");
+  f->batch_size = batch_size;
+  f->fetch = fetch;
+  *out = f.release();
+  DF_API_END
+}
+int dfgpu_filter_push_host(dfgpu_filter* f, const dfgpu_column* cols, int32_t n_cols) {
+  DF_API_BEGIN(f ? f->ctx : nullptr)
+  set_device(f->ctx);
+  std::vector<DCol> v;
+  for (int i = 0; i < n_cols; ++i) v.push_back(upload_column(f->ctx, cols[i]));
+  filter_push(f, v);
+  DF_API_END
+}
+int dfgpu_filter_push_device(dfgpu_filter* f, const dfgpu_column* cols, int32_t n_cols) {
+  DF_API_BEGIN(f ? f->ctx : nullptr)
+  std::vector<DCol> v;
+  for (int i = 0; i < n_cols; ++i) v.push_back(device_view(cols[i]));
+  filter_push(f, v);
+  DF_API_END
+}
+int dfgpu_filter_finish(dfgpu_filter* f) {
+  DF_API_BEGIN(f ? f->ctx : nullptr)
+  DF_CHECK(!f->finished, DFGPU_ERR_STATE, "finish called twice");
+  f->finished = true;
+  set_device(f->ctx);
+  filter_flush(f, true);
+  DF_API_END
+}
+int dfgpu_filter_next(dfgpu_filter* f, int host, dfgpu_batch** out) {
+  dfgpu_ctx* _ctx = f ? f->ctx : nullptr;
+  try {
+    DF_CHECK(f && out, DFGPU_ERR_INVALID, "null argument");
+    if (f->outq.empty()) { *out = nullptr; return DFGPU_END; }
+    BatchPtr b = std::move(f->outq.front());
+    f->outq.pop_front();
+    if (host) { set_device(f->ctx); b = to_host_batch(f->ctx, *b); }
+    *out = b.release();
+    return DFGPU_OK;
+  } catch (const dfgpu::Error& e) { if (_ctx) _ctx->last_error = e.what(); return e.code; }
+  catch (const std::exception& e) { if (_ctx) _ctx->last_error = e.what(); return DFGPU_ERR_INVALID; }
+}
+int64_t dfgpu_filter_metric(dfgpu_filter* f, const char* name) {
+  if (!f || !name) return -1;
+  std::string s(name);
+  if (s == "input_rows") return f->m_input_rows;
+  if (s == "output_rows") return f->m_output_rows;
+  if (s == "input_batches") return f->m_input_batches;
+  if (s == "output_batches") return f->m_output_batches;
+  if (s == "selectivity_num") return f->total_rows;   // filter.rs:1312-1330: selectivity = output_rows / input_rows
+  if (s == "selectivity_den") return f->m_input_rows;
+  return -1;
+}
+void dfgpu_filter_destroy(dfgpu_filter* f) {
+  if (!f) return;
+  cudaSetDevice(f->ctx->device);
+  delete f;
+}
+
+static int expr_evaluate_common(dfgpu_ctx* ctx, std::vector<DCol>& v, int64_t n_rows, const dfgpu_expr_node* expr, int32_t n_nodes, dfgpu_batch** out) {
+  std::vector<int32_t> types;
+  for (auto& c : v) types.push_back(c.type);
+  ExprPlan plan = plan_expr(types.data(), (int)types.size(), expr, n_nodes);
+  EvalResult ev = evaluate_expr(ctx, plan, v, n_rows, true, false);
+  BatchPtr b(new dfgpu_batch());
+  b->ctx = ctx; b->rows = n_rows; b->host = false;
+  b->cols.push_back(std::move(ev.column));
+  *out = b.release();
+  return DFGPU_OK;
+}
+int dfgpu_expr_evaluate_device(dfgpu_ctx* ctx, const dfgpu_column* cols, int32_t n_cols, int64_t n_rows, const dfgpu_expr_node* expr, int32_t n_nodes, dfgpu_batch** out) {
+  DF_API_BEGIN(ctx)
+  set_device(ctx);
+  std::vector<DCol> v;
+  for (int i = 0; i < n_cols; ++i) v.push_back(device_view(cols[i]));
+  expr_evaluate_common(ctx, v, n_rows, expr, n_nodes, out);
+  DF_API_END
+}
+int dfgpu_expr_evaluate_host(dfgpu_ctx* ctx, const dfgpu_column* cols, int32_t n_cols, int64_t n_rows, const dfgpu_expr_node* expr, int32_t n_nodes, dfgpu_batch** out) {
+  DF_API_BEGIN(ctx)
+  set_device(ctx);
+  std::vector<DCol> v;
+  for (int i = 0; i < n_cols; ++i) v.push_back(upload_column(ctx, cols[i]));
+  dfgpu_batch* dev = nullptr;
+  expr_evaluate_common(ctx, v, n_rows, expr, n_nodes, &dev);
+  BatchPtr devp(dev);
+  *out = to_host_batch(ctx, *devp).release();
+  DF_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,771 @@
+// hash_join.cu — GpuHashJoinExec: build-side table construction + probe-side lookup/emit.
+//
+// Reference path being replaced (SURVEY.md §8a rows a9–a16):
+//   build : collect_left_input            joins/hash_join/exec.rs:2569-2776
+//           try_create_array_map          joins/hash_join/exec.rs:111-191   (perfect-hash / ArrayMap)
+//           update_hash / update_from_iter joins/utils.rs:2127-2165, joins/join_hash_map.rs:307-337
+//   probe : lookup_join_hashmap           joins/hash_join/stream.rs:396-438
+//           get_matched_indices_with_limit_offset  joins/join_hash_map.rs:389-484, chain.rs:29-70
+//           ArrayMap::lookup_and_get_indices       joins/array_map.rs:247-372
+//           equal_rows_arr                joins/utils.rs:2191-2257
+//           adjust_indices_by_join_type   joins/utils.rs:1432-1490
+//           build_batch_from_indices      joins/utils.rs:1332-1387
+//   final : process_unmatched_build_batch joins/hash_join/stream.rs:1002-1100
+//
+// B200 design (not a translation of the hashbrown + next[] structure):
+//   * one open-addressing table of 16-byte slots {tag:u64, head:u32, cnt:u32} sized 2x the build
+//     rows, or — when the reference would pick its ArrayMap — a direct-address array of
+//     {head,cnt}.  The join key (all key columns, <= 64 bits together) is stored *exactly* in the
+//     tag, so a probe needs one 16-byte load and no equal_rows_arr re-check.
+//   * duplicates: lock-free *sorted* chains through next[] built with atomicMin, so a probe walks
+//     matches in ascending build-row order == the reference's emission order
+//     (exec.rs:634-640 "Inner join output is expected to preserve both inputs order").
+//   * probe = count kernel (one table lookup per probe row, per-tile totals) -> single-block scan of
+//     tile totals -> emit kernel writing (build_idx, probe_idx) pairs in reference order ->
+//     one gather (`take`) kernel per output column.
+#include "batch.cuh"
+#include "scan.cuh"
+
+namespace dfgpu {
+
+constexpr uint32_t kEmpty32 = 0xFFFFFFFFu;
+constexpr uint64_t kEmpty64 = 0xFFFFFFFFFFFFFFFFull;
+constexpr uint32_t kVisitedBit = 0x80000000u;
+constexpr int kMaxKeys = 4;
+
+struct KeyCols {
+  int n;
+  const void* ptr[kMaxKeys];
+  const uint8_t* valid[kMaxKeys];
+  int64_t voff[kMaxKeys];
+  int width[kMaxKeys];   // bytes
+  int sgn[kMaxKeys];     // sign-extend (single-key mode: mirrors `as u64` of array_map.rs:123-135)
+  int shift[kMaxKeys];   // bit position when packing several columns
+};
+
+// returns false when any key column is NULL at `row`.
+// null_as_key: NullEqualsNull single-column mode — reported through *is_null instead.
+__device__ __forceinline__ bool load_tag(const KeyCols& kc, int64_t row, uint64_t* tag) {
+  uint64_t t = 0;
+  bool ok = true;
+#pragma unroll
+  for (int c = 0; c < kMaxKeys; ++c) {
+    if (c >= kc.n) break;
+    if (kc.valid[c] && !bit_get(kc.valid[c], kc.voff[c] + row)) ok = false;
+    uint64_t v;
+    switch (kc.width[c]) {
+      case 1: v = kc.sgn[c] ? (uint64_t)(int64_t)((const int8_t*)kc.ptr[c])[row] : (uint64_t)((const uint8_t*)kc.ptr[c])[row]; break;
+      case 2: v = kc.sgn[c] ? (uint64_t)(int64_t)((const int16_t*)kc.ptr[c])[row] : (uint64_t)((const uint16_t*)kc.ptr[c])[row]; break;
+      case 4: v = kc.sgn[c] ? (uint64_t)(int64_t)((const int32_t*)kc.ptr[c])[row] : (uint64_t)((const uint32_t*)kc.ptr[c])[row]; break;
+      default: v = ((const uint64_t*)kc.ptr[c])[row]; break;
+    }
+    if (kc.n > 1) { if (kc.width[c] < 8) v &= (1ull << (8 * kc.width[c])) - 1ull; v <<= kc.shift[c]; }
+    t |= v;
+  }
+  *tag = t;
+  return ok;
+}
+
+struct TableRef {
+  uint4* slots;       // hash mode: cap slots + 1 special slot (tag == all-ones) at index cap
+  uint64_t cap;
+  uint2* amap;        // array-map mode: {head,cnt} per key value in [amin, amin+arange]
+  uint64_t amin;
+  uint64_t asize;     // arange + 1
+  uint32_t* next;     // sorted chain links (kEmpty32 terminates)
+  uint2* null_slot;   // NullEqualsNull: the entry that collects NULL-key rows (else nullptr)
+  int force_collisions;  // mirror of feature force_hash_collisions: every key hashes to slot 0
+};
+
+__device__ __forceinline__ uint64_t slot_of(uint64_t tag, const TableRef& t) {
+  if (t.force_collisions) return 0;
+  return __umul64hi(hash_u64(tag, kSeedJoin), t.cap);  // fastrange on the upper hash bits
+}
+
+// find-or-claim the entry for `tag` (build side). Returns pointer to {head,cnt}.
+__device__ __forceinline__ uint32_t* claim_entry(const TableRef& t, uint64_t tag) {
+  if (t.amap) return (uint32_t*)&t.amap[tag - t.amin];
+  if (tag == kEmpty64) return ((uint32_t*)&t.slots[t.cap]) + 2;
+  uint64_t s = slot_of(tag, t);
+  while (true) {
+    unsigned long long* tp = (unsigned long long*)&t.slots[s];
+    unsigned long long cur = __ldcg(tp);
+    if (cur == kEmpty64) {
+      unsigned long long prev = atomicCAS(tp, (unsigned long long)kEmpty64, (unsigned long long)tag);
+      cur = (prev == kEmpty64) ? (unsigned long long)tag : prev;
+    }
+    if (cur == tag) return ((uint32_t*)tp) + 2;
+    if (++s == t.cap) s = 0;
+  }
+}
+
+// read-only lookup (probe side / final pass). Returns pointer to {head,cnt} or nullptr.
+__device__ __forceinline__ uint32_t* find_entry(const TableRef& t, uint64_t tag) {
+  if (t.amap) {
+    uint64_t i = tag - t.amin;  // wrapping: key_to_index of array_map.rs:159-166
+    if (i >= t.asize) return nullptr;
+    return (uint32_t*)&t.amap[i];
+  }
+  if (tag == kEmpty64) return ((uint32_t*)&t.slots[t.cap]) + 2;
+  uint64_t s = slot_of(tag, t);
+  while (true) {
+    const uint4 v = __ldcg(&t.slots[s]);
+    uint64_t cur = (uint64_t)v.x | ((uint64_t)v.y << 32);
+    if (cur == tag) return ((uint32_t*)&t.slots[s]) + 2;
+    if (cur == kEmpty64) return nullptr;
+    if (++s == t.cap) s = 0;
+  }
+}
+
+// lock-free sorted insert of `row` into the chain rooted at *head (all links only ever decrease)
+__device__ __forceinline__ void chain_insert(uint32_t* head, uint32_t* next, uint32_t row) {
+  uint32_t* p = head;
+  uint32_t x = row;
+  while (true) {
+    uint32_t old = atomicMin(p, x);
+    if (old == kEmpty32) return;
+    if (old > x) { p = &next[x]; x = old; }  // we displaced `old`: carry it behind x
+    else { p = &next[old]; }                 // keep walking
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// build
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) join_minmax_kernel(KeyCols kc, int64_t n, int sgn, unsigned long long* mm /* [min,max,valid] */) {
+  // min/max of a single integer key, as collect_left_input tracks for the perfect-hash decision (exec.rs:2585-2619)
+  long long lmin_s = LLONG_MAX, lmax_s = LLONG_MIN;
+  unsigned long long lmin_u = ~0ull, lmax_u = 0, cnt = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t t;
+    if (!load_tag(kc, i, &t)) continue;
+    cnt++;
+    if (sgn) { long long v = (long long)t; lmin_s = min(lmin_s, v); lmax_s = max(lmax_s, v); }
+    else { lmin_u = min(lmin_u, (unsigned long long)t); lmax_u = max(lmax_u, (unsigned long long)t); }
+  }
+  if (cnt) {
+    if (sgn) { atomicMin((long long*)&mm[0], lmin_s); atomicMax((long long*)&mm[1], lmax_s); }
+    else { atomicMin(&mm[0], lmin_u); atomicMax(&mm[1], lmax_u); }
+    atomicAdd(&mm[2], cnt);
+  }
+}
+
+__global__ void __launch_bounds__(256) join_build_kernel(KeyCols kc, int64_t n, TableRef t, unsigned long long* counters /* [distinct, valid_rows, null_rows] */) {
+  __shared__ unsigned int s_distinct, s_valid, s_null;
+  if (threadIdx.x == 0) { s_distinct = 0; s_valid = 0; s_null = 0; }
+  __syncthreads();
+  // rows are visited in DESCENDING order: a later (smaller) row then usually becomes the new chain
+  // head with two atomics, mirroring the reference's reverse iteration (exec.rs:2684-2702, array_map.rs:213)
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t row = n - 1 - i;
+    uint64_t tag;
+    bool ok = load_tag(kc, row, &tag);
+    uint32_t* e = nullptr;
+    if (ok) e = claim_entry(t, tag);
+    else if (t.null_slot) e = (uint32_t*)t.null_slot;  // NullEqualsNull
+    if (!ok) atomicAdd(&s_null, 1u);
+    if (!e) continue;  // NULL key under NullEqualsNothing: not inserted (utils.rs:2146-2155)
+    uint32_t old = atomicAdd(e + 1, 1u);
+    if (old == kEmpty32) atomicAdd(&s_distinct, 1u);
+    atomicAdd(&s_valid, 1u);
+    chain_insert(e, t.next, (uint32_t)row);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_distinct) atomicAdd(&counters[0], (unsigned long long)s_distinct);
+    if (s_valid) atomicAdd(&counters[1], (unsigned long long)s_valid);
+    if (s_null) atomicAdd(&counters[2], (unsigned long long)s_null);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// probe
+// ------------------------------------------------------------------------------------------
+constexpr int kProbeThreads = 256;
+constexpr int kProbeItems = 4;
+constexpr int kProbeTile = kProbeThreads * kProbeItems;
+
+enum EmitMode : int {
+  EMIT_PAIRS = 0,        // Inner / Left: one output row per match
+  EMIT_PAIRS_OUTER = 1,  // Right / Full: matches, or (NULL, probe) when none
+  EMIT_SEMI = 2,         // RightSemi: probe rows with >= 1 match
+  EMIT_ANTI = 3,         // RightAnti: probe rows with no match
+  EMIT_ALL = 4,          // RightMark: every probe row (+ mark column)
+  EMIT_NONE = 5          // LeftSemi / LeftAnti / LeftMark: only the visited flags matter
+};
+
+__device__ __forceinline__ uint32_t out_count_for(int mode, uint32_t cnt) {
+  switch (mode) {
+    case EMIT_PAIRS: return cnt;
+    case EMIT_PAIRS_OUTER: return cnt ? cnt : 1u;
+    case EMIT_SEMI: return cnt ? 1u : 0u;
+    case EMIT_ANTI: return cnt ? 0u : 1u;
+    case EMIT_ALL: return 1u;
+    default: return 0u;
+  }
+}
+
+// pass 1: one lookup per probe row.  Writes head[i] (first matching build row or kEmpty32),
+// cnt[i] (number of matching build rows; omitted when the build side is unique) and the per-tile
+// output-row total.
+template <bool UNIQUE>
+__global__ void __launch_bounds__(kProbeThreads) join_probe_count_kernel(KeyCols kc, int64_t n, TableRef t, int mode, int mark_visited,
+                                                                      uint32_t* __restrict__ head_out, uint32_t* __restrict__ cnt_out,
+                                                                      uint64_t* __restrict__ tile_sums, unsigned long long* __restrict__ hit_rows) {
+  const int64_t tile_base = (int64_t)blockIdx.x * kProbeTile;
+  uint32_t local_out = 0, local_hits = 0;
+#pragma unroll
+  for (int k = 0; k < kProbeItems; ++k) {
+    int64_t i = tile_base + k * kProbeThreads + threadIdx.x;
+    if (i >= n) break;
+    uint64_t tag;
+    bool ok = load_tag(kc, i, &tag);
+    uint32_t* e = nullptr;
+    if (ok) e = find_entry(t, tag);
+    else if (t.null_slot) e = (uint32_t*)t.null_slot;
+    uint32_t head = kEmpty32, cnt = 0;
+    if (e) {
+      uint2 hc = __ldcg((const uint2*)e);
+      if (hc.x != kEmpty32) {
+        head = hc.x;
+        cnt = (hc.y & ~kVisitedBit) + 1u;
+        if (mark_visited && !(hc.y & kVisitedBit)) atomicOr(e + 1, kVisitedBit);
+        local_hits++;
+      }
+    }
+    head_out[i] = head;
+    if (!UNIQUE) cnt_out[i] = cnt;
+    local_out += out_count_for(mode, cnt);
+  }
+  uint64_t tot = block_reduce_sum<kProbeThreads, uint64_t>((uint64_t)local_out);
+  uint64_t hits = block_reduce_sum<kProbeThreads, uint64_t>((uint64_t)local_hits);
+  if (threadIdx.x == 0) {
+    tile_sums[blockIdx.x] = tot;
+    if (hits) atomicAdd(hit_rows, (unsigned long long)hits);
+  }
+}
+
+// pass 2: emit (build_idx, probe_idx) pairs in reference order: probe-row order, and within one
+// probe row ascending build row (chain order).
+template <bool UNIQUE>
+__global__ void __launch_bounds__(kProbeThreads) join_emit_kernel(int64_t n, const uint32_t* __restrict__ head_in, const uint32_t* __restrict__ cnt_in,
+                                                               const uint32_t* __restrict__ next, const uint64_t* __restrict__ tile_offsets, int mode,
+                                                               uint32_t* __restrict__ build_idx, uint32_t* __restrict__ probe_idx) {
+  const int64_t tile_base = (int64_t)blockIdx.x * kProbeTile;
+  uint64_t base = tile_offsets[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kProbeItems; ++k) {
+    int64_t i = tile_base + k * kProbeThreads + threadIdx.x;
+    uint32_t head = kEmpty32, cnt = 0;
+    if (i < n) {
+      head = head_in[i];
+      cnt = UNIQUE ? (head != kEmpty32 ? 1u : 0u) : cnt_in[i];
+    }
+    uint32_t oc = i < n ? out_count_for(mode, cnt) : 0u;
+    uint32_t tot;
+    uint32_t ex = block_exclusive_scan<kProbeThreads, uint32_t>(oc, &tot);
+    uint64_t pos = base + ex;
+    if (oc) {
+      if (mode == EMIT_PAIRS || (mode == EMIT_PAIRS_OUTER && cnt)) {
+        uint32_t r = head;
+        for (uint32_t m = 0; m < cnt; ++m) {
+          build_idx[pos + m] = r;
+          probe_idx[pos + m] = (uint32_t)i;
+          if (!UNIQUE && m + 1 < cnt) r = next[r];
+        }
+      } else {
+        // outer padding / semi / anti / mark: one row; build index = first match or NULL
+        if (build_idx) build_idx[pos] = head;
+        probe_idx[pos] = (uint32_t)i;
+      }
+    }
+    base += tot;
+  }
+}
+
+// final pass over the build rows: which rows were matched by any probe row (the reference's
+// visited_indices_bitmap, exec.rs:2712-2723) — recovered from the per-key visited flag.
+__global__ void __launch_bounds__(256) join_build_flags_kernel(KeyCols kc, int64_t n, TableRef t, uint32_t* __restrict__ visited_words) {
+  int64_t nw = (n + 31) / 32;
+  int lane = threadIdx.x & 31;
+  for (int64_t wi = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; wi < nw; wi += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    int64_t row = wi * 32 + lane;
+    bool vis = false;
+    if (row < n) {
+      uint64_t tag;
+      bool ok = load_tag(kc, row, &tag);
+      uint32_t* e = nullptr;
+      if (ok) e = find_entry(t, tag);
+      else if (t.null_slot) e = (uint32_t*)t.null_slot;
+      if (e) { uint2 hc = __ldcg((const uint2*)e); vis = (hc.x != kEmpty32) && (hc.y & kVisitedBit); }
+    }
+    uint32_t w = __ballot_sync(0xffffffffu, vis);
+    if (lane == 0) visited_words[wi] = w;
+  }
+}
+
+// mark column: is_not_null(indices) (utils.rs:1358-1360) as a bit-packed Boolean column
+__global__ void mark_from_idx_kernel(const uint32_t* __restrict__ idx, int64_t n, uint32_t* __restrict__ out_words) {
+  int64_t nw = (n + 31) / 32;
+  int lane = threadIdx.x & 31;
+  for (int64_t wi = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; wi < nw; wi += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    int64_t i = wi * 32 + lane;
+    bool v = i < n && idx[i] != kEmpty32;
+    uint32_t w = __ballot_sync(0xffffffffu, v);
+    if (lane == 0) out_words[wi] = w;
+  }
+}
+
+}  // namespace dfgpu
+
+// ==========================================================================================
+// operator state
+// ==========================================================================================
+using namespace dfgpu;
+
+struct dfgpu_hashjoin {
+  dfgpu_ctx* ctx = nullptr;
+  dfgpu_hashjoin_options opt;
+  std::vector<int> build_types, probe_types, on_build, on_probe, out_side, out_index;
+  // build side
+  std::vector<std::vector<DCol>> build_parts;  // per pushed batch
+  std::vector<DCol> build_cols;                // concatenated
+  int64_t nB = 0;
+  bool built = false, probe_done = false;
+  DevBuf slots, amap, next, null_slot, counters;
+  TableRef table{};
+  KeyCols build_keys{};
+  bool use_array_map = false, unique = false;
+  int64_t distinct = 0, valid_rows = 0, null_rows = 0;
+  bool need_visited = false;
+  int emit_mode = EMIT_PAIRS;
+  // output
+  std::deque<BatchPtr> outq;
+  // metrics (BuildProbeJoinMetrics, joins/utils.rs:1756-1778)
+  int64_t m_build_rows = 0, m_build_batches = 0, m_input_rows = 0, m_input_batches = 0, m_output_rows = 0, m_output_batches = 0,
+          m_array_map = 0, m_probe_hits = 0;
+  bool probe_side_non_empty = false;
+};
+
+namespace dfgpu {
+
+static void make_keycols(const std::vector<DCol>& cols, const std::vector<int>& on, KeyCols* kc) {
+  memset(kc, 0, sizeof(*kc));
+  kc->n = (int)on.size();
+  int shift = 0;
+  for (int c = 0; c < kc->n; ++c) {
+    const DCol& col = cols[on[c]];
+    kc->ptr[c] = col.values;
+    kc->valid[c] = col.validity;
+    kc->voff[c] = col.offset;
+    kc->width[c] = type_width(col.type);
+    kc->sgn[c] = type_is_signed_int(col.type) ? 1 : 0;
+    kc->shift[c] = shift;
+    shift += 8 * kc->width[c];
+  }
+}
+
+static void check_join_keys(dfgpu_hashjoin* j) {
+  int bits = 0;
+  DF_CHECK(!j->on_build.empty() && j->on_build.size() <= kMaxKeys, DFGPU_ERR_UNSUPPORTED, "hash join: 1..4 key columns supported");
+  for (size_t c = 0; c < j->on_build.size(); ++c) {
+    int bt = j->build_types[j->on_build[c]], pt = j->probe_types[j->on_probe[c]];
+    DF_CHECK(type_width(bt) == type_width(pt) && type_is_float(bt) == type_is_float(pt) &&
+                 type_is_signed_int(bt) == type_is_signed_int(pt),
+             DFGPU_ERR_INVALID, "hash join: key types differ between build and probe side");
+    int w = type_width(bt);
+    DF_CHECK(w >= 1 && w <= 8, DFGPU_ERR_UNSUPPORTED, "hash join: key type must be a fixed-width type of <= 64 bits");
+    bits += 8 * w;
+  }
+  DF_CHECK(bits <= 64, DFGPU_ERR_UNSUPPORTED, "hash join: key columns wider than 64 bits together are not supported yet");
+  if (j->opt.null_equality == DFGPU_NULL_EQUALS_NULL)
+    DF_CHECK(j->on_build.size() == 1, DFGPU_ERR_UNSUPPORTED, "hash join: NullEqualsNull supported for single-column keys only");
+}
+
+static void push_build(dfgpu_hashjoin* j, std::vector<DCol>&& cols) {
+  DF_CHECK(!j->built, DFGPU_ERR_STATE, "push_build after finish_build");
+  DF_CHECK(cols.size() == j->build_types.size(), DFGPU_ERR_INVALID, "build batch column count mismatch");
+  int64_t rows = cols.empty() ? 0 : cols[0].length;
+  for (size_t c = 0; c < cols.size(); ++c) {
+    DF_CHECK(cols[c].type == j->build_types[c], DFGPU_ERR_INVALID, "build batch column type mismatch");
+    DF_CHECK(cols[c].length == rows, DFGPU_ERR_INVALID, "build batch ragged columns");
+  }
+  j->nB += rows;
+  j->m_build_rows += rows;
+  j->m_build_batches++;
+  if (rows > 0) j->build_parts.push_back(std::move(cols));
+}
+
+static void finish_build(dfgpu_hashjoin* j) {
+  DF_CHECK(!j->built, DFGPU_ERR_STATE, "finish_build called twice");
+  dfgpu_ctx* ctx = j->ctx;
+  set_device(ctx);
+  DF_CHECK(j->nB < (int64_t)kEmpty32, DFGPU_ERR_UNSUPPORTED, "hash join: build side must have < 2^32-1 rows");
+  // concat_batches (exec.rs:2705)
+  j->build_cols.clear();
+  for (size_t c = 0; c < j->build_types.size(); ++c) {
+    std::vector<DCol> parts;
+    for (auto& b : j->build_parts) parts.push_back(b[c]);
+    if (parts.empty()) j->build_cols.push_back(alloc_col(ctx, j->build_types[c], 0, false));
+    else j->build_cols.push_back(concat_columns(ctx, parts, j->build_types[c]));
+  }
+  j->build_parts.clear();
+  make_keycols(j->build_cols, j->on_build, &j->build_keys);
+  const int64_t n = j->nB;
+  j->counters.alloc(ctx, 8 * 8);
+  j->counters.zero();
+  j->next.alloc(ctx, (size_t)std::max<int64_t>(n, 1) * 4);
+  j->next.fill(0xFF);
+  memset(&j->table, 0, sizeof(j->table));
+  j->table.next = j->next.as<uint32_t>();
+  j->table.force_collisions = j->opt.force_hash_collisions;
+  if (j->opt.null_equality == DFGPU_NULL_EQUALS_NULL) {
+    j->null_slot.alloc(ctx, 8);
+    j->null_slot.fill(0xFF);
+    j->table.null_slot = j->null_slot.as<uint2>();
+  }
+
+  // ---- perfect-hash (ArrayMap) decision: try_create_array_map, exec.rs:111-191 ----
+  j->use_array_map = false;
+  const int kt = j->build_types[j->on_build[0]];
+  bool am_type_ok = j->on_build.size() == 1 && type_is_int(kt) && kt != DFGPU_DATE32 && kt != DFGPU_DATE64 && kt != DFGPU_TIMESTAMP;
+  // (ArrayMap::is_supported_type, array_map.rs:106-119: Int8..Int64, UInt8..UInt64 only)
+  if (am_type_ok && n > 0) {
+    bool null_block = false;
+    if (j->opt.null_equality == DFGPU_NULL_EQUALS_NULL) {
+      // exec.rs:124-131: any NULL build key disables the ArrayMap under NullEqualsNull
+      const DCol& kcol = j->build_cols[j->on_build[0]];
+      if (kcol.validity && count_set_bits(ctx, kcol.validity, kcol.offset, kcol.length) != kcol.length) null_block = true;
+    }
+    if (!null_block) {
+      DevBuf mm(ctx, 24);
+      unsigned long long init[3];
+      int sgn = type_is_signed_int(kt) ? 1 : 0;
+      if (sgn) { init[0] = (unsigned long long)LLONG_MAX; init[1] = (unsigned long long)LLONG_MIN; } else { init[0] = ~0ull; init[1] = 0; }
+      init[2] = 0;
+      DF_CUDA(cudaMemcpyAsync(mm.ptr, init, 24, cudaMemcpyHostToDevice, ctx->stream));
+      join_minmax_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(j->build_keys, n, sgn, mm.as<unsigned long long>());
+      DF_LAUNCH_CHECK(ctx);
+      unsigned long long h[3];
+      DF_CUDA(cudaMemcpyAsync(h, mm.ptr, 24, cudaMemcpyDeviceToHost, ctx->stream));
+      DF_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (h[2] > 0) {  // bounds exist only if some key is non-null (exec.rs:140-148)
+        uint64_t minv = h[0], maxv = h[1];
+        uint64_t range = maxv - minv;  // wrapping_sub, array_map.rs:154
+        bool ok = (uint64_t)n < 0xFFFFFFFFull && range != ~0ull;
+        if (ok) {
+          double dense_ratio = (double)n / ((double)range + 1.0);
+          if (range >= (uint64_t)j->opt.perfect_hash_join_small_build_threshold && dense_ratio <= j->opt.perfect_hash_join_min_key_density) ok = false;
+        }
+        // device memory guard (reservation.try_grow, exec.rs:181-182): at most 16 GiB for the direct array
+        if (ok && (range + 1) > (1ull << 31)) ok = false;
+        if (ok) {
+          j->use_array_map = true;
+          j->amap.alloc(ctx, (size_t)(range + 1) * 8);
+          j->amap.fill(0xFF);
+          j->table.amap = j->amap.as<uint2>();
+          j->table.amin = minv;
+          j->table.asize = range + 1;
+          j->m_array_map = 1;
+        }
+      }
+    }
+  }
+  if (!j->use_array_map) {
+    uint64_t cap = std::max<uint64_t>(1024, (uint64_t)n * 2);
+    j->slots.alloc(ctx, (size_t)(cap + 1) * 16);
+    j->slots.fill(0xFF);
+    j->table.slots = j->slots.as<uint4>();
+    j->table.cap = cap;
+  }
+  if (n > 0) {
+    join_build_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(j->build_keys, n, j->table, j->counters.as<unsigned long long>());
+    DF_LAUNCH_CHECK(ctx);
+  }
+  unsigned long long hc[3];
+  DF_CUDA(cudaMemcpyAsync(hc, j->counters.ptr, 24, cudaMemcpyDeviceToHost, ctx->stream));
+  DF_CUDA(cudaStreamSynchronize(ctx->stream));
+  j->distinct = (int64_t)hc[0];
+  j->valid_rows = (int64_t)hc[1];
+  j->null_rows = (int64_t)hc[2];
+  j->unique = (j->distinct == j->valid_rows);  // map.len() == next.len() fast path, join_hash_map.rs:410-429
+  j->built = true;
+}
+
+static void emit_batch(dfgpu_hashjoin* j, BatchPtr b) {
+  j->m_output_rows += b->rows;
+  j->m_output_batches++;
+  j->outq.push_back(std::move(b));
+}
+
+// build_batch_from_indices (utils.rs:1332-1387): one gather per output column
+static BatchPtr materialize(dfgpu_hashjoin* j, const std::vector<DCol>* probe_cols, const uint32_t* bidx, const uint32_t* pidx, int64_t n,
+                            bool bidx_nullable, bool pidx_all_null, const uint32_t* mark_src) {
+  dfgpu_ctx* ctx = j->ctx;
+  BatchPtr out(new dfgpu_batch());
+  out->ctx = ctx; out->rows = n; out->host = false;
+  for (size_t c = 0; c < j->out_side.size(); ++c) {
+    int side = j->out_side[c], ix = j->out_index[c];
+    if (side == 2) {
+      DCol m = alloc_col(ctx, DFGPU_BOOL, n, false);
+      if (n) {
+        mark_from_idx_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(mark_src, n, m.own_values->as<uint32_t>());
+        DF_LAUNCH_CHECK(ctx);
+      }
+      out->cols.push_back(std::move(m));
+    } else if (side == 0) {
+      if (!bidx) out->cols.push_back(null_column(ctx, j->build_types[ix], n));
+      else out->cols.push_back(take_column(ctx, j->build_cols[ix], bidx, n, bidx_nullable));
+    } else {
+      if (pidx_all_null || !probe_cols) out->cols.push_back(null_column(ctx, j->probe_types[ix], n));
+      else out->cols.push_back(take_column(ctx, (*probe_cols)[ix], pidx, n, false));
+    }
+  }
+  return out;
+}
+
+static void push_probe(dfgpu_hashjoin* j, std::vector<DCol>&& cols) {
+  DF_CHECK(j->built, DFGPU_ERR_STATE, "push_probe before finish_build");
+  DF_CHECK(!j->probe_done, DFGPU_ERR_STATE, "push_probe after finish_probe");
+  DF_CHECK(cols.size() == j->probe_types.size(), DFGPU_ERR_INVALID, "probe batch column count mismatch");
+  dfgpu_ctx* ctx = j->ctx;
+  set_device(ctx);
+  int64_t n = cols.empty() ? 0 : cols[0].length;
+  for (size_t c = 0; c < cols.size(); ++c) {
+    DF_CHECK(cols[c].type == j->probe_types[c], DFGPU_ERR_INVALID, "probe batch column type mismatch");
+    DF_CHECK(cols[c].length == n, DFGPU_ERR_INVALID, "probe batch ragged columns");
+  }
+  DF_CHECK(n < (int64_t)kEmpty32, DFGPU_ERR_UNSUPPORTED, "hash join: a probe batch must have < 2^32-1 rows");
+  j->m_input_rows += n;
+  j->m_input_batches++;
+  if (n == 0) return;
+  j->probe_side_non_empty = true;
+  const int mode = j->emit_mode;
+  // empty / unmatchable build side: build_batch_empty_build_side (utils.rs:1393-1430)
+  KeyCols pk;
+  make_keycols(cols, j->on_probe, &pk);
+  const int64_t ntiles = (n + kProbeTile - 1) / kProbeTile;
+  DevBuf head(ctx, (size_t)n * 4), cnt, tiles(ctx, (size_t)(ntiles + 1) * 8), hits(ctx, 8);
+  hits.zero();
+  if (!j->unique) cnt.alloc(ctx, (size_t)n * 4);
+  if (j->unique)
+    join_probe_count_kernel<true><<<(int)ntiles, kProbeThreads, 0, ctx->stream>>>(pk, n, j->table, mode, j->need_visited ? 1 : 0, head.as<uint32_t>(), nullptr,
+                                                                                  tiles.as<uint64_t>(), hits.as<unsigned long long>());
+  else
+    join_probe_count_kernel<false><<<(int)ntiles, kProbeThreads, 0, ctx->stream>>>(pk, n, j->table, mode, j->need_visited ? 1 : 0, head.as<uint32_t>(), cnt.as<uint32_t>(),
+                                                                                   tiles.as<uint64_t>(), hits.as<unsigned long long>());
+  DF_LAUNCH_CHECK(ctx);
+  if (mode == EMIT_NONE) {
+    j->m_probe_hits += (int64_t)read_scalar<unsigned long long>(ctx, hits.as<unsigned long long>());
+    return;
+  }
+  scan_tiles_kernel<1024><<<1, 1024, 0, ctx->stream>>>(tiles.as<uint64_t>(), ntiles, tiles.as<uint64_t>() + ntiles);
+  DF_LAUNCH_CHECK(ctx);
+  uint64_t total = read_scalar<uint64_t>(ctx, tiles.as<uint64_t>() + ntiles);
+  DF_CHECK(total < (uint64_t)kEmpty32 * 64ull, DFGPU_ERR_OOM, "hash join: output of one probe batch too large");
+  const bool need_bidx = (mode == EMIT_PAIRS || mode == EMIT_PAIRS_OUTER || mode == EMIT_ALL);
+  DevBuf bidx, pidx(ctx, (size_t)std::max<uint64_t>(total, 1) * 4);
+  if (need_bidx) bidx.alloc(ctx, (size_t)std::max<uint64_t>(total, 1) * 4);
+  if (j->unique)
+    join_emit_kernel<true><<<(int)ntiles, kProbeThreads, 0, ctx->stream>>>(n, head.as<uint32_t>(), nullptr, j->table.next, tiles.as<uint64_t>(), mode,
+                                                                          need_bidx ? bidx.as<uint32_t>() : nullptr, pidx.as<uint32_t>());
+  else
+    join_emit_kernel<false><<<(int)ntiles, kProbeThreads, 0, ctx->stream>>>(n, head.as<uint32_t>(), cnt.as<uint32_t>(), j->table.next, tiles.as<uint64_t>(), mode,
+                                                                           need_bidx ? bidx.as<uint32_t>() : nullptr, pidx.as<uint32_t>());
+  DF_LAUNCH_CHECK(ctx);
+  BatchPtr out;
+  if (mode == EMIT_PAIRS)
+    out = materialize(j, &cols, bidx.as<uint32_t>(), pidx.as<uint32_t>(), (int64_t)total, false, false, nullptr);
+  else if (mode == EMIT_PAIRS_OUTER)
+    out = materialize(j, &cols, bidx.as<uint32_t>(), pidx.as<uint32_t>(), (int64_t)total, true, false, nullptr);
+  else if (mode == EMIT_ALL)  // RightMark: build_batch and probe_batch swap roles (stream.rs:953-958); mark = is_not_null(match)
+    out = materialize(j, &cols, nullptr, pidx.as<uint32_t>(), (int64_t)total, true, false, bidx.as<uint32_t>());
+  else  // RightSemi / RightAnti: probe columns only
+    out = materialize(j, &cols, nullptr, pidx.as<uint32_t>(), (int64_t)total, true, false, nullptr);
+  j->m_probe_hits += (int64_t)read_scalar<unsigned long long>(ctx, hits.as<unsigned long long>());
+  if (out->rows > 0) emit_batch(j, std::move(out));
+}
+
+static void finish_probe(dfgpu_hashjoin* j) {
+  DF_CHECK(j->built, DFGPU_ERR_STATE, "finish_probe before finish_build");
+  DF_CHECK(!j->probe_done, DFGPU_ERR_STATE, "finish_probe called twice");
+  j->probe_done = true;
+  dfgpu_ctx* ctx = j->ctx;
+  set_device(ctx);
+  const int jt = j->opt.join_type;
+  // need_produce_result_in_final (utils.rs:1181-1190)
+  if (!(jt == DFGPU_JOIN_LEFT || jt == DFGPU_JOIN_FULL || jt == DFGPU_JOIN_LEFT_SEMI || jt == DFGPU_JOIN_LEFT_ANTI || jt == DFGPU_JOIN_LEFT_MARK)) return;
+  const int64_t n = j->nB;
+  if (n == 0) return;
+  // get_final_indices_from_bit_map (utils.rs:1210-1245)
+  int64_t nw = (n + 31) / 32;
+  DevBuf vis(ctx, (size_t)nw * 4);
+  join_build_flags_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(j->build_keys, n, j->table, vis.as<uint32_t>());
+  DF_LAUNCH_CHECK(ctx);
+  if (jt == DFGPU_JOIN_LEFT_MARK) {
+    // all build rows + mark column (visited)
+    DevBuf all(ctx, (size_t)n * 4);
+    fill_iota(ctx, all.as<uint32_t>(), n);
+    BatchPtr out(new dfgpu_batch());
+    out->ctx = ctx; out->rows = n; out->host = false;
+    for (size_t c = 0; c < j->out_side.size(); ++c) {
+      int side = j->out_side[c], ix = j->out_index[c];
+      if (side == 2) {
+        DCol m = alloc_col(ctx, DFGPU_BOOL, n, false);
+        DF_CUDA(cudaMemcpyAsync(m.own_values->ptr, vis.ptr, (size_t)nw * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        out->cols.push_back(std::move(m));
+      } else if (side == 0) out->cols.push_back(take_column(ctx, j->build_cols[ix], all.as<uint32_t>(), n, false));
+      else out->cols.push_back(null_column(ctx, j->probe_types[ix], n));
+    }
+    emit_batch(j, std::move(out));
+    return;
+  }
+  const int want_set = (jt == DFGPU_JOIN_LEFT_SEMI) ? 1 : 0;
+  DevBuf idx;
+  int64_t total = compact_flag_indices(ctx, vis.as<uint32_t>(), n, want_set, &idx);
+  if (total == 0) return;
+  BatchPtr out = materialize(j, nullptr, idx.as<uint32_t>(), nullptr, (int64_t)total, false, true, nullptr);
+  emit_batch(j, std::move(out));
+}
+
+}  // namespace dfgpu
+
+// ==========================================================================================
+// extern "C"
+// ==========================================================================================
+
+extern "C" {
+
+void dfgpu_hashjoin_default_options(dfgpu_hashjoin_options* o) {
+  memset(o, 0, sizeof(*o));
+  o->join_type = DFGPU_JOIN_INNER;
+  o->null_equality = DFGPU_NULL_EQUALS_NOTHING;
+  o->batch_size = 8192;
+  o->perfect_hash_join_small_build_threshold = 1024;  // config.rs:913
+  o->perfect_hash_join_min_key_density = 0.15;        // config.rs:923
+  o->force_hash_collisions = 0;
+  o->ordered_output = 1;
+}
+
+int dfgpu_hashjoin_create(dfgpu_ctx* ctx, const int32_t* build_types, int32_t n_build_cols, const int32_t* probe_types, int32_t n_probe_cols,
+                          const int32_t* on_build, const int32_t* on_probe, int32_t n_on, const int32_t* out_side, const int32_t* out_index,
+                          int32_t n_out, const dfgpu_hashjoin_options* opts, dfgpu_hashjoin** out) {
+  DF_API_BEGIN(ctx)
+  DF_CHECK(ctx && out && opts, DFGPU_ERR_INVALID, "null argument");
+  std::unique_ptr<dfgpu_hashjoin> j(new dfgpu_hashjoin());
+  j->ctx = ctx;
+  j->opt = *opts;
+  j->build_types.assign(build_types, build_types + n_build_cols);
+  j->probe_types.assign(probe_types, probe_types + n_probe_cols);
+  j->on_build.assign(on_build, on_build + n_on);
+  j->on_probe.assign(on_probe, on_probe + n_on);
+  j->out_side.assign(out_side, out_side + n_out);
+  j->out_index.assign(out_index, out_index + n_out);
+  for (int c = 0; c < n_on; ++c) {
+    DF_CHECK(on_build[c] >= 0 && on_build[c] < n_build_cols && on_probe[c] >= 0 && on_probe[c] < n_probe_cols, DFGPU_ERR_INVALID, "join key column index out of range");
+  }
+  for (int c = 0; c < n_out; ++c) {
+    int lim = out_side[c] == 0 ? n_build_cols : out_side[c] == 1 ? n_probe_cols : 1;
+    DF_CHECK(out_side[c] >= 0 && out_side[c] <= 2 && out_index[c] >= 0 && out_index[c] < lim, DFGPU_ERR_INVALID, "output column mapping out of range");
+  }
+  check_join_keys(j.get());
+  switch (opts->join_type) {
+    case DFGPU_JOIN_INNER: j->emit_mode = EMIT_PAIRS; break;
+    case DFGPU_JOIN_LEFT: j->emit_mode = EMIT_PAIRS; j->need_visited = true; break;
+    case DFGPU_JOIN_RIGHT: j->emit_mode = EMIT_PAIRS_OUTER; break;
+    case DFGPU_JOIN_FULL: j->emit_mode = EMIT_PAIRS_OUTER; j->need_visited = true; break;
+    case DFGPU_JOIN_RIGHT_SEMI: j->emit_mode = EMIT_SEMI; break;
+    case DFGPU_JOIN_RIGHT_ANTI: j->emit_mode = EMIT_ANTI; break;
+    case DFGPU_JOIN_RIGHT_MARK: j->emit_mode = EMIT_ALL; break;
+    case DFGPU_JOIN_LEFT_SEMI: case DFGPU_JOIN_LEFT_ANTI: case DFGPU_JOIN_LEFT_MARK: j->emit_mode = EMIT_NONE; j->need_visited = true; break;
+    default: throw Error(DFGPU_ERR_INVALID, "unknown join type");
+  }
+  *out = j.release();
+  DF_API_END
+}
+
+static std::vector<DCol> host_cols_to_device(dfgpu_ctx* ctx, const dfgpu_column* cols, int32_t n) {
+  set_device(ctx);
+  std::vector<DCol> v;
+  for (int i = 0; i < n; ++i) v.push_back(upload_column(ctx, cols[i]));
+  return v;
+}
+static std::vector<DCol> device_cols_copy(dfgpu_ctx* ctx, const dfgpu_column* cols, int32_t n) {
+  set_device(ctx);
+  std::vector<DCol> v;
+  for (int i = 0; i < n; ++i) v.push_back(copy_column_device(ctx, device_view(cols[i])));
+  return v;
+}
+static std::vector<DCol> device_cols_view(const dfgpu_column* cols, int32_t n) {
+  std::vector<DCol> v;
+  for (int i = 0; i < n; ++i) v.push_back(device_view(cols[i]));
+  return v;
+}
+
+int dfgpu_hashjoin_push_build_host(dfgpu_hashjoin* j, const dfgpu_column* cols, int32_t n_cols) {
+  DF_API_BEGIN(j ? j->ctx : nullptr)
+  push_build(j, host_cols_to_device(j->ctx, cols, n_cols));
+  DF_API_END
+}
+int dfgpu_hashjoin_push_build_device(dfgpu_hashjoin* j, const dfgpu_column* cols, int32_t n_cols) {
+  DF_API_BEGIN(j ? j->ctx : nullptr)
+  // the caller owns the input only until this call returns: keep a private copy (160 MB for C2's build side)
+  push_build(j, device_cols_copy(j->ctx, cols, n_cols));
+  DF_API_END
+}
+int dfgpu_hashjoin_finish_build(dfgpu_hashjoin* j) {
+  DF_API_BEGIN(j ? j->ctx : nullptr)
+  finish_build(j);
+  DF_API_END
+}
+int dfgpu_hashjoin_push_probe_host(dfgpu_hashjoin* j, const dfgpu_column* cols, int32_t n_cols) {
+  DF_API_BEGIN(j ? j->ctx : nullptr)
+  push_probe(j, host_cols_to_device(j->ctx, cols, n_cols));
+  DF_API_END
+}
+int dfgpu_hashjoin_push_probe_device(dfgpu_hashjoin* j, const dfgpu_column* cols, int32_t n_cols) {
+  DF_API_BEGIN(j ? j->ctx : nullptr)
+  push_probe(j, device_cols_view(cols, n_cols));  // consumed before returning (outputs are gathered copies)
+  DF_API_END
+}
+int dfgpu_hashjoin_finish_probe(dfgpu_hashjoin* j) {
+  DF_API_BEGIN(j ? j->ctx : nullptr)
+  finish_probe(j);
+  DF_API_END
+}
+int dfgpu_hashjoin_next(dfgpu_hashjoin* j, int host, dfgpu_batch** out) {
+  dfgpu_ctx* _ctx = j ? j->ctx : nullptr;
+  try {
+    DF_CHECK(j && out, DFGPU_ERR_INVALID, "null argument");
+    if (j->outq.empty()) { *out = nullptr; return DFGPU_END; }
+    BatchPtr b = std::move(j->outq.front());
+    j->outq.pop_front();
+    if (host) { set_device(j->ctx); b = to_host_batch(j->ctx, *b); }
+    *out = b.release();
+    return DFGPU_OK;
+  } catch (const dfgpu::Error& e) { if (_ctx) _ctx->last_error = e.what(); return e.code; }
+  catch (const std::exception& e) { if (_ctx) _ctx->last_error = e.what(); return DFGPU_ERR_INVALID; }
+}
+int64_t dfgpu_hashjoin_metric(dfgpu_hashjoin* j, const char* name) {
+  if (!j || !name) return -1;
+  std::string s(name);
+  if (s == "build_input_rows") return j->m_build_rows;
+  if (s == "build_input_batches") return j->m_build_batches;
+  if (s == "input_rows") return j->m_input_rows;
+  if (s == "input_batches") return j->m_input_batches;
+  if (s == "output_rows") return j->m_output_rows;
+  if (s == "output_batches") return j->m_output_batches;
+  if (s == "array_map_created_count") return j->m_array_map;
+  if (s == "probe_hits") return j->m_probe_hits;
+  if (s == "build_distinct_keys") return j->distinct;
+  if (s == "build_unique") return j->unique ? 1 : 0;
+  if (s == "build_null_key_rows") return j->null_rows;
+  return -1;
+}
+void dfgpu_hashjoin_destroy(dfgpu_hashjoin* j) {
+  if (!j) return;
+  cudaSetDevice(j->ctx->device);
+  delete j;
+}
+
+}  // extern "C"

@@ -1,0 +1,333 @@
+/*
+ * dfgpu.h — C ABI of libdfgpu.so: the B200 (sm_100a) kernel layer behind DataFusion's
+ * FilterExec / HashJoinExec / AggregateExec hot paths.
+ *
+ * This is boundary "b3" of SURVEY.md §8(b): the thin `extern "C"` library that a Rust
+ * `GpuFilterExec` / `GpuHashJoinExec` / `GpuAggregateExec` (each implementing
+ * `trait ExecutionPlan`, reference datafusion/physical-plan/src/execution_plan.rs:102, `execute` :696)
+ * binds with `extern "C" { ... }` + `arrow::ffi::{to_ffi, from_ffi}`.  Record batches cross as Arrow
+ * C Data Interface structs — the same structs DataFusion's own FFI layer wraps
+ * (reference datafusion/ffi/src/arrow_wrappers.rs:31,72; record_batch_stream.rs:101-167).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative dfgpu_status on error; the message is
+ *     retrievable with dfgpu_last_error(ctx).  Nothing unwinds across the boundary
+ *     (mirrors `Err` items in the stream, execution_plan.rs:529-537).
+ *   - plain pointers and sizes only.  `dfgpu_column` describes one Arrow primitive array
+ *     (values buffer + optional LSB validity bitmap + logical offset), either in host memory
+ *     (`*_host` / Arrow entry points) or already resident in HBM (`*_device` entry points).
+ *   - one handle per (operator, partition); a handle is not re-entrant; different handles are
+ *     independent (each ctx owns one CUDA stream) — the threading contract of
+ *     `ExecutionPlan::execute(partition, ..)` (execution_plan.rs:696).
+ *   - outputs are library-owned until dfgpu_batch_release.
+ */
+#ifndef DFGPU_H
+#define DFGPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- Arrow C Data Interface (https://arrow.apache.org/docs/format/CDataInterface.html) ---- */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+#define ARROW_FLAG_DICTIONARY_ORDERED 1
+#define ARROW_FLAG_NULLABLE 2
+#define ARROW_FLAG_MAP_KEYS_SORTED 4
+struct ArrowSchema {
+  const char* format;
+  const char* name;
+  const char* metadata;
+  int64_t flags;
+  int64_t n_children;
+  struct ArrowSchema** children;
+  struct ArrowSchema* dictionary;
+  void (*release)(struct ArrowSchema*);
+  void* private_data;
+};
+struct ArrowArray {
+  int64_t length;
+  int64_t null_count;
+  int64_t offset;
+  int64_t n_buffers;
+  int64_t n_children;
+  const void** buffers;
+  struct ArrowArray** children;
+  struct ArrowArray* dictionary;
+  void (*release)(struct ArrowArray*);
+  void* private_data;
+};
+#endif
+
+/* ---- status codes ---- */
+enum dfgpu_status {
+  DFGPU_OK = 0,
+  DFGPU_END = 1,              /* next_output: stream exhausted                                  */
+  DFGPU_ERR_INVALID = -1,     /* bad argument / unsupported shape (DataFusionError::Plan/Internal) */
+  DFGPU_ERR_CUDA = -2,        /* CUDA runtime error (DataFusionError::Execution)                */
+  DFGPU_ERR_UNSUPPORTED = -3, /* type / expression not handled on the GPU: caller keeps the CPU operator */
+  DFGPU_ERR_ARITH = -4,       /* e.g. integer division by zero (ArrowError::DivideByZero)        */
+  DFGPU_ERR_STATE = -5,       /* call sequence violation (push after finish, ...)               */
+  DFGPU_ERR_OOM = -6          /* device allocation failed (ResourcesExhausted)                   */
+};
+
+/* ---- physical types (Arrow primitive layouts) ---- */
+enum dfgpu_type {
+  DFGPU_BOOL = 1,   /* bit-packed values buffer */
+  DFGPU_INT8 = 2,
+  DFGPU_INT16 = 3,
+  DFGPU_INT32 = 4,
+  DFGPU_INT64 = 5,
+  DFGPU_UINT8 = 6,
+  DFGPU_UINT16 = 7,
+  DFGPU_UINT32 = 8,
+  DFGPU_UINT64 = 9,
+  DFGPU_FLOAT32 = 10,
+  DFGPU_FLOAT64 = 11,
+  DFGPU_DATE32 = 12,     /* int32 days  (TPC-H dates, benchmarks/src/tpch/mod.rs:52-122) */
+  DFGPU_DATE64 = 13,     /* int64 ms    */
+  DFGPU_TIMESTAMP = 14,  /* int64, unit carried by the Arrow schema only */
+  DFGPU_DECIMAL128 = 15  /* 16-byte little-endian two's complement (TPC-H money)           */
+};
+
+typedef struct dfgpu_column {
+  int32_t type;            /* enum dfgpu_type */
+  int32_t flags;           /* reserved, 0 */
+  int64_t length;          /* rows */
+  int64_t offset;          /* logical offset (elements) into values and validity */
+  int64_t null_count;      /* -1 = unknown */
+  const void* values;      /* values buffer */
+  const uint8_t* validity; /* Arrow LSB-numbered validity bitmap, or NULL = all valid */
+} dfgpu_column;
+
+typedef struct dfgpu_ctx dfgpu_ctx;       /* device + stream + allocator + last error */
+typedef struct dfgpu_batch dfgpu_batch;   /* library-owned output record batch (device or host) */
+typedef struct dfgpu_filter dfgpu_filter;       /* GpuFilterExec stream state    */
+typedef struct dfgpu_hashjoin dfgpu_hashjoin;   /* GpuHashJoinExec stream state  */
+typedef struct dfgpu_agg dfgpu_agg;             /* GpuAggregateExec stream state */
+
+/* ===================================================================================== */
+/* context, memory, timing                                                               */
+/* ===================================================================================== */
+
+/* stream: a cudaStream_t created by the caller (e.g. torch's current stream) or NULL to let the
+ * library create its own non-blocking stream. */
+int dfgpu_ctx_create(int device, void* stream, dfgpu_ctx** out);
+void dfgpu_ctx_destroy(dfgpu_ctx* ctx);
+const char* dfgpu_last_error(dfgpu_ctx* ctx);
+const char* dfgpu_version(void);
+int dfgpu_device_count(void);
+int dfgpu_sync(dfgpu_ctx* ctx);
+void* dfgpu_ctx_stream(dfgpu_ctx* ctx);
+
+int dfgpu_malloc(dfgpu_ctx* ctx, size_t bytes, void** out);     /* stream-ordered device allocation */
+int dfgpu_free(dfgpu_ctx* ctx, void* p);
+int dfgpu_host_alloc(dfgpu_ctx* ctx, size_t bytes, void** out); /* pinned host memory */
+int dfgpu_host_free(dfgpu_ctx* ctx, void* p);
+int dfgpu_memcpy_h2d(dfgpu_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on ctx stream */
+int dfgpu_memcpy_d2h(dfgpu_ctx* ctx, void* dst, const void* src, size_t bytes);
+int dfgpu_memset(dfgpu_ctx* ctx, void* dst, int value, size_t bytes);
+int dfgpu_flush_l2(dfgpu_ctx* ctx);  /* writes a >L2 scratch buffer (bench hygiene) */
+
+/* CUDA-event timing on the ctx stream (torch.cuda.Event only sees torch's stream). */
+int dfgpu_event_create(dfgpu_ctx* ctx, void** out);
+int dfgpu_event_record(dfgpu_ctx* ctx, void* ev);
+int dfgpu_event_elapsed_ms(dfgpu_ctx* ctx, void* start, void* stop, float* ms); /* syncs on stop */
+int dfgpu_event_destroy(dfgpu_ctx* ctx, void* ev);
+
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+int64_t dfgpu_launch_count(dfgpu_ctx* ctx);
+
+/* deterministic counter-based synthetic column generators, identical on host (oracle) and device
+ * so that billion-row inputs never cross PCIe.  kind: see dfgpu_gen_kind. */
+enum dfgpu_gen_kind {
+  DFGPU_GEN_SEQ = 0,        /* v = a + i                                    */
+  DFGPU_GEN_UNIFORM = 1,    /* v = a + splitmix64(seed, i) % b              */
+  DFGPU_GEN_SPLITMIX = 2,   /* v = splitmix64(seed, i)  (sparse unique-ish) */
+  DFGPU_GEN_PERM = 3,       /* v = a + bijection_b(i) over [0,b)  (dense unique) */
+  DFGPU_GEN_SPARSE_OF = 4   /* v = splitmix64(seed, splitmix64(seed2=a, i) % b): draws from the SPLITMIX key set */
+};
+int dfgpu_generate_i64(dfgpu_ctx* ctx, int kind, uint64_t seed, int64_t a, int64_t b, int64_t start,
+                       int64_t n, int64_t* out_device);
+
+/* ===================================================================================== */
+/* expressions: PhysicalExpr::evaluate (physical-expr-common/src/physical_expr.rs:88)     */
+/* ===================================================================================== */
+
+/* An expression is a post-order ("RPN") program of nodes, mirroring the tree walk of
+ * BinaryExpr::evaluate (physical-expr/src/expressions/binary.rs:536-676),
+ * Column::evaluate (column.rs:121) and Literal::evaluate (literal.rs:106). */
+enum dfgpu_expr_kind {
+  DFGPU_EXPR_COLUMN = 1,   /* a = column index in the input schema                 */
+  DFGPU_EXPR_LITERAL = 2,  /* type + value bits (lit_i64 / lit_f64) or is_null     */
+  DFGPU_EXPR_BINARY = 3,   /* a = dfgpu_op ; pops right then left                  */
+  DFGPU_EXPR_NOT = 4,
+  DFGPU_EXPR_IS_NULL = 5,
+  DFGPU_EXPR_IS_NOT_NULL = 6,
+  DFGPU_EXPR_NEGATIVE = 7,
+  DFGPU_EXPR_CAST = 8      /* type = target type                                    */
+};
+
+/* datafusion_expr::Operator (expr-common/src/operator.rs) subset on the hot path */
+enum dfgpu_op {
+  DFGPU_OP_EQ = 1, DFGPU_OP_NEQ = 2, DFGPU_OP_LT = 3, DFGPU_OP_LTEQ = 4, DFGPU_OP_GT = 5, DFGPU_OP_GTEQ = 6,
+  DFGPU_OP_PLUS = 7, DFGPU_OP_MINUS = 8, DFGPU_OP_MULTIPLY = 9, DFGPU_OP_DIVIDE = 10, DFGPU_OP_MODULO = 11,
+  DFGPU_OP_AND = 12, DFGPU_OP_OR = 13,
+  DFGPU_OP_IS_DISTINCT_FROM = 14, DFGPU_OP_IS_NOT_DISTINCT_FROM = 15,
+  DFGPU_OP_BITAND = 16, DFGPU_OP_BITOR = 17, DFGPU_OP_BITXOR = 18, DFGPU_OP_SHIFT_LEFT = 19, DFGPU_OP_SHIFT_RIGHT = 20
+};
+
+typedef struct dfgpu_expr_node {
+  int32_t kind;     /* dfgpu_expr_kind */
+  int32_t a;        /* column index or dfgpu_op */
+  int32_t type;     /* literal type / cast target */
+  int32_t is_null;  /* literal is NULL */
+  int64_t lit_i64;  /* integer / date / bool literal */
+  double lit_f64;   /* float literal */
+} dfgpu_expr_node;
+
+/* ===================================================================================== */
+/* FilterExec (physical-plan/src/filter.rs:85; hot loop poll_next :1364-1445)             */
+/* ===================================================================================== */
+
+/* schema: column types of the input batches; predicate: RPN program yielding Boolean;
+ * projection: column indices kept in the output (NULL = all, filter.rs:1402);
+ * batch_size: coalescer target (coalesce/mod.rs:61-65); fetch: row limit or -1 (filter.rs:623). */
+int dfgpu_filter_create(dfgpu_ctx* ctx, const int32_t* schema_types, int32_t n_cols,
+                        const dfgpu_expr_node* predicate, int32_t n_nodes,
+                        const int32_t* projection, int32_t n_projection,
+                        int64_t batch_size, int64_t fetch, dfgpu_filter** out);
+int dfgpu_filter_push_host(dfgpu_filter* f, const dfgpu_column* cols, int32_t n_cols);   /* H2D inside */
+int dfgpu_filter_push_device(dfgpu_filter* f, const dfgpu_column* cols, int32_t n_cols); /* HBM-resident */
+int dfgpu_filter_push_arrow(dfgpu_filter* f, const struct ArrowArray* batch, const struct ArrowSchema* schema);
+int dfgpu_filter_finish(dfgpu_filter* f);
+/* host=1: output buffers in pinned host memory (D2H inside); host=0: device pointers.
+ * returns DFGPU_OK with *out set, DFGPU_END when drained, <0 on error. */
+int dfgpu_filter_next(dfgpu_filter* f, int host, dfgpu_batch** out);
+int64_t dfgpu_filter_metric(dfgpu_filter* f, const char* name); /* "output_rows","input_rows","selectivity_num" … (filter.rs:1312-1330) */
+void dfgpu_filter_destroy(dfgpu_filter* f);
+
+/* stand-alone PhysicalExpr::evaluate on one batch → one output column (device) */
+int dfgpu_expr_evaluate_device(dfgpu_ctx* ctx, const dfgpu_column* cols, int32_t n_cols, int64_t n_rows,
+                               const dfgpu_expr_node* expr, int32_t n_nodes, dfgpu_batch** out);
+int dfgpu_expr_evaluate_host(dfgpu_ctx* ctx, const dfgpu_column* cols, int32_t n_cols, int64_t n_rows,
+                             const dfgpu_expr_node* expr, int32_t n_nodes, dfgpu_batch** out);
+
+/* ===================================================================================== */
+/* HashJoinExec (physical-plan/src/joins/hash_join/exec.rs:752; stream.rs:295)            */
+/* ===================================================================================== */
+
+/* datafusion_common::JoinType (common/src/join_type.rs) */
+enum dfgpu_join_type {
+  DFGPU_JOIN_INNER = 0, DFGPU_JOIN_LEFT = 1, DFGPU_JOIN_RIGHT = 2, DFGPU_JOIN_FULL = 3,
+  DFGPU_JOIN_LEFT_SEMI = 4, DFGPU_JOIN_RIGHT_SEMI = 5, DFGPU_JOIN_LEFT_ANTI = 6, DFGPU_JOIN_RIGHT_ANTI = 7,
+  DFGPU_JOIN_LEFT_MARK = 8, DFGPU_JOIN_RIGHT_MARK = 9
+};
+enum dfgpu_null_equality { DFGPU_NULL_EQUALS_NOTHING = 0, DFGPU_NULL_EQUALS_NULL = 1 };
+
+typedef struct dfgpu_hashjoin_options {
+  int32_t join_type;       /* dfgpu_join_type */
+  int32_t null_equality;   /* dfgpu_null_equality (joins/utils.rs:2122-2158) */
+  int64_t batch_size;      /* execution.batch_size, config.rs:904 */
+  /* perfect-hash (ArrayMap) selection — exec.rs:172-179, config.rs:913,923 */
+  int64_t perfect_hash_join_small_build_threshold; /* default 1024 */
+  double perfect_hash_join_min_key_density;        /* default 0.15 */
+  int32_t force_hash_collisions; /* mirror of cargo feature force_hash_collisions (hash_utils.rs:1185-1205) */
+  int32_t ordered_output;  /* 1 = reference order (probe order × ascending build index); 0 = any order */
+} dfgpu_hashjoin_options;
+void dfgpu_hashjoin_default_options(dfgpu_hashjoin_options* o);
+
+/* build = left child, probe = right child (exec.rs:768-776).  on_build/on_probe: key column indices.
+ * out_side[j]/out_index[j]: output column j is column out_index[j] of side out_side[j]
+ * (0 = build/left, 1 = probe/right, 2 = mark column) — ColumnIndex of joins/utils.rs:1332-1387. */
+int dfgpu_hashjoin_create(dfgpu_ctx* ctx,
+                          const int32_t* build_types, int32_t n_build_cols,
+                          const int32_t* probe_types, int32_t n_probe_cols,
+                          const int32_t* on_build, const int32_t* on_probe, int32_t n_on,
+                          const int32_t* out_side, const int32_t* out_index, int32_t n_out,
+                          const dfgpu_hashjoin_options* opts, dfgpu_hashjoin** out);
+int dfgpu_hashjoin_push_build_host(dfgpu_hashjoin* j, const dfgpu_column* cols, int32_t n_cols);
+int dfgpu_hashjoin_push_build_device(dfgpu_hashjoin* j, const dfgpu_column* cols, int32_t n_cols);
+int dfgpu_hashjoin_push_build_arrow(dfgpu_hashjoin* j, const struct ArrowArray* batch, const struct ArrowSchema* schema);
+int dfgpu_hashjoin_finish_build(dfgpu_hashjoin* j);  /* collect_left_input, exec.rs:2569-2776 */
+int dfgpu_hashjoin_push_probe_host(dfgpu_hashjoin* j, const dfgpu_column* cols, int32_t n_cols);
+int dfgpu_hashjoin_push_probe_device(dfgpu_hashjoin* j, const dfgpu_column* cols, int32_t n_cols);
+int dfgpu_hashjoin_push_probe_arrow(dfgpu_hashjoin* j, const struct ArrowArray* batch, const struct ArrowSchema* schema);
+int dfgpu_hashjoin_finish_probe(dfgpu_hashjoin* j);  /* ExhaustedProbeSide → process_unmatched_build_batch, stream.rs:1002 */
+int dfgpu_hashjoin_next(dfgpu_hashjoin* j, int host, dfgpu_batch** out);
+/* "build_input_rows","input_rows","output_rows","array_map_created_count","probe_hits" … (joins/utils.rs:1756-1778, exec.rs:108) */
+int64_t dfgpu_hashjoin_metric(dfgpu_hashjoin* j, const char* name);
+void dfgpu_hashjoin_destroy(dfgpu_hashjoin* j);
+
+/* ===================================================================================== */
+/* AggregateExec (physical-plan/src/aggregates/mod.rs:839; modes :289-362)                */
+/* ===================================================================================== */
+
+enum dfgpu_agg_mode {
+  DFGPU_AGG_PARTIAL = 0,           /* raw → state   (PartialHashAggregateStream, hash_stream.rs:141) */
+  DFGPU_AGG_FINAL = 1,             /* state → value (FinalHashAggregateStream, hash_stream.rs:236)   */
+  DFGPU_AGG_FINAL_PARTITIONED = 2,
+  DFGPU_AGG_SINGLE = 3,            /* raw → value   (SingleHashAggregateStream, single_stream.rs:88)  */
+  DFGPU_AGG_SINGLE_PARTITIONED = 4,
+  DFGPU_AGG_PARTIAL_REDUCE = 5     /* state → state */
+};
+enum dfgpu_agg_func {
+  DFGPU_AGG_SUM = 1,    /* functions-aggregate/src/sum.rs:308-321 (add_wrapping)      */
+  DFGPU_AGG_COUNT = 2,  /* functions-aggregate/src/count.rs:631-780                   */
+  DFGPU_AGG_MIN = 3,
+  DFGPU_AGG_MAX = 4,
+  DFGPU_AGG_AVG = 5,    /* state = [count:u64, sum] (aggregates/mod.rs:3591-3700)     */
+  DFGPU_AGG_COUNT_STAR = 6
+};
+typedef struct dfgpu_agg_desc {
+  int32_t func;        /* dfgpu_agg_func */
+  int32_t arg_col;     /* input column (raw modes) — in state modes the state columns follow the group columns in order */
+  int32_t filter_col;  /* Boolean FILTER (WHERE ..) column or -1 (accumulate.rs:373-470)  */
+  int32_t reserved;
+} dfgpu_agg_desc;
+
+/* input schema: raw modes = the child's columns; state modes = [group cols..., state cols...] as emitted
+ * by a Partial aggregate (sum: [sum]; count: [count]; avg: [count,sum]; min/max: [value]). */
+int dfgpu_agg_create(dfgpu_ctx* ctx, const int32_t* input_types, int32_t n_cols,
+                     const int32_t* group_cols, int32_t n_group,
+                     const dfgpu_agg_desc* aggs, int32_t n_aggs,
+                     int32_t mode, int64_t batch_size, int64_t capacity_hint, dfgpu_agg** out);
+int dfgpu_agg_push_host(dfgpu_agg* a, const dfgpu_column* cols, int32_t n_cols);
+int dfgpu_agg_push_device(dfgpu_agg* a, const dfgpu_column* cols, int32_t n_cols);
+int dfgpu_agg_push_arrow(dfgpu_agg* a, const struct ArrowArray* batch, const struct ArrowSchema* schema);
+int dfgpu_agg_finish(dfgpu_agg* a);
+int dfgpu_agg_next(dfgpu_agg* a, int host, dfgpu_batch** out);
+int64_t dfgpu_agg_metric(dfgpu_agg* a, const char* name); /* "num_groups","input_rows","output_rows","table_capacity","rehashes" */
+void dfgpu_agg_destroy(dfgpu_agg* a);
+
+/* ===================================================================================== */
+/* output batches                                                                        */
+/* ===================================================================================== */
+int64_t dfgpu_batch_num_rows(const dfgpu_batch* b);
+int32_t dfgpu_batch_num_columns(const dfgpu_batch* b);
+int dfgpu_batch_column(const dfgpu_batch* b, int32_t i, dfgpu_column* out);
+int dfgpu_batch_is_host(const dfgpu_batch* b);
+/* export a host batch as an Arrow C Data struct array; ownership of the buffers moves to the
+ * ArrowArray's release callback (record_batch_stream.rs:101-110 is the consumer side). */
+int dfgpu_batch_export_arrow(dfgpu_batch* b, struct ArrowArray* out_array, struct ArrowSchema* out_schema);
+void dfgpu_batch_release(dfgpu_batch* b);
+
+/* ===================================================================================== */
+/* exchange: RepartitionExec hash partitioning (physical-plan/src/repartition/mod.rs:1097-1145)
+ * — the local pass that precedes the NCCL all-to-all.                                    */
+/* ===================================================================================== */
+
+/* Scatter the rows of `cols` (device) into n_parts contiguous regions by
+ * partition = exchange_hash(key columns) % n_parts.  Output columns are library-owned device
+ * buffers of the same types; part_offsets_host[n_parts+1] receives the region boundaries. */
+int dfgpu_hash_partition_device(dfgpu_ctx* ctx, const dfgpu_column* cols, int32_t n_cols,
+                                const int32_t* key_cols, int32_t n_keys, int32_t n_parts,
+                                dfgpu_batch** out, int64_t* part_offsets_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFGPU_H */
