@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json metric on its config: rows/sec of the join hot path (HashJoinExec, config C2).
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One step = one complete inner hash join (build + probe + output materialisation) of
+  probe 100M rows {k:int64, pp:int64}  JOIN  build 10M rows {k:int64, pb:int64}   -> {k, pb, pp}
+with SPARSE UNIQUE build keys k = splitmix64(42, i) and probe keys drawn from them (100 % hit rate,
+fan-out 1, 100M output rows): SURVEY.md §8d C2(ii) — the case where the reference takes its hashbrown
+path (the dense-key / ArrayMap case is reported under "extra").  rows/sec = (build + probe rows) / time.
+
+* value  : device-resident inputs (generated in HBM by the shared counter-based generators), timed with
+           CUDA events on the launching stream; inputs (1.76 GB) exceed L2 (126 MB) so no L2 flush is needed.
+* e2e    : the same join through the C ABI with HOST buffers (pinned): H2D of both inputs and D2H of the
+           100M-row result inside the timed region.
+* roofline: the dominant kernel (join_probe: fused probe + materialise), algorithmic bytes = 40 B per
+           probe row (16 B read + 24 B written), duration from CUDA events around that kernel.
+* cpu_baseline / --impl reference: oracle/ C restatement of the reference's partitioned HashJoinExec
+           (RepartitionExec + per-partition build/probe/take), all host threads — kind "port": the
+           Rust reference cannot be built in this image.
+N > 1 (torchrun): weak scaling — every rank owns 100M probe + 10M build rows, rows are hash-partitioned
+on the GPU, exchanged with ONE all-to-all per column (NCCL via torch.distributed), then joined locally.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NB_PER_GPU = 10_000_000
+NP_PER_GPU = 100_000_000
+METRIC = "rows/sec join (HashJoinExec build+probe+emit, TPC-H-shaped int64 keys)"
+UNIT = "rows/s"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+
+    def __init__(self, device=0):
+        self.device, self.samples, self.proc = device, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """the reference arm: CPU restatement (oracle/, kind "port") on all host cores, bounded sample per step"""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    threads = os.cpu_count() or 1
+    nb, npr = NB_PER_GPU, NP_PER_GPU
+    # bounded sample: a 1/2-size instance of the same workload per step keeps K steps within minutes on small hosts
+    frac = 1.0 if threads >= 32 else 0.5
+    nb, npr = int(nb * frac), int(npr * frac)
+    bk = O.generate_i64(2, 42, 0, 0, nb, threads); bp = O.generate_i64(2, 7, 0, 0, nb, threads)
+    pk = O.generate_i64(4, 42, 43, nb, npr, threads); pp = O.generate_i64(2, 8, 0, 0, npr, threads)
+    for _ in range(max(1, min(args.warmup, 1))):
+        O.bench_join(bk, bp, pk, pp, threads=threads)
+    t = 0.0
+    for _ in range(args.steps):
+        secs, rows, _ = O.bench_join(bk, bp, pk, pp, threads=threads)
+        assert rows == npr
+        t += secs
+    value = (nb + npr) * args.steps / t
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+            "data": "synthetic (counter-based generators, identical to the GPU arm)",
+            "config": {"workload": "C2 HashJoinExec inner 100M x 10M int64, sparse unique keys, 100% hit (sample below)", "batch_size": 8192,
+                       "partition_mode": "Partitioned", "target_partitions": threads},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{npr} probe x {nb} build rows per step (fraction {frac} of C2), oracle/oracle.c oracle_bench_join: RepartitionExec(Hash) both sides + per-partition JoinHashMap build/probe/take, batch_size 8192"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def make_inputs(ctx, D, rank, world, nb, npr):
+    """rank r owns global rows [r*n, (r+1)*n) of both tables (the generators are counter-based)"""
+    nb_all = nb * world
+    bk = ctx.generate_i64(D.GEN_SPLITMIX, 42, 0, 0, rank * nb, nb)
+    bp = ctx.generate_i64(D.GEN_SPLITMIX, 7, 0, 0, rank * nb, nb)
+    pk = ctx.generate_i64(D.GEN_SPARSE_OF, 42, 43, nb_all, rank * npr, npr)
+    pp = ctx.generate_i64(D.GEN_SPLITMIX, 8, 0, 0, rank * npr, npr)
+    return bk, bp, pk, pp
+
+
+def join_step(ctx, D, build_cols, probe_cols, keep_output=False):
+    j = D.HashJoinHandle(ctx, [D.INT64, D.INT64], [D.INT64, D.INT64], [0], [0], [0, 0, 1], [0, 1, 1])
+    j.push_build_device(build_cols)
+    j.finish_build()
+    j.push_probe_device(probe_cols)
+    j.finish_probe()
+    rows = j.metric("output_rows")
+    outs = j.drain(host=False)
+    if not keep_output:
+        for b in outs:
+            b.release()
+        outs = []
+    j.close()
+    return rows, outs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    from datafusion_b200 import capi as D
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_
+        dist = dist_
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        tstream = torch.cuda.Stream()           # one explicit stream shared by torch (NCCL ordering) and libdfgpu
+        torch.cuda.set_stream(tstream)
+        ctx = D.Context(local, tstream.cuda_stream)
+    else:
+        ctx = D.Context(local)
+    nb, npr = NB_PER_GPU, NP_PER_GPU
+    bk, bp, pk, pp = make_inputs(ctx, D, rank, world, nb, npr)
+    col = lambda buf, n: D.DeviceColumn(ctx, D.INT64, n, buf)
+    build_cols, probe_cols = [col(bk, nb), col(bp, nb)], [col(pk, npr), col(pp, npr)]
+
+    def step():
+        if world == 1:
+            return join_step(ctx, D, build_cols, probe_cols)[0]
+        from datafusion_b200 import exchange
+        b2 = exchange.exchange_batch(ctx, build_cols, [0], dist)
+        p2 = exchange.exchange_batch(ctx, probe_cols, [0], dist)
+        return join_step(ctx, D, b2.columns(), p2.columns())[0]
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out_rows = step()
+    barrier()
+    ctx.set_kernel_timing(True)
+    ctx.kernel_time_reset()
+    launches0 = ctx.launches
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = ctx.event(), ctx.event()
+    ctx.record(e0)
+    for _ in range(args.steps):
+        out_rows = step()
+    ctx.record(e1)
+    ms = ctx.elapsed_ms(e0, e1)
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    launches = ctx.launches - launches0
+    ctx.set_kernel_timing(False)
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    probe_ms, probe_n = ctx.kernel_time("join_probe")
+    build_ms, build_n = ctx.kernel_time("join_build")
+    ms_per_step = ms / args.steps
+    value = (nb + npr) * world / (ms_per_step / 1000.0)
+
+    line = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        algo_bytes = 40.0 * npr                     # 16 B read + 24 B written per probe row
+        k_ms = probe_ms / max(probe_n, 1)
+        achieved = algo_bytes / (k_ms / 1000.0) / 1e9 if k_ms > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": "join_probe_fused_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
+                    "algorithmic_bytes_per_launch": algo_bytes, "build_kernel_ms": build_ms / max(build_n, 1),
+                    "whole_join_achieved_gbs": (16.0 * nb + 16.0 * npr + 24.0 * npr) / (ms_per_step / 1000.0) / 1e9 if world == 1 else None}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic (generated in HBM, counter-based)",
+                "config": {"workload": "C2 HashJoinExec inner 100M x 10M int64 per GPU, sparse unique build keys, 100% hit, output {k,pb,pp}",
+                           "rows_per_step": (nb + npr) * world, "output_rows_per_gpu": int(out_rows), "l2": "inputs (1.76 GB/GPU) exceed L2; no flush",
+                           "exchange": "hash partition + one NCCL all-to-all per column" if world > 1 else "none (single GPU)"},
+                "clocks": clk, "gpu_launches": int(launches), "roofline": roofline}
+
+    # ---- e2e through the C ABI with host (pinned) buffers: N = 1 only has a host leg per rank; we run it on every rank and take the max ----
+    h2d = 16 * (nb + npr)
+    hb = [ctx.pinned_empty(nb, np.int64), ctx.pinned_empty(nb, np.int64)]
+    hp = [ctx.pinned_empty(npr, np.int64), ctx.pinned_empty(npr, np.int64)]
+    import ctypes as C
+    for dst, src, n in ((hb[0], bk, nb), (hb[1], bp, nb), (hp[0], pk, npr), (hp[1], pp, npr)):
+        ctx.check(ctx.lib.dfgpu_memcpy_d2h(ctx.h, dst.ctypes.data_as(C.c_void_p), C.c_void_p(src.ptr), n * 8))
+    ctx.sync()
+
+    def e2e_step():
+        j = D.HashJoinHandle(ctx, [D.INT64, D.INT64], [D.INT64, D.INT64], [0], [0], [0, 0, 1], [0, 1, 1])
+        j.push_build_host([D.HostColumn(hb[0]), D.HostColumn(hb[1])])
+        j.finish_build()
+        j.push_probe_host([D.HostColumn(hp[0]), D.HostColumn(hp[1])])
+        j.finish_probe()
+        outs = j.drain(host=True)
+        rows = sum(o.num_rows for o in outs)
+        d2h = rows * 24
+        chk = int(np.ctypeslib.as_array((C.c_int64 * 1).from_address(outs[0].column(0).values))[0]) if outs else 0
+        for o in outs:
+            o.release()
+        j.close()
+        return rows, d2h, chk
+
+    if world == 1:
+        for _ in range(2):
+            e2e_step()
+        ctx.sync()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            rows, d2h, _ = e2e_step()
+        ctx.sync()
+        t1 = time.perf_counter()
+        e2e_val = (nb + npr) * args.e2e_steps / (t1 - t0)
+        line["e2e"] = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
+                       "ms_per_step": 1000 * (t1 - t0) / args.e2e_steps, "timer": "host wall clock around the C-ABI calls (includes H2D, kernels, D2H)"}
+    elif rank == 0:
+        line["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": None, "note": "host leg measured at N=1 only"}
+
+    if rank == 0:
+        # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload ----
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as O
+            threads = os.cpu_count() or 1
+            sb, sp = nb // 2, npr // 2
+            hbk = O.generate_i64(2, 42, 0, 0, sb, threads); hbp = O.generate_i64(2, 7, 0, 0, sb, threads)
+            hpk = O.generate_i64(4, 42, 43, sb, sp, threads); hpp = O.generate_i64(2, 8, 0, 0, sp, threads)
+            O.bench_join(hbk, hbp, hpk, hpp, threads=threads)
+            secs, rows, _ = O.bench_join(hbk, hbp, hpk, hpp, threads=threads)
+            line["cpu_baseline"] = {"value": (sb + sp) / secs, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{sp} probe x {sb} build rows (half of C2), one timed run after one warm-up; oracle_bench_join partitioned hash join on all host threads"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

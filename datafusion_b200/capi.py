@@ -90,6 +90,7 @@ EXPORTS = [
     "dfgpu_ctx_stream", "dfgpu_malloc", "dfgpu_free", "dfgpu_host_alloc", "dfgpu_host_free", "dfgpu_memcpy_h2d",
     "dfgpu_memcpy_d2h", "dfgpu_memset", "dfgpu_flush_l2", "dfgpu_event_create", "dfgpu_event_record",
     "dfgpu_event_elapsed_ms", "dfgpu_event_destroy", "dfgpu_launch_count", "dfgpu_generate_i64",
+    "dfgpu_set_kernel_timing", "dfgpu_kernel_time", "dfgpu_kernel_time_reset",
     "dfgpu_filter_create", "dfgpu_filter_push_host", "dfgpu_filter_push_device", "dfgpu_filter_push_arrow",
     "dfgpu_filter_finish", "dfgpu_filter_next", "dfgpu_filter_metric", "dfgpu_filter_destroy",
     "dfgpu_expr_evaluate_device", "dfgpu_expr_evaluate_host",
@@ -143,6 +144,9 @@ def load_library() -> C.CDLL:
     sig("dfgpu_event_elapsed_ms", C.c_int, [vp, vp, vp, P(C.c_float)])
     sig("dfgpu_event_destroy", C.c_int, [vp, vp])
     sig("dfgpu_launch_count", i64, [vp])
+    sig("dfgpu_set_kernel_timing", C.c_int, [vp, C.c_int])
+    sig("dfgpu_kernel_time", C.c_int, [vp, C.c_char_p, P(C.c_double), P(i64)])
+    sig("dfgpu_kernel_time_reset", C.c_int, [vp])
     sig("dfgpu_generate_i64", C.c_int, [vp, C.c_int, u64, i64, i64, i64, i64, vp])
     sig("dfgpu_filter_create", C.c_int, [vp, P(i32), i32, P(ExprNode), i32, P(i32), i32, i64, i64, P(vp)])
     for n in ("dfgpu_filter_push_host", "dfgpu_filter_push_device", "dfgpu_hashjoin_push_build_host",
@@ -209,6 +213,18 @@ class Context:
     @property
     def launches(self) -> int:
         return self.lib.dfgpu_launch_count(self.h)
+
+    def set_kernel_timing(self, on: bool):
+        self.check(self.lib.dfgpu_set_kernel_timing(self.h, 1 if on else 0))
+
+    def kernel_time(self, name: str):
+        """(total device ms, launches) of one kernel family since the last reset"""
+        ms, cnt = C.c_double(), C.c_int64()
+        self.check(self.lib.dfgpu_kernel_time(self.h, name.encode(), C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
+
+    def kernel_time_reset(self):
+        self.check(self.lib.dfgpu_kernel_time_reset(self.h))
 
     def flush_l2(self):
         self.check(self.lib.dfgpu_flush_l2(self.h))

@@ -589,11 +589,14 @@ static void agg_push(dfgpu_agg* a, const std::vector<DCol>& cols) {
       TableDev t = table_dev(a, a->tags, a->cap, a->counters, a->special_used);
       DF_CUDA(cudaMemsetAsync(a->counters.as<unsigned long long>() + 1, 0, 8, ctx->stream));
       int grid = grid_for(work, 256, kNumSMs * 8);
-      if (a->kw == 1)
-        agg_update_kernel<1><<<grid, 256, 0, ctx->stream>>>(g, set, t, done, work, list, overflow.as<uint32_t>(), a->counters.as<unsigned long long>() + 1);
-      else
-        agg_update_kernel<2><<<grid, 256, 0, ctx->stream>>>(g, set, t, done, work, list, overflow.as<uint32_t>(), a->counters.as<unsigned long long>() + 1);
-      DF_LAUNCH_CHECK(ctx);
+      {
+        KernelTimer kt(ctx, "agg_update");
+        if (a->kw == 1)
+          agg_update_kernel<1><<<grid, 256, 0, ctx->stream>>>(g, set, t, done, work, list, overflow.as<uint32_t>(), a->counters.as<unsigned long long>() + 1);
+        else
+          agg_update_kernel<2><<<grid, 256, 0, ctx->stream>>>(g, set, t, done, work, list, overflow.as<uint32_t>(), a->counters.as<unsigned long long>() + 1);
+        DF_LAUNCH_CHECK(ctx);
+      }
       unsigned long long hc[2];
       DF_CUDA(cudaMemcpyAsync(hc, a->counters.ptr, 16, cudaMemcpyDeviceToHost, ctx->stream));
       DF_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -8,6 +8,8 @@
 #include <vector>
 #include <memory>
 #include <stdexcept>
+#include <map>
+#include <mutex>
 #include "../../include/dfgpu.h"
 
 namespace dfgpu {
@@ -104,7 +106,16 @@ __host__ __device__ inline uint64_t splitmix64_at(uint64_t seed, uint64_t i) {
 // ------------------------------------------------------------------------------------------
 }  // namespace dfgpu
 
+struct dfgpu_kernel_timing {
+  std::string name;
+  double total_ms = 0;
+  int64_t count = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;  // recorded, not yet resolved
+};
+
 struct dfgpu_ctx {
+  bool time_kernels = false;                    // dfgpu_set_kernel_timing
+  std::vector<dfgpu_kernel_timing> timings;     // per kernel family
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -150,17 +161,58 @@ struct DevBuf {
   void fill(int byte) { if (ptr) DF_CUDA(cudaMemsetAsync(ptr, byte, bytes, ctx->stream)); }
 };
 
-// pinned host buffer
+// process-wide pool of pinned host blocks: cudaMallocHost of GB-sized buffers costs hundreds of ms
+// (page locking), so released blocks are kept and reused by size class (power-of-two buckets).
+struct PinnedPool {
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks;
+  size_t cached_bytes = 0;
+  static constexpr size_t kMaxCached = 24ull << 30;
+  static PinnedPool& get() { static PinnedPool* p = new PinnedPool(); return *p; }  // leaked on purpose: outlives ctx teardown order
+  static size_t bucket(size_t n) { size_t b = 4096; while (b < n) b <<= 1; return b; }
+  void* acquire(size_t n, size_t* got) {
+    size_t b = bucket(n);
+    {
+      std::lock_guard<std::mutex> g(mu);
+      auto it = free_blocks.find(b);
+      if (it != free_blocks.end()) { void* p = it->second; free_blocks.erase(it); cached_bytes -= b; *got = b; return p; }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, b);
+    if (e != cudaSuccess) {
+      trim();
+      e = cudaMallocHost(&p, b);
+      if (e != cudaSuccess) { cudaGetLastError(); throw Error(DFGPU_ERR_OOM, "pinned host allocation failed"); }
+    }
+    *got = b;
+    return p;
+  }
+  void release(void* p, size_t b) {
+    std::lock_guard<std::mutex> g(mu);
+    if (cached_bytes + b > kMaxCached) { cudaFreeHost(p); return; }
+    free_blocks.emplace(b, p);
+    cached_bytes += b;
+  }
+  void trim() {
+    std::lock_guard<std::mutex> g(mu);
+    for (auto& kv : free_blocks) cudaFreeHost(kv.second);
+    free_blocks.clear();
+    cached_bytes = 0;
+  }
+};
+
+// pinned host buffer (pooled)
 struct HostBuf {
   void* ptr = nullptr;
-  size_t bytes = 0;
+  size_t bytes = 0;      // requested
+  size_t cap = 0;        // pooled block size
   HostBuf() {}
   explicit HostBuf(size_t n) { alloc(n); }
   HostBuf(const HostBuf&) = delete;
   HostBuf& operator=(const HostBuf&) = delete;
-  HostBuf(HostBuf&& o) noexcept { ptr = o.ptr; bytes = o.bytes; o.ptr = nullptr; o.bytes = 0; }
+  HostBuf(HostBuf&& o) noexcept { ptr = o.ptr; bytes = o.bytes; cap = o.cap; o.ptr = nullptr; o.bytes = 0; o.cap = 0; }
   HostBuf& operator=(HostBuf&& o) noexcept {
-    if (this != &o) { release(); ptr = o.ptr; bytes = o.bytes; o.ptr = nullptr; o.bytes = 0; }
+    if (this != &o) { release(); ptr = o.ptr; bytes = o.bytes; cap = o.cap; o.ptr = nullptr; o.bytes = 0; o.cap = 0; }
     return *this;
   }
   ~HostBuf() { release(); }
@@ -168,9 +220,9 @@ struct HostBuf {
     release();
     bytes = n;
     if (n == 0) return;
-    DF_CUDA(cudaMallocHost(&ptr, n));
+    ptr = PinnedPool::get().acquire(n, &cap);
   }
-  void release() { if (ptr) { cudaFreeHost(ptr); ptr = nullptr; bytes = 0; } }
+  void release() { if (ptr) { PinnedPool::get().release(ptr, cap); ptr = nullptr; bytes = 0; cap = 0; } }
 };
 
 // A device-resident column: either a borrowed view or owning buffers.
@@ -205,6 +257,25 @@ inline DCol alloc_col(dfgpu_ctx* ctx, int type, int64_t rows, bool with_validity
   }
   return d;
 }
+
+// Optional per-kernel CUDA-event timing on the launching stream (bench.py's roofline numbers).
+struct KernelTimer {
+  dfgpu_ctx* ctx;
+  dfgpu_kernel_timing* slot = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  KernelTimer(dfgpu_ctx* c, const char* name) : ctx(c) {
+    if (!c->time_kernels) return;
+    for (auto& t : c->timings) if (t.name == name) { slot = &t; break; }
+    if (!slot) { c->timings.emplace_back(); c->timings.back().name = name; slot = &c->timings.back(); }
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, c->stream);
+  }
+  ~KernelTimer() {
+    if (!slot) return;
+    cudaEventRecord(e1, ctx->stream);
+    slot->pending.emplace_back(e0, e1);
+  }
+};
 
 #define DF_LAUNCH_CHECK(ctx)            \
   do {                                  \

@@ -96,6 +96,38 @@ const char* dfgpu_last_error(dfgpu_ctx* ctx) { return ctx ? ctx->last_error.c_st
 void* dfgpu_ctx_stream(dfgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int64_t dfgpu_launch_count(dfgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int dfgpu_set_kernel_timing(dfgpu_ctx* ctx, int enabled) {
+  if (!ctx) return DFGPU_ERR_INVALID;
+  ctx->time_kernels = enabled != 0;
+  return DFGPU_OK;
+}
+int dfgpu_kernel_time(dfgpu_ctx* ctx, const char* name, double* total_ms, int64_t* count) {
+  DF_API_BEGIN(ctx)
+  DF_CHECK(name && total_ms && count, DFGPU_ERR_INVALID, "null argument");
+  *total_ms = 0; *count = 0;
+  for (auto& t : ctx->timings) {
+    if (t.name != name) continue;
+    for (auto& pr : t.pending) {
+      DF_CUDA(cudaEventSynchronize(pr.second));
+      float ms = 0;
+      DF_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+      t.total_ms += ms; t.count++;
+      cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+    }
+    t.pending.clear();
+    *total_ms = t.total_ms; *count = t.count;
+  }
+  DF_API_END
+}
+int dfgpu_kernel_time_reset(dfgpu_ctx* ctx) {
+  DF_API_BEGIN(ctx)
+  for (auto& t : ctx->timings) {
+    for (auto& pr : t.pending) { cudaEventSynchronize(pr.second); cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    t.pending.clear(); t.total_ms = 0; t.count = 0;
+  }
+  DF_API_END
+}
+
 int dfgpu_sync(dfgpu_ctx* ctx) {
   DF_API_BEGIN(ctx)
   set_device(ctx);

@@ -150,31 +150,75 @@ __global__ void __launch_bounds__(256) join_minmax_kernel(KeyCols kc, int64_t n,
   }
 }
 
+struct alignas(16) Slot128 { unsigned long long lo, hi; };
+__device__ __forceinline__ Slot128 cas128(void* addr, Slot128 cmp, Slot128 val) {
+  Slot128 old;
+  asm volatile("{\n\t.reg .b128 c, v, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 v, {%4, %5};\n\tatom.global.cas.b128 o, [%6], c, v;\n\tmov.b128 {%0, %1}, o;\n\t}"
+               : "=l"(old.lo), "=l"(old.hi) : "l"(cmp.lo), "l"(cmp.hi), "l"(val.lo), "l"(val.hi), "l"(addr) : "memory");
+  return old;
+}
+
+// Insert `row` under `tag`.  The common case (first row of its key) is ONE 128-bit CAS that claims the
+// slot and installs {tag, head=row, cnt=0} together; only duplicates take the counter + sorted-chain path.
+// Returns true when this row created the key.
+__device__ __forceinline__ bool insert_row(const TableRef& t, uint64_t tag, uint32_t row) {
+  uint32_t* e = nullptr;
+  if (t.amap) {
+    unsigned long long* ep = (unsigned long long*)&t.amap[tag - t.amin];
+    unsigned long long prev = atomicCAS(ep, (unsigned long long)kEmpty64, (unsigned long long)row /* head=row, cnt=0 */);
+    if (prev == kEmpty64) return true;
+    e = (uint32_t*)ep;
+  } else if (tag == kEmpty64) {
+    e = ((uint32_t*)&t.slots[t.cap]) + 2;  // dedicated slot for the all-ones key
+  } else {
+    uint64_t s = slot_of(tag, t);
+    while (true) {
+      const uint4 v = __ldcg(&t.slots[s]);
+      uint64_t cur = (uint64_t)v.x | ((uint64_t)v.y << 32);
+      if (cur == kEmpty64) {
+        Slot128 prev = cas128(&t.slots[s], Slot128{kEmpty64, kEmpty64}, Slot128{tag, (unsigned long long)row /* head=row, cnt=0 */});
+        if (prev.lo == kEmpty64) return true;
+        cur = prev.lo;
+      }
+      if (cur == tag) { e = ((uint32_t*)&t.slots[s]) + 2; break; }
+      if (++s == t.cap) s = 0;
+    }
+  }
+  uint32_t old = atomicAdd(e + 1, 1u);
+  chain_insert(e, t.next, row);
+  return old == kEmpty32;  // only possible on the special / NULL slots (memset state)
+}
+
 __global__ void __launch_bounds__(256) join_build_kernel(KeyCols kc, int64_t n, TableRef t, unsigned long long* counters /* [distinct, valid_rows, null_rows] */) {
-  __shared__ unsigned int s_distinct, s_valid, s_null;
-  if (threadIdx.x == 0) { s_distinct = 0; s_valid = 0; s_null = 0; }
-  __syncthreads();
+  unsigned int distinct = 0, valid = 0, nulls = 0;
   // rows are visited in DESCENDING order: a later (smaller) row then usually becomes the new chain
   // head with two atomics, mirroring the reference's reverse iteration (exec.rs:2684-2702, array_map.rs:213)
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t row = n - 1 - i;
     uint64_t tag;
     bool ok = load_tag(kc, row, &tag);
-    uint32_t* e = nullptr;
-    if (ok) e = claim_entry(t, tag);
-    else if (t.null_slot) e = (uint32_t*)t.null_slot;  // NullEqualsNull
-    if (!ok) atomicAdd(&s_null, 1u);
-    if (!e) continue;  // NULL key under NullEqualsNothing: not inserted (utils.rs:2146-2155)
-    uint32_t old = atomicAdd(e + 1, 1u);
-    if (old == kEmpty32) atomicAdd(&s_distinct, 1u);
-    atomicAdd(&s_valid, 1u);
-    chain_insert(e, t.next, (uint32_t)row);
+    if (!ok) nulls++;
+    if (ok) {
+      distinct += insert_row(t, tag, (uint32_t)row) ? 1u : 0u;
+      valid++;
+    } else if (t.null_slot) {  // NullEqualsNull: NULL keys collect in their own entry
+      uint32_t* e = (uint32_t*)t.null_slot;
+      uint32_t old = atomicAdd(e + 1, 1u);
+      chain_insert(e, t.next, (uint32_t)row);
+      distinct += old == kEmpty32 ? 1u : 0u;
+      valid++;
+    }  // else: NULL key under NullEqualsNothing is not inserted (utils.rs:2146-2155)
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (s_distinct) atomicAdd(&counters[0], (unsigned long long)s_distinct);
-    if (s_valid) atomicAdd(&counters[1], (unsigned long long)s_valid);
-    if (s_null) atomicAdd(&counters[2], (unsigned long long)s_null);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    distinct += __shfl_xor_sync(0xffffffffu, distinct, d);
+    valid += __shfl_xor_sync(0xffffffffu, valid, d);
+    nulls += __shfl_xor_sync(0xffffffffu, nulls, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (distinct) atomicAdd(&counters[0], (unsigned long long)distinct);
+    if (valid) atomicAdd(&counters[1], (unsigned long long)valid);
+    if (nulls) atomicAdd(&counters[2], (unsigned long long)nulls);
   }
 }
 
@@ -280,6 +324,140 @@ __global__ void __launch_bounds__(kProbeThreads) join_emit_kernel(int64_t n, con
       }
     }
     base += tot;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused probe + materialise (unique build side, Inner/Left): one pass, reference order.
+//   tile = 256 threads x 4 consecutive probe rows; lookups -> matched (build,probe) pairs compacted in
+//   shared memory -> the tile's output offset through a decoupled look-back over tile descriptors
+//   (single pass, no global pair arrays, no second probe) -> coalesced writes of every output column,
+//   gathering build columns by build row and probe columns by probe row.
+// ------------------------------------------------------------------------------------------
+constexpr int kFusedThreads = 256;
+constexpr int kFusedItems = 4;
+constexpr int kFusedTile = kFusedThreads * kFusedItems;
+constexpr int kMaxFusedCols = 16;
+struct FusedCols {
+  int n;
+  const void* src[kMaxFusedCols];
+  void* dst[kMaxFusedCols];
+  int width[kMaxFusedCols];  // 1,2,4,8,16 bytes
+  int side[kMaxFusedCols];   // 0 build, 1 probe
+};
+#define kDescAgg (1ull << 62)
+#define kDescPrefix (2ull << 62)
+#define kDescMask ((1ull << 62) - 1ull)
+
+__global__ void __launch_bounds__(kFusedThreads) join_probe_fused_kernel(KeyCols kc, int64_t n, TableRef t, int mark_visited, FusedCols oc,
+                                                                      unsigned long long* __restrict__ tile_desc, unsigned int* __restrict__ tile_counter,
+                                                                      unsigned long long* __restrict__ totals /* [out_rows, hit_rows] */) {
+  __shared__ uint32_t s_b[kFusedTile], s_p[kFusedTile];
+  __shared__ unsigned int s_tile;
+  __shared__ unsigned long long s_base;
+  if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);  // dynamic tile order = look-back never waits on an unscheduled tile
+  __syncthreads();
+  const int64_t tile = s_tile;
+  const int64_t row0 = tile * kFusedTile + (int64_t)threadIdx.x * kFusedItems;
+  uint32_t heads[kFusedItems];
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < kFusedItems; ++k) {
+    heads[k] = kEmpty32;
+    const int64_t i = row0 + k;
+    if (i < n) {
+      uint64_t tag;
+      bool ok = load_tag(kc, i, &tag);
+      uint32_t* e = nullptr;
+      if (ok) e = find_entry(t, tag);
+      else if (t.null_slot) e = (uint32_t*)t.null_slot;
+      if (e) {
+        uint2 hc = __ldcg((const uint2*)e);
+        if (hc.x != kEmpty32) {
+          heads[k] = hc.x;
+          ++m;
+          if (mark_visited && !(hc.y & kVisitedBit)) atomicOr(e + 1, kVisitedBit);
+        }
+      }
+    }
+  }
+  uint32_t tot;
+  uint32_t ex = block_exclusive_scan<kFusedThreads, uint32_t>(m, &tot);
+#pragma unroll
+  for (int k = 0; k < kFusedItems; ++k)
+    if (heads[k] != kEmpty32) { s_b[ex] = heads[k]; s_p[ex] = (uint32_t)(row0 + k - tile * kFusedTile); ++ex; }
+  // ---- decoupled look-back (warp 0) ----
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    unsigned long long exclusive = 0;
+    if (tile == 0) {
+      if (lane == 0) atomicExch(&tile_desc[0], kDescPrefix | (unsigned long long)tot);
+    } else {
+      if (lane == 0) atomicExch(&tile_desc[tile], kDescAgg | (unsigned long long)tot);
+      int64_t look = tile - 1;
+      while (true) {
+        const int64_t idx = look - lane;
+        unsigned long long d = idx >= 0 ? *(volatile unsigned long long*)&tile_desc[idx] : kDescPrefix;  // virtual prefix 0 before tile 0
+        const unsigned st = (unsigned)(d >> 62);
+        const unsigned invalid = __ballot_sync(0xffffffffu, st == 0);
+        const unsigned prefix = __ballot_sync(0xffffffffu, st == 2);
+        const int first_prefix = prefix ? __ffs(prefix) - 1 : 32;
+        const int first_invalid = invalid ? __ffs(invalid) - 1 : 32;
+        if (first_invalid < first_prefix) continue;  // a predecessor in the window has not published yet: spin
+        unsigned long long contrib = (lane <= first_prefix && lane < 32) ? (d & kDescMask) : 0ull;
+        if (lane > first_prefix) contrib = 0;
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, dd);
+        exclusive += contrib;
+        if (first_prefix < 32) break;
+        look -= 32;
+      }
+      if (lane == 0) atomicExch(&tile_desc[tile], kDescPrefix | (exclusive + (unsigned long long)tot));
+    }
+    if (lane == 0) {
+      s_base = exclusive;
+      if ((tile + 1) * (int64_t)kFusedTile >= n) totals[0] = exclusive + tot;  // last tile: total output rows
+      if (tot) atomicAdd(&totals[1], (unsigned long long)tot);
+    }
+  }
+  __syncthreads();
+  const unsigned long long base = s_base;
+  const int64_t prow0 = tile * kFusedTile;
+  // ---- materialise: every output column, coalesced writes ----
+  for (int c = 0; c < oc.n; ++c) {
+    const bool build_side = oc.side[c] == 0;
+    switch (oc.width[c]) {
+      case 8: {
+        const uint64_t* src = (const uint64_t*)oc.src[c];
+        uint64_t* dst = (uint64_t*)oc.dst[c] + base;
+        for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = build_side ? src[s_b[j]] : src[prow0 + s_p[j]];
+        break;
+      }
+      case 4: {
+        const uint32_t* src = (const uint32_t*)oc.src[c];
+        uint32_t* dst = (uint32_t*)oc.dst[c] + base;
+        for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = build_side ? src[s_b[j]] : src[prow0 + s_p[j]];
+        break;
+      }
+      case 2: {
+        const uint16_t* src = (const uint16_t*)oc.src[c];
+        uint16_t* dst = (uint16_t*)oc.dst[c] + base;
+        for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = build_side ? src[s_b[j]] : src[prow0 + s_p[j]];
+        break;
+      }
+      case 1: {
+        const uint8_t* src = (const uint8_t*)oc.src[c];
+        uint8_t* dst = (uint8_t*)oc.dst[c] + base;
+        for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = build_side ? src[s_b[j]] : src[prow0 + s_p[j]];
+        break;
+      }
+      default: {
+        const uint4* src = (const uint4*)oc.src[c];
+        uint4* dst = (uint4*)oc.dst[c] + base;
+        for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = build_side ? src[s_b[j]] : src[prow0 + s_p[j]];
+        break;
+      }
+    }
   }
 }
 
@@ -479,6 +657,7 @@ static void finish_build(dfgpu_hashjoin* j) {
     j->table.cap = cap;
   }
   if (n > 0) {
+    KernelTimer kt(ctx, "join_build");
     join_build_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(j->build_keys, n, j->table, j->counters.as<unsigned long long>());
     DF_LAUNCH_CHECK(ctx);
   }
@@ -544,10 +723,50 @@ static void push_probe(dfgpu_hashjoin* j, std::vector<DCol>&& cols) {
   // empty / unmatchable build side: build_batch_empty_build_side (utils.rs:1393-1430)
   KeyCols pk;
   make_keycols(cols, j->on_probe, &pk);
+  // ---- fused single-pass path: unique build keys, one output row per matching probe row, plain columns ----
+  if (mode == EMIT_PAIRS && j->unique && !j->opt.force_hash_collisions && j->out_side.size() <= (size_t)kMaxFusedCols) {
+    bool plain = true;
+    for (size_t c = 0; c < j->out_side.size() && plain; ++c) {
+      const DCol& src = j->out_side[c] == 0 ? j->build_cols[j->out_index[c]] : (j->out_side[c] == 1 ? cols[j->out_index[c]] : cols[0]);
+      if (j->out_side[c] == 2 || src.type == DFGPU_BOOL || src.validity) plain = false;
+    }
+    if (plain) {
+      FusedCols oc;
+      memset(&oc, 0, sizeof(oc));
+      oc.n = (int)j->out_side.size();
+      BatchPtr out(new dfgpu_batch());
+      out->ctx = ctx; out->host = false;
+      for (int c = 0; c < oc.n; ++c) {
+        const DCol& src = j->out_side[c] == 0 ? j->build_cols[j->out_index[c]] : cols[j->out_index[c]];
+        DCol d = alloc_col(ctx, src.type, n, false);  // unique build: at most one output row per probe row
+        oc.src[c] = src.values; oc.dst[c] = d.own_values->ptr; oc.width[c] = type_width(src.type); oc.side[c] = j->out_side[c];
+        out->cols.push_back(std::move(d));
+      }
+      const int64_t nt = (n + kFusedTile - 1) / kFusedTile;
+      DevBuf desc(ctx, (size_t)nt * 8 + 32);
+      desc.zero();
+      unsigned long long* totals = (unsigned long long*)((char*)desc.ptr + (size_t)nt * 8);
+      unsigned int* counter = (unsigned int*)(totals + 2);
+      {
+        KernelTimer kt(ctx, "join_probe");
+        join_probe_fused_kernel<<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->table, j->need_visited ? 1 : 0, oc, desc.as<unsigned long long>(), counter, totals);
+        DF_LAUNCH_CHECK(ctx);
+      }
+      unsigned long long h[2];
+      DF_CUDA(cudaMemcpyAsync(h, totals, 16, cudaMemcpyDeviceToHost, ctx->stream));
+      DF_CUDA(cudaStreamSynchronize(ctx->stream));
+      out->rows = (int64_t)h[0];
+      for (auto& c : out->cols) c.length = out->rows;
+      j->m_probe_hits += (int64_t)h[1];
+      if (out->rows > 0) emit_batch(j, std::move(out));
+      return;
+    }
+  }
   const int64_t ntiles = (n + kProbeTile - 1) / kProbeTile;
   DevBuf head(ctx, (size_t)n * 4), cnt, tiles(ctx, (size_t)(ntiles + 1) * 8), hits(ctx, 8);
   hits.zero();
   if (!j->unique) cnt.alloc(ctx, (size_t)n * 4);
+  KernelTimer* ktp = new KernelTimer(ctx, "join_probe");
   if (j->unique)
     join_probe_count_kernel<true><<<(int)ntiles, kProbeThreads, 0, ctx->stream>>>(pk, n, j->table, mode, j->need_visited ? 1 : 0, head.as<uint32_t>(), nullptr,
                                                                                   tiles.as<uint64_t>(), hits.as<unsigned long long>());
@@ -555,6 +774,7 @@ static void push_probe(dfgpu_hashjoin* j, std::vector<DCol>&& cols) {
     join_probe_count_kernel<false><<<(int)ntiles, kProbeThreads, 0, ctx->stream>>>(pk, n, j->table, mode, j->need_visited ? 1 : 0, head.as<uint32_t>(), cnt.as<uint32_t>(),
                                                                                    tiles.as<uint64_t>(), hits.as<unsigned long long>());
   DF_LAUNCH_CHECK(ctx);
+  delete ktp;
   if (mode == EMIT_NONE) {
     j->m_probe_hits += (int64_t)read_scalar<unsigned long long>(ctx, hits.as<unsigned long long>());
     return;

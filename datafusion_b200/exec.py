@@ -1,0 +1,423 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+The reference's operators implement `trait ExecutionPlan` (datafusion/physical-plan/src/execution_plan.rs:102;
+`execute(partition, ctx) -> SendableRecordBatchStream` :696) and are driven by `collect(plan, ctx)` (:1752).
+No Rust toolchain exists in this image, so this module is the Python stand-in for the Rust shim
+(`GpuFilterExec` / `GpuHashJoinExec` / `GpuAggregateExec`): same constructor
+arguments, same output schemas, same error behaviour — all compute goes through the C ABI of
+libdfgpu.so (capi.py); nothing here computes on the CPU.
+
+Data model = pyarrow RecordBatch (crossing the boundary as Arrow C Data Interface structs, exactly as
+datafusion/ffi/src/record_batch_stream.rs:101-167 does).
+"""
+from __future__ import annotations
+
+from typing import Iterable, Iterator, List, Optional, Sequence, Tuple, Union
+
+import pyarrow as pa
+
+from . import capi as D
+
+
+# ---------------------------------------------------------------------------------------------
+# types
+# ---------------------------------------------------------------------------------------------
+def type_id(t: pa.DataType) -> int:
+    m = {pa.bool_(): D.BOOL, pa.int8(): D.INT8, pa.int16(): D.INT16, pa.int32(): D.INT32, pa.int64(): D.INT64,
+         pa.uint8(): D.UINT8, pa.uint16(): D.UINT16, pa.uint32(): D.UINT32, pa.uint64(): D.UINT64,
+         pa.float32(): D.FLOAT32, pa.float64(): D.FLOAT64, pa.date32(): D.DATE32, pa.date64(): D.DATE64}
+    if t in m:
+        return m[t]
+    if pa.types.is_timestamp(t):
+        return D.TIMESTAMP
+    if pa.types.is_decimal128(t):
+        return D.DECIMAL128
+    raise NotImplementedError(f"This feature is not implemented: GPU operators do not support Arrow type {t}")
+
+
+def arrow_type(tid: int) -> pa.DataType:
+    return {D.BOOL: pa.bool_(), D.INT8: pa.int8(), D.INT16: pa.int16(), D.INT32: pa.int32(), D.INT64: pa.int64(), D.UINT8: pa.uint8(),
+            D.UINT16: pa.uint16(), D.UINT32: pa.uint32(), D.UINT64: pa.uint64(), D.FLOAT32: pa.float32(), D.FLOAT64: pa.float64(),
+            D.DATE32: pa.date32(), D.DATE64: pa.date64(), D.TIMESTAMP: pa.timestamp("ns")}[tid]
+
+
+# ---------------------------------------------------------------------------------------------
+# expressions — PhysicalExpr (physical-expr-common/src/physical_expr.rs:76)
+# ---------------------------------------------------------------------------------------------
+class Expr:
+    def _bin(self, op, other):
+        return BinaryExpr(self, op, other if isinstance(other, Expr) else lit(other))
+
+    def __gt__(self, o): return self._bin(D.OP_GT, o)
+    def __ge__(self, o): return self._bin(D.OP_GTEQ, o)
+    def __lt__(self, o): return self._bin(D.OP_LT, o)
+    def __le__(self, o): return self._bin(D.OP_LTEQ, o)
+    def __eq__(self, o): return self._bin(D.OP_EQ, o)  # type: ignore[override]
+    def __ne__(self, o): return self._bin(D.OP_NEQ, o)  # type: ignore[override]
+    def __add__(self, o): return self._bin(D.OP_PLUS, o)
+    def __sub__(self, o): return self._bin(D.OP_MINUS, o)
+    def __mul__(self, o): return self._bin(D.OP_MULTIPLY, o)
+    def __truediv__(self, o): return self._bin(D.OP_DIVIDE, o)
+    def __mod__(self, o): return self._bin(D.OP_MODULO, o)
+    def __and__(self, o): return self._bin(D.OP_AND, o)
+    def __or__(self, o): return self._bin(D.OP_OR, o)
+    def __invert__(self): return UnaryExpr(D.EXPR_NOT, self)
+    def __neg__(self): return UnaryExpr(D.EXPR_NEGATIVE, self)
+    def is_null(self): return UnaryExpr(D.EXPR_IS_NULL, self)
+    def is_not_null(self): return UnaryExpr(D.EXPR_IS_NOT_NULL, self)
+    def is_distinct_from(self, o): return self._bin(D.OP_IS_DISTINCT_FROM, o)
+    def is_not_distinct_from(self, o): return self._bin(D.OP_IS_NOT_DISTINCT_FROM, o)
+    def cast(self, t: pa.DataType): return CastExpr(self, t)
+    __hash__ = None  # type: ignore[assignment]
+
+    def data_type(self, schema: pa.Schema) -> pa.DataType:
+        raise NotImplementedError
+
+    def rpn(self, schema: pa.Schema, out: list) -> None:
+        raise NotImplementedError
+
+
+class Column(Expr):
+    """expressions/column.rs:121"""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def data_type(self, schema): return schema.field(self.name).type
+
+    def rpn(self, schema, out):
+        ix = schema.get_field_index(self.name)
+        if ix < 0:
+            raise KeyError(f"Schema error: No field named {self.name}")
+        out.append((D.EXPR_COLUMN, ix, 0, 0, 0, 0.0))
+
+
+class Literal(Expr):
+    """expressions/literal.rs:106; value None = NULL of the given type"""
+
+    def __init__(self, value, type: Optional[pa.DataType] = None):
+        if type is None:
+            type = pa.bool_() if isinstance(value, bool) else pa.int64() if isinstance(value, int) else pa.float64()
+        self.value, self.type = value, type
+
+    def data_type(self, schema): return self.type
+
+    def rpn(self, schema, out):
+        tid = type_id(self.type)
+        isnull = 1 if self.value is None else 0
+        v = 0 if self.value is None else self.value
+        if tid in (D.FLOAT32, D.FLOAT64):
+            out.append((D.EXPR_LITERAL, 0, tid, isnull, 0, float(v)))
+        else:
+            if hasattr(v, "toordinal") and tid == D.DATE32:
+                import datetime
+                v = (v - datetime.date(1970, 1, 1)).days
+            out.append((D.EXPR_LITERAL, 0, tid, isnull, int(v), 0.0))
+
+
+class BinaryExpr(Expr):
+    """expressions/binary.rs:536-676.  Operand types must already agree (the planner's type coercion);
+    as a convenience an untyped Python literal adopts the other side's type."""
+
+    def __init__(self, left: Expr, op: int, right: Expr):
+        self.left, self.op, self.right = left, op, right
+
+    def _coerced(self, schema):
+        l, r = self.left, self.right
+        if isinstance(r, Literal) and not isinstance(l, Literal):
+            lt = l.data_type(schema)
+            if r.type != lt and (pa.types.is_integer(r.type) or pa.types.is_floating(r.type)) and not pa.types.is_boolean(lt):
+                r = Literal(r.value, lt)
+        elif isinstance(l, Literal) and not isinstance(r, Literal):
+            rt = r.data_type(schema)
+            if l.type != rt and (pa.types.is_integer(l.type) or pa.types.is_floating(l.type)) and not pa.types.is_boolean(rt):
+                l = Literal(l.value, rt)
+        return l, r
+
+    def data_type(self, schema):
+        if self.op in (D.OP_EQ, D.OP_NEQ, D.OP_LT, D.OP_LTEQ, D.OP_GT, D.OP_GTEQ, D.OP_AND, D.OP_OR, D.OP_IS_DISTINCT_FROM,
+                       D.OP_IS_NOT_DISTINCT_FROM):
+            return pa.bool_()
+        return self._coerced(schema)[0].data_type(schema)
+
+    def rpn(self, schema, out):
+        l, r = self._coerced(schema)
+        l.rpn(schema, out)
+        r.rpn(schema, out)
+        out.append((D.EXPR_BINARY, self.op, 0, 0, 0, 0.0))
+
+
+class UnaryExpr(Expr):
+    def __init__(self, kind: int, arg: Expr):
+        self.kind, self.arg = kind, arg
+
+    def data_type(self, schema):
+        return self.arg.data_type(schema) if self.kind == D.EXPR_NEGATIVE else pa.bool_()
+
+    def rpn(self, schema, out):
+        self.arg.rpn(schema, out)
+        out.append((self.kind, 0, 0, 0, 0, 0.0))
+
+
+class CastExpr(Expr):
+    def __init__(self, arg: Expr, to: pa.DataType):
+        self.arg, self.to = arg, to
+
+    def data_type(self, schema): return self.to
+
+    def rpn(self, schema, out):
+        self.arg.rpn(schema, out)
+        out.append((D.EXPR_CAST, 0, type_id(self.to), 0, 0, 0.0))
+
+
+def col(name: str) -> Column: return Column(name)
+def lit(value, type: Optional[pa.DataType] = None) -> Literal: return Literal(value, type)
+
+
+# ---------------------------------------------------------------------------------------------
+# plans
+# ---------------------------------------------------------------------------------------------
+class SessionConfig:
+    """the execution.* keys that change hot-path behaviour (common/src/config.rs:904-923)"""
+
+    def __init__(self, batch_size: int = 8192, perfect_hash_join_small_build_threshold: int = 1024,
+                 perfect_hash_join_min_key_density: float = 0.15, force_hash_collisions: bool = False, device: int = 0):
+        self.batch_size = batch_size
+        self.perfect_hash_join_small_build_threshold = perfect_hash_join_small_build_threshold
+        self.perfect_hash_join_min_key_density = perfect_hash_join_min_key_density
+        self.force_hash_collisions = force_hash_collisions
+        self.device = device
+
+
+class TaskContext:
+    """execution/src/task.rs:52 — owns the dfgpu context (device + stream)"""
+
+    def __init__(self, config: Optional[SessionConfig] = None, ctx: Optional[D.Context] = None):
+        self.config = config or SessionConfig()
+        self.gpu = ctx or D.Context(self.config.device)
+
+
+class ExecutionPlan:
+    schema: pa.Schema
+
+    def children(self) -> List["ExecutionPlan"]: return []
+    def name(self) -> str: return type(self).__name__
+    def execute(self, ctx: TaskContext) -> Iterator[pa.RecordBatch]: raise NotImplementedError
+    def metrics(self) -> dict: return {}
+
+
+class MemoryExec(ExecutionPlan):
+    """TestMemoryExec (physical-plan/src/test.rs): yields the given batches of ONE partition"""
+
+    def __init__(self, batches: Sequence[pa.RecordBatch], schema: Optional[pa.Schema] = None):
+        self.batches = list(batches)
+        self.schema = schema or self.batches[0].schema
+
+    def execute(self, ctx):
+        return iter(self.batches)
+
+
+def _rename(rb: pa.RecordBatch, schema: pa.Schema) -> pa.RecordBatch:
+    cols = []
+    for c, f in zip(rb.columns, schema):
+        cols.append(c if c.type == f.type else c.cast(f.type))
+    return pa.RecordBatch.from_arrays(cols, schema=schema)
+
+
+def _drain(op, schema) -> Iterator[pa.RecordBatch]:
+    while True:
+        b = op.next(host=True)
+        if b is None:
+            return
+        yield _rename(b.to_arrow(), schema)
+
+
+class GpuFilterExec(ExecutionPlan):
+    """FilterExec (physical-plan/src/filter.rs:85): FilterExecBuilder::new(predicate, input).with_projection(..).with_fetch(..)"""
+
+    def __init__(self, predicate: Expr, input: ExecutionPlan, projection: Optional[Sequence[int]] = None, fetch: Optional[int] = None):
+        self.predicate, self.input, self.projection, self.fetch = predicate, input, projection, fetch
+        if predicate.data_type(input.schema) != pa.bool_():
+            # filter.rs:139-145
+            raise ValueError(f"Error during planning: Filter predicate must return BOOLEAN values, got {predicate.data_type(input.schema)}")
+        fields = list(input.schema) if projection is None else [input.schema.field(i) for i in projection]
+        self.schema = pa.schema(fields)
+        self._metrics = {}
+
+    def children(self): return [self.input]
+
+    def execute(self, ctx):
+        nodes: list = []
+        self.predicate.rpn(self.input.schema, nodes)
+        types = [type_id(f.type) for f in self.input.schema]
+        op = D.FilterHandle(ctx.gpu, types, nodes, self.projection, ctx.config.batch_size, -1 if self.fetch is None else self.fetch)
+        try:
+            for rb in self.input.execute(ctx):
+                op.push_arrow(rb)
+                yield from _drain(op, self.schema)
+            op.finish()
+            yield from _drain(op, self.schema)
+            self._metrics = {k: op.metric(k) for k in ("input_rows", "output_rows", "selectivity_num", "selectivity_den")}
+        finally:
+            op.close()
+
+    def metrics(self): return self._metrics
+
+
+_JOIN_TYPES = {"Inner": D.JOIN_INNER, "Left": D.JOIN_LEFT, "Right": D.JOIN_RIGHT, "Full": D.JOIN_FULL, "LeftSemi": D.JOIN_LEFT_SEMI,
+               "RightSemi": D.JOIN_RIGHT_SEMI, "LeftAnti": D.JOIN_LEFT_ANTI, "RightAnti": D.JOIN_RIGHT_ANTI, "LeftMark": D.JOIN_LEFT_MARK,
+               "RightMark": D.JOIN_RIGHT_MARK}
+
+
+def build_join_schema(left: pa.Schema, right: pa.Schema, join_type: str) -> Tuple[pa.Schema, List[Tuple[int, int]]]:
+    """joins/utils.rs build_join_schema: output fields + ColumnIndex (side, index); side 0=left 1=right 2=mark"""
+    def nullable(fields): return [pa.field(f.name, f.type, True) for f in fields]
+    l, r = list(left), list(right)
+    if join_type in ("Inner", "Left", "Right", "Full"):
+        lf = nullable(l) if join_type in ("Right", "Full") else l
+        rf = nullable(r) if join_type in ("Left", "Full") else r
+        return pa.schema(lf + rf), [(0, i) for i in range(len(l))] + [(1, i) for i in range(len(r))]
+    if join_type in ("LeftSemi", "LeftAnti"):
+        return pa.schema(l), [(0, i) for i in range(len(l))]
+    if join_type in ("RightSemi", "RightAnti"):
+        return pa.schema(r), [(1, i) for i in range(len(r))]
+    if join_type == "LeftMark":
+        return pa.schema(l + [pa.field("mark", pa.bool_(), False)]), [(0, i) for i in range(len(l))] + [(2, 0)]
+    if join_type == "RightMark":
+        return pa.schema(r + [pa.field("mark", pa.bool_(), False)]), [(1, i) for i in range(len(r))] + [(2, 0)]
+    raise ValueError(join_type)
+
+
+class GpuHashJoinExec(ExecutionPlan):
+    """HashJoinExec::try_new(left, right, on, filter, join_type, projection, partition_mode, null_equality)
+    (physical-plan/src/joins/hash_join/exec.rs:752).  left = build side, right = probe side."""
+
+    def __init__(self, left: ExecutionPlan, right: ExecutionPlan, on: Sequence[Tuple[str, str]], join_type: str = "Inner",
+                 null_equality: str = "NullEqualsNothing", filter=None, projection: Optional[Sequence[int]] = None):
+        if not on:
+            raise ValueError("Error during planning: On constraints in HashJoinExec should be non-empty")  # exec.rs try_new
+        if filter is not None:
+            raise NotImplementedError("This feature is not implemented: join filters stay on the CPU HashJoinExec")
+        self.left, self.right, self.on, self.join_type, self.null_equality = left, right, list(on), join_type, null_equality
+        full, idx = build_join_schema(left.schema, right.schema, join_type)
+        if projection is not None:
+            full = pa.schema([full.field(i) for i in projection])
+            idx = [idx[i] for i in projection]
+        self.schema, self.column_indices = full, idx
+        self._metrics = {}
+
+    def children(self): return [self.left, self.right]
+
+    def execute(self, ctx):
+        cfg = ctx.config
+        bt = [type_id(f.type) for f in self.left.schema]
+        pt = [type_id(f.type) for f in self.right.schema]
+        ob = [self.left.schema.get_field_index(l) for l, _ in self.on]
+        op_ = [self.right.schema.get_field_index(r) for _, r in self.on]
+        if min(ob + op_) < 0:
+            raise KeyError("Schema error: join key not found")
+        op = D.HashJoinHandle(ctx.gpu, bt, pt, ob, op_, [s for s, _ in self.column_indices], [i for _, i in self.column_indices],
+                              _JOIN_TYPES[self.join_type], D.NULL_EQUALS_NULL if self.null_equality == "NullEqualsNull" else D.NULL_EQUALS_NOTHING,
+                              cfg.batch_size, cfg.perfect_hash_join_small_build_threshold, cfg.perfect_hash_join_min_key_density,
+                              cfg.force_hash_collisions)
+        try:
+            for rb in self.left.execute(ctx):     # collect_left_input
+                op.push_build_arrow(rb)
+            op.finish_build()
+            for rb in self.right.execute(ctx):    # FetchProbeBatch / ProcessProbeBatch
+                op.push_probe_arrow(rb)
+                yield from _drain(op, self.schema)
+            op.finish_probe()                     # ExhaustedProbeSide
+            yield from _drain(op, self.schema)
+            self._metrics = {k: op.metric(k) for k in ("build_input_rows", "input_rows", "output_rows", "array_map_created_count", "probe_hits")}
+        finally:
+            op.close()
+
+    def metrics(self): return self._metrics
+
+
+_AGG_FUNCS = {"sum": D.AGG_SUM, "count": D.AGG_COUNT, "min": D.AGG_MIN, "max": D.AGG_MAX, "avg": D.AGG_AVG, "count_star": D.AGG_COUNT_STAR}
+_AGG_MODES = {"Partial": D.AGG_PARTIAL, "Final": D.AGG_FINAL, "FinalPartitioned": D.AGG_FINAL_PARTITIONED, "Single": D.AGG_SINGLE,
+              "SinglePartitioned": D.AGG_SINGLE_PARTITIONED, "PartialReduce": D.AGG_PARTIAL_REDUCE}
+
+
+class AggregateExpr:
+    """AggregateFunctionExpr: func(arg) [FILTER (WHERE filter)] AS alias"""
+
+    def __init__(self, func: str, arg: Optional[str], alias: Optional[str] = None, filter: Optional[str] = None):
+        self.func, self.arg, self.filter = func.lower(), arg, filter
+        self.alias = alias or f"{func.upper()}({arg or '*'})"
+
+    def value_type(self, t: Optional[pa.DataType]) -> pa.DataType:
+        if self.func in ("count", "count_star"):
+            return pa.int64()
+        if self.func == "avg":
+            return pa.float64()
+        if self.func == "sum":  # Sum::return_type, functions-aggregate/src/sum.rs:232-261
+            return pa.float64() if pa.types.is_floating(t) else pa.uint64() if pa.types.is_unsigned_integer(t) else pa.int64()
+        return t
+
+    def state_fields(self, t: Optional[pa.DataType]) -> List[pa.Field]:
+        if self.func == "avg":  # [count, sum] (aggregates/mod.rs:3591-3700 snapshots)
+            return [pa.field(f"{self.alias}[count]", pa.uint64()), pa.field(f"{self.alias}[sum]", pa.float64())]
+        return [pa.field(f"{self.alias}[{self.func}]", self.value_type(t))]
+
+
+class GpuAggregateExec(ExecutionPlan):
+    """AggregateExec::try_new(mode, group_by, aggr_expr, filter_expr, input, input_schema) (aggregates/mod.rs:930)."""
+
+    def __init__(self, mode: str, group_by: Sequence[str], aggr_expr: Sequence[AggregateExpr], input: ExecutionPlan,
+                 input_schema: Optional[pa.Schema] = None, capacity_hint: int = 0):
+        if not group_by:
+            raise NotImplementedError("This feature is not implemented: aggregation without GROUP BY stays on the CPU AggregateExec")
+        self.mode, self.group_by, self.aggr_expr, self.input = mode, list(group_by), list(aggr_expr), input
+        self.input_schema = input_schema or input.schema  # schema of the RAW input (needed in Final modes for value types)
+        self.capacity_hint = capacity_hint
+        self.state_input = mode in ("Final", "FinalPartitioned", "PartialReduce")
+        self.state_output = mode in ("Partial", "PartialReduce")
+        gfields = [input.schema.field(g) for g in self.group_by]
+        afields: List[pa.Field] = []
+        for a in self.aggr_expr:
+            t = self.input_schema.field(a.arg).type if a.arg is not None else None
+            if self.state_output:
+                afields += a.state_fields(t)
+            else:
+                afields.append(pa.field(a.alias, a.value_type(t)))
+        self.schema = pa.schema([pa.field(f.name, f.type, True) for f in gfields] + afields)
+        self._metrics = {}
+
+    def children(self): return [self.input]
+
+    def execute(self, ctx):
+        isch = self.input.schema
+        types = [type_id(f.type) for f in isch]
+        gcols = [isch.get_field_index(g) for g in self.group_by]
+        aggs = []
+        for a in self.aggr_expr:
+            if self.state_input:
+                aggs.append((_AGG_FUNCS[a.func], -1, -1))
+            else:
+                aggs.append((_AGG_FUNCS[a.func], isch.get_field_index(a.arg) if a.arg is not None else -1,
+                             isch.get_field_index(a.filter) if a.filter else -1))
+        if self.state_input:  # layout contract: [group cols..., state cols...] in order
+            assert gcols == list(range(len(gcols))), "state input must start with the group columns"
+        op = D.AggHandle(ctx.gpu, types, gcols, aggs, _AGG_MODES[self.mode], ctx.config.batch_size, self.capacity_hint)
+        try:
+            for rb in self.input.execute(ctx):
+                op.push_arrow(rb)
+            op.finish()
+            bs = ctx.config.batch_size
+            for rb in _drain(op, self.schema):   # one big batch sliced by batch_size (aggregate_hash_table/common.rs:290)
+                for s in range(0, rb.num_rows, bs):
+                    yield rb.slice(s, bs)
+            self._metrics = {k: op.metric(k) for k in ("num_groups", "input_rows", "output_rows", "rehashes")}
+        finally:
+            op.close()
+
+    def metrics(self): return self._metrics
+
+
+def collect(plan: ExecutionPlan, ctx: Optional[TaskContext] = None) -> List[pa.RecordBatch]:
+    """physical-plan/src/execution_plan.rs:1752"""
+    ctx = ctx or TaskContext()
+    return [b for b in plan.execute(ctx) if b.num_rows > 0]

@@ -138,6 +138,14 @@ int dfgpu_event_record(dfgpu_ctx* ctx, void* ev);
 int dfgpu_event_elapsed_ms(dfgpu_ctx* ctx, void* start, void* stop, float* ms); /* syncs on stop */
 int dfgpu_event_destroy(dfgpu_ctx* ctx, void* ev);
 
+/* optional per-kernel-family CUDA-event timing on the ctx stream (bench.py's roofline numbers):
+ * when enabled, the dominant kernels are bracketed by events; dfgpu_kernel_time returns the
+ * accumulated device time and launch count of one family ("join_probe", "join_build", "agg_update",
+ * "filter_eval", "take", ...). */
+int dfgpu_set_kernel_timing(dfgpu_ctx* ctx, int enabled);
+int dfgpu_kernel_time(dfgpu_ctx* ctx, const char* name, double* total_ms, int64_t* count);
+int dfgpu_kernel_time_reset(dfgpu_ctx* ctx);
+
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 int64_t dfgpu_launch_count(dfgpu_ctx* ctx);
 

@@ -1,0 +1,408 @@
+"""oracle.py — Python face of the CPU restatement oracle (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product path (datafusion_b200/) never does.
+
+* join / group-by / repartition: ctypes over oracle/liboracle.so (oracle.c — each function cites the
+  reference file:line it restates).
+* expressions / FilterExec: numpy restatement of PhysicalExpr::evaluate
+  (physical-expr/src/expressions/binary.rs:536-676, physical-expr-common/src/datum.rs:36-105) and
+  filter_record_batch semantics (physical-plan/src/filter.rs:1339-1445).
+
+Columns are (values: np.ndarray, valid: np.ndarray[bool] | None) pairs.
+PARITY UNPINNED for hash VALUES only (foldhash 0.2 is not restated; outputs do not depend on it).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(_HERE, "liboracle.so")
+Col = Tuple[np.ndarray, Optional[np.ndarray]]
+
+J_INNER, J_LEFT, J_RIGHT, J_FULL, J_LEFT_SEMI, J_RIGHT_SEMI, J_LEFT_ANTI, J_RIGHT_ANTI, J_LEFT_MARK, J_RIGHT_MARK = range(10)
+A_SUM, A_COUNT, A_MIN, A_MAX, A_AVG, A_COUNT_STAR = range(1, 7)
+
+
+def build() -> None:
+    subprocess.check_call(["make", "-C", _HERE, "-s"])
+
+
+_lib = None
+
+
+class _JoinResult(C.Structure):
+    _fields_ = [("build_idx", C.POINTER(C.c_int64)), ("probe_idx", C.POINTER(C.c_int64)), ("mark", C.POINTER(C.c_int8)),
+                ("n", C.c_int64), ("used_array_map", C.c_int)]
+
+
+class _AggIn(C.Structure):
+    _fields_ = [("func", C.c_int), ("is_float", C.c_int), ("arg", C.c_void_p), ("arg_valid", C.c_void_p), ("arg2", C.c_void_p),
+                ("arg2_valid", C.c_void_p), ("filter", C.c_void_p), ("filter_valid", C.c_void_p)]
+
+
+class _GroupResult(C.Structure):
+    _fields_ = [("nkeys", C.c_int), ("naggs", C.c_int), ("ngroups", C.c_int64), ("key_vals", C.POINTER(C.POINTER(C.c_int64))),
+                ("key_valid", C.POINTER(C.POINTER(C.c_uint8))), ("out_i", C.POINTER(C.c_int64) * 8), ("out_f", C.POINTER(C.c_double) * 8),
+                ("out_c", C.POINTER(C.c_uint64) * 8), ("out_valid", C.POINTER(C.c_uint8) * 8)]
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            build()
+        _lib = C.CDLL(LIB)
+        _lib.oracle_bench_join.restype = C.c_double
+        _lib.oracle_bench_groupby.restype = C.c_double
+        _lib.oracle_version.restype = C.c_char_p
+    return _lib
+
+
+def _i64(a) -> np.ndarray:
+    a = np.asarray(a)
+    if a.dtype == np.bool_:
+        return a.astype(np.int64)
+    if a.dtype.kind == "f":
+        return np.ascontiguousarray(a.astype(np.float64)).view(np.int64)
+    if a.dtype == np.uint64:
+        return np.ascontiguousarray(a).view(np.int64)
+    return np.ascontiguousarray(a.astype(np.int64))
+
+
+def _u8(v: Optional[np.ndarray]):
+    return None if v is None else np.ascontiguousarray(np.asarray(v, dtype=bool).astype(np.uint8))
+
+
+def _ptr_array(arrs, ctype):
+    PT = C.POINTER(ctype)
+    out = (PT * max(len(arrs), 1))()
+    for i, a in enumerate(arrs):
+        out[i] = a.ctypes.data_as(PT) if a is not None else PT()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# hash join
+# ---------------------------------------------------------------------------------------------
+def hash_join_indices(build_keys: Sequence[Col], probe_keys: Sequence[Col], join_type: int = J_INNER, null_equals_null: bool = False,
+                      batch_size: int = 8192, phj_threshold: int = 1024, phj_density: float = 0.15, force_collisions: bool = False,
+                      build_batch_rows: Optional[Sequence[int]] = None, probe_batch_rows: Optional[Sequence[int]] = None,
+                      key_is_integer: bool = True):
+    """(build_idx, probe_idx, mark, used_array_map): -1 = NULL index.  Order = the reference's emission order."""
+    L = lib()
+    nk = len(build_keys)
+    nb = len(build_keys[0][0])
+    npr = len(probe_keys[0][0])
+    bk = [_i64(k[0]) for k in build_keys]
+    pk = [_i64(k[0]) for k in probe_keys]
+    bv = [_u8(k[1]) for k in build_keys]
+    pv = [_u8(k[1]) for k in probe_keys]
+    bbr = np.array(build_batch_rows if build_batch_rows is not None else [nb], np.int64)
+    pbr = np.array(probe_batch_rows if probe_batch_rows is not None else [npr], np.int64)
+    assert bbr.sum() == nb and pbr.sum() == npr
+    res = _JoinResult()
+    L.oracle_hash_join(C.c_int(nk), _ptr_array(bk, C.c_int64), _ptr_array(bv, C.c_uint8) if any(v is not None for v in bv) else None,
+                       C.c_int64(nb), bbr.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int(len(bbr)),
+                       _ptr_array(pk, C.c_int64), _ptr_array(pv, C.c_uint8) if any(v is not None for v in pv) else None, C.c_int64(npr),
+                       pbr.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int(len(pbr)), C.c_int(join_type), C.c_int(1 if null_equals_null else 0),
+                       C.c_int64(batch_size), C.c_int64(phj_threshold), C.c_double(phj_density), C.c_int(1 if force_collisions else 0),
+                       C.c_int(1 if key_is_integer else 0), C.byref(res), None)
+    n = res.n
+    if n == 0:
+        b, p, m = np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, bool)
+    else:
+        b = np.ctypeslib.as_array(res.build_idx, (n,)).copy()
+        p = np.ctypeslib.as_array(res.probe_idx, (n,)).copy()
+        m = np.ctypeslib.as_array(res.mark, (n,)).copy().astype(bool)
+    used = bool(res.used_array_map)
+    L.oracle_free_join_result(C.byref(res))
+    return b, p, m, used
+
+
+def take(col: Col, idx: np.ndarray) -> Col:
+    """arrow `take` with nullable indices (-1 -> NULL)"""
+    vals, valid = col
+    vals = np.asarray(vals)
+    safe = np.where(idx >= 0, idx, 0)
+    out = vals[safe] if len(vals) else np.zeros(len(idx), vals.dtype)
+    ov = idx >= 0
+    if valid is not None and len(vals):
+        ov = ov & np.asarray(valid, bool)[safe]
+    out = np.where(ov, out, np.zeros((), vals.dtype)) if len(idx) else out
+    return out, (None if ov.all() else ov)
+
+
+def hash_join(build: Sequence[Col], probe: Sequence[Col], on_build: Sequence[int], on_probe: Sequence[int], out_side: Sequence[int],
+              out_index: Sequence[int], **kw) -> List[Col]:
+    """Materialised join output (build_batch_from_indices, joins/utils.rs:1332-1387)."""
+    b, p, m, _ = hash_join_indices([build[i] for i in on_build], [probe[i] for i in on_probe], **kw)
+    jt = kw.get("join_type", J_INNER)
+    out = []
+    for side, ix in zip(out_side, out_index):
+        if side == 2:
+            out.append((m.copy(), None))
+        elif side == 0:
+            out.append(take(build[ix], b))
+        else:
+            out.append(take(probe[ix], p))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# group by
+# ---------------------------------------------------------------------------------------------
+def group_by(keys: Sequence[Col], aggs: Sequence[tuple], merge: bool = False, batch_size: int = 8192, force_collisions: bool = False):
+    """aggs: [(func, arg: Col | None, filter: Col | None)]   (merge: [(func, state_col(s)...)] with arg = count/sum state;
+    AVG merge passes arg=(count col) and a 4th element (sum col)).
+    Returns (group key columns in FIRST-SEEN order, [per aggregate dict(i=, f=, c=, valid=)])."""
+    L = lib()
+    nk = len(keys)
+    n = len(keys[0][0]) if nk else 0
+    kv = [_i64(k[0]) for k in keys]
+    kval = [_u8(k[1]) for k in keys]
+    kfloat = np.array([1 if np.asarray(k[0]).dtype.kind == "f" else 0 for k in keys], np.int32)
+    keep = []
+    ains = (_AggIn * max(len(aggs), 1))()
+    for i, ag in enumerate(aggs):
+        func, arg, filt = ag[0], ag[1], ag[2] if len(ag) > 2 else None
+        a = ains[i]
+        a.func = func
+        if arg is not None:
+            vals = np.asarray(arg[0])
+            if vals.dtype.kind == "f":
+                av = np.ascontiguousarray(vals.astype(np.float64)); a.is_float = 1
+            elif vals.dtype == np.uint64:
+                av = np.ascontiguousarray(vals); a.is_float = 2
+            else:
+                av = np.ascontiguousarray(vals.astype(np.int64)); a.is_float = 0
+            vv = _u8(arg[1])
+            keep += [av, vv]
+            a.arg = av.ctypes.data
+            a.arg_valid = vv.ctypes.data if vv is not None else None
+        if len(ag) > 3 and ag[3] is not None:  # AVG merge: sum column
+            sv = np.ascontiguousarray(np.asarray(ag[3][0]).astype(np.float64)); svv = _u8(ag[3][1])
+            keep += [sv, svv]
+            a.arg2 = sv.ctypes.data
+            a.arg2_valid = svv.ctypes.data if svv is not None else None
+            a.is_float = 1
+        if filt is not None:
+            fv = _u8(filt[0]); fvv = _u8(filt[1])
+            keep += [fv, fvv]
+            a.filter = fv.ctypes.data
+            a.filter_valid = fvv.ctypes.data if fvv is not None else None
+    res = _GroupResult()
+    L.oracle_group_by(C.c_int(nk), _ptr_array(kv, C.c_int64), _ptr_array(kval, C.c_uint8) if any(v is not None for v in kval) else None,
+                      kfloat.ctypes.data_as(C.POINTER(C.c_int)), C.c_int64(n), C.c_int(len(aggs)), ains, C.c_int(1 if merge else 0),
+                      C.c_int64(batch_size), C.c_int(1 if force_collisions else 0), C.byref(res))
+    ng = res.ngroups
+    out_keys = []
+    for c in range(nk):
+        vals = np.ctypeslib.as_array(res.key_vals[c], (max(ng, 1),))[:ng].copy()
+        valid = np.ctypeslib.as_array(res.key_valid[c], (max(ng, 1),))[:ng].copy().astype(bool)
+        src = np.asarray(keys[c][0])
+        if src.dtype.kind == "f":
+            vals = vals.view(np.float64).astype(src.dtype)
+        elif src.dtype == np.bool_:
+            vals = vals.astype(bool)
+        else:
+            vals = vals.astype(src.dtype) if src.dtype != np.uint64 else vals.view(np.uint64)
+        out_keys.append((vals, None if valid.all() else valid))
+    out_aggs = []
+    for a in range(len(aggs)):
+        out_aggs.append(dict(
+            i=np.ctypeslib.as_array(res.out_i[a], (max(ng, 1),))[:ng].copy(),
+            f=np.ctypeslib.as_array(res.out_f[a], (max(ng, 1),))[:ng].copy(),
+            c=np.ctypeslib.as_array(res.out_c[a], (max(ng, 1),))[:ng].copy(),
+            valid=np.ctypeslib.as_array(res.out_valid[a], (max(ng, 1),))[:ng].copy().astype(bool)))
+    L.oracle_free_group_result(C.byref(res))
+    return out_keys, out_aggs
+
+
+def agg_output_columns(func: int, r: dict, arg_dtype, state: bool) -> List[Col]:
+    """Shape one aggregate's oracle result like AggregateExec's output (state() or evaluate())."""
+    def nv(v):
+        return None if v.all() else v
+    if func == A_SUM:
+        if np.dtype(arg_dtype).kind == "f":
+            return [(r["f"], nv(r["valid"]))]
+        if np.dtype(arg_dtype).kind == "u":
+            return [(r["i"].view(np.uint64), nv(r["valid"]))]
+        return [(r["i"], nv(r["valid"]))]
+    if func in (A_COUNT, A_COUNT_STAR):
+        return [(r["c"].astype(np.int64), None)]
+    if func in (A_MIN, A_MAX):
+        if np.dtype(arg_dtype).kind == "f":
+            return [(r["f"].astype(arg_dtype), nv(r["valid"]))]
+        if np.dtype(arg_dtype) == np.uint64:
+            return [(r["i"].view(np.uint64), nv(r["valid"]))]
+        return [(r["i"].astype(arg_dtype), nv(r["valid"]))]
+    if func == A_AVG:
+        if state:
+            return [(r["c"].astype(np.uint64), None), (r["f"], None)]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return [(np.where(r["c"] > 0, r["f"] / np.maximum(r["c"], 1), 0.0), nv(r["c"] > 0))]
+    raise ValueError(func)
+
+
+# ---------------------------------------------------------------------------------------------
+# expressions (numpy)
+# ---------------------------------------------------------------------------------------------
+(E_COLUMN, E_LITERAL, E_BINARY, E_NOT, E_IS_NULL, E_IS_NOT_NULL, E_NEGATIVE, E_CAST) = range(1, 9)
+(OP_EQ, OP_NEQ, OP_LT, OP_LTEQ, OP_GT, OP_GTEQ, OP_PLUS, OP_MINUS, OP_MULTIPLY, OP_DIVIDE, OP_MODULO, OP_AND, OP_OR,
+ OP_IS_DISTINCT_FROM, OP_IS_NOT_DISTINCT_FROM, OP_BITAND, OP_BITOR, OP_BITXOR, OP_SHIFT_LEFT, OP_SHIFT_RIGHT) = range(1, 21)
+
+
+class ArrowDivideByZero(ArithmeticError):
+    pass
+
+
+def _total_order_key(x: np.ndarray) -> np.ndarray:
+    """IEEE-754 totalOrder as a sortable int64, after -0.0 -> +0.0 (datum.rs:88-105)"""
+    x = np.asarray(x, dtype=np.float64).copy()
+    x[x == 0] = 0.0
+    b = x.view(np.int64)
+    return b ^ ((b >> 63).astype(np.uint64) >> np.uint64(1)).astype(np.int64)
+
+
+def eval_expr(cols: Sequence[Col], nodes: Sequence[tuple], col_dtypes: Optional[Sequence] = None) -> Col:
+    """nodes: [(kind, a, np dtype or None, is_null, lit)] in post-order; returns (values, valid)."""
+    n = len(cols[0][0]) if cols else 0
+    st: List[Col] = []
+    for kind, a, dt, is_null, lit in nodes:
+        if kind == E_COLUMN:
+            v, val = cols[a]
+            st.append((np.asarray(v), None if val is None else np.asarray(val, bool)))
+        elif kind == E_LITERAL:
+            arr = np.full(n, 0 if is_null else lit, dtype=dt)
+            st.append((arr, np.zeros(n, bool) if is_null else None))
+        elif kind == E_BINARY:
+            (rv, rval), (lv, lval) = st.pop(), st.pop()
+            both = None
+            if lval is not None or rval is not None:
+                both = (np.ones(n, bool) if lval is None else lval) & (np.ones(n, bool) if rval is None else rval)
+            if a in (OP_AND, OP_OR):  # Kleene (binary.rs:1093-1116)
+                lt = lv.astype(bool) & (lval if lval is not None else True)
+                lf = ~lv.astype(bool) & (lval if lval is not None else True)
+                rt = rv.astype(bool) & (rval if rval is not None else True)
+                rf = ~rv.astype(bool) & (rval if rval is not None else True)
+                if a == OP_AND:
+                    res_t, res_f = lt & rt, lf | rf
+                else:
+                    res_t, res_f = lt | rt, lf & rf
+                valid = res_t | res_f
+                st.append((res_t, None if valid.all() else valid))
+            elif a in (OP_EQ, OP_NEQ, OP_LT, OP_LTEQ, OP_GT, OP_GTEQ, OP_IS_DISTINCT_FROM, OP_IS_NOT_DISTINCT_FROM):
+                if lv.dtype.kind == "f":
+                    x, y = _total_order_key(lv), _total_order_key(rv)
+                else:
+                    x, y = lv, rv
+                if a in (OP_IS_DISTINCT_FROM, OP_IS_NOT_DISTINCT_FROM):
+                    lvv = np.ones(n, bool) if lval is None else lval
+                    rvv = np.ones(n, bool) if rval is None else rval
+                    distinct = (lvv != rvv) | (lvv & rvv & (x != y))
+                    st.append((distinct if a == OP_IS_DISTINCT_FROM else ~distinct, None))
+                else:
+                    r = {OP_EQ: x == y, OP_NEQ: x != y, OP_LT: x < y, OP_LTEQ: x <= y, OP_GT: x > y, OP_GTEQ: x >= y}[a]
+                    if both is not None:
+                        r = r & both
+                    st.append((r, both))
+            else:
+                dtp = lv.dtype
+                act = np.ones(n, bool) if both is None else both
+                with np.errstate(all="ignore"):
+                    if dtp.kind == "f":
+                        if a == OP_PLUS: r = lv + rv
+                        elif a == OP_MINUS: r = lv - rv
+                        elif a == OP_MULTIPLY: r = lv * rv
+                        elif a == OP_DIVIDE: r = lv / rv
+                        elif a == OP_MODULO: r = np.fmod(lv, rv)
+                        else: raise ValueError(a)
+                    else:
+                        if a in (OP_DIVIDE, OP_MODULO):
+                            if np.any(act & (rv == 0)):
+                                raise ArrowDivideByZero("Divide by zero error")
+                            safe = np.where(rv == 0, 1, rv)
+                            if dtp.kind == "i":  # truncating division like Rust
+                                q = (np.abs(lv.astype(np.int64)) // np.abs(safe.astype(np.int64))) * np.sign(lv.astype(np.int64)) * np.sign(safe.astype(np.int64))
+                                r = q if a == OP_DIVIDE else lv.astype(np.int64) - q * safe.astype(np.int64)
+                                r = r.astype(dtp)
+                            else:
+                                r = (lv // safe) if a == OP_DIVIDE else (lv % safe)
+                        elif a == OP_PLUS: r = lv + rv   # numpy integer arrays wrap
+                        elif a == OP_MINUS: r = lv - rv
+                        elif a == OP_MULTIPLY: r = lv * rv
+                        elif a == OP_BITAND: r = lv & rv
+                        elif a == OP_BITOR: r = lv | rv
+                        elif a == OP_BITXOR: r = lv ^ rv
+                        elif a == OP_SHIFT_LEFT: r = np.where(rv.astype(np.uint64) < dtp.itemsize * 8, lv << (rv % (dtp.itemsize * 8)), 0).astype(dtp)
+                        elif a == OP_SHIFT_RIGHT: r = np.where(rv.astype(np.uint64) < dtp.itemsize * 8, lv >> (rv % (dtp.itemsize * 8)), lv >> (dtp.itemsize * 8 - 1) if dtp.kind == "i" else 0).astype(dtp)
+                        else: raise ValueError(a)
+                if both is not None:
+                    r = np.where(both, r, np.zeros((), r.dtype))
+                st.append((r.astype(dtp), both))
+        elif kind == E_NOT:
+            v, val = st.pop()
+            r = ~v.astype(bool)
+            st.append((r & val if val is not None else r, val))
+        elif kind == E_IS_NULL:
+            v, val = st.pop()
+            st.append((np.zeros(n, bool) if val is None else ~val, None))
+        elif kind == E_IS_NOT_NULL:
+            v, val = st.pop()
+            st.append((np.ones(n, bool) if val is None else val.copy(), None))
+        elif kind == E_NEGATIVE:
+            v, val = st.pop()
+            with np.errstate(all="ignore"):
+                st.append((-v, val))
+        elif kind == E_CAST:
+            v, val = st.pop()
+            with np.errstate(all="ignore"):
+                st.append((v.astype(dt), val))
+        else:
+            raise ValueError(kind)
+    assert len(st) == 1
+    return st[0]
+
+
+def filter_batch(cols: Sequence[Col], pred: Col, projection: Optional[Sequence[int]] = None) -> List[Col]:
+    """filter_record_batch: keep rows whose predicate is TRUE and non-NULL (filter.rs:1339-1361)."""
+    pv, pval = pred
+    keep = pv.astype(bool) & (pval if pval is not None else True)
+    proj = range(len(cols)) if projection is None else projection
+    out = []
+    for i in proj:
+        v, val = cols[i]
+        nv = None if val is None else np.asarray(val, bool)[keep]
+        out.append((np.asarray(v)[keep], None if nv is None or nv.all() else nv))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline timing (bench.py only)
+# ---------------------------------------------------------------------------------------------
+def generate_i64(kind: int, seed: int, a: int, b: int, n: int, threads: int = 1) -> np.ndarray:
+    out = np.empty(n, np.int64)
+    lib().oracle_generate_i64(C.c_int(kind), C.c_uint64(seed), C.c_int64(a), C.c_int64(b), C.c_int64(n), C.c_int(threads),
+                              out.ctypes.data_as(C.POINTER(C.c_int64)))
+    return out
+
+
+def bench_join(bk, bp, pk, pp, threads: int, batch_size: int = 8192, use_amap_rule: bool = True):
+    out = (C.c_uint64 * 2)()
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+    secs = lib().oracle_bench_join(p(bk), p(bp), C.c_int64(len(bk)), p(pk), p(pp), C.c_int64(len(pk)), C.c_int(threads), C.c_int64(batch_size),
+                                   C.c_int(1 if use_amap_rule else 0), out)
+    return secs, int(out[0]), int(out[1])
+
+
+def bench_groupby(g, v, threads: int, batch_size: int = 8192):
+    out = (C.c_uint64 * 2)()
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+    secs = lib().oracle_bench_groupby(p(g), p(v), C.c_int64(len(g)), C.c_int(threads), C.c_int64(batch_size), out)
+    return secs, int(out[0]), int(out[1])

@@ -1,0 +1,61 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/dfgpu.h declares; the product path fails loudly without a CUDA device (no CPU fallback)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from datafusion_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "dfgpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dfgpu_\w+)\s*\(", text)))
+
+
+def test_header_declares_what_binding_lists():
+    assert header_symbols() == sorted(capi.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load_library()
+    missing = [s for s in header_symbols() if not hasattr(lib, s)]
+    assert not missing, f"libdfgpu.so lacks {missing}"
+    assert b"sm_100a" in lib.dfgpu_version()
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", capi.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_oracle_linked_into_product():
+    out = subprocess.run(["nm", "-D", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle_" not in out
+    src = ""
+    for dp, _, fs in os.walk(os.path.join(ROOT, "datafusion_b200")):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src += open(os.path.join(dp, f)).read()
+    assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), "product code must not import the oracle"
+
+
+@pytest.mark.skipif(capi.load_library().dfgpu_device_count() > 0, reason="a GPU is present")
+def test_fails_loudly_without_gpu():
+    with pytest.raises(capi.DfgpuError):
+        capi.Context(0)
+
+
+def test_default_join_options_match_reference_config():
+    # config.rs:904 (batch_size 8192), :913 (threshold 1024), :923 (density 0.15)
+    import ctypes as C
+    opt = capi.HashJoinOptions()
+    capi.load_library().dfgpu_hashjoin_default_options(C.byref(opt))
+    assert (opt.batch_size, opt.perfect_hash_join_small_build_threshold) == (8192, 1024)
+    assert abs(opt.perfect_hash_join_min_key_density - 0.15) < 1e-12
+    assert opt.join_type == capi.JOIN_INNER and opt.null_equality == capi.NULL_EQUALS_NOTHING

@@ -1,0 +1,92 @@
+"""world_size-2 CPU (gloo) test of the N>1 host logic: per-destination counts exchange + all-to-all-v per
+column + local join must reproduce the global join (the exchange of RepartitionExec, repartition/mod.rs:1097-1145)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _partition_ids(keys: np.ndarray, n_parts: int) -> np.ndarray:
+    from oracle import oracle as O  # noqa: F401  (hash choice is irrelevant to the result; use a simple mixer)
+    k = keys.astype(np.uint64)
+    h = (k ^ (k >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    h ^= h >> np.uint64(27)
+    return (h % np.uint64(n_parts)).astype(np.int64)
+
+
+def _worker(rank, world, port, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from datafusion_b200 import exchange
+    from oracle import oracle as O
+    rng = np.random.default_rng(100 + rank)
+    nb, npr = 4000, 30000
+    # rank-local shards of both tables (global keys overlap across ranks)
+    bk = (np.arange(nb, dtype=np.int64) * world + rank) * 7 - 3
+    bp = rng.integers(0, 1 << 40, nb).astype(np.int64)
+    pk = rng.integers(0, nb * world, npr).astype(np.int64) * 7 - 3
+    pp = np.arange(npr, dtype=np.int64) + rank * 10**9
+
+    def exchange_cpu(cols, key):
+        pid = _partition_ids(cols[key], world)
+        order = np.argsort(pid, kind="stable")             # stable: rows keep input order inside each partition
+        send_counts = np.bincount(pid, minlength=world).tolist()
+        recv_counts = exchange.exchange_counts(dist, send_counts, torch.device("cpu"))
+        sc, rc, so, ro = exchange.plan_all_to_all(send_counts, recv_counts)
+        assert so[-1] == len(cols[0]) and ro[-1] == sum(recv_counts)
+        sent = [torch.from_numpy(np.ascontiguousarray(c[order])) for c in cols]
+        got = exchange.all_to_all_columns(dist, sent, sc, rc)
+        return [g.numpy() for g in got], rc
+
+    (rbk, rbp), _ = exchange_cpu([bk, bp], 0)
+    (rpk, rpp), rc = exchange_cpu([pk, pp], 0)
+    assert (_partition_ids(rbk, world) == rank).all() and (_partition_ids(rpk, world) == rank).all()   # co-partitioned
+    # inside every source block the original order is preserved
+    start = 0
+    for src, n in enumerate(rc):
+        blk = rpp[start:start + n] - src * 10**9
+        assert (np.diff(blk) > 0).all()
+        start += n
+    bi, pi, _, _ = O.hash_join_indices([(rbk, None)], [(rpk, None)])
+    local = np.stack([rbk[bi], rbp[bi], rpp[pi]], axis=1) if len(bi) else np.zeros((0, 3), np.int64)
+    out_q.put((rank, bk, bp, pk, pp, local))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_exchange_then_local_join_equals_global_join():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    from oracle import oracle as O
+    bk = np.concatenate([r[1] for r in res]); bp = np.concatenate([r[2] for r in res])
+    pk = np.concatenate([r[3] for r in res]); pp = np.concatenate([r[4] for r in res])
+    bi, pi, _, _ = O.hash_join_indices([(bk, None)], [(pk, None)])
+    glob = np.stack([bk[bi], bp[bi], pp[pi]], axis=1)
+    loc = np.concatenate([r[5] for r in res])
+    assert len(glob) == len(loc) > 0
+    assert np.array_equal(glob[np.lexsort(glob.T[::-1])], loc[np.lexsort(loc.T[::-1])])
+
+
+def test_plan_all_to_all_offsets():
+    from datafusion_b200 import exchange
+    sc, rc, so, ro = exchange.plan_all_to_all([3, 0, 5], [1, 2, 0])
+    assert so.tolist() == [0, 3, 3, 8] and ro.tolist() == [0, 1, 3, 3]

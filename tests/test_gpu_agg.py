@@ -1,0 +1,148 @@
+"""Parity of the CUDA AggregateExec path with the reference (golden KATs + oracle).  Group order is
+unspecified (the reference's is first-seen per partition): rows are compared sorted, as the
+reference's own aggregate fuzzers do (aggregation_fuzzer/mod.rs:59-86).  Integers: bit-exact;
+float SUM/AVG: 1e-9 relative (accumulation order differs)."""
+import numpy as np
+import pytest
+
+from datafusion_b200 import capi as D
+from oracle import oracle as O
+from harness import assert_cols_equal, col_from_list, gpu_group_by, load_golden
+
+pytestmark = pytest.mark.gpu
+MISC = load_golden("misc_kat.json")
+F = {O.A_SUM: D.AGG_SUM, O.A_COUNT: D.AGG_COUNT, O.A_MIN: D.AGG_MIN, O.A_MAX: D.AGG_MAX, O.A_AVG: D.AGG_AVG, O.A_COUNT_STAR: D.AGG_COUNT_STAR}
+
+
+def oracle_table(keys, aggs, arg_dtypes, state=False, **kw):
+    ok, res = O.group_by(keys, aggs, **kw)
+    cols = list(ok)
+    for (func, *_), r, dt in zip(aggs, res, arg_dtypes):
+        cols += O.agg_output_columns(func, r, dt, state)
+    return cols
+
+
+def close_cols(got, exp, float_cols):
+    g = [c for i, c in enumerate(got) if i not in float_cols]; e = [c for i, c in enumerate(exp) if i not in float_cols]
+    order_g = np.lexsort([np.asarray(c[0]).astype(np.float64) for c in g[::-1]]) if g else None
+    order_e = np.lexsort([np.asarray(c[0]).astype(np.float64) for c in e[::-1]]) if e else None
+    assert_cols_equal(g, e, ordered=False)
+    for i in float_cols:
+        a, b = np.asarray(got[i][0])[order_g], np.asarray(exp[i][0])[order_e]
+        assert np.allclose(a, b, rtol=1e-9, atol=1e-9), f"float column {i}"
+
+
+def test_gpu_aggregate_some_data(gpu_ctx):
+    m = MISC["aggregate_some_data"]
+    a = np.concatenate([np.array(b["a"], np.uint32) for b in m["batches"]]); v = np.concatenate([np.array(b["b"], np.float64) for b in m["batches"]])
+    part = gpu_group_by(gpu_ctx, [(a, None), (v, None)], [0], [(D.AGG_AVG, 1, -1)], mode=D.AGG_PARTIAL, batch_rows=4)
+    o = np.argsort(part[0][0])
+    assert part[0][0][o].tolist() == m["partial"]["a"] and part[1][0][o].tolist() == m["partial"]["count"] and part[2][0][o].tolist() == m["partial"]["sum"]
+    # Final over two identical partitions of partial state (check_aggregates, aggregates/mod.rs:3660-3700)
+    st = [(np.concatenate([c[0], c[0]]), None) for c in part]
+    fin = gpu_group_by(gpu_ctx, st, [0], [(D.AGG_AVG, -1, -1)], mode=D.AGG_FINAL, types=[D.UINT32, D.UINT64, D.FLOAT64])
+    o = np.argsort(fin[0][0])
+    assert fin[0][0][o].tolist() == m["final_avg"]["a"] and fin[1][0][o].tolist() == m["final_avg"]["avg"]
+
+
+def test_gpu_sum_count_null_state_and_wrapping(gpu_ctx):
+    m = MISC["sum_null_state"]
+    g = np.array(m["g"] + m["second_batch"]["g"], np.int64)
+    v = col_from_list(m["v"] + m["second_batch"]["v"], np.int64)
+    got = gpu_group_by(gpu_ctx, [(g, None), v], [0], [(D.AGG_SUM, 1, -1), (D.AGG_COUNT, 1, -1)], batch_rows=len(m["g"]))
+    o = np.argsort(got[0][0])
+    exp = m["expected"]
+    assert got[0][0][o].tolist() == exp["g"]
+    sums = [None if (got[1][1] is not None and not got[1][1][i]) else int(got[1][0][i]) for i in o]
+    assert sums == exp["sum"] and got[2][0][o].tolist() == exp["count"] and got[2][1] is None
+
+
+@pytest.mark.parametrize("n,groups,null_frac", [(50_000, 300, 0.0), (200_000, 50_000, 0.07), (1_000_000, 400_000, 0.0)])
+def test_gpu_vs_oracle_single_key(gpu_ctx, n, groups, null_frac):
+    rng = np.random.default_rng(n + groups)
+    k = (rng.integers(0, groups, n) * 104729 - 17).astype(np.int64)
+    kv = None if null_frac == 0 else rng.random(n) >= null_frac / 2       # NULL group keys form one group (primitive.rs:144-148)
+    v = rng.integers(-2**62, 2**62, n).astype(np.int64)                    # sums wrap (sum.rs:316)
+    vv = None if null_frac == 0 else rng.random(n) >= null_frac
+    f = rng.standard_normal(n)
+    filt = (rng.random(n) > 0.3, None if null_frac == 0 else rng.random(n) > 0.1)
+    cols = [(k, kv), (v, vv), (f, vv), filt]
+    aggs = [(O.A_SUM, (v, vv), None), (O.A_COUNT, (v, vv), None), (O.A_MIN, (v, vv), None), (O.A_MAX, (v, vv), None), (O.A_AVG, (f, vv), None),
+            (O.A_SUM, (v, vv), filt), (O.A_COUNT_STAR, None, None)]
+    exp = oracle_table([(k, kv)], aggs, [np.int64, np.int64, np.int64, np.int64, np.float64, np.int64, np.int64])
+    gaggs = [(D.AGG_SUM, 1, -1), (D.AGG_COUNT, 1, -1), (D.AGG_MIN, 1, -1), (D.AGG_MAX, 1, -1), (D.AGG_AVG, 2, -1), (D.AGG_SUM, 1, 3), (D.AGG_COUNT_STAR, -1, -1)]
+    for batch_rows, device in ((8192, False), (None, True)):
+        got = gpu_group_by(gpu_ctx, cols, [0], gaggs, batch_rows=batch_rows, device=device)
+        close_cols(got, exp, float_cols=[5])
+
+
+def test_gpu_multi_column_keys_and_128bit(gpu_ctx):
+    # TPC-H Q3 group key shape: (l_orderkey int64, o_orderdate date32, o_shippriority int32) = 128 bits
+    rng = np.random.default_rng(21)
+    n = 300_000
+    k1 = rng.integers(-2**62, 2**62, 20000).astype(np.int64)[rng.integers(0, 20000, n)]
+    k2 = rng.integers(8000, 8010, n).astype(np.int32); k3 = rng.integers(0, 2, n).astype(np.int32)
+    v = rng.integers(0, 10**9, n).astype(np.int64)
+    exp = oracle_table([(k1, None), (k2, None), (k3, None)], [(O.A_SUM, (v, None), None), (O.A_COUNT, (v, None), None)], [np.int64, np.int64])
+    got, h = gpu_group_by(gpu_ctx, [(k1, None), (k2, None), (k3, None), (v, None)], [0, 1, 2], [(D.AGG_SUM, 3, -1), (D.AGG_COUNT, 3, -1)],
+                          types=[D.INT64, D.DATE32, D.INT32, D.INT64], return_handle=True)
+    assert h.metric("key_words") == 2
+    h.close()
+    assert_cols_equal(got, exp, ordered=False)
+    # nullable two-column key (null flags live in the key): (NULL, 1) and (NULL, 2) are different groups
+    a = col_from_list([1, None, None, 1, None, 2], np.int32); b = col_from_list([1, 1, 2, 1, 1, None], np.int32)
+    vv = (np.arange(6, dtype=np.int64), None)
+    exp = oracle_table([a, b], [(O.A_SUM, vv, None)], [np.int64])
+    got = gpu_group_by(gpu_ctx, [a, b, vv], [0, 1], [(D.AGG_SUM, 2, -1)])
+    assert_cols_equal(got, exp, ordered=False)
+
+
+def test_gpu_partial_then_final_equals_single(gpu_ctx):
+    # Partial -> (exchange) -> Final merge must equal Single (aggregates/mod.rs:28-48)
+    rng = np.random.default_rng(8)
+    n = 400_000
+    k = rng.integers(0, 30_000, n).astype(np.int64); v = rng.integers(-10**12, 10**12, n).astype(np.int64); vv = rng.random(n) > 0.05
+    cols = [(k, None), (v, vv)]
+    aggs = [(D.AGG_SUM, 1, -1), (D.AGG_COUNT, 1, -1), (D.AGG_MIN, 1, -1), (D.AGG_MAX, 1, -1)]
+    single = gpu_group_by(gpu_ctx, cols, [0], aggs)
+    parts = [gpu_group_by(gpu_ctx, [(k[s:e], None), (v[s:e], vv[s:e])], [0], aggs, mode=D.AGG_PARTIAL) for s, e in ((0, 150_000), (150_000, 400_000))]
+    merged_in = []
+    for c in range(5):
+        vals = np.concatenate([p[c][0] for p in parts])
+        valid = np.concatenate([np.ones(len(p[c][0]), bool) if p[c][1] is None else p[c][1] for p in parts])
+        merged_in.append((vals, None if valid.all() else valid))
+    final = gpu_group_by(gpu_ctx, merged_in, [0], [(f, -1, -1) for f, _, _ in aggs], mode=D.AGG_FINAL)
+    assert_cols_equal(final, single, ordered=False)
+
+
+def test_gpu_table_growth_and_float_keys(gpu_ctx):
+    rng = np.random.default_rng(4)
+    n = 1_500_000
+    k = rng.permutation(n).astype(np.int64)            # every row its own group: forces overflow replay + rehash from 64K slots
+    v = np.ones(n, np.int64)
+    got, h = gpu_group_by(gpu_ctx, [(k, None), (v, None)], [0], [(D.AGG_SUM, 1, -1)], return_handle=True)
+    assert h.metric("num_groups") == n and h.metric("rehashes") >= 1
+    h.close()
+    assert np.array_equal(np.sort(got[0][0]), np.arange(n)) and (got[1][0] == 1).all()
+    fk = np.array([0.0, -0.0, 1.5, np.nan, np.nan, -0.0], np.float64)   # -0.0 folds into +0.0; NaN groups by bits (primitive.rs:75-98)
+    exp = oracle_table([(fk, None)], [(O.A_COUNT_STAR, None, None)], [np.int64])
+    got = gpu_group_by(gpu_ctx, [(fk, None)], [0], [(D.AGG_COUNT_STAR, -1, -1)])
+    assert_cols_equal(got, exp, ordered=False)
+
+
+def test_gpu_large_groupby_properties(gpu_ctx):
+    """BASELINE config C3 scaled (100M rows here, 1M groups; bench.py/scripts run 1B): checksum of the
+    group table against the oracle's Partial->Final multi-threaded run over the same generators."""
+    ctx = gpu_ctx
+    n, g = 100_000_000, 1_000_000
+    k = ctx.generate_i64(D.GEN_UNIFORM, 5, 0, g, 0, n); v = ctx.generate_i64(D.GEN_UNIFORM, 6, -2**31, 2**32, 0, n)
+    a = D.AggHandle(ctx, [D.INT64, D.INT64], [0], [(D.AGG_SUM, 1, -1), (D.AGG_COUNT, 1, -1)], capacity_hint=g)
+    a.push_device([D.DeviceColumn(ctx, D.INT64, n, k), D.DeviceColumn(ctx, D.INT64, n, v)]); a.finish()
+    outs = a.drain(host=True)
+    gk = np.concatenate([o.column_numpy(0)[0] for o in outs]); gs = np.concatenate([o.column_numpy(1)[0] for o in outs]); gc = np.concatenate([o.column_numpy(2)[0] for o in outs])
+    assert len(gk) == g and int(gc.sum()) == n and len(np.unique(gk)) == g
+    hk = O.generate_i64(1, 5, 0, g, n, 8); hv = O.generate_i64(1, 6, -2**31, 2**32, n, 8)
+    secs, groups, chk = O.bench_groupby(hk, hv, threads=8)
+    mine = int(gk.view(np.uint64).sum(dtype=np.uint64) * np.uint64(3) + gs.view(np.uint64).sum(dtype=np.uint64) * np.uint64(5) + gc.view(np.uint64).sum(dtype=np.uint64) * np.uint64(7))
+    assert groups == g and mine % 2**64 == chk
+    a.close()

@@ -1,0 +1,132 @@
+"""Parity of the CUDA FilterExec / PhysicalExpr::evaluate path with the numpy restatement oracle."""
+import numpy as np
+import pytest
+
+from datafusion_b200 import capi as D
+from oracle import oracle as O
+from harness import assert_cols_equal, col_from_list, gpu_filter, load_golden
+
+pytestmark = pytest.mark.gpu
+MISC = load_golden("misc_kat.json")
+NP2T = {np.dtype(np.int32): D.INT32, np.dtype(np.int64): D.INT64, np.dtype(np.float64): D.FLOAT64, np.dtype(np.float32): D.FLOAT32,
+        np.dtype(np.bool_): D.BOOL, np.dtype(np.uint32): D.UINT32, np.dtype(np.int8): D.INT8, np.dtype(np.uint64): D.UINT64}
+
+
+def C(i): return ("col", i)
+def L(v, dt, null=False): return ("lit", v, np.dtype(dt), null)
+def B(op, l, r): return ("bin", op, l, r)
+def U(kind, a): return ("un", kind, a)
+
+
+def to_nodes(e, gpu):
+    """expression tree -> post-order node lists for the C ABI (gpu=True) or the oracle"""
+    out = []
+    def walk(x):
+        if x[0] == "col":
+            out.append((D.EXPR_COLUMN, x[1], 0, 0, 0, 0.0) if gpu else (O.E_COLUMN, x[1], None, 0, 0))
+        elif x[0] == "lit":
+            _, v, dt, null = x
+            if gpu:
+                isf = dt.kind == "f"
+                out.append((D.EXPR_LITERAL, 0, NP2T[dt], 1 if null else 0, 0 if (isf or null) else int(v), float(v) if (isf and not null) else 0.0))
+            else:
+                out.append((O.E_LITERAL, 0, dt, 1 if null else 0, v))
+        elif x[0] == "bin":
+            walk(x[2]); walk(x[3])
+            out.append((D.EXPR_BINARY, x[1], 0, 0, 0, 0.0) if gpu else (O.E_BINARY, x[1], None, 0, 0))
+        else:
+            walk(x[2])
+            out.append((x[1], 0, 0, 0, 0, 0.0) if gpu else (x[1], 0, None, 0, 0))
+    walk(e)
+    return out
+
+
+def eval_gpu(ctx, cols, e):
+    arr = (D.Column * len(cols))(*[D.HostColumn(v, val).c() for v, val in cols])
+    keep = [D.HostColumn(v, val) for v, val in cols]
+    arr = (D.Column * len(cols))(*[k.c() for k in keep])
+    nodes = D.expr_nodes(to_nodes(e, True))
+    import ctypes as CT
+    out = CT.c_void_p()
+    ctx.check(ctx.lib.dfgpu_expr_evaluate_host(ctx.h, arr, len(cols), len(cols[0][0]), nodes, len(nodes), CT.byref(out)))
+    b = D.Batch(ctx, out.value)
+    return b.column_numpy(0)
+
+
+def test_gpu_expression_kats(gpu_ctx):
+    m = MISC["binary_comparison"]
+    a, b = (np.array(m["a"], np.int32), None), (np.array(m["b"], np.int32), None)
+    v, val = eval_gpu(gpu_ctx, [a, b], B(D.OP_LT, C(0), C(1)))
+    assert v.tolist() == m["expected"] and (val is None or val.all())
+    k = MISC["kleene"]
+    a, b = col_from_list(k["a"], bool), col_from_list(k["b"], bool)
+    for op, key in ((D.OP_AND, "and"), (D.OP_OR, "or")):
+        v, val = eval_gpu(gpu_ctx, [a, b], B(op, C(0), C(1)))
+        got = [None if (val is not None and not val[i]) else bool(v[i]) for i in range(len(v))]
+        assert got == k[key], key
+
+
+EXPRS = {
+    "i64 > lit": (B(D.OP_GT, C(0), L(1 << 31, np.int64)), True),
+    "(a > c) AND (b < 5 OR b IS NULL)": (B(D.OP_AND, B(D.OP_GT, C(0), L(1 << 30, np.int64)), B(D.OP_OR, B(D.OP_LT, C(1), L(5, np.int32)), U(D.EXPR_IS_NULL, C(1)))), True),
+    "a + a*3 - 7 >= c (wrapping)": (B(D.OP_GTEQ, B(D.OP_MINUS, B(D.OP_PLUS, C(0), B(D.OP_MULTIPLY, C(0), L(3, np.int64))), L(7, np.int64)), L(12345, np.int64)), True),
+    "b % 7 = 3": (B(D.OP_EQ, B(D.OP_MODULO, C(1), L(7, np.int32)), L(3, np.int32)), True),
+    "f*2.5 <= f+1 (f64)": (B(D.OP_LTEQ, B(D.OP_MULTIPLY, C(2), L(2.5, np.float64)), B(D.OP_PLUS, C(2), L(1.0, np.float64))), True),
+    "NOT(a = b64) IS DISTINCT": (B(D.OP_IS_DISTINCT_FROM, C(1), L(0, np.int32, True)), True),
+    "a / 3 (value)": (B(D.OP_DIVIDE, C(0), L(3, np.int64)), False),
+    "-b (value)": (U(D.EXPR_NEGATIVE, C(1)), False),
+    "f - f*f (value)": (B(D.OP_MINUS, C(2), B(D.OP_MULTIPLY, C(2), C(2))), False),
+}
+
+
+@pytest.mark.parametrize("name", list(EXPRS.keys()))
+@pytest.mark.parametrize("nulls", [False, True])
+def test_gpu_expr_vs_oracle(gpu_ctx, name, nulls):
+    e, is_pred = EXPRS[name]
+    rng = np.random.default_rng(abs(hash(name)) % 2**31)
+    n = 100_003
+    a = rng.integers(0, 1 << 32, n).astype(np.int64); b = rng.integers(-50, 50, n).astype(np.int32)
+    f = rng.standard_normal(n); f[::97] = np.nan; f[::89] = -0.0; f[::83] = 0.0
+    mk = (lambda: rng.random(n) > 0.1) if nulls else (lambda: None)
+    cols = [(a, mk()), (b, mk()), (f, mk())]
+    ev, evalid = O.eval_expr(cols, to_nodes(e, False))
+    gv, gvalid = eval_gpu(gpu_ctx, cols, e)
+    ok = np.ones(n, bool) if evalid is None else evalid
+    gok = np.ones(n, bool) if gvalid is None else gvalid
+    assert np.array_equal(ok, gok), "validity"
+    if ev.dtype.kind == "f":
+        assert np.array_equal(ev[ok].view(np.int64), gv[ok].view(np.int64)), "float bits"   # same IEEE ops, same order: bit-exact
+    else:
+        assert np.array_equal(ev[ok], gv[ok])
+    if is_pred:  # FilterExec over the same predicate: 128 batches of 8192 rows like config C1
+        exp = O.filter_batch(cols, (ev, evalid))
+        got, sizes = gpu_filter(gpu_ctx, cols, to_nodes(e, True), batch_rows=8192)
+        assert_cols_equal(got, exp, ordered=True, what=name)
+        assert all(s == 8192 for s in sizes[:-1]) and 0 < sizes[-1] <= 8192     # coalescer emits target-size batches
+
+
+def test_gpu_filter_c1_selectivities_projection_fetch(gpu_ctx):
+    # BASELINE config C1: x:int64 > c on 1M rows, 128 batches of 8192, selectivity 1/20/50/99 %
+    rng = np.random.default_rng(1)
+    n = 1 << 20
+    x = rng.integers(0, 1 << 32, n).astype(np.int64); y = rng.integers(0, 100, n).astype(np.int32); yv = rng.random(n) > 0.1
+    for sel in (0.01, 0.2, 0.5, 0.99):
+        c = int(np.quantile(x, 1 - sel))
+        e = B(D.OP_GT, C(0), L(c, np.int64))
+        keep = x > c
+        got, _ = gpu_filter(gpu_ctx, [(x, None), (y, yv)], to_nodes(e, True))
+        assert_cols_equal(got, [(x[keep], None), (y[keep], yv[keep])], ordered=True, what=f"sel={sel}")
+    got, _ = gpu_filter(gpu_ctx, [(x, None), (y, yv)], to_nodes(e, True), projection=[1], fetch=1000, device=True)
+    assert_cols_equal(got, [(y[keep][:1000], yv[keep][:1000])], ordered=True, what="projection+fetch")
+
+
+def test_gpu_divide_by_zero_is_an_error(gpu_ctx):
+    a = (np.array([4, 5, 6], np.int64), None); z = (np.array([2, 0, 3], np.int64), None)
+    with pytest.raises(D.DfgpuError) as ei:
+        eval_gpu(gpu_ctx, [a, z], B(D.OP_DIVIDE, C(0), C(1)))
+    assert "Divide by zero" in str(ei.value) and ei.value.code == -4
+    zn = (np.array([2, 0, 3], np.int64), np.array([True, False, True]))       # NULL divisor slot is skipped, not an error
+    v, val = eval_gpu(gpu_ctx, [a, zn], B(D.OP_DIVIDE, C(0), C(1)))
+    assert val.tolist() == [True, False, True] and v[[0, 2]].tolist() == [2, 2]
+    with pytest.raises(D.DfgpuError):
+        D.FilterHandle(gpu_ctx, [D.INT64], to_nodes(B(D.OP_PLUS, C(0), L(1, np.int64)), True))   # non-boolean predicate (filter.rs:1355)

@@ -1,0 +1,228 @@
+"""Pin the CPU restatement oracle against the reference's own known-answer fixtures (tests/golden/)
+and against an independent engine (pyarrow.acero).  CPU only."""
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from harness import assert_cols_equal, col_from_list, load_golden
+
+JT = {"Inner": O.J_INNER, "Left": O.J_LEFT, "Right": O.J_RIGHT, "Full": O.J_FULL, "LeftSemi": O.J_LEFT_SEMI, "RightSemi": O.J_RIGHT_SEMI,
+      "LeftAnti": O.J_LEFT_ANTI, "RightAnti": O.J_RIGHT_ANTI, "LeftMark": O.J_LEFT_MARK, "RightMark": O.J_RIGHT_MARK}
+KAT = load_golden("hash_join_kat.json")["cases"]
+MISC = load_golden("misc_kat.json")
+
+
+def kat_tables(case):
+    left = [col_from_list(v) for _, v in case["left"]]
+    right = [col_from_list(v) for _, v in case["right"]]
+    ln, rn = [n for n, _ in case["left"]], [n for n, _ in case["right"]]
+    on_b = [ln.index(l) for l, _ in case["on"]]
+    on_p = [rn.index(r) for _, r in case["on"]]
+    jt = case["join_type"]
+    if jt in ("LeftSemi", "LeftAnti"):
+        side, idx = [0] * len(ln), list(range(len(ln)))
+    elif jt in ("RightSemi", "RightAnti"):
+        side, idx = [1] * len(rn), list(range(len(rn)))
+    elif jt == "LeftMark":
+        side, idx = [0] * len(ln) + [2], list(range(len(ln))) + [0]
+    elif jt == "RightMark":
+        side, idx = [1] * len(rn) + [2], list(range(len(rn))) + [0]
+    else:
+        side, idx = [0] * len(ln) + [1] * len(rn), list(range(len(ln))) + list(range(len(rn)))
+    exp = []
+    for c in range(len(case["header"])):
+        vals = [r[c] for r in case["expected"]]
+        if side[c] == 2:
+            exp.append((np.array(vals, bool), None))
+        else:
+            exp.append(col_from_list(vals))
+    return left, right, on_b, on_p, side, idx, exp
+
+
+# the reference's template: batch_size x perfect-hash on/off (exec.rs:2929-2962)
+MATRIX = list(itertools.product([8192, 10, 5, 2, 1], [True, False]))
+
+
+@pytest.mark.parametrize("case", KAT, ids=[c["name"] for c in KAT])
+def test_oracle_reproduces_reference_join_snapshots(case):
+    left, right, on_b, on_p, side, idx, exp = kat_tables(case)
+    for batch_size, phj in MATRIX:
+        thr, dens = (819200, 0.0) if phj else (0, float("inf"))
+        got = O.hash_join(left, right, on_b, on_p, side, idx, join_type=JT[case["join_type"]],
+                          null_equals_null=case["null_equality"] == "NullEqualsNull", batch_size=batch_size, phj_threshold=thr, phj_density=dens)
+        assert_cols_equal(got, exp, ordered=not case["sorted"], what=f"{case['name']} bs={batch_size} phj={phj} ({case['ref']})")
+
+
+@pytest.mark.parametrize("case", KAT, ids=[c["name"] for c in KAT])
+def test_oracle_force_hash_collisions_is_output_invariant(case):
+    # the reference's force_hash_collisions CI job (extended.yml:110-128): same results with every hash = 0
+    left, right, on_b, on_p, side, idx, exp = kat_tables(case)
+    got = O.hash_join(left, right, on_b, on_p, side, idx, join_type=JT[case["join_type"]], phj_threshold=0, phj_density=float("inf"), force_collisions=True,
+                      null_equals_null=case["null_equality"] == "NullEqualsNull")
+    assert_cols_equal(got, exp, ordered=not case["sorted"], what=case["name"])
+
+
+def test_oracle_array_map_selection_rule():
+    # exec.rs:172-179: ArrayMap iff range < threshold or density > min density (single integer key, rows < 2^32)
+    k = np.arange(100, dtype=np.int64) * 3
+    _, _, _, used = O.hash_join_indices([(k, None)], [(k, None)])                      # range 297 < 1024
+    assert used
+    k2 = np.arange(1000, dtype=np.int64) * 100
+    _, _, _, used = O.hash_join_indices([(k2, None)], [(k2, None)])                    # range 99900, density 0.01
+    assert not used
+    k3 = np.arange(10000, dtype=np.int64) * 2
+    _, _, _, used = O.hash_join_indices([(k3, None)], [(k3, None)])                    # density 0.5 > 0.15
+    assert used
+    _, _, _, used = O.hash_join_indices([(k3, None), (k3, None)], [(k3, None), (k3, None)])  # two keys: never
+    assert not used
+
+
+def test_oracle_lookup_order_example():
+    m = MISC["join_lookup_doc_example"]
+    b = np.array(m["build"], np.int64); p = np.array(m["probe"], np.int64)
+    for phj in (True, False):
+        bi, pi, _, _ = O.hash_join_indices([(b, None)], [(p, None)], phj_threshold=819200 if phj else 0, phj_density=0.0 if phj else float("inf"))
+        assert bi.tolist() == m["expected_build_idx"] and pi.tolist() == m["expected_probe_idx"]
+    # resumable MapOffset (join_hash_map.rs:389-484): tiny batch sizes must not change the pairs
+    for bs in (1, 2, 3):
+        bi, pi, _, _ = O.hash_join_indices([(b, None)], [(p, None)], batch_size=bs, phj_threshold=0, phj_density=float("inf"))
+        assert bi.tolist() == m["expected_build_idx"] and pi.tolist() == m["expected_probe_idx"]
+
+
+def test_oracle_perfect_hash_edge_cases():
+    m = MISC["perfect_hash_negative"]
+    l = np.array(m["left"][0][1], np.int64); r = np.array(m["right"][0][1], np.int64)
+    for phj in (True, False):
+        got = O.hash_join([(l, None)], [(r, None)], [0], [0], [0, 1], [0, 0], phj_threshold=819200 if phj else 0, phj_density=0.0 if phj else float("inf"))
+        exp = [(np.array([x[0] for x in m["expected_sorted"]], np.int64), None), (np.array([x[1] for x in m["expected_sorted"]], np.int64), None)]
+        assert_cols_equal(got, exp, ordered=False)
+    m = MISC["perfect_hash_full_range"]
+    l = np.array(m["left_i64"], np.int64); r = np.array(m["right_i64"], np.int64)
+    bi, pi, _, used = O.hash_join_indices([(l, None)], [(r, None)], phj_threshold=819200, phj_density=0.0)
+    assert not used and l[bi].tolist() == [m["expected_sorted"][0][0]]
+
+
+def test_oracle_multi_batch_build_order():
+    # exec.rs:2684-2705: the hash-map path inserts batches.iter().rev() with growing offsets and concatenates the
+    # reversed list, so chains still come out in ORIGINAL build order; only the final unmatched-row pass
+    # (get_final_indices_from_bit_map, utils.rs:1210-1245) walks the reversed concatenation.
+    b = np.array([5, 5, 5, 5], np.int64); p = np.array([5], np.int64)
+    for phj in (False, True):
+        kw = dict(phj_threshold=819200, phj_density=0.0) if phj else dict(phj_threshold=0, phj_density=float("inf"))
+        bi, _, _, used = O.hash_join_indices([(b, None)], [(p, None)], build_batch_rows=[2, 2], **kw)
+        assert used == phj and bi.tolist() == [0, 1, 2, 3]
+    b2 = np.array([1, 2, 3, 4], np.int64); p2 = np.array([9], np.int64)
+    bi, pi, _, _ = O.hash_join_indices([(b2, None)], [(p2, None)], join_type=O.J_LEFT, build_batch_rows=[2, 2], phj_threshold=0, phj_density=float("inf"))
+    assert bi.tolist() == [2, 3, 0, 1] and pi.tolist() == [-1] * 4       # hash map: reversed-batch concatenation
+    bi, pi, _, _ = O.hash_join_indices([(b2, None)], [(p2, None)], join_type=O.J_LEFT, build_batch_rows=[2, 2])
+    assert bi.tolist() == [0, 1, 2, 3]                                     # ArrayMap: concat_batches(schema, batches), exec.rs:184
+
+
+def test_oracle_aggregate_some_data():
+    m = MISC["aggregate_some_data"]
+    a = np.concatenate([np.array(b["a"], np.uint32) for b in m["batches"]])
+    v = np.concatenate([np.array(b["b"], np.float64) for b in m["batches"]])
+    keys, res = O.group_by([(a, None)], [(O.A_AVG, (v, None), None)], batch_size=4)
+    assert keys[0][0].tolist() == m["partial"]["a"]           # first-seen order 2,3,4
+    assert res[0]["c"].tolist() == m["partial"]["count"] and res[0]["f"].tolist() == m["partial"]["sum"]
+    # Final over two identical partial partitions
+    pk = np.concatenate([keys[0][0], keys[0][0]]); pc = np.concatenate([res[0]["c"], res[0]["c"]]).astype(np.uint64); ps = np.concatenate([res[0]["f"], res[0]["f"]])
+    fkeys, fres = O.group_by([(pk, None)], [(O.A_AVG, (pc, None), None, (ps, None))], merge=True)
+    avg = O.agg_output_columns(O.A_AVG, fres[0], np.float64, state=False)[0][0]
+    assert fkeys[0][0].tolist() == m["final_avg"]["a"] and avg.tolist() == m["final_avg"]["avg"]
+
+
+def test_oracle_sum_count_null_state_and_wrapping():
+    m = MISC["sum_null_state"]
+    g1, v1 = np.array(m["g"], np.int64), col_from_list(m["v"], np.int64)
+    g2, v2 = np.array(m["second_batch"]["g"], np.int64), col_from_list(m["second_batch"]["v"], np.int64)
+    g = np.concatenate([g1, g2]); v = np.concatenate([v1[0], v2[0]])
+    valid = np.concatenate([v1[1] if v1[1] is not None else np.ones(len(g1), bool), v2[1] if v2[1] is not None else np.ones(len(g2), bool)])
+    keys, res = O.group_by([(g, None)], [(O.A_SUM, (v, valid), None), (O.A_COUNT, (v, valid), None)], batch_size=len(g1))
+    exp = m["expected"]
+    assert keys[0][0].tolist() == exp["g"]
+    s = O.agg_output_columns(O.A_SUM, res[0], np.int64, False)[0]
+    got_sum = [None if (s[1] is not None and not s[1][i]) else int(s[0][i]) for i in range(len(exp["g"]))]
+    assert got_sum == exp["sum"] and res[1]["c"].tolist() == exp["count"]
+
+
+def test_oracle_expressions_kat():
+    m = MISC["binary_comparison"]
+    a, b = np.array(m["a"], np.int32), np.array(m["b"], np.int32)
+    r = O.eval_expr([(a, None), (b, None)], [(O.E_COLUMN, 0, None, 0, 0), (O.E_COLUMN, 1, None, 0, 0), (O.E_BINARY, O.OP_LT, None, 0, 0)])
+    assert r[0].tolist() == m["expected"] and r[1] is None
+    k = MISC["kleene"]
+    a, b = col_from_list(k["a"], bool), col_from_list(k["b"], bool)
+    for op, key in ((O.OP_AND, "and"), (O.OP_OR, "or")):
+        v, val = O.eval_expr([a, b], [(O.E_COLUMN, 0, None, 0, 0), (O.E_COLUMN, 1, None, 0, 0), (O.E_BINARY, op, None, 0, 0)])
+        got = [None if (val is not None and not val[i]) else bool(v[i]) for i in range(len(v))]
+        assert got == k[key]
+    # float compare: -0.0 == +0.0, NaN == NaN under totalOrder (datum.rs:88-105)
+    x = np.array([0.0, -0.0, np.nan, 1.0]); y = np.array([-0.0, 0.0, np.nan, np.nan])
+    v, _ = O.eval_expr([(x, None), (y, None)], [(O.E_COLUMN, 0, None, 0, 0), (O.E_COLUMN, 1, None, 0, 0), (O.E_BINARY, O.OP_EQ, None, 0, 0)])
+    assert v.tolist() == [True, True, True, False]
+    v, _ = O.eval_expr([(x, None), (y, None)], [(O.E_COLUMN, 0, None, 0, 0), (O.E_COLUMN, 1, None, 0, 0), (O.E_BINARY, O.OP_LT, None, 0, 0)])
+    assert v.tolist() == [False, False, False, True]   # 1.0 < NaN in totalOrder
+    with pytest.raises(O.ArrowDivideByZero):
+        O.eval_expr([(np.array([1, 2], np.int64), None), (np.array([1, 0], np.int64), None)],
+                    [(O.E_COLUMN, 0, None, 0, 0), (O.E_COLUMN, 1, None, 0, 0), (O.E_BINARY, O.OP_DIVIDE, None, 0, 0)])
+
+
+# ---- independent cross-check: pyarrow.acero ------------------------------------------------
+def test_oracle_vs_acero_join_and_groupby():
+    import pyarrow as pa
+    rng = np.random.default_rng(7)
+    nb, npr = 3000, 20000
+    bk = rng.integers(0, 2000, nb).astype(np.int64); bp = np.arange(nb, dtype=np.int64)
+    pk = rng.integers(0, 2500, npr).astype(np.int64); pp = np.arange(npr, dtype=np.int64)
+    bvalid = rng.random(nb) > 0.05; pvalid = rng.random(npr) > 0.05
+    lt = pa.table({"k": pa.array(bk, mask=~bvalid), "pb": bp}); rt = pa.table({"k": pa.array(pk, mask=~pvalid), "pp": pp})
+    for jt, acero in ((O.J_INNER, "inner"), (O.J_LEFT, "left outer"), (O.J_RIGHT, "right outer"), (O.J_FULL, "full outer"),
+                      (O.J_LEFT_SEMI, "left semi"), (O.J_RIGHT_SEMI, "right semi"), (O.J_LEFT_ANTI, "left anti"), (O.J_RIGHT_ANTI, "right anti")):
+        bi, pi, _, _ = O.hash_join_indices([(bk, bvalid)], [(pk, pvalid)], join_type=jt, phj_threshold=0, phj_density=float("inf"))
+        ref = lt.join(rt, keys="k", join_type=acero, coalesce_keys=False)
+        got_pb = sorted((-1 if i < 0 else int(bp[i])) for i in bi) if "right semi" not in acero and "right anti" not in acero else None
+        got_pp = sorted((-1 if i < 0 else int(pp[i])) for i in pi) if "left semi" not in acero and "left anti" not in acero else None
+        if got_pb is not None:
+            assert got_pb == sorted(-1 if v is None else v for v in ref["pb"].to_pylist()), acero
+        if got_pp is not None:
+            assert got_pp == sorted(-1 if v is None else v for v in ref["pp"].to_pylist()), acero
+    g = rng.integers(0, 500, 50000).astype(np.int64); v = rng.integers(-1000, 1000, 50000).astype(np.int64); vv = rng.random(50000) > 0.1
+    keys, res = O.group_by([(g, None)], [(O.A_SUM, (v, vv), None), (O.A_COUNT, (v, vv), None), (O.A_MIN, (v, vv), None), (O.A_MAX, (v, vv), None)])
+    t = pa.table({"g": g, "v": pa.array(v, mask=~vv)}).group_by("g").aggregate([("v", "sum"), ("v", "count"), ("v", "min"), ("v", "max")]).sort_by("g")
+    o = np.argsort(keys[0][0])
+    assert keys[0][0][o].tolist() == t["g"].to_pylist()
+    assert res[0]["i"][o].tolist() == t["v_sum"].to_pylist() and res[1]["c"][o].tolist() == t["v_count"].to_pylist()
+    assert res[2]["i"][o].tolist() == t["v_min"].to_pylist() and res[3]["i"][o].tolist() == t["v_max"].to_pylist()
+
+
+def out_mapping(jt, nl, nr):
+    if jt in ("LeftSemi", "LeftAnti"):
+        return [0] * nl, list(range(nl))
+    if jt in ("RightSemi", "RightAnti"):
+        return [1] * nr, list(range(nr))
+    if jt == "LeftMark":
+        return [0] * nl + [2], list(range(nl)) + [0]
+    if jt == "RightMark":
+        return [1] * nr + [2], list(range(nr)) + [0]
+    return [0] * nl + [1] * nr, list(range(nl)) + list(range(nr))
+
+
+def expected_cols(rows, side):
+    exp = []
+    for c in range(len(side)):
+        vals = [r[c] for r in rows]
+        exp.append((np.array(vals, bool), None) if side[c] == 2 else col_from_list(vals))
+    return exp
+
+
+@pytest.mark.parametrize("jt", list(MISC["all_null_build_keys"]["expected_sorted"].keys()))
+def test_oracle_all_null_build_keys(jt):
+    m = MISC["all_null_build_keys"]
+    left = [col_from_list(v) for _, v in m["left"]]; right = [col_from_list(v) for _, v in m["right"]]
+    side, idx = out_mapping(jt, 2, 2)
+    for phj in (True, False):
+        got = O.hash_join(left, right, [1], [1], side, idx, join_type=JT[jt], phj_threshold=819200 if phj else 0, phj_density=0.0 if phj else float("inf"))
+        assert_cols_equal(got, expected_cols(m["expected_sorted"][jt], side), ordered=False, what=f"{jt} ({m['ref']})")
