@@ -10,6 +10,7 @@
 #include <stdexcept>
 #include <map>
 #include <mutex>
+#include <unordered_map>
 #include "../../include/dfgpu.h"
 
 namespace dfgpu {
@@ -114,6 +115,12 @@ struct dfgpu_kernel_timing {
 };
 
 struct dfgpu_ctx {
+  // per-ctx caching device allocator: every allocation and free of this library is ordered on ctx->stream,
+  // so a released block can be handed out again immediately (stream order makes the reuse safe) and the
+  // steady state performs no cudaMalloc / pool growth at all.
+  std::multimap<size_t, void*> dev_free;
+  std::unordered_map<void*, size_t> dev_sizes;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;  // lazily created: H2D / D2H streams of the pipelined host entry points
   bool time_kernels = false;                    // dfgpu_set_kernel_timing
   std::vector<dfgpu_kernel_timing> timings;     // per kernel family
   int device = 0;
@@ -130,6 +137,39 @@ struct dfgpu_ctx {
 namespace dfgpu {
 
 inline void set_device(dfgpu_ctx* ctx) { DF_CUDA(cudaSetDevice(ctx->device)); }
+
+inline size_t dev_bucket(size_t n) {
+  if (n <= 256) return 256;
+  size_t p = 256;
+  while (p * 2 <= n) p <<= 1;          // largest power of two <= n
+  size_t step = p >= (1u << 20) ? p / 8 : p;  // >= 1 MiB: 12.5 % granularity; small blocks: next power of two
+  return ((n + step - 1) / step) * step;
+}
+inline void dev_cache_trim(dfgpu_ctx* ctx) {
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->dev_free) { cudaFree(kv.second); ctx->dev_sizes.erase(kv.second); }
+  ctx->dev_free.clear();
+}
+inline void* dev_alloc(dfgpu_ctx* ctx, size_t n) {
+  const size_t b = dev_bucket(n);
+  auto it = ctx->dev_free.find(b);
+  if (it != ctx->dev_free.end()) { void* p = it->second; ctx->dev_free.erase(it); return p; }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, b);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    dev_cache_trim(ctx);
+    e = cudaMalloc(&p, b);
+    if (e != cudaSuccess) { cudaGetLastError(); throw Error(DFGPU_ERR_OOM, "device allocation of " + std::to_string(b) + " bytes failed"); }
+  }
+  ctx->dev_sizes[p] = b;
+  return p;
+}
+inline void dev_free(dfgpu_ctx* ctx, void* p) {
+  auto it = ctx->dev_sizes.find(p);
+  if (it == ctx->dev_sizes.end()) { cudaFree(p); return; }
+  ctx->dev_free.emplace(it->second, p);
+}
 
 // stream-ordered device buffer (cudaMallocAsync pool: no implicit device sync on alloc/free)
 struct DevBuf {
@@ -151,10 +191,10 @@ struct DevBuf {
     ctx = c;
     bytes = n;
     if (n == 0) { ptr = nullptr; return; }
-    DF_CUDA(cudaMallocAsync(&ptr, n, c->stream));
+    ptr = dev_alloc(c, n);
   }
   void release() {
-    if (ptr) { cudaFreeAsync(ptr, ctx->stream); ptr = nullptr; bytes = 0; }
+    if (ptr) { dev_free(ctx, ptr); ptr = nullptr; bytes = 0; }
   }
   template <class T> T* as() const { return reinterpret_cast<T*>(ptr); }
   void zero() { if (ptr) DF_CUDA(cudaMemsetAsync(ptr, 0, bytes, ctx->stream)); }

@@ -86,8 +86,11 @@ void dfgpu_ctx_destroy(dfgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  dev_cache_trim(ctx);
   if (ctx->l2_scratch) cudaFree(ctx->l2_scratch);
   if (ctx->pinned_scalar) cudaFreeHost(ctx->pinned_scalar);
+  if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+  if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -137,13 +140,13 @@ int dfgpu_sync(dfgpu_ctx* ctx) {
 int dfgpu_malloc(dfgpu_ctx* ctx, size_t bytes, void** out) {
   DF_API_BEGIN(ctx)
   set_device(ctx);
-  DF_CUDA(cudaMallocAsync(out, bytes ? bytes : 8, ctx->stream));
+  *out = dev_alloc(ctx, bytes ? bytes : 8);
   DF_API_END
 }
 int dfgpu_free(dfgpu_ctx* ctx, void* p) {
   DF_API_BEGIN(ctx)
   set_device(ctx);
-  if (p) DF_CUDA(cudaFreeAsync(p, ctx->stream));
+  if (p) dev_free(ctx, p);
   DF_API_END
 }
 int dfgpu_host_alloc(dfgpu_ctx* ctx, size_t bytes, void** out) {

@@ -349,6 +349,37 @@ struct FusedCols {
 #define kDescPrefix (2ull << 62)
 #define kDescMask ((1ull << 62) - 1ull)
 
+// decoupled look-back over tile descriptors (status in the top 2 bits, value below); called by warp 0.
+// Returns the exclusive prefix of `tot` for `tile` and publishes this tile's inclusive prefix.
+__device__ __forceinline__ unsigned long long tile_lookback(int64_t tile, uint32_t tot, unsigned long long* tile_desc) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long exclusive = 0;
+  if (tile == 0) {
+    if (lane == 0) atomicExch(&tile_desc[0], kDescPrefix | (unsigned long long)tot);
+    return 0;
+  }
+  if (lane == 0) atomicExch(&tile_desc[tile], kDescAgg | (unsigned long long)tot);
+  int64_t look = tile - 1;
+  while (true) {
+    const int64_t idx = look - lane;
+    unsigned long long d = idx >= 0 ? *(volatile unsigned long long*)&tile_desc[idx] : kDescPrefix;  // virtual prefix 0 before tile 0
+    const unsigned st = (unsigned)(d >> 62);
+    const unsigned invalid = __ballot_sync(0xffffffffu, st == 0);
+    const unsigned prefix = __ballot_sync(0xffffffffu, st == 2);
+    const int first_prefix = prefix ? __ffs(prefix) - 1 : 32;
+    const int first_invalid = invalid ? __ffs(invalid) - 1 : 32;
+    if (first_invalid < first_prefix) continue;  // a predecessor in the window has not published yet: spin
+    unsigned long long contrib = (lane <= first_prefix) ? (d & kDescMask) : 0ull;
+#pragma unroll
+    for (int dd = 16; dd > 0; dd >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, dd);
+    exclusive += contrib;
+    if (first_prefix < 32) break;
+    look -= 32;
+  }
+  if (lane == 0) atomicExch(&tile_desc[tile], kDescPrefix | (exclusive + (unsigned long long)tot));
+  return exclusive;
+}
+
 __global__ void __launch_bounds__(kFusedThreads) join_probe_fused_kernel(KeyCols kc, int64_t n, TableRef t, int mark_visited, FusedCols oc,
                                                                       unsigned long long* __restrict__ tile_desc, unsigned int* __restrict__ tile_counter,
                                                                       unsigned long long* __restrict__ totals /* [out_rows, hit_rows] */) {
@@ -386,35 +417,9 @@ __global__ void __launch_bounds__(kFusedThreads) join_probe_fused_kernel(KeyCols
 #pragma unroll
   for (int k = 0; k < kFusedItems; ++k)
     if (heads[k] != kEmpty32) { s_b[ex] = heads[k]; s_p[ex] = (uint32_t)(row0 + k - tile * kFusedTile); ++ex; }
-  // ---- decoupled look-back (warp 0) ----
   if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    unsigned long long exclusive = 0;
-    if (tile == 0) {
-      if (lane == 0) atomicExch(&tile_desc[0], kDescPrefix | (unsigned long long)tot);
-    } else {
-      if (lane == 0) atomicExch(&tile_desc[tile], kDescAgg | (unsigned long long)tot);
-      int64_t look = tile - 1;
-      while (true) {
-        const int64_t idx = look - lane;
-        unsigned long long d = idx >= 0 ? *(volatile unsigned long long*)&tile_desc[idx] : kDescPrefix;  // virtual prefix 0 before tile 0
-        const unsigned st = (unsigned)(d >> 62);
-        const unsigned invalid = __ballot_sync(0xffffffffu, st == 0);
-        const unsigned prefix = __ballot_sync(0xffffffffu, st == 2);
-        const int first_prefix = prefix ? __ffs(prefix) - 1 : 32;
-        const int first_invalid = invalid ? __ffs(invalid) - 1 : 32;
-        if (first_invalid < first_prefix) continue;  // a predecessor in the window has not published yet: spin
-        unsigned long long contrib = (lane <= first_prefix && lane < 32) ? (d & kDescMask) : 0ull;
-        if (lane > first_prefix) contrib = 0;
-#pragma unroll
-        for (int dd = 16; dd > 0; dd >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, dd);
-        exclusive += contrib;
-        if (first_prefix < 32) break;
-        look -= 32;
-      }
-      if (lane == 0) atomicExch(&tile_desc[tile], kDescPrefix | (exclusive + (unsigned long long)tot));
-    }
-    if (lane == 0) {
+    unsigned long long exclusive = tile_lookback(tile, tot, tile_desc);
+    if (threadIdx.x == 0) {
       s_base = exclusive;
       if ((tile + 1) * (int64_t)kFusedTile >= n) totals[0] = exclusive + tot;  // last tile: total output rows
       if (tot) atomicAdd(&totals[1], (unsigned long long)tot);
@@ -456,6 +461,165 @@ __global__ void __launch_bounds__(kFusedThreads) join_probe_fused_kernel(KeyCols
         uint4* dst = (uint4*)oc.dst[c] + base;
         for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = build_side ? src[s_b[j]] : src[prow0 + s_p[j]];
         break;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// inline-payload table (unique build keys, Inner join, narrow build side): the slot IS the build row.
+//   slot = {key:u64} or {key:u64, payload:u64} where payload packs every non-key build output column
+//   (<= 64 bits together).  A probe is ONE random access (one 64 B DRAM fetch) instead of table + gather,
+//   and build-key output columns are read from the probe key (bit-identical by the join condition).
+//   Dense keys (the reference's ArrayMap rule) use direct addressing slot = key - min instead of hashing.
+//   Any duplicate key or the all-ones key aborts the attempt (flag) and the generic table is built instead.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxPayloadCols = 8;
+struct PayloadCols { int n; const void* ptr[kMaxPayloadCols]; int width[kMaxPayloadCols]; int shift[kMaxPayloadCols]; };
+struct InlineRef { void* slots; uint64_t cap; int dense; uint64_t amin; };
+struct InlineOut {
+  int n;
+  int kind[kMaxFusedCols];   // 0: gather from a probe-side column by probe row; 1: extract from the payload word
+  const void* src[kMaxFusedCols];
+  void* dst[kMaxFusedCols];
+  int width[kMaxFusedCols];
+  int shift[kMaxFusedCols];
+  uint32_t* pidx_out;        // optional: matched probe row per output row (for nullable probe columns gathered afterwards)
+};
+
+__device__ __forceinline__ uint64_t load_payload(const PayloadCols& pc, int64_t row) {
+  uint64_t p = 0;
+#pragma unroll
+  for (int c = 0; c < kMaxPayloadCols; ++c) {
+    if (c >= pc.n) break;
+    uint64_t v;
+    switch (pc.width[c]) {
+      case 1: v = ((const uint8_t*)pc.ptr[c])[row]; break;
+      case 2: v = ((const uint16_t*)pc.ptr[c])[row]; break;
+      case 4: v = ((const uint32_t*)pc.ptr[c])[row]; break;
+      default: v = ((const uint64_t*)pc.ptr[c])[row]; break;
+    }
+    p |= v << pc.shift[c];
+  }
+  return p;
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) join_build_inline_kernel(KeyCols kc, PayloadCols pc, int64_t n, InlineRef t, unsigned long long* counters /* [valid, nulls, fail] */) {
+  unsigned int valid = 0, nulls = 0, fail = 0;
+  for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t tag;
+    if (!load_tag(kc, row, &tag)) { nulls++; continue; }  // NULL key: never matches under NullEqualsNothing
+    valid++;
+    if (tag == kEmpty64) { fail = 1; continue; }
+    const uint64_t pay = W == 2 ? load_payload(pc, row) : 0ull;
+    uint64_t s = t.dense ? (tag - t.amin) : __umul64hi(hash_u64(tag, kSeedJoin), t.cap);
+    while (true) {
+      unsigned long long prev;
+      if (W == 2) prev = cas128((Slot128*)t.slots + s, Slot128{kEmpty64, kEmpty64}, Slot128{tag, pay}).lo;
+      else prev = atomicCAS((unsigned long long*)t.slots + s, (unsigned long long)kEmpty64, (unsigned long long)tag);
+      if (prev == kEmpty64) break;
+      if (prev == tag) { fail = 1; break; }  // duplicate build key
+      if (++s == t.cap) s = 0;
+    }
+  }
+  fail = __any_sync(0xffffffffu, fail) ? 1u : 0u;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { valid += __shfl_xor_sync(0xffffffffu, valid, d); nulls += __shfl_xor_sync(0xffffffffu, nulls, d); }
+  if ((threadIdx.x & 31) == 0) {
+    if (valid) atomicAdd(&counters[0], (unsigned long long)valid);
+    if (nulls) atomicAdd(&counters[1], (unsigned long long)nulls);
+    if (fail) atomicExch(&counters[2], 1ull);
+  }
+}
+
+template <int W>
+__global__ void __launch_bounds__(kFusedThreads) join_probe_inline_kernel(KeyCols kc, int64_t n, InlineRef t, InlineOut oc,
+                                                                       unsigned long long* __restrict__ tile_desc, unsigned int* __restrict__ tile_counter,
+                                                                       unsigned long long* __restrict__ totals) {
+  __shared__ unsigned long long s_pay[W == 2 ? kFusedTile : 1];
+  __shared__ uint32_t s_p[kFusedTile];
+  __shared__ unsigned int s_tile;
+  __shared__ unsigned long long s_base;
+  if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+  __syncthreads();
+  const int64_t tile = s_tile;
+  const int64_t row0 = tile * kFusedTile + (int64_t)threadIdx.x * kFusedItems;
+  uint64_t tags[kFusedItems], slot[kFusedItems], pays[kFusedItems];
+  bool live[kFusedItems], hit[kFusedItems];
+  // phase 1: keys and first-slot loads for all 4 rows are issued before any is consumed (memory-level parallelism)
+#pragma unroll
+  for (int k = 0; k < kFusedItems; ++k) {
+    const int64_t i = row0 + k;
+    live[k] = i < n && load_tag(kc, i, &tags[k]) && tags[k] != kEmpty64;
+    hit[k] = false;
+    pays[k] = 0;
+    slot[k] = 0;
+    if (live[k]) {
+      if (t.dense) { slot[k] = tags[k] - t.amin; if (slot[k] >= t.cap) live[k] = false; }
+      else slot[k] = __umul64hi(hash_u64(tags[k], kSeedJoin), t.cap);
+    }
+  }
+  uint64_t cur[kFusedItems], curp[kFusedItems];
+#pragma unroll
+  for (int k = 0; k < kFusedItems; ++k) {
+    cur[k] = kEmpty64; curp[k] = 0;
+    if (live[k]) {
+      if (W == 2) { const uint4 v = __ldcg((const uint4*)t.slots + slot[k]); cur[k] = (uint64_t)v.x | ((uint64_t)v.y << 32); curp[k] = (uint64_t)v.z | ((uint64_t)v.w << 32); }
+      else cur[k] = __ldcg((const unsigned long long*)t.slots + slot[k]);
+    }
+  }
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < kFusedItems; ++k) {
+    if (!live[k]) continue;
+    while (true) {  // linear probing continues only on a foreign key (rare at load factor 0.5; never in dense mode)
+      if (cur[k] == tags[k]) { hit[k] = true; pays[k] = curp[k]; break; }
+      if (cur[k] == kEmpty64 || t.dense) break;
+      if (++slot[k] == t.cap) slot[k] = 0;
+      if (W == 2) { const uint4 v = __ldcg((const uint4*)t.slots + slot[k]); cur[k] = (uint64_t)v.x | ((uint64_t)v.y << 32); curp[k] = (uint64_t)v.z | ((uint64_t)v.w << 32); }
+      else cur[k] = __ldcg((const unsigned long long*)t.slots + slot[k]);
+    }
+    m += hit[k] ? 1u : 0u;
+  }
+  uint32_t tot;
+  uint32_t ex = block_exclusive_scan<kFusedThreads, uint32_t>(m, &tot);
+#pragma unroll
+  for (int k = 0; k < kFusedItems; ++k)
+    if (hit[k]) { if (W == 2) s_pay[ex] = pays[k]; s_p[ex] = (uint32_t)(row0 + k - tile * kFusedTile); ++ex; }
+  if (threadIdx.x < 32) {
+    unsigned long long exclusive = tile_lookback(tile, tot, tile_desc);
+    if (threadIdx.x == 0) {
+      s_base = exclusive;
+      if ((tile + 1) * (int64_t)kFusedTile >= n) totals[0] = exclusive + tot;
+      if (tot) atomicAdd(&totals[1], (unsigned long long)tot);
+    }
+  }
+  __syncthreads();
+  const unsigned long long base = s_base;
+  const int64_t prow0 = tile * kFusedTile;
+  if (oc.pidx_out) for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) oc.pidx_out[base + j] = (uint32_t)(prow0 + s_p[j]);
+  for (int c = 0; c < oc.n; ++c) {
+    if (oc.kind[c] == 0) {
+      switch (oc.width[c]) {
+        case 8: { const uint64_t* src = (const uint64_t*)oc.src[c]; uint64_t* dst = (uint64_t*)oc.dst[c] + base;
+                  for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = src[prow0 + s_p[j]]; break; }
+        case 4: { const uint32_t* src = (const uint32_t*)oc.src[c]; uint32_t* dst = (uint32_t*)oc.dst[c] + base;
+                  for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = src[prow0 + s_p[j]]; break; }
+        case 2: { const uint16_t* src = (const uint16_t*)oc.src[c]; uint16_t* dst = (uint16_t*)oc.dst[c] + base;
+                  for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = src[prow0 + s_p[j]]; break; }
+        case 1: { const uint8_t* src = (const uint8_t*)oc.src[c]; uint8_t* dst = (uint8_t*)oc.dst[c] + base;
+                  for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = src[prow0 + s_p[j]]; break; }
+        default: { const uint4* src = (const uint4*)oc.src[c]; uint4* dst = (uint4*)oc.dst[c] + base;
+                  for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = src[prow0 + s_p[j]]; break; }
+      }
+    } else if (oc.kind[c] == 1 && W == 2) {
+      const int sh = oc.shift[c];
+      switch (oc.width[c]) {
+        case 8: { uint64_t* dst = (uint64_t*)oc.dst[c] + base; for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = s_pay[j]; break; }
+        case 4: { uint32_t* dst = (uint32_t*)oc.dst[c] + base; for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = (uint32_t)(s_pay[j] >> sh); break; }
+        case 2: { uint16_t* dst = (uint16_t*)oc.dst[c] + base; for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = (uint16_t)(s_pay[j] >> sh); break; }
+        default: { uint8_t* dst = (uint8_t*)oc.dst[c] + base; for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = (uint8_t)(s_pay[j] >> sh); break; }
       }
     }
   }
@@ -517,6 +681,12 @@ struct dfgpu_hashjoin {
   int64_t distinct = 0, valid_rows = 0, null_rows = 0;
   bool need_visited = false;
   int emit_mode = EMIT_PAIRS;
+  // inline-payload table (unique keys, Inner, narrow build side)
+  bool inline_ok = false;
+  int inline_words = 0;
+  DevBuf inline_slots;
+  InlineRef iref{};
+  std::vector<int> out_kind, out_src, out_shift;  // per output column: kind (0 probe gather / 1 payload), probe column index, payload shift
   // output
   std::deque<BatchPtr> outq;
   // metrics (BuildProbeJoinMetrics, joins/utils.rs:1756-1778)
@@ -649,6 +819,64 @@ static void finish_build(dfgpu_hashjoin* j) {
       }
     }
   }
+  // ---- inline-payload attempt ----
+  j->inline_ok = false;
+  if (n > 0 && j->emit_mode == EMIT_PAIRS && !j->need_visited && j->opt.null_equality == DFGPU_NULL_EQUALS_NOTHING && !j->opt.force_hash_collisions &&
+      j->out_side.size() <= (size_t)kMaxFusedCols) {
+    bool ok = true;
+    int bits = 0;
+    PayloadCols pc;
+    memset(&pc, 0, sizeof(pc));
+    j->out_kind.assign(j->out_side.size(), 0); j->out_src.assign(j->out_side.size(), 0); j->out_shift.assign(j->out_side.size(), 0);
+    std::vector<int> pay_of_col(j->build_types.size(), -1);
+    for (size_t c = 0; c < j->out_side.size() && ok; ++c) {
+      const int side = j->out_side[c], ix = j->out_index[c];
+      if (side == 2) { ok = false; break; }
+      if (side == 1) { j->out_kind[c] = 0; j->out_src[c] = ix; if (j->probe_types[ix] == DFGPU_BOOL) ok = false; continue; }
+      // build side: a key column is read from the probe key (exact-tag equality makes them bit-identical)
+      int key_pos = -1;
+      for (size_t k = 0; k < j->on_build.size(); ++k) if (j->on_build[k] == ix) key_pos = (int)k;
+      if (key_pos >= 0 && type_width(j->build_types[ix]) == type_width(j->probe_types[j->on_probe[key_pos]])) { j->out_kind[c] = 0; j->out_src[c] = j->on_probe[key_pos]; continue; }
+      const DCol& bc = j->build_cols[ix];
+      const int w = type_width(bc.type);
+      if (bc.type == DFGPU_BOOL || bc.validity || w < 1 || w > 8) { ok = false; break; }
+      if (pay_of_col[ix] < 0) {
+        if (pc.n >= kMaxPayloadCols || bits + 8 * w > 64) { ok = false; break; }
+        pc.ptr[pc.n] = bc.values; pc.width[pc.n] = w; pc.shift[pc.n] = bits;
+        pay_of_col[ix] = bits;
+        bits += 8 * w; pc.n++;
+      }
+      j->out_kind[c] = 1; j->out_shift[c] = pay_of_col[ix];
+    }
+    if (ok) {
+      const int W = pc.n ? 2 : 1;
+      const uint64_t cap = j->use_array_map ? j->table.asize : std::max<uint64_t>(1024, (uint64_t)n * 2);
+      j->inline_slots.alloc(ctx, (size_t)cap * 8 * W);
+      j->inline_slots.fill(0xFF);
+      j->iref.slots = j->inline_slots.ptr; j->iref.cap = cap; j->iref.dense = j->use_array_map ? 1 : 0; j->iref.amin = j->table.amin;
+      DF_CUDA(cudaMemsetAsync(j->counters.ptr, 0, 64, ctx->stream));
+      {
+        KernelTimer kt(ctx, "join_build");
+        if (W == 2) join_build_inline_kernel<2><<<grid_for(n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(j->build_keys, pc, n, j->iref, j->counters.as<unsigned long long>());
+        else join_build_inline_kernel<1><<<grid_for(n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(j->build_keys, pc, n, j->iref, j->counters.as<unsigned long long>());
+        DF_LAUNCH_CHECK(ctx);
+      }
+      unsigned long long hc[3];
+      DF_CUDA(cudaMemcpyAsync(hc, j->counters.ptr, 24, cudaMemcpyDeviceToHost, ctx->stream));
+      DF_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (hc[2] == 0) {
+        j->inline_ok = true; j->inline_words = W;
+        j->distinct = j->valid_rows = (int64_t)hc[0]; j->null_rows = (int64_t)hc[1];
+        j->unique = true;
+        j->amap.release();   // the direct {head,cnt} array is not needed
+        j->next.release();
+        j->built = true;
+        return;
+      }
+      j->inline_slots.release();  // duplicates (or the all-ones key): fall through to the generic chained table
+      DF_CUDA(cudaMemsetAsync(j->counters.ptr, 0, 64, ctx->stream));
+    }
+  }
   if (!j->use_array_map) {
     uint64_t cap = std::max<uint64_t>(1024, (uint64_t)n * 2);
     j->slots.alloc(ctx, (size_t)(cap + 1) * 16);
@@ -723,6 +951,49 @@ static void push_probe(dfgpu_hashjoin* j, std::vector<DCol>&& cols) {
   // empty / unmatchable build side: build_batch_empty_build_side (utils.rs:1393-1430)
   KeyCols pk;
   make_keycols(cols, j->on_probe, &pk);
+  // ---- inline-payload path ----
+  if (j->inline_ok) {
+    InlineOut oc;
+    memset(&oc, 0, sizeof(oc));
+    oc.n = (int)j->out_side.size();
+    BatchPtr out(new dfgpu_batch());
+    out->ctx = ctx; out->host = false;
+    out->cols.resize(oc.n);
+    bool need_pidx = false;
+    for (int c = 0; c < oc.n; ++c) {
+      const int otype = j->out_side[c] == 0 ? j->build_types[j->out_index[c]] : j->probe_types[j->out_index[c]];
+      oc.kind[c] = j->out_kind[c]; oc.width[c] = type_width(otype); oc.shift[c] = j->out_shift[c];
+      if (j->out_kind[c] == 0 && (cols[j->out_src[c]].validity || otype == DFGPU_BOOL)) { oc.kind[c] = 2; need_pidx = true; continue; }  // gathered afterwards
+      DCol d = alloc_col(ctx, otype, n, false);
+      oc.dst[c] = d.own_values->ptr;
+      oc.src[c] = j->out_kind[c] == 0 ? cols[j->out_src[c]].values : nullptr;
+      out->cols[c] = std::move(d);
+    }
+    DevBuf pidx;
+    if (need_pidx) { pidx.alloc(ctx, (size_t)n * 4); oc.pidx_out = pidx.as<uint32_t>(); }
+    const int64_t nt = (n + kFusedTile - 1) / kFusedTile;
+    DevBuf desc(ctx, (size_t)nt * 8 + 32);
+    desc.zero();
+    unsigned long long* totals = (unsigned long long*)((char*)desc.ptr + (size_t)nt * 8);
+    unsigned int* counter = (unsigned int*)(totals + 2);
+    {
+      KernelTimer kt(ctx, "join_probe");
+      if (j->inline_words == 2) join_probe_inline_kernel<2><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
+      else join_probe_inline_kernel<1><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
+      DF_LAUNCH_CHECK(ctx);
+    }
+    unsigned long long h[2];
+    DF_CUDA(cudaMemcpyAsync(h, totals, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    DF_CUDA(cudaStreamSynchronize(ctx->stream));
+    out->rows = (int64_t)h[0];
+    for (int c = 0; c < oc.n; ++c) {
+      if (oc.kind[c] == 2) out->cols[c] = take_column(ctx, cols[j->out_src[c]], pidx.as<uint32_t>(), out->rows, false);
+      else out->cols[c].length = out->rows;
+    }
+    j->m_probe_hits += (int64_t)h[1];
+    if (out->rows > 0) emit_batch(j, std::move(out));
+    return;
+  }
   // ---- fused single-pass path: unique build keys, one output row per matching probe row, plain columns ----
   if (mode == EMIT_PAIRS && j->unique && !j->opt.force_hash_collisions && j->out_side.size() <= (size_t)kMaxFusedCols) {
     bool plain = true;
@@ -804,6 +1075,130 @@ static void push_probe(dfgpu_hashjoin* j, std::vector<DCol>&& cols) {
     out = materialize(j, &cols, nullptr, pidx.as<uint32_t>(), (int64_t)total, true, false, nullptr);
   j->m_probe_hits += (int64_t)read_scalar<unsigned long long>(ctx, hits.as<unsigned long long>());
   if (out->rows > 0) emit_batch(j, std::move(out));
+}
+
+// ------------------------------------------------------------------------------------------
+// pipelined host probe (inline table): the probe batch is cut into chunks; H2D of chunk i+1, the probe kernel
+// of chunk i and D2H of chunk i-1 run on three streams, so the PCIe link is busy in both directions while the
+// kernels run (the host entry point is PCIe-bound: 1.6 GB in + 2.4 GB out per C2 probe side vs ~4 ms of kernels).
+// Output rows land at consecutive offsets of ONE pinned host batch, in probe order.
+// ------------------------------------------------------------------------------------------
+static bool push_probe_host_pipelined(dfgpu_hashjoin* j, const dfgpu_column* hcols, int32_t n_cols) {
+  if (!j->inline_ok || n_cols != (int)j->probe_types.size()) return false;
+  const int64_t n = n_cols ? hcols[0].length : 0;
+  constexpr int64_t kChunk = 8ll << 20;
+  if (n < 2 * kChunk) return false;  // small batches: the simple path
+  for (int c = 0; c < n_cols; ++c) {
+    if (hcols[c].type != j->probe_types[c] || hcols[c].length != n) return false;
+    if (hcols[c].validity && hcols[c].null_count != 0) return false;
+    if (hcols[c].type == DFGPU_BOOL) return false;
+  }
+  dfgpu_ctx* ctx = j->ctx;
+  set_device(ctx);
+  if (!ctx->copy_in) { DF_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking)); DF_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking)); }
+  const int nout = (int)j->out_side.size();
+  const int64_t nchunks = (n + kChunk - 1) / kChunk;
+  // which probe columns are actually needed on the device (keys + gathered outputs)
+  std::vector<bool> need(n_cols, false);
+  for (int c : j->on_probe) need[c] = true;
+  for (int c = 0; c < nout; ++c) if (j->out_kind[c] == 0) need[j->out_src[c]] = true;
+  // double-buffered device staging
+  std::vector<std::vector<DevBuf>> din(2), dout(2);
+  std::vector<DevBuf> desc(2);
+  const int64_t nt = (kChunk + kFusedTile - 1) / kFusedTile;
+  for (int b = 0; b < 2; ++b) {
+    din[b].resize(n_cols); dout[b].resize(nout);
+    for (int c = 0; c < n_cols; ++c) if (need[c]) din[b][c].alloc(ctx, (size_t)kChunk * type_width(j->probe_types[c]));
+    for (int c = 0; c < nout; ++c) {
+      const int otype = j->out_side[c] == 0 ? j->build_types[j->out_index[c]] : j->probe_types[j->out_index[c]];
+      dout[b][c].alloc(ctx, (size_t)kChunk * type_width(otype));
+    }
+    desc[b].alloc(ctx, (size_t)nt * 8 + 32);
+  }
+  // the host result batch (capacity n rows: unique build keys => at most one output row per probe row)
+  BatchPtr hb(new dfgpu_batch());
+  hb->ctx = ctx; hb->host = true;
+  std::vector<int> owidth(nout);
+  for (int c = 0; c < nout; ++c) {
+    const int otype = j->out_side[c] == 0 ? j->build_types[j->out_index[c]] : j->probe_types[j->out_index[c]];
+    owidth[c] = type_width(otype);
+    HCol h;
+    h.type = otype; h.null_count = 0;
+    h.values = std::make_shared<HostBuf>((size_t)std::max<int64_t>(n, 1) * owidth[c]);
+    hb->hcols.push_back(std::move(h));
+  }
+  HostBuf totals_host((size_t)nchunks * 16);
+  std::vector<cudaEvent_t> ev_in(nchunks), ev_k(nchunks), ev_out(nchunks);
+  for (int64_t i = 0; i < nchunks; ++i) { DF_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming)); DF_CUDA(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming)); DF_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming)); }
+  cudaEvent_t ev_ready;
+  DF_CUDA(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+  DF_CUDA(cudaEventRecord(ev_ready, ctx->stream));  // build finished + staging allocated
+  DF_CUDA(cudaStreamWaitEvent(ctx->copy_in, ev_ready, 0));
+  DF_CUDA(cudaStreamWaitEvent(ctx->copy_out, ev_ready, 0));
+  auto issue_h2d = [&](int64_t i) {
+    const int b = (int)(i & 1);
+    const int64_t r0 = i * kChunk, len = std::min<int64_t>(kChunk, n - r0);
+    if (i >= 2) DF_CUDA(cudaStreamWaitEvent(ctx->copy_in, ev_k[i - 2], 0));  // staging buffer b consumed by chunk i-2's kernel
+    for (int c = 0; c < n_cols; ++c) {
+      if (!need[c]) continue;
+      const int w = type_width(j->probe_types[c]);
+      DF_CUDA(cudaMemcpyAsync(din[b][c].ptr, (const char*)hcols[c].values + (hcols[c].offset + r0) * w, (size_t)len * w, cudaMemcpyHostToDevice, ctx->copy_in));
+    }
+    DF_CUDA(cudaEventRecord(ev_in[i], ctx->copy_in));
+  };
+  int64_t out_rows = 0, hits = 0;
+  issue_h2d(0);
+  for (int64_t i = 0; i < nchunks; ++i) {
+    const int b = (int)(i & 1);
+    const int64_t r0 = i * kChunk, len = std::min<int64_t>(kChunk, n - r0);
+    if (i + 1 < nchunks) issue_h2d(i + 1);
+    DF_CUDA(cudaStreamWaitEvent(ctx->stream, ev_in[i], 0));
+    if (i >= 2) DF_CUDA(cudaStreamWaitEvent(ctx->stream, ev_out[i - 2], 0));  // output staging b drained by chunk i-2's D2H
+    std::vector<DCol> cols(n_cols);
+    for (int c = 0; c < n_cols; ++c) { cols[c].type = j->probe_types[c]; cols[c].length = len; cols[c].values = din[b][c].ptr; }
+    KeyCols pk;
+    make_keycols(cols, j->on_probe, &pk);
+    InlineOut oc;
+    memset(&oc, 0, sizeof(oc));
+    oc.n = nout;
+    for (int c = 0; c < nout; ++c) {
+      oc.kind[c] = j->out_kind[c]; oc.width[c] = owidth[c]; oc.shift[c] = j->out_shift[c]; oc.dst[c] = dout[b][c].ptr;
+      oc.src[c] = j->out_kind[c] == 0 ? din[b][j->out_src[c]].ptr : nullptr;
+    }
+    DF_CUDA(cudaMemsetAsync(desc[b].ptr, 0, desc[b].bytes, ctx->stream));
+    const int64_t ntl = (len + kFusedTile - 1) / kFusedTile;
+    unsigned long long* totals = (unsigned long long*)((char*)desc[b].ptr + (size_t)nt * 8);
+    unsigned int* counter = (unsigned int*)(totals + 2);
+    {
+      KernelTimer kt(ctx, "join_probe");
+      if (j->inline_words == 2) join_probe_inline_kernel<2><<<(int)ntl, kFusedThreads, 0, ctx->stream>>>(pk, len, j->iref, oc, desc[b].as<unsigned long long>(), counter, totals);
+      else join_probe_inline_kernel<1><<<(int)ntl, kFusedThreads, 0, ctx->stream>>>(pk, len, j->iref, oc, desc[b].as<unsigned long long>(), counter, totals);
+      DF_LAUNCH_CHECK(ctx);
+    }
+    DF_CUDA(cudaMemcpyAsync((char*)totals_host.ptr + i * 16, totals, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    DF_CUDA(cudaEventRecord(ev_k[i], ctx->stream));
+    DF_CUDA(cudaEventSynchronize(ev_k[i]));  // the chunk's output row count decides where its rows land on the host
+    const unsigned long long* th = (const unsigned long long*)((char*)totals_host.ptr + i * 16);
+    const int64_t rows = (int64_t)th[0];
+    hits += (int64_t)th[1];
+    for (int c = 0; c < nout; ++c)
+      if (rows) DF_CUDA(cudaMemcpyAsync((char*)hb->hcols[c].values->ptr + (size_t)out_rows * owidth[c], dout[b][c].ptr, (size_t)rows * owidth[c], cudaMemcpyDeviceToHost, ctx->copy_out));
+    DF_CUDA(cudaEventRecord(ev_out[i], ctx->copy_out));
+    out_rows += rows;
+  }
+  DF_CUDA(cudaStreamSynchronize(ctx->copy_out));
+  DF_CUDA(cudaStreamSynchronize(ctx->copy_in));
+  DF_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int64_t i = 0; i < nchunks; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_k[i]); cudaEventDestroy(ev_out[i]); }
+  cudaEventDestroy(ev_ready);
+  hb->rows = out_rows;
+  for (auto& h : hb->hcols) h.length = out_rows;
+  j->m_input_rows += n;
+  j->m_input_batches++;
+  j->m_probe_hits += hits;
+  j->probe_side_non_empty = true;
+  if (out_rows > 0) emit_batch(j, std::move(hb));
+  return true;
 }
 
 static void finish_probe(dfgpu_hashjoin* j) {
@@ -940,7 +1335,9 @@ int dfgpu_hashjoin_finish_build(dfgpu_hashjoin* j) {
 }
 int dfgpu_hashjoin_push_probe_host(dfgpu_hashjoin* j, const dfgpu_column* cols, int32_t n_cols) {
   DF_API_BEGIN(j ? j->ctx : nullptr)
-  push_probe(j, host_cols_to_device(j->ctx, cols, n_cols));
+  DF_CHECK(j->built, DFGPU_ERR_STATE, "push_probe before finish_build");
+  DF_CHECK(!j->probe_done, DFGPU_ERR_STATE, "push_probe after finish_probe");
+  if (!push_probe_host_pipelined(j, cols, n_cols)) push_probe(j, host_cols_to_device(j->ctx, cols, n_cols));
   DF_API_END
 }
 int dfgpu_hashjoin_push_probe_device(dfgpu_hashjoin* j, const dfgpu_column* cols, int32_t n_cols) {
@@ -960,7 +1357,8 @@ int dfgpu_hashjoin_next(dfgpu_hashjoin* j, int host, dfgpu_batch** out) {
     if (j->outq.empty()) { *out = nullptr; return DFGPU_END; }
     BatchPtr b = std::move(j->outq.front());
     j->outq.pop_front();
-    if (host) { set_device(j->ctx); b = to_host_batch(j->ctx, *b); }
+    if (host && !b->host) { set_device(j->ctx); b = to_host_batch(j->ctx, *b); }
+    DF_CHECK(host || !b->host, DFGPU_ERR_STATE, "this batch was produced on the host (pipelined host probe): call next(host=1)");
     *out = b.release();
     return DFGPU_OK;
   } catch (const dfgpu::Error& e) { if (_ctx) _ctx->last_error = e.what(); return e.code; }

@@ -29,6 +29,43 @@ __global__ void stream_red_kernel(const int4* in, unsigned long long* a, unsigne
     atomicAdd(&b[s], 1ull);
   }
 }
+// the group-by inner loop: stream {key,value}, find the key's slot (tag compare), 2 REDs; R rows per thread
+__global__ void fill_rand_kernel(int4* in, int64_t n, uint64_t groups) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t k = mix64(i * 2 + 1) % groups, v = mix64(i * 2 + 2);
+    in[i] = make_int4((int)k, (int)(k >> 32), (int)v, (int)(v >> 32));
+  }
+}
+__global__ void fill_tags_kernel(unsigned long long* tags, uint64_t slots, uint64_t groups) {
+  for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < groups; g += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t s = __umul64hi(mix64(g), slots);
+    while (atomicCAS(&tags[s], ~0ull, (unsigned long long)g) != ~0ull) { if (tags[s] == g) break; if (++s == slots) s = 0; }
+  }
+}
+template <int R, int TAG>
+__global__ void groupby_kernel(const int4* __restrict__ in, const unsigned long long* __restrict__ tags, unsigned long long* a, unsigned long long* b,
+                               uint64_t slots, int64_t n) {
+  for (int64_t base = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * R; base < n; base += (int64_t)gridDim.x * blockDim.x * R) {
+    int4 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = base + r < n ? in[base + r] : make_int4(0, 0, 0, 0);
+    uint64_t s[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { uint64_t k = ((uint64_t)(uint32_t)v[r].y << 32) | (uint32_t)v[r].x; s[r] = __umul64hi(mix64(k), slots); }
+    if (TAG) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        uint64_t k = ((uint64_t)(uint32_t)v[r].y << 32) | (uint32_t)v[r].x;
+        while (__ldcg(&tags[s[r]]) != k) { if (++s[r] == slots) s[r] = 0; }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) if (base + r < n) {
+      atomicAdd(&a[s[r]], ((unsigned long long)(uint32_t)v[r].w << 32) | (uint32_t)v[r].z);
+      atomicAdd(&b[s[r]], 1ull);
+    }
+  }
+}
 template <int W64>
 __global__ void smem_atomic_kernel(int64_t n, int slots, unsigned long long* out) {
   extern __shared__ unsigned long long sm[];
@@ -72,7 +109,7 @@ int main() {
   CK(cudaMalloc(&a, 1ull << 30)); CK(cudaMalloc(&b, 1ull << 30)); CK(cudaMalloc(&out, 1 << 20)); CK(cudaMalloc(&in, (size_t)n * 16));
   CK(cudaMemset(a, 0, 1ull << 30)); CK(cudaMemset(b, 0, 1ull << 30)); CK(cudaMemset(in, 1, (size_t)n * 16));
   const int grid = 148 * 8, blk = 256;
-  for (uint64_t slots : {1ull << 20, 1ull << 22, 1ull << 24, 1ull << 26}) {
+  for (uint64_t slots : {1ull << 22}) {
     printf("slots=%llu (%.0f MB of u64)\n", (unsigned long long)slots, slots * 8 / 1e6);
     float t;
     t = time_it([&] { red_kernel<0><<<grid, blk>>>(a, b, slots, n); }); printf("  1x RED.64            : %7.3f ms  %6.1f Gops/s\n", t, n / t / 1e6);
@@ -81,7 +118,17 @@ int main() {
     t = time_it([&] { red_kernel<3><<<grid, blk>>>(a, b, slots, n); }); printf("  1x RED.32            : %7.3f ms  %6.1f Gops/s\n", t, n / t / 1e6);
     t = time_it([&] { red_kernel<4><<<grid, blk>>>(a, b, slots, n); }); printf("  2x RED.32 adjacent   : %7.3f ms  %6.1f Grows/s\n", t, n / t / 1e6);
     t = time_it([&] { red_kernel<5><<<grid, blk>>>(a, b, slots, n); }); printf("  RED.64+RED.32 adj    : %7.3f ms  %6.1f Grows/s\n", t, n / t / 1e6);
-    t = time_it([&] { stream_red_kernel<<<grid, blk>>>(in, a, b, slots, n); }); printf("  stream16B + 2xRED.64 : %7.3f ms  %6.1f Grows/s\n", t, n / t / 1e6);
+  }
+  {
+    const uint64_t groups = 1000000, slots = 4000000;
+    unsigned long long* tags; CK(cudaMalloc(&tags, slots * 8)); CK(cudaMemset(tags, 0xFF, slots * 8));
+    fill_rand_kernel<<<grid, blk>>>(in, n, groups); fill_tags_kernel<<<grid, blk>>>(tags, slots, groups); CK(cudaDeviceSynchronize());
+    float t;
+    t = time_it([&] { groupby_kernel<1, 0><<<grid, blk>>>(in, tags, a, b, slots, n); }); printf("groupby R=1 no-tag : %7.3f ms %6.1f Grows/s\n", t, n / t / 1e6);
+    t = time_it([&] { groupby_kernel<1, 1><<<grid, blk>>>(in, tags, a, b, slots, n); }); printf("groupby R=1 tag    : %7.3f ms %6.1f Grows/s\n", t, n / t / 1e6);
+    t = time_it([&] { groupby_kernel<4, 1><<<grid, blk>>>(in, tags, a, b, slots, n); }); printf("groupby R=4 tag    : %7.3f ms %6.1f Grows/s\n", t, n / t / 1e6);
+    t = time_it([&] { groupby_kernel<4, 1><<<148 * 16, 128>>>(in, tags, a, b, slots, n); }); printf("groupby R=4 tag 128thr: %7.3f ms %6.1f Grows/s\n", t, n / t / 1e6);
+    t = time_it([&] { groupby_kernel<8, 1><<<grid, blk>>>(in, tags, a, b, slots, n); }); printf("groupby R=8 tag    : %7.3f ms %6.1f Grows/s\n", t, n / t / 1e6);
   }
   for (int slots : {2048, 8192, 16384}) {
     CK(cudaFuncSetAttribute(smem_atomic_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
