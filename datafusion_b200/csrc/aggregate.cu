@@ -185,6 +185,7 @@ struct TableDev {
   unsigned long long* ngroups;  // claimed regular slots
   uint64_t group_limit;         // stop claiming beyond this (load-factor guard)
   uint32_t* special_used;       // [0]: slot cap (key == all-ones), [1]: slot cap+1 (NULL group)
+  int bucketed;                 // probe sequences start on a 32-byte boundary (4 x 8-byte tags): one sector holds the first 4 candidates
 };
 
 __device__ __forceinline__ Key2 cas128(Key2* addr, Key2 cmp, Key2 val) {
@@ -198,6 +199,7 @@ __device__ __forceinline__ Key2 cas128(Key2* addr, Key2 cmp, Key2 val) {
 template <int KW>
 __device__ __forceinline__ uint64_t start_slot(const TableDev& t, const Key2& k) {
   uint64_t h = KW == 1 ? hash_u64(k.lo, kSeedAgg) : hash_combine(hash_u64(k.lo, kSeedAgg), k.hi);
+  if (KW == 1 && t.bucketed) return __umul64hi(h, t.cap >> 2) << 2;
   return __umul64hi(h, t.cap);
 }
 template <int KW>
@@ -295,6 +297,84 @@ __global__ void __launch_bounds__(256) agg_update_kernel(GroupCols g, AggSet agg
     }
   }
 }
+// ---- fast path: one non-null 8-byte key, every aggregate of the form acc[slot] += (column ? column[row] : 1) ----
+// (SUM over a non-null 8-byte integer column, COUNT / COUNT(*) without NULLs or FILTER, and their Final-mode
+// merges) — the C3 shape.  No type switches, no validity reads; 4 rows per thread with the loads hoisted.
+constexpr int kMaxFastAggs = 4;
+struct FastAggs { int n; const unsigned long long* col[kMaxFastAggs]; unsigned long long* acc[kMaxFastAggs]; };
+
+template <int R, int NA, int B>
+__global__ void __launch_bounds__(256) agg_update_fast_kernel(const unsigned long long* __restrict__ keys, FastAggs fa, TableDev t, int64_t row0, int64_t n,
+                                                           const uint32_t* __restrict__ row_list, uint32_t* __restrict__ overflow,
+                                                           unsigned long long* __restrict__ overflow_count) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < n; i0 += stride * R) {
+    int64_t row[R];
+    unsigned long long k[R], cur[R], v[R][NA];
+    uint4 bk0[B ? R : 1], bk1[B ? R : 1];
+    uint64_t s[R];
+    bool live[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t i = i0 + r * stride;
+      live[r] = i < n;
+      row[r] = live[r] ? row0 + (row_list ? (int64_t)row_list[i] : i) : row0;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) k[r] = live[r] ? keys[row[r]] : 0ull;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int a = 0; a < NA; ++a) v[r][a] = (fa.col[a] && live[r]) ? fa.col[a][row[r]] : 1ull;
+#pragma unroll
+    for (int r = 0; r < R; ++r) { s[r] = start_slot<1>(t, Key2{k[r], 0ull}); cur[r] = 0; }
+    if (B) {
+      // the 32-byte sector at the (aligned) start slot holds the first four candidates: fetch it whole
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        bk0[r] = make_uint4(0, 0, 0, 0); bk1[r] = bk0[r];
+        if (live[r] && k[r] != kEmptyKey) { const uint4* bp = (const uint4*)((const unsigned long long*)t.tags + s[r]); bk0[r] = __ldcg(bp); bk1[r] = __ldcg(bp + 1); }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (!(live[r] && k[r] != kEmptyKey)) continue;
+        const unsigned long long t0 = (unsigned long long)bk0[r].x | ((unsigned long long)bk0[r].y << 32), t1 = (unsigned long long)bk0[r].z | ((unsigned long long)bk0[r].w << 32);
+        const unsigned long long t2 = (unsigned long long)bk1[r].x | ((unsigned long long)bk1[r].y << 32), t3 = (unsigned long long)bk1[r].z | ((unsigned long long)bk1[r].w << 32);
+        // first slot that either holds the key or is empty (linear-probing order inside the sector)
+        if (t0 == k[r] || t0 == kEmptyKey) { cur[r] = t0; }
+        else if (t1 == k[r] || t1 == kEmptyKey) { cur[r] = t1; s[r] += 1; }
+        else if (t2 == k[r] || t2 == kEmptyKey) { cur[r] = t2; s[r] += 2; }
+        else { cur[r] = t3; s[r] += 3; }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) if (live[r] && k[r] != kEmptyKey) cur[r] = __ldcg((const unsigned long long*)t.tags + s[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      bool claimed = false;
+      uint64_t slot = ~0ull;
+      if (live[r]) {
+        if (k[r] == kEmptyKey) slot = find_or_claim<1>(t, Key2{k[r], 0ull}, false, true, &claimed);
+        else slot = find_or_claim_from<1>(t, Key2{k[r], 0ull}, s[r], Key2{cur[r], 0ull}, &claimed);
+      }
+      {
+        const unsigned act = __activemask();
+        const unsigned m = __ballot_sync(act, claimed);
+        if (m && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) atomicAdd(t.ngroups, (unsigned long long)__popc(m));
+      }
+      if (!live[r]) continue;
+      if (slot == ~0ull) {
+        unsigned long long pos = atomicAdd(overflow_count, 1ull);
+        overflow[pos] = (uint32_t)(row[r] - row0);
+        continue;
+      }
+#pragma unroll
+      for (int a = 0; a < NA; ++a) atomicAdd(&fa.acc[a][slot], v[r][a]);
+    }
+  }
+}
+
 struct AccArrays { int n; void* ptr[kMaxAggs * 3]; void* new_ptr[kMaxAggs * 3]; int elem[kMaxAggs * 3]; };
 
 // grow: re-insert every occupied slot of the old table into the new one and move its accumulators
@@ -474,7 +554,7 @@ struct dfgpu_agg {
   int64_t batch_size = 8192;
   int kw = 1;
   int key_bits = 0;
-  bool finished = false, emitted = false, hinted = false;
+  bool finished = false, emitted = false, hinted = false, bucketed = false;
   // key packing
   std::vector<int> g_shift, g_width_bits, g_null_bit;
   bool single_null_slot = false;
@@ -492,8 +572,9 @@ static TableDev table_dev(dfgpu_agg* a, DevBuf& tags, uint64_t cap, DevBuf& coun
   t.tags = tags.ptr;
   t.cap = cap;
   t.ngroups = counters.as<unsigned long long>();
-  t.group_limit = cap / 2;  // load factor <= 0.5
+  t.group_limit = cap / 8 * 5;  // claims stop at load factor 0.625; the host grows the table beyond 0.5
   t.special_used = special.as<uint32_t>();
+  t.bucketed = a->bucketed ? 1 : 0;
   return t;
 }
 
@@ -614,11 +695,25 @@ static void agg_push(dfgpu_agg* a, const std::vector<DCol>& cols) {
     // NullState: switch to explicit seen tracking once nulls or a filter show up (accumulate.rs:164-188)
     if ((in0 && in0->validity) || filt) ensure_seen(a, s);
   }
+  // fast-path eligibility (decided per batch: it depends on the validity of THIS batch's columns)
+  static const int fast_enabled = getenv("DFGPU_AGG_FAST") ? atoi(getenv("DFGPU_AGG_FAST")) : 1;
+  bool fast = fast_enabled && a->kw == 1 && g.n == 1 && g.width[0] == 8 && !g.valid[0] && !g.is_float[0] && set.n >= 1 && set.n <= kMaxFastAggs;
+  FastAggs fa;
+  memset(&fa, 0, sizeof(fa));
+  for (int i = 0; i < set.n && fast; ++i) {
+    const AggDev& d = set.a[i];
+    const bool sum_like = (d.func == DFGPU_AGG_SUM && d.cls != 2 && type_width(d.in0_type) == 8) || ((d.func == DFGPU_AGG_COUNT || d.func == DFGPU_AGG_COUNT_STAR) && d.merge);
+    const bool count_like = (d.func == DFGPU_AGG_COUNT || d.func == DFGPU_AGG_COUNT_STAR) && !d.merge;
+    if (d.filt || d.in0_valid || a->aggs[i].track_seen || !(sum_like || count_like)) { fast = false; break; }
+    fa.col[i] = sum_like ? (const unsigned long long*)d.in0 : nullptr;
+  }
+  fa.n = set.n;
   auto refresh_ptrs = [&]() {
     for (int i = 0; i < set.n; ++i) {
       set.a[i].acc0 = a->aggs[i].acc0.as<unsigned long long>();
       set.a[i].acc1 = a->aggs[i].acc1.as<unsigned long long>();
       set.a[i].seen = a->aggs[i].seen.as<uint8_t>();
+      if (i < kMaxFastAggs) fa.acc[i] = a->aggs[i].acc0.as<unsigned long long>();
     }
   };
   // chunked processing with ramp-up so an undersized table is discovered cheaply
@@ -641,7 +736,27 @@ static void agg_push(dfgpu_agg* a, const std::vector<DCol>& cols) {
       int grid = grid_for((work + 3) / 4, 256, kNumSMs * 8);
       {
         KernelTimer kt(ctx, "agg_update");
-        if (a->kw == 1)
+        if (fast) {
+          const unsigned long long* kp = (const unsigned long long*)g.ptr[0];
+          uint32_t* ov = overflow.as<uint32_t>();
+          unsigned long long* oc = a->counters.as<unsigned long long>() + 1;
+          if (a->bucketed) {
+            const int grid2 = grid_for((work + 1) / 2, 256, kNumSMs * 8);
+            switch (fa.n) {
+              case 1: agg_update_fast_kernel<2, 1, 1><<<grid2, 256, 0, ctx->stream>>>(kp, fa, t, done, work, list, ov, oc); break;
+              case 2: agg_update_fast_kernel<2, 2, 1><<<grid2, 256, 0, ctx->stream>>>(kp, fa, t, done, work, list, ov, oc); break;
+              case 3: agg_update_fast_kernel<2, 3, 1><<<grid2, 256, 0, ctx->stream>>>(kp, fa, t, done, work, list, ov, oc); break;
+              default: agg_update_fast_kernel<2, 4, 1><<<grid2, 256, 0, ctx->stream>>>(kp, fa, t, done, work, list, ov, oc); break;
+            }
+          } else {
+            switch (fa.n) {
+              case 1: agg_update_fast_kernel<4, 1, 0><<<grid, 256, 0, ctx->stream>>>(kp, fa, t, done, work, list, ov, oc); break;
+              case 2: agg_update_fast_kernel<4, 2, 0><<<grid, 256, 0, ctx->stream>>>(kp, fa, t, done, work, list, ov, oc); break;
+              case 3: agg_update_fast_kernel<4, 3, 0><<<grid, 256, 0, ctx->stream>>>(kp, fa, t, done, work, list, ov, oc); break;
+              default: agg_update_fast_kernel<4, 4, 0><<<grid, 256, 0, ctx->stream>>>(kp, fa, t, done, work, list, ov, oc); break;
+            }
+          }
+        } else if (a->kw == 1)
           agg_update_kernel<1, 4><<<grid, 256, 0, ctx->stream>>>(g, set, t, done, work, list, overflow.as<uint32_t>(), a->counters.as<unsigned long long>() + 1);
         else
           agg_update_kernel<2, 4><<<grid, 256, 0, ctx->stream>>>(g, set, t, done, work, list, overflow.as<uint32_t>(), a->counters.as<unsigned long long>() + 1);
@@ -652,8 +767,8 @@ static void agg_push(dfgpu_agg* a, const std::vector<DCol>& cols) {
       DF_CUDA(cudaStreamSynchronize(ctx->stream));
       a->m_num_groups = (int64_t)hc[0];
       if (hc[1] == 0) {
-        // keep the load factor below 1/4 ahead of the next chunk so steady-state chunks never overflow
-        if (hc[0] * 4 > a->cap) grow_table(a, a->cap * 4);
+        // grow once the load factor passes 1/2 (probe length and the claim budget of the next chunk)
+        if (hc[0] * 2 > a->cap) grow_table(a, a->cap * 4);
         break;
       }
       // deferred rows: grow, then replay just those rows
@@ -662,7 +777,7 @@ static void agg_push(dfgpu_agg* a, const std::vector<DCol>& cols) {
       list = replay.as<uint32_t>();
       work = (int64_t)hc[1];
       uint64_t want = std::max<uint64_t>(a->cap * 4, (hc[0] + hc[1]) * 2);
-      grow_table(a, want);
+      grow_table(a, (want + 3) & ~3ull);
     }
     done += m;
     chunk = std::min<int64_t>(chunk * 4, kMaxChunk);
@@ -832,7 +947,14 @@ int dfgpu_agg_create(dfgpu_ctx* ctx, const int32_t* input_types, int32_t n_cols,
   }
   // table
   uint64_t cap = 1 << 16;
-  if (capacity_hint > 0) { cap = std::max<uint64_t>(cap, (uint64_t)capacity_hint * 4); a->hinted = true; }
+  // with a hint the table is sized for load factor 0.5 at the hinted group count: tags + accumulators of the C3
+  // shape are then 48 MB and stay L2-resident next to the input stream (at 0.25 the 96 MB table thrashed:
+  // ncu showed 8.6 GB DRAM reads for 4 GB of input, profiles/r1e_agg_update_250M_rows.csv)
+  static const int cap_mult = getenv("DFGPU_AGG_CAPMULT") ? atoi(getenv("DFGPU_AGG_CAPMULT")) : 3;
+  static const int bucket_env = getenv("DFGPU_AGG_BUCKET") ? atoi(getenv("DFGPU_AGG_BUCKET")) : 1;
+  a->bucketed = bucket_env != 0;
+  if (capacity_hint > 0) { cap = std::max<uint64_t>(cap, (uint64_t)capacity_hint * cap_mult); a->hinted = true; }
+  cap = (cap + 3) & ~3ull;
   a->cap = cap;
   a->counters.alloc(ctx, 16); a->counters.zero();
   a->special_used.alloc(ctx, 8); a->special_used.zero();

@@ -120,6 +120,8 @@ struct dfgpu_ctx {
   // steady state performs no cudaMalloc / pool growth at all.
   std::multimap<size_t, void*> dev_free;
   std::unordered_map<void*, size_t> dev_sizes;
+  size_t dev_free_bytes = 0;
+  size_t dev_cache_limit = 24ull << 30;  // idle blocks kept for reuse; beyond it the largest idle blocks are returned to the driver
   cudaStream_t copy_in = nullptr, copy_out = nullptr;  // lazily created: H2D / D2H streams of the pipelined host entry points
   bool time_kernels = false;                    // dfgpu_set_kernel_timing
   std::vector<dfgpu_kernel_timing> timings;     // per kernel family
@@ -149,11 +151,12 @@ inline void dev_cache_trim(dfgpu_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->dev_free) { cudaFree(kv.second); ctx->dev_sizes.erase(kv.second); }
   ctx->dev_free.clear();
+  ctx->dev_free_bytes = 0;
 }
 inline void* dev_alloc(dfgpu_ctx* ctx, size_t n) {
   const size_t b = dev_bucket(n);
   auto it = ctx->dev_free.find(b);
-  if (it != ctx->dev_free.end()) { void* p = it->second; ctx->dev_free.erase(it); return p; }
+  if (it != ctx->dev_free.end()) { void* p = it->second; ctx->dev_free.erase(it); ctx->dev_free_bytes -= b; return p; }
   void* p = nullptr;
   cudaError_t e = cudaMalloc(&p, b);
   if (e != cudaSuccess) {
@@ -169,6 +172,17 @@ inline void dev_free(dfgpu_ctx* ctx, void* p) {
   auto it = ctx->dev_sizes.find(p);
   if (it == ctx->dev_sizes.end()) { cudaFree(p); return; }
   ctx->dev_free.emplace(it->second, p);
+  ctx->dev_free_bytes += it->second;
+  if (ctx->dev_free_bytes > ctx->dev_cache_limit) {
+    cudaStreamSynchronize(ctx->stream);  // blocks about to be returned may still be in use by queued work
+    while (ctx->dev_free_bytes > ctx->dev_cache_limit / 2 && !ctx->dev_free.empty()) {
+      auto last = std::prev(ctx->dev_free.end());  // largest idle block first
+      cudaFree(last->second);
+      ctx->dev_free_bytes -= last->first;
+      ctx->dev_sizes.erase(last->second);
+      ctx->dev_free.erase(last);
+    }
+  }
 }
 
 // stream-ordered device buffer (cudaMallocAsync pool: no implicit device sync on alloc/free)

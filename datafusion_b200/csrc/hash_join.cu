@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(kFusedThreads) join_probe_fused_kernel(KeyCols
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxPayloadCols = 8;
 struct PayloadCols { int n; const void* ptr[kMaxPayloadCols]; int width[kMaxPayloadCols]; int shift[kMaxPayloadCols]; };
-struct InlineRef { void* slots; uint64_t cap; int dense; uint64_t amin; };
+struct InlineRef { void* slots; uint64_t cap; int dense; uint64_t amin; int bucket; /* probe sequences start on a 4-slot boundary (one 64 B line for 16 B slots) */ };
 struct InlineOut {
   int n;
   int kind[kMaxFusedCols];   // 0: gather from a probe-side column by probe row; 1: extract from the payload word
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(256) join_build_inline_kernel(KeyCols kc, Payl
     valid++;
     if (tag == kEmpty64) { fail = 1; continue; }
     const uint64_t pay = W == 2 ? load_payload(pc, row) : 0ull;
-    uint64_t s = t.dense ? (tag - t.amin) : __umul64hi(hash_u64(tag, kSeedJoin), t.cap);
+    uint64_t s = t.dense ? (tag - t.amin) : (t.bucket ? (__umul64hi(hash_u64(tag, kSeedJoin), t.cap >> 2) << 2) : __umul64hi(hash_u64(tag, kSeedJoin), t.cap));
     while (true) {
       unsigned long long prev;
       if (W == 2) prev = cas128((Slot128*)t.slots + s, Slot128{kEmpty64, kEmpty64}, Slot128{tag, pay}).lo;
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(256) join_build_inline_kernel(KeyCols kc, Payl
 }
 
 template <int W>
-__global__ void __launch_bounds__(kFusedThreads) join_probe_inline_kernel(KeyCols kc, int64_t n, InlineRef t, InlineOut oc,
+__global__ void __launch_bounds__(kFusedThreads) join_probe_inline_v0_kernel(KeyCols kc, int64_t n, InlineRef t, InlineOut oc,
                                                                        unsigned long long* __restrict__ tile_desc, unsigned int* __restrict__ tile_counter,
                                                                        unsigned long long* __restrict__ totals) {
   __shared__ unsigned long long s_pay[W == 2 ? kFusedTile : 1];
@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(kFusedThreads) join_probe_inline_kernel(KeyCol
     slot[k] = 0;
     if (live[k]) {
       if (t.dense) { slot[k] = tags[k] - t.amin; if (slot[k] >= t.cap) live[k] = false; }
-      else slot[k] = __umul64hi(hash_u64(tags[k], kSeedJoin), t.cap);
+      else slot[k] = t.bucket ? (__umul64hi(hash_u64(tags[k], kSeedJoin), t.cap >> 2) << 2) : __umul64hi(hash_u64(tags[k], kSeedJoin), t.cap);
     }
   }
   uint64_t cur[kFusedItems], curp[kFusedItems];
@@ -599,6 +599,263 @@ __global__ void __launch_bounds__(kFusedThreads) join_probe_inline_kernel(KeyCol
   const unsigned long long base = s_base;
   const int64_t prow0 = tile * kFusedTile;
   if (oc.pidx_out) for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) oc.pidx_out[base + j] = (uint32_t)(prow0 + s_p[j]);
+  for (int c = 0; c < oc.n; ++c) {
+    if (oc.kind[c] == 0) {
+      switch (oc.width[c]) {
+        case 8: { const uint64_t* src = (const uint64_t*)oc.src[c]; uint64_t* dst = (uint64_t*)oc.dst[c] + base;
+                  for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = src[prow0 + s_p[j]]; break; }
+        case 4: { const uint32_t* src = (const uint32_t*)oc.src[c]; uint32_t* dst = (uint32_t*)oc.dst[c] + base;
+                  for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = src[prow0 + s_p[j]]; break; }
+        case 2: { const uint16_t* src = (const uint16_t*)oc.src[c]; uint16_t* dst = (uint16_t*)oc.dst[c] + base;
+                  for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = src[prow0 + s_p[j]]; break; }
+        case 1: { const uint8_t* src = (const uint8_t*)oc.src[c]; uint8_t* dst = (uint8_t*)oc.dst[c] + base;
+                  for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = src[prow0 + s_p[j]]; break; }
+        default: { const uint4* src = (const uint4*)oc.src[c]; uint4* dst = (uint4*)oc.dst[c] + base;
+                  for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = src[prow0 + s_p[j]]; break; }
+      }
+    } else if (oc.kind[c] == 1 && W == 2) {
+      const int sh = oc.shift[c];
+      switch (oc.width[c]) {
+        case 8: { uint64_t* dst = (uint64_t*)oc.dst[c] + base; for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = s_pay[j]; break; }
+        case 4: { uint32_t* dst = (uint32_t*)oc.dst[c] + base; for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = (uint32_t)(s_pay[j] >> sh); break; }
+        case 2: { uint16_t* dst = (uint16_t*)oc.dst[c] + base; for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = (uint16_t)(s_pay[j] >> sh); break; }
+        default: { uint8_t* dst = (uint8_t*)oc.dst[c] + base; for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = (uint8_t)(s_pay[j] >> sh); break; }
+      }
+    }
+  }
+}
+
+constexpr int kStageCols = 4;   // probe-side output columns staged through shared memory (8 B each per row)
+
+// width-generic loads / stores of one value as 64 bits
+__device__ __forceinline__ uint64_t load_w(const void* p, int width, int64_t i) {
+  switch (width) {
+    case 1: return ((const uint8_t*)p)[i];
+    case 2: return ((const uint16_t*)p)[i];
+    case 4: return ((const uint32_t*)p)[i];
+    default: return ((const uint64_t*)p)[i];
+  }
+}
+__device__ __forceinline__ void store_w(void* p, int width, uint64_t i, uint64_t v) {
+  switch (width) {
+    case 1: ((uint8_t*)p)[i] = (uint8_t)v; break;
+    case 2: ((uint16_t*)p)[i] = (uint16_t)v; break;
+    case 4: ((uint32_t*)p)[i] = (uint32_t)v; break;
+    default: ((uint64_t*)p)[i] = v; break;
+  }
+}
+
+// Tile = 256 threads x 4 rows, rows interleaved (row = tile_base + k*256 + tid) so every global load of a
+// probe column is one fully coalesced 2 KB wavefront.  Matched rows are ranked in row order with warp
+// ballots + one 32-entry scan, their output values (payload word + up to 4 probe-side columns, read while
+// the lines are hot) are staged in shared memory, the tile's output offset comes from the decoupled
+// look-back, and every output column is then written with fully coalesced stores.
+template <int W>
+__global__ void __launch_bounds__(kFusedThreads) join_probe_inline_kernel(KeyCols kc, int64_t n, InlineRef t, InlineOut oc,
+                                                                       unsigned long long* __restrict__ tile_desc, unsigned int* __restrict__ tile_counter,
+                                                                       unsigned long long* __restrict__ totals) {
+  __shared__ unsigned long long s_pay[W == 2 ? kFusedTile : 1];
+  __shared__ unsigned long long s_val[kStageCols][kFusedTile];
+  __shared__ uint32_t s_p[kFusedTile];
+  __shared__ uint32_t s_cnt[kFusedItems * (kFusedThreads / 32) + 1];
+  __shared__ unsigned int s_tile;
+  __shared__ unsigned long long s_base;
+  if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+  __syncthreads();
+  const int64_t tile = s_tile;
+  const int64_t prow0 = tile * kFusedTile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t tags[kFusedItems], slot[kFusedItems], pays[kFusedItems], cur[kFusedItems], curp[kFusedItems];
+  bool live[kFusedItems], hit[kFusedItems];
+  // phase 1: keys, then first-slot loads, for all 4 rows before any is consumed (memory-level parallelism)
+#pragma unroll
+  for (int k = 0; k < kFusedItems; ++k) {
+    const int64_t i = prow0 + k * kFusedThreads + threadIdx.x;
+    live[k] = i < n && load_tag(kc, i, &tags[k]) && tags[k] != kEmpty64;
+    hit[k] = false; pays[k] = 0; slot[k] = 0;
+    if (live[k]) {
+      if (t.dense) { slot[k] = tags[k] - t.amin; if (slot[k] >= t.cap) live[k] = false; }
+      else slot[k] = __umul64hi(hash_u64(tags[k], kSeedJoin), t.cap);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kFusedItems; ++k) {
+    cur[k] = kEmpty64; curp[k] = 0;
+    if (live[k]) {
+      if (W == 2) { const uint4 v = __ldcg((const uint4*)t.slots + slot[k]); cur[k] = (uint64_t)v.x | ((uint64_t)v.y << 32); curp[k] = (uint64_t)v.z | ((uint64_t)v.w << 32); }
+      else cur[k] = __ldcg((const unsigned long long*)t.slots + slot[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kFusedItems; ++k) {
+    if (!live[k]) continue;
+    while (true) {  // linear probing continues only on a foreign key (never in dense mode)
+      if (cur[k] == tags[k]) { hit[k] = true; pays[k] = curp[k]; break; }
+      if (cur[k] == kEmpty64 || t.dense) break;
+      if (++slot[k] == t.cap) slot[k] = 0;
+      if (W == 2) { const uint4 v = __ldcg((const uint4*)t.slots + slot[k]); cur[k] = (uint64_t)v.x | ((uint64_t)v.y << 32); curp[k] = (uint64_t)v.z | ((uint64_t)v.w << 32); }
+      else cur[k] = __ldcg((const unsigned long long*)t.slots + slot[k]);
+    }
+  }
+  // phase 2: rank the matches in row order: (k, warp) segments are consecutive row ranges
+  uint32_t bal[kFusedItems];
+#pragma unroll
+  for (int k = 0; k < kFusedItems; ++k) {
+    bal[k] = __ballot_sync(0xffffffffu, hit[k]);
+    if (lane == 0) s_cnt[k * (kFusedThreads / 32) + warp] = __popc(bal[k]);
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of the 32 segment counts
+    uint32_t c = s_cnt[lane], inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t nb = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += nb; }
+    s_cnt[lane] = inc - c;
+    if (lane == 31) s_cnt[32] = inc;
+  }
+  __syncthreads();
+  const uint32_t tot = s_cnt[32];
+  // phase 3: stage output values of the matched rows
+#pragma unroll
+  for (int k = 0; k < kFusedItems; ++k) {
+    if (!hit[k]) continue;
+    const uint32_t pos = s_cnt[k * (kFusedThreads / 32) + warp] + __popc(bal[k] & ((1u << lane) - 1u));
+    const int64_t i = prow0 + k * kFusedThreads + threadIdx.x;
+    if (W == 2) s_pay[pos] = pays[k];
+    s_p[pos] = (uint32_t)(i - prow0);
+    int sc = 0;
+    for (int c = 0; c < oc.n; ++c)
+      if (oc.kind[c] == 0 && oc.width[c] <= 8 && sc < kStageCols) { s_val[sc][pos] = load_w(oc.src[c], oc.width[c], i); ++sc; }
+  }
+  if (threadIdx.x < 32) {
+    unsigned long long exclusive = tile_lookback(tile, tot, tile_desc);
+    if (threadIdx.x == 0) {
+      s_base = exclusive;
+      if ((tile + 1) * (int64_t)kFusedTile >= n) totals[0] = exclusive + tot;
+      if (tot) atomicAdd(&totals[1], (unsigned long long)tot);
+    }
+  }
+  __syncthreads();
+  const unsigned long long base = s_base;
+  if (oc.pidx_out) for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) oc.pidx_out[base + j] = (uint32_t)(prow0 + s_p[j]);
+  // phase 4: coalesced column writes
+  int sc = 0;
+  for (int c = 0; c < oc.n; ++c) {
+    if (oc.kind[c] == 0) {
+      if (oc.width[c] <= 8 && sc < kStageCols) {
+        const unsigned long long* sv = s_val[sc++];
+        switch (oc.width[c]) {
+          case 8: { uint64_t* dst = (uint64_t*)oc.dst[c] + base; for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = sv[j]; break; }
+          case 4: { uint32_t* dst = (uint32_t*)oc.dst[c] + base; for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = (uint32_t)sv[j]; break; }
+          case 2: { uint16_t* dst = (uint16_t*)oc.dst[c] + base; for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = (uint16_t)sv[j]; break; }
+          default: { uint8_t* dst = (uint8_t*)oc.dst[c] + base; for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = (uint8_t)sv[j]; break; }
+        }
+      } else if (oc.width[c] == 16) {
+        const uint4* src = (const uint4*)oc.src[c]; uint4* dst = (uint4*)oc.dst[c] + base;
+        for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = src[prow0 + s_p[j]];
+      } else {
+        for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) store_w(oc.dst[c], oc.width[c], base + j, load_w(oc.src[c], oc.width[c], prow0 + s_p[j]));
+      }
+    } else if (oc.kind[c] == 1 && W == 2) {
+      const int sh = oc.shift[c];
+      switch (oc.width[c]) {
+        case 8: { uint64_t* dst = (uint64_t*)oc.dst[c] + base; for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = s_pay[j]; break; }
+        case 4: { uint32_t* dst = (uint32_t*)oc.dst[c] + base; for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = (uint32_t)(s_pay[j] >> sh); break; }
+        case 2: { uint16_t* dst = (uint16_t*)oc.dst[c] + base; for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = (uint16_t)(s_pay[j] >> sh); break; }
+        default: { uint8_t* dst = (uint8_t*)oc.dst[c] + base; for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) dst[j] = (uint8_t)(s_pay[j] >> sh); break; }
+      }
+    }
+  }
+}
+
+// Tile = 256 threads x 4 rows, rows interleaved (row = tile_base + k*256 + tid) so every global load of a
+// probe column is one fully coalesced 2 KB wavefront.  Matched rows are ranked in row order with warp
+// ballots + one 32-entry scan, their output values (payload word + up to 4 probe-side columns, read while
+// the lines are hot) are staged in shared memory, the tile's output offset comes from the decoupled
+// look-back, and every output column is then written with fully coalesced stores.
+template <int W>
+__global__ void __launch_bounds__(kFusedThreads) join_probe_inline_v2_kernel(KeyCols kc, int64_t n, InlineRef t, InlineOut oc,
+                                                                       unsigned long long* __restrict__ tile_desc, unsigned int* __restrict__ tile_counter,
+                                                                       unsigned long long* __restrict__ totals) {
+  __shared__ unsigned long long s_pay[W == 2 ? kFusedTile : 1];
+  __shared__ uint32_t s_p[kFusedTile];
+  __shared__ uint32_t s_cnt[kFusedItems * (kFusedThreads / 32) + 1];
+  __shared__ unsigned int s_tile;
+  __shared__ unsigned long long s_base;
+  if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+  __syncthreads();
+  const int64_t tile = s_tile;
+  const int64_t prow0 = tile * kFusedTile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t tags[kFusedItems], slot[kFusedItems], pays[kFusedItems], cur[kFusedItems], curp[kFusedItems];
+  bool live[kFusedItems], hit[kFusedItems];
+  // phase 1: keys, then first-slot loads, for all 4 rows before any is consumed (memory-level parallelism)
+#pragma unroll
+  for (int k = 0; k < kFusedItems; ++k) {
+    const int64_t i = prow0 + k * kFusedThreads + threadIdx.x;
+    live[k] = i < n && load_tag(kc, i, &tags[k]) && tags[k] != kEmpty64;
+    hit[k] = false; pays[k] = 0; slot[k] = 0;
+    if (live[k]) {
+      if (t.dense) { slot[k] = tags[k] - t.amin; if (slot[k] >= t.cap) live[k] = false; }
+      else slot[k] = __umul64hi(hash_u64(tags[k], kSeedJoin), t.cap);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kFusedItems; ++k) {
+    cur[k] = kEmpty64; curp[k] = 0;
+    if (live[k]) {
+      if (W == 2) { const uint4 v = __ldcg((const uint4*)t.slots + slot[k]); cur[k] = (uint64_t)v.x | ((uint64_t)v.y << 32); curp[k] = (uint64_t)v.z | ((uint64_t)v.w << 32); }
+      else cur[k] = __ldcg((const unsigned long long*)t.slots + slot[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kFusedItems; ++k) {
+    if (!live[k]) continue;
+    while (true) {  // linear probing continues only on a foreign key (never in dense mode)
+      if (cur[k] == tags[k]) { hit[k] = true; pays[k] = curp[k]; break; }
+      if (cur[k] == kEmpty64 || t.dense) break;
+      if (++slot[k] == t.cap) slot[k] = 0;
+      if (W == 2) { const uint4 v = __ldcg((const uint4*)t.slots + slot[k]); cur[k] = (uint64_t)v.x | ((uint64_t)v.y << 32); curp[k] = (uint64_t)v.z | ((uint64_t)v.w << 32); }
+      else cur[k] = __ldcg((const unsigned long long*)t.slots + slot[k]);
+    }
+  }
+  // phase 2: rank the matches in row order: (k, warp) segments are consecutive row ranges
+  uint32_t bal[kFusedItems];
+#pragma unroll
+  for (int k = 0; k < kFusedItems; ++k) {
+    bal[k] = __ballot_sync(0xffffffffu, hit[k]);
+    if (lane == 0) s_cnt[k * (kFusedThreads / 32) + warp] = __popc(bal[k]);
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of the 32 segment counts
+    uint32_t c = s_cnt[lane], inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t nb = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += nb; }
+    s_cnt[lane] = inc - c;
+    if (lane == 31) s_cnt[32] = inc;
+  }
+  __syncthreads();
+  const uint32_t tot = s_cnt[32];
+  // phase 3: stage output values of the matched rows
+#pragma unroll
+  for (int k = 0; k < kFusedItems; ++k) {
+    if (!hit[k]) continue;
+    const uint32_t pos = s_cnt[k * (kFusedThreads / 32) + warp] + __popc(bal[k] & ((1u << lane) - 1u));
+    const int64_t i = prow0 + k * kFusedThreads + threadIdx.x;
+    if (W == 2) s_pay[pos] = pays[k];
+    s_p[pos] = (uint32_t)(i - prow0);
+  }
+  if (threadIdx.x < 32) {
+    unsigned long long exclusive = tile_lookback(tile, tot, tile_desc);
+    if (threadIdx.x == 0) {
+      s_base = exclusive;
+      if ((tile + 1) * (int64_t)kFusedTile >= n) totals[0] = exclusive + tot;
+      if (tot) atomicAdd(&totals[1], (unsigned long long)tot);
+    }
+  }
+  __syncthreads();
+  const unsigned long long base = s_base;
+  if (oc.pidx_out) for (uint32_t j = threadIdx.x; j < tot; j += kFusedThreads) oc.pidx_out[base + j] = (uint32_t)(prow0 + s_p[j]);
+  // phase 4: coalesced column writes
   for (int c = 0; c < oc.n; ++c) {
     if (oc.kind[c] == 0) {
       switch (oc.width[c]) {
@@ -850,10 +1107,13 @@ static void finish_build(dfgpu_hashjoin* j) {
     }
     if (ok) {
       const int W = pc.n ? 2 : 1;
-      const uint64_t cap = j->use_array_map ? j->table.asize : std::max<uint64_t>(1024, (uint64_t)n * 2);
+      static const int cap_pct = getenv("DFGPU_JOIN_CAP_PCT") ? atoi(getenv("DFGPU_JOIN_CAP_PCT")) : 250;  // table slots per 100 build rows
+      const uint64_t cap = j->use_array_map ? j->table.asize : ((std::max<uint64_t>(1024, (uint64_t)n * cap_pct / 100) + 3) & ~3ull);
       j->inline_slots.alloc(ctx, (size_t)cap * 8 * W);
       j->inline_slots.fill(0xFF);
+      static const int bucket_env = getenv("DFGPU_JOIN_BUCKET") ? atoi(getenv("DFGPU_JOIN_BUCKET")) : 0;
       j->iref.slots = j->inline_slots.ptr; j->iref.cap = cap; j->iref.dense = j->use_array_map ? 1 : 0; j->iref.amin = j->table.amin;
+      j->iref.bucket = (bucket_env && !j->use_array_map) ? 1 : 0;
       DF_CUDA(cudaMemsetAsync(j->counters.ptr, 0, 64, ctx->stream));
       {
         KernelTimer kt(ctx, "join_build");
@@ -978,8 +1238,17 @@ static void push_probe(dfgpu_hashjoin* j, std::vector<DCol>&& cols) {
     unsigned int* counter = (unsigned int*)(totals + 2);
     {
       KernelTimer kt(ctx, "join_probe");
-      if (j->inline_words == 2) join_probe_inline_kernel<2><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
-      else join_probe_inline_kernel<1><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
+      static const int variant = getenv("DFGPU_JOIN_VARIANT") ? atoi(getenv("DFGPU_JOIN_VARIANT")) : 0;
+      if (variant == 2) {
+        if (j->inline_words == 2) join_probe_inline_v2_kernel<2><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
+        else join_probe_inline_v2_kernel<1><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
+      } else if (variant == 0) {
+        if (j->inline_words == 2) join_probe_inline_v0_kernel<2><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
+        else join_probe_inline_v0_kernel<1><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
+      } else {
+        if (j->inline_words == 2) join_probe_inline_kernel<2><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
+        else join_probe_inline_kernel<1><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
+      }
       DF_LAUNCH_CHECK(ctx);
     }
     unsigned long long h[2];

@@ -55,6 +55,118 @@ __global__ void __launch_bounds__(256) partition_flags_kernel(PartKeys k, int64_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// single-pass radix-style partition (n_parts <= 32, columns without validity):
+//   hist kernel   : per tile (256 thr x 8 rows) and partition, the row count (warp ballots, no atomics)
+//   scan          : exclusive scan of the partition-major [part][tile] count matrix (one block)
+//   scatter kernel: every row's stable rank inside its tile+partition from the same ballots; rows are staged
+//                   in shared memory grouped by partition and leave as contiguous runs (coalesced stores)
+// Order inside a partition = input order (stable), identical to the flag/compaction path below.
+// ------------------------------------------------------------------------------------------
+constexpr int kPartThreads = 256;
+constexpr int kPartItems = 8;
+constexpr int kPartTile = kPartThreads * kPartItems;
+constexpr int kPartMaxFast = 32;
+constexpr int kPartMaxCols = 16;
+struct PartCols { int n; const void* src[kPartMaxCols]; void* dst[kPartMaxCols]; int width[kPartMaxCols]; };
+
+__global__ void __launch_bounds__(kPartThreads) partition_hist_kernel(PartKeys k, int64_t n, int n_parts, int64_t ntiles, unsigned long long* __restrict__ hist /* [n_parts][ntiles] */) {
+  __shared__ uint32_t s_cnt[kPartMaxFast];
+  const int64_t base = (int64_t)blockIdx.x * kPartTile;
+  if (threadIdx.x < kPartMaxFast) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int it = 0; it < kPartItems; ++it) {
+    const int64_t row = base + it * kPartThreads + threadIdx.x;
+    const int pid = row < n ? (int)(exchange_hash(k, row) % (uint64_t)n_parts) : -1;
+    for (int p = 0; p < n_parts; ++p) {
+      const uint32_t m = __ballot_sync(0xffffffffu, pid == p);
+      if (lane == 0 && m) atomicAdd(&s_cnt[p], __popc(m));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < n_parts) hist[(int64_t)threadIdx.x * ntiles + blockIdx.x] = s_cnt[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kPartThreads) partition_scatter_kernel(PartKeys k, PartCols pc, int64_t n, int n_parts, int64_t ntiles,
+                                                                       const unsigned long long* __restrict__ offs /* scanned [n_parts][ntiles] */) {
+  __shared__ uint32_t s_seg[kPartItems * (kPartThreads / 32)][kPartMaxFast + 1];  // counts per (item, warp) segment and partition (+1: bank padding)
+  __shared__ uint32_t s_pstart[kPartMaxFast + 1];
+  __shared__ unsigned long long s_goff[kPartMaxFast];
+  __shared__ uint8_t s_pid[kPartTile];
+  __shared__ __align__(16) unsigned char s_stage[kPartTile * 16];
+  const int64_t base = (int64_t)blockIdx.x * kPartTile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = kPartThreads / 32;
+  int pid[kPartItems];
+  uint32_t rank[kPartItems];
+#pragma unroll
+  for (int it = 0; it < kPartItems; ++it) {
+    const int64_t row = base + it * kPartThreads + threadIdx.x;
+    pid[it] = row < n ? (int)(exchange_hash(k, row) % (uint64_t)n_parts) : -1;
+    rank[it] = 0;
+    for (int p = 0; p < n_parts; ++p) {
+      const uint32_t m = __ballot_sync(0xffffffffu, pid[it] == p);
+      if (pid[it] == p) rank[it] = __popc(m & ((1u << lane) - 1u));
+      if (lane == 0) s_seg[it * NW + warp][p] = __popc(m);
+    }
+  }
+  __syncthreads();
+  // per partition: exclusive prefix over the 64 (item, warp) segments, in row order
+  if (threadIdx.x < n_parts) {
+    uint32_t run = 0;
+    for (int sgm = 0; sgm < kPartItems * NW; ++sgm) { uint32_t c = s_seg[sgm][threadIdx.x]; s_seg[sgm][threadIdx.x] = run; run += c; }
+    s_pstart[threadIdx.x] = run;  // partition total, turned into starts below
+    s_goff[threadIdx.x] = offs[(int64_t)threadIdx.x * ntiles + blockIdx.x];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int p = 0; p < n_parts; ++p) { uint32_t c = s_pstart[p]; s_pstart[p] = run; run += c; }
+    s_pstart[n_parts] = run;
+  }
+  __syncthreads();
+  uint32_t lpos[kPartItems];
+#pragma unroll
+  for (int it = 0; it < kPartItems; ++it) {
+    lpos[it] = 0;
+    if (pid[it] >= 0) {
+      lpos[it] = s_pstart[pid[it]] + s_seg[it * NW + warp][pid[it]] + rank[it];
+      s_pid[lpos[it]] = (uint8_t)pid[it];
+    }
+  }
+  const uint32_t tile_rows = s_pstart[n_parts];
+  for (int c = 0; c < pc.n; ++c) {
+    __syncthreads();
+    const int w = pc.width[c];
+#pragma unroll
+    for (int it = 0; it < kPartItems; ++it) {
+      if (pid[it] < 0) continue;
+      const int64_t row = base + it * kPartThreads + threadIdx.x;
+      switch (w) {
+        case 1: ((uint8_t*)s_stage)[lpos[it]] = ((const uint8_t*)pc.src[c])[row]; break;
+        case 2: ((uint16_t*)s_stage)[lpos[it]] = ((const uint16_t*)pc.src[c])[row]; break;
+        case 4: ((uint32_t*)s_stage)[lpos[it]] = ((const uint32_t*)pc.src[c])[row]; break;
+        case 8: ((uint64_t*)s_stage)[lpos[it]] = ((const uint64_t*)pc.src[c])[row]; break;
+        default: ((uint4*)s_stage)[lpos[it]] = ((const uint4*)pc.src[c])[row]; break;
+      }
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < tile_rows; j += kPartThreads) {
+      const int p = s_pid[j];
+      const unsigned long long d = s_goff[p] + (j - s_pstart[p]);
+      switch (w) {
+        case 1: ((uint8_t*)pc.dst[c])[d] = ((const uint8_t*)s_stage)[j]; break;
+        case 2: ((uint16_t*)pc.dst[c])[d] = ((const uint16_t*)s_stage)[j]; break;
+        case 4: ((uint32_t*)pc.dst[c])[d] = ((const uint32_t*)s_stage)[j]; break;
+        case 8: ((uint64_t*)pc.dst[c])[d] = ((const uint64_t*)s_stage)[j]; break;
+        default: ((uint4*)pc.dst[c])[d] = ((const uint4*)s_stage)[j]; break;
+      }
+    }
+  }
+}
+
 }  // namespace dfgpu
 
 using namespace dfgpu;
@@ -83,7 +195,38 @@ extern "C" int dfgpu_hash_partition_device(dfgpu_ctx* ctx, const dfgpu_column* c
   BatchPtr b(new dfgpu_batch());
   b->ctx = ctx; b->rows = n; b->host = false;
   for (int p = 0; p <= n_parts; ++p) part_offsets_host[p] = 0;
-  if (n > 0) {
+  bool fast = n > 0 && n_parts <= kPartMaxFast && n_cols <= kPartMaxCols;
+  for (int i = 0; i < n_cols && fast; ++i) if (v[i].validity || v[i].type == DFGPU_BOOL) fast = false;
+  if (fast) {
+    const int64_t ntiles = (n + kPartTile - 1) / kPartTile;
+    DevBuf hist(ctx, (size_t)(n_parts * ntiles + 1) * 8);
+    {
+      KernelTimer kt(ctx, "partition");
+      partition_hist_kernel<<<(int)ntiles, kPartThreads, 0, ctx->stream>>>(pk, n, n_parts, ntiles, hist.as<unsigned long long>());
+      DF_LAUNCH_CHECK(ctx);
+      scan_tiles_kernel<1024><<<1, 1024, 0, ctx->stream>>>((uint64_t*)hist.ptr, (int64_t)n_parts * ntiles, (uint64_t*)hist.ptr + (int64_t)n_parts * ntiles);
+      DF_LAUNCH_CHECK(ctx);
+    }
+    PartCols pc;
+    memset(&pc, 0, sizeof(pc));
+    pc.n = n_cols;
+    for (int i = 0; i < n_cols; ++i) {
+      DCol d = alloc_col(ctx, v[i].type, n, false);
+      pc.src[i] = v[i].values; pc.dst[i] = d.own_values->ptr; pc.width[i] = type_width(v[i].type);
+      b->cols.push_back(std::move(d));
+    }
+    {
+      KernelTimer kt(ctx, "partition");
+      partition_scatter_kernel<<<(int)ntiles, kPartThreads, 0, ctx->stream>>>(pk, pc, n, n_parts, ntiles, hist.as<unsigned long long>());
+      DF_LAUNCH_CHECK(ctx);
+    }
+    // partition starts = scanned offsets of tile 0 of every partition
+    std::vector<unsigned long long> starts(n_parts);
+    DF_CUDA(cudaMemcpy2DAsync(starts.data(), 8, hist.ptr, (size_t)ntiles * 8, 8, (size_t)n_parts, cudaMemcpyDeviceToHost, ctx->stream));
+    DF_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int p = 0; p < n_parts; ++p) part_offsets_host[p] = (int64_t)starts[p];
+    part_offsets_host[n_parts] = n;
+  } else if (n > 0) {
     const int64_t nw = (n + 31) / 32;
     DevBuf flags(ctx, (size_t)n_parts * nw * 4), perm(ctx, (size_t)n * 4);
     partition_flags_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(pk, n, n_parts, flags.as<uint32_t>());

@@ -81,7 +81,9 @@ def exchange_batch(ctx: D.Context, cols, key_cols: Sequence[int], dist) -> Excha
     batch, offs = D.hash_partition_device(ctx, cols, list(key_cols), world)
     send_counts = [offs[p + 1] - offs[p] for p in range(world)]
     dev = torch.device("cuda", ctx.device)
-    ctx.sync()  # partitioned buffers complete before NCCL reads them (no-op cost when streams are shared)
+    shared_stream = (ctx.lib.dfgpu_ctx_stream(ctx.h) or 0) == torch.cuda.current_stream().cuda_stream
+    if not shared_stream:
+        ctx.sync()  # partitioned buffers must be complete before NCCL (ordered on torch's stream) reads them
     recv_counts = exchange_counts(dist, send_counts, dev)
     send_tensors, types = [], []
     for i in range(batch.num_columns):
@@ -92,5 +94,6 @@ def exchange_batch(ctx: D.Context, cols, key_cols: Sequence[int], dist) -> Excha
         send_tensors.append(torch.as_tensor(view, device=dev)[: c.length])
         types.append(c.type)
     recv = all_to_all_columns(dist, send_tensors, send_counts, recv_counts)
-    torch.cuda.current_stream().synchronize()
+    if not shared_stream:
+        torch.cuda.current_stream().synchronize()
     return ExchangedBatch(ctx, recv, types, int(sum(recv_counts)), batch)

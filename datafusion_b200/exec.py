@@ -264,6 +264,50 @@ class GpuFilterExec(ExecutionPlan):
     def metrics(self): return self._metrics
 
 
+class GpuProjectionExec(ExecutionPlan):
+    """ProjectionExec over PhysicalExpr::evaluate (physical-expr-common/src/physical_expr.rs:88): each output column is
+    one expression evaluated on the GPU; plain `Column` expressions are passed through untouched (zero copy on the host)."""
+
+    def __init__(self, exprs: Sequence[Tuple[Expr, str]], input: ExecutionPlan):
+        self.exprs, self.input = list(exprs), input
+        self.schema = pa.schema([pa.field(name, e.data_type(input.schema)) for e, name in self.exprs])
+
+    def children(self): return [self.input]
+
+    def execute(self, ctx):
+        import ctypes as C
+        import numpy as np
+        isch = self.input.schema
+        for rb in self.input.execute(ctx):
+            cols = []
+            for e, name in self.exprs:
+                if isinstance(e, Column):
+                    cols.append(rb.column(isch.get_field_index(e.name)))
+                    continue
+                nodes: list = []
+                e.rpn(isch, nodes)
+                hcols, keep = [], []
+                for i, f in enumerate(isch):
+                    arr = rb.column(i)
+                    if pa.types.is_date32(f.type):
+                        vals = np.asarray(arr.cast(pa.int32()).fill_null(0))
+                    elif pa.types.is_boolean(f.type):
+                        vals = np.asarray(arr.fill_null(False))
+                    else:
+                        vals = np.asarray(arr.fill_null(0))
+                    valid = None if arr.null_count == 0 else ~np.asarray(arr.is_null())
+                    keep.append(D.HostColumn(vals, valid, type_id(f.type)))
+                arrc = (D.Column * len(keep))(*[k.c() for k in keep])
+                na = D.expr_nodes(nodes)
+                out = C.c_void_p()
+                ctx.gpu.check(ctx.gpu.lib.dfgpu_expr_evaluate_host(ctx.gpu.h, arrc, len(keep), rb.num_rows, na, len(nodes), C.byref(out)))
+                b = D.Batch(ctx.gpu, out.value)
+                res = b.to_arrow().column(0)
+                t = e.data_type(isch)
+                cols.append(res if res.type == t else res.cast(t))
+            yield pa.RecordBatch.from_arrays(cols, schema=self.schema)
+
+
 _JOIN_TYPES = {"Inner": D.JOIN_INNER, "Left": D.JOIN_LEFT, "Right": D.JOIN_RIGHT, "Full": D.JOIN_FULL, "LeftSemi": D.JOIN_LEFT_SEMI,
                "RightSemi": D.JOIN_RIGHT_SEMI, "LeftAnti": D.JOIN_LEFT_ANTI, "RightAnti": D.JOIN_RIGHT_ANTI, "LeftMark": D.JOIN_LEFT_MARK,
                "RightMark": D.JOIN_RIGHT_MARK}
