@@ -173,12 +173,23 @@ def main():
     col = lambda buf, n: D.DeviceColumn(ctx, D.INT64, n, buf)
     build_cols, probe_cols = [col(bk, nb), col(bp, nb)], [col(pk, npr), col(pp, npr)]
 
+    px_b = px_p = None
+    if world > 1:
+        from datafusion_b200 import exchange
+        if os.environ.get("DFGPU_EXCHANGE", "peer") == "peer":
+            # persistent receive buffers, mapped into every peer through CUDA IPC (25 % headroom over the uniform share)
+            px_b = exchange.PeerExchange(ctx, dist, [D.INT64, D.INT64], int(nb * 1.25))
+            px_p = exchange.PeerExchange(ctx, dist, [D.INT64, D.INT64], int(npr * 1.25))
+
     def step():
         if world == 1:
             return join_step(ctx, D, build_cols, probe_cols)[0]
-        from datafusion_b200 import exchange
-        b2 = exchange.exchange_batch(ctx, build_cols, [0], dist)
-        p2 = exchange.exchange_batch(ctx, probe_cols, [0], dist)
+        if px_b is not None:   # fused partition + exchange: rows are written straight into the owners' HBM over NVLink
+            b2 = px_b.exchange(build_cols, [0])
+            p2 = px_p.exchange(probe_cols, [0])
+        else:                  # local partition + one NCCL all-to-all per column
+            b2 = exchange.exchange_batch(ctx, build_cols, [0], dist)
+            p2 = exchange.exchange_batch(ctx, probe_cols, [0], dist)
         return join_step(ctx, D, b2.columns(), p2.columns())[0]
 
     def barrier():
@@ -231,7 +242,7 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic (generated in HBM, counter-based)",
                 "config": {"workload": "C2 HashJoinExec inner 100M x 10M int64 per GPU, sparse unique build keys, 100% hit, output {k,pb,pp}",
                            "rows_per_step": (nb + npr) * world, "output_rows_per_gpu": int(out_rows), "l2": "inputs (1.76 GB/GPU) exceed L2; no flush",
-                           "exchange": "hash partition + one NCCL all-to-all per column" if world > 1 else "none (single GPU)"},
+                           "exchange": ("fused hash partition + direct peer-memory scatter over NVLink (CUDA IPC), NCCL only for counts/barrier" if os.environ.get("DFGPU_EXCHANGE", "peer") == "peer" else "hash partition + one NCCL all-to-all per column") if world > 1 else "none (single GPU)"},
                 "clocks": clk, "gpu_launches": int(launches), "roofline": roofline}
 
     # ---- e2e through the C ABI with host (pinned) buffers (N = 1: the host leg has no exchange) ----

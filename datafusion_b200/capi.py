@@ -102,6 +102,8 @@ EXPORTS = [
     "dfgpu_agg_next", "dfgpu_agg_metric", "dfgpu_agg_destroy",
     "dfgpu_batch_num_rows", "dfgpu_batch_num_columns", "dfgpu_batch_column", "dfgpu_batch_is_host",
     "dfgpu_batch_export_arrow", "dfgpu_batch_release", "dfgpu_hash_partition_device",
+    "dfgpu_partition_plan_create", "dfgpu_partition_plan_scatter_peer", "dfgpu_partition_plan_destroy",
+    "dfgpu_ipc_export", "dfgpu_ipc_import", "dfgpu_ipc_close",
 ]
 
 _lib = None
@@ -176,6 +178,12 @@ def load_library() -> C.CDLL:
     sig("dfgpu_batch_is_host", C.c_int, [vp])
     sig("dfgpu_batch_export_arrow", C.c_int, [vp, vp, vp])
     sig("dfgpu_hash_partition_device", C.c_int, [vp, P(Column), i32, P(i32), i32, i32, P(vp), P(i64)])
+    sig("dfgpu_partition_plan_create", C.c_int, [vp, P(Column), i32, P(i32), i32, i32, P(i64), P(vp)])
+    sig("dfgpu_partition_plan_scatter_peer", C.c_int, [vp, P(vp), P(i64)])
+    sig("dfgpu_partition_plan_destroy", None, [vp])
+    sig("dfgpu_ipc_export", C.c_int, [vp, vp, C.c_char_p])
+    sig("dfgpu_ipc_import", C.c_int, [vp, C.c_char_p, P(vp)])
+    sig("dfgpu_ipc_close", C.c_int, [vp, vp])
     _lib = lib
     return lib
 

@@ -69,6 +69,9 @@ constexpr int kPartTile = kPartThreads * kPartItems;
 constexpr int kPartMaxFast = 32;
 constexpr int kPartMaxCols = 16;
 struct PartCols { int n; const void* src[kPartMaxCols]; void* dst[kPartMaxCols]; int width[kPartMaxCols]; };
+// peer mode: partition p's rows go to dst_table[p * n_cols + c] (a pointer into rank p's receive buffer, mapped
+// through CUDA IPC: stores travel over NVLink) starting at row dst_row[p]; nullptr table = local output columns
+struct PeerDst { void* const* dst_table; const long long* dst_row; };
 
 __global__ void __launch_bounds__(kPartThreads) partition_hist_kernel(PartKeys k, int64_t n, int n_parts, int64_t ntiles, unsigned long long* __restrict__ hist /* [n_parts][ntiles] */) {
   __shared__ uint32_t s_cnt[kPartMaxFast];
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(kPartThreads) partition_hist_kernel(PartKeys k
 }
 
 __global__ void __launch_bounds__(kPartThreads) partition_scatter_kernel(PartKeys k, PartCols pc, int64_t n, int n_parts, int64_t ntiles,
-                                                                       const unsigned long long* __restrict__ offs /* scanned [n_parts][ntiles] */) {
+                                                                       const unsigned long long* __restrict__ offs /* scanned [n_parts][ntiles] */, PeerDst peer) {
   __shared__ uint32_t s_seg[kPartItems * (kPartThreads / 32)][kPartMaxFast + 1];  // counts per (item, warp) segment and partition (+1: bank padding)
   __shared__ uint32_t s_pstart[kPartMaxFast + 1];
   __shared__ unsigned long long s_goff[kPartMaxFast];
@@ -118,7 +121,9 @@ __global__ void __launch_bounds__(kPartThreads) partition_scatter_kernel(PartKey
     uint32_t run = 0;
     for (int sgm = 0; sgm < kPartItems * NW; ++sgm) { uint32_t c = s_seg[sgm][threadIdx.x]; s_seg[sgm][threadIdx.x] = run; run += c; }
     s_pstart[threadIdx.x] = run;  // partition total, turned into starts below
-    s_goff[threadIdx.x] = offs[(int64_t)threadIdx.x * ntiles + blockIdx.x];
+    const unsigned long long o = offs[(int64_t)threadIdx.x * ntiles + blockIdx.x];
+    // peer mode: position inside this rank's block of partition p, shifted to where that block starts at the receiver
+    s_goff[threadIdx.x] = peer.dst_table ? (unsigned long long)peer.dst_row[threadIdx.x] + (o - offs[(int64_t)threadIdx.x * ntiles]) : o;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -156,12 +161,13 @@ __global__ void __launch_bounds__(kPartThreads) partition_scatter_kernel(PartKey
     for (uint32_t j = threadIdx.x; j < tile_rows; j += kPartThreads) {
       const int p = s_pid[j];
       const unsigned long long d = s_goff[p] + (j - s_pstart[p]);
+      void* dstc = peer.dst_table ? peer.dst_table[p * pc.n + c] : pc.dst[c];
       switch (w) {
-        case 1: ((uint8_t*)pc.dst[c])[d] = ((const uint8_t*)s_stage)[j]; break;
-        case 2: ((uint16_t*)pc.dst[c])[d] = ((const uint16_t*)s_stage)[j]; break;
-        case 4: ((uint32_t*)pc.dst[c])[d] = ((const uint32_t*)s_stage)[j]; break;
-        case 8: ((uint64_t*)pc.dst[c])[d] = ((const uint64_t*)s_stage)[j]; break;
-        default: ((uint4*)pc.dst[c])[d] = ((const uint4*)s_stage)[j]; break;
+        case 1: ((uint8_t*)dstc)[d] = ((const uint8_t*)s_stage)[j]; break;
+        case 2: ((uint16_t*)dstc)[d] = ((const uint16_t*)s_stage)[j]; break;
+        case 4: ((uint32_t*)dstc)[d] = ((const uint32_t*)s_stage)[j]; break;
+        case 8: ((uint64_t*)dstc)[d] = ((const uint64_t*)s_stage)[j]; break;
+        default: ((uint4*)dstc)[d] = ((const uint4*)s_stage)[j]; break;
       }
     }
   }
@@ -217,7 +223,7 @@ extern "C" int dfgpu_hash_partition_device(dfgpu_ctx* ctx, const dfgpu_column* c
     }
     {
       KernelTimer kt(ctx, "partition");
-      partition_scatter_kernel<<<(int)ntiles, kPartThreads, 0, ctx->stream>>>(pk, pc, n, n_parts, ntiles, hist.as<unsigned long long>());
+      partition_scatter_kernel<<<(int)ntiles, kPartThreads, 0, ctx->stream>>>(pk, pc, n, n_parts, ntiles, hist.as<unsigned long long>(), PeerDst{nullptr, nullptr});
       DF_LAUNCH_CHECK(ctx);
     }
     // partition starts = scanned offsets of tile 0 of every partition
@@ -247,5 +253,111 @@ extern "C" int dfgpu_hash_partition_device(dfgpu_ctx* ctx, const dfgpu_column* c
     for (int i = 0; i < n_cols; ++i) b->cols.push_back(alloc_col(ctx, v[i].type, 0, false));
   }
   *out = b.release();
+  DF_API_END
+}
+
+// ------------------------------------------------------------------------------------------
+// fused partition + exchange over peer memory: phase 1 counts, phase 2 scatters straight into the peers'
+// receive buffers (pointers obtained through CUDA IPC).  Between the phases the caller all-gathers the counts so
+// every rank knows where its block starts in each receiver (datafusion_b200/exchange.py PeerExchange).
+// ------------------------------------------------------------------------------------------
+struct dfgpu_partition_plan {
+  dfgpu_ctx* ctx;
+  PartKeys pk;
+  PartCols pc;
+  int64_t n, ntiles;
+  int n_parts;
+  DevBuf hist, dst_table, dst_row;
+};
+
+extern "C" int dfgpu_partition_plan_create(dfgpu_ctx* ctx, const dfgpu_column* cols, int32_t n_cols, const int32_t* key_cols, int32_t n_keys,
+                                           int32_t n_parts, int64_t* counts_host, dfgpu_partition_plan** out) {
+  DF_API_BEGIN(ctx)
+  DF_CHECK(ctx && cols && key_cols && out && counts_host, DFGPU_ERR_INVALID, "null argument");
+  DF_CHECK(n_keys >= 1 && n_keys <= kMaxPartKeys && n_parts >= 1 && n_parts <= kPartMaxFast && n_cols >= 1 && n_cols <= kPartMaxCols, DFGPU_ERR_UNSUPPORTED,
+           "peer partition: 1..4 keys, <= 32 partitions, <= 16 columns");
+  set_device(ctx);
+  std::unique_ptr<dfgpu_partition_plan> pl(new dfgpu_partition_plan());
+  pl->ctx = ctx; pl->n_parts = n_parts;
+  std::vector<DCol> v;
+  for (int i = 0; i < n_cols; ++i) {
+    v.push_back(device_view(cols[i]));
+    DF_CHECK(!v[i].validity && v[i].type != DFGPU_BOOL, DFGPU_ERR_UNSUPPORTED, "peer partition: nullable / boolean columns are not supported yet");
+  }
+  pl->n = v[0].length;
+  DF_CHECK(pl->n < 0xFFFFFFFFll, DFGPU_ERR_UNSUPPORTED, "peer partition: < 2^32-1 rows per call");
+  memset(&pl->pk, 0, sizeof(pl->pk)); memset(&pl->pc, 0, sizeof(pl->pc));
+  pl->pk.n = n_keys;
+  for (int c = 0; c < n_keys; ++c) {
+    const DCol& col = v[key_cols[c]];
+    int w = type_width(col.type);
+    DF_CHECK(w >= 1 && w <= 8, DFGPU_ERR_UNSUPPORTED, "peer partition: key must be a fixed-width type of <= 64 bits");
+    pl->pk.ptr[c] = col.values; pl->pk.width[c] = w;
+  }
+  pl->pc.n = n_cols;
+  for (int i = 0; i < n_cols; ++i) { pl->pc.src[i] = v[i].values; pl->pc.width[i] = type_width(v[i].type); }
+  pl->ntiles = std::max<int64_t>(1, (pl->n + kPartTile - 1) / kPartTile);
+  pl->hist.alloc(ctx, (size_t)(n_parts * pl->ntiles + 1) * 8);
+  {
+    KernelTimer kt(ctx, "partition");
+    partition_hist_kernel<<<(int)pl->ntiles, kPartThreads, 0, ctx->stream>>>(pl->pk, pl->n, n_parts, pl->ntiles, pl->hist.as<unsigned long long>());
+    DF_LAUNCH_CHECK(ctx);
+    scan_tiles_kernel<1024><<<1, 1024, 0, ctx->stream>>>((uint64_t*)pl->hist.ptr, (int64_t)n_parts * pl->ntiles, (uint64_t*)pl->hist.ptr + (int64_t)n_parts * pl->ntiles);
+    DF_LAUNCH_CHECK(ctx);
+  }
+  std::vector<unsigned long long> starts(n_parts);
+  DF_CUDA(cudaMemcpy2DAsync(starts.data(), 8, pl->hist.ptr, (size_t)pl->ntiles * 8, 8, (size_t)n_parts, cudaMemcpyDeviceToHost, ctx->stream));
+  DF_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int p = 0; p < n_parts; ++p) counts_host[p] = (int64_t)((p + 1 < n_parts ? starts[p + 1] : (unsigned long long)pl->n) - starts[p]);
+  *out = pl.release();
+  DF_API_END
+}
+
+extern "C" int dfgpu_partition_plan_scatter_peer(dfgpu_partition_plan* pl, void* const* dst_bases /* [n_parts * n_cols] */, const int64_t* dst_row_offset /* [n_parts] */) {
+  DF_API_BEGIN(pl ? pl->ctx : nullptr)
+  dfgpu_ctx* ctx = pl->ctx;
+  set_device(ctx);
+  const size_t tb = (size_t)pl->n_parts * pl->pc.n * sizeof(void*);
+  pl->dst_table.alloc(ctx, tb);
+  pl->dst_row.alloc(ctx, (size_t)pl->n_parts * 8);
+  DF_CUDA(cudaMemcpyAsync(pl->dst_table.ptr, dst_bases, tb, cudaMemcpyHostToDevice, ctx->stream));
+  DF_CUDA(cudaMemcpyAsync(pl->dst_row.ptr, dst_row_offset, (size_t)pl->n_parts * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (pl->n > 0) {
+    KernelTimer kt(ctx, "partition");
+    partition_scatter_kernel<<<(int)pl->ntiles, kPartThreads, 0, ctx->stream>>>(pl->pk, pl->pc, pl->n, pl->n_parts, pl->ntiles, pl->hist.as<unsigned long long>(),
+                                                                               PeerDst{(void* const*)pl->dst_table.ptr, (const long long*)pl->dst_row.ptr});
+    DF_LAUNCH_CHECK(ctx);
+  }
+  DF_API_END
+}
+
+extern "C" void dfgpu_partition_plan_destroy(dfgpu_partition_plan* pl) {
+  if (!pl) return;
+  cudaSetDevice(pl->ctx->device);
+  delete pl;
+}
+
+// CUDA IPC plumbing: a rank exports its receive buffers once, peers map them and write through NVLink
+extern "C" int dfgpu_ipc_export(dfgpu_ctx* ctx, void* dev_ptr, uint8_t* handle_out /* 64 bytes */) {
+  DF_API_BEGIN(ctx)
+  set_device(ctx);
+  cudaIpcMemHandle_t h;
+  DF_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out, &h, 64);
+  DF_API_END
+}
+extern "C" int dfgpu_ipc_import(dfgpu_ctx* ctx, const uint8_t* handle, void** peer_ptr_out) {
+  DF_API_BEGIN(ctx)
+  set_device(ctx);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  DF_CUDA(cudaIpcOpenMemHandle(peer_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  DF_API_END
+}
+extern "C" int dfgpu_ipc_close(dfgpu_ctx* ctx, void* peer_ptr) {
+  DF_API_BEGIN(ctx)
+  set_device(ctx);
+  if (peer_ptr) DF_CUDA(cudaIpcCloseMemHandle(peer_ptr));
   DF_API_END
 }

@@ -335,6 +335,21 @@ int dfgpu_hash_partition_device(dfgpu_ctx* ctx, const dfgpu_column* cols, int32_
                                 const int32_t* key_cols, int32_t n_keys, int32_t n_parts,
                                 dfgpu_batch** out, int64_t* part_offsets_host);
 
+/* Fused partition + exchange over peer memory (NVLink): the scatter writes each row straight into the receive
+ * buffer of the GPU that owns its partition — no staging copy, no NCCL payload transfer.  Phase 1 counts rows per
+ * destination (the caller all-gathers the counts to learn where its block starts in every receiver), phase 2
+ * scatters.  dst_bases[p * n_cols + c] points at column c of rank p's receive buffer (mapped with dfgpu_ipc_import;
+ * the local pointer for p == own rank); dst_row_offset[p] is the first row this rank owns in that buffer. */
+typedef struct dfgpu_partition_plan dfgpu_partition_plan;
+int dfgpu_partition_plan_create(dfgpu_ctx* ctx, const dfgpu_column* cols, int32_t n_cols, const int32_t* key_cols, int32_t n_keys,
+                                int32_t n_parts, int64_t* counts_host, dfgpu_partition_plan** out);
+int dfgpu_partition_plan_scatter_peer(dfgpu_partition_plan* plan, void* const* dst_bases, const int64_t* dst_row_offset);
+void dfgpu_partition_plan_destroy(dfgpu_partition_plan* plan);
+/* CUDA IPC: export a device allocation made with dfgpu_malloc (64-byte handle) / map a peer's allocation */
+int dfgpu_ipc_export(dfgpu_ctx* ctx, void* dev_ptr, uint8_t* handle_out);
+int dfgpu_ipc_import(dfgpu_ctx* ctx, const uint8_t* handle, void** peer_ptr_out);
+int dfgpu_ipc_close(dfgpu_ctx* ctx, void* peer_ptr);
+
 #ifdef __cplusplus
 }
 #endif
