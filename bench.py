@@ -323,6 +323,31 @@ def main():
                                                           "achieved_gbs": (16.0 * gn + 24.0 * ng) / ms_g / 1e6, "frac_of_hbm_peak": (16.0 * gn + 24.0 * ng) / ms_g / 1e6 / peak,
                                                           "note": "bound by L2 atomics (2 RED + 1 tag read per row; measured RED peak 197 Gop/s), not HBM"}
         gk.free(); gv.free()
+        # FilterExec: x:int64 > c over 100M rows x 2 columns, selectivity 20 % (C1's predicate at a size that is not launch-bound)
+        fn = 100_000_000
+        fx = ctx.generate_i64(D.GEN_UNIFORM, 1, 0, 1 << 32, 0, fn); fy = ctx.generate_i64(D.GEN_SPLITMIX, 2, 0, 0, 0, fn)
+        nodes = [(D.EXPR_COLUMN, 0, 0, 0, 0, 0.0), (D.EXPR_LITERAL, 0, D.INT64, 0, int((1 << 32) * 0.8), 0.0), (D.EXPR_BINARY, D.OP_GT, 0, 0, 0, 0.0)]
+
+        def filter_step():
+            f = D.FilterHandle(ctx, [D.INT64, D.INT64], nodes, batch_size=0)
+            f.push_device([col(fx, fn), col(fy, fn)])
+            f.finish()
+            outs = f.drain(host=False)
+            kept = sum(o.num_rows for o in outs)
+            for o in outs:
+                o.release()
+            f.close()
+            return kept
+        filter_step()
+        ctx.record(e0)
+        for _ in range(3):
+            kept = filter_step()
+        ctx.record(e1)
+        ms_f = ctx.elapsed_ms(e0, e1) / 3
+        fbytes = 16.0 * fn + 16.0 * kept   # both columns read once, kept rows of both columns written
+        extra["C1_shape_filter_100M_rows_sel20"] = {"ms_per_step": ms_f, "rows_per_s": fn / ms_f * 1e3, "kept": int(kept),
+                                                   "achieved_gbs": fbytes / ms_f / 1e6, "frac_of_hbm_peak": fbytes / ms_f / 1e6 / peak}
+        fx.free(); fy.free()
         line["extra"] = extra
 
     if rank == 0:

@@ -190,6 +190,43 @@ __device__ __forceinline__ uint64_t cast_value(uint64_t v, int from, int to) {
   return wrap_to_type(iv, to);
 }
 
+// evaluate the post-order program for one row: value bits + validity
+__device__ __forceinline__ uint64_t eval_row(const EProgram& p, int64_t row, bool* ok_out, int* err) {
+  uint64_t sv[kMaxStack];
+  bool sk[kMaxStack];
+  int sp = 0;
+#pragma unroll 1
+  for (int i = 0; i < p.n; ++i) {
+    const ENode& nd = p.node[i];
+    switch (nd.kind) {
+      case DFGPU_EXPR_COLUMN:
+    sk[sp] = !(nd.valid && !bit_get(nd.valid, nd.voff + row));
+    sv[sp] = load_col_value(nd, row);
+    ++sp;
+    break;
+      case DFGPU_EXPR_LITERAL:
+    sk[sp] = !nd.lit_null; sv[sp] = nd.lit; ++sp;
+    break;
+      case DFGPU_EXPR_BINARY: {
+    uint64_t r; bool ok;
+    eval_binary(nd, sv[sp - 2], sk[sp - 2], sv[sp - 1], sk[sp - 1], &r, &ok, err);
+    sp -= 1; sv[sp - 1] = r; sk[sp - 1] = ok;
+    break;
+      }
+      case DFGPU_EXPR_NOT: sv[sp - 1] = sv[sp - 1] ? 0 : 1; break;  // NULL stays NULL
+      case DFGPU_EXPR_IS_NULL: sv[sp - 1] = sk[sp - 1] ? 0 : 1; sk[sp - 1] = true; break;
+      case DFGPU_EXPR_IS_NOT_NULL: sv[sp - 1] = sk[sp - 1] ? 1 : 0; sk[sp - 1] = true; break;
+      case DFGPU_EXPR_NEGATIVE:
+    if (cls_of(nd.out_type) == C_F64) sv[sp - 1] ^= 0x8000000000000000ull;
+    else sv[sp - 1] = wrap_to_type(0ull - sv[sp - 1], nd.out_type);  // neg_wrapping
+    break;
+      case DFGPU_EXPR_CAST: sv[sp - 1] = cast_value(sv[sp - 1], nd.in_type, nd.out_type); break;
+    }
+  }
+  *ok_out = sk[0];
+  return sv[0];
+}
+
 // One kernel evaluates the whole expression.  Outputs: typed values (or bit-packed booleans),
 // validity words, and — for predicates — the selection words (valid AND true).
 __global__ void __launch_bounds__(256) expr_eval_kernel(EProgram p, int64_t n, void* __restrict__ out_values, uint32_t* __restrict__ out_boolwords,
@@ -203,38 +240,7 @@ __global__ void __launch_bounds__(256) expr_eval_kernel(EProgram p, int64_t n, v
     uint64_t rv = 0;
     bool rok = false;
     if (row < n) {
-      uint64_t sv[kMaxStack];
-      bool sk[kMaxStack];
-      int sp = 0;
-#pragma unroll 1
-      for (int i = 0; i < p.n; ++i) {
-        const ENode& nd = p.node[i];
-        switch (nd.kind) {
-          case DFGPU_EXPR_COLUMN:
-            sk[sp] = !(nd.valid && !bit_get(nd.valid, nd.voff + row));
-            sv[sp] = load_col_value(nd, row);
-            ++sp;
-            break;
-          case DFGPU_EXPR_LITERAL:
-            sk[sp] = !nd.lit_null; sv[sp] = nd.lit; ++sp;
-            break;
-          case DFGPU_EXPR_BINARY: {
-            uint64_t r; bool ok;
-            eval_binary(nd, sv[sp - 2], sk[sp - 2], sv[sp - 1], sk[sp - 1], &r, &ok, &err);
-            sp -= 1; sv[sp - 1] = r; sk[sp - 1] = ok;
-            break;
-          }
-          case DFGPU_EXPR_NOT: sv[sp - 1] = sv[sp - 1] ? 0 : 1; break;  // NULL stays NULL
-          case DFGPU_EXPR_IS_NULL: sv[sp - 1] = sk[sp - 1] ? 0 : 1; sk[sp - 1] = true; break;
-          case DFGPU_EXPR_IS_NOT_NULL: sv[sp - 1] = sk[sp - 1] ? 1 : 0; sk[sp - 1] = true; break;
-          case DFGPU_EXPR_NEGATIVE:
-            if (cls_of(nd.out_type) == C_F64) sv[sp - 1] ^= 0x8000000000000000ull;
-            else sv[sp - 1] = wrap_to_type(0ull - sv[sp - 1], nd.out_type);  // neg_wrapping
-            break;
-          case DFGPU_EXPR_CAST: sv[sp - 1] = cast_value(sv[sp - 1], nd.in_type, nd.out_type); break;
-        }
-      }
-      rv = sv[0]; rok = sk[0];
+      rv = eval_row(p, row, &rok, &err);
       if (!rok) rv = 0;
       if (out_values) {
         switch (root_type) {
@@ -313,6 +319,93 @@ __global__ void __launch_bounds__(256) cmp_i64_scalar_kernel(const int64_t* __re
       select_words[w] = word;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused FilterExec: predicate -> ordered compaction -> projected columns, ONE pass over the batch
+// (tile = 256 threads x 4 consecutive rows; selected rows ranked by a block scan, tile offsets by decoupled
+// look-back, every projected column written with coalesced stores).  No selection bitmap, index list or
+// per-column gather kernels touch HBM.
+// ------------------------------------------------------------------------------------------
+constexpr int kFiltThreads = 256;
+constexpr int kFiltItems = 4;
+constexpr int kFiltTile = kFiltThreads * kFiltItems;
+constexpr int kMaxFiltCols = 16;
+struct FilterCols { int n; const void* src[kMaxFiltCols]; void* dst[kMaxFiltCols]; int width[kMaxFiltCols]; };
+
+template <int FAST>
+__global__ void __launch_bounds__(kFiltThreads) filter_fused_kernel(const EProgram* __restrict__ prog, const int64_t* __restrict__ fast_col, int fast_op, int64_t fast_lit,
+                                                                  int64_t n, FilterCols fc, unsigned long long* __restrict__ tile_desc,
+                                                                  unsigned int* __restrict__ tile_counter, unsigned long long* __restrict__ totals, int* __restrict__ err_flag) {
+  __shared__ uint32_t s_p[kFiltTile];
+  __shared__ unsigned int s_tile;
+  __shared__ unsigned long long s_base;
+  if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+  __syncthreads();
+  const int64_t tile = s_tile;
+  const int64_t row0 = tile * kFiltTile + (int64_t)threadIdx.x * kFiltItems;
+  bool keep[kFiltItems];
+  uint32_t m = 0;
+  int err = 0;
+  if (FAST) {
+    int64_t v[kFiltItems];
+#pragma unroll
+    for (int k = 0; k < kFiltItems; ++k) v[k] = row0 + k < n ? fast_col[row0 + k] : 0;
+#pragma unroll
+    for (int k = 0; k < kFiltItems; ++k) {
+      bool r;
+      switch (fast_op) {
+        case DFGPU_OP_EQ: r = v[k] == fast_lit; break;
+        case DFGPU_OP_NEQ: r = v[k] != fast_lit; break;
+        case DFGPU_OP_LT: r = v[k] < fast_lit; break;
+        case DFGPU_OP_LTEQ: r = v[k] <= fast_lit; break;
+        case DFGPU_OP_GT: r = v[k] > fast_lit; break;
+        default: r = v[k] >= fast_lit; break;
+      }
+      keep[k] = r && row0 + k < n;
+      m += keep[k] ? 1u : 0u;
+    }
+  } else {
+#pragma unroll 1
+    for (int k = 0; k < kFiltItems; ++k) {
+      keep[k] = false;
+      if (row0 + k < n) {
+        bool ok;
+        uint64_t val = eval_row(*prog, row0 + k, &ok, &err);
+        keep[k] = ok && (val & 1);   // NULL predicate rows are dropped (filter_record_batch)
+      }
+      m += keep[k] ? 1u : 0u;
+    }
+  }
+  uint32_t tot;
+  uint32_t ex = block_exclusive_scan<kFiltThreads, uint32_t>(m, &tot);
+#pragma unroll
+  for (int k = 0; k < kFiltItems; ++k) if (keep[k]) s_p[ex++] = (uint32_t)(threadIdx.x * kFiltItems + k);
+  if (threadIdx.x < 32) {
+    unsigned long long exclusive = tile_lookback(tile, tot, tile_desc);
+    if (threadIdx.x == 0) {
+      s_base = exclusive;
+      if ((tile + 1) * (int64_t)kFiltTile >= n) totals[0] = exclusive + tot;
+    }
+  }
+  __syncthreads();
+  const unsigned long long base = s_base;
+  const int64_t prow0 = tile * kFiltTile;
+  for (int c = 0; c < fc.n; ++c) {
+    switch (fc.width[c]) {
+      case 8: { const uint64_t* src = (const uint64_t*)fc.src[c]; uint64_t* dst = (uint64_t*)fc.dst[c] + base;
+                for (uint32_t j = threadIdx.x; j < tot; j += kFiltThreads) dst[j] = src[prow0 + s_p[j]]; break; }
+      case 4: { const uint32_t* src = (const uint32_t*)fc.src[c]; uint32_t* dst = (uint32_t*)fc.dst[c] + base;
+                for (uint32_t j = threadIdx.x; j < tot; j += kFiltThreads) dst[j] = src[prow0 + s_p[j]]; break; }
+      case 2: { const uint16_t* src = (const uint16_t*)fc.src[c]; uint16_t* dst = (uint16_t*)fc.dst[c] + base;
+                for (uint32_t j = threadIdx.x; j < tot; j += kFiltThreads) dst[j] = src[prow0 + s_p[j]]; break; }
+      case 1: { const uint8_t* src = (const uint8_t*)fc.src[c]; uint8_t* dst = (uint8_t*)fc.dst[c] + base;
+                for (uint32_t j = threadIdx.x; j < tot; j += kFiltThreads) dst[j] = src[prow0 + s_p[j]]; break; }
+      default: { const uint4* src = (const uint4*)fc.src[c]; uint4* dst = (uint4*)fc.dst[c] + base;
+                for (uint32_t j = threadIdx.x; j < tot; j += kFiltThreads) dst[j] = src[prow0 + s_p[j]]; break; }
+    }
+  }
+  if (err) atomicOr(err_flag, err);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -419,6 +512,23 @@ static uint64_t literal_bits(const dfgpu_expr_node& nd) {
   }
 }
 
+static void bind_program(const ExprPlan& plan, const std::vector<DCol>& cols, EProgram* prog) {
+  memset(prog, 0, sizeof(*prog));
+  prog->n = (int)plan.nodes.size();
+  for (int i = 0; i < prog->n; ++i) {
+    const dfgpu_expr_node& nd = plan.nodes[i];
+    ENode& e = prog->node[i];
+    e.kind = nd.kind; e.op = nd.a; e.in_type = plan.in_type[i]; e.out_type = plan.out_type[i];
+    if (nd.kind == DFGPU_EXPR_COLUMN) {
+      const DCol& c = cols[nd.a];
+      DF_CHECK(c.type == plan.out_type[i], DFGPU_ERR_INVALID, "expression: batch column type differs from the planned schema");
+      e.col = c.values; e.valid = c.validity; e.voff = c.offset;
+    } else if (nd.kind == DFGPU_EXPR_LITERAL) {
+      e.lit = literal_bits(nd); e.lit_null = nd.is_null;
+    }
+  }
+}
+
 // Evaluate `plan` over device columns.  want_select: also produce selection words (valid & true).
 struct EvalResult { DCol column; DevBuf select_words; };
 
@@ -450,23 +560,7 @@ EvalResult evaluate_expr(dfgpu_ctx* ctx, const ExprPlan& plan, const std::vector
     }
   }
   EProgram prog;
-  memset(&prog, 0, sizeof(prog));
-  prog.n = (int)plan.nodes.size();
-  bool any_nullable = false;
-  for (int i = 0; i < prog.n; ++i) {
-    const dfgpu_expr_node& nd = plan.nodes[i];
-    ENode& e = prog.node[i];
-    e.kind = nd.kind; e.op = nd.a; e.in_type = plan.in_type[i]; e.out_type = plan.out_type[i];
-    if (nd.kind == DFGPU_EXPR_COLUMN) {
-      const DCol& c = cols[nd.a];
-      DF_CHECK(c.type == plan.out_type[i], DFGPU_ERR_INVALID, "expression: batch column type differs from the planned schema");
-      e.col = c.values; e.valid = c.validity; e.voff = c.offset;
-      any_nullable |= (c.validity != nullptr);
-    } else if (nd.kind == DFGPU_EXPR_LITERAL) {
-      e.lit = literal_bits(nd); e.lit_null = nd.is_null;
-      any_nullable |= (nd.is_null != 0);
-    }
-  }
+  bind_program(plan, cols, &prog);
   const int rt = plan.root_type;
   if (want_column) {
     res.column = alloc_col(ctx, rt, n, true);
@@ -484,7 +578,6 @@ EvalResult evaluate_expr(dfgpu_ctx* ctx, const ExprPlan& plan, const std::vector
     if (e & ERR_OVERFLOW) throw Error(DFGPU_ERR_ARITH, "Arrow error: Arithmetic overflow");
   }
   if (want_column) res.column.null_count = -1;
-  (void)any_nullable;
   return res;
 }
 
@@ -559,6 +652,65 @@ static void filter_push(dfgpu_filter* f, const std::vector<DCol>& cols) {
   f->m_input_batches++;
   if (n == 0 || f->limit_reached) return;
   DF_CHECK(n < 0xFFFFFFFFll, DFGPU_ERR_UNSUPPORTED, "filter: a batch must have < 2^32-1 rows");
+  // ---- fused single-pass path: plain projected columns, no fetch limit ----
+  bool fusable = f->fetch < 0 && f->projection.size() <= (size_t)kMaxFiltCols;
+  for (int pc : f->projection) if (cols[pc].validity || cols[pc].type == DFGPU_BOOL) fusable = false;
+  static const int fused_enabled = getenv("DFGPU_FILTER_FUSED") ? atoi(getenv("DFGPU_FILTER_FUSED")) : 0;
+  if (fusable && fused_enabled) {
+    FilterCols fc;
+    memset(&fc, 0, sizeof(fc));
+    fc.n = (int)f->projection.size();
+    std::vector<DCol> part;
+    for (int c = 0; c < fc.n; ++c) {
+      const DCol& src = cols[f->projection[c]];
+      DCol d = alloc_col(ctx, src.type, n, false);
+      fc.src[c] = src.values; fc.dst[c] = d.own_values->ptr; fc.width[c] = type_width(src.type);
+      part.push_back(std::move(d));
+    }
+    const int64_t nt = (n + kFiltTile - 1) / kFiltTile;
+    DevBuf desc(ctx, (size_t)nt * 8 + 32), progbuf, err(ctx, 4);
+    desc.zero();
+    err.zero();
+    unsigned long long* totals = (unsigned long long*)((char*)desc.ptr + (size_t)nt * 8);
+    unsigned int* counter = (unsigned int*)(totals + 2);
+    const ExprPlan& plan = f->plan;
+    bool fast = plan.nodes.size() == 3 && plan.nodes[0].kind == DFGPU_EXPR_COLUMN && plan.nodes[1].kind == DFGPU_EXPR_LITERAL && plan.nodes[2].kind == DFGPU_EXPR_BINARY &&
+                plan.nodes[2].a >= DFGPU_OP_EQ && plan.nodes[2].a <= DFGPU_OP_GTEQ && !plan.nodes[1].is_null;
+    if (fast) {
+      const DCol& c = cols[plan.nodes[0].a];
+      fast = cls_of(c.type) == C_I64 && type_width(c.type) == 8 && !c.validity;
+    }
+    {
+      KernelTimer kt(ctx, "filter_fused");
+      if (fast) {
+        filter_fused_kernel<1><<<(int)nt, kFiltThreads, 0, ctx->stream>>>(nullptr, (const int64_t*)cols[plan.nodes[0].a].values, plan.nodes[2].a, (int64_t)literal_bits(plan.nodes[1]), n,
+                                                                          fc, desc.as<unsigned long long>(), counter, totals, err.as<int>());
+      } else {
+        EProgram prog;
+        bind_program(plan, cols, &prog);
+        progbuf.alloc(ctx, sizeof(EProgram));
+        DF_CUDA(cudaMemcpyAsync(progbuf.ptr, &prog, sizeof(EProgram), cudaMemcpyHostToDevice, ctx->stream));
+        DF_CUDA(cudaStreamSynchronize(ctx->stream));  // `prog` lives on this stack frame
+        filter_fused_kernel<0><<<(int)nt, kFiltThreads, 0, ctx->stream>>>((const EProgram*)progbuf.ptr, nullptr, 0, 0, n, fc, desc.as<unsigned long long>(), counter, totals, err.as<int>());
+      }
+      DF_LAUNCH_CHECK(ctx);
+    }
+    unsigned long long h[2];
+    int herr = 0;
+    DF_CUDA(cudaMemcpyAsync(h, totals, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    DF_CUDA(cudaMemcpyAsync(&herr, err.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    DF_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (herr & ERR_DIV_ZERO) throw Error(DFGPU_ERR_ARITH, "Arrow error: Divide by zero error");
+    if (herr & ERR_OVERFLOW) throw Error(DFGPU_ERR_ARITH, "Arrow error: Arithmetic overflow");
+    const int64_t kept = (int64_t)h[0];
+    if (kept == 0) return;
+    for (auto& c : part) c.length = kept;
+    f->total_rows += kept;
+    f->pending.push_back(std::move(part));
+    f->pending_rows += kept;
+    filter_flush(f, false);
+    return;
+  }
   EvalResult ev = evaluate_expr(ctx, f->plan, cols, n, false, true);
   DevBuf idx;
   int64_t kept = compact_flag_indices(ctx, ev.select_words.as<uint32_t>(), n, 1, &idx);

@@ -69,4 +69,41 @@ __global__ void scan_tiles_kernel(uint64_t* __restrict__ sums, int64_t n, uint64
   if (threadIdx.x == 0) *total_out = carry;
 }
 
+// ---- single-pass ordered compaction support: tile descriptors + decoupled look-back ----
+#define kDescAgg (1ull << 62)
+#define kDescPrefix (2ull << 62)
+#define kDescMask ((1ull << 62) - 1ull)
+
+// decoupled look-back over tile descriptors (status in the top 2 bits, value below); called by warp 0.
+// Returns the exclusive prefix of `tot` for `tile` and publishes this tile's inclusive prefix.
+__device__ __forceinline__ unsigned long long tile_lookback(int64_t tile, uint32_t tot, unsigned long long* tile_desc) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long exclusive = 0;
+  if (tile == 0) {
+    if (lane == 0) atomicExch(&tile_desc[0], kDescPrefix | (unsigned long long)tot);
+    return 0;
+  }
+  if (lane == 0) atomicExch(&tile_desc[tile], kDescAgg | (unsigned long long)tot);
+  int64_t look = tile - 1;
+  while (true) {
+    const int64_t idx = look - lane;
+    unsigned long long d = idx >= 0 ? *(volatile unsigned long long*)&tile_desc[idx] : kDescPrefix;  // virtual prefix 0 before tile 0
+    const unsigned st = (unsigned)(d >> 62);
+    const unsigned invalid = __ballot_sync(0xffffffffu, st == 0);
+    const unsigned prefix = __ballot_sync(0xffffffffu, st == 2);
+    const int first_prefix = prefix ? __ffs(prefix) - 1 : 32;
+    const int first_invalid = invalid ? __ffs(invalid) - 1 : 32;
+    if (first_invalid < first_prefix) continue;  // a predecessor in the window has not published yet: spin
+    unsigned long long contrib = (lane <= first_prefix) ? (d & kDescMask) : 0ull;
+#pragma unroll
+    for (int dd = 16; dd > 0; dd >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, dd);
+    exclusive += contrib;
+    if (first_prefix < 32) break;
+    look -= 32;
+  }
+  if (lane == 0) atomicExch(&tile_desc[tile], kDescPrefix | (exclusive + (unsigned long long)tot));
+  return exclusive;
+}
+
+
 }  // namespace dfgpu

@@ -26,4 +26,16 @@ if which in ("all", "agg"):
         print("groups", a.metric("num_groups"))
         for b in a.drain(host=False): b.release()
         a.close()
+if which in ("all", "filter"):
+    n = int(100_000_000 * scale)
+    x = ctx.generate_i64(D.GEN_UNIFORM, 1, 0, 1 << 32, 0, n); y = ctx.generate_i64(D.GEN_SPLITMIX, 2, 0, 0, 0, n)
+    c = int((1 << 32) * 0.8)   # selectivity 20 % (the reference's default guess, filter.rs:79)
+    nodes = [(D.EXPR_COLUMN, 0, 0, 0, 0, 0.0), (D.EXPR_LITERAL, 0, D.INT64, 0, c, 0.0), (D.EXPR_BINARY, D.OP_GT, 0, 0, 0, 0.0)]
+    for it in range(2):
+        f = D.FilterHandle(ctx, [D.INT64, D.INT64], nodes, batch_size=0)
+        f.push_device([col(x, n), col(y, n)]); f.finish()
+        outs = f.drain(host=False)
+        print("filter kept", sum(o.num_rows for o in outs))
+        for b in outs: b.release()
+        f.close()
 ctx.sync()

@@ -81,6 +81,7 @@ def main():
         if "JoinFilter" in body or "filter" in name or "struct" in name or "dict" in name or "null_aware" in name:
             continue
         tables = {}
+        repeat = {"left": 1, "right": 1}
         ok = True
         for side in ("left", "right"):
             mm = re.search(r"let %s = (\w+)\(" % side, body)
@@ -88,9 +89,10 @@ def main():
                 ok = False
                 break
             fn = mm.group(1)
-            if fn in ("build_table", "build_table_two_cols"):
+            if fn in ("build_table", "build_table_two_cols", "build_table_two_batches"):
                 e = balanced(body, body.index("(", mm.start()))
                 tables[side] = parse_table_call(body[mm.start():e])
+                repeat[side] = 2 if fn == "build_table_two_batches" else 1   # exec.rs:3853-3861: the same batch twice
             elif fn in helpers:
                 tables[side] = helpers[fn]
             else:
@@ -113,9 +115,17 @@ def main():
         jt = re.search(r"JoinType::(\w+)", body)
         ne = re.search(r"NullEquality::(\w+)", body)
         snap = re.search(r'assert_snapshot!\(\s*(batches_to_string|batches_to_sort_string)\(&batches\),\s*@r"(.*?)"\s*\)', body, re.S)
-        if not jt or not snap:
+        sorted_cmp = None
+        if snap:
+            rows = [l.strip() for l in snap.group(2).split("\n") if l.strip().startswith("|")]
+            sorted_cmp = snap.group(1) == "batches_to_sort_string"
+        else:  # let expected = ["+--+", "| a |", ...]; assert_batches[_sorted]_eq!(expected, &batches)
+            arr = re.search(r'let expected = \[(.*?)\];\s*assert_batches(_sorted)?_eq!\(expected, &batches\)', body, re.S)
+            if arr:
+                rows = [q.strip() for q in re.findall(r'"([^"]*)"', arr.group(1)) if q.strip().startswith("|")]
+                sorted_cmp = arr.group(2) is not None
+        if not jt or sorted_cmp is None or not rows:
             continue
-        rows = [l.strip() for l in snap.group(2).split("\n") if l.strip().startswith("|")]
         header = [c.strip() for c in rows[0].strip("|").split("|")]
         exp = []
         for r in rows[1:]:
@@ -124,7 +134,8 @@ def main():
         partitioned = "partitioned_join_collect" in body or "PartitionMode::Partitioned" in body
         cases.append(dict(name=name, ref="datafusion/physical-plan/src/joins/hash_join/exec.rs:%d" % line, left=tables["left"], right=tables["right"],
                           on=pairs, join_type=jt.group(1), null_equality=ne.group(1) if ne else "NullEqualsNothing",
-                          sorted=snap.group(1) == "batches_to_sort_string", partitioned=partitioned, header=header, expected=exp))
+                          sorted=sorted_cmp, partitioned=partitioned, header=header, expected=exp,
+                          left_repeat=repeat["left"], right_repeat=repeat["right"]))
     json.dump(dict(source=SRC, note="transcribed by tests/golden/extract_hash_join_kat.py; do not edit by hand", cases=cases), open(OUT, "w"), indent=1)
     print("wrote %d cases to %s" % (len(cases), OUT))
     for c in cases:

@@ -39,7 +39,8 @@ def test_join_snapshots_through_arrow_boundary(gpu_ctx, case):
         for phj in (True, False):
             cfg = SessionConfig(batch_size=batch_size, perfect_hash_join_small_build_threshold=819200 if phj else 0,
                                 perfect_hash_join_min_key_density=0.0 if phj else float("inf"))
-            join = GpuHashJoinExec(MemoryExec([left]), MemoryExec([right]), on, case["join_type"], case["null_equality"])
+            join = GpuHashJoinExec(MemoryExec([left] * case.get("left_repeat", 1)), MemoryExec([right] * case.get("right_repeat", 1)), on,
+                                   case["join_type"], case["null_equality"])
             got = table_rows(collect(join, TaskContext(cfg, gpu_ctx)))
             assert len(join.schema) == len(case["header"])
             exp = case["expected"]

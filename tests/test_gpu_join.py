@@ -25,9 +25,10 @@ def test_gpu_matches_reference_join_snapshots(gpu_ctx, case):
     left, right, on_b, on_p, side, idx, exp = kat_tables(case)
     for batch_size, phj in MATRIX:
         thr, dens = (819200, 0.0) if phj else (0, float("inf"))
+        nl, nr = len(case["left"][0][1]), len(case["right"][0][1])
         got, h = gpu_hash_join(gpu_ctx, left, right, on_b, on_p, side, idx, GJT[case["join_type"]],
                                D.NULL_EQUALS_NULL if case["null_equality"] == "NullEqualsNull" else D.NULL_EQUALS_NOTHING,
-                               batch_size=batch_size, phj=(thr, dens), probe_batch_rows=batch_size, return_handle=True)
+                               batch_size=batch_size, phj=(thr, dens), probe_batch_rows=min(batch_size, nr), build_batch_rows=nl, return_handle=True)
         ordered = (not case["sorted"]) and case["join_type"] in ORDERED
         assert_cols_equal(got, exp, ordered=ordered, what=f"{case['name']} bs={batch_size} phj={phj} ({case['ref']})")
         # assert_phj_used (exec.rs: array_map_created_count metric)

@@ -15,8 +15,9 @@ MISC = load_golden("misc_kat.json")
 
 
 def kat_tables(case):
-    left = [col_from_list(v) for _, v in case["left"]]
-    right = [col_from_list(v) for _, v in case["right"]]
+    # build_table_two_batches (exec.rs:3853-3861) feeds the same batch twice: case["left_repeat"/"right_repeat"]
+    left = [col_from_list(list(v) * case.get("left_repeat", 1)) for _, v in case["left"]]
+    right = [col_from_list(list(v) * case.get("right_repeat", 1)) for _, v in case["right"]]
     ln, rn = [n for n, _ in case["left"]], [n for n, _ in case["right"]]
     on_b = [ln.index(l) for l, _ in case["on"]]
     on_p = [rn.index(r) for _, r in case["on"]]
@@ -50,8 +51,10 @@ def test_oracle_reproduces_reference_join_snapshots(case):
     left, right, on_b, on_p, side, idx, exp = kat_tables(case)
     for batch_size, phj in MATRIX:
         thr, dens = (819200, 0.0) if phj else (0, float("inf"))
+        nl, nr = len(case["left"][0][1]), len(case["right"][0][1])
         got = O.hash_join(left, right, on_b, on_p, side, idx, join_type=JT[case["join_type"]],
-                          null_equals_null=case["null_equality"] == "NullEqualsNull", batch_size=batch_size, phj_threshold=thr, phj_density=dens)
+                          null_equals_null=case["null_equality"] == "NullEqualsNull", batch_size=batch_size, phj_threshold=thr, phj_density=dens,
+                          build_batch_rows=[nl] * case.get("left_repeat", 1), probe_batch_rows=[nr] * case.get("right_repeat", 1))
         assert_cols_equal(got, exp, ordered=not case["sorted"], what=f"{case['name']} bs={batch_size} phj={phj} ({case['ref']})")
 
 
