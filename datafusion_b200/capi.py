@@ -94,7 +94,7 @@ EXPORTS = [
     "dfgpu_filter_create", "dfgpu_filter_push_host", "dfgpu_filter_push_device", "dfgpu_filter_push_arrow",
     "dfgpu_filter_finish", "dfgpu_filter_next", "dfgpu_filter_metric", "dfgpu_filter_destroy",
     "dfgpu_expr_evaluate_device", "dfgpu_expr_evaluate_host",
-    "dfgpu_hashjoin_default_options", "dfgpu_hashjoin_create", "dfgpu_hashjoin_push_build_host",
+    "dfgpu_hashjoin_default_options", "dfgpu_hashjoin_create", "dfgpu_hashjoin_set_filter", "dfgpu_hashjoin_push_build_host",
     "dfgpu_hashjoin_push_build_device", "dfgpu_hashjoin_push_build_arrow", "dfgpu_hashjoin_finish_build",
     "dfgpu_hashjoin_push_probe_host", "dfgpu_hashjoin_push_probe_device", "dfgpu_hashjoin_push_probe_arrow",
     "dfgpu_hashjoin_finish_probe", "dfgpu_hashjoin_next", "dfgpu_hashjoin_metric", "dfgpu_hashjoin_destroy",
@@ -171,6 +171,7 @@ def load_library() -> C.CDLL:
     sig("dfgpu_hashjoin_default_options", None, [P(HashJoinOptions)])
     sig("dfgpu_hashjoin_create", C.c_int, [vp, P(i32), i32, P(i32), i32, P(i32), P(i32), i32, P(i32), P(i32), i32,
                                            P(HashJoinOptions), P(vp)])
+    sig("dfgpu_hashjoin_set_filter", C.c_int, [vp, P(i32), P(i32), i32, P(ExprNode), i32])
     sig("dfgpu_agg_create", C.c_int, [vp, P(i32), i32, P(i32), i32, P(AggDesc), i32, i32, i64, i64, P(vp)])
     sig("dfgpu_batch_num_rows", i64, [vp])
     sig("dfgpu_batch_num_columns", i32, [vp])
@@ -560,6 +561,11 @@ class HashJoinHandle(_Operator):
         ctx.check(ctx.lib.dfgpu_hashjoin_create(ctx.h, _i32arr(build_types), len(build_types), _i32arr(probe_types), len(probe_types),
                                                 _i32arr(on_build), _i32arr(on_probe), len(on_build), _i32arr(out_side), _i32arr(out_index),
                                                 len(out_side), C.byref(opt), C.byref(self.h)))
+
+    def set_filter(self, col_side, col_index, nodes):
+        """JoinFilter: intermediate column c = column col_index[c] of side col_side[c] (0 build / 1 probe); nodes = RPN over them"""
+        na = expr_nodes(nodes)
+        self.ctx.check(self.ctx.lib.dfgpu_hashjoin_set_filter(self.h, _i32arr(col_side), _i32arr(col_index), len(col_side), na, len(nodes)))
 
     def push_build_host(self, cols): self._push("dfgpu_hashjoin_push_build_host", cols)
     def push_build_device(self, cols): self._push("dfgpu_hashjoin_push_build_device", cols)

@@ -16,6 +16,7 @@
 // Selection = that bitmap -> popcount/scan -> index list -> one gather per projected column.
 #include "batch.cuh"
 #include "scan.cuh"
+#include "expr.cuh"
 
 namespace dfgpu {
 
@@ -411,12 +412,6 @@ __global__ void __launch_bounds__(kFiltThreads) filter_fused_kernel(const EProgr
 // ------------------------------------------------------------------------------------------
 // host side: type inference + program binding
 // ------------------------------------------------------------------------------------------
-struct ExprPlan {
-  std::vector<dfgpu_expr_node> nodes;
-  std::vector<int> in_type, out_type;
-  int root_type = 0;
-};
-
 static bool is_cmp_op(int op) { return (op >= DFGPU_OP_EQ && op <= DFGPU_OP_GTEQ) || op == DFGPU_OP_IS_DISTINCT_FROM || op == DFGPU_OP_IS_NOT_DISTINCT_FROM; }
 static bool is_arith_op(int op) { return op >= DFGPU_OP_PLUS && op <= DFGPU_OP_MODULO; }
 static bool is_bit_op(int op) { return op >= DFGPU_OP_BITAND && op <= DFGPU_OP_SHIFT_RIGHT; }
@@ -530,7 +525,6 @@ static void bind_program(const ExprPlan& plan, const std::vector<DCol>& cols, EP
 }
 
 // Evaluate `plan` over device columns.  want_select: also produce selection words (valid & true).
-struct EvalResult { DCol column; DevBuf select_words; };
 
 EvalResult evaluate_expr(dfgpu_ctx* ctx, const ExprPlan& plan, const std::vector<DCol>& cols, int64_t n, bool want_column, bool want_select) {
   EvalResult res;

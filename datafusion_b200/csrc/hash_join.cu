@@ -25,6 +25,7 @@
 //     one gather (`take`) kernel per output column.
 #include "batch.cuh"
 #include "scan.cuh"
+#include "expr.cuh"
 
 namespace dfgpu {
 
@@ -903,6 +904,11 @@ struct dfgpu_hashjoin {
   int64_t distinct = 0, valid_rows = 0, null_rows = 0;
   bool need_visited = false;
   int emit_mode = EMIT_PAIRS;
+  // JoinFilter (joins/utils.rs apply_join_filter_to_indices :1248-1320): residual predicate over an intermediate batch
+  bool has_filter = false;
+  std::vector<int> filt_side, filt_index;
+  ExprPlan filt_plan;
+  DevBuf visited_rows;   // per build ROW visited bitmap (with a filter, rows of one key can differ)
   // inline-payload table (unique keys, Inner, narrow build side)
   bool inline_ok = false;
   int inline_words = 0;
@@ -1043,7 +1049,7 @@ static void finish_build(dfgpu_hashjoin* j) {
   }
   // ---- inline-payload attempt ----
   j->inline_ok = false;
-  if (n > 0 && j->emit_mode == EMIT_PAIRS && !j->need_visited && j->opt.null_equality == DFGPU_NULL_EQUALS_NOTHING && !j->opt.force_hash_collisions &&
+  if (n > 0 && !j->has_filter && j->emit_mode == EMIT_PAIRS && !j->need_visited && j->opt.null_equality == DFGPU_NULL_EQUALS_NOTHING && !j->opt.force_hash_collisions &&
       j->out_side.size() <= (size_t)kMaxFusedCols) {
     bool ok = true;
     int bits = 0;
@@ -1121,6 +1127,7 @@ static void finish_build(dfgpu_hashjoin* j) {
   j->valid_rows = (int64_t)hc[1];
   j->null_rows = (int64_t)hc[2];
   j->unique = (j->distinct == j->valid_rows);  // map.len() == next.len() fast path, join_hash_map.rs:410-429
+  if (j->has_filter && j->need_visited) { j->visited_rows.alloc(ctx, (size_t)((n + 31) / 32 + 1) * 4); j->visited_rows.zero(); }
   j->built = true;
 }
 
@@ -1154,6 +1161,125 @@ static BatchPtr materialize(dfgpu_hashjoin* j, const std::vector<DCol>* probe_co
     }
   }
   return out;
+}
+
+__global__ void scatter_u32_kernel(const uint32_t* __restrict__ pos, int64_t n, uint32_t* __restrict__ dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[pos[i]] = 0u;
+}
+__global__ void mark_bits_kernel(const uint32_t* __restrict__ idx, int64_t n, uint32_t* __restrict__ words) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = idx[i];
+    atomicOr(&words[r >> 5], 1u << (r & 31));
+  }
+}
+
+static DCol idx_as_col(const uint32_t* p, int64_t n) {
+  DCol d;
+  d.type = DFGPU_UINT32; d.length = n; d.values = p; d.null_count = 0;
+  return d;
+}
+
+// Probe with a JoinFilter: candidate pairs -> filter on the intermediate batch -> join-type handling from the
+// surviving pairs (stream.rs:896-948: apply_join_filter_to_indices, then visited bitmap + adjust_indices_by_join_type).
+static void push_probe_filtered(dfgpu_hashjoin* j, const std::vector<DCol>& cols, const KeyCols& pk, int64_t n) {
+  dfgpu_ctx* ctx = j->ctx;
+  const int jt = j->opt.join_type;
+  // 1. every candidate pair (equal keys), reference order
+  const int64_t ntiles = (n + kProbeTile - 1) / kProbeTile;
+  DevBuf head(ctx, (size_t)n * 4), cnt(ctx, (size_t)n * 4), tiles(ctx, (size_t)(ntiles + 1) * 8), hits(ctx, 8);
+  hits.zero();
+  join_probe_count_kernel<false><<<(int)ntiles, kProbeThreads, 0, ctx->stream>>>(pk, n, j->table, EMIT_PAIRS, 0, head.as<uint32_t>(), cnt.as<uint32_t>(),
+                                                                                 tiles.as<uint64_t>(), hits.as<unsigned long long>());
+  DF_LAUNCH_CHECK(ctx);
+  scan_tiles_kernel<1024><<<1, 1024, 0, ctx->stream>>>(tiles.as<uint64_t>(), ntiles, tiles.as<uint64_t>() + ntiles);
+  DF_LAUNCH_CHECK(ctx);
+  const int64_t total = (int64_t)read_scalar<uint64_t>(ctx, tiles.as<uint64_t>() + ntiles);
+  DevBuf bidx(ctx, (size_t)std::max<int64_t>(total, 1) * 4), pidx(ctx, (size_t)std::max<int64_t>(total, 1) * 4);
+  join_emit_kernel<false><<<(int)ntiles, kProbeThreads, 0, ctx->stream>>>(n, head.as<uint32_t>(), cnt.as<uint32_t>(), j->table.next, tiles.as<uint64_t>(), EMIT_PAIRS,
+                                                                         bidx.as<uint32_t>(), pidx.as<uint32_t>());
+  DF_LAUNCH_CHECK(ctx);
+  // 2. the filter's intermediate batch (only the referenced columns are gathered) and its predicate
+  DCol fb, fp;  // surviving pairs
+  int64_t kept = 0;
+  if (total > 0) {
+    std::vector<DCol> inter;
+    for (size_t c = 0; c < j->filt_side.size(); ++c)
+      inter.push_back(j->filt_side[c] == 0 ? take_column(ctx, j->build_cols[j->filt_index[c]], bidx.as<uint32_t>(), total, false)
+                                           : take_column(ctx, cols[j->filt_index[c]], pidx.as<uint32_t>(), total, false));
+    EvalResult ev = evaluate_expr(ctx, j->filt_plan, inter, total, false, true);
+    DevBuf sel;
+    kept = compact_flag_indices(ctx, ev.select_words.as<uint32_t>(), total, 1, &sel);
+    if (kept > 0) {
+      fb = take_column(ctx, idx_as_col(bidx.as<uint32_t>(), total), sel.as<uint32_t>(), kept, false);
+      fp = take_column(ctx, idx_as_col(pidx.as<uint32_t>(), total), sel.as<uint32_t>(), kept, false);
+    }
+  }
+  const uint32_t* fbp = kept ? (const uint32_t*)fb.values : nullptr;
+  const uint32_t* fpp = kept ? (const uint32_t*)fp.values : nullptr;
+  // 3. visited build rows (Left / Full / LeftSemi / LeftAnti / LeftMark)
+  if (j->need_visited && kept > 0) {
+    mark_bits_kernel<<<grid_for(kept, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(fbp, kept, j->visited_rows.as<uint32_t>());
+    DF_LAUNCH_CHECK(ctx);
+  }
+  // 4. probe rows that kept at least one pair
+  DevBuf pm(ctx, (size_t)((n + 31) / 32) * 4);
+  pm.zero();
+  if (kept > 0) {
+    mark_bits_kernel<<<grid_for(kept, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(fpp, kept, pm.as<uint32_t>());
+    DF_LAUNCH_CHECK(ctx);
+  }
+  j->m_probe_hits += count_set_bits(ctx, pm.as<uint8_t>(), 0, n);
+  BatchPtr out;
+  switch (jt) {
+    case DFGPU_JOIN_INNER: case DFGPU_JOIN_LEFT:
+      if (kept) out = materialize(j, &cols, fbp, fpp, kept, false, false, nullptr);
+      break;
+    case DFGPU_JOIN_RIGHT: case DFGPU_JOIN_FULL: {
+      // matched pairs, then the unmatched probe rows of this batch (append_right_indices, utils.rs:1509-1570)
+      DevBuf un;
+      const int64_t nun = compact_flag_indices(ctx, pm.as<uint32_t>(), n, 0, &un);
+      const int64_t tot2 = kept + nun;
+      if (tot2 == 0) break;
+      DevBuf b2(ctx, (size_t)tot2 * 4), p2(ctx, (size_t)tot2 * 4);
+      if (kept) {
+        DF_CUDA(cudaMemcpyAsync(b2.ptr, fbp, (size_t)kept * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        DF_CUDA(cudaMemcpyAsync(p2.ptr, fpp, (size_t)kept * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+      if (nun) {
+        DF_CUDA(cudaMemsetAsync((char*)b2.ptr + (size_t)kept * 4, 0xFF, (size_t)nun * 4, ctx->stream));  // NULL build index
+        DF_CUDA(cudaMemcpyAsync((char*)p2.ptr + (size_t)kept * 4, un.ptr, (size_t)nun * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+      out = materialize(j, &cols, b2.as<uint32_t>(), p2.as<uint32_t>(), tot2, true, false, nullptr);
+      break;
+    }
+    case DFGPU_JOIN_RIGHT_SEMI: case DFGPU_JOIN_RIGHT_ANTI: {
+      DevBuf sel;
+      const int64_t ns = compact_flag_indices(ctx, pm.as<uint32_t>(), n, jt == DFGPU_JOIN_RIGHT_SEMI ? 1 : 0, &sel);
+      if (ns) out = materialize(j, &cols, nullptr, sel.as<uint32_t>(), ns, true, false, nullptr);
+      break;
+    }
+    case DFGPU_JOIN_RIGHT_MARK: {
+      DevBuf all(ctx, (size_t)n * 4), markidx(ctx, (size_t)n * 4);
+      fill_iota(ctx, all.as<uint32_t>(), n);
+      // mark source: an index array whose NULL marker encodes "no surviving pair"
+      DF_CUDA(cudaMemsetAsync(markidx.ptr, 0xFF, (size_t)n * 4, ctx->stream));
+      if (kept) {
+        DevBuf msel;
+        const int64_t nm = compact_flag_indices(ctx, pm.as<uint32_t>(), n, 1, &msel);
+        // scatter 0 into the matched positions
+        if (nm) {
+          DCol zeros = alloc_col(ctx, DFGPU_UINT32, nm, false);
+          zeros.own_values->zero();
+          scatter_u32_kernel<<<grid_for(nm, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(msel.as<uint32_t>(), nm, markidx.as<uint32_t>());
+          DF_LAUNCH_CHECK(ctx);
+        }
+      }
+      out = materialize(j, &cols, nullptr, all.as<uint32_t>(), n, true, false, markidx.as<uint32_t>());
+      break;
+    }
+    default: break;  // LeftSemi / LeftAnti / LeftMark: produced by finish_probe from visited_rows
+  }
+  if (out && out->rows > 0) emit_batch(j, std::move(out));
 }
 
 static void push_probe(dfgpu_hashjoin* j, std::vector<DCol>&& cols) {
@@ -1229,6 +1355,7 @@ static void push_probe(dfgpu_hashjoin* j, std::vector<DCol>&& cols) {
     return;
   }
   // ---- fused single-pass path: unique build keys, one output row per matching probe row, plain columns ----
+  if (j->has_filter) { push_probe_filtered(j, cols, pk, n); return; }
   if (mode == EMIT_PAIRS && j->unique && !j->opt.force_hash_collisions && j->out_side.size() <= (size_t)kMaxFusedCols) {
     bool plain = true;
     for (size_t c = 0; c < j->out_side.size() && plain; ++c) {
@@ -1449,8 +1576,12 @@ static void finish_probe(dfgpu_hashjoin* j) {
   // get_final_indices_from_bit_map (utils.rs:1210-1245)
   int64_t nw = (n + 31) / 32;
   DevBuf vis(ctx, (size_t)nw * 4);
-  join_build_flags_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(j->build_keys, n, j->table, vis.as<uint32_t>());
-  DF_LAUNCH_CHECK(ctx);
+  if (j->has_filter) {
+    DF_CUDA(cudaMemcpyAsync(vis.ptr, j->visited_rows.ptr, (size_t)nw * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    join_build_flags_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(j->build_keys, n, j->table, vis.as<uint32_t>());
+    DF_LAUNCH_CHECK(ctx);
+  }
   if (jt == DFGPU_JOIN_LEFT_MARK) {
     // all build rows + mark column (visited)
     DevBuf all(ctx, (size_t)n * 4);
@@ -1551,6 +1682,24 @@ static std::vector<DCol> device_cols_view(const dfgpu_column* cols, int32_t n) {
   return v;
 }
 
+int dfgpu_hashjoin_set_filter(dfgpu_hashjoin* j, const int32_t* col_side, const int32_t* col_index, int32_t n_cols, const dfgpu_expr_node* expr, int32_t n_nodes) {
+  DF_API_BEGIN(j ? j->ctx : nullptr)
+  DF_CHECK(j && col_side && col_index && expr && n_cols >= 1, DFGPU_ERR_INVALID, "null argument");
+  DF_CHECK(!j->built && j->build_parts.empty(), DFGPU_ERR_STATE, "set_filter must be called before any batch is pushed");
+  std::vector<int32_t> types;
+  for (int c = 0; c < n_cols; ++c) {
+    DF_CHECK(col_side[c] == 0 || col_side[c] == 1, DFGPU_ERR_INVALID, "join filter column side must be 0 (build) or 1 (probe)");
+    const auto& tv = col_side[c] == 0 ? j->build_types : j->probe_types;
+    DF_CHECK(col_index[c] >= 0 && col_index[c] < (int)tv.size(), DFGPU_ERR_INVALID, "join filter column index out of range");
+    types.push_back(tv[col_index[c]]);
+  }
+  j->filt_plan = plan_expr(types.data(), n_cols, expr, n_nodes);
+  DF_CHECK(j->filt_plan.root_type == DFGPU_BOOL, DFGPU_ERR_INVALID, "join filter expression must return Boolean");
+  j->filt_side.assign(col_side, col_side + n_cols);
+  j->filt_index.assign(col_index, col_index + n_cols);
+  j->has_filter = true;
+  DF_API_END
+}
 int dfgpu_hashjoin_push_build_host(dfgpu_hashjoin* j, const dfgpu_column* cols, int32_t n_cols) {
   DF_API_BEGIN(j ? j->ctx : nullptr)
   push_build(j, host_cols_to_device(j->ctx, cols, n_cols));

@@ -332,6 +332,14 @@ def build_join_schema(left: pa.Schema, right: pa.Schema, join_type: str) -> Tupl
     raise ValueError(join_type)
 
 
+class JoinFilter:
+    """joins/utils.rs JoinFilter: `expression` over an intermediate batch whose column c ("f0", "f1", ...) is
+    column_indices[c] = (side "left"|"right", index)"""
+
+    def __init__(self, expression: Expr, column_indices: Sequence[Tuple[str, int]]):
+        self.expression, self.column_indices = expression, list(column_indices)
+
+
 class GpuHashJoinExec(ExecutionPlan):
     """HashJoinExec::try_new(left, right, on, filter, join_type, projection, partition_mode, null_equality)
     (physical-plan/src/joins/hash_join/exec.rs:752).  left = build side, right = probe side."""
@@ -340,8 +348,7 @@ class GpuHashJoinExec(ExecutionPlan):
                  null_equality: str = "NullEqualsNothing", filter=None, projection: Optional[Sequence[int]] = None):
         if not on:
             raise ValueError("Error during planning: On constraints in HashJoinExec should be non-empty")  # exec.rs try_new
-        if filter is not None:
-            raise NotImplementedError("This feature is not implemented: join filters stay on the CPU HashJoinExec")
+        self.filter = filter
         self.left, self.right, self.on, self.join_type, self.null_equality = left, right, list(on), join_type, null_equality
         full, idx = build_join_schema(left.schema, right.schema, join_type)
         if projection is not None:
@@ -364,6 +371,12 @@ class GpuHashJoinExec(ExecutionPlan):
                               _JOIN_TYPES[self.join_type], D.NULL_EQUALS_NULL if self.null_equality == "NullEqualsNull" else D.NULL_EQUALS_NOTHING,
                               cfg.batch_size, cfg.perfect_hash_join_small_build_threshold, cfg.perfect_hash_join_min_key_density,
                               cfg.force_hash_collisions)
+        if self.filter is not None:
+            fields = [(self.left.schema if sd == "left" else self.right.schema).field(ix) for sd, ix in self.filter.column_indices]
+            inter = pa.schema([pa.field(f"f{i}", f.type) for i, f in enumerate(fields)])
+            nodes: list = []
+            self.filter.expression.rpn(inter, nodes)
+            op.set_filter([0 if sd == "left" else 1 for sd, _ in self.filter.column_indices], [ix for _, ix in self.filter.column_indices], nodes)
         try:
             for rb in self.left.execute(ctx):     # collect_left_input
                 op.push_build_arrow(rb)

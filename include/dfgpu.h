@@ -257,6 +257,11 @@ int dfgpu_hashjoin_create(dfgpu_ctx* ctx,
                           const int32_t* on_build, const int32_t* on_probe, int32_t n_on,
                           const int32_t* out_side, const int32_t* out_index, int32_t n_out,
                           const dfgpu_hashjoin_options* opts, dfgpu_hashjoin** out);
+/* optional JoinFilter (joins/utils.rs:1248-1320 apply_join_filter_to_indices; hash_join/stream.rs:896-906): a Boolean
+ * expression over an intermediate batch whose column c is column col_index[c] of side col_side[c] (0 build, 1 probe).
+ * Must be called before the first push.  NULL / false filter results drop the candidate pair. */
+int dfgpu_hashjoin_set_filter(dfgpu_hashjoin* j, const int32_t* col_side, const int32_t* col_index, int32_t n_cols,
+                              const dfgpu_expr_node* expr, int32_t n_nodes);
 int dfgpu_hashjoin_push_build_host(dfgpu_hashjoin* j, const dfgpu_column* cols, int32_t n_cols);
 int dfgpu_hashjoin_push_build_device(dfgpu_hashjoin* j, const dfgpu_column* cols, int32_t n_cols);
 int dfgpu_hashjoin_push_build_arrow(dfgpu_hashjoin* j, const struct ArrowArray* batch, const struct ArrowSchema* schema);

@@ -284,7 +284,8 @@ O_API int oracle_hash_join(int nkeys, const int64_t* const* bkeys_in, const uint
                            const int64_t* const* pkeys, const uint8_t* const* pvalid, int64_t np_,
                            const int64_t* probe_batch_rows, int n_probe_batches,
                            int join_type, int null_equals_null, int64_t batch_size, int64_t phj_threshold, double phj_density,
-                           int force_collisions, int key_is_integer, JoinResult* res, int64_t* build_order_out) {
+                           int force_collisions, int key_is_integer, JoinResult* res, int64_t* build_order_out,
+                           int (*pair_filter)(int64_t build_row, int64_t probe_row) /* JoinFilter on ORIGINAL row numbers, or NULL */) {
   memset(res, 0, sizeof(*res));
   Vec64 out_b = {0}, out_p = {0}, out_m = {0};
   /* ---- perfect-hash decision: try_create_array_map, exec.rs:111-191 ---- */
@@ -412,6 +413,11 @@ O_API int oracle_hash_join(int nkeys, const int64_t* const* bkeys_in, const uint
         }
         bi.n = pi.n = m;
       } else m = bi.n;
+      if (pair_filter) { /* apply_join_filter_to_indices (utils.rs:1248-1320): after the key check, before visited/adjust */
+        int64_t m2 = 0;
+        for (int64_t k = 0; k < m; ++k) if (pair_filter(order[bi.p[k]], pstart + pi.p[k])) { bi.p[m2] = bi.p[k]; pi.p[m2] = pi.p[k]; ++m2; }
+        m = bi.n = pi.n = m2;
+      }
       if (need_final) for (int64_t k = 0; k < m; ++k) visited[bi.p[k]] = 1;
       int64_t last_joined = m ? pi.p[m - 1] : -1;
       int64_t range_start = joined_probe_idx < 0 ? 0 : joined_probe_idx + 1;

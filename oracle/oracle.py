@@ -64,6 +64,9 @@ def lib() -> C.CDLL:
     return _lib
 
 
+_PAIR_FILTER = C.CFUNCTYPE(C.c_int, C.c_int64, C.c_int64)
+
+
 def _i64(a) -> np.ndarray:
     a = np.asarray(a)
     if a.dtype == np.bool_:
@@ -93,7 +96,7 @@ def _ptr_array(arrs, ctype):
 def hash_join_indices(build_keys: Sequence[Col], probe_keys: Sequence[Col], join_type: int = J_INNER, null_equals_null: bool = False,
                       batch_size: int = 8192, phj_threshold: int = 1024, phj_density: float = 0.15, force_collisions: bool = False,
                       build_batch_rows: Optional[Sequence[int]] = None, probe_batch_rows: Optional[Sequence[int]] = None,
-                      key_is_integer: bool = True):
+                      key_is_integer: bool = True, pair_filter=None):
     """(build_idx, probe_idx, mark, used_array_map): -1 = NULL index.  Order = the reference's emission order."""
     L = lib()
     nk = len(build_keys)
@@ -112,7 +115,8 @@ def hash_join_indices(build_keys: Sequence[Col], probe_keys: Sequence[Col], join
                        _ptr_array(pk, C.c_int64), _ptr_array(pv, C.c_uint8) if any(v is not None for v in pv) else None, C.c_int64(npr),
                        pbr.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int(len(pbr)), C.c_int(join_type), C.c_int(1 if null_equals_null else 0),
                        C.c_int64(batch_size), C.c_int64(phj_threshold), C.c_double(phj_density), C.c_int(1 if force_collisions else 0),
-                       C.c_int(1 if key_is_integer else 0), C.byref(res), None)
+                       C.c_int(1 if key_is_integer else 0), C.byref(res), None,
+                       _PAIR_FILTER(lambda b, p: 1 if pair_filter(int(b), int(p)) else 0) if pair_filter is not None else None)
     n = res.n
     if n == 0:
         b, p, m = np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, bool)
@@ -141,6 +145,18 @@ def take(col: Col, idx: np.ndarray) -> Col:
 def hash_join(build: Sequence[Col], probe: Sequence[Col], on_build: Sequence[int], on_probe: Sequence[int], out_side: Sequence[int],
               out_index: Sequence[int], **kw) -> List[Col]:
     """Materialised join output (build_batch_from_indices, joins/utils.rs:1332-1387)."""
+    if "filter" in kw:   # (col_side, col_index, nodes): evaluated per candidate pair with the numpy expression oracle
+        fs, fi, nodes = kw.pop("filter")
+
+        def pf(brow, prow):
+            cols = []
+            for sd, ix in zip(fs, fi):
+                v, val = (build if sd == 0 else probe)[ix]
+                r = brow if sd == 0 else prow
+                cols.append((np.asarray(v)[r:r + 1], None if val is None else np.asarray(val, bool)[r:r + 1]))
+            rv, rvalid = eval_expr(cols, nodes)
+            return bool(rv[0]) and (rvalid is None or bool(rvalid[0]))
+        kw["pair_filter"] = pf
     b, p, m, _ = hash_join_indices([build[i] for i in on_build], [probe[i] for i in on_probe], **kw)
     jt = kw.get("join_type", J_INNER)
     out = []

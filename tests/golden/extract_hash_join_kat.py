@@ -78,7 +78,11 @@ def main():
             continue
         if "for join_type in" in body:  # multi-join-type loops are transcribed by hand into misc_kat.json
             continue
-        if "JoinFilter" in body or "filter" in name or "struct" in name or "dict" in name or "null_aware" in name:
+        # join_*_with_filter tests share prepare_join_filter() (exec.rs:5556-5583): left.c@2 > right.c@2
+        shared_filter = "prepare_join_filter()" in body and "JoinFilter::new" not in body
+        if ("JoinFilter" in body or "filter" in name) and not shared_filter:
+            continue
+        if "struct" in name or "dict" in name or "null_aware" in name:
             continue
         tables = {}
         repeat = {"left": 1, "right": 1}
@@ -135,7 +139,8 @@ def main():
         cases.append(dict(name=name, ref="datafusion/physical-plan/src/joins/hash_join/exec.rs:%d" % line, left=tables["left"], right=tables["right"],
                           on=pairs, join_type=jt.group(1), null_equality=ne.group(1) if ne else "NullEqualsNothing",
                           sorted=sorted_cmp, partitioned=partitioned, header=header, expected=exp,
-                          left_repeat=repeat["left"], right_repeat=repeat["right"]))
+                          left_repeat=repeat["left"], right_repeat=repeat["right"],
+                          filter=({"col_side": [0, 1], "col_index": [2, 2], "op": "gt", "ref": "exec.rs:5556-5583 prepare_join_filter"} if shared_filter else None)))
     json.dump(dict(source=SRC, note="transcribed by tests/golden/extract_hash_join_kat.py; do not edit by hand", cases=cases), open(OUT, "w"), indent=1)
     print("wrote %d cases to %s" % (len(cases), OUT))
     for c in cases:

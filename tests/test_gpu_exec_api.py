@@ -5,8 +5,8 @@ import numpy as np
 import pyarrow as pa
 import pytest
 
-from datafusion_b200.exec import (AggregateExpr, GpuAggregateExec, GpuFilterExec, GpuHashJoinExec, MemoryExec, SessionConfig, TaskContext, col,
-                                  collect, lit)
+from datafusion_b200.exec import (AggregateExpr, GpuAggregateExec, GpuFilterExec, GpuHashJoinExec, JoinFilter, MemoryExec, SessionConfig, TaskContext,
+                                  col, collect, lit)
 from harness import load_golden
 
 pytestmark = pytest.mark.gpu
@@ -39,8 +39,11 @@ def test_join_snapshots_through_arrow_boundary(gpu_ctx, case):
         for phj in (True, False):
             cfg = SessionConfig(batch_size=batch_size, perfect_hash_join_small_build_threshold=819200 if phj else 0,
                                 perfect_hash_join_min_key_density=0.0 if phj else float("inf"))
+            jf = None
+            if case.get("filter"):   # prepare_join_filter (exec.rs:5556-5583): JoinFilter(c@0 > c@1, [Left:2, Right:2])
+                jf = JoinFilter(col("f0") > col("f1"), [("left", 2), ("right", 2)])
             join = GpuHashJoinExec(MemoryExec([left] * case.get("left_repeat", 1)), MemoryExec([right] * case.get("right_repeat", 1)), on,
-                                   case["join_type"], case["null_equality"])
+                                   case["join_type"], case["null_equality"], filter=jf)
             got = table_rows(collect(join, TaskContext(cfg, gpu_ctx)))
             assert len(join.schema) == len(case["header"])
             exp = case["expected"]

@@ -9,7 +9,7 @@ import pytest
 from datafusion_b200 import capi as D
 from oracle import oracle as O
 from harness import assert_cols_equal, col_from_list, gpu_hash_join, load_golden
-from test_oracle_golden import JT, KAT, MATRIX, MISC, expected_cols, kat_tables, out_mapping
+from test_oracle_golden import JT, KAT, MATRIX, MISC, expected_cols, kat_filter, kat_tables, out_mapping
 
 pytestmark = pytest.mark.gpu
 GJT = {"Inner": D.JOIN_INNER, "Left": D.JOIN_LEFT, "Right": D.JOIN_RIGHT, "Full": D.JOIN_FULL, "LeftSemi": D.JOIN_LEFT_SEMI,
@@ -28,7 +28,8 @@ def test_gpu_matches_reference_join_snapshots(gpu_ctx, case):
         nl, nr = len(case["left"][0][1]), len(case["right"][0][1])
         got, h = gpu_hash_join(gpu_ctx, left, right, on_b, on_p, side, idx, GJT[case["join_type"]],
                                D.NULL_EQUALS_NULL if case["null_equality"] == "NullEqualsNull" else D.NULL_EQUALS_NOTHING,
-                               batch_size=batch_size, phj=(thr, dens), probe_batch_rows=min(batch_size, nr), build_batch_rows=nl, return_handle=True)
+                               batch_size=batch_size, phj=(thr, dens), probe_batch_rows=min(batch_size, nr), build_batch_rows=nl, return_handle=True,
+                               filter=kat_filter(case, gpu=True))
         ordered = (not case["sorted"]) and case["join_type"] in ORDERED
         assert_cols_equal(got, exp, ordered=ordered, what=f"{case['name']} bs={batch_size} phj={phj} ({case['ref']})")
         # assert_phj_used (exec.rs: array_map_created_count metric)
@@ -90,6 +91,20 @@ def test_gpu_vs_oracle_random(gpu_ctx, jt, dup, null_frac, phj):
     exp = O.hash_join(build, probe, [0], [0], side, idx, join_type=JT[jt], probe_batch_rows=[5000, 5000, 5000], batch_size=8192, **kw)
     got = gpu_hash_join(gpu_ctx, build, probe, [0], [0], side, idx, GJT[jt], phj=(kw["phj_threshold"], kw["phj_density"]), probe_batch_rows=5000)
     assert_cols_equal(got, exp, ordered=jt in ORDERED, what=f"{jt} dup={dup} nulls={null_frac} phj={phj}")
+
+
+@pytest.mark.parametrize("jt", ALL_TYPES)
+def test_gpu_join_filter_vs_oracle(gpu_ctx, jt):
+    # JoinFilter (residual predicate) on every join type: build.payload % 7 > probe.payload % 5 over duplicate-heavy keys
+    rng = np.random.default_rng(hash(("filter", jt)) % 2**32)
+    build, probe = random_tables(rng, 3000, 12000, 1500, 3, 0.05)
+    build[1] = (build[1][0] % 7, None); probe[1] = ((probe[1][0] % 5).astype(np.int64), None)
+    side, idx = out_mapping(jt, 2, 2)
+    onodes = [(O.E_COLUMN, 0, None, 0, 0), (O.E_COLUMN, 1, None, 0, 0), (O.E_BINARY, O.OP_GT, None, 0, 0)]
+    gnodes = [(D.EXPR_COLUMN, 0, 0, 0, 0, 0.0), (D.EXPR_COLUMN, 1, 0, 0, 0, 0.0), (D.EXPR_BINARY, D.OP_GT, 0, 0, 0, 0.0)]
+    exp = O.hash_join(build, probe, [0], [0], side, idx, join_type=JT[jt], filter=([0, 1], [1, 1], onodes), phj_threshold=0, phj_density=float("inf"))
+    got = gpu_hash_join(gpu_ctx, build, probe, [0], [0], side, idx, GJT[jt], phj=(0, float("inf")), probe_batch_rows=5000, filter=([0, 1], [1, 1], gnodes))
+    assert_cols_equal(got, exp, ordered=jt in ("Inner", "RightSemi", "RightAnti", "RightMark"), what=jt)
 
 
 def test_gpu_inner_exact_order_with_chains_multibatch_and_device_path(gpu_ctx):

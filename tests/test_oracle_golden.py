@@ -42,6 +42,19 @@ def kat_tables(case):
     return left, right, on_b, on_p, side, idx, exp
 
 
+def kat_filter(case, gpu=False):
+    """the shared JoinFilter of the *_with_filter tests: intermediate[0] > intermediate[1]"""
+    f = case.get("filter")
+    if not f:
+        return None
+    if gpu:
+        from datafusion_b200 import capi as D
+        nodes = [(D.EXPR_COLUMN, 0, 0, 0, 0, 0.0), (D.EXPR_COLUMN, 1, 0, 0, 0, 0.0), (D.EXPR_BINARY, D.OP_GT, 0, 0, 0, 0.0)]
+    else:
+        nodes = [(O.E_COLUMN, 0, None, 0, 0), (O.E_COLUMN, 1, None, 0, 0), (O.E_BINARY, O.OP_GT, None, 0, 0)]
+    return f["col_side"], f["col_index"], nodes
+
+
 # the reference's template: batch_size x perfect-hash on/off (exec.rs:2929-2962)
 MATRIX = list(itertools.product([8192, 10, 5, 2, 1], [True, False]))
 
@@ -52,7 +65,8 @@ def test_oracle_reproduces_reference_join_snapshots(case):
     for batch_size, phj in MATRIX:
         thr, dens = (819200, 0.0) if phj else (0, float("inf"))
         nl, nr = len(case["left"][0][1]), len(case["right"][0][1])
-        got = O.hash_join(left, right, on_b, on_p, side, idx, join_type=JT[case["join_type"]],
+        fkw = {"filter": kat_filter(case)} if case.get("filter") else {}
+        got = O.hash_join(left, right, on_b, on_p, side, idx, join_type=JT[case["join_type"]], **fkw,
                           null_equals_null=case["null_equality"] == "NullEqualsNull", batch_size=batch_size, phj_threshold=thr, phj_density=dens,
                           build_batch_rows=[nl] * case.get("left_repeat", 1), probe_batch_rows=[nr] * case.get("right_repeat", 1))
         assert_cols_equal(got, exp, ordered=not case["sorted"], what=f"{case['name']} bs={batch_size} phj={phj} ({case['ref']})")
@@ -62,7 +76,8 @@ def test_oracle_reproduces_reference_join_snapshots(case):
 def test_oracle_force_hash_collisions_is_output_invariant(case):
     # the reference's force_hash_collisions CI job (extended.yml:110-128): same results with every hash = 0
     left, right, on_b, on_p, side, idx, exp = kat_tables(case)
-    got = O.hash_join(left, right, on_b, on_p, side, idx, join_type=JT[case["join_type"]], phj_threshold=0, phj_density=float("inf"), force_collisions=True,
+    fkw = {"filter": kat_filter(case)} if case.get("filter") else {}
+    got = O.hash_join(left, right, on_b, on_p, side, idx, join_type=JT[case["join_type"]], phj_threshold=0, phj_density=float("inf"), force_collisions=True, **fkw,
                       null_equals_null=case["null_equality"] == "NullEqualsNull")
     assert_cols_equal(got, exp, ordered=not case["sorted"], what=case["name"])
 
