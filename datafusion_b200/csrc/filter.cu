@@ -649,7 +649,7 @@ static void filter_push(dfgpu_filter* f, const std::vector<DCol>& cols) {
   // ---- fused single-pass path: plain projected columns, no fetch limit ----
   bool fusable = f->fetch < 0 && f->projection.size() <= (size_t)kMaxFiltCols;
   for (int pc : f->projection) if (cols[pc].validity || cols[pc].type == DFGPU_BOOL) fusable = false;
-  static const int fused_enabled = getenv("DFGPU_FILTER_FUSED") ? atoi(getenv("DFGPU_FILTER_FUSED")) : 0;
+  static const int fused_enabled = getenv("DFGPU_FILTER_FUSED") ? atoi(getenv("DFGPU_FILTER_FUSED")) : 1;
   if (fusable && fused_enabled) {
     FilterCols fc;
     memset(&fc, 0, sizeof(fc));
