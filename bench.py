@@ -157,34 +157,41 @@ def main():
 
     from datafusion_b200 import capi as D
     dist = None
+    xmode = os.environ.get("DFGPU_EXCHANGE", "pipelined") if world > 1 else "none"
+    nb, npr = NB_PER_GPU, NP_PER_GPU
+    pj = px_b = px_p = None
     if world > 1:
         import torch
         import torch.distributed as dist_
+        from datafusion_b200 import exchange
         dist = dist_
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        tstream = torch.cuda.Stream()           # one explicit stream shared by torch (NCCL ordering) and libdfgpu
-        torch.cuda.set_stream(tstream)
-        ctx = D.Context(local, tstream.cuda_stream)
+        if xmode == "pipelined":
+            # exchange stream + join stream; persistent receive buffers mapped into every peer through CUDA IPC (25 % headroom)
+            pj = exchange.PartitionedHashJoin(local, dist, [D.INT64, D.INT64], [D.INT64, D.INT64], [0], [0], [0, 0, 1], [0, 1, 1],
+                                              int(nb * 1.25), int(npr * 1.25), n_chunks=int(os.environ.get("DFGPU_CHUNKS", "1")))
+            ctx = pj.ctx
+            torch.cuda.set_stream(pj.js)
+        else:
+            tstream = torch.cuda.Stream()           # one explicit stream shared by torch (NCCL ordering) and libdfgpu
+            torch.cuda.set_stream(tstream)
+            ctx = D.Context(local, tstream.cuda_stream)
+            if xmode == "peer":
+                px_b = exchange.PeerExchange(ctx, dist, [D.INT64, D.INT64], int(nb * 1.25))
+                px_p = exchange.PeerExchange(ctx, dist, [D.INT64, D.INT64], int(npr * 1.25))
     else:
         ctx = D.Context(local)
-    nb, npr = NB_PER_GPU, NP_PER_GPU
     bk, bp, pk, pp = make_inputs(ctx, D, rank, world, nb, npr)
     col = lambda buf, n: D.DeviceColumn(ctx, D.INT64, n, buf)
     build_cols, probe_cols = [col(bk, nb), col(bp, nb)], [col(pk, npr), col(pp, npr)]
 
-    px_b = px_p = None
-    if world > 1:
-        from datafusion_b200 import exchange
-        if os.environ.get("DFGPU_EXCHANGE", "peer") == "peer":
-            # persistent receive buffers, mapped into every peer through CUDA IPC (25 % headroom over the uniform share)
-            px_b = exchange.PeerExchange(ctx, dist, [D.INT64, D.INT64], int(nb * 1.25))
-            px_p = exchange.PeerExchange(ctx, dist, [D.INT64, D.INT64], int(npr * 1.25))
-
     def step():
         if world == 1:
             return join_step(ctx, D, build_cols, probe_cols)[0]
-        if px_b is not None:   # fused partition + exchange: rows are written straight into the owners' HBM over NVLink
+        if pj is not None:     # chunked peer scatter on the exchange stream overlapped with build/probe on the join stream
+            return pj.run(build_cols, probe_cols, keep_output=False)[0]
+        if px_b is not None:   # fused partition + exchange, then the join (no overlap)
             b2 = px_b.exchange(build_cols, [0])
             p2 = px_p.exchange(probe_cols, [0])
         else:                  # local partition + one NCCL all-to-all per column
@@ -204,7 +211,8 @@ def main():
     barrier()
     ctx.set_kernel_timing(True)
     ctx.kernel_time_reset()
-    launches0 = ctx.launches
+    all_launches = lambda: ctx.launches + (pj.ctx_x.launches if pj is not None else 0)
+    launches0 = all_launches()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -216,7 +224,7 @@ def main():
     ms = ctx.elapsed_ms(e0, e1)
     barrier()
     clk = clocks.stop() if rank == 0 else None
-    launches = ctx.launches - launches0
+    launches = all_launches() - launches0
     ctx.set_kernel_timing(False)
     if dist is not None:
         import torch
@@ -231,7 +239,8 @@ def main():
     line = None
     if rank == 0:
         peak, peak_src = peaks()
-        algo_bytes = 40.0 * npr                     # 16 B read + 24 B written per probe row
+        launches_per_step = max(probe_n, 1) / args.steps          # 1 at N=1; one per exchanged chunk in the pipelined N>1 path
+        algo_bytes = 40.0 * float(out_rows) / launches_per_step   # 16 B read + 24 B written per probe row
         k_ms = probe_ms / max(probe_n, 1)
         achieved = algo_bytes / (k_ms / 1000.0) / 1e9 if k_ms > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": "join_probe_inline_kernel<2>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -242,7 +251,9 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic (generated in HBM, counter-based)",
                 "config": {"workload": "C2 HashJoinExec inner 100M x 10M int64 per GPU, sparse unique build keys, 100% hit, output {k,pb,pp}",
                            "rows_per_step": (nb + npr) * world, "output_rows_per_gpu": int(out_rows), "l2": "inputs (1.76 GB/GPU) exceed L2; no flush",
-                           "exchange": ("fused hash partition + direct peer-memory scatter over NVLink (CUDA IPC), NCCL only for counts/barrier" if os.environ.get("DFGPU_EXCHANGE", "peer") == "peer" else "hash partition + one NCCL all-to-all per column") if world > 1 else "none (single GPU)"},
+                           "exchange": {"none": "none (single GPU)", "pipelined": "fused hash partition + peer-memory scatter over NVLink (CUDA IPC) in chunks on an exchange stream, overlapped with build/probe on the join stream; NCCL only for counts/barriers",
+                                        "peer": "fused hash partition + direct peer-memory scatter over NVLink (CUDA IPC), NCCL only for counts/barrier",
+                                        "nccl": "hash partition + one NCCL all-to-all per column"}.get(xmode, xmode)},
                 "clocks": clk, "gpu_launches": int(launches), "roofline": roofline}
 
     # ---- e2e through the C ABI with host (pinned) buffers (N = 1: the host leg has no exchange) ----

@@ -102,7 +102,8 @@ EXPORTS = [
     "dfgpu_agg_next", "dfgpu_agg_metric", "dfgpu_agg_destroy",
     "dfgpu_batch_num_rows", "dfgpu_batch_num_columns", "dfgpu_batch_column", "dfgpu_batch_is_host",
     "dfgpu_batch_export_arrow", "dfgpu_batch_release", "dfgpu_hash_partition_device",
-    "dfgpu_partition_plan_create", "dfgpu_partition_plan_scatter_peer", "dfgpu_partition_plan_destroy",
+    "dfgpu_partition_plan_create", "dfgpu_partition_plan_scatter_peer", "dfgpu_partition_plan_create_chunked",
+    "dfgpu_partition_plan_scatter_peer_chunk", "dfgpu_partition_plan_destroy",
     "dfgpu_ipc_export", "dfgpu_ipc_import", "dfgpu_ipc_close",
 ]
 
@@ -181,6 +182,8 @@ def load_library() -> C.CDLL:
     sig("dfgpu_hash_partition_device", C.c_int, [vp, P(Column), i32, P(i32), i32, i32, P(vp), P(i64)])
     sig("dfgpu_partition_plan_create", C.c_int, [vp, P(Column), i32, P(i32), i32, i32, P(i64), P(vp)])
     sig("dfgpu_partition_plan_scatter_peer", C.c_int, [vp, P(vp), P(i64)])
+    sig("dfgpu_partition_plan_create_chunked", C.c_int, [vp, P(Column), i32, P(i32), i32, i32, i32, P(i64), P(vp)])
+    sig("dfgpu_partition_plan_scatter_peer_chunk", C.c_int, [vp, i32, P(vp), P(i64)])
     sig("dfgpu_partition_plan_destroy", None, [vp])
     sig("dfgpu_ipc_export", C.c_int, [vp, vp, C.c_char_p])
     sig("dfgpu_ipc_import", C.c_int, [vp, C.c_char_p, P(vp)])
@@ -593,6 +596,14 @@ class AggHandle(_Operator):
     def push_device(self, cols): self._push("dfgpu_agg_push_device", cols)
     def push_arrow(self, rb): self._push_arrow("dfgpu_agg_push_arrow", rb)
     def finish(self): self.ctx.check(self.ctx.lib.dfgpu_agg_finish(self.h))
+
+
+def evaluate_device(ctx: Context, cols, n_rows: int, nodes) -> "Batch":
+    """PhysicalExpr::evaluate on device columns -> a one-column device batch"""
+    na = expr_nodes(nodes)
+    out = C.c_void_p()
+    ctx.check(ctx.lib.dfgpu_expr_evaluate_device(ctx.h, _cols(cols), len(cols), int(n_rows), na, len(nodes), C.byref(out)))
+    return Batch(ctx, out.value)
 
 
 def hash_partition_device(ctx: Context, cols, key_cols, n_parts: int):

@@ -144,10 +144,26 @@ __global__ void __launch_bounds__(256) join_minmax_kernel(KeyCols kc, int64_t n,
     if (sgn) { long long v = (long long)t; lmin_s = min(lmin_s, v); lmax_s = max(lmax_s, v); }
     else { lmin_u = min(lmin_u, (unsigned long long)t); lmax_u = max(lmax_u, (unsigned long long)t); }
   }
-  if (cnt) {
-    if (sgn) { atomicMin((long long*)&mm[0], lmin_s); atomicMax((long long*)&mm[1], lmax_s); }
-    else { atomicMin(&mm[0], lmin_u); atomicMax(&mm[1], lmax_u); }
-    atomicAdd(&mm[2], cnt);
+  // block-level reduction first: one atomic triple per block, not per thread (the same three addresses serialise in L2)
+  unsigned long long kmin = sgn ? (unsigned long long)lmin_s ^ (1ull << 63) : lmin_u;   // order-preserving map of signed keys onto unsigned
+  unsigned long long kmax = sgn ? (unsigned long long)lmax_s ^ (1ull << 63) : lmax_u;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, d));
+    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, d));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  }
+  __shared__ unsigned long long s_red[3][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_red[0][warp] = kmin; s_red[1][warp] = kmax; s_red[2][warp] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { kmin = min(kmin, s_red[0][w]); kmax = max(kmax, s_red[1][w]); cnt += s_red[2][w]; }
+    if (cnt) {
+      if (sgn) { atomicMin((long long*)&mm[0], (long long)(kmin ^ (1ull << 63))); atomicMax((long long*)&mm[1], (long long)(kmax ^ (1ull << 63))); }
+      else { atomicMin(&mm[0], kmin); atomicMax(&mm[1], kmax); }
+      atomicAdd(&mm[2], cnt);
+    }
   }
 }
 

@@ -53,17 +53,23 @@ __device__ __forceinline__ T block_reduce_sum(T v) {
   return r;  // valid in warp 0
 }
 
-// Device-wide exclusive scan of `n` uint64 tile sums, in place, by a single block (n is the
-// number of tiles: <= a few hundred thousand).  total written to *total_out.
+// Exclusive scan of `n` uint64 tile sums, in place, one block per row: block r scans sums[r*n .. (r+1)*n) and
+// writes that row's total to total_out[r] (a <<<1, NT>>> launch is the plain device-wide scan of n values).
 template <int NT>
 __global__ void scan_tiles_kernel(uint64_t* __restrict__ sums, int64_t n, uint64_t* __restrict__ total_out) {
+  constexpr int IPT = 8;   // consecutive items per thread and round: 8192 items per block-wide scan
+  sums += (int64_t)blockIdx.x * n;
+  total_out += blockIdx.x;
   uint64_t carry = 0;
-  for (int64_t base = 0; base < n; base += NT) {
-    int64_t i = base + threadIdx.x;
-    uint64_t v = i < n ? sums[i] : 0;
+  for (int64_t base = 0; base < n; base += (int64_t)NT * IPT) {
+    const int64_t i0 = base + (int64_t)threadIdx.x * IPT;
+    uint64_t v[IPT], sum = 0;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) { v[k] = i0 + k < n ? sums[i0 + k] : 0; sum += v[k]; }
     uint64_t tot;
-    uint64_t ex = block_exclusive_scan<NT, uint64_t>(v, &tot);
-    if (i < n) sums[i] = carry + ex;
+    uint64_t ex = carry + block_exclusive_scan<NT, uint64_t>(sum, &tot);
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) { if (i0 + k < n) sums[i0 + k] = ex; ex += v[k]; }
     carry += tot;
   }
   if (threadIdx.x == 0) *total_out = carry;

@@ -349,6 +349,13 @@ typedef struct dfgpu_partition_plan dfgpu_partition_plan;
 int dfgpu_partition_plan_create(dfgpu_ctx* ctx, const dfgpu_column* cols, int32_t n_cols, const int32_t* key_cols, int32_t n_keys,
                                 int32_t n_parts, int64_t* counts_host, dfgpu_partition_plan** out);
 int dfgpu_partition_plan_scatter_peer(dfgpu_partition_plan* plan, void* const* dst_bases, const int64_t* dst_row_offset);
+/* Chunked form, for overlapping the exchange with the consumer (RepartitionExec streams batches to HashJoinExec the
+ * same way, repartition/mod.rs:1320-1400): the input is cut into n_chunks contiguous row ranges, counts_host is
+ * [n_chunks][n_parts], and each chunk is scattered by its own call (dst_row_offset[p] = first row of this rank's
+ * (chunk, p) block at receiver p) so the receiver can start on chunk c while chunk c+1 is still on the wire. */
+int dfgpu_partition_plan_create_chunked(dfgpu_ctx* ctx, const dfgpu_column* cols, int32_t n_cols, const int32_t* key_cols, int32_t n_keys,
+                                        int32_t n_parts, int32_t n_chunks, int64_t* counts_host, dfgpu_partition_plan** out);
+int dfgpu_partition_plan_scatter_peer_chunk(dfgpu_partition_plan* plan, int32_t chunk, void* const* dst_bases, const int64_t* dst_row_offset);
 void dfgpu_partition_plan_destroy(dfgpu_partition_plan* plan);
 /* CUDA IPC: export a device allocation made with dfgpu_malloc (64-byte handle) / map a peer's allocation */
 int dfgpu_ipc_export(dfgpu_ctx* ctx, void* dev_ptr, uint8_t* handle_out);

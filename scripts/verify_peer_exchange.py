@@ -45,5 +45,18 @@ if rank == 0:
     exp = np.stack([hbk[bi], hbp[bi], hpp[pi]], axis=1)
     # per-rank sums mod 2^62 do not add linearly; compare the row count and a wrapping checksum instead
     print("global rows", int(cnt.item()), "oracle rows", len(exp), "rows_match", int(cnt.item()) == len(exp), flush=True)
+# pipelined partitioned join (chunked scatter overlapped with the probe): same multiset of rows as the unpipelined path
+pj = exchange.PartitionedHashJoin(local, dist, [D.INT64, D.INT64], [D.INT64, D.INT64], [0], [0], [0, 0, 1], [0, 1, 1], int(nb * 1.5), int(npr * 1.5), n_chunks=5)
+for rep in range(2):
+    rows, pouts = pj.run([col(bk, nb), col(bp, nb)], [col(pk, npr), col(pp, npr)])
+    pj.ctx.sync()
+    ploc = np.stack([np.concatenate([ctx.to_host(o.column(c).values, o.num_rows * 8).view(np.int64).copy() for o in pouts]) for c in range(3)], axis=1)
+    a_sorted = loc[np.lexsort(loc.T[::-1])]; b_sorted = ploc[np.lexsort(ploc.T[::-1])]
+    same = rows == len(loc) and np.array_equal(a_sorted, b_sorted)
+    # inside one chunk the probe-side order is source rank then source row: pp (col 2) must be increasing per chunk batch
+    mono = all(bool(np.all(np.diff(ctx.to_host(o.column(2).values, o.num_rows * 8).view(np.int64)) > 0)) for o in pouts if o.num_rows > 1)
+    ok &= same and mono
+    print(f"rank {rank} pipelined rep {rep}: rows={rows} batches={len(pouts)} same_multiset={same} per_chunk_order={mono}", flush=True)
+    for o in pouts: o.release()
 print(f"rank {rank} exchange_identical={ok}", flush=True)
 dist.barrier(); dist.destroy_process_group()

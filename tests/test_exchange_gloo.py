@@ -90,3 +90,30 @@ def test_plan_all_to_all_offsets():
     from datafusion_b200 import exchange
     sc, rc, so, ro = exchange.plan_all_to_all([3, 0, 5], [1, 2, 0])
     assert so.tolist() == [0, 3, 3, 8] and ro.tolist() == [0, 1, 3, 3]
+
+
+def test_peer_chunk_layout_is_a_disjoint_cover():
+    """layout of the chunked peer exchange: every (src, chunk, dst) block lands in its own range of the receiver's buffer,
+    the ranges tile [0, total) exactly, and chunk c of all sources is one contiguous slice (what the pipelined join consumes)"""
+    from datafusion_b200.exchange import peer_chunk_layout
+    rng = np.random.default_rng(3)
+    for world, chunks in ((2, 1), (2, 4), (8, 3), (5, 7)):
+        m = rng.integers(0, 50, size=(world, chunks, world))
+        m[rng.integers(0, world), rng.integers(0, chunks), :] = 0        # an empty block
+        layouts = [peer_chunk_layout(m, r) for r in range(world)]
+        for dst in range(world):
+            total = int(m[:, :, dst].sum())
+            owner = np.full(total, -1)
+            for src in range(world):
+                dst_row = layouts[src][0]
+                for c in range(chunks):
+                    lo = int(dst_row[c][dst]); hi = lo + int(m[src, c, dst])
+                    assert (owner[lo:hi] == -1).all()
+                    owner[lo:hi] = c * world + src
+            assert (owner >= 0).all()
+            assert (np.diff(owner) >= 0).all()                            # chunk-major, then source rank
+            _, start, rows, mx = layouts[dst]
+            for c in range(chunks):
+                assert rows[c] == m[:, c, dst].sum()
+                assert start[c] == m[:, :c, dst].sum()
+            assert mx == m.sum(axis=(0, 1)).max()

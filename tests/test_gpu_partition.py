@@ -18,7 +18,7 @@ def mix64(x):
     return x
 
 
-@pytest.mark.parametrize("n_parts", [2, 8, 5])
+@pytest.mark.parametrize("n_parts", [1, 2, 8, 5, 13, 32])
 def test_hash_partition_is_stable_and_complete(gpu_ctx, n_parts):
     rng = np.random.default_rng(n_parts)
     n = 100_007
@@ -58,3 +58,71 @@ def test_partitioned_join_equals_global_join(gpu_ctx):
     got = [(np.concatenate([o[c][0] for o in outs]), None) for c in range(4)]
     exp = O.hash_join([(bk, None), (bp, None)], [(pk, None), (pp, None)], [0], [0], [0, 0, 1, 1], [0, 1, 0, 1])
     assert_cols_equal(got, exp, ordered=False)
+
+
+@pytest.mark.parametrize("n_parts", [3, 8, 16])
+def test_hash_partition_int32_key_many_widths(gpu_ctx, n_parts):
+    # non-8-byte key (generic hash path) with 1/2/4/8-byte payload columns: same stable-order contract
+    rng = np.random.default_rng(40 + n_parts)
+    n = 70_001
+    k = rng.integers(0, 5000, n).astype(np.int32)
+    cols_np = [k, rng.integers(-100, 100, n).astype(np.int8), rng.integers(0, 60000, n).astype(np.uint16), rng.random(n).astype(np.float32),
+               np.arange(n, dtype=np.int64), rng.random(n)]
+    cols = [D.DeviceColumn.from_host(gpu_ctx, D.HostColumn(x)) for x in cols_np]
+    batch, offs = D.hash_partition_device(gpu_ctx, cols, [0], n_parts)
+    with np.errstate(over="ignore"):
+        h = mix64(k.astype(np.uint64) + SEED_EXCHANGE)
+    pid = np.array([(int(x) * n_parts) >> 64 for x in h], dtype=np.int64)
+    order = np.argsort(pid, kind="stable")
+    for i, x in enumerate(cols_np):
+        assert np.array_equal(batch.column_numpy(i)[0], x[order]), f"column {i}"
+    assert offs[-1] == n and [offs[p + 1] - offs[p] for p in range(n_parts)] == np.bincount(pid, minlength=n_parts).tolist()
+
+
+@pytest.mark.parametrize("n_parts,n_chunks", [(2, 1), (8, 4), (5, 7), (12, 3)])
+def test_chunked_peer_plan_scatters_every_chunk_to_its_block(gpu_ctx, n_parts, n_chunks):
+    """dfgpu_partition_plan_create_chunked / _scatter_peer_chunk with every "peer" buffer on this GPU: chunk c of
+    partition p must land, in input order, at the offset the caller passed — the contract PartitionedHashJoin's
+    receive layout (exchange.peer_chunk_layout) is built on."""
+    import ctypes as C
+    ctx = gpu_ctx
+    rng = np.random.default_rng(n_parts * 10 + n_chunks)
+    n = 50_000 + n_parts
+    k = rng.integers(-2**62, 2**62, n).astype(np.int64); v = np.arange(n, dtype=np.int64)
+    cols = [D.DeviceColumn.from_host(ctx, D.HostColumn(x)) for x in (k, v)]
+    counts = (C.c_int64 * (n_parts * n_chunks))()
+    plan = C.c_void_p()
+    ctx.check(ctx.lib.dfgpu_partition_plan_create_chunked(ctx.h, D._cols(cols), 2, D._i32arr([0]), 1, n_parts, n_chunks, counts, C.byref(plan)))
+    try:
+        cnt = np.array(list(counts), dtype=np.int64).reshape(n_chunks, n_parts)
+        with np.errstate(over="ignore"):
+            h = mix64(k.view(np.uint64) + SEED_EXCHANGE)
+        pid = np.array([(int(x) * n_parts) >> 64 for x in h], dtype=np.int64)
+        tile = 2048
+        ntiles = (n + tile - 1) // tile
+        bounds = [min(n, (ntiles * c // n_chunks) * tile) for c in range(n_chunks)] + [n]
+        for c in range(n_chunks):
+            assert cnt[c].tolist() == np.bincount(pid[bounds[c]:bounds[c + 1]], minlength=n_parts).tolist()
+        # one receive buffer per partition, chunk-major layout with a 3-row gap before every block
+        gap = 3
+        bufs = [[D.DeviceBuffer(ctx, (int(cnt[:, p].sum()) + gap * n_chunks + 1) * 8) for _ in range(2)] for p in range(n_parts)]
+        bases = (C.c_void_p * (n_parts * 2))(*[bufs[p][c].ptr for p in range(n_parts) for c in range(2)])
+        starts = np.zeros((n_chunks, n_parts), dtype=np.int64)
+        for p in range(n_parts):
+            run = 0
+            for c in range(n_chunks):
+                run += gap
+                starts[c, p] = run
+                run += cnt[c, p]
+        for c in reversed(range(n_chunks)):      # any order of chunk calls must work
+            rows = (C.c_int64 * n_parts)(*[int(x) for x in starts[c]])
+            ctx.check(ctx.lib.dfgpu_partition_plan_scatter_peer_chunk(plan, c, bases, rows))
+        ctx.sync()
+        for p in range(n_parts):
+            for c in range(n_chunks):
+                sel = np.nonzero(pid[bounds[c]:bounds[c + 1]] == p)[0] + bounds[c]
+                for ci, src in enumerate((k, v)):
+                    got = ctx.to_host(bufs[p][ci].ptr + int(starts[c, p]) * 8, len(sel) * 8).view(np.int64)
+                    assert np.array_equal(got, src[sel]), (p, c, ci)
+    finally:
+        ctx.lib.dfgpu_partition_plan_destroy(plan)
