@@ -243,8 +243,13 @@ def main():
         algo_bytes = 40.0 * float(out_rows) / launches_per_step   # 16 B read + 24 B written per probe row
         k_ms = probe_ms / max(probe_n, 1)
         achieved = algo_bytes / (k_ms / 1000.0) / 1e9 if k_ms > 0 else 0.0
-        roofline = {"bound": "hbm", "kernel": "join_probe_inline_kernel<2>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
+        # DRAM bytes per launch of the probe kernel from the ncu --set full capture of this workload (profiles/r1h_final_kernels.csv:
+        # dram__bytes_read.sum 12.94 GB + dram__bytes_write.sum 2.38 GB); only meaningful for the one-launch-per-step N=1 shape
+        traffic = 15.32e9 if world == 1 else None
+        roofline = {"bound": "hbm", "kernel": "join_probe_inline_v0_kernel<2>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1h_final_kernels.csv)",
+                    "traffic_note": "3.8x the algorithmic 4.0 GB: every probe row is one random 16 B table lookup that costs a 64 B DRAM fetch (+ L2 pair-sector fill); the kernel sits on the measured DRAM random-access rate, not on bytes (DESIGN.md §4)",
+                    "peak_source": peak_src, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
                     "algorithmic_bytes_per_launch": algo_bytes, "build_kernel_ms": build_ms / max(build_n, 1),
                     "whole_join_achieved_gbs": (16.0 * nb + 16.0 * npr + 24.0 * npr) / (ms_per_step / 1000.0) / 1e9 if world == 1 else None}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -293,8 +298,50 @@ def main():
         e2e_val = (nb + npr) * args.e2e_steps / (t1 - t0)
         line["e2e"] = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
                        "ms_per_step": 1000 * (t1 - t0) / args.e2e_steps, "timer": "host wall clock around the C-ABI calls (includes H2D, kernels, D2H)"}
+    elif pj is not None:
+        # N > 1: every rank uploads its shard from pinned host memory, runs the exchange + join, and downloads its output rows
+        # into pinned host memory; wall clock between barriers, max over ranks
+        import torch
+        hb = [ctx.pinned_empty(nb, np.int64), ctx.pinned_empty(nb, np.int64)]
+        hp = [ctx.pinned_empty(npr, np.int64), ctx.pinned_empty(npr, np.int64)]
+        for dst, src, n in ((hb[0], bk, nb), (hb[1], bp, nb), (hp[0], pk, npr), (hp[1], pp, npr)):
+            ctx.check(ctx.lib.dfgpu_memcpy_d2h(ctx.h, dst.ctypes.data_as(C.c_void_p), C.c_void_p(src.ptr), n * 8))
+        ctx.sync()
+        out_cap = int(npr * 1.25)
+        hout = [ctx.pinned_empty(out_cap, np.int64) for _ in range(3)]
+
+        def e2e_step_multi():
+            for dst, src, n in ((bk, hb[0], nb), (bp, hb[1], nb), (pk, hp[0], npr), (pp, hp[1], npr)):
+                ctx.check(ctx.lib.dfgpu_memcpy_h2d(ctx.h, C.c_void_p(dst.ptr), src.ctypes.data_as(C.c_void_p), n * 8))
+            ctx.sync()                                   # the exchange stream reads the inputs
+            rows, outs = pj.run(build_cols, probe_cols, keep_output=True)
+            off = 0
+            for o in outs:
+                if off + o.num_rows > out_cap:
+                    raise RuntimeError("e2e: output exceeds the pinned result buffers")
+                for c in range(3):
+                    ctx.check(ctx.lib.dfgpu_memcpy_d2h(ctx.h, C.c_void_p(hout[c].ctypes.data + off * 8), C.c_void_p(o.column(c).values), o.num_rows * 8))
+                off += o.num_rows
+            ctx.sync()
+            for o in outs:
+                o.release()
+            return rows
+
+        e2e_step_multi()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            rows = e2e_step_multi()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            secs = float(dt.item())
+            line["e2e"] = {"value": (nb + npr) * world * args.e2e_steps / secs, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": int(rows) * 24 * world,
+                           "steps": args.e2e_steps, "ms_per_step": 1000 * secs / args.e2e_steps,
+                           "timer": "host wall clock between barriers, max over ranks; per rank: H2D of its shard from pinned memory -> exchange + join -> D2H of its output rows (no H2D/D2H overlap at N>1 yet)"}
     elif rank == 0:
-        line["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": None, "note": "host leg measured at N=1 only"}
+        line["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": None, "note": "host leg is measured in the default (pipelined) exchange mode only"}
 
     if rank == 0 and world == 1 and not args.no_extra:
         # ---- other BASELINE configs, device resident (context for the headline; not part of `value`) ----
