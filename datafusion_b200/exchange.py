@@ -346,9 +346,87 @@ class PartitionedHashJoin:
             cols.append(c)
         return cols
 
+    # -- streaming form: build once, then any number of probe batches (each call is collective) ----------------
+    def build(self, build_cols):
+        """exchange the build side and build this rank's table (collect_left_input of the partitioned join)"""
+        torch, world = self.torch, self.world
+        assert getattr(self, "_join", None) is None, "PartitionedHashJoin: build() called twice without finish()"
+        plan = None
+        try:
+            with torch.cuda.stream(self.xs):
+                plan, cnt, _ = self._plan(build_cols, self.on_build, 1)
+                allc = torch.empty(world * world, dtype=torch.int64, device=self.dev)
+                self.dist.all_gather_into_tensor(allc, torch.from_numpy(cnt.reshape(-1)).to(self.dev))
+                m = allc.view(world, 1, world).cpu().numpy()
+                row, start, rows, mx = peer_chunk_layout(m, self.rank)
+                if mx > self.px_b.cap:
+                    raise RuntimeError(f"PartitionedHashJoin: build receive buffer would overflow ({mx} rows > capacity {self.px_b.cap})")
+                self._scatter(plan, self.px_b, 0, row[0])
+                self.dist.all_reduce(self._flag)
+                ev = torch.cuda.Event(); ev.record(self.xs)
+            self._join = D.HashJoinHandle(self.ctx, self.build_types, self.probe_types, self.on_build, self.on_probe, self.out_side, self.out_index, **self.join_kwargs)
+            self.js.wait_event(ev)
+            self._join.push_build_device(self._slice(self.px_b, start[0], rows[0]))
+            self._join.finish_build()
+            self.xs.synchronize()
+        finally:
+            if plan is not None:
+                self.ctx_x.lib.dfgpu_partition_plan_destroy(plan)
+
+    def probe(self, probe_cols, n_chunks: int = None, keep_output: bool = True):
+        """exchange one probe batch (in n_chunks pieces, scatter of piece c+1 overlapping the probe of piece c) and probe
+        it; returns the device output batches.  Host-synchronous: the batch is fully consumed when the call returns."""
+        torch, world = self.torch, self.world
+        C = int(n_chunks or self.n_chunks)
+        j = self._join
+        plan, outs = None, []
+        try:
+            with torch.cuda.stream(self.xs):
+                plan, cnt, _ = self._plan(probe_cols, self.on_probe, C)
+                allc = torch.empty(world * C * world, dtype=torch.int64, device=self.dev)
+                self.dist.all_gather_into_tensor(allc, torch.from_numpy(cnt.reshape(-1)).to(self.dev))   # also: the receive buffers are free again
+                m = allc.view(world, C, world).cpu().numpy()
+                row, start, rows, mx = peer_chunk_layout(m, self.rank)
+                if mx > self.px_p.cap:
+                    raise RuntimeError(f"PartitionedHashJoin: probe receive buffer would overflow ({mx} rows > capacity {self.px_p.cap})")
+                evs = []
+                for c in range(C):
+                    self._scatter(plan, self.px_p, c, row[c])
+                    self.dist.all_reduce(self._flag)
+                    e = torch.cuda.Event(); e.record(self.xs); evs.append(e)
+            for c in range(C):
+                self.js.wait_event(evs[c])
+                j.push_probe_device(self._slice(self.px_p, start[c], rows[c]))
+                got = j.drain(host=False)
+                if keep_output:
+                    outs += got
+                else:
+                    for b in got:
+                        b.release()
+            self.xs.synchronize()
+            return outs
+        finally:
+            if plan is not None:
+                self.ctx_x.lib.dfgpu_partition_plan_destroy(plan)
+
+    def finish(self, keep_output: bool = True):
+        """ExhaustedProbeSide: final (unmatched build) rows for outer joins; closes the join.  Returns (output_rows, batches)."""
+        j = self._join
+        try:
+            j.finish_probe()
+            tail = j.drain(host=False)
+            if not keep_output:
+                for b in tail:
+                    b.release()
+                tail = []
+            return j.metric("output_rows"), tail
+        finally:
+            j.close()
+            self._join = None
+
     def run(self, build_cols, probe_cols, keep_output: bool = True):
-        """build_cols / probe_cols: this rank's device-resident input columns (complete before the call).  Returns
-        (output_rows, [device batches])."""
+        """build_cols / probe_cols: this rank's device-resident input columns (complete before the call).  One fused
+        step: both sides' counts travel in ONE collective.  Returns (output_rows, [device batches])."""
         torch, world, C = self.torch, self.world, self.n_chunks
         plans = []
         try:

@@ -58,5 +58,22 @@ for rep in range(2):
     ok &= same and mono
     print(f"rank {rank} pipelined rep {rep}: rows={rows} batches={len(pouts)} same_multiset={same} per_chunk_order={mono}", flush=True)
     for o in pouts: o.release()
+# streaming form: build once, three probe batches, finish — same multiset again
+def view(buf, lo, hi):
+    c = D.Column()
+    c.type, c.flags, c.length, c.offset, c.null_count, c.values, c.validity = D.INT64, 0, hi - lo, 0, 0, buf.ptr + lo * 8, None
+    return c
+pj.build([col(bk, nb), col(bp, nb)])
+souts = []
+cuts = [0, npr // 3, npr // 3 + 17, npr]
+for lo, hi in zip(cuts[:-1], cuts[1:]):
+    souts += pj.probe([view(pk, lo, hi), view(pp, lo, hi)], n_chunks=2)
+rows2, tail = pj.finish()
+pj.ctx.sync()
+sloc = np.stack([np.concatenate([ctx.to_host(o.column(c).values, o.num_rows * 8).view(np.int64).copy() for o in souts + tail]) for c in range(3)], axis=1)
+same = rows2 == len(loc) and np.array_equal(loc[np.lexsort(loc.T[::-1])], sloc[np.lexsort(sloc.T[::-1])])
+ok &= same
+print(f"rank {rank} streaming build/probe x3/finish: rows={rows2} same_multiset={same}", flush=True)
+for o in souts + tail: o.release()
 print(f"rank {rank} exchange_identical={ok}", flush=True)
 dist.barrier(); dist.destroy_process_group()
