@@ -154,6 +154,8 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if world == 1:
+        args.e2e_steps = max(args.e2e_steps, 1)     # the single-GPU line always carries the host leg
 
     from datafusion_b200 import capi as D
     dist = None
@@ -360,9 +362,12 @@ def main():
             return rows
 
         e2e_err = None if setup_ok else (setup_err or "pinned host allocation failed on another rank")
+        rows = 0
         try:
             if not setup_ok:
                 raise RuntimeError(e2e_err)
+            if args.e2e_steps <= 0:
+                raise RuntimeError("--e2e-steps 0: host leg skipped")
             e2e_step_multi()
             barrier()
             t0 = time.perf_counter()
