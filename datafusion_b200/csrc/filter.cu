@@ -168,11 +168,14 @@ __device__ __forceinline__ void eval_binary(const ENode& nd, uint64_t a, bool av
     case DFGPU_OP_BITAND: z = a & b; break;
     case DFGPU_OP_BITOR: z = a | b; break;
     case DFGPU_OP_BITXOR: z = a ^ b; break;
-    case DFGPU_OP_SHIFT_LEFT: { int w = type_width(nd.out_type) * 8; z = (b < (uint64_t)w) ? (a << b) : 0; break; }
+    // arrow's bitwise_shift_left / _right are `wrapping_shl` / `wrapping_shr`: the shift amount is taken modulo the bit width
+    // (binary.rs bitwise_shift_array_overflow_test: 2 << 100 = 32 for Int32), sign-propagating for signed types
+    case DFGPU_OP_SHIFT_LEFT: { const int w = type_width(nd.out_type) * 8; z = a << (b & (uint64_t)(w - 1)); break; }
     case DFGPU_OP_SHIFT_RIGHT: {
-      int w = type_width(nd.out_type) * 8;
-      if (c == C_I64) z = (b < (uint64_t)w) ? (uint64_t)((long long)a >> b) : (uint64_t)((long long)a >> 63);
-      else z = (b < (uint64_t)w) ? (a >> b) : 0;
+      const int w = type_width(nd.out_type) * 8;
+      const uint64_t sh = b & (uint64_t)(w - 1);
+      if (c == C_I64) z = (uint64_t)((long long)a >> sh);
+      else z = a >> sh;
       break;
     }
   }

@@ -356,8 +356,11 @@ def eval_expr(cols: Sequence[Col], nodes: Sequence[tuple], col_dtypes: Optional[
                         elif a == OP_BITAND: r = lv & rv
                         elif a == OP_BITOR: r = lv | rv
                         elif a == OP_BITXOR: r = lv ^ rv
-                        elif a == OP_SHIFT_LEFT: r = np.where(rv.astype(np.uint64) < dtp.itemsize * 8, lv << (rv % (dtp.itemsize * 8)), 0).astype(dtp)
-                        elif a == OP_SHIFT_RIGHT: r = np.where(rv.astype(np.uint64) < dtp.itemsize * 8, lv >> (rv % (dtp.itemsize * 8)), lv >> (dtp.itemsize * 8 - 1) if dtp.kind == "i" else 0).astype(dtp)
+                        elif a in (OP_SHIFT_LEFT, OP_SHIFT_RIGHT):
+                            # arrow-arith bitwise_shift_left/right = wrapping_shl / wrapping_shr: shift amount modulo the bit
+                            # width (binary.rs:5073 bitwise_shift_array_overflow_test: 2 << 100 = 32 for Int32)
+                            sh = (rv.astype(np.int64) & (dtp.itemsize * 8 - 1)).astype(dtp)
+                            r = ((lv << sh) if a == OP_SHIFT_LEFT else (lv >> sh)).astype(dtp)
                         else: raise ValueError(a)
                 if both is not None:
                     r = np.where(both, r, np.zeros((), r.dtype))

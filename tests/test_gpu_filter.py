@@ -66,6 +66,42 @@ def test_gpu_expression_kats(gpu_ctx):
         assert got == k[key], key
 
 
+from test_oracle_golden import EXPR_KAT, as_py, expr_kat_expected, expr_kat_inputs
+
+_GOPS = {"eq": D.OP_EQ, "neq": D.OP_NEQ, "lt": D.OP_LT, "lteq": D.OP_LTEQ, "gt": D.OP_GT, "gteq": D.OP_GTEQ, "plus": D.OP_PLUS, "minus": D.OP_MINUS,
+         "multiply": D.OP_MULTIPLY, "divide": D.OP_DIVIDE, "modulo": D.OP_MODULO, "and": D.OP_AND, "or": D.OP_OR, "is_distinct_from": D.OP_IS_DISTINCT_FROM,
+         "is_not_distinct_from": D.OP_IS_NOT_DISTINCT_FROM, "bitand": D.OP_BITAND, "bitor": D.OP_BITOR, "bitxor": D.OP_BITXOR,
+         "shift_left": D.OP_SHIFT_LEFT, "shift_right": D.OP_SHIFT_RIGHT}
+_GT = {"int32": D.INT32, "uint32": D.UINT32, "int64": D.INT64, "float64": D.FLOAT64, "bool": D.BOOL}
+
+
+@pytest.mark.parametrize("case", EXPR_KAT, ids=[c["name"] for c in EXPR_KAT])
+def test_gpu_reproduces_reference_binary_expr_tests(gpu_ctx, case):
+    """the reference's own BinaryExpr known-answer tests (binary.rs test module), through dfgpu_expr_evaluate_host"""
+    import ctypes as CT
+    cols = expr_kat_inputs(case)
+    keep = [D.HostColumn(v, val) for v, val in cols]
+    arr = (D.Column * len(cols))(*[k.c() for k in keep])
+    nodes = []
+    for item in case["rpn"]:
+        if item[0] == "col":
+            nodes.append((D.EXPR_COLUMN, item[1], 0, 0, 0, 0.0))
+        elif item[0] == "lit":
+            nodes.append((D.EXPR_LITERAL, 0, _GT[item[1]], 0, item[2], 0.0))
+        else:
+            nodes.append((D.EXPR_BINARY, _GOPS[item[1]], 0, 0, 0, 0.0))
+    na = D.expr_nodes(nodes)
+    out = CT.c_void_p()
+    rc = gpu_ctx.lib.dfgpu_expr_evaluate_host(gpu_ctx.h, arr, len(cols), len(cols[0][0]), na, len(nodes), CT.byref(out))
+    if "error" in case:
+        assert rc != 0 and case["error"].lower() in gpu_ctx.last_error().lower()
+        return
+    gpu_ctx.check(rc)
+    b = D.Batch(gpu_ctx, out.value)
+    assert b.column(0).type == _GT[case["expected"]["type"]], case["name"]
+    assert as_py(b.column_numpy(0), case["expected"]["type"]) == expr_kat_expected(case), f"{case['name']} ({case['ref']})"
+
+
 EXPRS = {
     "i64 > lit": (B(D.OP_GT, C(0), L(1 << 31, np.int64)), True),
     "(a > c) AND (b < 5 OR b IS NULL)": (B(D.OP_AND, B(D.OP_GT, C(0), L(1 << 30, np.int64)), B(D.OP_OR, B(D.OP_LT, C(1), L(5, np.int32)), U(D.EXPR_IS_NULL, C(1)))), True),

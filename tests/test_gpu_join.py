@@ -26,15 +26,19 @@ def test_gpu_matches_reference_join_snapshots(gpu_ctx, case):
     for batch_size, phj in MATRIX:
         thr, dens = (819200, 0.0) if phj else (0, float("inf"))
         nl, nr = len(case["left"][0][1]), len(case["right"][0][1])
+        tmap = {"date32": D.DATE32}
+        bt = [tmap.get(case.get("types", {}).get(n), D.INT32) for n, _ in case["left"]]
+        pt = [tmap.get(case.get("types", {}).get(n), D.INT32) for n, _ in case["right"]]
         got, h = gpu_hash_join(gpu_ctx, left, right, on_b, on_p, side, idx, GJT[case["join_type"]],
                                D.NULL_EQUALS_NULL if case["null_equality"] == "NullEqualsNull" else D.NULL_EQUALS_NOTHING,
                                batch_size=batch_size, phj=(thr, dens), probe_batch_rows=min(batch_size, nr), build_batch_rows=nl, return_handle=True,
-                               filter=kat_filter(case, gpu=True))
+                               filter=kat_filter(case, gpu=True), build_types=bt, probe_types=pt)
         ordered = (not case["sorted"]) and case["join_type"] in ORDERED
         assert_cols_equal(got, exp, ordered=ordered, what=f"{case['name']} bs={batch_size} phj={phj} ({case['ref']})")
-        # assert_phj_used (exec.rs: array_map_created_count metric)
-        if len(on_b) == 1 and len(left[0][0]) > 0:
-            assert h.metric("array_map_created_count") == (1 if phj else 0)
+        # assert_phj_used (exec.rs: array_map_created_count metric); "phj_expected": false = the reference asserts it is NOT used
+        want = case.get("phj_expected", "config")
+        if want is not None and len(on_b) == 1 and len(left[0][0]) > 0 and "types" not in case:
+            assert h.metric("array_map_created_count") == (1 if (phj and want == "config") else 0), case["name"]
         h.close()
 
 

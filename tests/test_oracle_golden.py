@@ -10,7 +10,7 @@ from harness import assert_cols_equal, col_from_list, load_golden
 
 JT = {"Inner": O.J_INNER, "Left": O.J_LEFT, "Right": O.J_RIGHT, "Full": O.J_FULL, "LeftSemi": O.J_LEFT_SEMI, "RightSemi": O.J_RIGHT_SEMI,
       "LeftAnti": O.J_LEFT_ANTI, "RightAnti": O.J_RIGHT_ANTI, "LeftMark": O.J_LEFT_MARK, "RightMark": O.J_RIGHT_MARK}
-KAT = load_golden("hash_join_kat.json")["cases"]
+KAT = load_golden("hash_join_kat.json")["cases"] + load_golden("hash_join_kat_extra.json")["cases"]
 MISC = load_golden("misc_kat.json")
 
 
@@ -43,15 +43,33 @@ def kat_tables(case):
 
 
 def kat_filter(case, gpu=False):
-    """the shared JoinFilter of the *_with_filter tests: intermediate[0] > intermediate[1]"""
+    """JoinFilter of a fixture: the shared `intermediate[0] > intermediate[1]` of the *_with_filter tests
+    (prepare_join_filter, exec.rs:5556-5583), or the post-order program in filter["rpn"] (semi / anti filter tests)."""
     f = case.get("filter")
     if not f:
         return None
+    rpn = f.get("rpn") or [["col", 0], ["col", 1], ["op", "gt"]]
     if gpu:
         from datafusion_b200 import capi as D
-        nodes = [(D.EXPR_COLUMN, 0, 0, 0, 0, 0.0), (D.EXPR_COLUMN, 1, 0, 0, 0, 0.0), (D.EXPR_BINARY, D.OP_GT, 0, 0, 0, 0.0)]
+        ops = {"gt": D.OP_GT, "neq": D.OP_NEQ, "eq": D.OP_EQ, "lt": D.OP_LT}
+        nodes = []
+        for kind, v in rpn:
+            if kind == "col":
+                nodes.append((D.EXPR_COLUMN, v, 0, 0, 0, 0.0))
+            elif kind == "lit_i32":
+                nodes.append((D.EXPR_LITERAL, 0, D.INT32, 0, v, 0.0))
+            else:
+                nodes.append((D.EXPR_BINARY, ops[v], 0, 0, 0, 0.0))
     else:
-        nodes = [(O.E_COLUMN, 0, None, 0, 0), (O.E_COLUMN, 1, None, 0, 0), (O.E_BINARY, O.OP_GT, None, 0, 0)]
+        ops = {"gt": O.OP_GT, "neq": O.OP_NEQ, "eq": O.OP_EQ, "lt": O.OP_LT}
+        nodes = []
+        for kind, v in rpn:
+            if kind == "col":
+                nodes.append((O.E_COLUMN, v, None, 0, 0))
+            elif kind == "lit_i32":
+                nodes.append((O.E_LITERAL, 0, np.int32, 0, v))
+            else:
+                nodes.append((O.E_BINARY, ops[v], None, 0, 0))
     return f["col_side"], f["col_index"], nodes
 
 
@@ -68,8 +86,14 @@ def test_oracle_reproduces_reference_join_snapshots(case):
         fkw = {"filter": kat_filter(case)} if case.get("filter") else {}
         got = O.hash_join(left, right, on_b, on_p, side, idx, join_type=JT[case["join_type"]], **fkw,
                           null_equals_null=case["null_equality"] == "NullEqualsNull", batch_size=batch_size, phj_threshold=thr, phj_density=dens,
-                          build_batch_rows=[nl] * case.get("left_repeat", 1), probe_batch_rows=[nr] * case.get("right_repeat", 1))
+                          build_batch_rows=[nl] * case.get("left_repeat", 1), probe_batch_rows=[nr] * case.get("right_repeat", 1) if nr else None)
         assert_cols_equal(got, exp, ordered=not case["sorted"], what=f"{case['name']} bs={batch_size} phj={phj} ({case['ref']})")
+        # assert_phj_used(&metrics, use_perfect_hash_join_as_possible): the ArrayMap rule of try_create_array_map (exec.rs:111-191)
+        want = case.get("phj_expected", "config")
+        if want is not None and len(on_b) == 1 and nl > 0 and "types" not in case:
+            _, _, _, used = O.hash_join_indices([left[on_b[0]]], [right[on_p[0]]], null_equals_null=case["null_equality"] == "NullEqualsNull",
+                                                phj_threshold=thr, phj_density=dens)
+            assert bool(used) == bool(phj and want == "config"), f"{case['name']}: array map used={used}"
 
 
 @pytest.mark.parametrize("case", KAT, ids=[c["name"] for c in KAT])
@@ -186,6 +210,48 @@ def test_oracle_expressions_kat():
     with pytest.raises(O.ArrowDivideByZero):
         O.eval_expr([(np.array([1, 2], np.int64), None), (np.array([1, 0], np.int64), None)],
                     [(O.E_COLUMN, 0, None, 0, 0), (O.E_COLUMN, 1, None, 0, 0), (O.E_BINARY, O.OP_DIVIDE, None, 0, 0)])
+
+
+EXPR_KAT = load_golden("expr_kat.json")["cases"]
+_NP = {"int32": np.int32, "uint32": np.uint32, "int64": np.int64, "float64": np.float64, "bool": bool}
+_OPS = {"eq": O.OP_EQ, "neq": O.OP_NEQ, "lt": O.OP_LT, "lteq": O.OP_LTEQ, "gt": O.OP_GT, "gteq": O.OP_GTEQ, "plus": O.OP_PLUS, "minus": O.OP_MINUS,
+        "multiply": O.OP_MULTIPLY, "divide": O.OP_DIVIDE, "modulo": O.OP_MODULO, "and": O.OP_AND, "or": O.OP_OR, "is_distinct_from": O.OP_IS_DISTINCT_FROM,
+        "is_not_distinct_from": O.OP_IS_NOT_DISTINCT_FROM, "bitand": O.OP_BITAND, "bitor": O.OP_BITOR, "bitxor": O.OP_BITXOR,
+        "shift_left": O.OP_SHIFT_LEFT, "shift_right": O.OP_SHIFT_RIGHT}
+
+
+def expr_kat_inputs(case):
+    return [col_from_list(c["values"], _NP[c["type"]]) for c in case["cols"]]
+
+
+def expr_kat_expected(case):
+    e = case["expected"]
+    return [None if v is None else (bool(v) if e["type"] == "bool" else v) for v in e["values"]]
+
+
+def as_py(col, type_name):
+    v, val = col
+    return [None if (val is not None and not val[i]) else (bool(v[i]) if type_name == "bool" else v[i].item()) for i in range(len(v))]
+
+
+@pytest.mark.parametrize("case", EXPR_KAT, ids=[c["name"] for c in EXPR_KAT])
+def test_oracle_reproduces_reference_binary_expr_tests(case):
+    cols = expr_kat_inputs(case)
+    nodes = []
+    for item in case["rpn"]:
+        if item[0] == "col":
+            nodes.append((O.E_COLUMN, item[1], None, 0, 0))
+        elif item[0] == "lit":
+            nodes.append((O.E_LITERAL, 0, _NP[item[1]], 0, item[2]))
+        else:
+            nodes.append((O.E_BINARY, _OPS[item[1]], None, 0, 0))
+    if "error" in case:
+        with pytest.raises(O.ArrowDivideByZero):
+            O.eval_expr(cols, nodes)
+        return
+    got = O.eval_expr(cols, nodes)
+    assert np.asarray(got[0]).dtype == np.dtype(_NP[case["expected"]["type"]]), case["name"]
+    assert as_py(got, case["expected"]["type"]) == expr_kat_expected(case), f"{case['name']} ({case['ref']})"
 
 
 # ---- independent cross-check: pyarrow.acero ------------------------------------------------
