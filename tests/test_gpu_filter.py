@@ -94,7 +94,7 @@ def test_gpu_reproduces_reference_binary_expr_tests(gpu_ctx, case):
     out = CT.c_void_p()
     rc = gpu_ctx.lib.dfgpu_expr_evaluate_host(gpu_ctx.h, arr, len(cols), len(cols[0][0]), na, len(nodes), CT.byref(out))
     if "error" in case:
-        assert rc != 0 and case["error"].lower() in gpu_ctx.last_error().lower()
+        assert rc < 0 and case["error"].lower() in gpu_ctx.lib.dfgpu_last_error(gpu_ctx.h).decode().lower()
         return
     gpu_ctx.check(rc)
     b = D.Batch(gpu_ctx, out.value)
