@@ -146,3 +146,29 @@ def test_gpu_large_groupby_properties(gpu_ctx):
     mine = int(gk.view(np.uint64).sum(dtype=np.uint64) * np.uint64(3) + gs.view(np.uint64).sum(dtype=np.uint64) * np.uint64(5) + gc.view(np.uint64).sum(dtype=np.uint64) * np.uint64(7))
     assert groups == g and mine % 2**64 == chk
     a.close()
+
+
+def test_gpu_single_aggregate_planning_kat(gpu_ctx):
+    m = MISC["single_aggregate_planning"]
+    got = gpu_group_by(gpu_ctx, [(np.array(m["a_u32"], np.uint32), None), (np.array(m["b_f64"], np.float64), None)], [0], [(D.AGG_SUM, 1, -1)], batch_rows=2)
+    o = np.argsort(got[0][0])
+    assert got[0][0][o].tolist() == m["expected"]["a"] and got[1][0][o].tolist() == m["expected"]["sum"]
+
+
+@pytest.mark.parametrize("name", ["skip_aggregation_after_first_batch", "skip_aggregation_after_threshold"])
+def test_gpu_final_accepts_the_references_skip_aggregation_states(gpu_ctx, name):
+    """aggregates/mod.rs:5431-5603: the reference's Partial may pass rows through unaggregated; GPU Final over exactly those
+    states == GPU Single over the raw rows == the reference's final counts."""
+    m = MISC[name]
+    key = np.concatenate([np.array(b["key"], np.int32) for b in m["batches"]]); val = np.concatenate([np.array(b["val"], np.int32) for b in m["batches"]])
+    single = gpu_group_by(gpu_ctx, [(key, None), (val, None)], [0], [(D.AGG_COUNT, 1, -1)], batch_rows=3)
+    rp = m["reference_partial"]
+    final = gpu_group_by(gpu_ctx, [(np.array(rp["key"], np.int32), None), (np.array(rp["count"], np.int64), None)], [0], [(D.AGG_COUNT, -1, -1)], mode=D.AGG_FINAL)
+    for got in (single, final):
+        o = np.argsort(got[0][0])
+        assert got[0][0][o].tolist() == m["final"]["key"] and got[1][0][o].tolist() == m["final"]["count"]
+    # and our own Partial states (always aggregated) merge to the same result
+    part = gpu_group_by(gpu_ctx, [(key, None), (val, None)], [0], [(D.AGG_COUNT, 1, -1)], mode=D.AGG_PARTIAL, batch_rows=3)
+    fin2 = gpu_group_by(gpu_ctx, part, [0], [(D.AGG_COUNT, -1, -1)], mode=D.AGG_FINAL)
+    o = np.argsort(fin2[0][0])
+    assert fin2[0][0][o].tolist() == m["final"]["key"] and fin2[1][0][o].tolist() == m["final"]["count"]

@@ -310,3 +310,26 @@ def test_oracle_all_null_build_keys(jt):
     for phj in (True, False):
         got = O.hash_join(left, right, [1], [1], side, idx, join_type=JT[jt], phj_threshold=819200 if phj else 0, phj_density=0.0 if phj else float("inf"))
         assert_cols_equal(got, expected_cols(m["expected_sorted"][jt], side), ordered=False, what=f"{jt} ({m['ref']})")
+
+
+def test_oracle_single_aggregate_planning_kat():
+    m = MISC["single_aggregate_planning"]
+    keys, res = O.group_by([(np.array(m["a_u32"], np.uint32), None)], [(O.A_SUM, (np.array(m["b_f64"], np.float64), None), None)], batch_size=2)
+    s = O.agg_output_columns(O.A_SUM, res[0], np.float64, False)[0][0]
+    o = np.argsort(keys[0][0])
+    assert keys[0][0][o].tolist() == m["expected"]["a"] and s[o].tolist() == m["expected"]["sum"]
+
+
+@pytest.mark.parametrize("name", ["skip_aggregation_after_first_batch", "skip_aggregation_after_threshold"])
+def test_oracle_final_accepts_the_references_skip_aggregation_states(name):
+    """The reference's Partial stream may stop aggregating and pass rows through as single-row states
+    (skip_partial_aggregation_probe_*; aggregates/mod.rs:5431-5603).  Whatever it emitted, Final over those states must equal
+    Single over the raw input — the contract that lets a GPU Partial (which always aggregates) feed a CPU Final and vice versa."""
+    m = MISC[name]
+    key = np.concatenate([np.array(b["key"], np.int32) for b in m["batches"]]); val = np.concatenate([np.array(b["val"], np.int32) for b in m["batches"]])
+    sk, sres = O.group_by([(key, None)], [(O.A_COUNT, (val, None), None)])
+    rp = m["reference_partial"]
+    fk, fres = O.group_by([(np.array(rp["key"], np.int32), None)], [(O.A_COUNT, (np.array(rp["count"], np.int64), None), None)], merge=True)
+    for keys, res in ((sk, sres), (fk, fres)):
+        o = np.argsort(keys[0][0])
+        assert keys[0][0][o].tolist() == m["final"]["key"] and res[0]["c"][o].tolist() == m["final"]["count"]
