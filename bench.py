@@ -453,6 +453,31 @@ def main():
         extra["C1_shape_filter_100M_rows_sel20"] = {"ms_per_step": ms_f, "rows_per_s": fn / ms_f * 1e3, "kept": int(kept),
                                                    "achieved_gbs": fbytes / ms_f / 1e6, "frac_of_hbm_peak": fbytes / ms_f / 1e6 / peak}
         fx.free(); fy.free()
+        # C4: TPC-H Q3-shaped pipeline at SF100, device resident, operator by operator through the C ABI (scripts/q3_device_pipeline.py)
+        try:
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
+            import q3_device_pipeline as Q
+            sf = float(os.environ.get("DFGPU_Q3_SF", "100"))
+            cu, orr, li = Q.gen_tables(ctx, sf)
+            for _ in range(2):
+                res, st = Q.run_q3(ctx, cu, orr, li)
+                for b in res:
+                    b.release()
+            e0, e1 = ctx.event(), ctx.event()
+            ctx.record(e0)
+            for _ in range(3):
+                res, st = Q.run_q3(ctx, cu, orr, li)
+                for b in res:
+                    b.release()
+            ctx.record(e1)
+            ms_q = ctx.elapsed_ms(e0, e1) / 3
+            in_rows = cu.rows + orr.rows + li.rows
+            q_bytes = 9.0 * cu.rows + 24.0 * orr.rows + 28.0 * li.rows            # every input column once
+            extra["C4_tpch_q3_pipeline_device_resident"] = {"scale_factor": sf, "ms_per_step": ms_q, "rows_per_s": in_rows / ms_q * 1e3, "input_rows": in_rows, "stages": st,
+                                                            "achieved_gbs": q_bytes / ms_q / 1e6, "frac_of_hbm_peak": q_bytes / ms_q / 1e6 / peak,
+                                                            "note": "filter x3 -> RightSemi join -> Inner join -> projection -> 3-key group-by SUM; int64 fixed-point money; synthetic TPC-H-shaped tables generated in HBM"}
+        except Exception as exc:
+            extra["C4_tpch_q3_pipeline_device_resident"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         line["extra"] = extra
 
     if rank == 0:

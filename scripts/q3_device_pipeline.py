@@ -1,0 +1,143 @@
+"""BASELINE config C4, device resident: the TPC-H Q3-shaped operator pipeline of the reference's physical plan
+(sqllogictest/test_files/tpch/plans/q3.slt.part:60-76), every operator through the C ABI with HBM-resident columns:
+
+    FilterExec(c_mktsegment = 1)                                   customer   (1 = 'BUILDING')
+    FilterExec(o_orderdate < 1995-03-15)                           orders
+    HashJoinExec RightSemi (c_custkey = o_custkey)                 -> orders of BUILDING customers
+    FilterExec(l_shipdate > 1995-03-15)                            lineitem
+    HashJoinExec Inner (o_orderkey = l_orderkey)
+    ProjectionExec rev = l_extendedprice * (100 - l_discount)      (int64 fixed point: cents x hundredths, exact)
+    AggregateExec gby [l_orderkey, o_orderdate, o_shippriority] SUM(rev)
+
+Tables are synthetic with TPC-H cardinalities (SF x 150k customers, 1.5M orders, 6M lineitems), generated in HBM with the
+counter-based generators + the expression kernels: sparse order keys (8 of every 32, as dbgen), a third of the customers
+without orders, dates uniform over 1992-01-01..1998-08-02 (+ up to 121 days for ship dates).  Dates are int32 days."""
+import datetime
+
+import numpy as np
+
+from datafusion_b200 import capi as D
+
+EPOCH = datetime.date(1970, 1, 1)
+D0, D1 = (datetime.date(1992, 1, 1) - EPOCH).days, (datetime.date(1998, 8, 2) - EPOCH).days
+CUT = (datetime.date(1995, 3, 15) - EPOCH).days
+
+
+def C(i): return [(D.EXPR_COLUMN, i, 0, 0, 0, 0.0)]
+def L(v, t=None): return [(D.EXPR_LITERAL, 0, t if t is not None else D.INT64, 0, int(v), 0.0)]
+def B(op, l, r): return l + r + [(D.EXPR_BINARY, op, 0, 0, 0, 0.0)]
+def CAST(e, t): return e + [(D.EXPR_CAST, 0, t, 0, 0, 0.0)]
+
+
+class Table:
+    def __init__(self, names, types, cols, rows, keep):
+        self.names, self.types, self.cols, self.rows, self._keep = names, types, cols, rows, keep
+
+    def host(self, ctx):
+        return {n: ctx.to_host(c.values, self.rows * D.WIDTH[t]).view(D.NP_OF_TYPE[t]).copy() for n, t, c in zip(self.names, self.types, self.cols)}
+
+
+def _col(buf, n, t=None):
+    c = D.Column()
+    c.type, c.flags, c.length, c.offset, c.null_count, c.values, c.validity = (t if t is not None else D.INT64), 0, n, 0, 0, buf.ptr, None
+    return c
+
+
+def gen_tables(ctx, sf, seed=1):
+    nc, no, nl = int(150_000 * sf), int(1_500_000 * sf), int(6_000_000 * sf)
+    keep = []
+
+    def gen(kind, s, a, b, n):
+        buf = ctx.generate_i64(kind, s, a, b, 0, n); keep.append(buf)
+        return _col(buf, n)
+
+    def ev(cols, n, nodes):
+        b = D.evaluate_device(ctx, cols, n, nodes); keep.append(b)
+        c = b.column(0)
+        c.validity = None; c.null_count = 0          # inputs have no NULLs
+        return c
+
+    sparse = lambda e: B(D.OP_PLUS, B(D.OP_PLUS, B(D.OP_MULTIPLY, B(D.OP_DIVIDE, e, L(8)), L(32)), B(D.OP_MODULO, e, L(8))), L(1))   # 8 of every 32 keys
+    customer = Table(["c_custkey", "c_mktsegment"], [D.INT64, D.INT64], [gen(D.GEN_SEQ, 0, 1, 0, nc), gen(D.GEN_UNIFORM, seed + 1, 0, 5, nc)], nc, keep)
+    oidx = gen(D.GEN_SEQ, 0, 0, 0, no)
+    orders = Table(["o_orderkey", "o_custkey", "o_orderdate", "o_shippriority"], [D.INT64, D.INT64, D.INT32, D.INT32],
+                   [ev([oidx], no, sparse(C(0))), gen(D.GEN_UNIFORM, seed + 2, 1, max(nc * 2 // 3, 1), no),
+                    ev([gen(D.GEN_UNIFORM, seed + 3, D0, D1 - D0 + 1, no)], no, CAST(C(0), D.INT32)),
+                    ev([oidx], no, CAST(B(D.OP_MULTIPLY, C(0), L(0)), D.INT32))], no, keep)
+    lidx = gen(D.GEN_UNIFORM, seed + 4, 0, no, nl)
+    lineitem = Table(["l_orderkey", "l_extendedprice", "l_discount", "l_shipdate"], [D.INT64, D.INT64, D.INT64, D.INT32],
+                     [ev([lidx], nl, sparse(C(0))), gen(D.GEN_UNIFORM, seed + 5, 90_000, 10_410_000, nl), gen(D.GEN_UNIFORM, seed + 6, 0, 11, nl),
+                      ev([gen(D.GEN_UNIFORM, seed + 7, D0 + 1, D1 - D0 + 121, nl)], nl, CAST(C(0), D.INT32))], nl, keep)
+    ctx.sync()
+    return customer, orders, lineitem
+
+
+def _filter(ctx, t, nodes, projection):
+    f = D.FilterHandle(ctx, t.types, nodes, projection, batch_size=0)
+    f.push_device(t.cols); f.finish()
+    outs = f.drain(host=False)
+    f.close()
+    return outs
+
+
+def _bcols(batches):
+    assert len(batches) == 1, "the pipeline runs on whole-table batches"
+    return [batches[0].column(i) for i in range(batches[0].num_columns)]
+
+
+def run_q3(ctx, customer, orders, lineitem):
+    """returns (result batches [l_orderkey, o_orderdate, o_shippriority, revenue], stage row counts)"""
+    stages = {}
+    c = _filter(ctx, customer, B(D.OP_EQ, C(1), L(1)), [0])
+    o = _filter(ctx, orders, B(D.OP_LT, C(2), L(CUT, D.INT32)), None)
+    stages["customer_building"], stages["orders_before_cut"] = c[0].num_rows if c else 0, o[0].num_rows if o else 0
+    semi = D.HashJoinHandle(ctx, [D.INT64], orders.types, [0], [1], [1, 1, 1], [0, 2, 3], D.JOIN_RIGHT_SEMI)
+    semi.push_build_device(_bcols(c)); semi.finish_build()
+    semi.push_probe_device(_bcols(o)); semi.finish_probe()
+    so = semi.drain(host=False)
+    semi.close()
+    stages["orders_of_building_customers"] = sum(b.num_rows for b in so)
+    l = _filter(ctx, lineitem, B(D.OP_GT, C(3), L(CUT, D.INT32)), [0, 1, 2])
+    stages["lineitem_after_cut"] = l[0].num_rows if l else 0
+    inner = D.HashJoinHandle(ctx, [D.INT64, D.INT32, D.INT32], [D.INT64, D.INT64, D.INT64], [0], [0], [1, 0, 0, 1, 1], [0, 1, 2, 1, 2])
+    inner.push_build_device(_bcols(so)); inner.finish_build()
+    inner.push_probe_device(_bcols(l)); inner.finish_probe()
+    jo = inner.drain(host=False)
+    inner.close()
+    jc = _bcols(jo) if jo else None
+    stages["joined_rows"] = jo[0].num_rows if jo else 0
+    res = []
+    if jc is not None:
+        n = jo[0].num_rows
+        rev = D.evaluate_device(ctx, jc, n, B(D.OP_MULTIPLY, C(3), B(D.OP_MINUS, L(100), C(4))))
+        rc = rev.column(0)
+        agg = D.AggHandle(ctx, [D.INT64, D.INT32, D.INT32, D.INT64], [0, 1, 2], [(D.AGG_SUM, 3, -1)], D.AGG_SINGLE_PARTITIONED, 8192, max(stages["orders_of_building_customers"], 1024))
+        agg.push_device([jc[0], jc[1], jc[2], rc]); agg.finish()
+        res = agg.drain(host=False)
+        agg.close()
+        rev.release()
+    stages["groups"] = sum(b.num_rows for b in res)
+    for b in c + o + so + l + jo:
+        b.release()
+    return res, stages
+
+
+def q3_expected(c, o, l):
+    """independent numpy / pandas evaluation on the downloaded tables"""
+    import pandas as pd
+    ck = set(c["c_custkey"][c["c_mktsegment"] == 1].tolist())
+    od = pd.DataFrame(o); od = od[(od.o_orderdate < CUT) & od.o_custkey.isin(ck)]
+    ld = pd.DataFrame(l); ld = ld[ld.l_shipdate > CUT]
+    j = ld.merge(od, left_on="l_orderkey", right_on="o_orderkey")
+    j["rev"] = j.l_extendedprice * (100 - j.l_discount)
+    g = j.groupby(["l_orderkey", "o_orderdate", "o_shippriority"], as_index=False)["rev"].sum()
+    return sorted(zip(g.l_orderkey.tolist(), g.o_orderdate.tolist(), g.o_shippriority.tolist(), g.rev.tolist()))
+
+
+def result_rows(ctx, res):
+    out = []
+    for b in res:
+        cols = [b.column(i) for i in range(4)]
+        arrs = [ctx.to_host(cc.values, b.num_rows * D.WIDTH[cc.type]).view(D.NP_OF_TYPE[cc.type]) for cc in cols]
+        out += list(zip(*[a.tolist() for a in arrs]))
+    return sorted(out)
