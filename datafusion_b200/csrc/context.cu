@@ -72,6 +72,14 @@ int dfgpu_ctx_create(int device, void* stream, dfgpu_ctx** out) {
     if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
     else { DF_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
     DF_CUDA(cudaMallocHost(&ctx->pinned_scalar, 256));
+    // idle-block cache limit: half of the device memory (SF100-sized pipelines free > 24 GB of temporaries per step; trimming
+    // them costs a device sync + cudaFree / cudaMalloc round trips every step), DFGPU_DEV_CACHE_GB overrides
+    {
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) ctx->dev_cache_limit = std::max<size_t>(ctx->dev_cache_limit, total_b / 2);
+      else cudaGetLastError();
+      if (const char* e = getenv("DFGPU_DEV_CACHE_GB")) { const long gb = atol(e); if (gb > 0) ctx->dev_cache_limit = (size_t)gb << 30; }
+    }
     // keep freed blocks in the pool: operators re-allocate similar sizes every batch
     cudaMemPool_t pool;
     DF_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));

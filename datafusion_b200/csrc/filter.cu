@@ -574,7 +574,17 @@ EvalResult evaluate_expr(dfgpu_ctx* ctx, const ExprPlan& plan, const std::vector
     if (e & ERR_DIV_ZERO) throw Error(DFGPU_ERR_ARITH, "Arrow error: Divide by zero error");
     if (e & ERR_OVERFLOW) throw Error(DFGPU_ERR_ARITH, "Arrow error: Arithmetic overflow");
   }
-  if (want_column) res.column.null_count = -1;
+  if (want_column) {
+    // an expression over columns that carry no validity bitmap in THIS batch and without NULL literals cannot produce a NULL
+    // (errors, not NULLs, come out of division by zero): drop the all-ones bitmap so consumers keep their no-NULL fast paths
+    bool can_null = false;
+    for (const auto& nd : plan.nodes) {
+      if (nd.kind == DFGPU_EXPR_COLUMN && cols[nd.a].validity) can_null = true;
+      if (nd.kind == DFGPU_EXPR_LITERAL && nd.is_null) can_null = true;
+    }
+    if (can_null) res.column.null_count = -1;
+    else { res.column.null_count = 0; res.column.validity = nullptr; res.column.own_validity.reset(); }
+  }
   return res;
 }
 
