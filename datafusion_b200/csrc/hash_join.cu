@@ -130,6 +130,19 @@ __device__ __forceinline__ void chain_insert(uint32_t* head, uint32_t* next, uin
   }
 }
 
+// null-aware LeftAnti: build rows whose key is NULL are treated as visited, so the final pass does not emit them
+__global__ void __launch_bounds__(256) mark_null_keys_kernel(const uint8_t* __restrict__ valid, int64_t voff, int64_t n, uint32_t* __restrict__ vis) {
+  const int64_t nw = (n + 31) / 32;
+  for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < nw; w += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t m = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int64_t row = w * 32 + b;
+      if (row < n && !bit_get(valid, voff + row)) m |= 1u << b;
+    }
+    if (m) vis[w] |= m;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // build
 // ------------------------------------------------------------------------------------------
@@ -1122,6 +1135,7 @@ struct dfgpu_hashjoin {
   int64_t m_build_rows = 0, m_build_batches = 0, m_input_rows = 0, m_input_batches = 0, m_output_rows = 0, m_output_batches = 0,
           m_array_map = 0, m_probe_hits = 0;
   bool probe_side_non_empty = false;
+  bool probe_has_null = false;   // null-aware LeftAnti: a NULL probe key was seen (JoinLeftData::probe_side_has_null)
 };
 
 namespace dfgpu {
@@ -1499,6 +1513,35 @@ static void push_probe(dfgpu_hashjoin* j, std::vector<DCol>&& cols) {
   j->m_input_batches++;
   if (n == 0) return;
   j->probe_side_non_empty = true;
+  if (j->opt.null_aware) {   // NOT IN semantics (stream.rs:755-806, 937-956)
+    const DCol& kcol = cols[j->on_probe[0]];
+    const bool key_has_null = kcol.validity && count_set_bits(ctx, kcol.validity, kcol.offset, n) != n;
+    if (j->opt.join_type == DFGPU_JOIN_LEFT_ANTI) {
+      if (key_has_null) j->probe_has_null = true;   // a NULL in the subquery: NOT IN is never TRUE, nothing is output
+      if (j->probe_has_null) return;
+    } else {  // RightAnti
+      if (j->null_rows > 0) return;                 // build side has a NULL key: no probe row qualifies
+      if (key_has_null && j->nB > 0) {              // NULL probe keys are not emitted (an empty build side emits every row)
+        const int64_t nw = (n + 31) / 32;
+        DevBuf bits(ctx, (size_t)(nw + 1) * 4);
+        bits.zero();
+        bitmap_or_copy(ctx, bits.as<uint8_t>(), 0, kcol.validity, kcol.offset, n);
+        DevBuf idx;
+        const int64_t keep = compact_flag_indices(ctx, bits.as<uint32_t>(), n, 1, &idx);
+        j->m_input_rows -= n; j->m_input_batches--;
+        if (keep == 0) { j->m_input_rows += n; j->m_input_batches++; return; }
+        std::vector<DCol> kept;
+        for (size_t c = 0; c < cols.size(); ++c) {
+          DCol t = take_column(ctx, cols[c], idx.as<uint32_t>(), keep, false);
+          if ((int)c == j->on_probe[0]) { t.validity = nullptr; t.null_count = 0; t.own_validity.reset(); }   // every kept key is valid
+          kept.push_back(std::move(t));
+        }
+        push_probe(j, std::move(kept));
+        j->m_input_rows += n - keep;
+        return;
+      }
+    }
+  }
   const int mode = j->emit_mode;
   // empty / unmatchable build side: build_batch_empty_build_side (utils.rs:1393-1430)
   KeyCols pk;
@@ -1806,6 +1849,14 @@ static void finish_probe(dfgpu_hashjoin* j) {
     join_build_flags_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(j->build_keys, n, j->table, vis.as<uint32_t>());
     DF_LAUNCH_CHECK(ctx);
   }
+  if (j->opt.null_aware && jt == DFGPU_JOIN_LEFT_ANTI) {   // stream.rs:1016-1072
+    if (j->probe_has_null) return;
+    const DCol& k = j->build_cols[j->on_build[0]];
+    if (j->probe_side_non_empty && k.validity) {   // NULL NOT IN (non-empty) is never TRUE; NULL NOT IN (empty) is
+      mark_null_keys_kernel<<<grid_for(nw, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(k.validity, k.offset, n, vis.as<uint32_t>());
+      DF_LAUNCH_CHECK(ctx);
+    }
+  }
   if (jt == DFGPU_JOIN_LEFT_MARK) {
     // all build rows + mark column (visited)
     DevBuf all(ctx, (size_t)n * 4);
@@ -1856,6 +1907,11 @@ int dfgpu_hashjoin_create(dfgpu_ctx* ctx, const int32_t* build_types, int32_t n_
                           int32_t n_out, const dfgpu_hashjoin_options* opts, dfgpu_hashjoin** out) {
   DF_API_BEGIN(ctx)
   DF_CHECK(ctx && out && opts, DFGPU_ERR_INVALID, "null argument");
+  if (opts->null_aware) {   // HashJoinExecBuilder validation, exec.rs:429-455
+    DF_CHECK(opts->join_type == DFGPU_JOIN_LEFT_ANTI || opts->join_type == DFGPU_JOIN_RIGHT_ANTI, DFGPU_ERR_INVALID,
+             "null_aware can only be true for LeftAnti joins and RightAnti joins with `CollectLeft` `PartitionMode`");
+    DF_CHECK(n_on == 1, DFGPU_ERR_INVALID, "null_aware anti join only supports single column join key");
+  }
   std::unique_ptr<dfgpu_hashjoin> j(new dfgpu_hashjoin());
   j->ctx = ctx;
   j->opt = *opts;
@@ -1910,6 +1966,7 @@ int dfgpu_hashjoin_set_filter(dfgpu_hashjoin* j, const int32_t* col_side, const 
   DF_API_BEGIN(j ? j->ctx : nullptr)
   DF_CHECK(j && col_side && col_index && expr && n_cols >= 1, DFGPU_ERR_INVALID, "null argument");
   DF_CHECK(!j->built && j->build_parts.empty(), DFGPU_ERR_STATE, "set_filter must be called before any batch is pushed");
+  DF_CHECK(!(j->opt.null_aware && j->opt.join_type == DFGPU_JOIN_RIGHT_ANTI), DFGPU_ERR_INVALID, "null_aware RightAnti join does not support a join filter");
   std::vector<int32_t> types;
   for (int c = 0; c < n_cols; ++c) {
     DF_CHECK(col_side[c] == 0 || col_side[c] == 1, DFGPU_ERR_INVALID, "join filter column side must be 0 (build) or 1 (probe)");

@@ -245,6 +245,10 @@ typedef struct dfgpu_hashjoin_options {
   double perfect_hash_join_min_key_density;        /* default 0.15 */
   int32_t force_hash_collisions; /* mirror of cargo feature force_hash_collisions (hash_utils.rs:1185-1205) */
   int32_t ordered_output;  /* 1 = reference order (probe order × ascending build index); 0 = any order */
+  int32_t null_aware;      /* NOT IN semantics (HashJoinExec::null_aware, exec.rs:429-455, stream.rs:755-806, 1016-1072): LeftAnti /
+                            * RightAnti on ONE key column; a NULL on the other side empties the result, NULL keys of the
+                            * preserved side are never emitted (unless the other side is empty) */
+  int32_t reserved0;
 } dfgpu_hashjoin_options;
 void dfgpu_hashjoin_default_options(dfgpu_hashjoin_options* o);
 

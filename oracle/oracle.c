@@ -285,7 +285,8 @@ O_API int oracle_hash_join(int nkeys, const int64_t* const* bkeys_in, const uint
                            const int64_t* probe_batch_rows, int n_probe_batches,
                            int join_type, int null_equals_null, int64_t batch_size, int64_t phj_threshold, double phj_density,
                            int force_collisions, int key_is_integer, JoinResult* res, int64_t* build_order_out,
-                           int (*pair_filter)(int64_t build_row, int64_t probe_row) /* JoinFilter on ORIGINAL row numbers, or NULL */) {
+                           int (*pair_filter)(int64_t build_row, int64_t probe_row) /* JoinFilter on ORIGINAL row numbers, or NULL */,
+                           int null_aware /* NOT IN semantics for LeftAnti / RightAnti on one key column (exec.rs:429-455, stream.rs:755-806) */) {
   memset(res, 0, sizeof(*res));
   Vec64 out_b = {0}, out_p = {0}, out_m = {0};
   /* ---- perfect-hash decision: try_create_array_map, exec.rs:111-191 ---- */
@@ -368,9 +369,17 @@ O_API int oracle_hash_join(int nkeys, const int64_t* const* bkeys_in, const uint
   /* ---- probe, batch by batch (stream.rs:687-1000) ---- */
   Vec64 pi = {0}, bi = {0};
   int64_t pstart = 0;
+  int build_has_null = 0, probe_side_has_null = 0, probe_side_non_empty = 0;   /* JoinLeftData::build_side_has_null & the shared probe flags */
+  if (bvalid[0]) for (int64_t i = 0; i < nb; ++i) if (!bvalid[0][i]) { build_has_null = 1; break; }
   for (int pb = 0; pb < n_probe_batches; ++pb) {
     const int64_t len = probe_batch_rows[pb];
     if (len == 0) continue;
+    if (null_aware && join_type == J_RIGHT_ANTI && build_has_null) { pstart += len; continue; }   /* stream.rs:763-769 */
+    if (null_aware && join_type == J_LEFT_ANTI) {                                                    /* stream.rs:770-805 */
+      probe_side_non_empty = 1;
+      if (pvalid && pvalid[0]) for (int64_t i = 0; i < len; ++i) if (!pvalid[0][pstart + i]) { probe_side_has_null = 1; break; }
+      if (probe_side_has_null) { pstart += len; continue; }
+    }
     /* is_empty = !has_matchable_build_rows(): build_batch_empty_build_side (utils.rs:1393-1430) */
     if (matchable_rows == 0) {
       if (join_type == J_RIGHT || join_type == J_FULL || join_type == J_RIGHT_ANTI || join_type == J_RIGHT_MARK) {
@@ -452,16 +461,18 @@ O_API int oracle_hash_join(int nkeys, const int64_t* const* bkeys_in, const uint
           }
           break;
         }
-        case J_RIGHT_ANTI: { /* get_anti_indices */
+        case J_RIGHT_ANTI: { /* get_anti_indices; a null-aware RightAnti does not emit NULL probe keys (stream.rs:937-956) */
+          #define ANTI_EMIT(u) do { if (!(null_aware && pv[0] && !pv[0][(u)])) { v_push(&out_b, -1); v_push(&out_p, pstart + (u)); v_push(&out_m, 0); } } while (0)
           int64_t nextu = range_start;
           for (int64_t k = 0; k < m; ++k) {
             int64_t idx = pi.p[k];
             if (idx < range_start) continue;
             if (idx >= range_end) break;
-            for (int64_t u = nextu; u < idx; ++u) { v_push(&out_b, -1); v_push(&out_p, pstart + u); v_push(&out_m, 0); }
+            for (int64_t u = nextu; u < idx; ++u) ANTI_EMIT(u);
             nextu = idx + 1;
           }
-          for (int64_t u = nextu; u < range_end; ++u) { v_push(&out_b, -1); v_push(&out_p, pstart + u); v_push(&out_m, 0); }
+          for (int64_t u = nextu; u < range_end; ++u) ANTI_EMIT(u);
+          #undef ANTI_EMIT
           break;
         }
         case J_RIGHT_MARK: { /* get_mark_indices + left_indices = range */
@@ -483,8 +494,10 @@ O_API int oracle_hash_join(int nkeys, const int64_t* const* bkeys_in, const uint
     pstart += len;
   }
   /* ---- process_unmatched_build_batch (stream.rs:1002-1100) + get_final_indices_from_bit_map (utils.rs:1210-1245) ---- */
-  if (need_final) {
+  if (need_final && !(null_aware && probe_side_has_null)) {   /* stream.rs:1016-1027: a NULL on the probe side empties a null-aware anti join */
     for (int64_t i = 0; i < nb; ++i) {
+      /* stream.rs:1036-1072: NULL build keys are not output once the probe side was non-empty (NULL NOT IN (empty) is TRUE) */
+      if (null_aware && join_type == J_LEFT_ANTI && probe_side_non_empty && bvalid[0] && !bvalid[0][i]) continue;
       if (join_type == J_LEFT_MARK) { v_push(&out_b, i); v_push(&out_p, -1); v_push(&out_m, visited[i]); }
       else if (join_type == J_LEFT_SEMI) { if (visited[i]) { v_push(&out_b, i); v_push(&out_p, -1); v_push(&out_m, 0); } }
       else if (!visited[i]) { v_push(&out_b, i); v_push(&out_p, -1); v_push(&out_m, 0); }

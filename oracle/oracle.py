@@ -96,7 +96,7 @@ def _ptr_array(arrs, ctype):
 def hash_join_indices(build_keys: Sequence[Col], probe_keys: Sequence[Col], join_type: int = J_INNER, null_equals_null: bool = False,
                       batch_size: int = 8192, phj_threshold: int = 1024, phj_density: float = 0.15, force_collisions: bool = False,
                       build_batch_rows: Optional[Sequence[int]] = None, probe_batch_rows: Optional[Sequence[int]] = None,
-                      key_is_integer: bool = True, pair_filter=None):
+                      key_is_integer: bool = True, pair_filter=None, null_aware: bool = False):
     """(build_idx, probe_idx, mark, used_array_map): -1 = NULL index.  Order = the reference's emission order."""
     L = lib()
     nk = len(build_keys)
@@ -116,7 +116,8 @@ def hash_join_indices(build_keys: Sequence[Col], probe_keys: Sequence[Col], join
                        pbr.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int(len(pbr)), C.c_int(join_type), C.c_int(1 if null_equals_null else 0),
                        C.c_int64(batch_size), C.c_int64(phj_threshold), C.c_double(phj_density), C.c_int(1 if force_collisions else 0),
                        C.c_int(1 if key_is_integer else 0), C.byref(res), None,
-                       _PAIR_FILTER(lambda b, p: 1 if pair_filter(int(b), int(p)) else 0) if pair_filter is not None else None)
+                       _PAIR_FILTER(lambda b, p: 1 if pair_filter(int(b), int(p)) else 0) if pair_filter is not None else None,
+                       C.c_int(1 if null_aware else 0))
     n = res.n
     if n == 0:
         b, p, m = np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, bool)

@@ -32,7 +32,7 @@ def test_gpu_matches_reference_join_snapshots(gpu_ctx, case):
         got, h = gpu_hash_join(gpu_ctx, left, right, on_b, on_p, side, idx, GJT[case["join_type"]],
                                D.NULL_EQUALS_NULL if case["null_equality"] == "NullEqualsNull" else D.NULL_EQUALS_NOTHING,
                                batch_size=batch_size, phj=(thr, dens), probe_batch_rows=min(batch_size, nr), build_batch_rows=nl, return_handle=True,
-                               filter=kat_filter(case, gpu=True), build_types=bt, probe_types=pt)
+                               filter=kat_filter(case, gpu=True), build_types=bt, probe_types=pt, null_aware=bool(case.get("null_aware")))
         ordered = (not case["sorted"]) and case["join_type"] in ORDERED
         assert_cols_equal(got, exp, ordered=ordered, what=f"{case['name']} bs={batch_size} phj={phj} ({case['ref']})")
         # assert_phj_used (exec.rs: array_map_created_count metric); "phj_expected": false = the reference asserts it is NOT used
@@ -218,3 +218,34 @@ def test_gpu_l2_sliced_probe_is_identical_to_single_pass(gpu_ctx, monkeypatch, n
         assert h.metric("array_map_created_count") == 0
         h.close()
         assert_cols_equal(got, exp, ordered=True, what=f"sliced probe S={n_slices} payload={with_payload} device={device}")
+
+
+def test_gpu_null_aware_validation(gpu_ctx):
+    """HashJoinExecBuilder validation (exec.rs:429-455; tests exec.rs:7586-7745): null_aware needs LeftAnti / RightAnti, a single
+    key column, and — for RightAnti — no join filter."""
+    with pytest.raises(D.DfgpuError, match="null_aware can only be true for LeftAnti joins and RightAnti joins"):
+        D.HashJoinHandle(gpu_ctx, [D.INT32, D.INT32], [D.INT32, D.INT32], [0], [0], [0, 1], [0, 0], D.JOIN_INNER, null_aware=True)
+    with pytest.raises(D.DfgpuError, match="null_aware anti join only supports single column join key"):
+        D.HashJoinHandle(gpu_ctx, [D.INT32, D.INT32], [D.INT32, D.INT32], [0, 1], [0, 1], [0, 0], [0, 1], D.JOIN_LEFT_ANTI, null_aware=True)
+    nodes = [(D.EXPR_COLUMN, 0, 0, 0, 0, 0.0), (D.EXPR_LITERAL, 0, D.INT32, 0, 8, 0.0), (D.EXPR_BINARY, D.OP_NEQ, 0, 0, 0, 0.0)]
+    j = D.HashJoinHandle(gpu_ctx, [D.INT32, D.INT32], [D.INT32, D.INT32], [0], [0], [1, 1], [0, 1], D.JOIN_RIGHT_ANTI, null_aware=True)
+    with pytest.raises(D.DfgpuError, match="null_aware RightAnti join does not support a join filter"):
+        j.set_filter([0], [1], nodes)
+    j.close()
+    j = D.HashJoinHandle(gpu_ctx, [D.INT32, D.INT32], [D.INT32, D.INT32], [0], [0], [0, 0], [0, 1], D.JOIN_LEFT_ANTI, null_aware=True)
+    j.set_filter([1], [1], nodes)      # allowed for LeftAnti (test_null_aware_filter_rejected_only_for_right_anti)
+    j.close()
+
+
+def test_gpu_null_aware_anti_large_random(gpu_ctx):
+    """null-aware anti joins against the oracle on larger random inputs (NULLs on the preserved side only, several probe batches)"""
+    rng = np.random.default_rng(11)
+    bk = rng.integers(0, 5000, 20000).astype(np.int64); pk = rng.integers(0, 8000, 70000).astype(np.int64)
+    for jt, gjt, bnull, pnull in ((O.J_LEFT_ANTI, D.JOIN_LEFT_ANTI, True, False), (O.J_RIGHT_ANTI, D.JOIN_RIGHT_ANTI, False, True)):
+        build = [(bk, (rng.random(len(bk)) > 0.05) if bnull else None), (np.arange(len(bk), dtype=np.int64), None)]
+        probe = [(pk, (rng.random(len(pk)) > 0.05) if pnull else None), (np.arange(len(pk), dtype=np.int64), None)]
+        side, idx = ([0, 0], [0, 1]) if jt == O.J_LEFT_ANTI else ([1, 1], [0, 1])
+        exp = O.hash_join(build, probe, [0], [0], side, idx, join_type=jt, null_aware=True, probe_batch_rows=[30000, 40000])
+        got = gpu_hash_join(gpu_ctx, build, probe, [0], [0], side, idx, gjt, probe_batch_rows=30000 if jt == O.J_LEFT_ANTI else 40000, null_aware=True)
+        assert len(exp[0][0]) > 0
+        assert_cols_equal(got, exp, ordered=False, what=f"null-aware {jt}")

@@ -84,7 +84,7 @@ def test_oracle_reproduces_reference_join_snapshots(case):
         thr, dens = (819200, 0.0) if phj else (0, float("inf"))
         nl, nr = len(case["left"][0][1]), len(case["right"][0][1])
         fkw = {"filter": kat_filter(case)} if case.get("filter") else {}
-        got = O.hash_join(left, right, on_b, on_p, side, idx, join_type=JT[case["join_type"]], **fkw,
+        got = O.hash_join(left, right, on_b, on_p, side, idx, join_type=JT[case["join_type"]], **fkw, null_aware=bool(case.get("null_aware")),
                           null_equals_null=case["null_equality"] == "NullEqualsNull", batch_size=batch_size, phj_threshold=thr, phj_density=dens,
                           build_batch_rows=[nl] * case.get("left_repeat", 1), probe_batch_rows=[nr] * case.get("right_repeat", 1) if nr else None)
         assert_cols_equal(got, exp, ordered=not case["sorted"], what=f"{case['name']} bs={batch_size} phj={phj} ({case['ref']})")
@@ -102,7 +102,7 @@ def test_oracle_force_hash_collisions_is_output_invariant(case):
     left, right, on_b, on_p, side, idx, exp = kat_tables(case)
     fkw = {"filter": kat_filter(case)} if case.get("filter") else {}
     got = O.hash_join(left, right, on_b, on_p, side, idx, join_type=JT[case["join_type"]], phj_threshold=0, phj_density=float("inf"), force_collisions=True, **fkw,
-                      null_equals_null=case["null_equality"] == "NullEqualsNull")
+                      null_equals_null=case["null_equality"] == "NullEqualsNull", null_aware=bool(case.get("null_aware")))
     assert_cols_equal(got, exp, ordered=not case["sorted"], what=case["name"])
 
 
