@@ -80,7 +80,7 @@ __device__ __forceinline__ int cmp_f64_total(double a, double b) {
   return x < y ? -1 : (x > y ? 1 : 0);
 }
 
-enum ErrBits : int { ERR_DIV_ZERO = 1, ERR_OVERFLOW = 2 };
+enum ErrBits : int { ERR_DIV_ZERO = 1, ERR_OVERFLOW = 2, ERR_CAST = 4 };
 
 __device__ __forceinline__ void eval_binary(const ENode& nd, uint64_t a, bool av, uint64_t b, bool bv, uint64_t* r, bool* rv, int* err) {
   const int op = nd.op;
@@ -182,7 +182,9 @@ __device__ __forceinline__ void eval_binary(const ENode& nd, uint64_t a, bool av
   *r = wrap_to_type(z, nd.out_type);
 }
 
-__device__ __forceinline__ uint64_t cast_value(uint64_t v, int from, int to) {
+// CastExpr with the default CastOptions { safe: false } (expressions/cast.rs:37-40): a value that does not fit the integer target is
+// an error ("Can't cast value ..."), not a wrapped or NULL result; NULL slots never raise.  Float -> int truncates toward zero.
+__device__ __forceinline__ uint64_t cast_value(uint64_t v, int from, int to, bool valid, int* err) {
   int cf = cls_of(from), ct = cls_of(to);
   if (ct == C_F64) {
     double d = cf == C_F64 ? __longlong_as_double((long long)v) : (cf == C_U64 || cf == C_BOOL ? (double)v : (double)(long long)v);
@@ -190,7 +192,21 @@ __device__ __forceinline__ uint64_t cast_value(uint64_t v, int from, int to) {
     return (uint64_t)__double_as_longlong(d);
   }
   if (ct == C_BOOL) return cf == C_F64 ? (__longlong_as_double((long long)v) != 0.0) : (v != 0);
-  uint64_t iv = cf == C_F64 ? (ct == C_U64 ? (uint64_t)__longlong_as_double((long long)v) : (uint64_t)(long long)__longlong_as_double((long long)v)) : v;
+  const int w = type_width(to) * 8;
+  uint64_t iv = v;
+  bool fits = true;
+  if (cf == C_F64) {
+    const double d = __longlong_as_double((long long)v);
+    const double t = trunc(d);
+    fits = isfinite(d) && (ct == C_U64 ? (t >= 0.0 && t < ldexp(1.0, w)) : (t >= -ldexp(1.0, w - 1) && t < ldexp(1.0, w - 1)));
+    iv = !fits ? 0ull : (ct == C_U64 ? (uint64_t)t : (uint64_t)(long long)t);
+  } else if (cf == C_I64) {
+    const long long x = (long long)v;
+    fits = ct == C_I64 ? (w == 64 || (x >= -(1ll << (w - 1)) && x < (1ll << (w - 1)))) : (x >= 0 && (w == 64 || x < (1ll << w)));
+  } else if (cf == C_U64) {
+    fits = ct == C_I64 ? (v < (1ull << (w - 1))) : (w == 64 || v < (1ull << w));
+  }
+  if (!fits) { if (valid) *err |= ERR_CAST; return 0; }
   return wrap_to_type(iv, to);
 }
 
@@ -224,7 +240,7 @@ __device__ __forceinline__ uint64_t eval_row(const EProgram& p, int64_t row, boo
     if (cls_of(nd.out_type) == C_F64) sv[sp - 1] ^= 0x8000000000000000ull;
     else sv[sp - 1] = wrap_to_type(0ull - sv[sp - 1], nd.out_type);  // neg_wrapping
     break;
-      case DFGPU_EXPR_CAST: sv[sp - 1] = cast_value(sv[sp - 1], nd.in_type, nd.out_type); break;
+      case DFGPU_EXPR_CAST: sv[sp - 1] = cast_value(sv[sp - 1], nd.in_type, nd.out_type, sk[sp - 1], err); break;
     }
   }
   *ok_out = sk[0];
@@ -573,6 +589,7 @@ EvalResult evaluate_expr(dfgpu_ctx* ctx, const ExprPlan& plan, const std::vector
     int e = read_scalar<int>(ctx, err.as<int>());
     if (e & ERR_DIV_ZERO) throw Error(DFGPU_ERR_ARITH, "Arrow error: Divide by zero error");
     if (e & ERR_OVERFLOW) throw Error(DFGPU_ERR_ARITH, "Arrow error: Arithmetic overflow");
+    if (e & ERR_CAST) throw Error(DFGPU_ERR_ARITH, "Arrow error: Cast error: Can't cast value to the target type (out of range)");
   }
   if (want_column) {
     // an expression over columns that carry no validity bitmap in THIS batch and without NULL literals cannot produce a NULL
@@ -709,6 +726,7 @@ static void filter_push(dfgpu_filter* f, const std::vector<DCol>& cols) {
     DF_CUDA(cudaStreamSynchronize(ctx->stream));
     if (herr & ERR_DIV_ZERO) throw Error(DFGPU_ERR_ARITH, "Arrow error: Divide by zero error");
     if (herr & ERR_OVERFLOW) throw Error(DFGPU_ERR_ARITH, "Arrow error: Arithmetic overflow");
+    if (herr & ERR_CAST) throw Error(DFGPU_ERR_ARITH, "Arrow error: Cast error: Can't cast value to the target type (out of range)");
     const int64_t kept = (int64_t)h[0];
     if (kept == 0) return;
     for (auto& c : part) c.length = kept;

@@ -279,6 +279,10 @@ class ArrowDivideByZero(ArithmeticError):
     pass
 
 
+class ArrowCastError(ArithmeticError):
+    """arrow-cast with CastOptions { safe: false } — DataFusion's DEFAULT_CAST_OPTIONS (expressions/cast.rs:37-40)"""
+
+
 def _total_order_key(x: np.ndarray) -> np.ndarray:
     """IEEE-754 totalOrder as a sortable int64, after -0.0 -> +0.0 (datum.rs:88-105)"""
     x = np.asarray(x, dtype=np.float64).copy()
@@ -382,8 +386,24 @@ def eval_expr(cols: Sequence[Col], nodes: Sequence[tuple], col_dtypes: Optional[
                 st.append((-v, val))
         elif kind == E_CAST:
             v, val = st.pop()
-            with np.errstate(all="ignore"):
-                st.append((v.astype(dt), val))
+            tgt = np.dtype(dt)
+            act = np.ones(n, bool) if val is None else np.asarray(val, bool)
+            if tgt.kind in "iu" and v.dtype.kind in "iuf":
+                # out-of-range values fail the cast (they neither wrap nor become NULL); float -> int truncates toward zero
+                info = np.iinfo(tgt)
+                if v.dtype.kind == "f":
+                    t = np.trunc(v.astype(np.float64))
+                    fits = np.isfinite(v) & (t >= float(info.min)) & (t < float(info.max) + 1.0)
+                else:
+                    fits = np.array([info.min <= int(x) <= info.max for x in v.tolist()], bool) if len(v) else np.zeros(0, bool)
+                if np.any(act & ~fits):
+                    raise ArrowCastError("Can't cast value to the target type")
+                with np.errstate(all="ignore"):
+                    out = np.where(fits, np.trunc(v) if v.dtype.kind == "f" else v, 0).astype(tgt)
+                st.append((out, val))
+            else:
+                with np.errstate(all="ignore"):
+                    st.append((v.astype(tgt), val))
         else:
             raise ValueError(kind)
     assert len(st) == 1

@@ -88,6 +88,8 @@ def test_gpu_reproduces_reference_binary_expr_tests(gpu_ctx, case):
             nodes.append((D.EXPR_COLUMN, item[1], 0, 0, 0, 0.0))
         elif item[0] == "lit":
             nodes.append((D.EXPR_LITERAL, 0, _GT[item[1]], 0, item[2], 0.0))
+        elif item[0] == "cast":
+            nodes.append((D.EXPR_CAST, 0, _GT[item[1]], 0, 0, 0.0))
         else:
             nodes.append((D.EXPR_BINARY, _GOPS[item[1]], 0, 0, 0, 0.0))
     na = D.expr_nodes(nodes)
@@ -166,3 +168,27 @@ def test_gpu_divide_by_zero_is_an_error(gpu_ctx):
     assert val.tolist() == [True, False, True] and v[[0, 2]].tolist() == [2, 2]
     with pytest.raises(D.DfgpuError):
         D.FilterHandle(gpu_ctx, [D.INT64], to_nodes(B(D.OP_PLUS, C(0), L(1, np.int64)), True))   # non-boolean predicate (filter.rs:1355)
+
+
+def test_gpu_cast_out_of_range_is_an_error(gpu_ctx):
+    """same contract as test_oracle_cast_out_of_range_is_an_error (expressions/cast.rs:37-40 DEFAULT_CAST_OPTIONS)"""
+    import ctypes as CT
+
+    def cast(col, t):
+        keep = D.HostColumn(*col)
+        arr = (D.Column * 1)(keep.c())
+        nodes = D.expr_nodes([(D.EXPR_COLUMN, 0, 0, 0, 0, 0.0), (D.EXPR_CAST, 0, t, 0, 0, 0.0)])
+        out = CT.c_void_p()
+        rc = gpu_ctx.lib.dfgpu_expr_evaluate_host(gpu_ctx.h, arr, 1, len(col[0]), nodes, 2, CT.byref(out))
+        if rc < 0:
+            return rc, gpu_ctx.lib.dfgpu_last_error(gpu_ctx.h).decode()
+        return 0, D.Batch(gpu_ctx, out.value).column_numpy(0)
+
+    for col, t in (((np.array([1, -1], np.int32), None), D.UINT32), ((np.array([1 << 40], np.int64), None), D.INT32),
+                   ((np.array([1 << 63], np.uint64), None), D.INT64), ((np.array([np.nan]), None), D.INT64), ((np.array([3e10]), None), D.INT32)):
+        rc, msg = cast(col, t)
+        assert rc < 0 and "cast" in msg.lower(), (col, t, msg)
+    rc, (v, val) = cast((np.array([3.9, -3.9, 0.0]), None), D.INT32)
+    assert rc == 0 and v.tolist() == [3, -3, 0]
+    rc, (v, val) = cast((np.array([5, 1 << 40], np.int64), np.array([True, False])), D.INT32)
+    assert rc == 0 and v[0] == 5 and val.tolist() == [True, False]

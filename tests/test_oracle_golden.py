@@ -243,6 +243,8 @@ def test_oracle_reproduces_reference_binary_expr_tests(case):
             nodes.append((O.E_COLUMN, item[1], None, 0, 0))
         elif item[0] == "lit":
             nodes.append((O.E_LITERAL, 0, _NP[item[1]], 0, item[2]))
+        elif item[0] == "cast":
+            nodes.append((O.E_CAST, 0, _NP[item[1]], 0, 0))
         else:
             nodes.append((O.E_BINARY, _OPS[item[1]], None, 0, 0))
     if "error" in case:
@@ -333,3 +335,17 @@ def test_oracle_final_accepts_the_references_skip_aggregation_states(name):
     for keys, res in ((sk, sres), (fk, fres)):
         o = np.argsort(keys[0][0])
         assert keys[0][0][o].tolist() == m["final"]["key"] and res[0]["c"][o].tolist() == m["final"]["count"]
+
+
+def test_oracle_cast_out_of_range_is_an_error():
+    """DEFAULT_CAST_OPTIONS = { safe: false } (expressions/cast.rs:37-40): arrow-cast reports "Can't cast value ..." for values
+    outside the integer target's range; NULL slots never raise; float -> int truncates toward zero."""
+    cast = lambda col, dt: O.eval_expr([col], [(O.E_COLUMN, 0, None, 0, 0), (O.E_CAST, 0, dt, 0, 0)])
+    for col, dt in (((np.array([1, -1], np.int32), None), np.uint32), ((np.array([1 << 40], np.int64), None), np.int32),
+                    ((np.array([1 << 63], np.uint64), None), np.int64), ((np.array([np.nan]), None), np.int64), ((np.array([3e10]), None), np.int32)):
+        with pytest.raises(O.ArrowCastError):
+            cast(col, dt)
+    v, val = cast((np.array([3.9, -3.9, 0.0]), None), np.int32)
+    assert v.tolist() == [3, -3, 0] and val is None
+    v, val = cast((np.array([5, 1 << 40], np.int64), np.array([True, False])), np.int32)    # the out-of-range value sits under a NULL
+    assert v[0] == 5 and val.tolist() == [True, False]
