@@ -59,3 +59,29 @@ def test_default_join_options_match_reference_config():
     assert (opt.batch_size, opt.perfect_hash_join_small_build_threshold) == (8192, 1024)
     assert abs(opt.perfect_hash_join_min_key_density - 0.15) < 1e-12
     assert opt.join_type == capi.JOIN_INNER and opt.null_equality == capi.NULL_EQUALS_NOTHING
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors in capi.py must have exactly the layout a C compiler gives include/dfgpu.h (size and every field
+    offset): compile a probe against the header with gcc and compare."""
+    import ctypes as C
+    structs = {"dfgpu_column": capi.Column, "dfgpu_expr_node": capi.ExprNode, "dfgpu_hashjoin_options": capi.HashJoinOptions, "dfgpu_agg_desc": capi.AggDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dfgpu.h"', 'int main(void) {']
+    for cname, st in structs.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in st._fields_:
+            lines.append(f'  printf(" {fname}=%zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    for line in out:
+        parts = line.split()
+        st = structs[parts[0]]
+        assert int(parts[1]) == C.sizeof(st), parts[0]
+        for item in parts[2:]:
+            fname, off = item.split("=")
+            assert getattr(st, fname).offset == int(off), (parts[0], fname)
