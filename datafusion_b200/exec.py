@@ -341,14 +341,14 @@ class JoinFilter:
 
 
 class GpuHashJoinExec(ExecutionPlan):
-    """HashJoinExec::try_new(left, right, on, filter, join_type, projection, partition_mode, null_equality)
+    """HashJoinExec::try_new(left, right, on, filter, join_type, projection, partition_mode, null_equality, null_aware)
     (physical-plan/src/joins/hash_join/exec.rs:752).  left = build side, right = probe side."""
 
     def __init__(self, left: ExecutionPlan, right: ExecutionPlan, on: Sequence[Tuple[str, str]], join_type: str = "Inner",
-                 null_equality: str = "NullEqualsNothing", filter=None, projection: Optional[Sequence[int]] = None):
+                 null_equality: str = "NullEqualsNothing", filter=None, projection: Optional[Sequence[int]] = None, null_aware: bool = False):
         if not on:
             raise ValueError("Error during planning: On constraints in HashJoinExec should be non-empty")  # exec.rs try_new
-        self.filter = filter
+        self.filter, self.null_aware = filter, bool(null_aware)
         self.left, self.right, self.on, self.join_type, self.null_equality = left, right, list(on), join_type, null_equality
         full, idx = build_join_schema(left.schema, right.schema, join_type)
         if projection is not None:
@@ -370,7 +370,7 @@ class GpuHashJoinExec(ExecutionPlan):
         op = D.HashJoinHandle(ctx.gpu, bt, pt, ob, op_, [s for s, _ in self.column_indices], [i for _, i in self.column_indices],
                               _JOIN_TYPES[self.join_type], D.NULL_EQUALS_NULL if self.null_equality == "NullEqualsNull" else D.NULL_EQUALS_NOTHING,
                               cfg.batch_size, cfg.perfect_hash_join_small_build_threshold, cfg.perfect_hash_join_min_key_density,
-                              cfg.force_hash_collisions)
+                              cfg.force_hash_collisions, self.null_aware)
         if self.filter is not None:
             fields = [(self.left.schema if sd == "left" else self.right.schema).field(ix) for sd, ix in self.filter.column_indices]
             inter = pa.schema([pa.field(f"f{i}", f.type) for i, f in enumerate(fields)])
