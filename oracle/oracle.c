@@ -253,6 +253,37 @@ static int amap_lookup(const ArrayMap* a, const int64_t* key, const uint8_t* val
   return 0;
 }
 
+/* ---- step-level entry points: one get_matched_indices_with_limit_offset call, so the reference's own unit tests of the
+ * maps (joins/array_map.rs:428-600, joins/join_hash_map.rs:497-575) can be replayed tuple by tuple (tests/test_oracle_golden.py).
+ * off / next_off = {idx, has_next, next} of MapOffset; returns 1 when a next offset exists (Some), 0 for None. ---- */
+O_API int oracle_array_map_step(const int64_t* build, const uint8_t* bvalid, int64_t nb, uint64_t min_val, uint64_t max_val,
+                                const int64_t* probe, const uint8_t* pvalid, int64_t np_, int64_t limit, const int64_t* off,
+                                int64_t* pi_out, int64_t* bi_out, int64_t* n_out, int64_t* next_off) {
+  ArrayMap a; memset(&a, 0, sizeof(a));
+  amap_fill(&a, build, bvalid, nb, min_val, max_val);
+  Vec64 pi = {0}, bi = {0};
+  MapOffset cur = {off[0], (int)off[1], (uint64_t)off[2]}, nx = {0, 0, 0};
+  int has = amap_lookup(&a, probe, pvalid, np_, limit, cur, &pi, &bi, &nx);
+  for (int64_t k = 0; k < bi.n; ++k) { pi_out[k] = pi.p[k]; bi_out[k] = bi.p[k]; }
+  *n_out = bi.n;
+  next_off[0] = nx.idx; next_off[1] = nx.has_next; next_off[2] = (int64_t)nx.next;
+  free(pi.p); free(bi.p); free(a.data); free(a.next);
+  return has;
+}
+O_API int oracle_join_hash_map_step(const uint64_t* build_hashes, int64_t nb, const uint64_t* probe_hashes, const uint8_t* valid_keys, int64_t np_,
+                                    int64_t limit, const int64_t* off, int64_t* pi_out, int64_t* bi_out, int64_t* n_out, int64_t* next_off) {
+  JoinHashMap m; jhm_init(&m, (uint64_t)nb);
+  for (int64_t i = 0; i < nb; ++i) jhm_insert(&m, (uint64_t)i, build_hashes[i]);   /* update_from_iter(iter.enumerate(), 0): forward order */
+  Vec64 pi = {0}, bi = {0};
+  MapOffset cur = {off[0], (int)off[1], (uint64_t)off[2]}, nx = {0, 0, 0};
+  int has = jhm_lookup(&m, probe_hashes, valid_keys, np_, limit, cur, &pi, &bi, &nx);
+  for (int64_t k = 0; k < bi.n; ++k) { pi_out[k] = pi.p[k]; bi_out[k] = bi.p[k]; }
+  *n_out = bi.n;
+  next_off[0] = nx.idx; next_off[1] = nx.has_next; next_off[2] = (int64_t)nx.next;
+  free(pi.p); free(bi.p); jhm_free(&m);
+  return has;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* join driver: collect_left_input + HashJoinStream state machine                              */
 /* ------------------------------------------------------------------------------------------ */

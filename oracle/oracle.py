@@ -130,6 +130,39 @@ def hash_join_indices(build_keys: Sequence[Col], probe_keys: Sequence[Col], join
     return b, p, m, used
 
 
+def _step(fn, head_args, probe_n, limit, offset):
+    cap = max(int(limit), 1) + 8
+    pi = np.zeros(cap * 4 + probe_n + 8, np.int64); bi = np.zeros_like(pi)
+    n = C.c_int64(0)
+    off = np.array([offset[0], 0 if offset[1] is None else 1, 0 if offset[1] is None else offset[1]], np.int64)
+    nxt = np.zeros(3, np.int64)
+    has = fn(*head_args, C.c_int64(limit), off.ctypes.data_as(C.POINTER(C.c_int64)), pi.ctypes.data_as(C.POINTER(C.c_int64)),
+             bi.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(n), nxt.ctypes.data_as(C.POINTER(C.c_int64)))
+    nx = None if not has else (int(nxt[0]), int(nxt[2]) if nxt[1] else None)
+    return pi[:n.value].tolist(), bi[:n.value].tolist(), nx
+
+
+def array_map_step(build: Col, min_val: int, max_val: int, probe: Col, limit: int, offset=(0, None)):
+    """one ArrayMap::get_matched_indices_with_limit_offset call -> (probe_indices, build_indices, next MapOffset or None)"""
+    L = lib()
+    b, p = _i64(build[0]), _i64(probe[0])
+    bv, pv = _u8(build[1]), _u8(probe[1])
+    args = (b.ctypes.data_as(C.POINTER(C.c_int64)), bv.ctypes.data_as(C.POINTER(C.c_uint8)) if bv is not None else None, C.c_int64(len(b)),
+            C.c_uint64(min_val & (2**64 - 1)), C.c_uint64(max_val & (2**64 - 1)), p.ctypes.data_as(C.POINTER(C.c_int64)),
+            pv.ctypes.data_as(C.POINTER(C.c_uint8)) if pv is not None else None, C.c_int64(len(p)))
+    return _step(L.oracle_array_map_step, args, len(p), limit, offset)
+
+
+def join_hash_map_step(build_hashes, probe_hashes, valid_keys, limit: int, offset=(0, None)):
+    """one JoinHashMap::get_matched_indices_with_limit_offset call on raw hash values (build rows inserted in forward order)"""
+    L = lib()
+    b = np.ascontiguousarray(np.asarray(build_hashes, np.uint64)); p = np.ascontiguousarray(np.asarray(probe_hashes, np.uint64))
+    v = _u8(valid_keys)
+    args = (b.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_int64(len(b)), p.ctypes.data_as(C.POINTER(C.c_uint64)),
+            v.ctypes.data_as(C.POINTER(C.c_uint8)) if v is not None else None, C.c_int64(len(p)))
+    return _step(L.oracle_join_hash_map_step, args, len(p), limit, offset)
+
+
 def take(col: Col, idx: np.ndarray) -> Col:
     """arrow `take` with nullable indices (-1 -> NULL)"""
     vals, valid = col

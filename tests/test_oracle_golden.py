@@ -349,3 +349,36 @@ def test_oracle_cast_out_of_range_is_an_error():
     assert v.tolist() == [3, -3, 0] and val is None
     v, val = cast((np.array([5, 1 << 40], np.int64), np.array([True, False])), np.int32)    # the out-of-range value sits under a NULL
     assert v[0] == 5 and val.tolist() == [True, False]
+
+
+def test_oracle_array_map_replays_the_references_unit_tests():
+    """joins/array_map.rs:428-600, call by call: indices AND the resumption offsets (MapOffset) must be the reference's"""
+    i32 = lambda xs: (np.array(xs, np.int64), None)
+    # test_array_map_limit_offset_duplicate_elements
+    build, probe = i32([1, 1, 2]), i32([1, 2])
+    off, results = (0, None), []
+    while off is not None:
+        pi, bi, off = O.array_map_step(build, 1, 2, probe, 1, off)
+        results.append((pi, bi, off))
+    assert results == [([0], [0], (0, 2)), ([0], [1], (0, 0)), ([1], [2], None)]
+    # test_array_map_with_limit_and_misses
+    build, probe = i32([1, 2]), i32([10, 1, 2])
+    pi, bi, off = O.array_map_step(build, 1, 2, probe, 1)
+    assert (pi, bi, off) == ([1], [0], (2, None))
+    assert O.array_map_step(build, 1, 2, probe, 1, off) == ([2], [1], None)
+    # test_array_map_with_build_duplicates_and_misses
+    assert O.array_map_step(i32([1, 1]), 1, 1, i32([10, 1, 20, 1]), 3) == ([1, 1, 3], [0, 1, 0], (3, 2))
+    # test_array_map_rejects_large_out_of_range_probe_key (UInt64 keys; the NULL probe key never matches)
+    probe = (np.array([3, (1 << 32) + 3, 11, 0], np.int64), np.array([True, True, True, False]))
+    assert O.array_map_step(i32(list(range(11))), 0, 10, probe, 10) == ([0], [3], None)
+    # test_array_map_i64_with_negative_and_positive_numbers (min = -5 as u64, wrapping range)
+    assert O.array_map_step(i32([-5, 0, 5, -2, 3, 10]), -5, 10, i32([0, -5, 10, -1]), 10) == ([0, 1, 2], [1, 0, 5], None)
+
+
+def test_oracle_join_hash_map_replays_the_references_unit_tests():
+    """joins/join_hash_map.rs:517-575: NULL probe keys are skipped (valid_keys), chains come out newest row first"""
+    assert O.join_hash_map_step([10, 20, 30], [10, 20, 30], np.array([True, False, True]), 8192) == ([0, 2], [0, 2], None)
+    assert O.join_hash_map_step([10, 20, 10, 20], [10, 20], np.array([False, True]), 8192) == ([1, 1], [3, 1], None)
+    # test_contain_hashes, via lookups: only the inserted hashes match
+    pi, bi, _ = O.join_hash_map_step([10, 20, 30], [10, 11, 20, 21, 30, 31], None, 8192)
+    assert pi == [0, 2, 4] and bi == [0, 1, 2]
