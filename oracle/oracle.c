@@ -253,6 +253,32 @@ static int amap_lookup(const ArrayMap* a, const int64_t* key, const uint8_t* val
   return 0;
 }
 
+/* equal_rows_arr (joins/utils.rs:2191-2257): keep the candidate pairs whose key columns are equal; two NULLs are equal only under
+ * NullEqualsNull.  Filters bi / pi in place, returns the number kept. */
+static int64_t equal_rows_filter(int nkeys, const int64_t* const* bkeys, const uint8_t* const* bvalid, const int64_t* const* pk, const uint8_t* const* pv,
+                                 int null_equals_null, Vec64* bi, Vec64* pi) {
+  int64_t m = 0;
+  for (int64_t k = 0; k < bi->n; ++k) {
+    int eq = 1;
+    for (int c = 0; c < nkeys && eq; ++c) {
+      int ln = bvalid[c] && !bvalid[c][bi->p[k]], rn = pv[c] && !pv[c][pi->p[k]];
+      if (ln || rn) eq = (ln && rn && null_equals_null);
+      else eq = bkeys[c][bi->p[k]] == pk[c][pi->p[k]];
+    }
+    if (eq) { bi->p[m] = bi->p[k]; pi->p[m] = pi->p[k]; ++m; }
+  }
+  bi->n = pi->n = m;
+  return m;
+}
+O_API int64_t oracle_equal_rows(int nkeys, const int64_t* const* lkeys, const uint8_t* const* lvalid, const int64_t* const* rkeys, const uint8_t* const* rvalid,
+                                int null_equals_null, int64_t* left_idx, int64_t* right_idx, int64_t n) {
+  if (nkeys == 0) return 0;   /* "empty keys returns empty" (utils.rs test_equal_rows_arr_empty_keys_returns_empty) */
+  Vec64 bi = {left_idx, n, n}, pi = {right_idx, n, n};
+  const uint8_t* lv[8]; const uint8_t* rv[8];
+  for (int c = 0; c < nkeys; ++c) { lv[c] = lvalid ? lvalid[c] : NULL; rv[c] = rvalid ? rvalid[c] : NULL; }
+  return equal_rows_filter(nkeys, lkeys, lv, rkeys, rv, null_equals_null, &bi, &pi);
+}
+
 /* ---- step-level entry points: one get_matched_indices_with_limit_offset call, so the reference's own unit tests of the
  * maps (joins/array_map.rs:428-600, joins/join_hash_map.rs:497-575) can be replayed tuple by tuple (tests/test_oracle_golden.py).
  * off / next_off = {idx, has_next, next} of MapOffset; returns 1 when a next offset exists (Some), 0 for None. ---- */
@@ -441,18 +467,8 @@ O_API int oracle_hash_join(int nkeys, const int64_t* const* bkeys_in, const uint
       else has_next = jhm_lookup(&map, h, valid_keys, len, batch_size, off, &pi, &bi, &next_off);
       /* equal_rows_arr (utils.rs:2191-2257): drop hash-collision false positives */
       int64_t m = 0;
-      if (!use_amap) {
-        for (int64_t k = 0; k < bi.n; ++k) {
-          int eq = 1;
-          for (int c = 0; c < nkeys && eq; ++c) {
-            int ln = bvalid[c] && !bvalid[c][bi.p[k]], rn = pv[c] && !pv[c][pi.p[k]];
-            if (ln || rn) eq = (ln && rn && null_equals_null);
-            else eq = bkeys[c][bi.p[k]] == pk[c][pi.p[k]];
-          }
-          if (eq) { bi.p[m] = bi.p[k]; pi.p[m] = pi.p[k]; ++m; }
-        }
-        bi.n = pi.n = m;
-      } else m = bi.n;
+      if (!use_amap) m = equal_rows_filter(nkeys, (const int64_t* const*)bkeys, (const uint8_t* const*)bvalid, pk, pv, null_equals_null, &bi, &pi);
+      else m = bi.n;
       if (pair_filter) { /* apply_join_filter_to_indices (utils.rs:1248-1320): after the key check, before visited/adjust */
         int64_t m2 = 0;
         for (int64_t k = 0; k < m; ++k) if (pair_filter(order[bi.p[k]], pstart + pi.p[k])) { bi.p[m2] = bi.p[k]; pi.p[m2] = pi.p[k]; ++m2; }

@@ -163,6 +163,19 @@ def join_hash_map_step(build_hashes, probe_hashes, valid_keys, limit: int, offse
     return _step(L.oracle_join_hash_map_step, args, len(p), limit, offset)
 
 
+def equal_rows(left_idx, right_idx, left_keys: Sequence[Col], right_keys: Sequence[Col], null_equals_null: bool = False):
+    """equal_rows_arr (joins/utils.rs:2191-2257): filter candidate (build, probe) index pairs by key equality"""
+    L = lib()
+    L.oracle_equal_rows.restype = C.c_int64
+    li = np.ascontiguousarray(np.asarray(left_idx, np.int64)).copy(); ri = np.ascontiguousarray(np.asarray(right_idx, np.int64)).copy()
+    lk = [_i64(k[0]) for k in left_keys]; rk = [_i64(k[0]) for k in right_keys]
+    lv = [_u8(k[1]) for k in left_keys]; rv = [_u8(k[1]) for k in right_keys]
+    n = L.oracle_equal_rows(C.c_int(len(lk)), _ptr_array(lk, C.c_int64) if lk else None, _ptr_array(lv, C.c_uint8) if lk else None,
+                            _ptr_array(rk, C.c_int64) if rk else None, _ptr_array(rv, C.c_uint8) if rk else None, C.c_int(1 if null_equals_null else 0),
+                            li.ctypes.data_as(C.POINTER(C.c_int64)), ri.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int64(len(li)))
+    return li[:n].tolist(), ri[:n].tolist()
+
+
 def take(col: Col, idx: np.ndarray) -> Col:
     """arrow `take` with nullable indices (-1 -> NULL)"""
     vals, valid = col

@@ -382,3 +382,18 @@ def test_oracle_join_hash_map_replays_the_references_unit_tests():
     # test_contain_hashes, via lookups: only the inserted hashes match
     pi, bi, _ = O.join_hash_map_step([10, 20, 30], [10, 11, 20, 21, 30, 31], None, 8192)
     assert pi == [0, 2, 4] and bi == [0, 1, 2]
+
+
+def test_oracle_equal_rows_replays_the_references_unit_tests():
+    """joins/utils.rs:4625-4870 (equal_rows_arr): the collision filter between hash lookup and emission.  String key columns of the
+    reference test are dictionary-coded to integers here (a->0 .. d->3): only equality matters."""
+    i = lambda xs: col_from_list(xs, np.int64)
+    code = {"a": 0, "b": 1, "c": 2, "d": 3}
+    left = [i([1, 2, 2, 3]), i([code[x] for x in "abcd"])]; right = [i([2, 2, 3, 4]), i([code[x] for x in "bdda"])]
+    assert O.equal_rows([0, 1, 2, 3], [0, 0, 1, 2], left, right) == ([1, 3], [0, 2])                      # test_equal_rows_arr_filters_candidate_pairs
+    assert O.equal_rows([0, 1, 2], [0, 1, 2], [], []) == ([], [])                                          # ..._empty_keys_returns_empty
+    l, r = [i([1, None, 2, None])], [i([None, 1, 2, None])]
+    assert O.equal_rows([0, 1, 2, 3], [1, 0, 2, 3], l, r, null_equals_null=False) == ([0, 2], [1, 2])      # ..._respects_null_equality
+    assert O.equal_rows([0, 1, 2, 3], [1, 0, 2, 3], l, r, null_equals_null=True) == ([0, 1, 2, 3], [1, 0, 2, 3])
+    f = lambda xs: (np.array(xs, np.float64).view(np.int64), None)                                         # ..._single_float_col_uses_general_path
+    assert O.equal_rows([0, 1], [0, 1], [f([1.0, 2.0])], [f([1.0, 3.0])]) == ([0], [0])
