@@ -172,3 +172,16 @@ def test_gpu_final_accepts_the_references_skip_aggregation_states(gpu_ctx, name)
     fin2 = gpu_group_by(gpu_ctx, part, [0], [(D.AGG_COUNT, -1, -1)], mode=D.AGG_FINAL)
     o = np.argsort(fin2[0][0])
     assert fin2[0][0][o].tolist() == m["final"]["key"] and fin2[1][0][o].tolist() == m["final"]["count"]
+
+
+def test_gpu_vectorized_group_values_intern_kat(gpu_ctx):
+    """multi_group_by/mod.rs:1986-1997, 2260-2540 (VectorizedTestDataSet): three nullable key columns with every NULL / repeated /
+    already-in-map combination over three batches -> the reference's 17 groups (string columns dictionary-coded to int16)"""
+    from test_oracle_golden import group_rows, vectorized_group_values_case
+    cols, exp, sizes = vectorized_group_values_case()
+    cols = [cols[0], (cols[1][0].astype(np.int16), cols[1][1]), (cols[2][0].astype(np.int16), cols[2][1])]
+    ones = (np.ones(len(cols[0][0]), np.int64), None)
+    for batch_rows in (14, 5, None):
+        got = gpu_group_by(gpu_ctx, cols + [ones], [0, 1, 2], [(D.AGG_COUNT, 3, -1)], batch_rows=batch_rows)
+        assert group_rows(got[:3]) == exp
+        assert int(got[3][0].sum()) == sum(sizes)

@@ -397,3 +397,32 @@ def test_oracle_equal_rows_replays_the_references_unit_tests():
     assert O.equal_rows([0, 1, 2, 3], [1, 0, 2, 3], l, r, null_equals_null=True) == ([0, 1, 2, 3], [1, 0, 2, 3])
     f = lambda xs: (np.array(xs, np.float64).view(np.int64), None)                                         # ..._single_float_col_uses_general_path
     assert O.equal_rows([0, 1], [0, 1], [f([1.0, 2.0])], [f([1.0, 3.0])]) == ([0], [0])
+
+
+def vectorized_group_values_case():
+    """tests/golden/misc_kat.json vectorized_group_values_intern with the string columns dictionary-coded (only equality matters)"""
+    m = MISC["vectorized_group_values_intern"]
+    codes = {}
+
+    def code(x):
+        return None if x is None else codes.setdefault(x, len(codes) + 1)
+    cols = [col_from_list([x for b in m["batches"] for x in b["col1"]], np.int64),
+            col_from_list([code(x) for b in m["batches"] for x in b["col2"]], np.int32),
+            col_from_list([code(x) for b in m["batches"] for x in b["col3"]], np.int32)]
+    exp = sorted(zip(m["expected"]["col1"], [code(x) for x in m["expected"]["col2"]], [code(x) for x in m["expected"]["col3"]]),
+                 key=lambda r: tuple((v is None, v or 0) for v in r))
+    return cols, exp, [len(b["col1"]) for b in m["batches"]]
+
+
+def group_rows(cols):
+    rows = list(zip(*[[None if (c[1] is not None and not c[1][i]) else int(c[0][i]) for i in range(len(c[0]))] for c in cols]))
+    return sorted(rows, key=lambda r: tuple((v is None, v or 0) for v in r))
+
+
+def test_oracle_vectorized_group_values_intern_kat():
+    cols, exp, sizes = vectorized_group_values_case()
+    ones = (np.ones(len(cols[0][0]), np.int64), None)
+    for bs in (8192, 14, 5, 1):   # one intern call per 14-row batch in the reference; the grouping must not depend on the batching
+        keys, res = O.group_by(cols, [(O.A_COUNT, ones, None)], batch_size=bs)
+        assert group_rows(keys) == exp
+        assert int(res[0]["c"].sum()) == sum(sizes) and len(keys[0][0]) == 17
