@@ -72,7 +72,8 @@ _GOPS = {"eq": D.OP_EQ, "neq": D.OP_NEQ, "lt": D.OP_LT, "lteq": D.OP_LTEQ, "gt":
          "multiply": D.OP_MULTIPLY, "divide": D.OP_DIVIDE, "modulo": D.OP_MODULO, "and": D.OP_AND, "or": D.OP_OR, "is_distinct_from": D.OP_IS_DISTINCT_FROM,
          "is_not_distinct_from": D.OP_IS_NOT_DISTINCT_FROM, "bitand": D.OP_BITAND, "bitor": D.OP_BITOR, "bitxor": D.OP_BITXOR,
          "shift_left": D.OP_SHIFT_LEFT, "shift_right": D.OP_SHIFT_RIGHT}
-_GT = {"int32": D.INT32, "uint32": D.UINT32, "int64": D.INT64, "float64": D.FLOAT64, "bool": D.BOOL}
+_GT = {"int8": D.INT8, "int16": D.INT16, "int32": D.INT32, "uint32": D.UINT32, "int64": D.INT64, "float32": D.FLOAT32, "float64": D.FLOAT64, "bool": D.BOOL}
+_GUNARY = {"not": D.EXPR_NOT, "is_null": D.EXPR_IS_NULL, "is_not_null": D.EXPR_IS_NOT_NULL, "negative": D.EXPR_NEGATIVE}
 
 
 @pytest.mark.parametrize("case", EXPR_KAT, ids=[c["name"] for c in EXPR_KAT])
@@ -90,6 +91,8 @@ def test_gpu_reproduces_reference_binary_expr_tests(gpu_ctx, case):
             nodes.append((D.EXPR_LITERAL, 0, _GT[item[1]], 0, item[2], 0.0))
         elif item[0] == "cast":
             nodes.append((D.EXPR_CAST, 0, _GT[item[1]], 0, 0, 0.0))
+        elif item[0] in _GUNARY:
+            nodes.append((_GUNARY[item[0]], 0, 0, 0, 0, 0.0))
         else:
             nodes.append((D.EXPR_BINARY, _GOPS[item[1]], 0, 0, 0, 0.0))
     na = D.expr_nodes(nodes)

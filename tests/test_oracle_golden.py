@@ -213,7 +213,8 @@ def test_oracle_expressions_kat():
 
 
 EXPR_KAT = load_golden("expr_kat.json")["cases"]
-_NP = {"int32": np.int32, "uint32": np.uint32, "int64": np.int64, "float64": np.float64, "bool": bool}
+_NP = {"int8": np.int8, "int16": np.int16, "int32": np.int32, "uint32": np.uint32, "int64": np.int64, "float32": np.float32, "float64": np.float64, "bool": bool}
+_UNARY = {"not": O.E_NOT, "is_null": O.E_IS_NULL, "is_not_null": O.E_IS_NOT_NULL, "negative": O.E_NEGATIVE}
 _OPS = {"eq": O.OP_EQ, "neq": O.OP_NEQ, "lt": O.OP_LT, "lteq": O.OP_LTEQ, "gt": O.OP_GT, "gteq": O.OP_GTEQ, "plus": O.OP_PLUS, "minus": O.OP_MINUS,
         "multiply": O.OP_MULTIPLY, "divide": O.OP_DIVIDE, "modulo": O.OP_MODULO, "and": O.OP_AND, "or": O.OP_OR, "is_distinct_from": O.OP_IS_DISTINCT_FROM,
         "is_not_distinct_from": O.OP_IS_NOT_DISTINCT_FROM, "bitand": O.OP_BITAND, "bitor": O.OP_BITOR, "bitxor": O.OP_BITXOR,
@@ -245,6 +246,8 @@ def test_oracle_reproduces_reference_binary_expr_tests(case):
             nodes.append((O.E_LITERAL, 0, _NP[item[1]], 0, item[2]))
         elif item[0] == "cast":
             nodes.append((O.E_CAST, 0, _NP[item[1]], 0, 0))
+        elif item[0] in _UNARY:
+            nodes.append((_UNARY[item[0]], 0, None, 0, 0))
         else:
             nodes.append((O.E_BINARY, _OPS[item[1]], None, 0, 0))
     if "error" in case:
