@@ -313,6 +313,59 @@ def agg_output_columns(func: int, r: dict, arg_dtype, state: bool) -> List[Col]:
     raise ValueError(func)
 
 
+def partial_aggregate_with_skip(key_batches: Sequence[Sequence[Col]], arg_batches: Sequence[Col], func: int,
+                                probe_rows_threshold: int = 100_000, probe_ratio_threshold: float = 0.8):
+    """AggregateMode::Partial with the skip-partial-aggregation probe (aggregates/skip_partial.rs:69-110, the streams'
+    SkippingAggregation state, convert_batch_to_state partial_table.rs:199-238), for ONE aggregate (SUM or COUNT).
+
+    After every aggregated batch the probe adds the batch's rows and takes the current group count; once input_rows >=
+    probe_rows_threshold it decides `should_skip = groups / rows > ratio` (and keeps re-deciding on later batches until it says
+    skip).  On skip the stream emits all current groups, then every later batch is converted row by row into a state row
+    (COUNT: 1 / 0 by validity, SUM: the value).  Returns (key columns, state column) in emission order."""
+    assert func in (A_SUM, A_COUNT)
+    nk = len(key_batches[0])
+    out_keys = [[] for _ in range(nk)]; out_kvalid = [[] for _ in range(nk)]
+    out_state, out_svalid = [], []
+    rows_seen, should_skip, agg_upto = 0, False, 0
+
+    def emit_groups(upto):
+        if upto == 0:
+            return
+        keys = [(np.concatenate([np.asarray(b[c][0]) for b in key_batches[:upto]]),
+                 None if all(b[c][1] is None for b in key_batches[:upto]) else np.concatenate([np.ones(len(b[c][0]), bool) if b[c][1] is None else b[c][1] for b in key_batches[:upto]]))
+                for c in range(nk)]
+        arg = (np.concatenate([np.asarray(a[0]) for a in arg_batches[:upto]]),
+               None if all(a[1] is None for a in arg_batches[:upto]) else np.concatenate([np.ones(len(a[0]), bool) if a[1] is None else a[1] for a in arg_batches[:upto]]))
+        gk, res = group_by(keys, [(func, arg, None)])
+        for c in range(nk):
+            out_keys[c].append(np.asarray(gk[c][0])); out_kvalid[c].append(np.ones(len(gk[c][0]), bool) if gk[c][1] is None else gk[c][1])
+        st = agg_output_columns(func, res[0], np.asarray(arg[0]).dtype, True)[0]
+        out_state.append(np.asarray(st[0]).astype(np.int64)); out_svalid.append(np.ones(len(st[0]), bool) if st[1] is None else st[1])
+
+    for bi, (kb, ab) in enumerate(zip(key_batches, arg_batches)):
+        n = len(kb[0][0])
+        if should_skip:                                  # SkippingAggregation: one state row per input row
+            for c in range(nk):
+                out_keys[c].append(np.asarray(kb[c][0])); out_kvalid[c].append(np.ones(n, bool) if kb[c][1] is None else np.asarray(kb[c][1], bool))
+            valid = np.ones(n, bool) if ab[1] is None else np.asarray(ab[1], bool)
+            out_state.append(valid.astype(np.int64) if func == A_COUNT else np.asarray(ab[0]).astype(np.int64)); out_svalid.append(np.ones(n, bool) if func == A_COUNT else valid)
+            continue
+        agg_upto = bi + 1
+        rows_seen += n
+        if rows_seen >= probe_rows_threshold:
+            keys = [(np.concatenate([np.asarray(b[c][0]) for b in key_batches[:agg_upto]]), None) for c in range(nk)]
+            groups = len(group_by(keys, [])[0][0][0]) if nk else 1
+            should_skip = groups / rows_seen > probe_ratio_threshold
+            if should_skip:
+                emit_groups(agg_upto)
+    if not should_skip:
+        emit_groups(agg_upto)
+    cat = lambda xs, dt=None: np.concatenate(xs) if xs else np.zeros(0, dt or np.int64)
+    keys = [(cat(out_keys[c]), None if all(v.all() for v in out_kvalid[c]) else cat(out_kvalid[c], bool)) for c in range(nk)]
+    sv = cat(out_svalid, bool)
+    return keys, (cat(out_state), None if sv.all() else sv)
+
+
 # ---------------------------------------------------------------------------------------------
 # expressions (numpy)
 # ---------------------------------------------------------------------------------------------

@@ -429,3 +429,16 @@ def test_oracle_vectorized_group_values_intern_kat():
         keys, res = O.group_by(cols, [(O.A_COUNT, ones, None)], batch_size=bs)
         assert group_rows(keys) == exp
         assert int(res[0]["c"].sum()) == sum(sizes) and len(keys[0][0]) == 17
+
+
+@pytest.mark.parametrize("name,threshold", [("skip_aggregation_after_first_batch", 2), ("skip_aggregation_after_threshold", 5)])
+def test_oracle_reproduces_the_references_skip_partial_output(name, threshold):
+    """aggregates/mod.rs:5431-5603: with probe_rows_threshold = 2 / 5 and ratio 0.1 the reference's Partial stream emits exactly these
+    state rows in exactly this order (aggregated groups first, then one row per passed-through input row)."""
+    m = MISC[name]
+    kb = [[(np.array(b["key"], np.int32), None)] for b in m["batches"]]; ab = [(np.array(b["val"], np.int32), None) for b in m["batches"]]
+    keys, state = O.partial_aggregate_with_skip(kb, ab, O.A_COUNT, probe_rows_threshold=threshold, probe_ratio_threshold=0.1)
+    assert keys[0][0].tolist() == m["reference_partial"]["key"] and state[0].tolist() == m["reference_partial"]["count"]
+    # the default thresholds (100 000 rows, 0.8) never trigger on this input: plain aggregation
+    keys, state = O.partial_aggregate_with_skip(kb, ab, O.A_COUNT)
+    assert sorted(zip(keys[0][0].tolist(), state[0].tolist())) == sorted(zip(m["final"]["key"], m["final"]["count"]))
