@@ -509,6 +509,27 @@ def eval_expr(cols: Sequence[Col], nodes: Sequence[tuple], col_dtypes: Optional[
     return st[0]
 
 
+def coalesce_sizes(input_sizes: Sequence[int], target_batch_size: int, fetch: Optional[int] = None) -> List[int]:
+    """LimitedBatchCoalescer (physical-plan/src/coalesce/mod.rs:27-147): row counts of the completed output batches for a stream
+    of input batches — full `target_batch_size` batches while rows keep coming, the remainder at finish; `fetch` truncates the batch
+    that crosses the limit and stops the stream (PushBatchStatus::LimitReached)."""
+    out, buffered, total = [], 0, 0
+    for n in input_sizes:
+        if fetch is not None:
+            if total >= fetch:
+                break
+            n = min(n, fetch - total)
+        total += n
+        buffered += n
+        while buffered >= target_batch_size:
+            out.append(target_batch_size); buffered -= target_batch_size
+        if fetch is not None and total >= fetch:
+            break
+    if buffered:
+        out.append(buffered)
+    return out
+
+
 def filter_batch(cols: Sequence[Col], pred: Col, projection: Optional[Sequence[int]] = None) -> List[Col]:
     """filter_record_batch: keep rows whose predicate is TRUE and non-NULL (filter.rs:1339-1361)."""
     pv, pval = pred

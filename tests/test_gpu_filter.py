@@ -195,3 +195,17 @@ def test_gpu_cast_out_of_range_is_an_error(gpu_ctx):
     assert rc == 0 and v.tolist() == [3, -3, 0]
     rc, (v, val) = cast((np.array([5, 1 << 40], np.int64), np.array([True, False])), D.INT32)
     assert rc == 0 and v[0] == 5 and val.tolist() == [True, False]
+
+
+@pytest.mark.parametrize("case", MISC["limited_batch_coalescer"]["cases"], ids=[c["name"] for c in MISC["limited_batch_coalescer"]["cases"]])
+def test_gpu_filter_coalescer_reproduces_reference_batch_sizes(gpu_ctx, case):
+    """coalesce/mod.rs:156-228: FilterExec pushes its filtered batches through LimitedBatchCoalescer(batch_size, fetch); with a predicate
+    that keeps every row the output batch sizes must be the reference's (uint32 input batches of 8 / 100 rows, values 0..n)."""
+    sizes_in = case["input_sizes"]
+    assert len(set(sizes_in)) == 1
+    per = sizes_in[0]
+    vals = np.concatenate([np.arange(per, dtype=np.uint32) for _ in sizes_in])
+    nodes = [(D.EXPR_COLUMN, 0, 0, 0, 0, 0.0), (D.EXPR_LITERAL, 0, D.UINT32, 0, 0, 0.0), (D.EXPR_BINARY, D.OP_GTEQ, 0, 0, 0, 0.0)]
+    res, sizes = gpu_filter(gpu_ctx, [(vals, None)], nodes, batch_rows=per, batch_size=case["target"], fetch=-1 if case["fetch"] is None else case["fetch"])
+    assert sizes == case["expected"], case["name"]
+    assert res[0][0].tolist() == vals[:sum(case["expected"])].tolist()

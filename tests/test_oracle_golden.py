@@ -442,3 +442,8 @@ def test_oracle_reproduces_the_references_skip_partial_output(name, threshold):
     # the default thresholds (100 000 rows, 0.8) never trigger on this input: plain aggregation
     keys, state = O.partial_aggregate_with_skip(kb, ab, O.A_COUNT)
     assert sorted(zip(keys[0][0].tolist(), state[0].tolist())) == sorted(zip(m["final"]["key"], m["final"]["count"]))
+
+
+@pytest.mark.parametrize("case", MISC["limited_batch_coalescer"]["cases"], ids=[c["name"] for c in MISC["limited_batch_coalescer"]["cases"]])
+def test_oracle_limited_batch_coalescer_kat(case):
+    assert O.coalesce_sizes(case["input_sizes"], case["target"], case["fetch"]) == case["expected"]
