@@ -109,7 +109,7 @@ def run_reference(args, rank, world):
             "config": {"workload": "C2 HashJoinExec inner 100M x 10M int64, sparse unique keys, 100% hit (sample below)", "batch_size": 8192,
                        "partition_mode": "Partitioned", "target_partitions": threads},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{npr} probe x {nb} build rows per step (fraction {frac} of C2), oracle/oracle.c oracle_bench_join: RepartitionExec(Hash) both sides + per-partition JoinHashMap build/probe/take, batch_size 8192"},
+                             "sample": f"{npr} probe x {nb} build rows per step (fraction {frac} of C2), oracle/oracle.c oracle_bench_join: RepartitionExec(Hash) both sides + per-partition JoinHashMap build/probe/take, batch_size 8192; inputs and repartition buffers resident (pre-faulted) before the clock starts"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -491,7 +491,7 @@ def main():
             O.bench_join(hbk, hbp, hpk, hpp, threads=threads)
             secs, rows, _ = O.bench_join(hbk, hbp, hpk, hpp, threads=threads)
             line["cpu_baseline"] = {"value": (sb + sp) / secs, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{sp} probe x {sb} build rows (half of C2), one timed run after one warm-up; oracle_bench_join partitioned hash join on all host threads"}
+                                    "sample": f"{sp} probe x {sb} build rows (half of C2), one timed run after one warm-up; oracle_bench_join partitioned hash join on all host threads, buffers pre-faulted"}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
