@@ -447,3 +447,17 @@ def test_oracle_reproduces_the_references_skip_partial_output(name, threshold):
 @pytest.mark.parametrize("case", MISC["limited_batch_coalescer"]["cases"], ids=[c["name"] for c in MISC["limited_batch_coalescer"]["cases"]])
 def test_oracle_limited_batch_coalescer_kat(case):
     assert O.coalesce_sizes(case["input_sizes"], case["target"], case["fetch"]) == case["expected"]
+
+
+def test_oracle_join_with_hash_collisions_kat():
+    """hash_join/exec.rs:5381-5510 (join_with_hash_collisions_64 / _u32): both build rows sit under BOTH probe hashes (a hand-built
+    colliding JoinHashMap); lookup_join_hashmap's equality check must leave exactly (build 0, probe 0), (build 1, probe 1).
+    Restated with force_collisions (every hash equal), which produces the same candidate pairs."""
+    a = (np.array([10, 20], np.int64), None)
+    for bs in (8192, 1):
+        bi, pi, _, _ = O.hash_join_indices([a], [a], force_collisions=True, phj_threshold=0, phj_density=float("inf"), batch_size=bs)
+        assert bi.tolist() == [0, 1] and pi.tolist() == [0, 1]
+    # the raw-map view of the same situation: every probe hash finds the whole chain, newest row first
+    pi, bi, nx = O.join_hash_map_step([7, 7], [7, 7], None, 8192)
+    assert (pi, bi, nx) == ([0, 0, 1, 1], [1, 0, 1, 0], None)
+    assert O.equal_rows(bi, pi, [a], [a]) == ([0, 1], [0, 1]) or sorted(zip(*O.equal_rows(bi, pi, [a], [a]))) == [(0, 0), (1, 1)]
