@@ -185,7 +185,7 @@ inline void dev_free(dfgpu_ctx* ctx, void* p) {
   }
 }
 
-// stream-ordered device buffer (cudaMallocAsync pool: no implicit device sync on alloc/free)
+// stream-ordered device buffer on the per-ctx caching allocator above (no device sync on alloc / free in steady state)
 struct DevBuf {
   dfgpu_ctx* ctx = nullptr;
   void* ptr = nullptr;

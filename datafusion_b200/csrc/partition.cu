@@ -3,8 +3,8 @@
 // partition_grouped_take :1237).  On 8 GPUs this pass feeds one NCCL all-to-all; rows keep their
 // input order inside every partition (the reference's per-partition `take` is order preserving).
 //
-// round-1 implementation: partition id per row -> one flag bitmap per partition (warp ballots) ->
-// per-partition ordered index compaction into one permutation -> one gather per column.
+// Three implementations, chosen per call: packed-counter kernels for <= 8 partitions (one box), warp-match kernels for 9..32,
+// and a flag-bitmap + compaction + gather path for everything else (nullable / boolean columns, > 32 partitions).
 #include "batch.cuh"
 #include "scan.cuh"
 
