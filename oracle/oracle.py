@@ -313,6 +313,23 @@ def agg_output_columns(func: int, r: dict, arg_dtype, state: bool) -> List[Col]:
     raise ValueError(func)
 
 
+def expand_grouping_sets(keys: Sequence[Col], masks: Sequence[Sequence[bool]]):
+    """PhysicalGroupBy with grouping sets (aggregates/mod.rs:368-560 `PhysicalGroupBy { expr, null_expr, groups }`; evaluate_group_by
+    :3149-3192): every input row is evaluated once per grouping set, with the group columns the set masks out replaced by NULL and an
+    extra `__grouping_id` key (UInt8 for <= 8 group columns) whose bit (n-1-i) is set when column i is NULLed.
+    Returns (expanded key columns + the grouping-id column, number of copies)."""
+    n = len(keys[0][0])
+    nk = len(keys)
+    out = []
+    for c in range(nk):
+        vals = np.concatenate([np.asarray(keys[c][0]) for _ in masks])
+        valid = np.concatenate([(np.zeros(n, bool) if m[c] else (np.ones(n, bool) if keys[c][1] is None else np.asarray(keys[c][1], bool))) for m in masks])
+        out.append((vals, None if valid.all() else valid))
+    gid = np.concatenate([np.full(n, sum((1 << (nk - 1 - i)) for i in range(nk) if m[i]), np.uint8) for m in masks])
+    out.append((gid, None))
+    return out, len(masks)
+
+
 def partial_aggregate_with_skip(key_batches: Sequence[Sequence[Col]], arg_batches: Sequence[Col], func: int,
                                 probe_rows_threshold: int = 100_000, probe_ratio_threshold: float = 0.8):
     """AggregateMode::Partial with the skip-partial-aggregation probe (aggregates/skip_partial.rs:69-110, the streams'

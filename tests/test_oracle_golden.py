@@ -461,3 +461,27 @@ def test_oracle_join_with_hash_collisions_kat():
     pi, bi, nx = O.join_hash_map_step([7, 7], [7, 7], None, 8192)
     assert (pi, bi, nx) == ([0, 0, 1, 1], [1, 0, 1, 0], None)
     assert O.equal_rows(bi, pi, [a], [a]) == ([0, 1], [0, 1]) or sorted(zip(*O.equal_rows(bi, pi, [a], [a]))) == [(0, 0), (1, 1)]
+
+
+def grouping_sets_case():
+    m, sd = MISC["check_grouping_sets"], MISC["aggregate_some_data"]
+    a = np.concatenate([np.array(b["a"], np.uint32) for b in sd["batches"]]); b = np.concatenate([np.array(x["b"], np.float64) for x in sd["batches"]])
+    keys, copies = O.expand_grouping_sets([(a, None), (b, None)], m["masks"])
+    ones = (np.ones(len(a) * copies, np.int8), None)                       # COUNT(lit(1i8))
+    e = m["expected"]
+    exp = sorted(zip(e["a"], e["b"], e["grouping_id"], e["count"]), key=lambda r: tuple((v is None, v or 0) for v in r))
+    return keys, ones, exp
+
+
+def grouping_rows(keys, counts):
+    py = lambda c: [None if (c[1] is not None and not c[1][i]) else (float(c[0][i]) if np.asarray(c[0]).dtype.kind == "f" else int(c[0][i])) for i in range(len(c[0]))]
+    return sorted(zip(py(keys[0]), py(keys[1]), py(keys[2]), [int(x) for x in counts]), key=lambda r: tuple((v is None, v or 0) for v in r))
+
+
+def test_oracle_check_grouping_sets_kat():
+    keys, ones, exp = grouping_sets_case()
+    gk, res = O.group_by(keys, [(O.A_COUNT, ones, None)])
+    assert grouping_rows(gk, res[0]["c"]) == exp
+    # Partial -> Final over the partial states gives the same 12 rows (the test's second half)
+    fk, fres = O.group_by(gk, [(O.A_COUNT, (res[0]["c"].astype(np.int64), None), None)], merge=True)
+    assert grouping_rows(fk, fres[0]["c"]) == exp
