@@ -185,3 +185,16 @@ def test_gpu_vectorized_group_values_intern_kat(gpu_ctx):
         got = gpu_group_by(gpu_ctx, cols + [ones], [0, 1, 2], [(D.AGG_COUNT, 3, -1)], batch_rows=batch_rows)
         assert group_rows(got[:3]) == exp
         assert int(got[3][0].sum()) == sum(sizes)
+
+
+def test_gpu_check_grouping_sets_kat(gpu_ctx):
+    """aggregates/mod.rs:3428-3590 (check_grouping_sets): GROUPING SETS ((a), (b), (a,b)) are expressed through the ABI as one pass per
+    set with the masked-out group columns pushed as all-NULL columns plus the UInt8 __grouping_id key — Single, and Partial -> Final."""
+    from test_oracle_golden import grouping_rows, grouping_sets_case
+    keys, ones, exp = grouping_sets_case()
+    cols = keys + [ones]
+    got = gpu_group_by(gpu_ctx, cols, [0, 1, 2], [(D.AGG_COUNT, 3, -1)], batch_rows=8)      # one push per (set, input batch) of the reference
+    assert grouping_rows(got[:3], got[3][0]) == exp
+    part = gpu_group_by(gpu_ctx, cols, [0, 1, 2], [(D.AGG_COUNT, 3, -1)], mode=D.AGG_PARTIAL, batch_rows=8)
+    fin = gpu_group_by(gpu_ctx, part, [0, 1, 2], [(D.AGG_COUNT, -1, -1)], mode=D.AGG_FINAL)
+    assert grouping_rows(fin[:3], fin[3][0]) == exp
