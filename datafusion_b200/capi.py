@@ -28,6 +28,7 @@ NULL_EQUALS_NOTHING, NULL_EQUALS_NULL = 0, 1
 
 AGG_PARTIAL, AGG_FINAL, AGG_FINAL_PARTITIONED, AGG_SINGLE, AGG_SINGLE_PARTITIONED, AGG_PARTIAL_REDUCE = range(6)
 AGG_SUM, AGG_COUNT, AGG_MIN, AGG_MAX, AGG_AVG, AGG_COUNT_STAR = range(1, 7)
+STAGE_INNER, STAGE_SEMI, STAGE_ANTI = range(3)
 
 GEN_SEQ, GEN_UNIFORM, GEN_SPLITMIX, GEN_PERM, GEN_SPARSE_OF = range(5)
 
@@ -68,6 +69,19 @@ class AggDesc(C.Structure):
     _fields_ = [("func", C.c_int32), ("arg_col", C.c_int32), ("filter_col", C.c_int32), ("reserved", C.c_int32)]
 
 
+class LookupOptions(C.Structure):
+    _fields_ = [("expected_rows", C.c_int64), ("key_min", C.c_int64), ("key_max", C.c_int64), ("has_key_range", C.c_int32),
+                ("n_acc_words", C.c_int32), ("membership_filter", C.c_int32), ("reserved", C.c_int32)]
+
+
+class PipelineStage(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("key_col", C.c_int32), ("lookup", C.c_void_p)]
+
+
+class PipelineAgg(C.Structure):
+    _fields_ = [("func", C.c_int32), ("n_nodes", C.c_int32), ("expr", C.c_void_p)]
+
+
 class ArrowSchema(C.Structure):
     pass
 
@@ -105,6 +119,10 @@ EXPORTS = [
     "dfgpu_partition_plan_create", "dfgpu_partition_plan_scatter_peer", "dfgpu_partition_plan_create_chunked",
     "dfgpu_partition_plan_scatter_peer_chunk", "dfgpu_partition_plan_destroy",
     "dfgpu_ipc_export", "dfgpu_ipc_import", "dfgpu_ipc_close",
+    "dfgpu_lookup_default_options", "dfgpu_lookup_create", "dfgpu_lookup_metric", "dfgpu_lookup_destroy", "dfgpu_column_minmax_device",
+    "dfgpu_pipeline_create", "dfgpu_pipeline_sink_build", "dfgpu_pipeline_sink_aggregate", "dfgpu_pipeline_sink_output",
+    "dfgpu_pipeline_push_host", "dfgpu_pipeline_push_device", "dfgpu_pipeline_push_arrow", "dfgpu_pipeline_finish",
+    "dfgpu_pipeline_next", "dfgpu_pipeline_metric", "dfgpu_pipeline_destroy",
 ]
 
 _lib = None
@@ -188,6 +206,22 @@ def load_library() -> C.CDLL:
     sig("dfgpu_ipc_export", C.c_int, [vp, vp, C.c_char_p])
     sig("dfgpu_ipc_import", C.c_int, [vp, C.c_char_p, P(vp)])
     sig("dfgpu_ipc_close", C.c_int, [vp, vp])
+    sig("dfgpu_lookup_default_options", None, [P(LookupOptions)])
+    sig("dfgpu_lookup_create", C.c_int, [vp, i32, P(i32), i32, P(LookupOptions), P(vp)])
+    sig("dfgpu_lookup_metric", i64, [vp, C.c_char_p])
+    sig("dfgpu_lookup_destroy", None, [vp])
+    sig("dfgpu_column_minmax_device", C.c_int, [vp, P(Column), P(i64), P(i64), P(i64)])
+    sig("dfgpu_pipeline_create", C.c_int, [vp, P(i32), i32, P(ExprNode), i32, P(PipelineStage), i32, P(vp)])
+    sig("dfgpu_pipeline_sink_build", C.c_int, [vp, vp, i32, P(i32), i32])
+    sig("dfgpu_pipeline_sink_aggregate", C.c_int, [vp, P(i32), i32, P(PipelineAgg), i32, i32, i64])
+    sig("dfgpu_pipeline_sink_output", C.c_int, [vp, P(i32), i32, i64])
+    sig("dfgpu_pipeline_push_host", C.c_int, [vp, P(Column), i32])
+    sig("dfgpu_pipeline_push_device", C.c_int, [vp, P(Column), i32])
+    sig("dfgpu_pipeline_push_arrow", C.c_int, [vp, vp, vp])
+    sig("dfgpu_pipeline_finish", C.c_int, [vp])
+    sig("dfgpu_pipeline_next", C.c_int, [vp, C.c_int, P(vp)])
+    sig("dfgpu_pipeline_metric", i64, [vp, C.c_char_p])
+    sig("dfgpu_pipeline_destroy", None, [vp])
     _lib = lib
     return lib
 
@@ -614,3 +648,81 @@ def hash_partition_device(ctx: Context, cols, key_cols, n_parts: int):
     offs = (C.c_int64 * (n_parts + 1))()
     ctx.check(ctx.lib.dfgpu_hash_partition_device(ctx.h, arr, len(cols), _i32arr(key_cols), len(key_cols), n_parts, C.byref(out), offs))
     return Batch(ctx, out.value), list(offs)
+
+
+def column_minmax_device(ctx: Context, col) -> tuple:
+    """(min, max, non-null count) of an integer column resident in HBM — the bounds collect_left_input tracks (exec.rs:2585-2619)"""
+    c = col.c() if not isinstance(col, Column) else col
+    mn, mx, cnt = C.c_int64(), C.c_int64(), C.c_int64()
+    ctx.check(ctx.lib.dfgpu_column_minmax_device(ctx.h, C.byref(c), C.byref(mn), C.byref(mx), C.byref(cnt)))
+    return mn.value, mx.value, cnt.value
+
+
+class Lookup:
+    """dfgpu_lookup: the build side of a fused join (unique keys, <= 64 bits of payload, optional accumulator words)"""
+
+    def __init__(self, ctx: Context, key_type: int, payload_types=(), expected_rows: int = 0, key_range=None, n_acc_words: int = 0,
+                 membership_filter: int = -1):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        opt = LookupOptions()
+        ctx.lib.dfgpu_lookup_default_options(C.byref(opt))
+        opt.expected_rows, opt.n_acc_words, opt.membership_filter = int(expected_rows), int(n_acc_words), int(membership_filter)
+        if key_range is not None:
+            opt.has_key_range, opt.key_min, opt.key_max = 1, int(key_range[0]), int(key_range[1])
+        ctx.check(ctx.lib.dfgpu_lookup_create(ctx.h, key_type, _i32arr(list(payload_types)), len(payload_types), C.byref(opt), C.byref(self.h)))
+
+    def metric(self, name: str) -> int:
+        return self.ctx.lib.dfgpu_lookup_metric(self.h, name.encode())
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.dfgpu_lookup_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Pipeline(_Operator):
+    """dfgpu_pipeline: predicate -> probe stage(s) -> sink, one pass.  stages: [(kind, key_col, Lookup)]"""
+    _next_fn, _destroy_fn, _metric_fn = "dfgpu_pipeline_next", "dfgpu_pipeline_destroy", "dfgpu_pipeline_metric"
+
+    def __init__(self, ctx, input_types, predicate=None, stages=()):
+        super().__init__(ctx)
+        self._keep = [st[2] for st in stages]
+        na = expr_nodes(predicate) if predicate else None
+        sa = (PipelineStage * max(len(stages), 1))()
+        for i, (kind, key_col, lk) in enumerate(stages):
+            sa[i].kind, sa[i].key_col, sa[i].lookup = kind, key_col, lk.h
+        ctx.check(ctx.lib.dfgpu_pipeline_create(ctx.h, _i32arr(input_types), len(input_types), na, len(predicate) if predicate else 0,
+                                                sa, len(stages), C.byref(self.h)))
+
+    def sink_build(self, target: Lookup, key_col: int, payload_cols=()):
+        self._keep.append(target)
+        self.ctx.check(self.ctx.lib.dfgpu_pipeline_sink_build(self.h, target.h, key_col, _i32arr(list(payload_cols)), len(payload_cols)))
+
+    def sink_aggregate(self, group_cols, aggs, mode=AGG_SINGLE, batch_size=0):
+        """aggs: [(func, nodes or None)]"""
+        arr = (PipelineAgg * max(len(aggs), 1))()
+        self._agg_nodes = []
+        for i, (f, nodes) in enumerate(aggs):
+            arr[i].func = f
+            if nodes:
+                na = expr_nodes(nodes)
+                self._agg_nodes.append(na)
+                arr[i].n_nodes, arr[i].expr = len(nodes), C.addressof(na)
+            else:
+                arr[i].n_nodes, arr[i].expr = 0, None
+        self.ctx.check(self.ctx.lib.dfgpu_pipeline_sink_aggregate(self.h, _i32arr(list(group_cols)), len(group_cols), arr, len(aggs), mode, batch_size))
+
+    def sink_output(self, out_cols, batch_size=0):
+        self.ctx.check(self.ctx.lib.dfgpu_pipeline_sink_output(self.h, _i32arr(list(out_cols)), len(out_cols), batch_size))
+
+    def push_host(self, cols): self._push("dfgpu_pipeline_push_host", cols)
+    def push_device(self, cols): self._push("dfgpu_pipeline_push_device", cols)
+    def push_arrow(self, rb): self._push_arrow("dfgpu_pipeline_push_arrow", rb)
+    def finish(self): self.ctx.check(self.ctx.lib.dfgpu_pipeline_finish(self.h))

@@ -1984,6 +1984,9 @@ int dfgpu_hashjoin_set_filter(dfgpu_hashjoin* j, const int32_t* col_side, const 
 int dfgpu_hashjoin_push_build_host(dfgpu_hashjoin* j, const dfgpu_column* cols, int32_t n_cols) {
   DF_API_BEGIN(j ? j->ctx : nullptr)
   push_build(j, host_cols_to_device(j->ctx, cols, n_cols));
+  // the caller owns the host buffers only until this call returns (dfgpu.h): pinned sources are copied asynchronously,
+  // so the H2D copies must have completed before we hand the buffers back
+  DF_CUDA(cudaStreamSynchronize(j->ctx->stream));
   DF_API_END
 }
 int dfgpu_hashjoin_push_build_device(dfgpu_hashjoin* j, const dfgpu_column* cols, int32_t n_cols) {

@@ -291,6 +291,14 @@ def peer_chunk_layout(m, rank: int):
     return dst_row, chunk_start[:, rank].copy(), per_chunk[:, rank].copy(), int(per_chunk.sum(axis=0).max())
 
 
+def _check_distributed_join(join_kwargs, supported, who):
+    jt = join_kwargs.get("join_type", D.JOIN_INNER)
+    if jt not in supported:
+        raise D.DfgpuError(-3, f"{who}: join type {jt} needs a visited bitmap shared by all probe partitions; not supported across GPUs")
+    if join_kwargs.get("null_aware"):
+        raise D.DfgpuError(-3, f"{who}: null-aware anti joins need global NULL flags; not supported across GPUs")
+
+
 class PartitionedHashJoin:
     """PartitionMode::Partitioned hash join over the GPUs of one box (hash_join/exec.rs:1312-1325 + the two
     RepartitionExec(Hash) inputs, repartition/mod.rs:1097-1145), with the exchange fused into the pipeline:
@@ -307,6 +315,9 @@ class PartitionedHashJoin:
     def __init__(self, device: int, dist, build_types, probe_types, on_build, on_probe, out_side, out_index,
                  cap_build_rows: int, cap_probe_rows: int, n_chunks: int = 4, **join_kwargs):
         import torch
+        # co-partitioned inputs: every key lives on exactly one rank, so every join type is rank-local — except null-aware
+        # anti joins, whose probe_has_null / build-NULL flags are global and which the reference only plans as CollectLeft
+        _check_distributed_join(join_kwargs, tuple(range(10)), "PartitionedHashJoin")
         self.torch, self.dist = torch, dist
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
         self.xs, self.js = torch.cuda.Stream(device), torch.cuda.Stream(device)
@@ -557,7 +568,13 @@ class BroadcastHashJoin:
     """PartitionMode::CollectLeft across GPUs (hash_join/exec.rs:1326-1336): the (small) build side is replicated on
     every GPU with one all-gather per column, the probe side stays where it is — no probe-side exchange at all."""
 
+    # join types whose output depends only on (replicated build table, local probe rows): safe with a per-rank replica.
+    # Left / Full / LeftSemi / LeftAnti / LeftMark emit build rows from ONE visited bitmap shared by all probe partitions
+    # (exec.rs:206/274 report_probe_completed, stream.rs:1026): a per-rank replica would emit them once per rank.
+    SUPPORTED = (D.JOIN_INNER, D.JOIN_RIGHT, D.JOIN_RIGHT_SEMI, D.JOIN_RIGHT_ANTI, D.JOIN_RIGHT_MARK)
+
     def __init__(self, ctx: D.Context, dist, build_types, probe_types, on_build, on_probe, out_side, out_index, **join_kwargs):
+        _check_distributed_join(join_kwargs, self.SUPPORTED, "BroadcastHashJoin")
         self.ctx, self.dist = ctx, dist
         self.args = (list(build_types), list(probe_types), list(on_build), list(on_probe), list(out_side), list(out_index))
         self.join_kwargs = join_kwargs

@@ -20,6 +20,10 @@
  *     independent (each ctx owns one CUDA stream) — the threading contract of
  *     `ExecutionPlan::execute(partition, ..)` (execution_plan.rs:696).
  *   - outputs are library-owned until dfgpu_batch_release.
+ *   - input lifetime: HOST buffers (`*_host`, `*_arrow`) belong to the caller again as soon as the call returns (the
+ *     library has finished its H2D copies by then, also from pinned memory).  DEVICE inputs (`*_device`) are read on
+ *     the ctx stream: they must be complete in that stream's order (or on the legacy stream) and stay unmodified until
+ *     the next call on the same handle that synchronises — dfgpu_sync, finish_*, next — returns.
  */
 #ifndef DFGPU_H
 #define DFGPU_H
@@ -319,6 +323,84 @@ int dfgpu_agg_finish(dfgpu_agg* a);
 int dfgpu_agg_next(dfgpu_agg* a, int host, dfgpu_batch** out);
 int64_t dfgpu_agg_metric(dfgpu_agg* a, const char* name); /* "num_groups","input_rows","output_rows","table_capacity","rehashes" */
 void dfgpu_agg_destroy(dfgpu_agg* a);
+
+/* ===================================================================================== */
+/* Fused pipeline: FilterExec -> HashJoinExec probe side(s) -> sink, ONE pass over HBM.
+ *
+ * The reference streams 8192-row batches FilterExec (filter.rs:1364-1445) -> HashJoinStream::process_probe_batch
+ * (hash_join/stream.rs:740) -> AggregateHashTable::aggregate_batch_inner (aggregate_hash_table/common.rs:205-236) so
+ * intermediates stay in cache.  The GPU analogue is one kernel per pipeline (the operators between two pipeline
+ * breakers): every input row is read once, filtered, probed and either inserted into the next join's build table,
+ * aggregated, or emitted — no intermediate batch round-trips HBM.  A physical-optimizer rule replaces
+ *   AggregateExec(HashJoinExec(build, FilterExec(scan)))   /   HashJoinExec build side = HashJoinExec(RightSemi ..)
+ * by these handles where the shapes below apply and keeps the unfused Gpu*Exec operators (DFGPU_ERR_UNSUPPORTED) otherwise.
+ *
+ * dfgpu_lookup  = the build side of a fused join: unique keys (<= 64 bits), <= 64 bits of payload columns, optional
+ *                 membership filter (the GPU form of dynamic filter pushdown: PartitionBounds + hash-table membership,
+ *                 joins/hash_join/shared_bounds.rs, partitioned_hash_eval.rs, join_hash_map.rs:486 contain_hashes) and
+ *                 optional accumulator words per record for an aggregation whose group keys are functionally
+ *                 determined by the join key (group id == build row).
+ * dfgpu_pipeline= source batch -> predicate -> probe stage(s) -> sink.
+ * "virtual columns" of a pipeline: the input columns [0, n_cols) followed by the payload fields of every INNER
+ * stage in stage order; expressions, group columns, build payloads and outputs address this space. */
+/* ===================================================================================== */
+typedef struct dfgpu_lookup dfgpu_lookup;
+typedef struct dfgpu_pipeline dfgpu_pipeline;
+
+typedef struct dfgpu_lookup_options {
+  int64_t expected_rows;   /* 0 = unknown: the first build push counts its survivors first; the table grows by rehash */
+  int64_t key_min, key_max;/* valid when has_key_range (column statistics, or dfgpu_column_minmax_device — the bounds
+                            * collect_left_input tracks, exec.rs:2585-2619) */
+  int32_t has_key_range;
+  int32_t n_acc_words;     /* 8-byte accumulator words reserved in every record for a downstream fused aggregation */
+  int32_t membership_filter; /* 1 = build a blocked Bloom filter next to the table, 0 = never, -1 = when the table exceeds L2 */
+  int32_t reserved;
+} dfgpu_lookup_options;
+void dfgpu_lookup_default_options(dfgpu_lookup_options* o);
+/* payload_types: the non-key build columns carried by a match (<= 64 bits together, no NULLs); none = key set only
+ * (semi / anti joins; duplicates allowed).  Dense key ranges without payload become a bitmap (the reference's
+ * ArrayMap idea, exec.rs:111-191, at one bit per key). */
+int dfgpu_lookup_create(dfgpu_ctx* ctx, int32_t key_type, const int32_t* payload_types, int32_t n_payload,
+                        const dfgpu_lookup_options* opts, dfgpu_lookup** out);
+int64_t dfgpu_lookup_metric(dfgpu_lookup* l, const char* name); /* "rows","capacity","mode"(0 hash,1 bitmap),"table_bytes","filter_bytes","rehashes" */
+void dfgpu_lookup_destroy(dfgpu_lookup* l);
+/* min / max / non-null count of one integer column (device resident): feeds dfgpu_lookup_options.key_min/key_max */
+int dfgpu_column_minmax_device(dfgpu_ctx* ctx, const dfgpu_column* col, int64_t* min_out, int64_t* max_out, int64_t* valid_out);
+
+enum dfgpu_stage_kind { DFGPU_STAGE_INNER = 0, DFGPU_STAGE_SEMI = 1, DFGPU_STAGE_ANTI = 2 };
+typedef struct dfgpu_pipeline_stage {
+  int32_t kind;          /* dfgpu_stage_kind: the pipeline input is the PROBE (right) side — Inner / RightSemi / RightAnti */
+  int32_t key_col;       /* input column holding the probe key (NULL keys never match, utils.rs:2146-2155) */
+  dfgpu_lookup* lookup;  /* must be completely built before the first push */
+} dfgpu_pipeline_stage;
+typedef struct dfgpu_pipeline_agg {
+  int32_t func;                 /* dfgpu_agg_func */
+  int32_t n_nodes;              /* argument expression over the virtual columns (RPN); 0 for COUNT(*) */
+  const dfgpu_expr_node* expr;
+} dfgpu_pipeline_agg;
+
+/* predicate: Boolean RPN over the INPUT columns, or NULL (no FilterExec below the probe) */
+int dfgpu_pipeline_create(dfgpu_ctx* ctx, const int32_t* input_types, int32_t n_cols,
+                          const dfgpu_expr_node* predicate, int32_t n_pred_nodes,
+                          const dfgpu_pipeline_stage* stages, int32_t n_stages, dfgpu_pipeline** out);
+/* exactly one sink, chosen before the first push:
+ *  build     : surviving rows become records of `target` (key = virtual column key_col, payload = payload_cols in
+ *              the order of the lookup's payload_types) — the pipeline IS the build side of the next join;
+ *  aggregate : AggregateExec over the surviving rows; group_cols must be the probe key of one INNER stage plus payload
+ *              fields of that stage (group id == build row; anything else -> DFGPU_ERR_UNSUPPORTED, use dfgpu_agg);
+ *              mode = DFGPU_AGG_SINGLE* or DFGPU_AGG_PARTIAL (state columns as dfgpu_agg emits them);
+ *  output    : surviving rows, columns = out_cols of the virtual schema, input order preserved. */
+int dfgpu_pipeline_sink_build(dfgpu_pipeline* p, dfgpu_lookup* target, int32_t key_col, const int32_t* payload_cols, int32_t n_payload);
+int dfgpu_pipeline_sink_aggregate(dfgpu_pipeline* p, const int32_t* group_cols, int32_t n_group,
+                                  const dfgpu_pipeline_agg* aggs, int32_t n_aggs, int32_t mode, int64_t batch_size);
+int dfgpu_pipeline_sink_output(dfgpu_pipeline* p, const int32_t* out_cols, int32_t n_out, int64_t batch_size);
+int dfgpu_pipeline_push_host(dfgpu_pipeline* p, const dfgpu_column* cols, int32_t n_cols);    /* H2D inside, overlapped with the kernel in row chunks */
+int dfgpu_pipeline_push_device(dfgpu_pipeline* p, const dfgpu_column* cols, int32_t n_cols);
+int dfgpu_pipeline_push_arrow(dfgpu_pipeline* p, const struct ArrowArray* batch, const struct ArrowSchema* schema);
+int dfgpu_pipeline_finish(dfgpu_pipeline* p);
+int dfgpu_pipeline_next(dfgpu_pipeline* p, int host, dfgpu_batch** out);
+int64_t dfgpu_pipeline_metric(dfgpu_pipeline* p, const char* name); /* "input_rows","sink_rows","output_rows","num_groups" */
+void dfgpu_pipeline_destroy(dfgpu_pipeline* p);
 
 /* ===================================================================================== */
 /* output batches                                                                        */

@@ -122,6 +122,52 @@ def run_q3(ctx, customer, orders, lineitem):
     return res, stages
 
 
+def run_q3_fused(ctx, customer, orders, lineitem):
+    """the same plan as three fused pipelines (dfgpu_pipeline): every table is read once, no intermediate batch touches HBM
+
+        P1  customer : FilterExec(c_mktsegment = 1)                      -> build L1 = key set {c_custkey}   (dense range -> bitmap)
+        P2  orders   : FilterExec(o_orderdate < CUT) -> RightSemi vs L1  -> build L2 = {o_orderkey -> (o_orderdate, o_shippriority)}
+        P3  lineitem : FilterExec(l_shipdate > CUT)  -> Inner vs L2      -> AggregateExec gby [l_orderkey, o_orderdate, o_shippriority]
+                                                                            SUM(l_extendedprice * (100 - l_discount))
+    The group keys are the join key plus build-side columns, so the group id is the build row and the sums live in L2's records."""
+    stages = {}
+    kmin, kmax, _ = D.column_minmax_device(ctx, customer.cols[0])       # the bounds collect_left_input tracks (exec.rs:2585-2619)
+    l1 = D.Lookup(ctx, D.INT64, [], key_range=(kmin, kmax))
+    p1 = D.Pipeline(ctx, customer.types, B(D.OP_EQ, C(1), L(1)))
+    p1.sink_build(l1, 0, [])
+    p1.push_device(customer.cols); p1.finish()
+    stages["customer_building"] = p1.metric("sink_rows")
+    p1.close()
+    l2 = D.Lookup(ctx, D.INT64, [D.INT32, D.INT32], n_acc_words=2, membership_filter=-1)
+    p2 = D.Pipeline(ctx, orders.types, B(D.OP_LT, C(2), L(CUT, D.INT32)), [(D.STAGE_SEMI, 1, l1)])
+    p2.sink_build(l2, 0, [2, 3])
+    p2.push_device(orders.cols); p2.finish()
+    stages["orders_of_building_customers"] = p2.metric("sink_rows")
+    p2.close()
+    p3 = D.Pipeline(ctx, lineitem.types, B(D.OP_GT, C(3), L(CUT, D.INT32)), [(D.STAGE_INNER, 0, l2)])
+    p3.sink_aggregate([0, 4, 5], [(D.AGG_SUM, B(D.OP_MULTIPLY, C(1), B(D.OP_MINUS, L(100), C(2))))], D.AGG_SINGLE_PARTITIONED)
+    p3.push_device(lineitem.cols); p3.finish()
+    res = p3.drain(host=False)
+    stages["joined_rows"] = p3.metric("sink_rows")
+    stages["groups"] = p3.metric("num_groups")
+    stages["lookup_bytes"] = l2.metric("table_bytes"); stages["filter_bytes"] = l2.metric("filter_bytes")
+    p3.close(); l2.close(); l1.close()
+    return res, stages
+
+
+def result_fingerprint(ctx, res):
+    """order-independent fingerprint of the result rows (row count, wrapping sums of every column) — the same formula the CPU
+    arm's oracle_bench_q3 returns"""
+    n, sums = 0, [0, 0, 0, 0]
+    for b in res:
+        n += b.num_rows
+        for i in range(4):
+            cc = b.column(i)
+            a = ctx.to_host(cc.values, b.num_rows * D.WIDTH[cc.type]).view(D.NP_OF_TYPE[cc.type])
+            sums[i] = (sums[i] + int(a.astype(np.int64).view(np.uint64).sum(dtype=np.uint64))) & (2**64 - 1)
+    return [n] + sums
+
+
 def q3_expected(c, o, l):
     """independent numpy / pandas evaluation on the downloaded tables"""
     import pandas as pd

@@ -20,3 +20,21 @@ def test_q3_device_pipeline_matches_pandas(gpu_ctx, sf):
     assert got == exp
     for b in res:
         b.release()
+
+
+@pytest.mark.parametrize("sf", [0.01, 0.3])
+def test_q3_fused_pipelines_match_pandas_and_unfused(gpu_ctx, sf):
+    """the three fused pipelines (dfgpu_pipeline) give the rows of the operator-by-operator path and of pandas, bit-exact"""
+    import q3_device_pipeline as Q
+    customer, orders, lineitem = Q.gen_tables(gpu_ctx, sf)
+    res, stages = Q.run_q3_fused(gpu_ctx, customer, orders, lineitem)
+    got = Q.result_rows(gpu_ctx, res)
+    ref, rstages = Q.run_q3(gpu_ctx, customer, orders, lineitem)
+    assert Q.result_fingerprint(gpu_ctx, res) == Q.result_fingerprint(gpu_ctx, ref)
+    for k in ("customer_building", "orders_of_building_customers", "joined_rows", "groups"):
+        assert stages[k] == rstages[k], k
+    exp = Q.q3_expected(customer.host(gpu_ctx), orders.host(gpu_ctx), lineitem.host(gpu_ctx))
+    assert stages["groups"] == len(exp) > 0
+    assert got == exp
+    for b in res + ref:
+        b.release()
