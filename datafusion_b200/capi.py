@@ -119,7 +119,7 @@ EXPORTS = [
     "dfgpu_partition_plan_create", "dfgpu_partition_plan_scatter_peer", "dfgpu_partition_plan_create_chunked",
     "dfgpu_partition_plan_scatter_peer_chunk", "dfgpu_partition_plan_destroy",
     "dfgpu_ipc_export", "dfgpu_ipc_import", "dfgpu_ipc_close",
-    "dfgpu_lookup_default_options", "dfgpu_lookup_create", "dfgpu_lookup_metric", "dfgpu_lookup_destroy", "dfgpu_column_minmax_device",
+    "dfgpu_lookup_default_options", "dfgpu_lookup_create", "dfgpu_lookup_metric", "dfgpu_lookup_destroy", "dfgpu_column_minmax_device", "dfgpu_column_sum_device",
     "dfgpu_pipeline_create", "dfgpu_pipeline_sink_build", "dfgpu_pipeline_sink_aggregate", "dfgpu_pipeline_sink_output",
     "dfgpu_pipeline_push_host", "dfgpu_pipeline_push_device", "dfgpu_pipeline_push_arrow", "dfgpu_pipeline_finish",
     "dfgpu_pipeline_next", "dfgpu_pipeline_metric", "dfgpu_pipeline_destroy",
@@ -211,6 +211,7 @@ def load_library() -> C.CDLL:
     sig("dfgpu_lookup_metric", i64, [vp, C.c_char_p])
     sig("dfgpu_lookup_destroy", None, [vp])
     sig("dfgpu_column_minmax_device", C.c_int, [vp, P(Column), P(i64), P(i64), P(i64)])
+    sig("dfgpu_column_sum_device", C.c_int, [vp, P(Column), P(u64), P(i64)])
     sig("dfgpu_pipeline_create", C.c_int, [vp, P(i32), i32, P(ExprNode), i32, P(PipelineStage), i32, P(vp)])
     sig("dfgpu_pipeline_sink_build", C.c_int, [vp, vp, i32, P(i32), i32])
     sig("dfgpu_pipeline_sink_aggregate", C.c_int, [vp, P(i32), i32, P(PipelineAgg), i32, i32, i64])
@@ -656,6 +657,14 @@ def column_minmax_device(ctx: Context, col) -> tuple:
     mn, mx, cnt = C.c_int64(), C.c_int64(), C.c_int64()
     ctx.check(ctx.lib.dfgpu_column_minmax_device(ctx.h, C.byref(c), C.byref(mn), C.byref(mx), C.byref(cnt)))
     return mn.value, mx.value, cnt.value
+
+
+def column_sum_device(ctx: Context, col) -> int:
+    """wrapping (mod 2^64) sum of the non-NULL values of an integer column resident in HBM"""
+    c = col.c() if not isinstance(col, Column) else col
+    s, cnt = C.c_uint64(), C.c_int64()
+    ctx.check(ctx.lib.dfgpu_column_sum_device(ctx.h, C.byref(c), C.byref(s), C.byref(cnt)))
+    return s.value
 
 
 class Lookup:

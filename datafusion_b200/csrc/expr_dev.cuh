@@ -245,6 +245,61 @@ __device__ __forceinline__ uint64_t eval_nodes(const ENode* __restrict__ nodes, 
   *ok_out = sk[0];
   return sv[0];
 }
+// Register-resident variant for shallow programs (stack depth <= DEPTH): every stack slot is addressed through fully
+// unrolled selects, so the stack never leaves the register file (the indexed arrays of eval_nodes live in local memory,
+// which costs an L1 round trip per push / pop and — in divergent consumers — real L2 / DRAM traffic).
+template <int DEPTH>
+__device__ __forceinline__ uint64_t eval_nodes_reg(const ENode* __restrict__ nodes, int n_nodes, int64_t row, bool* ok_out, int* err, const uint64_t* ext = nullptr) {
+  uint64_t sv[DEPTH];
+  bool sk[DEPTH];
+#pragma unroll
+  for (int d = 0; d < DEPTH; ++d) { sv[d] = 0; sk[d] = false; }
+  int sp = 0;
+#define DF_PUSH(V, K) do { const uint64_t _v = (V); const bool _k = (K); _Pragma("unroll") for (int d = 0; d < DEPTH; ++d) if (d == sp) { sv[d] = _v; sk[d] = _k; } ++sp; } while (0)
+#define DF_GET(I, V, K) do { _Pragma("unroll") for (int d = 0; d < DEPTH; ++d) if (d == (I)) { V = sv[d]; K = sk[d]; } } while (0)
+#define DF_SET(I, V, K) do { const uint64_t _v = (V); const bool _k = (K); _Pragma("unroll") for (int d = 0; d < DEPTH; ++d) if (d == (I)) { sv[d] = _v; sk[d] = _k; } } while (0)
+#pragma unroll 1
+  for (int i = 0; i < n_nodes; ++i) {
+    const ENode& nd = nodes[i];
+    if (nd.kind == DFGPU_EXPR_COLUMN) {
+      DF_PUSH(load_col_value(nd, row), !(nd.valid && !bit_get(nd.valid, nd.voff + row)));
+    } else if (nd.kind == DFGPU_EXPR_LITERAL) {
+      DF_PUSH(nd.lit, !nd.lit_null);
+    } else if (nd.kind == kExprExt) {
+      uint64_t v = ext[nd.voff] >> (int)nd.lit;
+      const int w = type_width(nd.out_type);
+      if (w < 8) { v &= (1ull << (8 * w)) - 1ull; if (type_is_signed_int(nd.out_type)) v = (uint64_t)(((int64_t)(v << (64 - 8 * w))) >> (64 - 8 * w)); }
+      if (nd.out_type == DFGPU_FLOAT32) { float f = __uint_as_float((uint32_t)v); v = (uint64_t)__double_as_longlong((double)f); }
+      DF_PUSH(v, true);
+    } else if (nd.kind == DFGPU_EXPR_BINARY) {
+      uint64_t a = 0, b = 0, r; bool ak = false, bk = false, ok;
+      DF_GET(sp - 2, a, ak); DF_GET(sp - 1, b, bk);
+      eval_binary(nd, a, ak, b, bk, &r, &ok, err);
+      sp -= 1;
+      DF_SET(sp - 1, r, ok);
+    } else {
+      uint64_t a = 0; bool ak = false;
+      DF_GET(sp - 1, a, ak);
+      switch (nd.kind) {
+        case DFGPU_EXPR_NOT: a = a ? 0 : 1; break;  // NULL stays NULL
+        case DFGPU_EXPR_IS_NULL: a = ak ? 0 : 1; ak = true; break;
+        case DFGPU_EXPR_IS_NOT_NULL: a = ak ? 1 : 0; ak = true; break;
+        case DFGPU_EXPR_NEGATIVE:
+          if (cls_of(nd.out_type) == C_F64) a ^= 0x8000000000000000ull;
+          else a = wrap_to_type(0ull - a, nd.out_type);  // neg_wrapping
+          break;
+        case DFGPU_EXPR_CAST: a = cast_value(a, nd.in_type, nd.out_type, ak, err); break;
+      }
+      DF_SET(sp - 1, a, ak);
+    }
+  }
+#undef DF_PUSH
+#undef DF_GET
+#undef DF_SET
+  *ok_out = sk[0];
+  return sv[0];
+}
+
 __device__ __forceinline__ uint64_t eval_row(const EProgram& p, int64_t row, bool* ok_out, int* err) { return eval_nodes(p.node, p.n, row, ok_out, err); }
 
 }  // namespace dfgpu

@@ -46,13 +46,13 @@ struct LookupDev {
   unsigned long long* bloom; uint64_t bloom_blocks;
   uint32_t* bits; uint64_t kmin, ksize;
 };
-struct ColRef { const void* ptr; const uint8_t* valid; int64_t voff; int width, sgn; };
+struct ColRef { const void* ptr; const uint8_t* valid; int64_t voff; int width, sgn, vec /* base pointer 16-byte aligned: 128-bit loads allowed */, pad; };
 struct StageDev { int kind, key_col; LookupDev lk; };
 struct ExtDef { int stage, shift, width, type; };
-struct AggDef { int func, cls, word, nn_word, start, n; };
+struct AggDef { int func, cls, word, nn_word, start, n, small, pad; };
 struct PipeParams {
-  int n_cols; ColRef col[kMaxPipeCols];
-  int pred_mode /* 0 none, 1 conjunction of col <cmp> literal, 2 interpreter */, n_terms, pred_start, pred_n;
+  int n_cols, hints; ColRef col[kMaxPipeCols];
+  int pred_mode /* 0 none, 1 conjunction of col <cmp> literal, 2 interpreter */, n_terms, pred_start, pred_n, pred_small, first_hash /* first stage backed by a hash table, -1 = none */;
   int term_col[kMaxTerms], term_op[kMaxTerms], term_uns[kMaxTerms]; long long term_lit[kMaxTerms];
   int n_stages; StageDev stage[kMaxStages];
   int n_ext; ExtDef ext[kMaxExt];
@@ -65,6 +65,7 @@ struct PipeParams {
 
 // ---- cache-policy loads: the table scan is read-once (evict first), the lookup structures should stay in L2 ----
 __device__ __forceinline__ uint64_t policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint64_t policy_normal() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); return p; }
 __device__ __forceinline__ uint64_t policy_evict_last() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
 __device__ __forceinline__ uint64_t ld_stream_int(const void* base, int width, int sgn, int64_t row, uint64_t pol) {
   switch (width) {
@@ -88,9 +89,11 @@ __device__ __forceinline__ Rec128 rec_cas128(void* addr, Rec128 cmp, Rec128 val)
 
 __device__ __forceinline__ uint64_t lk_hash(uint64_t key) { return hash_u64(key, kSeedJoin); }
 __device__ __forceinline__ void bloom_pos(uint64_t h, uint64_t blocks, uint64_t* block, unsigned long long* mask) {
-  const uint64_t h2 = h * 0x9E3779B97F4A7C15ull;   // decorrelate from the fastrange slot (which consumes the top bits of h)
-  *block = __umul64hi(h2, blocks);
-  *mask = (1ull << (h2 & 63)) | (1ull << ((h2 >> 6) & 63)) | (1ull << ((h2 >> 12) & 63)) | (1ull << ((h2 >> 18) & 63));
+  // block from the top 32 hash bits (a 32-bit fastrange: the table slot uses the same bits, so a key's filter block and its
+  // record are neighbours in their structures — harmless), the four probe bits from the low 24 bits
+  *block = ((h >> 32) * (blocks & 0xFFFFFFFFull)) >> 32;
+  const uint32_t l = (uint32_t)h;
+  *mask = (1ull << (l & 63)) | (1ull << ((l >> 6) & 63)) | (1ull << ((l >> 12) & 63)) | (1ull << ((l >> 18) & 63));
 }
 
 // insert one record; returns 0 inserted, 1 duplicate key, 2 cannot store this key
@@ -137,208 +140,333 @@ __device__ __forceinline__ void red_f64_min(unsigned long long* p, double v, boo
 }
 
 // ------------------------------------------------------------------------------------------
-// the pipeline kernel.  Persistent blocks walk 1024-row tiles; a thread owns rows tile*1024 + k*256 + tid (k < 4) so
-// every column load of a warp is one coalesced wavefront, and the loads of the four rows are issued back to back
-// (memory-level parallelism) before any is consumed.
+// the pipeline kernel.  Every WARP runs the pipeline on its own 256-row tiles, in two phases, with no block barrier:
+//   phase A (every row, cheap, coalesced): a lane owns 8 consecutive rows and reads them with 128-bit loads (a warp request
+//     is 512 contiguous bytes per instruction); it evaluates the predicate, the bitmap stages and the Bloom pre-test of the
+//     hash stages, and appends the survivors (row, first hash key) to the warp's queue in shared memory;
+//   phase B (survivors only, dense): whenever the queue holds >= 128 entries every lane takes four of them — all lanes busy,
+//     four table lookups in flight per lane — resolves the hash stages and feeds the sink (record insert / accumulator RED).
+// Without the queue the expensive tail (a DRAM lookup, the argument interpreter, an insert CAS) runs at warp granularity for
+// the few live lanes of every warp: that cost 27 warp-instructions and 143 B of DRAM traffic per row on Q3's lineitem pass.
 // ------------------------------------------------------------------------------------------
+constexpr int kWarpRows = 8, kWarpTile = 32 * kWarpRows, kPhaseB = 4, kPhaseBGroup = 32 * kPhaseB, kQueueCap = kPhaseBGroup + kWarpTile;
+constexpr int kPipeWarps = kPipeThreads / 32;
+
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) { asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void red_add_f64(unsigned long long* p, double v) { asm volatile("red.global.add.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ void red_min_s64(unsigned long long* p, long long v) { asm volatile("red.global.min.s64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void red_max_s64(unsigned long long* p, long long v) { asm volatile("red.global.max.s64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void red_min_u64(unsigned long long* p, unsigned long long v) { asm volatile("red.global.min.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void red_max_u64(unsigned long long* p, unsigned long long v) { asm volatile("red.global.max.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+
+// one out-of-line copy of each interpreter: the kernel stays small enough for the instruction cache
+__device__ __noinline__ uint64_t pipe_eval(const ENode* nodes, int n, int small, int64_t row, const uint64_t* ext, int* err_ok /* [0]=err bits (or-ed), [1]=valid */) {
+  bool ok;
+  int err = 0;
+  const uint64_t v = small ? eval_nodes_reg<4>(nodes, n, row, &ok, &err, ext) : eval_nodes(nodes, n, row, &ok, &err, ext);
+  err_ok[0] |= err; err_ok[1] = ok ? 1 : 0;
+  return v;
+}
+
+__device__ __forceinline__ uint4 ld_stream_v4(const void* p, uint64_t pol) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ uint2 ld_stream_v2(const void* p, uint64_t pol) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ uint64_t ext32(uint32_t x, int sgn) { return sgn ? (uint64_t)(int64_t)(int32_t)x : (uint64_t)x; }
+__device__ __forceinline__ uint64_t ext16(uint32_t x, int sgn) { return sgn ? (uint64_t)(int64_t)(int16_t)x : (uint64_t)(x & 0xFFFFu); }
+__device__ __forceinline__ uint64_t ext8(uint32_t x, int sgn) { return sgn ? (uint64_t)(int64_t)(int8_t)x : (uint64_t)(x & 0xFFu); }
+// 8 consecutive elements starting at row0 (a multiple of 8), sign / zero extended to 64 bits
+__device__ __forceinline__ void load8(const ColRef& c, int64_t row0, int64_t n, uint64_t v[kWarpRows], uint64_t pol) {
+  if (c.vec && row0 + kWarpRows <= n) {
+    switch (c.width) {
+      case 8: {
+        const char* p = (const char*)c.ptr + row0 * 8;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const uint4 x = ld_stream_v4(p + 16 * q, pol); v[2 * q] = (uint64_t)x.x | ((uint64_t)x.y << 32); v[2 * q + 1] = (uint64_t)x.z | ((uint64_t)x.w << 32); }
+        break;
+      }
+      case 4: {
+        const char* p = (const char*)c.ptr + row0 * 4;
+        const uint4 x = ld_stream_v4(p, pol), y = ld_stream_v4(p + 16, pol);
+        v[0] = ext32(x.x, c.sgn); v[1] = ext32(x.y, c.sgn); v[2] = ext32(x.z, c.sgn); v[3] = ext32(x.w, c.sgn);
+        v[4] = ext32(y.x, c.sgn); v[5] = ext32(y.y, c.sgn); v[6] = ext32(y.z, c.sgn); v[7] = ext32(y.w, c.sgn);
+        break;
+      }
+      case 2: {
+        const uint4 x = ld_stream_v4((const char*)c.ptr + row0 * 2, pol);
+        v[0] = ext16(x.x, c.sgn); v[1] = ext16(x.x >> 16, c.sgn); v[2] = ext16(x.y, c.sgn); v[3] = ext16(x.y >> 16, c.sgn);
+        v[4] = ext16(x.z, c.sgn); v[5] = ext16(x.z >> 16, c.sgn); v[6] = ext16(x.w, c.sgn); v[7] = ext16(x.w >> 16, c.sgn);
+        break;
+      }
+      default: {
+        const uint2 x = ld_stream_v2((const char*)c.ptr + row0, pol);
+        v[0] = ext8(x.x, c.sgn); v[1] = ext8(x.x >> 8, c.sgn); v[2] = ext8(x.x >> 16, c.sgn); v[3] = ext8(x.x >> 24, c.sgn);
+        v[4] = ext8(x.y, c.sgn); v[5] = ext8(x.y >> 8, c.sgn); v[6] = ext8(x.y >> 16, c.sgn); v[7] = ext8(x.y >> 24, c.sgn);
+        break;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kWarpRows; ++j) v[j] = row0 + j < n ? ld_stream_int(c.ptr, c.width, c.sgn, row0 + j, pol) : 0ull;
+  }
+}
+// validity bits of the same 8 rows (bit j = row0 + j is non-NULL)
+__device__ __forceinline__ uint32_t valid8(const ColRef& c, int64_t row0, int64_t n) {
+  if (!c.valid) return 0xFFu;
+  const int nb = (int)min((int64_t)kWarpRows, n - row0);
+  return nb > 0 ? load_bits32(c.valid, c.voff + row0, nb) : 0u;
+}
+
 template <int SINK>
 __global__ void __launch_bounds__(kPipeThreads) pipe_kernel(const PipeParams* __restrict__ gp, int64_t n, unsigned long long* __restrict__ counters /* [alive, inserted, fail, err] */) {
   __shared__ PipeParams sp;
+  __shared__ uint32_t q_rows[kPipeWarps][kQueueCap];
+  __shared__ unsigned long long q_keys[kPipeWarps][kQueueCap];
   for (int i = threadIdx.x; i < (int)(sizeof(PipeParams) / 4); i += kPipeThreads) ((uint32_t*)&sp)[i] = ((const uint32_t*)gp)[i];
   __syncthreads();
-  const uint64_t pol_stream = policy_evict_first();
-  const uint64_t pol_keep = policy_evict_last();
+  const uint64_t pol_stream = (sp.hints & 1) ? policy_evict_first() : policy_normal();
+  const uint64_t pol_keep = (sp.hints & 2) ? policy_evict_last() : policy_normal();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint32_t* q_row = q_rows[wib];
+  unsigned long long* q_key = q_keys[wib];
   unsigned int alive_cnt = 0, ins_cnt = 0;
-  int err = 0, fail = 0;
-  const int64_t ntiles = (n + kPipeTile - 1) / kPipeTile;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t base = tile * kPipeTile + threadIdx.x;
-    bool alive[kPipeItems];
+  int err_ok[2] = {0, 0};
+  int fail = 0;
+  unsigned int qn = 0;   // queue length (warp-uniform)
+  const int64_t ntiles = (n + kWarpTile - 1) / kWarpTile;
+  const int64_t gwarp = (int64_t)blockIdx.x * kPipeWarps + wib, nwarps = (int64_t)gridDim.x * kPipeWarps;
+  for (int64_t tile = gwarp; tile < ntiles + nwarps; tile += nwarps) {   // one extra trip per warp drains its queue
+    const bool draining = tile >= ntiles;
+    if (!draining) {
+      // =============================== phase A ===============================
+      const int64_t row0 = tile * kWarpTile + (int64_t)lane * kWarpRows;
+      uint32_t mask = row0 + kWarpRows <= n ? 0xFFu : (row0 < n ? (1u << (int)(n - row0)) - 1u : 0u);
+      uint64_t key0[kWarpRows];
 #pragma unroll
-    for (int k = 0; k < kPipeItems; ++k) alive[k] = base + k * kPipeThreads < n;
-    // ---- FilterExec ----
-    if (sp.pred_mode == 1) {
+      for (int j = 0; j < kWarpRows; ++j) key0[j] = 0;
+      if (sp.pred_mode == 1) {   // FilterExec, conjunction of `column <cmp> literal`
 #pragma unroll 1
-      for (int t = 0; t < sp.n_terms; ++t) {
-        const ColRef c = sp.col[sp.term_col[t]];
-        uint64_t v[kPipeItems];
+        for (int t = 0; t < sp.n_terms; ++t) {
+          const ColRef c = sp.col[sp.term_col[t]];
+          uint64_t v[kWarpRows];
+          load8(c, row0, n, v, pol_stream);
+          mask &= valid8(c, row0, n);            // a NULL predicate drops the row
+          const int op = sp.term_op[t];
+          const long long lit = sp.term_lit[t];
+          uint32_t lt = 0, eq = 0;
+          if (sp.term_uns[t]) {
 #pragma unroll
-        for (int k = 0; k < kPipeItems; ++k) v[k] = alive[k] ? ld_stream_int(c.ptr, c.width, c.sgn, base + k * kPipeThreads, pol_stream) : 0ull;
-        const int op = sp.term_op[t];
-        const long long lit = sp.term_lit[t];
+            for (int j = 0; j < kWarpRows; ++j) { lt |= (uint32_t)(v[j] < (uint64_t)lit) << j; eq |= (uint32_t)(v[j] == (uint64_t)lit) << j; }
+          } else {
 #pragma unroll
-        for (int k = 0; k < kPipeItems; ++k) {
-          if (!alive[k]) continue;
-          if (c.valid && !bit_get(c.valid, c.voff + base + k * kPipeThreads)) { alive[k] = false; continue; }   // NULL predicate drops the row
-          int cmp;
-          if (sp.term_uns[t]) cmp = v[k] < (uint64_t)lit ? -1 : (v[k] > (uint64_t)lit ? 1 : 0);
-          else cmp = (long long)v[k] < lit ? -1 : ((long long)v[k] > lit ? 1 : 0);
-          bool r;
+            for (int j = 0; j < kWarpRows; ++j) { lt |= (uint32_t)((long long)v[j] < lit) << j; eq |= (uint32_t)((long long)v[j] == lit) << j; }
+          }
+          uint32_t r;
           switch (op) {
-            case DFGPU_OP_EQ: r = cmp == 0; break;
-            case DFGPU_OP_NEQ: r = cmp != 0; break;
-            case DFGPU_OP_LT: r = cmp < 0; break;
-            case DFGPU_OP_LTEQ: r = cmp <= 0; break;
-            case DFGPU_OP_GT: r = cmp > 0; break;
-            default: r = cmp >= 0; break;
+            case DFGPU_OP_EQ: r = eq; break;
+            case DFGPU_OP_NEQ: r = ~eq; break;
+            case DFGPU_OP_LT: r = lt; break;
+            case DFGPU_OP_LTEQ: r = lt | eq; break;
+            case DFGPU_OP_GT: r = ~(lt | eq); break;
+            default: r = ~lt; break;
           }
-          alive[k] = r;
+          mask &= r;
         }
-      }
-    } else if (sp.pred_mode == 2) {
+      } else if (sp.pred_mode == 2) {   // FilterExec, general expression
 #pragma unroll 1
-      for (int k = 0; k < kPipeItems; ++k) {
-        if (!alive[k]) continue;
-        bool ok;
-        const uint64_t val = eval_nodes(sp.pool + sp.pred_start, sp.pred_n, base + k * kPipeThreads, &ok, &err);
-        alive[k] = ok && (val & 1);
+        for (int j = 0; j < kWarpRows; ++j) {
+          if (!((mask >> j) & 1u)) continue;
+          const uint64_t val = pipe_eval(sp.pool + sp.pred_start, sp.pred_n, sp.pred_small, row0 + j, nullptr, err_ok);
+          if (!(err_ok[1] && (val & 1))) mask &= ~(1u << j);
+        }
       }
+      // bitmap stages decide here; hash stages get their Bloom pre-test (the pushed-down membership filter)
+#pragma unroll
+      for (int s = 0; s < kMaxStages; ++s) {
+        if (s >= sp.n_stages) continue;
+        const StageDev& st = sp.stage[s];
+        const bool bitmap = st.lk.mode == LK_BITMAP;
+        if (!bitmap && s != sp.first_hash && !(st.lk.bloom && st.kind != DFGPU_STAGE_ANTI)) continue;   // nothing cheap to do for this stage
+        if (!__any_sync(0xffffffffu, mask != 0)) continue;
+        const ColRef kc = sp.col[st.key_col];
+        uint64_t key[kWarpRows];
+        load8(kc, row0, n, key, pol_stream);
+        const uint32_t kvalid = valid8(kc, row0, n);
+        if (bitmap) {
+          uint32_t w[kWarpRows];
+#pragma unroll
+          for (int j = 0; j < kWarpRows; ++j) {
+            const uint64_t i = key[j] - st.lk.kmin;
+            w[j] = (((mask & kvalid) >> j) & 1u) && i < st.lk.ksize ? __ldg(&st.lk.bits[i >> 5]) : 0u;
+          }
+          uint32_t found = 0;
+#pragma unroll
+          for (int j = 0; j < kWarpRows; ++j) found |= ((w[j] >> ((key[j] - st.lk.kmin) & 31)) & 1u) << j;   // NULL keys never match (w = 0)
+          mask &= st.kind == DFGPU_STAGE_ANTI ? ~found : found;
+        } else {
+          if (s == sp.first_hash) {
+#pragma unroll
+            for (int j = 0; j < kWarpRows; ++j) key0[j] = key[j];
+          }
+          if (st.kind != DFGPU_STAGE_ANTI) {
+            mask &= kvalid;                      // NULL keys never match
+            if (st.lk.bloom) {
+              unsigned long long bw[kWarpRows], bm[kWarpRows];
+#pragma unroll
+              for (int j = 0; j < kWarpRows; ++j) {
+                uint64_t b; bloom_pos(lk_hash(key[j]), st.lk.bloom_blocks, &b, &bm[j]);
+                bw[j] = ((mask >> j) & 1u) ? ld_keep_u64(&st.lk.bloom[b], pol_keep) : 0ull;
+              }
+              uint32_t pass = 0;
+#pragma unroll
+              for (int j = 0; j < kWarpRows; ++j) pass |= (uint32_t)((bw[j] & bm[j]) == bm[j]) << j;
+              mask &= pass;
+            }
+          }
+        }
+      }
+      // append the survivors to the warp's queue (exclusive scan of the per-lane counts)
+      const unsigned int cnt = __popc(mask);
+      unsigned int incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+      unsigned int pos = qn + incl - cnt;
+#pragma unroll
+      for (int j = 0; j < kWarpRows; ++j)
+        if ((mask >> j) & 1u) { q_row[pos] = (uint32_t)(row0 + j); q_key[pos] = key0[j]; ++pos; }
+      qn += __shfl_sync(0xffffffffu, incl, 31);
+      __syncwarp();
     }
-    // ---- HashJoinExec probe side(s) ----
-    uint64_t pay[kMaxStages][kPipeItems];
-    unsigned long long* arec[kPipeItems];
+    // =============================== phase B ===============================
+    while (qn >= (unsigned)kPhaseBGroup || (draining && qn > 0)) {
+      const unsigned int take = qn >= (unsigned)kPhaseBGroup ? (unsigned)kPhaseBGroup : qn;
+      const unsigned int qbase = qn - take;   // consume from the tail: nothing has to move
+      bool live[kPhaseB];
+      int64_t row[kPhaseB];
+      uint64_t pay[kMaxStages][kPhaseB];
+      unsigned long long* arec[kPhaseB];
 #pragma unroll
-    for (int k = 0; k < kPipeItems; ++k) arec[k] = nullptr;
-#pragma unroll
-    for (int s = 0; s < kMaxStages; ++s) {
-#pragma unroll
-      for (int k = 0; k < kPipeItems; ++k) pay[s][k] = 0;
-      if (s >= sp.n_stages) continue;
-      const StageDev& st = sp.stage[s];
-      const ColRef kc = sp.col[st.key_col];
-      uint64_t key[kPipeItems];
-      bool live[kPipeItems], found[kPipeItems];
-#pragma unroll
-      for (int k = 0; k < kPipeItems; ++k) {
-        live[k] = alive[k]; found[k] = false; key[k] = 0;
-        if (live[k]) {
-          key[k] = ld_stream_int(kc.ptr, kc.width, kc.sgn, base + k * kPipeThreads, pol_stream);
-          if (kc.valid && !bit_get(kc.valid, kc.voff + base + k * kPipeThreads)) live[k] = false;   // NULL keys never match
-        }
-      }
-      if (st.lk.mode == LK_BITMAP) {
-        uint32_t w[kPipeItems];
-#pragma unroll
-        for (int k = 0; k < kPipeItems; ++k) {
-          const uint64_t i = key[k] - st.lk.kmin;
-          w[k] = (live[k] && i < st.lk.ksize) ? __ldg(&st.lk.bits[i >> 5]) : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < kPipeItems; ++k) found[k] = live[k] && ((w[k] >> ((key[k] - st.lk.kmin) & 31)) & 1u);
-      } else {
-        uint64_t h[kPipeItems];
-#pragma unroll
-        for (int k = 0; k < kPipeItems; ++k) { h[k] = lk_hash(key[k]); if (key[k] == kEmptyKey) live[k] = false; }
-        if (st.lk.bloom) {   // membership filter first: an L2-resident 8-byte probe instead of a DRAM miss for rows without a partner
-          unsigned long long bw[kPipeItems], bm[kPipeItems];
-#pragma unroll
-          for (int k = 0; k < kPipeItems; ++k) {
-            uint64_t b; bloom_pos(h[k], st.lk.bloom_blocks, &b, &bm[k]);
-            bw[k] = live[k] ? ld_keep_u64(&st.lk.bloom[b], pol_keep) : 0ull;
-          }
-#pragma unroll
-          for (int k = 0; k < kPipeItems; ++k) live[k] = live[k] && ((bw[k] & bm[k]) == bm[k]);
-        }
-        uint64_t slot[kPipeItems], ck[kPipeItems], cp[kPipeItems];
-#pragma unroll
-        for (int k = 0; k < kPipeItems; ++k) {
-          slot[k] = __umul64hi(h[k], st.lk.cap); ck[k] = kEmptyKey; cp[k] = 0;
-          if (live[k]) {
-            const unsigned long long* r = st.lk.recs + slot[k] * (uint64_t)st.lk.stride;
-            if (st.lk.has_payload) { const uint4 v = __ldcg((const uint4*)r); ck[k] = (uint64_t)v.x | ((uint64_t)v.y << 32); cp[k] = (uint64_t)v.z | ((uint64_t)v.w << 32); }
-            else ck[k] = __ldcg(r);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < kPipeItems; ++k) {
-          if (!live[k]) continue;
-          while (true) {   // linear probing continues only past a foreign key (load factor <= 0.5)
-            if (ck[k] == key[k]) { found[k] = true; break; }
-            if (ck[k] == kEmptyKey) break;
-            if (++slot[k] == st.lk.cap) slot[k] = 0;
-            const unsigned long long* r = st.lk.recs + slot[k] * (uint64_t)st.lk.stride;
-            if (st.lk.has_payload) { const uint4 v = __ldcg((const uint4*)r); ck[k] = (uint64_t)v.x | ((uint64_t)v.y << 32); cp[k] = (uint64_t)v.z | ((uint64_t)v.w << 32); }
-            else ck[k] = __ldcg(r);
-          }
-          if (found[k]) { pay[s][k] = cp[k]; if (SINK == SINK_AGG && s == sp.agg_stage) arec[k] = st.lk.recs + slot[k] * (uint64_t)st.lk.stride; }
-        }
+      for (int u = 0; u < kPhaseB; ++u) {
+        const unsigned int e = u * 32 + lane;
+        live[u] = e < take; row[u] = live[u] ? (int64_t)q_row[qbase + e] : 0; arec[u] = nullptr;
       }
 #pragma unroll
-      for (int k = 0; k < kPipeItems; ++k) alive[k] = alive[k] && (st.kind == DFGPU_STAGE_ANTI ? !found[k] : found[k]);
-    }
-    // ---- sink ----
+      for (int s = 0; s < kMaxStages; ++s) {
 #pragma unroll
-    for (int k = 0; k < kPipeItems; ++k) {
-      if (!alive[k]) continue;
-      const int64_t row = base + k * kPipeThreads;
-      alive_cnt++;
-      if (SINK == SINK_BUILD) {
-        const ColRef kc = sp.col[sp.bkey_col];
-        if (kc.valid && !bit_get(kc.valid, kc.voff + row)) continue;   // NULL build keys are not inserted (utils.rs:2146-2155)
-        const uint64_t key = ld_stream_int(kc.ptr, kc.width, kc.sgn, row, pol_stream);
-        uint64_t p = 0;
-        for (int c = 0; c < sp.n_bpay; ++c) {
-          const int src = sp.bpay_src[c];
-          uint64_t v;
-          if (src < sp.n_cols) v = ld_stream_int(sp.col[src].ptr, sp.col[src].width, 0, row, pol_stream);
-          else { const ExtDef e = sp.ext[src - sp.n_cols]; uint64_t w = 0;
+        for (int u = 0; u < kPhaseB; ++u) pay[s][u] = 0;
+        if (s >= sp.n_stages) continue;
+        const StageDev& st = sp.stage[s];
+        if (st.lk.mode == LK_BITMAP) continue;   // decided in phase A
+        const ColRef kc = sp.col[st.key_col];
+        uint64_t key[kPhaseB], slot[kPhaseB], ck[kPhaseB], cp[kPhaseB];
+        bool look[kPhaseB], found[kPhaseB];
 #pragma unroll
-                 for (int s = 0; s < kMaxStages; ++s) if (s == e.stage) w = pay[s][k];
-                 v = ext_field(w, e.shift, e.width, DFGPU_UINT64); }
-          if (sp.bpay_width[c] < 8) v &= (1ull << (8 * sp.bpay_width[c])) - 1ull;
-          p |= v << sp.bpay_shift[c];
+        for (int u = 0; u < kPhaseB; ++u) {
+          found[u] = false; look[u] = live[u]; key[u] = 0;
+          if (look[u]) {
+            key[u] = s == sp.first_hash ? q_key[qbase + u * 32 + lane] : ld_stream_int(kc.ptr, kc.width, kc.sgn, row[u], pol_stream);
+            if ((kc.valid && !bit_get(kc.valid, kc.voff + row[u])) || key[u] == kEmptyKey) look[u] = false;   // NULL keys never match
+          }
+          slot[u] = __umul64hi(lk_hash(key[u]), st.lk.cap); ck[u] = kEmptyKey; cp[u] = 0;
+          if (look[u]) {
+            const unsigned long long* r = st.lk.recs + slot[u] * (uint64_t)st.lk.stride;
+            if (st.lk.has_payload) { const uint4 v = __ldcg((const uint4*)r); ck[u] = (uint64_t)v.x | ((uint64_t)v.y << 32); cp[u] = (uint64_t)v.z | ((uint64_t)v.w << 32); }
+            else ck[u] = __ldcg(r);
+          }
         }
-        const int rc = lk_insert(sp.target, key, p);
-        if (rc == 0) ins_cnt++;
-        else if (rc == 2 || sp.target_unique) fail |= rc;
-      } else if (SINK == SINK_AGG) {
-        unsigned long long* rec = arec[k];
+#pragma unroll
+        for (int u = 0; u < kPhaseB; ++u) {
+          if (look[u]) {
+            while (true) {   // linear probing continues only past a foreign key (load factor <= 0.5)
+              if (ck[u] == key[u]) { found[u] = true; break; }
+              if (ck[u] == kEmptyKey) break;
+              if (++slot[u] == st.lk.cap) slot[u] = 0;
+              const unsigned long long* r = st.lk.recs + slot[u] * (uint64_t)st.lk.stride;
+              if (st.lk.has_payload) { const uint4 v = __ldcg((const uint4*)r); ck[u] = (uint64_t)v.x | ((uint64_t)v.y << 32); cp[u] = (uint64_t)v.z | ((uint64_t)v.w << 32); }
+              else ck[u] = __ldcg(r);
+            }
+            if (found[u]) { pay[s][u] = cp[u]; if (SINK == SINK_AGG && s == sp.agg_stage) arec[u] = st.lk.recs + slot[u] * (uint64_t)st.lk.stride; }
+          }
+          live[u] = live[u] && (st.kind == DFGPU_STAGE_ANTI ? !found[u] : found[u]);
+        }
+      }
+      // ---- sink ----
+#pragma unroll
+      for (int u = 0; u < kPhaseB; ++u) {
         uint64_t ext[kMaxStages];
 #pragma unroll
-        for (int s = 0; s < kMaxStages; ++s) ext[s] = pay[s][k];
-        atomicAdd(rec + sp.rows_word, 1ull);
-        for (int a = 0; a < sp.n_aggs; ++a) {
-          const AggDef ag = sp.agg[a];
-          if (ag.func == DFGPU_AGG_COUNT_STAR) continue;   // = the row counter
-          bool ok;
-          const uint64_t v = eval_nodes(sp.pool + ag.start, ag.n, row, &ok, &err, ext);
-          if (!ok) continue;                               // NULL inputs are skipped (accumulate.rs:373-470)
-          if (ag.nn_word >= 0) atomicAdd(rec + ag.nn_word, 1ull);
-          switch (ag.func) {
-            case DFGPU_AGG_COUNT: atomicAdd(rec + ag.word, 1ull); break;
-            case DFGPU_AGG_SUM: case DFGPU_AGG_AVG:
-              if (ag.cls == C_F64) atomicAdd((double*)(rec + ag.word), __longlong_as_double((long long)v));
-              else atomicAdd(rec + ag.word, (unsigned long long)v);   // add_wrapping (sum.rs:316)
-              break;
-            case DFGPU_AGG_MIN:
-              if (ag.cls == C_F64) red_f64_min(rec + ag.word, __longlong_as_double((long long)v), false);
-              else if (ag.cls == C_U64) atomicMin(rec + ag.word, (unsigned long long)v);
-              else atomicMin((long long*)(rec + ag.word), (long long)v);
-              break;
-            case DFGPU_AGG_MAX:
-              if (ag.cls == C_F64) red_f64_min(rec + ag.word, __longlong_as_double((long long)v), true);
-              else if (ag.cls == C_U64) atomicMax(rec + ag.word, (unsigned long long)v);
-              else atomicMax((long long*)(rec + ag.word), (long long)v);
-              break;
+        for (int s = 0; s < kMaxStages; ++s) ext[s] = pay[s][u];
+        if (!live[u]) continue;
+        alive_cnt++;
+        if (SINK == SINK_BUILD) {
+          const ColRef kc = sp.col[sp.bkey_col];
+          if (kc.valid && !bit_get(kc.valid, kc.voff + row[u])) continue;   // NULL build keys are not inserted (utils.rs:2146-2155)
+          const uint64_t key = ld_stream_int(kc.ptr, kc.width, kc.sgn, row[u], pol_stream);
+          uint64_t p = 0;
+          for (int c = 0; c < sp.n_bpay; ++c) {
+            const int src = sp.bpay_src[c];
+            uint64_t v;
+            if (src < sp.n_cols) v = ld_stream_int(sp.col[src].ptr, sp.col[src].width, 0, row[u], pol_stream);
+            else { const ExtDef e = sp.ext[src - sp.n_cols]; v = ext_field(ext[e.stage], e.shift, e.width, DFGPU_UINT64); }
+            if (sp.bpay_width[c] < 8) v &= (1ull << (8 * sp.bpay_width[c])) - 1ull;
+            p |= v << sp.bpay_shift[c];
+          }
+          const int rc = lk_insert(sp.target, key, p);
+          if (rc == 0) ins_cnt++;
+          else if (rc == 2 || sp.target_unique) fail |= rc;
+        } else if (SINK == SINK_AGG) {
+          unsigned long long* rec = arec[u];
+          red_add_u64(rec + sp.rows_word, 1ull);
+          for (int a = 0; a < sp.n_aggs; ++a) {
+            const AggDef ag = sp.agg[a];
+            if (ag.func == DFGPU_AGG_COUNT_STAR) continue;   // = the row counter
+            const uint64_t v = pipe_eval(sp.pool + ag.start, ag.n, ag.small, row[u], ext, err_ok);
+            if (!err_ok[1]) continue;                        // NULL inputs are skipped (accumulate.rs:373-470)
+            if (ag.nn_word >= 0) red_add_u64(rec + ag.nn_word, 1ull);
+            switch (ag.func) {
+              case DFGPU_AGG_COUNT: red_add_u64(rec + ag.word, 1ull); break;
+              case DFGPU_AGG_SUM: case DFGPU_AGG_AVG:
+                if (ag.cls == C_F64) red_add_f64(rec + ag.word, __longlong_as_double((long long)v));
+                else red_add_u64(rec + ag.word, (unsigned long long)v);   // add_wrapping (sum.rs:316)
+                break;
+              case DFGPU_AGG_MIN:
+                if (ag.cls == C_F64) red_f64_min(rec + ag.word, __longlong_as_double((long long)v), false);
+                else if (ag.cls == C_U64) red_min_u64(rec + ag.word, (unsigned long long)v);
+                else red_min_s64(rec + ag.word, (long long)v);
+                break;
+              case DFGPU_AGG_MAX:
+                if (ag.cls == C_F64) red_f64_min(rec + ag.word, __longlong_as_double((long long)v), true);
+                else if (ag.cls == C_U64) red_max_u64(rec + ag.word, (unsigned long long)v);
+                else red_max_s64(rec + ag.word, (long long)v);
+                break;
+            }
           }
         }
       }
+      qn = qbase;
+      __syncwarp();
     }
   }
   // block-level counter reduction: one atomic per block and counter
-  __shared__ unsigned int s_red[2][kPipeThreads / 32];
+  __shared__ unsigned int s_red[2][kPipeWarps];
   __shared__ int s_flag[2];
   if (threadIdx.x == 0) { s_flag[0] = 0; s_flag[1] = 0; }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) { alive_cnt += __shfl_xor_sync(0xffffffffu, alive_cnt, d); ins_cnt += __shfl_xor_sync(0xffffffffu, ins_cnt, d); }
   __syncthreads();
-  if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = alive_cnt; s_red[1][threadIdx.x >> 5] = ins_cnt; }
+  if (lane == 0) { s_red[0][wib] = alive_cnt; s_red[1][wib] = ins_cnt; }
   if (fail) atomicOr(&s_flag[0], fail);
-  if (err) atomicOr(&s_flag[1], err);
+  if (err_ok[0]) atomicOr(&s_flag[1], err_ok[0]);
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long a = 0, b = 0;
-    for (int w = 0; w < kPipeThreads / 32; ++w) { a += s_red[0][w]; b += s_red[1][w]; }
+    for (int w = 0; w < kPipeWarps; ++w) { a += s_red[0][w]; b += s_red[1][w]; }
     if (a) atomicAdd(&counters[0], a);
     if (b) atomicAdd(&counters[1], b);
     if (s_flag[0]) atomicOr(&counters[2], (unsigned long long)s_flag[0]);
@@ -572,6 +700,24 @@ __global__ void __launch_bounds__(256) col_minmax_kernel(ColRef c, int64_t n, in
   if ((threadIdx.x & 31) == 0 && cnt) { atomicMin(&mm[0], kmin); atomicMax(&mm[1], kmax); atomicAdd(&mm[2], cnt); }
 }
 
+// wrapping sum of an integer column (sign / zero extended to 64 bits): order-independent fingerprints of large results
+__global__ void __launch_bounds__(256) col_sum_kernel(ColRef c, int64_t n, unsigned long long* out /* [sum, valid] */) {
+  unsigned long long s = 0, cnt = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (c.valid && !bit_get(c.valid, c.voff + i)) continue;
+    switch (c.width) {
+      case 1: s += c.sgn ? (uint64_t)(int64_t)((const int8_t*)c.ptr)[i] : ((const uint8_t*)c.ptr)[i]; break;
+      case 2: s += c.sgn ? (uint64_t)(int64_t)((const int16_t*)c.ptr)[i] : ((const uint16_t*)c.ptr)[i]; break;
+      case 4: s += c.sgn ? (uint64_t)(int64_t)((const int32_t*)c.ptr)[i] : ((const uint32_t*)c.ptr)[i]; break;
+      default: s += ((const uint64_t*)c.ptr)[i]; break;
+    }
+    cnt++;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, d); cnt += __shfl_xor_sync(0xffffffffu, cnt, d); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], s); atomicAdd(&out[1], cnt); }
+}
+
 }  // namespace dfgpu
 
 // ==========================================================================================
@@ -662,6 +808,7 @@ static void lookup_reserve(dfgpu_lookup* l, int64_t rows) {
 static ColRef col_ref(const DCol& c) {
   ColRef r;
   r.ptr = c.values; r.valid = c.validity; r.voff = c.offset; r.width = type_width(c.type); r.sgn = type_is_signed_int(c.type) ? 1 : 0;
+  r.vec = ((uintptr_t)c.values % 16 == 0) ? 1 : 0; r.pad = 0;
   return r;
 }
 
@@ -690,6 +837,17 @@ static int bind_pool(const dfgpu_pipeline* p, const ExprPlan& plan, const std::v
   return start;
 }
 
+// largest evaluation-stack depth of a post-order program (the register-resident interpreter handles <= 4)
+static int plan_depth(const ExprPlan& plan) {
+  int sp = 0, mx = 0;
+  for (const auto& nd : plan.nodes) {
+    if (nd.kind == DFGPU_EXPR_COLUMN || nd.kind == DFGPU_EXPR_LITERAL) sp++;
+    else if (nd.kind == DFGPU_EXPR_BINARY) sp--;
+    mx = std::max(mx, sp);
+  }
+  return mx;
+}
+
 static bool expr_can_be_null(const ExprPlan& plan, const std::vector<DCol>& cols) {
   for (const auto& nd : plan.nodes) {
     if (nd.kind == DFGPU_EXPR_COLUMN && nd.a < (int)cols.size() && cols[nd.a].validity) return true;
@@ -701,6 +859,8 @@ static bool expr_can_be_null(const ExprPlan& plan, const std::vector<DCol>& cols
 static void fill_params(dfgpu_pipeline* p, const std::vector<DCol>& cols, PipeParams* pp) {
   memset(pp, 0, sizeof(*pp));
   pp->n_cols = (int)cols.size();
+  static const int hints_env = getenv("DFGPU_PIPE_HINTS") ? atoi(getenv("DFGPU_PIPE_HINTS")) : 3;
+  pp->hints = hints_env;
   for (size_t c = 0; c < cols.size(); ++c) pp->col[c] = col_ref(cols[c]);
   int pool_used = 0;
   pp->pred_mode = 0;
@@ -729,9 +889,12 @@ static void fill_params(dfgpu_pipeline* p, const std::vector<DCol>& cols, PipePa
       pp->pred_mode = 2;
       pp->pred_start = bind_pool(p, p->pred, cols, pp, &pool_used);
       pp->pred_n = (int)p->pred.nodes.size();
+      pp->pred_small = plan_depth(p->pred) <= 4 ? 1 : 0;
     }
   }
   pp->n_stages = (int)p->stages.size();
+  pp->first_hash = -1;
+  for (size_t s = 0; s < p->stages.size(); ++s) if (p->stages[s].lookup->mode == LK_HASH && pp->first_hash < 0) pp->first_hash = (int)s;
   for (size_t s = 0; s < p->stages.size(); ++s) {
     pp->stage[s].kind = p->stages[s].kind; pp->stage[s].key_col = p->stages[s].key_col; pp->stage[s].lk = lookup_dev(p->stages[s].lookup);
   }
@@ -755,6 +918,7 @@ static void fill_params(dfgpu_pipeline* p, const std::vector<DCol>& cols, PipePa
       d.func = ag.func; d.cls = ag.cls; d.word = ag.word; d.nn_word = ag.nn_word; d.start = 0; d.n = 0;
       if (ag.has_expr) {
         d.start = bind_pool(p, ag.plan, cols, pp, &pool_used); d.n = (int)ag.plan.nodes.size();
+        d.small = plan_depth(ag.plan) <= 4 ? 1 : 0;
         if (ag.nn_word < 0 && ag.func != DFGPU_AGG_COUNT)
           DF_CHECK(!expr_can_be_null(ag.plan, cols), DFGPU_ERR_UNSUPPORTED, "pipeline: nullable aggregate input needs one more accumulator word in the lookup (n_acc_words)");
       }
@@ -772,7 +936,12 @@ template <int SINK>
 static void launch_pipe(dfgpu_pipeline* p, int64_t n, const char* timer_name) {
   dfgpu_ctx* ctx = p->ctx;
   const int64_t ntiles = (n + kPipeTile - 1) / kPipeTile;
-  static const int blocks_per_sm = getenv("DFGPU_PIPE_BLOCKS_PER_SM") ? atoi(getenv("DFGPU_PIPE_BLOCKS_PER_SM")) : 4;
+  static const int blocks_env = getenv("DFGPU_PIPE_BLOCKS_PER_SM") ? atoi(getenv("DFGPU_PIPE_BLOCKS_PER_SM")) : 0;
+  int blocks_per_sm = blocks_env;
+  if (blocks_per_sm <= 0) {   // persistent blocks: exactly one resident wave (a second wave would start after the first finished)
+    DF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, pipe_kernel<SINK>, kPipeThreads, 0));
+    blocks_per_sm = std::max(1, blocks_per_sm);
+  }
   const int grid = (int)std::min<int64_t>(ntiles, (int64_t)kNumSMs * blocks_per_sm);
   KernelTimer kt(ctx, timer_name);
   pipe_kernel<SINK><<<grid, kPipeThreads, 0, ctx->stream>>>((const PipeParams*)p->params_dev.ptr, n, p->counters.as<unsigned long long>());
@@ -1059,6 +1228,26 @@ int dfgpu_column_minmax_device(dfgpu_ctx* ctx, const dfgpu_column* col, int64_t*
   if (h[2] == 0) { *min_out = 0; *max_out = -1; }
   else if (uns) { *min_out = (int64_t)h[0]; *max_out = (int64_t)h[1]; }
   else { *min_out = (int64_t)(h[0] ^ (1ull << 63)); *max_out = (int64_t)(h[1] ^ (1ull << 63)); }
+  DF_API_END
+}
+
+int dfgpu_column_sum_device(dfgpu_ctx* ctx, const dfgpu_column* col, uint64_t* sum_out, int64_t* valid_out) {
+  DF_API_BEGIN(ctx)
+  DF_CHECK(ctx && col && sum_out, DFGPU_ERR_INVALID, "null argument");
+  DF_CHECK(key_type_ok(col->type), DFGPU_ERR_UNSUPPORTED, "column sum: integer-like columns only");
+  set_device(ctx);
+  DCol c = device_view(*col);
+  DevBuf acc(ctx, 16);
+  acc.zero();
+  if (c.length > 0) {
+    col_sum_kernel<<<grid_for(c.length, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(col_ref(c), c.length, acc.as<unsigned long long>());
+    DF_LAUNCH_CHECK(ctx);
+  }
+  unsigned long long h[2];
+  DF_CUDA(cudaMemcpyAsync(h, acc.ptr, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  DF_CUDA(cudaStreamSynchronize(ctx->stream));
+  *sum_out = h[0];
+  if (valid_out) *valid_out = (int64_t)h[1];
   DF_API_END
 }
 

@@ -1044,4 +1044,296 @@ O_API double oracle_bench_groupby(const int64_t* g, const int64_t* v, int64_t n,
   return t1 - t0;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* TPC-H Q3-shaped pipeline (BASELINE config C4), run the way the reference's physical plan runs */
+/* it (sqllogictest/test_files/tpch/plans/q3.slt.part:60-76) with target_partitions = T threads: */
+/*   FilterExec(c_mktsegment = 1)            -> RepartitionExec Hash(c_custkey)  \                */
+/*   FilterExec(o_orderdate < cut)           -> RepartitionExec Hash(o_custkey)  -> HashJoinExec Partitioned RightSemi */
+/*                                           -> RepartitionExec Hash(o_orderkey) \                */
+/*   FilterExec(l_shipdate > cut) projection -> RepartitionExec Hash(l_orderkey) -> HashJoinExec Partitioned Inner     */
+/*   -> AggregateExec SinglePartitioned gby [l_orderkey, o_orderdate, o_shippriority] SUM(l_extendedprice * (100 - l_discount)) */
+/* Batches of batch_size rows; JoinHashMap + equal_rows for both joins; multi-column group table. */
+/* Money is int64 fixed point as in the GPU arm.                               */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { const void* src; void* dst; int width; } PCol;
+typedef struct {
+  int64_t n;            /* input rows */
+  int64_t cap;          /* rows the repartitioned buffers can hold */
+  int ncols;
+  PCol col[4];          /* projected columns moved by the exchange */
+  uint32_t** sel;       /* per thread: surviving row offsets within its chunk */
+  uint16_t** pid;       /* per thread: output partition of each surviving row */
+  int64_t* nsel;        /* per thread */
+  int64_t* cnt;         /* [T][T] input chunk x output partition */
+  int64_t* off;         /* [T][T] scatter offsets */
+  int64_t* part;        /* [T+1] partition boundaries */
+} Exchange;
+
+static void exchange_offsets(Exchange* x, int T) { /* partition-major, then input chunk */
+  int64_t pos = 0;
+  for (int p = 0; p < T; ++p) { x->part[p] = pos; for (int c = 0; c < T; ++c) { x->off[c * T + p] = pos; pos += x->cnt[c * T + p]; } }
+  x->part[T] = pos;
+}
+/* the `take` of BatchPartitioner (repartition/mod.rs:1111-1145): one pass per column over this thread's selected rows */
+static void exchange_scatter(Exchange* x, int t, int T, int64_t i0) {
+  int64_t* o = (int64_t*)malloc((size_t)T * 8);
+  const uint32_t* sel = x->sel[t]; const uint16_t* pid = x->pid[t]; const int64_t ns = x->nsel[t];
+  for (int c = 0; c < x->ncols; ++c) {
+    memcpy(o, &x->off[t * T], (size_t)T * 8);
+    if (x->col[c].width == 8) { const int64_t* s = (const int64_t*)x->col[c].src + i0; int64_t* d = (int64_t*)x->col[c].dst; for (int64_t j = 0; j < ns; ++j) d[o[pid[j]]++] = s[sel[j]]; }
+    else { const int32_t* s = (const int32_t*)x->col[c].src + i0; int32_t* d = (int32_t*)x->col[c].dst; for (int64_t j = 0; j < ns; ++j) d[o[pid[j]]++] = s[sel[j]]; }
+  }
+  free(o);
+}
+
+typedef struct {
+  uint64_t* hashes; int64_t* gidx; uint64_t mask; int64_t len, cap;
+  int64_t* k0; int32_t* k1; int32_t* k2; int64_t* sum;
+} Q3Groups; /* GroupValuesColumn restated for (int64, date32, int32) keys (multi_group_by/mod.rs:455-512) + one SUM accumulator */
+static void q3g_init(Q3Groups* g) {
+  g->mask = (1u << 12) - 1; g->hashes = (uint64_t*)calloc(g->mask + 1, 8); g->gidx = (int64_t*)malloc((g->mask + 1) * 8); memset(g->gidx, 0xFF, (g->mask + 1) * 8);
+  g->len = 0; g->cap = 1 << 11;
+  g->k0 = (int64_t*)malloc((size_t)g->cap * 8); g->k1 = (int32_t*)malloc((size_t)g->cap * 4); g->k2 = (int32_t*)malloc((size_t)g->cap * 4); g->sum = (int64_t*)calloc((size_t)g->cap, 8);
+}
+static inline int64_t q3g_intern(Q3Groups* g, uint64_t h, int64_t a, int32_t b, int32_t c) {
+  uint64_t s = o_mix64(h) & g->mask;
+  while (g->gidx[s] >= 0) { const int64_t i = g->gidx[s]; if (g->hashes[s] == h && g->k0[i] == a && g->k1[i] == b && g->k2[i] == c) return i; s = (s + 1) & g->mask; }
+  if (g->len == g->cap) {
+    g->cap *= 2;
+    g->k0 = (int64_t*)realloc(g->k0, (size_t)g->cap * 8); g->k1 = (int32_t*)realloc(g->k1, (size_t)g->cap * 4); g->k2 = (int32_t*)realloc(g->k2, (size_t)g->cap * 4);
+    g->sum = (int64_t*)realloc(g->sum, (size_t)g->cap * 8); memset(g->sum + g->len, 0, (size_t)(g->cap - g->len) * 8);
+  }
+  const int64_t i = g->len++;
+  g->k0[i] = a; g->k1[i] = b; g->k2[i] = c; g->hashes[s] = h; g->gidx[s] = i;
+  if ((uint64_t)g->len * 2 > g->mask) {
+    const uint64_t nm = (g->mask + 1) * 4 - 1;
+    uint64_t* nh = (uint64_t*)calloc(nm + 1, 8); int64_t* ng = (int64_t*)malloc((nm + 1) * 8); memset(ng, 0xFF, (nm + 1) * 8);
+    for (uint64_t t = 0; t <= g->mask; ++t) if (g->gidx[t] >= 0) { uint64_t s2 = o_mix64(g->hashes[t]) & nm; while (ng[s2] >= 0) s2 = (s2 + 1) & nm; nh[s2] = g->hashes[t]; ng[s2] = g->gidx[t]; }
+    free(g->hashes); free(g->gidx); g->hashes = nh; g->gidx = ng; g->mask = nm;
+  }
+  return i;
+}
+static void q3g_free(Q3Groups* g) { free(g->hashes); free(g->gidx); free(g->k0); free(g->k1); free(g->k2); free(g->sum); }
+
+typedef struct Q3Shared {
+  int T; int64_t bs; int32_t cut;
+  int64_t nc, no, nl;
+  const int64_t *c_key, *c_seg, *o_key, *o_cust, *l_key, *l_price, *l_disc; const int32_t *o_date, *o_prio, *l_ship;
+  Exchange xc, xo, xl, xs;                  /* customer, orders, lineitem, semi-join output */
+  /* semi-join output per partition, before its exchange */
+  int64_t** so_key; int32_t** so_date; int32_t** so_prio;
+  pthread_barrier_t* bar; double* t_start;
+  uint64_t* out;                            /* [T][6]: groups, sum key, sum date, sum prio, sum revenue, joined rows */
+  int64_t* stage;                           /* [T][3]: customers kept, orders kept by the semi join, lineitems kept */
+} Q3Shared;
+typedef struct { int tid; Q3Shared* sh; } Q3Thread;
+
+static void exchange_alloc(Exchange* x, int T, int64_t n, int64_t cap, int ncols, const int* widths) {
+  memset(x, 0, sizeof(*x));
+  x->n = n; x->cap = cap; x->ncols = ncols;
+  for (int c = 0; c < ncols; ++c) { x->col[c].width = widths[c]; x->col[c].dst = malloc((size_t)(cap ? cap : 1) * (size_t)widths[c]); }
+  x->sel = (uint32_t**)calloc((size_t)T, sizeof(void*)); x->pid = (uint16_t**)calloc((size_t)T, sizeof(void*));
+  x->nsel = (int64_t*)calloc((size_t)T, 8); x->cnt = (int64_t*)calloc((size_t)T * T, 8); x->off = (int64_t*)calloc((size_t)T * T, 8); x->part = (int64_t*)calloc((size_t)T + 1, 8);
+}
+static void exchange_free(Exchange* x, int T) {
+  for (int c = 0; c < x->ncols; ++c) free(x->col[c].dst);
+  for (int t = 0; t < T; ++t) { free(x->sel[t]); free(x->pid[t]); }
+  free(x->sel); free(x->pid); free(x->nsel); free(x->cnt); free(x->off); free(x->part);
+}
+static void exchange_prefault(Exchange* x, int t, int T) { /* untimed: batch memory of a long-running engine is recycled, not freshly faulted */
+  const int64_t a = x->cap * t / T, b = x->cap * (t + 1) / T;
+  for (int c = 0; c < x->ncols; ++c) memset((char*)x->col[c].dst + a * x->col[c].width, 0, (size_t)(b - a) * (size_t)x->col[c].width);
+  const int64_t i0 = x->n * t / T, i1 = x->n * (t + 1) / T;
+  x->sel[t] = (uint32_t*)malloc((size_t)(i1 - i0 + 1) * 4); x->pid[t] = (uint16_t*)malloc((size_t)(i1 - i0 + 1) * 2);
+  memset(x->sel[t], 0, (size_t)(i1 - i0 + 1) * 4); memset(x->pid[t], 0, (size_t)(i1 - i0 + 1) * 2);
+}
+
+static void* q3_bench_thread(void* arg) {
+  Q3Thread* me = (Q3Thread*)arg; Q3Shared* S = me->sh;
+  const int t = me->tid, T = S->T; const int64_t bs = S->bs;
+  exchange_prefault(&S->xc, t, T); exchange_prefault(&S->xo, t, T); exchange_prefault(&S->xl, t, T);
+  { /* the semi output of partition t cannot exceed the orders routed to it; sized after the orders exchange, prefaulted via xs.dst */
+    const int64_t a = S->xs.cap * t / T, b = S->xs.cap * (t + 1) / T;
+    for (int c = 0; c < S->xs.ncols; ++c) memset((char*)S->xs.col[c].dst + a * S->xs.col[c].width, 0, (size_t)(b - a) * (size_t)S->xs.col[c].width);
+  }
+  pthread_barrier_wait(S->bar);
+  if (t == 0) *S->t_start = now_s();
+  /* ---- FilterExec + BatchPartitioner::Hash, pass 1 (predicate, partition id, counts) for the three scans ---- */
+  { const int64_t i0 = S->nc * t / T, i1 = S->nc * (t + 1) / T; int64_t ns = 0; Exchange* x = &S->xc;
+    for (int64_t i = i0; i < i1; ++i) if (S->c_seg[i] == 1) { const int p = (int)(o_hash((uint64_t)S->c_key[i], SEED_REPART) % (uint64_t)T); x->sel[t][ns] = (uint32_t)(i - i0); x->pid[t][ns] = (uint16_t)p; x->cnt[t * T + p]++; ++ns; }
+    x->nsel[t] = ns; S->stage[t * 3 + 0] = ns; }
+  { const int64_t i0 = S->no * t / T, i1 = S->no * (t + 1) / T; int64_t ns = 0; Exchange* x = &S->xo;
+    for (int64_t i = i0; i < i1; ++i) if (S->o_date[i] < S->cut) { const int p = (int)(o_hash((uint64_t)S->o_cust[i], SEED_REPART) % (uint64_t)T); x->sel[t][ns] = (uint32_t)(i - i0); x->pid[t][ns] = (uint16_t)p; x->cnt[t * T + p]++; ++ns; }
+    x->nsel[t] = ns; }
+  { const int64_t i0 = S->nl * t / T, i1 = S->nl * (t + 1) / T; int64_t ns = 0; Exchange* x = &S->xl;
+    for (int64_t i = i0; i < i1; ++i) if (S->l_ship[i] > S->cut) { const int p = (int)(o_hash((uint64_t)S->l_key[i], SEED_REPART) % (uint64_t)T); x->sel[t][ns] = (uint32_t)(i - i0); x->pid[t][ns] = (uint16_t)p; x->cnt[t * T + p]++; ++ns; }
+    x->nsel[t] = ns; S->stage[t * 3 + 2] = ns; }
+  pthread_barrier_wait(S->bar);
+  if (t == 0) exchange_offsets(&S->xc, T);
+  if (t == 1 % T) exchange_offsets(&S->xo, T);
+  if (t == 2 % T) exchange_offsets(&S->xl, T);
+  pthread_barrier_wait(S->bar);
+  exchange_scatter(&S->xc, t, T, S->nc * t / T); exchange_scatter(&S->xo, t, T, S->no * t / T); exchange_scatter(&S->xl, t, T, S->nl * t / T);
+  pthread_barrier_wait(S->bar);
+  /* ---- partition t: HashJoinExec RightSemi (c_custkey = o_custkey), projection [o_orderkey, o_orderdate, o_shippriority] ---- */
+  Vec64 pi = {0}, bi = {0};
+  uint64_t* h = NULL;
+  {
+    const int64_t nb = S->xc.part[t + 1] - S->xc.part[t], np_ = S->xo.part[t + 1] - S->xo.part[t];
+    const int64_t* bk = (const int64_t*)S->xc.col[0].dst + S->xc.part[t];
+    const int64_t* pkey = (const int64_t*)S->xo.col[0].dst + S->xo.part[t]; const int64_t* pcust = (const int64_t*)S->xo.col[1].dst + S->xo.part[t];
+    const int32_t* pdate = (const int32_t*)S->xo.col[2].dst + S->xo.part[t]; const int32_t* pprio = (const int32_t*)S->xo.col[3].dst + S->xo.part[t];
+    int64_t* sk = (int64_t*)malloc((size_t)(np_ + 1) * 8); int32_t* sd = (int32_t*)malloc((size_t)(np_ + 1) * 4); int32_t* sp = (int32_t*)malloc((size_t)(np_ + 1) * 4);
+    S->so_key[t] = sk; S->so_date[t] = sd; S->so_prio[t] = sp;
+    JoinHashMap m; jhm_init(&m, (uint64_t)nb);
+    h = (uint64_t*)malloc((size_t)((nb > bs ? nb : bs) + 1) * 8);
+    for (int64_t i = 0; i < nb; ++i) h[i] = o_hash((uint64_t)bk[i], SEED_JOIN);
+    for (int64_t i = nb - 1; i >= 0; --i) jhm_insert(&m, (uint64_t)i, h[i]);
+    int64_t ns = 0; Exchange* x = &S->xs;
+    x->sel[t] = NULL; x->pid[t] = (uint16_t*)malloc((size_t)(np_ + 1) * 2);
+    for (int64_t s = 0; s < np_; s += bs) {
+      const int64_t len = np_ - s < bs ? np_ - s : bs;
+      for (int64_t i = 0; i < len; ++i) h[i] = o_hash((uint64_t)pcust[s + i], SEED_JOIN);
+      MapOffset off = {0, 0, 0}, nx;
+      for (;;) {
+        const int more = jhm_lookup(&m, h, NULL, len, bs, off, &pi, &bi, &nx);
+        int64_t last = -1;
+        for (int64_t k = 0; k < bi.n; ++k) {
+          if (bk[bi.p[k]] != pcust[s + pi.p[k]]) continue;            /* equal_rows_arr */
+          if (pi.p[k] == last) continue;                              /* get_semi_indices: each probe row once (utils.rs:1461-1466) */
+          last = pi.p[k];
+          const int64_t r = s + pi.p[k];
+          sk[ns] = pkey[r]; sd[ns] = pdate[r]; sp[ns] = pprio[r];   /* take */
+          const int p = (int)(o_hash((uint64_t)pkey[r], SEED_REPART) % (uint64_t)T); x->pid[t][ns] = (uint16_t)p; x->cnt[t * T + p]++; ++ns;
+        }
+        if (!more) break;
+        off = nx;
+      }
+    }
+    x->nsel[t] = ns; S->stage[t * 3 + 1] = ns;
+    free(h); h = NULL; jhm_free(&m);
+  }
+  pthread_barrier_wait(S->bar);
+  if (t == 0) exchange_offsets(&S->xs, T);
+  pthread_barrier_wait(S->bar);
+  { /* RepartitionExec Hash(o_orderkey) of the semi-join output */
+    int64_t* o = (int64_t*)malloc((size_t)T * 8); const uint16_t* pid = S->xs.pid[t]; const int64_t ns = S->xs.nsel[t];
+    memcpy(o, &S->xs.off[t * T], (size_t)T * 8); { int64_t* d = (int64_t*)S->xs.col[0].dst; for (int64_t j = 0; j < ns; ++j) d[o[pid[j]]++] = S->so_key[t][j]; }
+    memcpy(o, &S->xs.off[t * T], (size_t)T * 8); { int32_t* d = (int32_t*)S->xs.col[1].dst; for (int64_t j = 0; j < ns; ++j) d[o[pid[j]]++] = S->so_date[t][j]; }
+    memcpy(o, &S->xs.off[t * T], (size_t)T * 8); { int32_t* d = (int32_t*)S->xs.col[2].dst; for (int64_t j = 0; j < ns; ++j) d[o[pid[j]]++] = S->so_prio[t][j]; }
+    free(o);
+  }
+  pthread_barrier_wait(S->bar);
+  /* ---- partition t: HashJoinExec Inner (o_orderkey = l_orderkey) -> AggregateExec SinglePartitioned ---- */
+  {
+    const int64_t nb = S->xs.part[t + 1] - S->xs.part[t], np_ = S->xl.part[t + 1] - S->xl.part[t];
+    const int64_t* bk = (const int64_t*)S->xs.col[0].dst + S->xs.part[t]; const int32_t* bd = (const int32_t*)S->xs.col[1].dst + S->xs.part[t]; const int32_t* bp = (const int32_t*)S->xs.col[2].dst + S->xs.part[t];
+    const int64_t* pk = (const int64_t*)S->xl.col[0].dst + S->xl.part[t]; const int64_t* pprice = (const int64_t*)S->xl.col[1].dst + S->xl.part[t]; const int64_t* pdisc = (const int64_t*)S->xl.col[2].dst + S->xl.part[t];
+    JoinHashMap m; jhm_init(&m, (uint64_t)nb);
+    h = (uint64_t*)malloc((size_t)((nb > bs ? nb : bs) + 1) * 8);
+    for (int64_t i = 0; i < nb; ++i) h[i] = o_hash((uint64_t)bk[i], SEED_JOIN);
+    for (int64_t i = nb - 1; i >= 0; --i) jhm_insert(&m, (uint64_t)i, h[i]);
+    /* join output batch: [o_orderdate, o_shippriority, l_orderkey, l_extendedprice, l_discount] */
+    int32_t* od = (int32_t*)malloc((size_t)bs * 4); int32_t* op = (int32_t*)malloc((size_t)bs * 4);
+    int64_t* ok = (int64_t*)malloc((size_t)bs * 8); int64_t* oe = (int64_t*)malloc((size_t)bs * 8); int64_t* odi = (int64_t*)malloc((size_t)bs * 8);
+    int64_t* rev = (int64_t*)malloc((size_t)bs * 8); uint64_t* gh = (uint64_t*)malloc((size_t)bs * 8); int64_t* gi = (int64_t*)malloc((size_t)bs * 8);
+    Q3Groups G; q3g_init(&G);
+    uint64_t joined = 0;
+    for (int64_t s = 0; s < np_; s += bs) {
+      const int64_t len = np_ - s < bs ? np_ - s : bs;
+      for (int64_t i = 0; i < len; ++i) h[i] = o_hash((uint64_t)pk[s + i], SEED_JOIN);
+      MapOffset off = {0, 0, 0}, nx;
+      for (;;) {
+        const int more = jhm_lookup(&m, h, NULL, len, bs, off, &pi, &bi, &nx);
+        int64_t mm = 0;
+        for (int64_t k = 0; k < bi.n; ++k) if (bk[bi.p[k]] == pk[s + pi.p[k]]) { bi.p[mm] = bi.p[k]; pi.p[mm] = pi.p[k]; ++mm; }   /* equal_rows_arr */
+        for (int64_t k = 0; k < mm; ++k) od[k] = bd[bi.p[k]];                /* build_batch_from_indices: take per column */
+        for (int64_t k = 0; k < mm; ++k) op[k] = bp[bi.p[k]];
+        for (int64_t k = 0; k < mm; ++k) ok[k] = pk[s + pi.p[k]];
+        for (int64_t k = 0; k < mm; ++k) oe[k] = pprice[s + pi.p[k]];
+        for (int64_t k = 0; k < mm; ++k) odi[k] = pdisc[s + pi.p[k]];
+        /* AggregateExec: evaluate the argument, hash the three group columns, intern, update the SUM accumulator */
+        for (int64_t k = 0; k < mm; ++k) rev[k] = (int64_t)((uint64_t)oe[k] * (uint64_t)(100 - odi[k]));
+        for (int64_t k = 0; k < mm; ++k) gh[k] = o_hash((uint64_t)ok[k], SEED_AGG);
+        for (int64_t k = 0; k < mm; ++k) gh[k] = o_hash((uint64_t)(int64_t)od[k], gh[k]);
+        for (int64_t k = 0; k < mm; ++k) gh[k] = o_hash((uint64_t)(int64_t)op[k], gh[k]);
+        for (int64_t k = 0; k < mm; ++k) gi[k] = q3g_intern(&G, gh[k], ok[k], od[k], op[k]);
+        for (int64_t k = 0; k < mm; ++k) G.sum[gi[k]] = (int64_t)((uint64_t)G.sum[gi[k]] + (uint64_t)rev[k]);
+        joined += (uint64_t)mm;
+        if (!more) break;
+        off = nx;
+      }
+    }
+    uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int64_t g = 0; g < G.len; ++g) { s0 += (uint64_t)G.k0[g]; s1 += (uint64_t)(int64_t)G.k1[g]; s2 += (uint64_t)(int64_t)G.k2[g]; s3 += (uint64_t)G.sum[g]; }
+    uint64_t* o = &S->out[t * 6];
+    o[0] = (uint64_t)G.len; o[1] = s0; o[2] = s1; o[3] = s2; o[4] = s3; o[5] = joined;
+    q3g_free(&G); free(h); jhm_free(&m);
+    free(od); free(op); free(ok); free(oe); free(odi); free(rev); free(gh); free(gi);
+  }
+  free(pi.p); free(bi.p);
+  return NULL;
+}
+
+/* generate the synthetic TPC-H-shaped tables exactly as scripts/q3_device_pipeline.py gen_tables does on the device */
+typedef struct { int tid, T; int64_t nc, no, nl; uint64_t seed; int64_t d0, d1;
+                 int64_t *c_key, *c_seg, *o_key, *o_cust, *l_key, *l_price, *l_disc; int32_t *o_date, *o_prio, *l_ship; } Q3Gen;
+static inline int64_t q3_sparse(int64_t e) { return (e / 8) * 32 + (e % 8) + 1; }
+static void* q3_gen_thread(void* arg) {
+  Q3Gen* g = (Q3Gen*)arg; const int t = g->tid, T = g->T; const uint64_t sd = g->seed;
+  for (int64_t i = g->nc * t / T; i < g->nc * (t + 1) / T; ++i) { g->c_key[i] = 1 + i; g->c_seg[i] = (int64_t)(o_splitmix64_at(sd + 1, (uint64_t)i) % 5u); }
+  const int64_t cb = g->nc * 2 / 3 > 1 ? g->nc * 2 / 3 : 1;
+  for (int64_t i = g->no * t / T; i < g->no * (t + 1) / T; ++i) {
+    g->o_key[i] = q3_sparse(i); g->o_cust[i] = 1 + (int64_t)(o_splitmix64_at(sd + 2, (uint64_t)i) % (uint64_t)cb);
+    g->o_date[i] = (int32_t)(g->d0 + (int64_t)(o_splitmix64_at(sd + 3, (uint64_t)i) % (uint64_t)(g->d1 - g->d0 + 1))); g->o_prio[i] = 0;
+  }
+  for (int64_t i = g->nl * t / T; i < g->nl * (t + 1) / T; ++i) {
+    g->l_key[i] = q3_sparse((int64_t)(o_splitmix64_at(sd + 4, (uint64_t)i) % (uint64_t)g->no));
+    g->l_price[i] = 90000 + (int64_t)(o_splitmix64_at(sd + 5, (uint64_t)i) % 10410000u); g->l_disc[i] = (int64_t)(o_splitmix64_at(sd + 6, (uint64_t)i) % 11u);
+    g->l_ship[i] = (int32_t)(g->d0 + 1 + (int64_t)(o_splitmix64_at(sd + 7, (uint64_t)i) % (uint64_t)(g->d1 - g->d0 + 121)));
+  }
+  return NULL;
+}
+O_API void oracle_q3_generate(int64_t nc, int64_t no, int64_t nl, uint64_t seed, int64_t d0, int64_t d1, int threads,
+                              int64_t* c_key, int64_t* c_seg, int64_t* o_key, int64_t* o_cust, int32_t* o_date, int32_t* o_prio,
+                              int64_t* l_key, int64_t* l_price, int64_t* l_disc, int32_t* l_ship) {
+  const int T = threads < 1 ? 1 : threads;
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)T); Q3Gen* jobs = (Q3Gen*)malloc(sizeof(Q3Gen) * (size_t)T);
+  for (int t = 0; t < T; ++t) { jobs[t] = (Q3Gen){t, T, nc, no, nl, seed, d0, d1, c_key, c_seg, o_key, o_cust, l_key, l_price, l_disc, o_date, o_prio, l_ship}; pthread_create(&th[t], NULL, q3_gen_thread, &jobs[t]); }
+  for (int t = 0; t < T; ++t) pthread_join(th[t], NULL);
+  free(th); free(jobs);
+}
+
+/* returns seconds; out[0..5] = groups, sum l_orderkey, sum o_orderdate, sum o_shippriority, sum revenue (all mod 2^64), joined rows;
+ * out[6..8] = customers kept, orders kept by the semi join, lineitems kept */
+O_API double oracle_bench_q3(int64_t nc, int64_t no, int64_t nl, const int64_t* c_key, const int64_t* c_seg, const int64_t* o_key, const int64_t* o_cust,
+                             const int32_t* o_date, const int32_t* o_prio, const int64_t* l_key, const int64_t* l_price, const int64_t* l_disc,
+                             const int32_t* l_ship, int32_t cut, int threads, int64_t batch_size, uint64_t* out) {
+  int T = threads < 1 ? 1 : threads;
+  if (T > 65535) T = 65535;
+  Q3Shared S; memset(&S, 0, sizeof(S));
+  S.T = T; S.bs = batch_size; S.cut = cut; S.nc = nc; S.no = no; S.nl = nl;
+  S.c_key = c_key; S.c_seg = c_seg; S.o_key = o_key; S.o_cust = o_cust; S.o_date = o_date; S.o_prio = o_prio; S.l_key = l_key; S.l_price = l_price; S.l_disc = l_disc; S.l_ship = l_ship;
+  const int wc[1] = {8}, wo[4] = {8, 8, 4, 4}, wl[3] = {8, 8, 8}, ws[3] = {8, 4, 4};
+  exchange_alloc(&S.xc, T, nc, nc, 1, wc); S.xc.col[0].src = c_key;
+  exchange_alloc(&S.xo, T, no, no, 4, wo); S.xo.col[0].src = o_key; S.xo.col[1].src = o_cust; S.xo.col[2].src = o_date; S.xo.col[3].src = o_prio;
+  exchange_alloc(&S.xl, T, nl, nl, 3, wl); S.xl.col[0].src = l_key; S.xl.col[1].src = l_price; S.xl.col[2].src = l_disc;
+  exchange_alloc(&S.xs, T, 0, no, 3, ws);
+  S.so_key = (int64_t**)calloc((size_t)T, sizeof(void*)); S.so_date = (int32_t**)calloc((size_t)T, sizeof(void*)); S.so_prio = (int32_t**)calloc((size_t)T, sizeof(void*));
+  pthread_barrier_t bar; pthread_barrier_init(&bar, NULL, (unsigned)T);
+  S.bar = &bar; double t0 = now_s(); S.t_start = &t0;
+  S.out = (uint64_t*)calloc((size_t)T * 6, 8); S.stage = (int64_t*)calloc((size_t)T * 3, 8);
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)T); Q3Thread* args = (Q3Thread*)malloc(sizeof(Q3Thread) * (size_t)T);
+  for (int t = 0; t < T; ++t) { args[t].tid = t; args[t].sh = &S; pthread_create(&th[t], NULL, q3_bench_thread, &args[t]); }
+  for (int t = 0; t < T; ++t) pthread_join(th[t], NULL);
+  const double t1 = now_s();
+  for (int k = 0; k < 9; ++k) out[k] = 0;
+  for (int t = 0; t < T; ++t) { for (int k = 0; k < 6; ++k) out[k] += S.out[t * 6 + k]; for (int k = 0; k < 3; ++k) out[6 + k] += (uint64_t)S.stage[t * 3 + k]; }
+  for (int t = 0; t < T; ++t) { free(S.so_key[t]); free(S.so_date[t]); free(S.so_prio[t]); }
+  free(S.so_key); free(S.so_date); free(S.so_prio);
+  exchange_free(&S.xc, T); exchange_free(&S.xo, T); exchange_free(&S.xl, T); exchange_free(&S.xs, T);
+  free(S.out); free(S.stage); free(th); free(args); pthread_barrier_destroy(&bar);
+  return t1 - t0;
+}
+
 O_API const char* oracle_version(void) { return "oracle 0.1 (restatement of apache/datafusion 55.0.0 hot path; parity unpinned for hash VALUES only)"; }

@@ -583,3 +583,36 @@ def bench_groupby(g, v, threads: int, batch_size: int = 8192):
     p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
     secs = lib().oracle_bench_groupby(p(g), p(v), C.c_int64(len(g)), C.c_int(threads), C.c_int64(batch_size), out)
     return secs, int(out[0]), int(out[1])
+
+
+# ---- TPC-H Q3-shaped pipeline (BASELINE config C4) ----
+Q3_D0, Q3_D1, Q3_CUT = 8035, 10440, 9204    # days since epoch of 1992-01-01, 1998-08-02, 1995-03-15
+
+
+def q3_generate(sf: float, seed: int = 1, threads: int = 1) -> dict:
+    """host copy of scripts/q3_device_pipeline.py gen_tables (same counter-based formulae, bit-identical tables)"""
+    nc, no, nl = int(150_000 * sf), int(1_500_000 * sf), int(6_000_000 * sf)
+    t = {"c_custkey": np.empty(nc, np.int64), "c_mktsegment": np.empty(nc, np.int64),
+         "o_orderkey": np.empty(no, np.int64), "o_custkey": np.empty(no, np.int64), "o_orderdate": np.empty(no, np.int32), "o_shippriority": np.empty(no, np.int32),
+         "l_orderkey": np.empty(nl, np.int64), "l_extendedprice": np.empty(nl, np.int64), "l_discount": np.empty(nl, np.int64), "l_shipdate": np.empty(nl, np.int32)}
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    L = lib()
+    L.oracle_q3_generate.restype = None
+    L.oracle_q3_generate(C.c_int64(nc), C.c_int64(no), C.c_int64(nl), C.c_uint64(seed), C.c_int64(Q3_D0), C.c_int64(Q3_D1), C.c_int(threads),
+                         p(t["c_custkey"]), p(t["c_mktsegment"]), p(t["o_orderkey"]), p(t["o_custkey"]), p(t["o_orderdate"]), p(t["o_shippriority"]),
+                         p(t["l_orderkey"]), p(t["l_extendedprice"]), p(t["l_discount"]), p(t["l_shipdate"]))
+    return t
+
+
+def bench_q3(t: dict, threads: int, batch_size: int = 8192, cut: int = Q3_CUT):
+    """(seconds, fingerprint [groups, sum l_orderkey, sum o_orderdate, sum o_shippriority, sum revenue], stage rows dict)"""
+    out = (C.c_uint64 * 9)()
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    L = lib()
+    L.oracle_bench_q3.restype = C.c_double
+    secs = L.oracle_bench_q3(C.c_int64(len(t["c_custkey"])), C.c_int64(len(t["o_orderkey"])), C.c_int64(len(t["l_orderkey"])),
+                             p(t["c_custkey"]), p(t["c_mktsegment"]), p(t["o_orderkey"]), p(t["o_custkey"]), p(t["o_orderdate"]), p(t["o_shippriority"]),
+                             p(t["l_orderkey"]), p(t["l_extendedprice"]), p(t["l_discount"]), p(t["l_shipdate"]), C.c_int32(cut), C.c_int(threads),
+                             C.c_int64(batch_size), out)
+    o = [int(x) for x in out]
+    return secs, o[:5], {"joined_rows": o[5], "customer_building": o[6], "orders_of_building_customers": o[7], "lineitem_after_cut": o[8]}

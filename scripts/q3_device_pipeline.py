@@ -155,16 +155,43 @@ def run_q3_fused(ctx, customer, orders, lineitem):
     return res, stages
 
 
+def run_q3_fused_host(ctx, c_host, o_host, l_host, c_types, o_types, l_types):
+    """the fused plan fed with HOST columns through the C ABI (`*_push_host`: H2D copies inside), result rows drained to host memory.
+    The customer table (the small build side) is uploaded once and read twice: key bounds (what collect_left_input tracks), then the build.
+    returns (host result batches, stage rows, D2H bytes)"""
+    stages = {}
+    c_dev = [D.DeviceColumn.from_host(ctx, h) for h in c_host]
+    kmin, kmax, _ = D.column_minmax_device(ctx, c_dev[0])
+    l1 = D.Lookup(ctx, D.INT64, [], key_range=(kmin, kmax))
+    p1 = D.Pipeline(ctx, c_types, B(D.OP_EQ, C(1), L(1)))
+    p1.sink_build(l1, 0, [])
+    p1.push_device(c_dev); p1.finish(); p1.close()
+    l2 = D.Lookup(ctx, D.INT64, [D.INT32, D.INT32], n_acc_words=2, membership_filter=-1)
+    p2 = D.Pipeline(ctx, o_types, B(D.OP_LT, C(2), L(CUT, D.INT32)), [(D.STAGE_SEMI, 1, l1)])
+    p2.sink_build(l2, 0, [2, 3])
+    p2.push_host(o_host); p2.finish()
+    stages["orders_of_building_customers"] = p2.metric("sink_rows")
+    p2.close()
+    p3 = D.Pipeline(ctx, l_types, B(D.OP_GT, C(3), L(CUT, D.INT32)), [(D.STAGE_INNER, 0, l2)])
+    p3.sink_aggregate([0, 4, 5], [(D.AGG_SUM, B(D.OP_MULTIPLY, C(1), B(D.OP_MINUS, L(100), C(2))))], D.AGG_SINGLE_PARTITIONED)
+    p3.push_host(l_host); p3.finish()
+    res = p3.drain(host=True)
+    stages["joined_rows"], stages["groups"] = p3.metric("sink_rows"), p3.metric("num_groups")
+    d2h = sum(b.num_rows for b in res) * (8 + 4 + 4 + 8)
+    p3.close(); l2.close(); l1.close()
+    for c in c_dev:
+        c.values.free()
+    return res, stages, d2h
+
+
 def result_fingerprint(ctx, res):
-    """order-independent fingerprint of the result rows (row count, wrapping sums of every column) — the same formula the CPU
-    arm's oracle_bench_q3 returns"""
+    """order-independent fingerprint of the result rows (row count, wrapping sums of every column, computed on the device) —
+    the same formula the CPU arm's oracle_bench_q3 returns"""
     n, sums = 0, [0, 0, 0, 0]
     for b in res:
         n += b.num_rows
         for i in range(4):
-            cc = b.column(i)
-            a = ctx.to_host(cc.values, b.num_rows * D.WIDTH[cc.type]).view(D.NP_OF_TYPE[cc.type])
-            sums[i] = (sums[i] + int(a.astype(np.int64).view(np.uint64).sum(dtype=np.uint64))) & (2**64 - 1)
+            sums[i] = (sums[i] + D.column_sum_device(ctx, b.column(i))) & (2**64 - 1)
     return [n] + sums
 
 
