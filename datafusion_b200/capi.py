@@ -28,7 +28,7 @@ NULL_EQUALS_NOTHING, NULL_EQUALS_NULL = 0, 1
 
 AGG_PARTIAL, AGG_FINAL, AGG_FINAL_PARTITIONED, AGG_SINGLE, AGG_SINGLE_PARTITIONED, AGG_PARTIAL_REDUCE = range(6)
 AGG_SUM, AGG_COUNT, AGG_MIN, AGG_MAX, AGG_AVG, AGG_COUNT_STAR = range(1, 7)
-STAGE_INNER, STAGE_SEMI, STAGE_ANTI = range(3)
+STAGE_INNER, STAGE_SEMI, STAGE_ANTI, STAGE_MAYBE = range(4)
 
 GEN_SEQ, GEN_UNIFORM, GEN_SPLITMIX, GEN_PERM, GEN_SPARSE_OF = range(5)
 
@@ -71,7 +71,7 @@ class AggDesc(C.Structure):
 
 class LookupOptions(C.Structure):
     _fields_ = [("expected_rows", C.c_int64), ("key_min", C.c_int64), ("key_max", C.c_int64), ("has_key_range", C.c_int32),
-                ("n_acc_words", C.c_int32), ("membership_filter", C.c_int32), ("reserved", C.c_int32)]
+                ("n_acc_words", C.c_int32), ("membership_filter", C.c_int32), ("filter_only", C.c_int32)]
 
 
 class PipelineStage(C.Structure):
@@ -119,7 +119,8 @@ EXPORTS = [
     "dfgpu_partition_plan_create", "dfgpu_partition_plan_scatter_peer", "dfgpu_partition_plan_create_chunked",
     "dfgpu_partition_plan_scatter_peer_chunk", "dfgpu_partition_plan_destroy",
     "dfgpu_ipc_export", "dfgpu_ipc_import", "dfgpu_ipc_close",
-    "dfgpu_lookup_default_options", "dfgpu_lookup_create", "dfgpu_lookup_metric", "dfgpu_lookup_destroy", "dfgpu_column_minmax_device", "dfgpu_column_sum_device",
+    "dfgpu_lookup_default_options", "dfgpu_lookup_create", "dfgpu_lookup_metric", "dfgpu_lookup_destroy", "dfgpu_lookup_clear",
+    "dfgpu_lookup_filter_buffer", "dfgpu_lookup_filter_allreduce_peer", "dfgpu_pipeline_sink_output_unordered", "dfgpu_column_minmax_device", "dfgpu_column_sum_device",
     "dfgpu_pipeline_create", "dfgpu_pipeline_sink_build", "dfgpu_pipeline_sink_aggregate", "dfgpu_pipeline_sink_output",
     "dfgpu_pipeline_push_host", "dfgpu_pipeline_push_device", "dfgpu_pipeline_push_arrow", "dfgpu_pipeline_finish",
     "dfgpu_pipeline_next", "dfgpu_pipeline_metric", "dfgpu_pipeline_destroy",
@@ -210,6 +211,10 @@ def load_library() -> C.CDLL:
     sig("dfgpu_lookup_create", C.c_int, [vp, i32, P(i32), i32, P(LookupOptions), P(vp)])
     sig("dfgpu_lookup_metric", i64, [vp, C.c_char_p])
     sig("dfgpu_lookup_destroy", None, [vp])
+    sig("dfgpu_lookup_clear", C.c_int, [vp])
+    sig("dfgpu_lookup_filter_buffer", C.c_int, [vp, P(vp), P(u64)])
+    sig("dfgpu_lookup_filter_allreduce_peer", C.c_int, [vp, P(vp), i32, i32])
+    sig("dfgpu_pipeline_sink_output_unordered", C.c_int, [vp, P(i32), i32, i64])
     sig("dfgpu_column_minmax_device", C.c_int, [vp, P(Column), P(i64), P(i64), P(i64)])
     sig("dfgpu_column_sum_device", C.c_int, [vp, P(Column), P(u64), P(i64)])
     sig("dfgpu_pipeline_create", C.c_int, [vp, P(i32), i32, P(ExprNode), i32, P(PipelineStage), i32, P(vp)])
@@ -671,18 +676,32 @@ class Lookup:
     """dfgpu_lookup: the build side of a fused join (unique keys, <= 64 bits of payload, optional accumulator words)"""
 
     def __init__(self, ctx: Context, key_type: int, payload_types=(), expected_rows: int = 0, key_range=None, n_acc_words: int = 0,
-                 membership_filter: int = -1):
+                 membership_filter: int = -1, filter_only: bool = False):
         self.ctx = ctx
         self.h = C.c_void_p()
         opt = LookupOptions()
         ctx.lib.dfgpu_lookup_default_options(C.byref(opt))
         opt.expected_rows, opt.n_acc_words, opt.membership_filter = int(expected_rows), int(n_acc_words), int(membership_filter)
+        opt.filter_only = 1 if filter_only else 0
         if key_range is not None:
             opt.has_key_range, opt.key_min, opt.key_max = 1, int(key_range[0]), int(key_range[1])
         ctx.check(ctx.lib.dfgpu_lookup_create(ctx.h, key_type, _i32arr(list(payload_types)), len(payload_types), C.byref(opt), C.byref(self.h)))
 
     def metric(self, name: str) -> int:
         return self.ctx.lib.dfgpu_lookup_metric(self.h, name.encode())
+
+    def clear(self):
+        self.ctx.check(self.ctx.lib.dfgpu_lookup_clear(self.h))
+
+    def filter_buffer(self):
+        """(device pointer, bytes) of the membership filter"""
+        p, n = C.c_void_p(), C.c_uint64()
+        self.ctx.check(self.ctx.lib.dfgpu_lookup_filter_buffer(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def filter_allreduce_peer(self, peer_ptrs, rank: int):
+        arr = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
+        self.ctx.check(self.ctx.lib.dfgpu_lookup_filter_allreduce_peer(self.h, arr, rank, len(peer_ptrs)))
 
     def close(self):
         if self.h:
@@ -728,8 +747,9 @@ class Pipeline(_Operator):
                 arr[i].n_nodes, arr[i].expr = 0, None
         self.ctx.check(self.ctx.lib.dfgpu_pipeline_sink_aggregate(self.h, _i32arr(list(group_cols)), len(group_cols), arr, len(aggs), mode, batch_size))
 
-    def sink_output(self, out_cols, batch_size=0):
-        self.ctx.check(self.ctx.lib.dfgpu_pipeline_sink_output(self.h, _i32arr(list(out_cols)), len(out_cols), batch_size))
+    def sink_output(self, out_cols, batch_size=0, ordered=True):
+        fn = self.ctx.lib.dfgpu_pipeline_sink_output if ordered else self.ctx.lib.dfgpu_pipeline_sink_output_unordered
+        self.ctx.check(fn(self.h, _i32arr(list(out_cols)), len(out_cols), batch_size))
 
     def push_host(self, cols): self._push("dfgpu_pipeline_push_host", cols)
     def push_device(self, cols): self._push("dfgpu_pipeline_push_device", cols)

@@ -38,7 +38,8 @@ constexpr uint64_t kEmptyKey = ~0ull;
 constexpr int kMaxPipeCols = 16, kMaxStages = 3, kMaxPipeAggs = 4, kMaxExt = 8, kMaxTerms = 4, kPoolNodes = 56, kMaxBuildPay = 8;
 constexpr int kPipeThreads = 256, kPipeItems = 4, kPipeTile = kPipeThreads * kPipeItems;
 enum LookupMode : int { LK_HASH = 0, LK_BITMAP = 1 };
-enum SinkKind : int { SINK_NONE = 0, SINK_COUNT = 1, SINK_BUILD = 2, SINK_AGG = 3, SINK_OUTPUT = 4 };
+enum SinkKind : int { SINK_NONE = 0, SINK_COUNT = 1, SINK_BUILD = 2, SINK_AGG = 3, SINK_OUTPUT = 4, SINK_OUTPUT_ANY = 5 /* row order unspecified */ };
+constexpr int kStageMaybe = 3;   // DFGPU_STAGE_MAYBE
 
 struct LookupDev {
   int mode, stride /* 8-byte words per record */, has_payload, pad;
@@ -60,6 +61,8 @@ struct PipeParams {
   LookupDev target; int bkey_col, target_unique, n_bpay, bpay_src[kMaxBuildPay], bpay_shift[kMaxBuildPay], bpay_width[kMaxBuildPay];
   // aggregate sink (group id == record of stage `agg_stage`)
   int agg_stage, rows_word, n_aggs; AggDef agg[kMaxPipeAggs];
+  // unordered output sink
+  int n_out, out_src[kMaxPipeCols], out_width[kMaxPipeCols]; void* out_dst[kMaxPipeCols]; unsigned long long* out_counter;
   ENode pool[kPoolNodes];
 };
 
@@ -106,6 +109,10 @@ __device__ __forceinline__ int lk_insert(const LookupDev& t, uint64_t key, uint6
   }
   if (key == kEmptyKey) return 2;
   const uint64_t h = lk_hash(key);
+  if (t.cap == 0) {   // filter-only lookup: membership bits, no table
+    uint64_t b; unsigned long long m; bloom_pos(h, t.bloom_blocks, &b, &m); atomicOr(&t.bloom[b], m);
+    return 0;
+  }
   uint64_t s = __umul64hi(h, t.cap);
   int rc = 0;
   while (true) {
@@ -293,6 +300,7 @@ __global__ void __launch_bounds__(kPipeThreads) pipe_kernel(const PipeParams* __
         const StageDev& st = sp.stage[s];
         const bool bitmap = st.lk.mode == LK_BITMAP;
         if (!bitmap && s != sp.first_hash && !(st.lk.bloom && st.kind != DFGPU_STAGE_ANTI)) continue;   // nothing cheap to do for this stage
+        if (!bitmap && st.kind == kStageMaybe && !st.lk.bloom) continue;                                // may-contain without a filter: everything may
         if (!__any_sync(0xffffffffu, mask != 0)) continue;
         const ColRef kc = sp.col[st.key_col];
         uint64_t key[kWarpRows];
@@ -362,7 +370,7 @@ __global__ void __launch_bounds__(kPipeThreads) pipe_kernel(const PipeParams* __
         for (int u = 0; u < kPhaseB; ++u) pay[s][u] = 0;
         if (s >= sp.n_stages) continue;
         const StageDev& st = sp.stage[s];
-        if (st.lk.mode == LK_BITMAP) continue;   // decided in phase A
+        if (st.lk.mode == LK_BITMAP || st.kind == kStageMaybe) continue;   // decided in phase A
         const ColRef kc = sp.col[st.key_col];
         uint64_t key[kPhaseB], slot[kPhaseB], ck[kPhaseB], cp[kPhaseB];
         bool look[kPhaseB], found[kPhaseB];
@@ -397,8 +405,38 @@ __global__ void __launch_bounds__(kPipeThreads) pipe_kernel(const PipeParams* __
         }
       }
       // ---- sink ----
+      if (SINK == SINK_OUTPUT_ANY) {   // rows leave in arrival order: one global reservation per 128-row group, coalesced column writes
+        unsigned int tot = 0, mypos[kPhaseB];
+#pragma unroll
+        for (int u = 0; u < kPhaseB; ++u) { const unsigned m = __ballot_sync(0xffffffffu, live[u]); mypos[u] = tot + __popc(m & ((1u << lane) - 1u)); tot += __popc(m); }
+        unsigned long long obase = 0;
+        if (lane == 0 && tot) obase = atomicAdd(sp.out_counter, (unsigned long long)tot);
+        obase = __shfl_sync(0xffffffffu, obase, 0);
+#pragma unroll
+        for (int u = 0; u < kPhaseB; ++u) {
+          if (!live[u]) continue;
+          alive_cnt++;
+          for (int c = 0; c < sp.n_out; ++c) {
+            const int src = sp.out_src[c], w = sp.out_width[c];
+            uint64_t v;
+            if (src < sp.n_cols) v = ld_stream_int(sp.col[src].ptr, w, 0, row[u], pol_stream);
+            else { const ExtDef e = sp.ext[src - sp.n_cols]; uint64_t wd = 0;
+#pragma unroll
+                   for (int s = 0; s < kMaxStages; ++s) if (s == e.stage) wd = pay[s][u];
+                   v = ext_field(wd, e.shift, e.width, DFGPU_UINT64); }
+            const unsigned long long o = obase + mypos[u];
+            switch (w) {
+              case 1: ((uint8_t*)sp.out_dst[c])[o] = (uint8_t)v; break;
+              case 2: ((uint16_t*)sp.out_dst[c])[o] = (uint16_t)v; break;
+              case 4: ((uint32_t*)sp.out_dst[c])[o] = (uint32_t)v; break;
+              default: ((uint64_t*)sp.out_dst[c])[o] = v; break;
+            }
+          }
+        }
+      }
 #pragma unroll
       for (int u = 0; u < kPhaseB; ++u) {
+        if (SINK == SINK_OUTPUT_ANY) break;
         uint64_t ext[kMaxStages];
 #pragma unroll
         for (int s = 0; s < kMaxStages; ++s) ext[s] = pay[s][u];
@@ -677,6 +715,22 @@ __global__ void __launch_bounds__(256) lookup_emit_kernel(LookupDev t, const uin
   }
 }
 
+// OR-all-reduce of n_ranks membership filters of identical geometry over peer memory (NVLink): this rank merges slice
+// `rank` of every filter (reads of the peers' slices travel over NVLink) and writes the merged slice into every rank's
+// filter.  Slice r of rank q's buffer is read only by rank r, and written by rank r only after it has read it.
+constexpr int kMaxPeers = 8;
+struct PeerWords { unsigned long long* p[kMaxPeers]; };
+__global__ void __launch_bounds__(256) filter_allreduce_peer_kernel(PeerWords pw, int rank, int n_ranks, uint64_t blocks) {
+  const uint64_t lo = blocks * (uint64_t)rank / (uint64_t)n_ranks, hi = blocks * (uint64_t)(rank + 1) / (uint64_t)n_ranks;
+  for (uint64_t i = lo + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < hi; i += (uint64_t)gridDim.x * blockDim.x) {
+    unsigned long long acc = 0;
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q) if (q < n_ranks) acc |= pw.p[q][i];
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q) if (q < n_ranks) pw.p[q][i] = acc;
+  }
+}
+
 __global__ void __launch_bounds__(256) col_minmax_kernel(ColRef c, int64_t n, int uns, unsigned long long* mm /* [min,max,valid] */) {
   unsigned long long kmin = ~0ull, kmax = 0, cnt = 0;   // order-preserving map of signed keys onto unsigned
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -735,7 +789,7 @@ struct dfgpu_lookup {
   DevBuf recs, bloom, bits;
   uint64_t cap = 0, bloom_blocks = 0, kmin = 0, ksize = 0;
   int64_t rows = 0, rehashes = 0;
-  bool acc_claimed = false;
+  bool acc_claimed = false, filter_only = false;
 };
 
 struct PipeAgg { int func; ExprPlan plan; bool has_expr = false; int word = -1, nn_word = -1, cnt_word = -1, cls = C_I64, arg_type = 0; };
@@ -753,7 +807,7 @@ struct dfgpu_pipeline {
   // aggregate sink
   std::vector<int> group_cols; std::vector<PipeAgg> aggs; int agg_mode = DFGPU_AGG_SINGLE, agg_stage = -1, rows_word = -1; bool acc_ready = false;
   // output sink
-  std::vector<int> out_cols;
+  std::vector<int> out_cols; bool out_ordered = true;
   std::vector<std::vector<DCol>> out_parts; int64_t out_rows_pending = 0;
   int64_t batch_size = 0;
   bool finished = false;
@@ -778,7 +832,7 @@ static bool key_type_ok(int t) { int w = type_width(t); return w >= 1 && w <= 8 
 
 // (re)allocate a hash lookup for at least `rows` records at load factor <= 0.5; existing records are rehashed
 static void lookup_reserve(dfgpu_lookup* l, int64_t rows) {
-  if (l->mode != LK_HASH) return;
+  if (l->mode != LK_HASH || l->filter_only) return;
   dfgpu_ctx* ctx = l->ctx;
   const uint64_t need = std::max<uint64_t>(1024, (uint64_t)rows * 2);
   if (l->cap >= need) return;
@@ -894,7 +948,7 @@ static void fill_params(dfgpu_pipeline* p, const std::vector<DCol>& cols, PipePa
   }
   pp->n_stages = (int)p->stages.size();
   pp->first_hash = -1;
-  for (size_t s = 0; s < p->stages.size(); ++s) if (p->stages[s].lookup->mode == LK_HASH && pp->first_hash < 0) pp->first_hash = (int)s;
+  for (size_t s = 0; s < p->stages.size(); ++s) if (p->stages[s].lookup->mode == LK_HASH && p->stages[s].kind != DFGPU_STAGE_MAYBE && pp->first_hash < 0) pp->first_hash = (int)s;
   for (size_t s = 0; s < p->stages.size(); ++s) {
     pp->stage[s].kind = p->stages[s].kind; pp->stage[s].key_col = p->stages[s].key_col; pp->stage[s].lk = lookup_dev(p->stages[s].lookup);
   }
@@ -995,7 +1049,7 @@ static void pipeline_push(dfgpu_pipeline* p, const std::vector<DCol>& cols) {
   unsigned long long h[4];
   if (p->sink == SINK_BUILD) {
     dfgpu_lookup* t = p->target;
-    if (t->mode == LK_HASH && (uint64_t)(t->rows + n) * 2 > t->cap) {
+    if (t->mode == LK_HASH && !t->filter_only && (uint64_t)(t->rows + n) * 2 > t->cap) {
       // the batch may not fit at load factor 0.5: count its survivors first (same kernel, counting sink), then size the table
       fill_params(p, cols, &pp);
       upload_params(p, pp);
@@ -1024,8 +1078,36 @@ static void pipeline_push(dfgpu_pipeline* p, const std::vector<DCol>& cols) {
     read_counters(p, h);
     check_errors(h[3]);
     p->m_sink_rows += (int64_t)h[0];
-  } else {  // SINK_OUTPUT
+  } else if (!p->out_ordered) {   // SINK_OUTPUT, row order unspecified: the two-phase kernel, one global reservation per 128 survivors
     DF_CHECK(n < 0xFFFFFFFFll, DFGPU_ERR_UNSUPPORTED, "pipeline: a batch must have < 2^32-1 rows");
+    fill_params(p, cols, &pp);
+    std::vector<DCol> part;
+    pp.n_out = (int)p->out_cols.size();
+    for (int c = 0; c < pp.n_out; ++c) {
+      const int src = p->out_cols[c];
+      if (src < (int)cols.size()) DF_CHECK(!cols[src].validity, DFGPU_ERR_UNSUPPORTED, "pipeline output: nullable columns stay on the unfused operators");
+      DCol d = alloc_col(ctx, p->vtypes[src], n, false);
+      pp.out_src[c] = src; pp.out_width[c] = type_width(p->vtypes[src]); pp.out_dst[c] = d.own_values->ptr;
+      part.push_back(std::move(d));
+    }
+    p->counters.zero();
+    pp.out_counter = p->counters.as<unsigned long long>() + 4;
+    upload_params(p, pp);
+    launch_pipe<SINK_OUTPUT_ANY>(p, n, "pipeline_output");
+    unsigned long long h8[8];
+    DF_CUDA(cudaMemcpyAsync(h8, p->counters.ptr, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    DF_CUDA(cudaStreamSynchronize(ctx->stream));
+    check_errors(h8[3]);
+    const int64_t kept = (int64_t)h8[4];
+    p->m_sink_rows += kept;
+    if (kept > 0) {
+      for (auto& c : part) c.length = kept;
+      p->out_parts.push_back(std::move(part));
+      p->out_rows_pending += kept;
+    }
+  } else {  // SINK_OUTPUT, input order preserved
+    DF_CHECK(n < 0xFFFFFFFFll, DFGPU_ERR_UNSUPPORTED, "pipeline: a batch must have < 2^32-1 rows");
+    for (auto& st : p->stages) DF_CHECK(st.kind != DFGPU_STAGE_MAYBE, DFGPU_ERR_UNSUPPORTED, "pipeline: MAYBE stages feed an exchange — use the unordered output sink");
     fill_params(p, cols, &pp);
     upload_params(p, pp);
     p->counters.zero();
@@ -1185,7 +1267,16 @@ int dfgpu_lookup_create(dfgpu_ctx* ctx, int32_t key_type, const int32_t* payload
       l->bits.zero();
     }
   }
-  if (l->mode == LK_HASH && l->opt.expected_rows > 0) lookup_reserve(l.get(), l->opt.expected_rows);
+  if (l->opt.filter_only) {
+    DF_CHECK(l->mode == LK_HASH && !l->has_payload && l->opt.n_acc_words == 0, DFGPU_ERR_INVALID, "lookup: a filter-only lookup is a key set without payload");
+    DF_CHECK(l->opt.expected_rows > 0, DFGPU_ERR_INVALID, "lookup: a filter-only lookup needs expected_rows (its geometry is fixed up front)");
+    l->filter_only = true;
+    l->bloom_blocks = std::max<uint64_t>(1024, (uint64_t)l->opt.expected_rows / 4);   // 16 bits per key
+    DF_CHECK(l->bloom_blocks < (1ull << 32), DFGPU_ERR_UNSUPPORTED, "lookup: filter too large");
+    l->bloom.alloc(ctx, (size_t)l->bloom_blocks * 8);
+    l->bloom.zero();
+  }
+  if (l->mode == LK_HASH && !l->filter_only && l->opt.expected_rows > 0) lookup_reserve(l.get(), l->opt.expected_rows);
   *out = l.release();
   DF_API_END
 }
@@ -1200,6 +1291,43 @@ int64_t dfgpu_lookup_metric(dfgpu_lookup* l, const char* name) {
   if (s == "rehashes") return l->rehashes;
   if (s == "stride_bytes") return l->stride * 8;
   return -1;
+}
+int dfgpu_lookup_clear(dfgpu_lookup* l) {
+  DF_API_BEGIN(l ? l->ctx : nullptr)
+  DF_CHECK(l, DFGPU_ERR_INVALID, "null argument");
+  DF_CHECK(!l->acc_claimed, DFGPU_ERR_STATE, "lookup: accumulators in use by a pipeline");
+  dfgpu_ctx* ctx = l->ctx;
+  set_device(ctx);
+  if (l->mode == LK_BITMAP) l->bits.zero();
+  else {
+    if (l->cap) { lookup_init_kernel<<<grid_for((int64_t)l->cap * l->stride, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(l->recs.as<unsigned long long>(), l->cap, l->stride); DF_LAUNCH_CHECK(ctx); }
+    if (l->bloom.ptr) l->bloom.zero();
+  }
+  l->rows = 0;
+  DF_API_END
+}
+int dfgpu_lookup_filter_buffer(dfgpu_lookup* l, void** words_dev, uint64_t* n_bytes) {
+  DF_API_BEGIN(l ? l->ctx : nullptr)
+  DF_CHECK(l && words_dev && n_bytes, DFGPU_ERR_INVALID, "null argument");
+  *words_dev = l->bloom.ptr; *n_bytes = (uint64_t)l->bloom_blocks * 8;
+  DF_API_END
+}
+int dfgpu_lookup_filter_allreduce_peer(dfgpu_lookup* l, void* const* peer_words, int32_t rank, int32_t n_ranks) {
+  DF_API_BEGIN(l ? l->ctx : nullptr)
+  DF_CHECK(l && peer_words, DFGPU_ERR_INVALID, "null argument");
+  DF_CHECK(n_ranks >= 1 && n_ranks <= kMaxPeers && rank >= 0 && rank < n_ranks, DFGPU_ERR_INVALID, "filter all-reduce: 1..8 ranks of one box");
+  DF_CHECK(l->bloom.ptr && l->bloom_blocks > 0, DFGPU_ERR_STATE, "filter all-reduce: the lookup has no membership filter");
+  dfgpu_ctx* ctx = l->ctx;
+  set_device(ctx);
+  PeerWords pw;
+  memset(&pw, 0, sizeof(pw));
+  for (int q = 0; q < n_ranks; ++q) { DF_CHECK(peer_words[q], DFGPU_ERR_INVALID, "filter all-reduce: null peer pointer"); pw.p[q] = (unsigned long long*)peer_words[q]; }
+  DF_CHECK(pw.p[rank] == l->bloom.as<unsigned long long>(), DFGPU_ERR_INVALID, "filter all-reduce: peer_words[rank] must be this lookup's own filter");
+  const uint64_t slice = l->bloom_blocks / (uint64_t)n_ranks + 1;
+  KernelTimer kt(ctx, "filter_allreduce");
+  filter_allreduce_peer_kernel<<<grid_for((int64_t)slice, 256, kNumSMs * 4), 256, 0, ctx->stream>>>(pw, rank, n_ranks, l->bloom_blocks);
+  DF_LAUNCH_CHECK(ctx);
+  DF_API_END
 }
 void dfgpu_lookup_destroy(dfgpu_lookup* l) {
   if (!l) return;
@@ -1269,7 +1397,8 @@ int dfgpu_pipeline_create(dfgpu_ctx* ctx, const int32_t* input_types, int32_t n_
   for (int s = 0; s < n_stages; ++s) {
     const dfgpu_pipeline_stage& st = stages[s];
     DF_CHECK(st.lookup, DFGPU_ERR_INVALID, "pipeline: stage without a lookup");
-    DF_CHECK(st.kind >= DFGPU_STAGE_INNER && st.kind <= DFGPU_STAGE_ANTI, DFGPU_ERR_INVALID, "pipeline: unknown stage kind");
+    DF_CHECK(st.kind >= DFGPU_STAGE_INNER && st.kind <= DFGPU_STAGE_MAYBE, DFGPU_ERR_INVALID, "pipeline: unknown stage kind");
+    DF_CHECK(!st.lookup->filter_only || st.kind == DFGPU_STAGE_MAYBE, DFGPU_ERR_INVALID, "pipeline: a filter-only lookup can only back a MAYBE stage");
     DF_CHECK(st.key_col >= 0 && st.key_col < n_cols, DFGPU_ERR_INVALID, "pipeline: stage key column out of range");
     const int kt = input_types[st.key_col], lt = st.lookup->key_type;
     DF_CHECK(key_type_ok(kt) && type_width(kt) == type_width(lt) && type_is_signed_int(kt) == type_is_signed_int(lt), DFGPU_ERR_INVALID,
@@ -1376,6 +1505,12 @@ int dfgpu_pipeline_sink_output(dfgpu_pipeline* p, const int32_t* out_cols, int32
   }
   p->batch_size = batch_size; p->sink = SINK_OUTPUT;
   DF_API_END
+}
+
+int dfgpu_pipeline_sink_output_unordered(dfgpu_pipeline* p, const int32_t* out_cols, int32_t n_out, int64_t batch_size) {
+  const int rc = dfgpu_pipeline_sink_output(p, out_cols, n_out, batch_size);
+  if (rc == DFGPU_OK) p->out_ordered = false;
+  return rc;
 }
 
 int dfgpu_pipeline_push_device(dfgpu_pipeline* p, const dfgpu_column* cols, int32_t n_cols) {

@@ -354,7 +354,8 @@ typedef struct dfgpu_lookup_options {
   int32_t has_key_range;
   int32_t n_acc_words;     /* 8-byte accumulator words reserved in every record for a downstream fused aggregation */
   int32_t membership_filter; /* 1 = build a blocked Bloom filter next to the table, 0 = never, -1 = when the table exceeds L2 */
-  int32_t reserved;
+  int32_t filter_only;       /* 1 = membership filter WITHOUT a table (16 bits per expected_rows key): the pushed-down dynamic filter of a join
+                              * whose exact probe happens downstream of an exchange; backs DFGPU_STAGE_MAYBE stages only */
 } dfgpu_lookup_options;
 void dfgpu_lookup_default_options(dfgpu_lookup_options* o);
 /* payload_types: the non-key build columns carried by a match (<= 64 bits together, no NULLs); none = key set only
@@ -362,6 +363,16 @@ void dfgpu_lookup_default_options(dfgpu_lookup_options* o);
  * ArrayMap idea, exec.rs:111-191, at one bit per key). */
 int dfgpu_lookup_create(dfgpu_ctx* ctx, int32_t key_type, const int32_t* payload_types, int32_t n_payload,
                         const dfgpu_lookup_options* opts, dfgpu_lookup** out);
+/* forget every record / key / filter bit, keep the allocations (a persistent build side refilled per query) */
+int dfgpu_lookup_clear(dfgpu_lookup* l);
+/* the membership filter as raw 64-bit blocks (device pointer + size): exported with dfgpu_ipc_export for the peer all-reduce below */
+int dfgpu_lookup_filter_buffer(dfgpu_lookup* l, void** words_dev, uint64_t* n_bytes);
+/* OR-all-reduce of the membership filters of n_ranks lookups of IDENTICAL geometry (same expected_rows) over peer memory (NVLink):
+ * peer_words[r] = rank r's filter buffer (mapped with dfgpu_ipc_import; this lookup's own buffer for r == rank).  This rank merges
+ * slice `rank` of every filter and writes the merged slice back into every rank's filter — a reduce-scatter + all-gather in one
+ * kernel, no NCCL payload (NCCL has no bitwise OR).  The caller places a barrier before (all filters built) and after (all slices
+ * merged) the call.  Reference analogue: SharedBuildAccumulator merging per-partition bounds / membership (shared_bounds.rs). */
+int dfgpu_lookup_filter_allreduce_peer(dfgpu_lookup* l, void* const* peer_words, int32_t rank, int32_t n_ranks);
 int64_t dfgpu_lookup_metric(dfgpu_lookup* l, const char* name); /* "rows","capacity","mode"(0 hash,1 bitmap),"table_bytes","filter_bytes","rehashes" */
 void dfgpu_lookup_destroy(dfgpu_lookup* l);
 /* min / max / non-null count of one integer column (device resident): feeds dfgpu_lookup_options.key_min/key_max */
@@ -370,7 +381,11 @@ int dfgpu_column_minmax_device(dfgpu_ctx* ctx, const dfgpu_column* col, int64_t*
  * results too large to compare row by row (SURVEY.md §8d "Large-config verification") */
 int dfgpu_column_sum_device(dfgpu_ctx* ctx, const dfgpu_column* col, uint64_t* sum_out, int64_t* valid_out);
 
-enum dfgpu_stage_kind { DFGPU_STAGE_INNER = 0, DFGPU_STAGE_SEMI = 1, DFGPU_STAGE_ANTI = 2 };
+enum dfgpu_stage_kind {
+  DFGPU_STAGE_INNER = 0, DFGPU_STAGE_SEMI = 1, DFGPU_STAGE_ANTI = 2,
+  DFGPU_STAGE_MAYBE = 3   /* membership pre-filter only (may have false positives, never false negatives): the dynamic filter a downstream
+                           * join pushes into this scan (joins/hash_join/shared_bounds.rs); the exact join runs after the exchange */
+};
 typedef struct dfgpu_pipeline_stage {
   int32_t kind;          /* dfgpu_stage_kind: the pipeline input is the PROBE (right) side — Inner / RightSemi / RightAnti */
   int32_t key_col;       /* input column holding the probe key (NULL keys never match, utils.rs:2146-2155) */
@@ -397,6 +412,9 @@ int dfgpu_pipeline_sink_build(dfgpu_pipeline* p, dfgpu_lookup* target, int32_t k
 int dfgpu_pipeline_sink_aggregate(dfgpu_pipeline* p, const int32_t* group_cols, int32_t n_group,
                                   const dfgpu_pipeline_agg* aggs, int32_t n_aggs, int32_t mode, int64_t batch_size);
 int dfgpu_pipeline_sink_output(dfgpu_pipeline* p, const int32_t* out_cols, int32_t n_out, int64_t batch_size);
+/* the same, row order unspecified (what a RepartitionExec consumer sees anyway, repartition/mod.rs:1320-1400): runs on the two-phase
+ * kernel and is several times faster than the ordered sink on selective pipelines */
+int dfgpu_pipeline_sink_output_unordered(dfgpu_pipeline* p, const int32_t* out_cols, int32_t n_out, int64_t batch_size);
 int dfgpu_pipeline_push_host(dfgpu_pipeline* p, const dfgpu_column* cols, int32_t n_cols);    /* H2D inside, overlapped with the kernel in row chunks */
 int dfgpu_pipeline_push_device(dfgpu_pipeline* p, const dfgpu_column* cols, int32_t n_cols);
 int dfgpu_pipeline_push_arrow(dfgpu_pipeline* p, const struct ArrowArray* batch, const struct ArrowSchema* schema);

@@ -1336,4 +1336,69 @@ O_API double oracle_bench_q3(int64_t nc, int64_t no, int64_t nl, const int64_t* 
   return t1 - t0;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Streaming verifier of the Q3-shaped query at ANY scale (the multi-GPU runs: SF100 x N does not fit   */
+/* the partitioned port's buffers): no table is materialised — rows are regenerated from the counter-   */
+/* based generators on the fly.  An independent algorithm (one shared open-addressing table built with  */
+/* CAS, atomic adds), used only to fingerprint the expected result.                                     */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { int64_t key; int32_t date, prio; int64_t sum; int64_t rows; } Q3Slot;
+typedef struct {
+  int tid, T; int64_t NC, NO, NL; uint64_t seed; int64_t d0, d1; int32_t cut;
+  uint64_t* cbits; Q3Slot* tab; uint64_t mask;
+  pthread_barrier_t* bar; uint64_t* qualified;
+} Q3Stream;
+static void* q3_stream_thread(void* arg) {
+  Q3Stream* g = (Q3Stream*)arg; const int t = g->tid, T = g->T; const uint64_t sd = g->seed;
+  for (int64_t i = g->NC * t / T; i < g->NC * (t + 1) / T; ++i)          /* customers of the BUILDING segment: bit c_custkey */
+    if (o_splitmix64_at(sd + 1, (uint64_t)i) % 5u == 1) __atomic_fetch_or(&g->cbits[(uint64_t)(1 + i) >> 6], 1ull << ((1 + i) & 63), __ATOMIC_RELAXED);
+  pthread_barrier_wait(g->bar);
+  const int64_t cb = g->NC * 2 / 3 > 1 ? g->NC * 2 / 3 : 1;
+  uint64_t q = 0;
+  for (int64_t i = g->NO * t / T; i < g->NO * (t + 1) / T; ++i) {      /* orders before the cut whose customer qualifies */
+    const int32_t date = (int32_t)(g->d0 + (int64_t)(o_splitmix64_at(sd + 3, (uint64_t)i) % (uint64_t)(g->d1 - g->d0 + 1)));
+    if (!(date < g->cut)) continue;
+    const int64_t cust = 1 + (int64_t)(o_splitmix64_at(sd + 2, (uint64_t)i) % (uint64_t)cb);
+    if (!((g->cbits[(uint64_t)cust >> 6] >> (cust & 63)) & 1)) continue;
+    const int64_t key = q3_sparse(i);
+    uint64_t s = o_mix64((uint64_t)key) & g->mask;
+    for (;;) { int64_t expect = 0; if (__atomic_compare_exchange_n(&g->tab[s].key, &expect, key, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) break; s = (s + 1) & g->mask; }
+    g->tab[s].date = date; g->tab[s].prio = 0;
+    ++q;
+  }
+  g->qualified[t] = q;
+  pthread_barrier_wait(g->bar);
+  for (int64_t i = g->NL * t / T; i < g->NL * (t + 1) / T; ++i) {      /* lineitems after the cut, joined and summed */
+    const int32_t ship = (int32_t)(g->d0 + 1 + (int64_t)(o_splitmix64_at(sd + 7, (uint64_t)i) % (uint64_t)(g->d1 - g->d0 + 121)));
+    if (!(ship > g->cut)) continue;
+    const int64_t key = q3_sparse((int64_t)(o_splitmix64_at(sd + 4, (uint64_t)i) % (uint64_t)g->NO));
+    uint64_t s = o_mix64((uint64_t)key) & g->mask;
+    while (g->tab[s].key != 0 && g->tab[s].key != key) s = (s + 1) & g->mask;
+    if (g->tab[s].key == 0) continue;
+    const int64_t price = 90000 + (int64_t)(o_splitmix64_at(sd + 5, (uint64_t)i) % 10410000u), disc = (int64_t)(o_splitmix64_at(sd + 6, (uint64_t)i) % 11u);
+    __atomic_fetch_add(&g->tab[s].sum, (int64_t)((uint64_t)price * (uint64_t)(100 - disc)), __ATOMIC_RELAXED);
+    __atomic_fetch_add(&g->tab[s].rows, 1, __ATOMIC_RELAXED);
+  }
+  return NULL;
+}
+/* out[0..4] = groups, sum l_orderkey, sum o_orderdate, sum o_shippriority, sum revenue (mod 2^64); out[5] = joined rows; out[6] = qualified orders.
+ * est_qualified: capacity hint for the table (rows); returns 0 on success, -1 if the table would overflow */
+O_API int oracle_q3_stream_fingerprint(int64_t NC, int64_t NO, int64_t NL, uint64_t seed, int64_t d0, int64_t d1, int32_t cut, int threads, uint64_t* out) {
+  const int T = threads < 1 ? 1 : threads;
+  uint64_t cap = 1024; while (cap < (uint64_t)NO / 4) cap <<= 1;   /* ~10 % of the orders qualify: load factor <= 0.4 */
+  Q3Slot* tab = (Q3Slot*)calloc(cap, sizeof(Q3Slot));
+  uint64_t* cbits = (uint64_t*)calloc((size_t)(NC + 2) / 64 + 2, 8);
+  uint64_t* qualified = (uint64_t*)calloc((size_t)T, 8);
+  if (!tab || !cbits) { free(tab); free(cbits); free(qualified); return -1; }
+  pthread_barrier_t bar; pthread_barrier_init(&bar, NULL, (unsigned)T);
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)T); Q3Stream* jobs = (Q3Stream*)malloc(sizeof(Q3Stream) * (size_t)T);
+  for (int t = 0; t < T; ++t) { jobs[t] = (Q3Stream){t, T, NC, NO, NL, seed, d0, d1, cut, cbits, tab, cap - 1, &bar, qualified}; pthread_create(&th[t], NULL, q3_stream_thread, &jobs[t]); }
+  for (int t = 0; t < T; ++t) pthread_join(th[t], NULL);
+  for (int k = 0; k < 7; ++k) out[k] = 0;
+  for (uint64_t s = 0; s < cap; ++s) if (tab[s].rows > 0) { out[0]++; out[1] += (uint64_t)tab[s].key; out[2] += (uint64_t)(int64_t)tab[s].date; out[3] += (uint64_t)(int64_t)tab[s].prio; out[4] += (uint64_t)tab[s].sum; out[5] += (uint64_t)tab[s].rows; }
+  for (int t = 0; t < T; ++t) out[6] += qualified[t];
+  free(tab); free(cbits); free(qualified); free(th); free(jobs); pthread_barrier_destroy(&bar);
+  return 0;
+}
+
 O_API const char* oracle_version(void) { return "oracle 0.1 (restatement of apache/datafusion 55.0.0 hot path; parity unpinned for hash VALUES only)"; }

@@ -616,3 +616,16 @@ def bench_q3(t: dict, threads: int, batch_size: int = 8192, cut: int = Q3_CUT):
                              C.c_int64(batch_size), out)
     o = [int(x) for x in out]
     return secs, o[:5], {"joined_rows": o[5], "customer_building": o[6], "orders_of_building_customers": o[7], "lineitem_after_cut": o[8]}
+
+
+def q3_stream_fingerprint(sf_total: float, seed: int = 1, threads: int = 1, cut: int = Q3_CUT):
+    """expected result fingerprint of the Q3-shaped query over the SF(sf_total) database, computed by streaming regeneration
+    (no table in memory): ([groups, sum l_orderkey, sum o_orderdate, sum o_shippriority, sum revenue], joined rows, qualified orders)"""
+    nc, no, nl = int(150_000 * sf_total), int(1_500_000 * sf_total), int(6_000_000 * sf_total)
+    out = (C.c_uint64 * 7)()
+    rc = lib().oracle_q3_stream_fingerprint(C.c_int64(nc), C.c_int64(no), C.c_int64(nl), C.c_uint64(seed), C.c_int64(Q3_D0), C.c_int64(Q3_D1),
+                                           C.c_int32(cut), C.c_int(threads), out)
+    if rc != 0:
+        raise MemoryError("q3_stream_fingerprint: table allocation failed")
+    o = [int(x) for x in out]
+    return o[:5], o[5], o[6]

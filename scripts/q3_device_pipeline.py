@@ -43,12 +43,14 @@ def _col(buf, n, t=None):
     return c
 
 
-def gen_tables(ctx, sf, seed=1):
+def gen_tables(ctx, sf, seed=1, rank=0, world=1):
+    """rank's shard (rows [rank*n, (rank+1)*n) of every table) of the SF(sf*world) database; world == 1 is the whole SF(sf) database"""
     nc, no, nl = int(150_000 * sf), int(1_500_000 * sf), int(6_000_000 * sf)
+    NC, NO = nc * world, no * world
     keep = []
 
-    def gen(kind, s, a, b, n):
-        buf = ctx.generate_i64(kind, s, a, b, 0, n); keep.append(buf)
+    def gen(kind, s, a, b, n, start=0):
+        buf = ctx.generate_i64(kind, s, a, b, start, n); keep.append(buf)
         return _col(buf, n)
 
     def ev(cols, n, nodes):
@@ -58,16 +60,16 @@ def gen_tables(ctx, sf, seed=1):
         return c
 
     sparse = lambda e: B(D.OP_PLUS, B(D.OP_PLUS, B(D.OP_MULTIPLY, B(D.OP_DIVIDE, e, L(8)), L(32)), B(D.OP_MODULO, e, L(8))), L(1))   # 8 of every 32 keys
-    customer = Table(["c_custkey", "c_mktsegment"], [D.INT64, D.INT64], [gen(D.GEN_SEQ, 0, 1, 0, nc), gen(D.GEN_UNIFORM, seed + 1, 0, 5, nc)], nc, keep)
-    oidx = gen(D.GEN_SEQ, 0, 0, 0, no)
+    customer = Table(["c_custkey", "c_mktsegment"], [D.INT64, D.INT64], [gen(D.GEN_SEQ, 0, 1 + rank * nc, 0, nc), gen(D.GEN_UNIFORM, seed + 1, 0, 5, nc, rank * nc)], nc, keep)
+    oidx = gen(D.GEN_SEQ, 0, rank * no, 0, no)
     orders = Table(["o_orderkey", "o_custkey", "o_orderdate", "o_shippriority"], [D.INT64, D.INT64, D.INT32, D.INT32],
-                   [ev([oidx], no, sparse(C(0))), gen(D.GEN_UNIFORM, seed + 2, 1, max(nc * 2 // 3, 1), no),
-                    ev([gen(D.GEN_UNIFORM, seed + 3, D0, D1 - D0 + 1, no)], no, CAST(C(0), D.INT32)),
+                   [ev([oidx], no, sparse(C(0))), gen(D.GEN_UNIFORM, seed + 2, 1, max(NC * 2 // 3, 1), no, rank * no),
+                    ev([gen(D.GEN_UNIFORM, seed + 3, D0, D1 - D0 + 1, no, rank * no)], no, CAST(C(0), D.INT32)),
                     ev([oidx], no, CAST(B(D.OP_MULTIPLY, C(0), L(0)), D.INT32))], no, keep)
-    lidx = gen(D.GEN_UNIFORM, seed + 4, 0, no, nl)
+    lidx = gen(D.GEN_UNIFORM, seed + 4, 0, NO, nl, rank * nl)
     lineitem = Table(["l_orderkey", "l_extendedprice", "l_discount", "l_shipdate"], [D.INT64, D.INT64, D.INT64, D.INT32],
-                     [ev([lidx], nl, sparse(C(0))), gen(D.GEN_UNIFORM, seed + 5, 90_000, 10_410_000, nl), gen(D.GEN_UNIFORM, seed + 6, 0, 11, nl),
-                      ev([gen(D.GEN_UNIFORM, seed + 7, D0 + 1, D1 - D0 + 121, nl)], nl, CAST(C(0), D.INT32))], nl, keep)
+                     [ev([lidx], nl, sparse(C(0))), gen(D.GEN_UNIFORM, seed + 5, 90_000, 10_410_000, nl, rank * nl), gen(D.GEN_UNIFORM, seed + 6, 0, 11, nl, rank * nl),
+                      ev([gen(D.GEN_UNIFORM, seed + 7, D0 + 1, D1 - D0 + 121, nl, rank * nl)], nl, CAST(C(0), D.INT32))], nl, keep)
     ctx.sync()
     return customer, orders, lineitem
 

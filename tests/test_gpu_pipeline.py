@@ -228,3 +228,65 @@ def test_pipeline_divide_by_zero_in_aggregate_argument_is_an_error(gpu_ctx):
         p.push_host([D.HostColumn(np.array([1, 2, 9], np.int64)), D.HostColumn(np.array([5, 0, 0], np.int64))])
     assert ei.value.code == -4      # row 2 joins and divides by zero; row 3 never reaches the expression (no partner)
     p.close(); look.close()
+
+
+def test_pipeline_unordered_output_and_maybe_stage(gpu_ctx):
+    """the exchange-feeding shape of the multi-GPU plan: scan -> predicate -> MAYBE(membership filter of a downstream join) -> unordered
+    output.  The filter has no false negatives (every true partner survives) and few false positives; the exact join downstream gives the
+    unfused result."""
+    rng = np.random.default_rng(23)
+    nb, npr = 40_000, 300_000
+    bk = (rng.permutation(400_000)[:nb].astype(np.int64)) * 7 + 3
+    pk = (rng.integers(0, 400_000, npr).astype(np.int64)) * 7 + 3
+    pv = rng.integers(0, 10**9, npr).astype(np.int64); pd = rng.integers(0, 100, npr).astype(np.int32)
+    filt = D.Lookup(gpu_ctx, D.INT64, [], expected_rows=nb, filter_only=True)
+    b = D.Pipeline(gpu_ctx, [D.INT64]); b.sink_build(filt, 0, []); b.push_host([D.HostColumn(bk)]); b.finish(); b.close()
+    assert filt.filter_buffer()[1] == max(1024, nb // 4) * 8
+    pred = B(D.OP_LT, C(2), L(60, np.int32))
+    p = D.Pipeline(gpu_ctx, [D.INT64, D.INT64, D.INT32], to_nodes(pred, True), [(D.STAGE_MAYBE, 0, filt)])
+    p.sink_output([0, 1], ordered=False)
+    push_all(p, [(pk, None), (pv, None), (pd, None)], None, 100_000, True, gpu_ctx, [])
+    p.finish()
+    got = batches_to_cols(p.drain(host=False), 2)
+    p.close()
+    keep = pd < 60
+    true_partner = keep & np.isin(pk, bk)
+    gset = set(zip(got[0][0].tolist(), got[1][0].tolist()))
+    assert set(zip(pk[true_partner].tolist(), pv[true_partner].tolist())) <= gset          # no false negatives
+    assert len(got[0][0]) <= true_partner.sum() + 0.05 * keep.sum()                        # few false positives (16 bits per key)
+    assert gset <= set(zip(pk[keep].tolist(), pv[keep].tolist())) and len(gset) == len(got[0][0])
+    # downstream exact join over the survivors == the unfused join over everything
+    look, _ = build_lookup(gpu_ctx, [(bk, None)], [D.INT64], 0, [], n_acc_words=2, membership_filter=0)
+    q = D.Pipeline(gpu_ctx, [D.INT64, D.INT64], None, [(D.STAGE_INNER, 0, look)])
+    q.sink_aggregate([0], [(D.AGG_SUM, to_nodes(C(1), True))])
+    q.push_host([D.HostColumn(got[0][0]), D.HostColumn(got[1][0])]); q.finish()
+    res = batches_to_cols(q.drain(host=True), 2)
+    keys, r = O.group_by([(pk[true_partner], None)], [(O.A_SUM, (pv[true_partner], None), None)])
+    assert_cols_equal(res, [keys[0]] + O.agg_output_columns(O.A_SUM, r[0], np.int64, False), ordered=False, what="maybe + exact join")
+    q.close(); look.close()
+    # clear() empties the filter: nothing may pass any more
+    filt.clear()
+    p = D.Pipeline(gpu_ctx, [D.INT64, D.INT64, D.INT32], None, [(D.STAGE_MAYBE, 0, filt)])
+    p.sink_output([0], ordered=False)
+    p.push_host([D.HostColumn(pk), D.HostColumn(pv), D.HostColumn(pd)]); p.finish()
+    assert p.drain(host=True) == [] and p.metric("sink_rows") == 0
+    p.close(); filt.close()
+
+
+def test_pipeline_unordered_output_matches_ordered(gpu_ctx):
+    rng = np.random.default_rng(29)
+    n = 500_000
+    k = rng.integers(0, 5000, n).astype(np.int64); v = rng.integers(-10**6, 10**6, n).astype(np.int64)
+    look = D.Lookup(gpu_ctx, D.INT64, [], key_range=(0, 4999))
+    b = D.Pipeline(gpu_ctx, [D.INT64]); b.sink_build(look, 0, []); b.push_host([D.HostColumn(np.arange(0, 5000, 3, dtype=np.int64))]); b.finish(); b.close()
+    outs = []
+    for ordered in (True, False):
+        p = D.Pipeline(gpu_ctx, [D.INT64, D.INT64], to_nodes(B(D.OP_GT, C(1), L(0, np.int64)), True), [(D.STAGE_SEMI, 0, look)])
+        p.sink_output([1, 0], ordered=ordered)
+        p.push_host([D.HostColumn(k), D.HostColumn(v)]); p.finish()
+        outs.append(batches_to_cols(p.drain(host=True), 2))
+        p.close()
+    m = (v > 0) & (k % 3 == 0)
+    assert_cols_equal(outs[0], [(v[m], None), (k[m], None)], ordered=True, what="ordered output")
+    assert_cols_equal(outs[1], [(v[m], None), (k[m], None)], ordered=False, what="unordered output")
+    look.close()

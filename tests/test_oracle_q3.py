@@ -49,3 +49,13 @@ def test_q3_generator_matches_pandas_evaluation():
     g = j.groupby(["l_orderkey", "o_orderdate", "o_shippriority"], as_index=False)["rev"].sum()
     _, fp, _ = O.bench_q3(t, 4)
     assert fp == fingerprint([g.l_orderkey.values, g.o_orderdate.values, g.o_shippriority.values, g.rev.values])
+
+
+@pytest.mark.parametrize("sf", [0.05, 0.4])
+def test_streaming_verifier_agrees_with_the_partitioned_port(sf):
+    """the low-memory verifier used for the multi-GPU scale factors (regenerates rows on the fly, shared CAS table) and the
+    partitioned port are different algorithms over the same generators: same fingerprint"""
+    t = O.q3_generate(sf, threads=2)
+    _, fp, st = O.bench_q3(t, 4)
+    sfp, joined, qualified = O.q3_stream_fingerprint(sf, threads=3)
+    assert sfp == fp and joined == st["joined_rows"] and qualified == st["orders_of_building_customers"]
