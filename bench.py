@@ -202,8 +202,8 @@ def secondary_configs(ctx, D, peak):
     pk = ctx.generate_i64(D.GEN_SPARSE_OF, 42, 43, nb, 0, npr); pp = ctx.generate_i64(D.GEN_SPLITMIX, 8, 0, 0, 0, npr)
     build_cols, probe_cols = [col(bk, nb), col(bp, nb)], [col(pk, npr), col(pp, npr)]
 
-    def join_step(keep=False):
-        j = D.HashJoinHandle(ctx, [D.INT64, D.INT64], [D.INT64, D.INT64], [0], [0], [0, 0, 1], [0, 1, 1])
+    def join_step(keep=False, ordered=True):
+        j = D.HashJoinHandle(ctx, [D.INT64, D.INT64], [D.INT64, D.INT64], [0], [0], [0, 0, 1], [0, 1, 1], ordered_output=ordered)
         j.push_build_device(build_cols); j.finish_build()
         j.push_probe_device(probe_cols); j.finish_probe()
         rows = j.metric("output_rows")
@@ -236,6 +236,22 @@ def secondary_configs(ctx, D, peak):
     out["C2_join_100Mx10M_sparse_unique"] = {"ms_per_step": ms, "rows_per_s": (nb + npr) / ms * 1e3, "achieved_gbs": algo / ms / 1e6, "frac": algo / ms / 1e6 / peak,
                                              "probe_kernel_ms": pms / max(pn, 1), "probe_kernel_frac": 40.0 * npr / (pms / max(pn, 1)) / 1e6 / peak if pn else None,
                                              "fingerprint": fp, "verified": "rows + sum(k + 3 pb + 5 pp) mod 2^64 == closed form over the generators"}
+    # the same join when the consumer ignores row order (ordered_output = 0): radix-partitioned probe, TMA-staged partition pass
+    for _ in range(2):
+        join_step(ordered=False)
+    ctx.set_kernel_timing(True); ctx.kernel_time_reset()
+    ctx.record(e0)
+    for _ in range(5):
+        join_step(ordered=False)
+    ctx.record(e1)
+    ms_r = ctx.elapsed_ms(e0, e1) / 5
+    rp_ms, rp_n = ctx.kernel_time("radix_partition"); pr_ms, pr_n = ctx.kernel_time("join_probe")
+    ctx.set_kernel_timing(False)
+    rows, fp_r = join_step(keep=True, ordered=False)
+    assert fp_r == exp, f"C2 radix join fingerprint {fp_r} != closed form {exp}"
+    out["C2_join_100Mx10M_sparse_unique_radix_partitioned"] = {"ms_per_step": ms_r, "rows_per_s": (nb + npr) / ms_r * 1e3, "achieved_gbs": algo / ms_r / 1e6, "frac": algo / ms_r / 1e6 / peak,
+                                                               "partition_ms": rp_ms / max(rp_n, 1), "probe_kernel_ms": pr_ms / max(pr_n, 1), "fingerprint": fp_r,
+                                                               "note": "ordered_output = 0: probe side radix-partitioned on the top hash bits (TMA bulk loads / stores), per-partition probe with the sub-table L2-resident"}
     for b in (bk, bp, pk, pp):
         b.free()
     # ---- C3: group-by SUM / COUNT, 1B rows -> 1M groups ----

@@ -592,7 +592,7 @@ class HashJoinHandle(_Operator):
 
     def __init__(self, ctx, build_types, probe_types, on_build, on_probe, out_side, out_index, join_type=JOIN_INNER,
                  null_equality=NULL_EQUALS_NOTHING, batch_size=8192, phj_threshold=None, phj_density=None, force_hash_collisions=False,
-                 null_aware=False):
+                 null_aware=False, ordered_output=True):
         super().__init__(ctx)
         opt = HashJoinOptions()
         ctx.lib.dfgpu_hashjoin_default_options(C.byref(opt))
@@ -603,6 +603,7 @@ class HashJoinHandle(_Operator):
             opt.perfect_hash_join_min_key_density = phj_density
         opt.force_hash_collisions = 1 if force_hash_collisions else 0
         opt.null_aware = 1 if null_aware else 0
+        opt.ordered_output = 1 if ordered_output else 0   # 0: the consumer ignores row order (aggregate / repartition above) -> the radix-partitioned probe may run
         ctx.check(ctx.lib.dfgpu_hashjoin_create(ctx.h, _i32arr(build_types), len(build_types), _i32arr(probe_types), len(probe_types),
                                                 _i32arr(on_build), _i32arr(on_probe), len(on_build), _i32arr(out_side), _i32arr(out_index),
                                                 len(out_side), C.byref(opt), C.byref(self.h)))

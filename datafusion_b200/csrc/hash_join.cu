@@ -1097,6 +1097,8 @@ __global__ void mark_from_idx_kernel(const uint32_t* __restrict__ idx, int64_t n
 
 }  // namespace dfgpu
 
+#include "radix_probe.cuh"
+
 // ==========================================================================================
 // operator state
 // ==========================================================================================
@@ -1133,7 +1135,7 @@ struct dfgpu_hashjoin {
   std::deque<BatchPtr> outq;
   // metrics (BuildProbeJoinMetrics, joins/utils.rs:1756-1778)
   int64_t m_build_rows = 0, m_build_batches = 0, m_input_rows = 0, m_input_batches = 0, m_output_rows = 0, m_output_batches = 0,
-          m_array_map = 0, m_probe_hits = 0;
+          m_array_map = 0, m_probe_hits = 0, m_radix_probes = 0;
   bool probe_side_non_empty = false;
   bool probe_has_null = false;   // null-aware LeftAnti: a NULL probe key was seen (JoinLeftData::probe_side_has_null)
 };
@@ -1563,6 +1565,70 @@ static void push_probe(dfgpu_hashjoin* j, std::vector<DCol>&& cols) {
       oc.dst[c] = d.own_values->ptr;
       oc.src[c] = j->out_kind[c] == 0 ? cols[j->out_src[c]].values : nullptr;
       out->cols[c] = std::move(d);
+    }
+    // ---- radix-partitioned probe (row order not required, table several times the L2): radix_probe.cuh ----
+    {
+      static const int radix_env = getenv("DFGPU_JOIN_RADIX") ? atoi(getenv("DFGPU_JOIN_RADIX")) : 1;
+      static const int radix_mb = std::max(1, getenv("DFGPU_JOIN_RADIX_MB") ? atoi(getenv("DFGPU_JOIN_RADIX_MB")) : 40);
+      const size_t tbytes = (size_t)j->iref.cap * 8 * j->inline_words;
+      const int force_parts = getenv("DFGPU_JOIN_RADIX_PARTS") ? atoi(getenv("DFGPU_JOIN_RADIX_PARTS")) : 0;   // tests force the path on small inputs
+      bool radix = radix_env && !j->opt.ordered_output && !j->iref.dense && !j->iref.bucket && !need_pidx && pk.n == 1 && pk.width[0] == 8 && !pk.valid[0] &&
+                   ((uintptr_t)pk.ptr[0] % 16 == 0) && ((tbytes > (size_t)96 << 20 && n >= (1ll << 22)) || force_parts >= 2);
+      // every probe-side output column must be the key column or ONE other plain 8-byte column (it rides in the 16-byte record)
+      int carry = -1;
+      RadixOut ro;
+      memset(&ro, 0, sizeof(ro));
+      ro.n = oc.n;
+      for (int c = 0; c < oc.n && radix; ++c) {
+        ro.width[c] = oc.width[c]; ro.dst[c] = oc.dst[c]; ro.shift[c] = oc.shift[c];
+        if (oc.kind[c] == 1) { ro.kind[c] = 2; continue; }
+        const int src = j->out_src[c];
+        if (src == j->on_probe[0]) { ro.kind[c] = 0; continue; }
+        if (type_width(cols[src].type) != 8 || ((uintptr_t)cols[src].values % 16 != 0) || (carry >= 0 && carry != src)) { radix = false; break; }
+        carry = src; ro.kind[c] = 1;
+      }
+      if (radix) {
+        int bits = 1;
+        const size_t want = force_parts >= 2 ? (size_t)force_parts : (tbytes + ((size_t)radix_mb << 20) - 1) / ((size_t)radix_mb << 20);
+        while ((1u << bits) < want && bits < 6) ++bits;
+        const int P = 1 << bits;
+        const unsigned long long* keys = (const unsigned long long*)pk.ptr[0];
+        const unsigned long long* vals = carry >= 0 ? (const unsigned long long*)cols[carry].values : keys;
+        DevBuf recs(ctx, (size_t)n * 16), meta(ctx, (size_t)(3 * kRadixMaxParts + 8) * 8);
+        meta.zero();
+        unsigned long long* counts = meta.as<unsigned long long>();
+        unsigned long long* cursor = counts + kRadixMaxParts;
+        unsigned long long* bounds = cursor + kRadixMaxParts;      // [P + 1]
+        unsigned long long* rtot = bounds + kRadixMaxParts + 1;    // output rows
+        unsigned int* rtile = (unsigned int*)(rtot + 1);
+        static bool attr_set = false;
+        if (!attr_set) { DF_CUDA(cudaFuncSetAttribute(radix_scatter_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kRadixTile * 8)); attr_set = true; }
+        {
+          KernelTimer kt(ctx, "radix_partition");
+          radix_hist_kernel<<<kNumSMs * 8, 256, 0, ctx->stream>>>(keys, n, bits, counts);
+          DF_LAUNCH_CHECK(ctx);
+          radix_prefix_kernel<<<1, 32, 0, ctx->stream>>>(counts, P, cursor, bounds);
+          DF_LAUNCH_CHECK(ctx);
+          const int64_t rtiles = (n + kRadixTile - 1) / kRadixTile;
+          radix_scatter_tma_kernel<<<(int)std::min<int64_t>(rtiles, kNumSMs * 3), kRadixThreads, 4 * kRadixTile * 8, ctx->stream>>>(keys, vals, n, bits, cursor, recs.as<RadixRec>());
+          DF_LAUNCH_CHECK(ctx);
+        }
+        {
+          KernelTimer kt(ctx, "join_probe");
+          if (j->inline_words == 2) radix_probe_kernel<2><<<kNumSMs * 6, 256, 0, ctx->stream>>>(recs.as<RadixRec>(), n, j->iref, ro, rtile, rtot);
+          else radix_probe_kernel<1><<<kNumSMs * 6, 256, 0, ctx->stream>>>(recs.as<RadixRec>(), n, j->iref, ro, rtile, rtot);
+          DF_LAUNCH_CHECK(ctx);
+        }
+        unsigned long long hrows = 0;
+        DF_CUDA(cudaMemcpyAsync(&hrows, rtot, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        DF_CUDA(cudaStreamSynchronize(ctx->stream));
+        out->rows = (int64_t)hrows;
+        for (int c = 0; c < oc.n; ++c) out->cols[c].length = out->rows;
+        j->m_probe_hits += (int64_t)hrows;
+        j->m_radix_probes++;
+        if (out->rows > 0) emit_batch(j, std::move(out));
+        return;
+      }
     }
     DevBuf pidx;
     if (need_pidx) { pidx.alloc(ctx, (size_t)n * 4); oc.pidx_out = pidx.as<uint32_t>(); }
@@ -2042,6 +2108,7 @@ int64_t dfgpu_hashjoin_metric(dfgpu_hashjoin* j, const char* name) {
   if (s == "output_batches") return j->m_output_batches;
   if (s == "array_map_created_count") return j->m_array_map;
   if (s == "probe_hits") return j->m_probe_hits;
+  if (s == "radix_partitioned_probes") return j->m_radix_probes;
   if (s == "build_distinct_keys") return j->distinct;
   if (s == "build_unique") return j->unique ? 1 : 0;
   if (s == "build_null_key_rows") return j->null_rows;

@@ -6,7 +6,7 @@ if [ "$1" == "--gpus" ]; then G="--gpus $2"; shift 2; fi
 T=$1; shift
 for i in $(seq 1 40); do
   out=$(/usr/local/graft/bin/gpurun $G --timeout $T -- "$@" 2>&1)
-  if echo "$out" | grep -q "status=transient\|status=busy\|rc=3"; then sleep 45; continue; fi
+  if echo "$out" | grep -q "status=transient\|status=busy\|rc=3\|already running"; then sleep 45; continue; fi
   echo "$out"; exit 0
 done
 echo "$out"; exit 3

@@ -249,3 +249,29 @@ def test_gpu_null_aware_anti_large_random(gpu_ctx):
         got = gpu_hash_join(gpu_ctx, build, probe, [0], [0], side, idx, gjt, probe_batch_rows=30000 if jt == O.J_LEFT_ANTI else 40000, null_aware=True)
         assert len(exp[0][0]) > 0
         assert_cols_equal(got, exp, ordered=False, what=f"null-aware {jt}")
+
+
+@pytest.mark.parametrize("parts", [2, 8, 64])
+@pytest.mark.parametrize("with_payload", [True, False])
+def test_gpu_radix_partitioned_probe_gives_the_same_rows(gpu_ctx, monkeypatch, parts, with_payload):
+    """The radix-partitioned probe (radix_probe.cuh: TMA-staged partition pass + per-partition probe; taken when the caller does not need
+    probe order) must return the reference's rows as a multiset: unique build keys, ~60 % hit rate, odd row counts, a ragged last 2048-row
+    tile, several probe batches.  DFGPU_JOIN_RADIX_PARTS forces the path on inputs far smaller than the L2."""
+    rng = np.random.default_rng(91 + parts)
+    nb, npr = 30_000, 201_777
+    bk = rng.permutation(100_000)[:nb].astype(np.int64) * 1_000_003 - 5
+    build = [(bk, None), (rng.integers(-2**62, 2**62, nb).astype(np.int64), None)]
+    pk = rng.integers(0, 100_000, npr).astype(np.int64) * 1_000_003 - 5
+    probe = [(pk, None), (rng.integers(-2**62, 2**62, npr).astype(np.int64), None)]
+    side, idx = ([0, 0, 1, 1], [0, 1, 0, 1]) if with_payload else ([0, 1, 1], [0, 0, 1])
+    exp = O.hash_join(build, probe, [0], [0], side, idx, phj_threshold=0, phj_density=float("inf"))
+    monkeypatch.setenv("DFGPU_JOIN_RADIX_PARTS", str(parts))
+    got, h = gpu_hash_join(gpu_ctx, build, probe, [0], [0], side, idx, phj=(0, float("inf")), probe_batch_rows=70_001, device=True, return_handle=True, ordered_output=False)
+    assert h.metric("radix_partitioned_probes") == 3 and h.metric("array_map_created_count") == 0
+    h.close()
+    assert_cols_equal(got, exp, ordered=False, what=f"radix probe P={parts} payload={with_payload}")
+    # with ordered_output (the default) the same handle configuration keeps the exact reference order and never takes the radix path
+    got, h = gpu_hash_join(gpu_ctx, build, probe, [0], [0], side, idx, phj=(0, float("inf")), probe_batch_rows=70_001, device=True, return_handle=True)
+    assert h.metric("radix_partitioned_probes") == 0
+    h.close()
+    assert_cols_equal(got, exp, ordered=True, what="ordered path untouched")
