@@ -20,6 +20,10 @@ struct ENode {
   int out_type;
   const void* col; const uint8_t* valid; int64_t voff;  // COLUMN (BOOL: voff is also the value bit offset)
   uint64_t lit; int lit_null;
+  // short-circuit guards (BinaryExpr::evaluate, binary.rs:536-600 + check_short_circuit :1182): when this node lies in the RHS of an
+  // AND / OR whose LHS lets the reference skip or pre-select the RHS for this batch, an error raised here counts only on the rows the
+  // reference would have evaluated: bit s of g_and = "stack slot s (that AND's LHS) must be TRUE", of g_or = "... must be FALSE".
+  uint16_t g_and, g_or;
 };
 struct EProgram { int n; ENode node[kMaxNodes]; };
 
@@ -228,7 +232,16 @@ __device__ __forceinline__ uint64_t eval_nodes(const ENode* __restrict__ nodes, 
       }
       case DFGPU_EXPR_BINARY: {
     uint64_t r; bool ok;
-    eval_binary(nd, sv[sp - 2], sk[sp - 2], sv[sp - 1], sk[sp - 1], &r, &ok, err);
+    int e = 0;
+    eval_binary(nd, sv[sp - 2], sk[sp - 2], sv[sp - 1], sk[sp - 1], &r, &ok, &e);
+    if (e) {
+      bool counts = true;
+      for (int g = 0; g < kMaxStack; ++g) {
+        if ((nd.g_and >> g) & 1) counts = counts && sk[g] && sv[g];
+        if ((nd.g_or >> g) & 1) counts = counts && sk[g] && !sv[g];
+      }
+      if (counts) *err |= e;
+    }
     sp -= 1; sv[sp - 1] = r; sk[sp - 1] = ok;
     break;
       }
@@ -239,7 +252,19 @@ __device__ __forceinline__ uint64_t eval_nodes(const ENode* __restrict__ nodes, 
     if (cls_of(nd.out_type) == C_F64) sv[sp - 1] ^= 0x8000000000000000ull;
     else sv[sp - 1] = wrap_to_type(0ull - sv[sp - 1], nd.out_type);  // neg_wrapping
     break;
-      case DFGPU_EXPR_CAST: sv[sp - 1] = cast_value(sv[sp - 1], nd.in_type, nd.out_type, sk[sp - 1], err); break;
+      case DFGPU_EXPR_CAST: {
+    int e = 0;
+    sv[sp - 1] = cast_value(sv[sp - 1], nd.in_type, nd.out_type, sk[sp - 1], &e);
+    if (e) {
+      bool counts = true;
+      for (int g = 0; g < kMaxStack; ++g) {
+        if ((nd.g_and >> g) & 1) counts = counts && sk[g] && sv[g];
+        if ((nd.g_or >> g) & 1) counts = counts && sk[g] && !sv[g];
+      }
+      if (counts) *err |= e;
+    }
+    break;
+      }
     }
   }
   *ok_out = sk[0];
@@ -274,7 +299,17 @@ __device__ __forceinline__ uint64_t eval_nodes_reg(const ENode* __restrict__ nod
     } else if (nd.kind == DFGPU_EXPR_BINARY) {
       uint64_t a = 0, b = 0, r; bool ak = false, bk = false, ok;
       DF_GET(sp - 2, a, ak); DF_GET(sp - 1, b, bk);
-      eval_binary(nd, a, ak, b, bk, &r, &ok, err);
+      int e = 0;
+      eval_binary(nd, a, ak, b, bk, &r, &ok, &e);
+      if (e) {
+        bool counts = true;
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) {
+          if ((nd.g_and >> d) & 1) counts = counts && sk[d] && sv[d];
+          if ((nd.g_or >> d) & 1) counts = counts && sk[d] && !sv[d];
+        }
+        if (counts) *err |= e;
+      }
       sp -= 1;
       DF_SET(sp - 1, r, ok);
     } else {
@@ -288,7 +323,20 @@ __device__ __forceinline__ uint64_t eval_nodes_reg(const ENode* __restrict__ nod
           if (cls_of(nd.out_type) == C_F64) a ^= 0x8000000000000000ull;
           else a = wrap_to_type(0ull - a, nd.out_type);  // neg_wrapping
           break;
-        case DFGPU_EXPR_CAST: a = cast_value(a, nd.in_type, nd.out_type, ak, err); break;
+        case DFGPU_EXPR_CAST: {
+          int e = 0;
+          a = cast_value(a, nd.in_type, nd.out_type, ak, &e);
+          if (e) {
+            bool counts = true;
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) {
+              if ((nd.g_and >> d) & 1) counts = counts && sk[d] && sv[d];
+              if ((nd.g_or >> d) & 1) counts = counts && sk[d] && !sv[d];
+            }
+            if (counts) *err |= e;
+          }
+          break;
+        }
       }
       DF_SET(sp - 1, a, ak);
     }

@@ -280,7 +280,66 @@ ExprPlan plan_expr(const int32_t* schema_types, int n_cols, const dfgpu_expr_nod
   }
   DF_CHECK(stack.size() == 1, DFGPU_ERR_INVALID, "expression: malformed program (stack must end with one value)");
   p.root_type = p.out_type[n_nodes - 1];
+  // ---- short-circuit guards: AND / OR nodes whose RHS can raise an error ----
+  {
+    std::vector<int> start(n_nodes), depth_before(n_nodes);
+    int sp = 0;
+    for (int i = 0; i < n_nodes; ++i) {
+      depth_before[i] = sp;
+      const int k = nodes[i].kind;
+      if (k == DFGPU_EXPR_COLUMN || k == DFGPU_EXPR_LITERAL) { start[i] = i; sp++; }
+      else if (k == DFGPU_EXPR_BINARY) { const int rhs_start = start[i - 1]; start[i] = start[rhs_start - 1]; sp--; }
+      else start[i] = start[i - 1];
+    }
+    for (int i = 0; i < n_nodes; ++i) {
+      if (nodes[i].kind != DFGPU_EXPR_BINARY || (nodes[i].a != DFGPU_OP_AND && nodes[i].a != DFGPU_OP_OR)) continue;
+      const int rhs_start = start[i - 1], lhs_start = start[rhs_start - 1];
+      bool can_error = false;
+      for (int j = rhs_start; j < i; ++j) {
+        if (nodes[j].kind == DFGPU_EXPR_CAST) can_error = true;
+        if (nodes[j].kind == DFGPU_EXPR_BINARY && (nodes[j].a == DFGPU_OP_DIVIDE || nodes[j].a == DFGPU_OP_MODULO) && !type_is_float(p.in_type[j])) can_error = true;
+      }
+      if (!can_error) continue;
+      ExprGuard g;
+      g.op_idx = i; g.lhs_start = lhs_start; g.rhs_start = rhs_start; g.slot = depth_before[lhs_start]; g.is_and = nodes[i].a == DFGPU_OP_AND;
+      if (g.slot < 16) p.guards.push_back(g);
+    }
+  }
   return p;
+}
+
+// check_short_circuit (binary.rs:1182-1290) per batch: the RHS of AND is skipped when the LHS has no NULLs and is all false, and evaluated
+// only on the LHS-true rows when at most 20 % of them are true (PRE_SELECTION_THRESHOLD); OR symmetrically; a scalar LHS always
+// short-circuits.  In those cases an error raised inside the RHS counts only on the rows the reference evaluates.
+std::vector<std::pair<uint16_t, uint16_t>> resolve_guards(dfgpu_ctx* ctx, const ExprPlan& plan, const std::vector<DCol>& cols, int64_t n) {
+  std::vector<std::pair<uint16_t, uint16_t>> masks(plan.nodes.size(), {0, 0});
+  if (plan.guards.empty() || n <= 0) return masks;
+  std::vector<int32_t> types;
+  for (auto& c : cols) types.push_back(c.type);
+  for (const ExprGuard& g : plan.guards) {
+    bool active = false;
+    const int lhs_n = g.rhs_start - g.lhs_start;
+    if (lhs_n == 1 && plan.nodes[g.lhs_start].kind == DFGPU_EXPR_LITERAL) active = !plan.nodes[g.lhs_start].is_null;   // scalar LHS: ReturnLeft / ReturnRight
+    else {
+      bool evaluable = true;
+      for (int j = g.lhs_start; j < g.rhs_start; ++j) if (plan.nodes[j].kind == DFGPU_EXPR_COLUMN && plan.nodes[j].a >= (int)cols.size()) evaluable = false;
+      if (evaluable) {
+        ExprPlan sub = plan_expr(types.data(), (int)types.size(), plan.nodes.data() + g.lhs_start, lhs_n);
+        EvalResult ev = evaluate_expr(ctx, sub, cols, n, true, false);
+        const int64_t nulls = ev.column.validity ? n - count_set_bits(ctx, ev.column.validity, ev.column.offset, n) : 0;
+        if (nulls == 0) {
+          const int64_t t = count_set_bits(ctx, (const uint8_t*)ev.column.values, ev.column.offset, n);
+          const int64_t rare = g.is_and ? t : n - t;          // the rows that still depend on the RHS
+          active = rare == 0 || ((float)rare / (float)n <= 0.2f);
+        }
+      }
+    }
+    if (!active) continue;
+    for (int j = g.rhs_start; j < g.op_idx; ++j) {
+      if (g.is_and) masks[j].first |= (uint16_t)(1u << g.slot); else masks[j].second |= (uint16_t)(1u << g.slot);
+    }
+  }
+  return masks;
 }
 
 uint64_t literal_bits(const dfgpu_expr_node& nd) {
@@ -301,7 +360,7 @@ uint64_t literal_bits(const dfgpu_expr_node& nd) {
   }
 }
 
-void bind_program(const ExprPlan& plan, const std::vector<DCol>& cols, EProgram* prog) {
+void bind_program(const ExprPlan& plan, const std::vector<DCol>& cols, EProgram* prog, const std::vector<std::pair<uint16_t, uint16_t>>* gmasks) {
   memset(prog, 0, sizeof(*prog));
   prog->n = (int)plan.nodes.size();
   for (int i = 0; i < prog->n; ++i) {
@@ -315,6 +374,7 @@ void bind_program(const ExprPlan& plan, const std::vector<DCol>& cols, EProgram*
     } else if (nd.kind == DFGPU_EXPR_LITERAL) {
       e.lit = literal_bits(nd); e.lit_null = nd.is_null;
     }
+    if (gmasks) { e.g_and = (*gmasks)[i].first; e.g_or = (*gmasks)[i].second; }
   }
 }
 
@@ -348,7 +408,8 @@ EvalResult evaluate_expr(dfgpu_ctx* ctx, const ExprPlan& plan, const std::vector
     }
   }
   EProgram prog;
-  bind_program(plan, cols, &prog);
+  const auto gmasks = resolve_guards(ctx, plan, cols, n);
+  bind_program(plan, cols, &prog, &gmasks);
   const int rt = plan.root_type;
   if (want_column) {
     res.column = alloc_col(ctx, rt, n, true);
@@ -486,7 +547,8 @@ static void filter_push(dfgpu_filter* f, const std::vector<DCol>& cols) {
                                                                           fc, desc.as<unsigned long long>(), counter, totals, err.as<int>());
       } else {
         EProgram prog;
-        bind_program(plan, cols, &prog);
+        const auto gmasks = resolve_guards(ctx, plan, cols, n);
+        bind_program(plan, cols, &prog, &gmasks);
         progbuf.alloc(ctx, sizeof(EProgram));
         DF_CUDA(cudaMemcpyAsync(progbuf.ptr, &prog, sizeof(EProgram), cudaMemcpyHostToDevice, ctx->stream));
         DF_CUDA(cudaStreamSynchronize(ctx->stream));  // `prog` lives on this stack frame

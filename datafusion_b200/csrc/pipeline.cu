@@ -869,6 +869,8 @@ static ColRef col_ref(const DCol& c) {
 // bind a planned expression into pool nodes; virtual columns >= n_cols become payload-field nodes
 static int bind_pool(const dfgpu_pipeline* p, const ExprPlan& plan, const std::vector<DCol>& cols, PipeParams* pp, int* pool_used) {
   const int start = *pool_used;
+  const int64_t n_rows = cols.empty() ? 0 : cols[0].length;
+  const auto gmasks = resolve_guards(p->ctx, plan, cols, n_rows);   // short-circuit AND / OR: which RHS errors count on which rows (binary.rs:1182)
   DF_CHECK(start + (int)plan.nodes.size() <= kPoolNodes, DFGPU_ERR_UNSUPPORTED, "pipeline: expressions too large (56 nodes in total)");
   for (size_t i = 0; i < plan.nodes.size(); ++i) {
     const dfgpu_expr_node& nd = plan.nodes[i];
@@ -886,6 +888,7 @@ static int bind_pool(const dfgpu_pipeline* p, const ExprPlan& plan, const std::v
     } else if (nd.kind == DFGPU_EXPR_LITERAL) {
       e.lit = literal_bits(nd); e.lit_null = nd.is_null;
     }
+    e.g_and = gmasks[i].first; e.g_or = gmasks[i].second;
   }
   *pool_used = start + (int)plan.nodes.size();
   return start;

@@ -407,8 +407,80 @@ def _total_order_key(x: np.ndarray) -> np.ndarray:
     return b ^ ((b >> 63).astype(np.uint64) >> np.uint64(1)).astype(np.int64)
 
 
+PRE_SELECTION_THRESHOLD = np.float32(0.2)   # binary.rs:1160
+
+
+def _subtree_starts(nodes):
+    st, start = [], [0] * len(nodes)
+    for i, nd in enumerate(nodes):
+        if nd[0] in (E_COLUMN, E_LITERAL):
+            start[i] = i
+        elif nd[0] == E_BINARY:
+            start[i] = start[start[i - 1] - 1]
+        else:
+            start[i] = start[i - 1]
+    return start
+
+
 def eval_expr(cols: Sequence[Col], nodes: Sequence[tuple], col_dtypes: Optional[Sequence] = None) -> Col:
-    """nodes: [(kind, a, np dtype or None, is_null, lit)] in post-order; returns (values, valid)."""
+    """PhysicalExpr::evaluate over a batch.  nodes: [(kind, a, np dtype or None, is_null, lit)] in post-order; returns (values, valid).
+    AND / OR follow BinaryExpr::evaluate (binary.rs:536-600): the LHS is evaluated first and check_short_circuit (:1182-1290) may return
+    it as is, return the RHS, or evaluate the RHS only on the pre-selected rows (filter_record_batch + scatter) — which also decides on
+    which rows an error inside the RHS (division by zero, failed cast) can surface."""
+    nodes = list(nodes)
+    starts = _subtree_starts(nodes)
+
+    def ev(lo, hi, cs):
+        kind, a = nodes[hi - 1][0], nodes[hi - 1][1]
+        n = len(cs[0][0]) if cs else 0
+        if kind == E_BINARY and a in (OP_AND, OP_OR):
+            is_and = a == OP_AND
+            rlo = starts[hi - 2]
+            lhs = ev(lo, rlo, cs)
+            lv, lval = lhs
+            scalar_lhs = (rlo - lo == 1 and nodes[lo][0] == E_LITERAL)
+            if scalar_lhs:
+                if nodes[lo][3]:                       # NULL scalar: no short circuit
+                    return _kleene(is_and, lhs, ev(rlo, hi - 1, cs))
+                is_true = bool(nodes[lo][4])
+                return lhs if (is_and and not is_true) or (not is_and and is_true) else ev(rlo, hi - 1, cs)
+            if lval is not None and not np.asarray(lval, bool).all() or n == 0:
+                return _kleene(is_and, lhs, ev(rlo, hi - 1, cs))          # arrays with nulls can't be short-circuited
+            tc = int(np.count_nonzero(lv))
+            if is_and and tc == 0 or (not is_and and tc == n):
+                return (np.asarray(lv, bool), None)                          # ReturnLeft
+            if is_and and tc == n or (not is_and and tc == 0):
+                return ev(rlo, hi - 1, cs)                                   # ReturnRight
+            rare = tc if is_and else n - tc
+            if np.float32(rare) / np.float32(n) <= PRE_SELECTION_THRESHOLD:
+                mask = np.asarray(lv, bool) if is_and else ~np.asarray(lv, bool)
+                sel = [(np.asarray(v)[mask], None if val is None else np.asarray(val, bool)[mask]) for v, val in cs]
+                rv, rval = ev(rlo, hi - 1, sel)
+                out = np.full(n, not is_and, bool)                           # fill_value: false for AND, true for OR
+                out[mask] = np.asarray(rv, bool)
+                valid = None
+                if rval is not None and not np.asarray(rval, bool).all():
+                    valid = np.ones(n, bool); valid[mask] = rval
+                    out[mask] &= rval
+                return (out, valid)
+            return _kleene(is_and, lhs, ev(rlo, hi - 1, cs))
+        if kind in (E_COLUMN, E_LITERAL):
+            return _eval_flat(cs, nodes[lo:hi])
+        if kind == E_BINARY:
+            rlo = starts[hi - 2]
+            l, r = ev(lo, rlo, cs), ev(rlo, hi - 1, cs)
+            return _eval_flat([l, r], [(E_COLUMN, 0, None, 0, 0), (E_COLUMN, 1, None, 0, 0), nodes[hi - 1]])
+        c = ev(lo, hi - 1, cs)
+        return _eval_flat([c], [(E_COLUMN, 0, None, 0, 0), nodes[hi - 1]])
+    return ev(0, len(nodes), list(cols))
+
+
+def _kleene(is_and, lhs, rhs):
+    return _eval_flat([lhs, rhs], [(E_COLUMN, 0, None, 0, 0), (E_COLUMN, 1, None, 0, 0), (E_BINARY, OP_AND if is_and else OP_OR, None, 0, 0)])
+
+
+def _eval_flat(cols: Sequence[Col], nodes: Sequence[tuple]) -> Col:
+    """the straight stack machine (every node over every row)"""
     n = len(cols[0][0]) if cols else 0
     st: List[Col] = []
     for kind, a, dt, is_null, lit in nodes:
