@@ -523,6 +523,9 @@ __global__ void __launch_bounds__(256) agg_emit_kernel(EmitDesc d, const uint32_
   }
 }
 
+__global__ void __launch_bounds__(256) salt_kernel(uint16_t* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (uint16_t)(i & 1023);
+}
 __global__ void fill_u64_kernel(unsigned long long* p, uint64_t n, unsigned long long v) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -563,6 +566,11 @@ struct dfgpu_agg {
   uint64_t cap = 0;
   std::deque<BatchPtr> outq;
   int64_t m_input_rows = 0, m_output_rows = 0, m_rehashes = 0, m_num_groups = 0, m_input_batches = 0;
+  // no GROUP BY (AggregateStream, aggregates/aggregate_stream.rs): a composite of two grouped handles, see scalar_* below
+  bool scalar = false;
+  dfgpu_agg* inner1 = nullptr;   // rows -> 1024 partial states (hidden key = row & 1023: a single accumulator would serialise every atomic)
+  dfgpu_agg* inner2 = nullptr;   // <= 1024 states -> the one output row
+  std::vector<int> scalar_state_types;
 };
 
 namespace dfgpu {
@@ -646,8 +654,24 @@ static void ensure_seen(dfgpu_agg* a, AggState& s) {
   DF_LAUNCH_CHECK(ctx);
 }
 
+static void agg_finish(dfgpu_agg* a);
 static void agg_push(dfgpu_agg* a, const std::vector<DCol>& cols) {
   DF_CHECK(!a->finished, DFGPU_ERR_STATE, "push after finish");
+  if (a->scalar) {
+    DF_CHECK(cols.size() == a->input_types.size(), DFGPU_ERR_INVALID, "aggregate input column count mismatch");
+    dfgpu_ctx* ctx = a->ctx;
+    set_device(ctx);
+    const int64_t n = cols.empty() ? 0 : cols[0].length;
+    a->m_input_rows += n; a->m_input_batches++;
+    if (n == 0) return;
+    DCol salt = alloc_col(ctx, DFGPU_UINT16, n, false);
+    salt_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>((uint16_t*)salt.own_values->ptr, n);
+    DF_LAUNCH_CHECK(ctx);
+    std::vector<DCol> v{salt};
+    v.insert(v.end(), cols.begin(), cols.end());
+    agg_push(a->inner1, v);
+    return;
+  }
   DF_CHECK(cols.size() == a->input_types.size(), DFGPU_ERR_INVALID, "aggregate input column count mismatch");
   dfgpu_ctx* ctx = a->ctx;
   set_device(ctx);
@@ -784,8 +808,59 @@ static void agg_push(dfgpu_agg* a, const std::vector<DCol>& cols) {
   }
 }
 
+// one all-NULL / zero state row: what fresh accumulators report (SUM / MIN / MAX / AVG sum: NULL, counts: 0)
+static std::vector<DCol> scalar_empty_state(dfgpu_agg* a) {
+  dfgpu_ctx* ctx = a->ctx;
+  std::vector<DCol> v;
+  DCol key = alloc_col(ctx, DFGPU_UINT16, 1, false);
+  key.own_values->zero();
+  v.push_back(key);
+  size_t k = 0;
+  for (auto& st : a->inner1->aggs) {
+    const int n_state = st.func == DFGPU_AGG_AVG ? 2 : 1;
+    for (int j = 0; j < n_state; ++j, ++k) {
+      const int t = a->scalar_state_types[k];
+      const bool is_count = st.func == DFGPU_AGG_COUNT || st.func == DFGPU_AGG_COUNT_STAR || (st.func == DFGPU_AGG_AVG && j == 0);
+      DCol c = alloc_col(ctx, t, 1, !is_count);
+      c.own_values->zero();
+      if (!is_count) { c.own_validity->zero(); c.null_count = 1; }
+      v.push_back(c);
+    }
+  }
+  return v;
+}
+
 static void agg_finish(dfgpu_agg* a) {
   DF_CHECK(!a->finished, DFGPU_ERR_STATE, "finish called twice");
+  if (a->scalar) {
+    a->finished = true;
+    dfgpu_ctx* ctx = a->ctx;
+    set_device(ctx);
+    agg_finish(a->inner1);
+    bool any = false;
+    while (!a->inner1->outq.empty()) {
+      BatchPtr b = std::move(a->inner1->outq.front());
+      a->inner1->outq.pop_front();
+      if (b->rows == 0) continue;
+      any = true;
+      std::vector<DCol> v = b->cols;
+      DCol key = alloc_col(ctx, DFGPU_UINT16, b->rows, false);   // every partial state merges into ONE group
+      key.own_values->zero();
+      v[0] = key;
+      agg_push(a->inner2, v);
+    }
+    if (!any) agg_push(a->inner2, scalar_empty_state(a));
+    agg_finish(a->inner2);
+    while (!a->inner2->outq.empty()) {
+      BatchPtr b = std::move(a->inner2->outq.front());
+      a->inner2->outq.pop_front();
+      b->cols.erase(b->cols.begin());                            // drop the hidden key
+      a->m_output_rows += b->rows;
+      a->outq.push_back(std::move(b));
+    }
+    a->m_num_groups = 1;
+    return;
+  }
   a->finished = true;
   dfgpu_ctx* ctx = a->ctx;
   set_device(ctx);
@@ -868,7 +943,40 @@ int dfgpu_agg_create(dfgpu_ctx* ctx, const int32_t* input_types, int32_t n_cols,
                      const dfgpu_agg_desc* aggs, int32_t n_aggs, int32_t mode, int64_t batch_size, int64_t capacity_hint, dfgpu_agg** out) {
   DF_API_BEGIN(ctx)
   DF_CHECK(ctx && out, DFGPU_ERR_INVALID, "null argument");
-  DF_CHECK(n_group >= 1 && n_group <= kMaxGroupCols, DFGPU_ERR_UNSUPPORTED, "aggregate: 1..8 group columns supported (no-GROUP-BY aggregation stays on the CPU operator)");
+  DF_CHECK(n_group >= 0 && n_group <= kMaxGroupCols, DFGPU_ERR_UNSUPPORTED, "aggregate: at most 8 group columns");
+  if (n_group == 0) {
+    // ---- AggregateStream (no GROUP BY, aggregates/aggregate_stream.rs): exactly one output row, also for empty input ----
+    DF_CHECK(n_aggs >= 1 && n_aggs <= kMaxAggs, DFGPU_ERR_INVALID, "aggregate without GROUP BY needs 1..8 aggregate expressions");
+    const bool state_in = (mode == DFGPU_AGG_FINAL || mode == DFGPU_AGG_FINAL_PARTITIONED || mode == DFGPU_AGG_PARTIAL_REDUCE);
+    const bool state_out = (mode == DFGPU_AGG_PARTIAL || mode == DFGPU_AGG_PARTIAL_REDUCE);
+    std::unique_ptr<dfgpu_agg> a(new dfgpu_agg());
+    a->ctx = ctx; a->scalar = true; a->mode = mode; a->state_input = state_in; a->state_output = state_out;
+    a->input_types.assign(input_types, input_types + n_cols);
+    std::vector<int32_t> t1{DFGPU_UINT16};
+    t1.insert(t1.end(), input_types, input_types + n_cols);
+    std::vector<dfgpu_agg_desc> d1(aggs, aggs + n_aggs);
+    if (!state_in) for (auto& d : d1) { if (d.func != DFGPU_AGG_COUNT_STAR) d.arg_col += 1; if (d.filter_col >= 0) d.filter_col += 1; }
+    const int32_t g0 = 0;
+    int rc = dfgpu_agg_create(ctx, t1.data(), (int)t1.size(), &g0, 1, d1.data(), n_aggs, state_in ? DFGPU_AGG_PARTIAL_REDUCE : DFGPU_AGG_PARTIAL, batch_size, 1024, &a->inner1);
+    if (rc != DFGPU_OK) throw Error(rc, ctx->last_error);
+    // state schema emitted by inner1: [salt, state columns...]
+    std::vector<int32_t> t2{DFGPU_UINT16};
+    for (auto& st : a->inner1->aggs) {
+      switch (st.func) {
+        case DFGPU_AGG_SUM: t2.push_back(st.cls == 2 ? DFGPU_FLOAT64 : (st.cls == 1 ? DFGPU_UINT64 : DFGPU_INT64)); break;
+        case DFGPU_AGG_COUNT: case DFGPU_AGG_COUNT_STAR: t2.push_back(DFGPU_INT64); break;
+        case DFGPU_AGG_MIN: case DFGPU_AGG_MAX: t2.push_back(st.out_type); break;
+        case DFGPU_AGG_AVG: t2.push_back(DFGPU_UINT64); t2.push_back(DFGPU_FLOAT64); break;
+      }
+    }
+    a->scalar_state_types.assign(t2.begin() + 1, t2.end());
+    std::vector<dfgpu_agg_desc> d2(aggs, aggs + n_aggs);
+    for (auto& d : d2) { d.arg_col = -1; d.filter_col = -1; }
+    rc = dfgpu_agg_create(ctx, t2.data(), (int)t2.size(), &g0, 1, d2.data(), n_aggs, state_out ? DFGPU_AGG_PARTIAL_REDUCE : DFGPU_AGG_FINAL, batch_size, 16, &a->inner2);
+    if (rc != DFGPU_OK) { dfgpu_agg_destroy(a->inner1); a->inner1 = nullptr; throw Error(rc, ctx->last_error); }
+    *out = a.release();
+    return DFGPU_OK;
+  }
   DF_CHECK(n_aggs >= 0 && n_aggs <= kMaxAggs, DFGPU_ERR_UNSUPPORTED, "aggregate: at most 8 aggregate expressions");
   set_device(ctx);
   std::unique_ptr<dfgpu_agg> a(new dfgpu_agg());
@@ -1015,6 +1123,8 @@ int64_t dfgpu_agg_metric(dfgpu_agg* a, const char* name) {
 void dfgpu_agg_destroy(dfgpu_agg* a) {
   if (!a) return;
   cudaSetDevice(a->ctx->device);
+  if (a->inner1) dfgpu_agg_destroy(a->inner1);
+  if (a->inner2) dfgpu_agg_destroy(a->inner2);
   delete a;
 }
 

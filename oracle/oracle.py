@@ -701,3 +701,43 @@ def q3_stream_fingerprint(sf_total: float, seed: int = 1, threads: int = 1, cut:
         raise MemoryError("q3_stream_fingerprint: table allocation failed")
     o = [int(x) for x in out]
     return o[:5], o[5], o[6]
+
+
+def scalar_aggregate(aggs: Sequence[tuple], state: bool = False) -> List[Col]:
+    """AggregateStream (no GROUP BY; aggregates/aggregate_stream.rs:360-400 poll loop, aggregate_batch :437 + finalize_aggregation, aggregates/mod.rs:2993-3020):
+    every input batch updates ONE accumulator per aggregate; at end of input exactly one row is emitted, also for empty input
+    (fresh accumulators: SUM / MIN / MAX / AVG -> NULL, COUNT -> 0).  aggs: [(func, arg: Col | None, filter: Col | None)];
+    state=True gives the Partial output (state columns) instead of the final values."""
+    out: List[Col] = []
+    for ag in aggs:
+        func, arg, filt = ag[0], ag[1], ag[2] if len(ag) > 2 else None
+        if arg is None:
+            n = len(filt[0]) if filt is not None else ag[3]
+            vals, act = np.zeros(n, np.int64), np.ones(n, bool)
+        else:
+            vals = np.asarray(arg[0]); act = np.ones(len(vals), bool) if arg[1] is None else np.asarray(arg[1], bool).copy()
+        if filt is not None:
+            act &= np.asarray(filt[0], bool) & (np.ones(len(act), bool) if filt[1] is None else np.asarray(filt[1], bool))
+        sel = vals[act]
+        cnt = int(act.sum())
+        one = lambda v, dt, valid: (np.array([v], dt), None if valid else np.array([False]))
+        if func in (A_COUNT, A_COUNT_STAR):
+            out.append(one(cnt, np.int64, True))
+        elif func == A_SUM:
+            if vals.dtype.kind == "f":
+                out.append(one(float(sel.astype(np.float64).sum()) if cnt else 0.0, np.float64, cnt > 0))
+            else:
+                dt = np.uint64 if vals.dtype.kind == "u" else np.int64
+                with np.errstate(over="ignore"):
+                    out.append(one(sel.astype(dt).sum(dtype=dt) if cnt else 0, dt, cnt > 0))
+        elif func in (A_MIN, A_MAX):
+            out.append(one((sel.min() if func == A_MIN else sel.max()) if cnt else 0, vals.dtype, cnt > 0))
+        elif func == A_AVG:
+            sm = float(sel.astype(np.float64).sum()) if cnt else 0.0
+            if state:
+                out.append(one(cnt, np.uint64, True)); out.append(one(sm, np.float64, cnt > 0))
+            else:
+                out.append(one(sm / cnt if cnt else 0.0, np.float64, cnt > 0))
+        else:
+            raise ValueError(func)
+    return out

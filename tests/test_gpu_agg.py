@@ -198,3 +198,39 @@ def test_gpu_check_grouping_sets_kat(gpu_ctx):
     part = gpu_group_by(gpu_ctx, cols, [0, 1, 2], [(D.AGG_COUNT, 3, -1)], mode=D.AGG_PARTIAL, batch_rows=8)
     fin = gpu_group_by(gpu_ctx, part, [0, 1, 2], [(D.AGG_COUNT, -1, -1)], mode=D.AGG_FINAL)
     assert grouping_rows(fin[:3], fin[3][0]) == exp
+
+
+@pytest.mark.parametrize("n,batch_rows", [(0, None), (1, None), (300_000, 70_001)])
+def test_gpu_aggregate_without_group_by(gpu_ctx, n, batch_rows):
+    """AggregateStream (no GROUP BY, aggregate_stream.rs): one output row, also for empty input; Single == Final(Partial) for every function"""
+    rng = np.random.default_rng(5 + n)
+    v = rng.integers(-10**12, 10**12, n).astype(np.int64); vv = rng.random(n) > 0.1
+    f = rng.normal(size=n); u = rng.integers(0, 2**40, n).astype(np.uint64)
+    flt = rng.random(n) > 0.5
+    cols = [(v, vv if n else None), (f, None), (u, None), (flt, None)]
+    aggs = [(D.AGG_SUM, 0, -1), (D.AGG_COUNT, 0, -1), (D.AGG_MIN, 0, 3), (D.AGG_MAX, 2, -1), (D.AGG_AVG, 1, -1), (D.AGG_COUNT_STAR, -1, -1), (D.AGG_SUM, 2, 3)]
+    oaggs = [(O.A_SUM, cols[0], None), (O.A_COUNT, cols[0], None), (O.A_MIN, cols[0], cols[3]), (O.A_MAX, cols[2], None), (O.A_AVG, cols[1], None),
+             (O.A_COUNT_STAR, None, None, n), (O.A_SUM, cols[2], cols[3])]
+    exp = O.scalar_aggregate(oaggs)
+    got = gpu_group_by(gpu_ctx, cols, [], aggs, batch_rows=batch_rows, device=True)
+    assert len(got) == len(exp) and all(len(c[0]) == 1 for c in got)
+    for i, (g, e) in enumerate(zip(got, exp)):
+        gvalid = g[1] is None or bool(g[1][0]); evalid = e[1] is None or bool(e[1][0])
+        assert gvalid == evalid, f"aggregate {i} validity"
+        if evalid:
+            if np.asarray(e[0]).dtype.kind == "f":
+                assert np.isclose(float(g[0][0]), float(e[0][0]), rtol=1e-9, atol=1e-9), f"aggregate {i}"
+            else:
+                assert int(g[0][0]) == int(e[0][0]), f"aggregate {i}"
+    # Partial -> Final gives the same row
+    part = gpu_group_by(gpu_ctx, cols, [], aggs, mode=D.AGG_PARTIAL, batch_rows=batch_rows, device=True)
+    pexp = O.scalar_aggregate(oaggs, state=True)
+    assert len(part) == len(pexp) == 8
+    types = [D.INT64, D.INT64, D.INT64, D.UINT64, D.UINT64, D.FLOAT64, D.INT64, D.UINT64]
+    st = [(np.concatenate([c[0], c[0][:0]]), c[1]) for c in part]
+    fin = gpu_group_by(gpu_ctx, st, [], [(a[0], -1, -1) for a in aggs], mode=D.AGG_FINAL, types=types)
+    for i, (g, e) in enumerate(zip(fin, exp)):
+        gvalid = g[1] is None or bool(g[1][0]); evalid = e[1] is None or bool(e[1][0])
+        assert gvalid == evalid
+        if evalid:
+            assert np.isclose(float(g[0][0]), float(e[0][0]), rtol=1e-9, atol=1e-9)
