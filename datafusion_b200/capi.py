@@ -101,7 +101,7 @@ ArrowArray._fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offse
 # every symbol include/dfgpu.h declares (tests check the library exports all of them)
 EXPORTS = [
     "dfgpu_ctx_create", "dfgpu_ctx_destroy", "dfgpu_last_error", "dfgpu_version", "dfgpu_device_count", "dfgpu_sync",
-    "dfgpu_ctx_stream", "dfgpu_malloc", "dfgpu_free", "dfgpu_host_alloc", "dfgpu_host_free", "dfgpu_memcpy_h2d",
+    "dfgpu_ctx_stream", "dfgpu_poll_ready", "dfgpu_malloc", "dfgpu_free", "dfgpu_host_alloc", "dfgpu_host_free", "dfgpu_memcpy_h2d",
     "dfgpu_memcpy_d2h", "dfgpu_memset", "dfgpu_flush_l2", "dfgpu_event_create", "dfgpu_event_record",
     "dfgpu_event_elapsed_ms", "dfgpu_event_destroy", "dfgpu_launch_count", "dfgpu_generate_i64",
     "dfgpu_set_kernel_timing", "dfgpu_kernel_time", "dfgpu_kernel_time_reset",
@@ -153,6 +153,7 @@ def load_library() -> C.CDLL:
     sig("dfgpu_device_count", C.c_int, [])
     sig("dfgpu_sync", C.c_int, [vp])
     sig("dfgpu_ctx_stream", vp, [vp])
+    sig("dfgpu_poll_ready", C.c_int, [vp])
     sig("dfgpu_malloc", C.c_int, [vp, C.c_size_t, P(vp)])
     sig("dfgpu_free", C.c_int, [vp, vp])
     sig("dfgpu_host_alloc", C.c_int, [vp, C.c_size_t, P(vp)])
@@ -261,6 +262,10 @@ class Context:
 
     def sync(self):
         self.check(self.lib.dfgpu_sync(self.h))
+
+    def poll_ready(self) -> bool:
+        """non-blocking: has everything queued on this context's stream completed?"""
+        return self.check(self.lib.dfgpu_poll_ready(self.h)) == 1
 
     @property
     def launches(self) -> int:

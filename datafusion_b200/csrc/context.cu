@@ -145,6 +145,18 @@ int dfgpu_sync(dfgpu_ctx* ctx) {
   DF_CUDA(cudaStreamSynchronize(ctx->stream));
   DF_API_END
 }
+// non-blocking: 1 = every piece of work queued on the ctx stream has completed, 0 = still running, < 0 = error.  The waker side of
+// the async contract: a Gpu*Exec stream's poll_next returns Poll::Pending while this is 0 instead of blocking a tokio worker
+// (execution_plan.rs:549-563 "must yield regularly").
+int dfgpu_poll_ready(dfgpu_ctx* ctx) {
+  if (!ctx) return DFGPU_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaError_t e = cudaStreamQuery(ctx->stream);
+  if (e == cudaSuccess) return 1;
+  if (e == cudaErrorNotReady) { cudaGetLastError(); return 0; }
+  ctx->last_error = std::string("CUDA error in dfgpu_poll_ready: ") + cudaGetErrorString(e);
+  return DFGPU_ERR_CUDA;
+}
 int dfgpu_malloc(dfgpu_ctx* ctx, size_t bytes, void** out) {
   DF_API_BEGIN(ctx)
   set_device(ctx);

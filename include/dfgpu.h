@@ -125,6 +125,9 @@ const char* dfgpu_last_error(dfgpu_ctx* ctx);
 const char* dfgpu_version(void);
 int dfgpu_device_count(void);
 int dfgpu_sync(dfgpu_ctx* ctx);
+/* non-blocking readiness of the ctx stream: 1 = all queued work done, 0 = still running, < 0 = error.  What a Gpu*Exec stream's
+ * poll_next consults before returning Poll::Pending — ExecutionPlan streams must never block a tokio worker (execution_plan.rs:549-563) */
+int dfgpu_poll_ready(dfgpu_ctx* ctx);
 void* dfgpu_ctx_stream(dfgpu_ctx* ctx);
 
 int dfgpu_malloc(dfgpu_ctx* ctx, size_t bytes, void** out);     /* stream-ordered device allocation */

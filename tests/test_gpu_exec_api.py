@@ -93,3 +93,19 @@ def test_aggregate_exec_partial_final_like_check_aggregates(gpu_ctx, task_ctx):
     fres = srt(table_rows(collect(final, task_ctx)))
     assert fres == [[a, v] for a, v in zip(m["final_avg"]["a"], m["final_avg"]["avg"])]
     assert final.metrics()["output_rows"] == 3
+
+
+def test_poll_ready_is_non_blocking_and_becomes_true(gpu_ctx):
+    """dfgpu_poll_ready: the waker side of the async contract (execution_plan.rs:549-563) — never blocks, 1 once the stream has drained"""
+    import time
+    from datafusion_b200 import capi as D
+    gpu_ctx.sync()
+    assert gpu_ctx.poll_ready() is True
+    buf = gpu_ctx.generate_i64(D.GEN_SPLITMIX, 1, 0, 0, 0, 200_000_000)      # queued asynchronously on the ctx stream
+    t0 = time.perf_counter()
+    first = gpu_ctx.poll_ready()
+    assert time.perf_counter() - t0 < 0.05                                     # answered without waiting for the kernel
+    while not gpu_ctx.poll_ready():
+        time.sleep(0.0005)
+    assert gpu_ctx.poll_ready() is True and first in (True, False)
+    buf.free()
