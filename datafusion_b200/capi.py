@@ -112,7 +112,7 @@ EXPORTS = [
     "dfgpu_hashjoin_push_build_device", "dfgpu_hashjoin_push_build_arrow", "dfgpu_hashjoin_finish_build",
     "dfgpu_hashjoin_push_probe_host", "dfgpu_hashjoin_push_probe_device", "dfgpu_hashjoin_push_probe_arrow",
     "dfgpu_hashjoin_finish_probe", "dfgpu_hashjoin_next", "dfgpu_hashjoin_metric", "dfgpu_hashjoin_destroy",
-    "dfgpu_agg_create", "dfgpu_agg_push_host", "dfgpu_agg_push_device", "dfgpu_agg_push_arrow", "dfgpu_agg_finish",
+    "dfgpu_agg_create", "dfgpu_agg_push_host", "dfgpu_agg_push_device", "dfgpu_agg_push_arrow", "dfgpu_agg_set_skip_partial", "dfgpu_agg_finish",
     "dfgpu_agg_next", "dfgpu_agg_metric", "dfgpu_agg_destroy",
     "dfgpu_batch_num_rows", "dfgpu_batch_num_columns", "dfgpu_batch_column", "dfgpu_batch_is_host",
     "dfgpu_batch_export_arrow", "dfgpu_batch_release", "dfgpu_hash_partition_device",
@@ -194,6 +194,7 @@ def load_library() -> C.CDLL:
                                            P(HashJoinOptions), P(vp)])
     sig("dfgpu_hashjoin_set_filter", C.c_int, [vp, P(i32), P(i32), i32, P(ExprNode), i32])
     sig("dfgpu_agg_create", C.c_int, [vp, P(i32), i32, P(i32), i32, P(AggDesc), i32, i32, i64, i64, P(vp)])
+    sig("dfgpu_agg_set_skip_partial", C.c_int, [vp, i64, C.c_double])
     sig("dfgpu_batch_num_rows", i64, [vp])
     sig("dfgpu_batch_num_columns", i32, [vp])
     sig("dfgpu_batch_column", C.c_int, [vp, i32, P(Column)])
@@ -639,6 +640,9 @@ class AggHandle(_Operator):
             descs[i].func, descs[i].arg_col, descs[i].filter_col, descs[i].reserved = f, a, fc, 0
         ctx.check(ctx.lib.dfgpu_agg_create(ctx.h, _i32arr(input_types), len(input_types), _i32arr(group_cols), len(group_cols),
                                            descs, len(aggs), mode, batch_size, capacity_hint, C.byref(self.h)))
+
+    def set_skip_partial(self, probe_rows_threshold: int, probe_ratio_threshold: float = 0.8):
+        self.ctx.check(self.ctx.lib.dfgpu_agg_set_skip_partial(self.h, int(probe_rows_threshold), float(probe_ratio_threshold)))
 
     def push_host(self, cols): self._push("dfgpu_agg_push_host", cols)
     def push_device(self, cols): self._push("dfgpu_agg_push_device", cols)

@@ -523,6 +523,61 @@ __global__ void __launch_bounds__(256) agg_emit_kernel(EmitDesc d, const uint32_
   }
 }
 
+// convert_to_state (GroupsAccumulator::convert_to_state, prim_op.rs / count.rs:722 / average.rs; partial_table.rs:199-238): in
+// SkippingAggregation mode every input row becomes its own state row — SUM / MIN / MAX state = the value (NULL when the value is NULL
+// or the FILTER rejects the row), COUNT state = 1 / 0, AVG state = [count 1 / 0, sum value].  One warp owns 32 rows: validity leaves
+// as ballot words.
+struct StateOut { void* v0; uint32_t* valid0; void* v1; uint32_t* valid1; int t0; };
+struct StateOuts { StateOut o[kMaxAggs]; };
+__global__ void __launch_bounds__(256) agg_convert_state_kernel(AggSet aggs, StateOuts outs, int64_t n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = (n + 31) / 32;
+  for (int64_t wi = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; wi < nw; wi += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int64_t row = wi * 32 + lane;
+    for (int i = 0; i < aggs.n; ++i) {
+      const AggDev& a = aggs.a[i];
+      const StateOut& o = outs.o[i];
+      bool pass = row < n;
+      if (pass && a.filt) pass = !(a.filt_valid && !bit_get(a.filt_valid, a.filt_voff + row)) && bit_get(a.filt, a.filt_off + row);
+      bool ok = pass && (a.func == DFGPU_AGG_COUNT_STAR || !(a.in0_valid && !bit_get(a.in0_valid, a.in0_voff + row)));
+      if (row < n) {
+        switch (a.func) {
+          case DFGPU_AGG_COUNT: case DFGPU_AGG_COUNT_STAR: ((int64_t*)o.v0)[row] = ok ? 1 : 0; break;
+          case DFGPU_AGG_SUM:
+            if (a.cls == 2) ((double*)o.v0)[row] = ok ? load_as_f64(a.in0, a.in0_type, row) : 0.0;
+            else ((uint64_t*)o.v0)[row] = !ok ? 0ull : (a.in0_type == DFGPU_UINT64 ? ((const uint64_t*)a.in0)[row] : (uint64_t)load_as_i64(a.in0, a.in0_type, row));
+            break;
+          case DFGPU_AGG_MIN: case DFGPU_AGG_MAX: {
+            uint64_t v = 0;
+            if (ok) {
+              if (a.in0_type == DFGPU_FLOAT64) { double d = ((const double*)a.in0)[row]; memcpy(&v, &d, 8); }
+              else if (a.in0_type == DFGPU_FLOAT32) { float f = ((const float*)a.in0)[row]; uint32_t b; memcpy(&b, &f, 4); v = b; }
+              else if (a.in0_type == DFGPU_UINT64) v = ((const uint64_t*)a.in0)[row];
+              else v = (uint64_t)load_as_i64(a.in0, a.in0_type, row);
+            }
+            switch (type_width(o.t0)) {
+              case 1: ((uint8_t*)o.v0)[row] = (uint8_t)v; break;
+              case 2: ((uint16_t*)o.v0)[row] = (uint16_t)v; break;
+              case 4: ((uint32_t*)o.v0)[row] = (uint32_t)v; break;
+              default: ((uint64_t*)o.v0)[row] = v; break;
+            }
+            break;
+          }
+          case DFGPU_AGG_AVG:
+            ((uint64_t*)o.v0)[row] = ok ? 1ull : 0ull;
+            ((double*)o.v1)[row] = ok ? load_as_f64(a.in0, a.in0_type, row) : 0.0;
+            break;
+        }
+      }
+      const uint32_t b = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) {
+        if (o.valid0) o.valid0[wi] = b;
+        if (o.valid1) o.valid1[wi] = b;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) salt_kernel(uint16_t* __restrict__ out, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (uint16_t)(i & 1023);
 }
@@ -566,6 +621,10 @@ struct dfgpu_agg {
   uint64_t cap = 0;
   std::deque<BatchPtr> outq;
   int64_t m_input_rows = 0, m_output_rows = 0, m_rehashes = 0, m_num_groups = 0, m_input_batches = 0;
+  // skip-partial-aggregation probe (aggregates/skip_partial.rs:69-110; config.rs skip_partial_aggregation_probe_*)
+  int64_t probe_rows_threshold = 100000; double probe_ratio_threshold = 0.8;
+  int64_t probe_rows = 0, m_skipped_rows = 0;
+  bool skipping = false;
   // no GROUP BY (AggregateStream, aggregates/aggregate_stream.rs): a composite of two grouped handles, see scalar_* below
   bool scalar = false;
   dfgpu_agg* inner1 = nullptr;   // rows -> 1024 partial states (hidden key = row & 1023: a single accumulator would serialise every atomic)
@@ -655,6 +714,49 @@ static void ensure_seen(dfgpu_agg* a, AggState& s) {
 }
 
 static void agg_finish(dfgpu_agg* a);
+static void agg_emit_table(dfgpu_agg* a);
+
+// SkippingAggregation: the batch leaves as one state row per input row (convert_batch_to_state, partial_table.rs:199-238)
+static void agg_convert_batch_to_state(dfgpu_agg* a, const std::vector<DCol>& cols, const AggSet& set, int64_t n) {
+  dfgpu_ctx* ctx = a->ctx;
+  BatchPtr out(new dfgpu_batch());
+  out->ctx = ctx; out->rows = n; out->host = false;
+  for (int gc : a->group_cols) out->cols.push_back(copy_column_device(ctx, cols[gc]));
+  StateOuts so;
+  memset(&so, 0, sizeof(so));
+  for (size_t i = 0; i < a->aggs.size(); ++i) {
+    const AggState& st = a->aggs[i];
+    switch (st.func) {
+      case DFGPU_AGG_COUNT: case DFGPU_AGG_COUNT_STAR: {
+        DCol c = alloc_col(ctx, DFGPU_INT64, n, false);
+        so.o[i].v0 = c.own_values->ptr; so.o[i].t0 = DFGPU_INT64;
+        out->cols.push_back(std::move(c));
+        break;
+      }
+      case DFGPU_AGG_AVG: {
+        DCol c = alloc_col(ctx, DFGPU_UINT64, n, false), sm = alloc_col(ctx, DFGPU_FLOAT64, n, true);
+        so.o[i].v0 = c.own_values->ptr; so.o[i].v1 = sm.own_values->ptr; so.o[i].valid1 = sm.own_validity->as<uint32_t>(); so.o[i].t0 = DFGPU_UINT64;
+        sm.null_count = -1;
+        out->cols.push_back(std::move(c)); out->cols.push_back(std::move(sm));
+        break;
+      }
+      default: {   // SUM / MIN / MAX
+        const int t = st.func == DFGPU_AGG_SUM ? (st.cls == 2 ? DFGPU_FLOAT64 : (st.cls == 1 ? DFGPU_UINT64 : DFGPU_INT64)) : st.out_type;
+        DCol c = alloc_col(ctx, t, n, true);
+        so.o[i].v0 = c.own_values->ptr; so.o[i].valid0 = c.own_validity->as<uint32_t>(); so.o[i].t0 = t;
+        c.null_count = -1;
+        out->cols.push_back(std::move(c));
+      }
+    }
+  }
+  agg_convert_state_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(set, so, n);
+  DF_LAUNCH_CHECK(ctx);
+  DF_CUDA(cudaStreamSynchronize(ctx->stream));   // the caller's input columns are consumed before the push returns
+  a->m_output_rows += n;
+  a->m_skipped_rows += n;
+  a->outq.push_back(std::move(out));
+}
+
 static void agg_push(dfgpu_agg* a, const std::vector<DCol>& cols) {
   DF_CHECK(!a->finished, DFGPU_ERR_STATE, "push after finish");
   if (a->scalar) {
@@ -719,6 +821,7 @@ static void agg_push(dfgpu_agg* a, const std::vector<DCol>& cols) {
     // NullState: switch to explicit seen tracking once nulls or a filter show up (accumulate.rs:164-188)
     if ((in0 && in0->validity) || filt) ensure_seen(a, s);
   }
+  if (a->skipping) { agg_convert_batch_to_state(a, cols, set, n); return; }
   // fast-path eligibility (decided per batch: it depends on the validity of THIS batch's columns)
   static const int fast_enabled = getenv("DFGPU_AGG_FAST") ? atoi(getenv("DFGPU_AGG_FAST")) : 1;
   bool fast = fast_enabled && a->kw == 1 && g.n == 1 && g.width[0] == 8 && !g.valid[0] && !g.is_float[0] && set.n >= 1 && set.n <= kMaxFastAggs;
@@ -806,6 +909,16 @@ static void agg_push(dfgpu_agg* a, const std::vector<DCol>& cols) {
     done += m;
     chunk = std::min<int64_t>(chunk * 4, kMaxChunk);
   }
+  // SkipAggregationProbe::update_state (skip_partial.rs:69-110), Partial mode only: once probe_rows_threshold rows are in, a
+  // groups / rows ratio above the threshold means aggregating here does not pay — emit the groups and pass later batches through
+  if (a->mode == DFGPU_AGG_PARTIAL && a->probe_rows_threshold > 0 && !a->group_cols.empty()) {
+    a->probe_rows += n;
+    if (a->probe_rows >= a->probe_rows_threshold && (double)a->m_num_groups / (double)a->probe_rows > a->probe_ratio_threshold) {
+      a->skipping = true;
+      agg_emit_table(a);
+      a->emitted = true;
+    }
+  }
 }
 
 // one all-NULL / zero state row: what fresh accumulators report (SUM / MIN / MAX / AVG sum: NULL, counts: 0)
@@ -862,8 +975,12 @@ static void agg_finish(dfgpu_agg* a) {
     return;
   }
   a->finished = true;
+  set_device(a->ctx);
+  if (!a->emitted) agg_emit_table(a);   // SkippingAggregation already emitted the groups when it switched (hash_stream.rs SkippingAggregation)
+}
+
+static void agg_emit_table(dfgpu_agg* a) {
   dfgpu_ctx* ctx = a->ctx;
-  set_device(ctx);
   // emit = group_values.emit(EmitTo::All) ++ acc.state()/evaluate() (common.rs:247-297)
   TableDev t = table_dev(a, a->tags, a->cap, a->counters, a->special_used);
   const uint64_t total = a->cap + 2;
@@ -1090,6 +1207,14 @@ int dfgpu_agg_push_device(dfgpu_agg* a, const dfgpu_column* cols, int32_t n_cols
   agg_push(a, v);  // fully consumed (stream-synchronised) before returning
   DF_API_END
 }
+int dfgpu_agg_set_skip_partial(dfgpu_agg* a, int64_t probe_rows_threshold, double probe_ratio_threshold) {
+  DF_API_BEGIN(a ? a->ctx : nullptr)
+  DF_CHECK(a, DFGPU_ERR_INVALID, "null argument");
+  DF_CHECK(a->m_input_rows == 0, DFGPU_ERR_STATE, "set_skip_partial must be called before the first push");
+  dfgpu_agg* t = a->scalar ? nullptr : a;
+  if (t) { t->probe_rows_threshold = probe_rows_threshold; t->probe_ratio_threshold = probe_ratio_threshold; }
+  DF_API_END
+}
 int dfgpu_agg_finish(dfgpu_agg* a) {
   DF_API_BEGIN(a ? a->ctx : nullptr)
   agg_finish(a);
@@ -1118,6 +1243,7 @@ int64_t dfgpu_agg_metric(dfgpu_agg* a, const char* name) {
   if (s == "table_capacity") return (int64_t)a->cap;
   if (s == "rehashes") return a->m_rehashes;
   if (s == "key_words") return a->kw;
+  if (s == "skipped_aggregation_rows") return a->m_skipped_rows;
   return -1;
 }
 void dfgpu_agg_destroy(dfgpu_agg* a) {

@@ -91,12 +91,29 @@ __device__ __forceinline__ Rec128 rec_cas128(void* addr, Rec128 cmp, Rec128 val)
 }
 
 __device__ __forceinline__ uint64_t lk_hash(uint64_t key) { return hash_u64(key, kSeedJoin); }
-__device__ __forceinline__ void bloom_pos(uint64_t h, uint64_t blocks, uint64_t* block, unsigned long long* mask) {
-  // block from the top 32 hash bits (a 32-bit fastrange: the table slot uses the same bits, so a key's filter block and its
-  // record are neighbours in their structures — harmless), the four probe bits from the low 24 bits
-  *block = ((h >> 32) * (blocks & 0xFFFFFFFFull)) >> 32;
-  const uint32_t l = (uint32_t)h;
-  *mask = (1ull << (l & 63)) | (1ull << ((l >> 6) & 63)) | (1ull << ((l >> 12) & 63)) | (1ull << ((l >> 18) & 63));
+// Membership filter = split-block Bloom filter: one 64-bit block per key (two 32-bit words, two probe bits in each), 16 bits per key.
+// Block and bit positions come from a 32-bit multiplicative hash of both key halves — the filter is probed for EVERY scanned row, so
+// its cost is counted in instructions: ~12 integer ops here against ~45 for mix64 + a 64-bit fastrange + four 64-bit shifts.
+struct BloomPos { uint32_t block, t; };   // t: 20 hash bits = four 5-bit probe positions (two per 32-bit word)
+__device__ __forceinline__ BloomPos bloom_pos(uint64_t key, uint64_t blocks) {
+  uint32_t h1 = ((uint32_t)key ^ ((uint32_t)(key >> 32) * 0x85EBCA6Bu)) * 0x9E3779B1u;
+  h1 ^= h1 >> 15;
+  BloomPos p;
+  p.block = __umulhi(h1, (uint32_t)blocks);
+  p.t = (h1 * 0xC2B2AE35u) >> 12;                           // the well-mixed upper 20 bits of a second multiply
+  return p;
+}
+__device__ __forceinline__ unsigned long long bloom_mask(uint32_t t) {
+  const uint32_t m0 = (1u << (t & 31)) | (1u << ((t >> 5) & 31)), m1 = (1u << ((t >> 10) & 31)) | (1u << ((t >> 15) & 31));
+  return ((unsigned long long)m1 << 32) | m0;
+}
+__device__ __forceinline__ void bloom_set(unsigned long long* bloom, uint64_t blocks, uint64_t key) {
+  const BloomPos p = bloom_pos(key, blocks);
+  atomicOr(&bloom[p.block], bloom_mask(p.t));
+}
+__device__ __forceinline__ bool bloom_test(unsigned long long w, uint32_t t) {
+  const uint32_t m0 = (1u << (t & 31)) | (1u << ((t >> 5) & 31)), m1 = (1u << ((t >> 10) & 31)) | (1u << ((t >> 15) & 31));
+  return ((uint32_t)w & m0) == m0 && ((uint32_t)(w >> 32) & m1) == m1;
 }
 
 // insert one record; returns 0 inserted, 1 duplicate key, 2 cannot store this key
@@ -110,7 +127,7 @@ __device__ __forceinline__ int lk_insert(const LookupDev& t, uint64_t key, uint6
   if (key == kEmptyKey) return 2;
   const uint64_t h = lk_hash(key);
   if (t.cap == 0) {   // filter-only lookup: membership bits, no table
-    uint64_t b; unsigned long long m; bloom_pos(h, t.bloom_blocks, &b, &m); atomicOr(&t.bloom[b], m);
+    bloom_set(t.bloom, t.bloom_blocks, key);
     return 0;
   }
   uint64_t s = __umul64hi(h, t.cap);
@@ -124,7 +141,7 @@ __device__ __forceinline__ int lk_insert(const LookupDev& t, uint64_t key, uint6
     if (prev == key) { rc = 1; break; }
     if (++s == t.cap) s = 0;
   }
-  if (rc == 0 && t.bloom) { uint64_t b; unsigned long long m; bloom_pos(h, t.bloom_blocks, &b, &m); atomicOr(&t.bloom[b], m); }
+  if (rc == 0 && t.bloom) bloom_set(t.bloom, t.bloom_blocks, key);
   return rc;
 }
 
@@ -150,13 +167,13 @@ __device__ __forceinline__ void red_f64_min(unsigned long long* p, double v, boo
 // the pipeline kernel.  Every WARP runs the pipeline on its own 256-row tiles, in two phases, with no block barrier:
 //   phase A (every row, cheap, coalesced): a lane owns 8 consecutive rows and reads them with 128-bit loads (a warp request
 //     is 512 contiguous bytes per instruction); it evaluates the predicate, the bitmap stages and the Bloom pre-test of the
-//     hash stages, and appends the survivors (row, first hash key) to the warp's queue in shared memory;
+//     hash stages, and appends the surviving row numbers to the warp's queue in shared memory;
 //   phase B (survivors only, dense): whenever the queue holds >= 128 entries every lane takes four of them — all lanes busy,
 //     four table lookups in flight per lane — resolves the hash stages and feeds the sink (record insert / accumulator RED).
 // Without the queue the expensive tail (a DRAM lookup, the argument interpreter, an insert CAS) runs at warp granularity for
 // the few live lanes of every warp: that cost 27 warp-instructions and 143 B of DRAM traffic per row on Q3's lineitem pass.
 // ------------------------------------------------------------------------------------------
-constexpr int kWarpRows = 8, kWarpTile = 32 * kWarpRows, kPhaseB = 4, kPhaseBGroup = 32 * kPhaseB, kQueueCap = kPhaseBGroup + kWarpTile;
+constexpr int kWarpRows = 8, kWarpTile = 32 * kWarpRows, kPhaseB = 2, kPhaseBGroup = 32 * kPhaseB, kQueueCap = kPhaseBGroup + kWarpTile;
 constexpr int kPipeWarps = kPipeThreads / 32;
 
 __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) { asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
@@ -165,6 +182,28 @@ __device__ __forceinline__ void red_min_s64(unsigned long long* p, long long v) 
 __device__ __forceinline__ void red_max_s64(unsigned long long* p, long long v) { asm volatile("red.global.max.s64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ void red_min_u64(unsigned long long* p, unsigned long long v) { asm volatile("red.global.min.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ void red_max_u64(unsigned long long* p, unsigned long long v) { asm volatile("red.global.max.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+
+// Pure 64-bit integer arithmetic (integer columns without NULLs in this batch, integer literals, payload fields, + - *): nothing can be
+// NULL, nothing can fail — a four-register stack and ~10 instructions per node instead of the general interpreter's ~100.
+__device__ __forceinline__ uint64_t eval_int_fast(const ENode* __restrict__ nodes, int n, int64_t row, const uint64_t* ext) {
+  uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;   // s0 = top of stack
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+    const ENode& nd = nodes[i];
+    if (nd.kind == DFGPU_EXPR_BINARY) {
+      uint64_t r = nd.op == DFGPU_OP_PLUS ? s1 + s0 : (nd.op == DFGPU_OP_MINUS ? s1 - s0 : s1 * s0);
+      if (type_width(nd.out_type) < 8) r = wrap_to_type(r, nd.out_type);
+      s0 = r; s1 = s2; s2 = s3;
+    } else {
+      uint64_t v;
+      if (nd.kind == DFGPU_EXPR_COLUMN) v = load_col_value(nd, row);
+      else if (nd.kind == DFGPU_EXPR_LITERAL) v = nd.lit;
+      else { v = ext[nd.voff] >> (int)nd.lit; const int w = type_width(nd.out_type); if (w < 8) { v &= (1ull << (8 * w)) - 1ull; if (type_is_signed_int(nd.out_type)) v = (uint64_t)(((int64_t)(v << (64 - 8 * w))) >> (64 - 8 * w)); } }
+      s3 = s2; s2 = s1; s1 = s0; s0 = v;
+    }
+  }
+  return s0;
+}
 
 // one out-of-line copy of each interpreter: the kernel stays small enough for the instruction cache
 __device__ __noinline__ uint64_t pipe_eval(const ENode* nodes, int n, int small, int64_t row, const uint64_t* ext, int* err_ok /* [0]=err bits (or-ed), [1]=valid */) {
@@ -218,9 +257,13 @@ __device__ __forceinline__ void load8(const ColRef& c, int64_t row0, int64_t n, 
         break;
       }
     }
-  } else {
+  } else {   // unaligned base or ragged tail: one scalar load site, results routed by selects (keeps v[] in registers, the code small)
+#pragma unroll 1
+    for (int j = 0; j < kWarpRows; ++j) {
+      const uint64_t x = row0 + j < n ? ld_stream_int(c.ptr, c.width, c.sgn, row0 + j, pol) : 0ull;
 #pragma unroll
-    for (int j = 0; j < kWarpRows; ++j) v[j] = row0 + j < n ? ld_stream_int(c.ptr, c.width, c.sgn, row0 + j, pol) : 0ull;
+      for (int k = 0; k < kWarpRows; ++k) if (k == j) v[k] = x;
+    }
   }
 }
 // validity bits of the same 8 rows (bit j = row0 + j is non-NULL)
@@ -231,17 +274,15 @@ __device__ __forceinline__ uint32_t valid8(const ColRef& c, int64_t row0, int64_
 }
 
 template <int SINK>
-__global__ void __launch_bounds__(kPipeThreads) pipe_kernel(const PipeParams* __restrict__ gp, int64_t n, unsigned long long* __restrict__ counters /* [alive, inserted, fail, err] */) {
+__global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams* __restrict__ gp, int64_t n, unsigned long long* __restrict__ counters /* [alive, inserted, fail, err] */) {
   __shared__ PipeParams sp;
   __shared__ uint32_t q_rows[kPipeWarps][kQueueCap];
-  __shared__ unsigned long long q_keys[kPipeWarps][kQueueCap];
   for (int i = threadIdx.x; i < (int)(sizeof(PipeParams) / 4); i += kPipeThreads) ((uint32_t*)&sp)[i] = ((const uint32_t*)gp)[i];
   __syncthreads();
   const uint64_t pol_stream = (sp.hints & 1) ? policy_evict_first() : policy_normal();
   const uint64_t pol_keep = (sp.hints & 2) ? policy_evict_last() : policy_normal();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t* q_row = q_rows[wib];
-  unsigned long long* q_key = q_keys[wib];
   unsigned int alive_cnt = 0, ins_cnt = 0;
   int err_ok[2] = {0, 0};
   int fail = 0;
@@ -254,9 +295,6 @@ __global__ void __launch_bounds__(kPipeThreads) pipe_kernel(const PipeParams* __
       // =============================== phase A ===============================
       const int64_t row0 = tile * kWarpTile + (int64_t)lane * kWarpRows;
       uint32_t mask = row0 + kWarpRows <= n ? 0xFFu : (row0 < n ? (1u << (int)(n - row0)) - 1u : 0u);
-      uint64_t key0[kWarpRows];
-#pragma unroll
-      for (int j = 0; j < kWarpRows; ++j) key0[j] = 0;
       if (sp.pred_mode == 1) {   // FilterExec, conjunction of `column <cmp> literal`
 #pragma unroll 1
         for (int t = 0; t < sp.n_terms; ++t) {
@@ -294,12 +332,14 @@ __global__ void __launch_bounds__(kPipeThreads) pipe_kernel(const PipeParams* __
         }
       }
       // bitmap stages decide here; hash stages get their Bloom pre-test (the pushed-down membership filter)
-#pragma unroll
-      for (int s = 0; s < kMaxStages; ++s) {
-        if (s >= sp.n_stages) continue;
+#pragma unroll 1
+      for (int s = 0; s < sp.n_stages; ++s) {
         const StageDev& st = sp.stage[s];
         const bool bitmap = st.lk.mode == LK_BITMAP;
-        if (!bitmap && s != sp.first_hash && !(st.lk.bloom && st.kind != DFGPU_STAGE_ANTI)) continue;   // nothing cheap to do for this stage
+        if (!bitmap && !(st.lk.bloom && st.kind != DFGPU_STAGE_ANTI)) {   // nothing cheap to test; NULL keys of an inner / semi stage still drop here
+          if (st.kind != DFGPU_STAGE_ANTI && sp.col[st.key_col].valid) mask &= valid8(sp.col[st.key_col], row0, n);
+          continue;
+        }
         if (!bitmap && st.kind == kStageMaybe && !st.lk.bloom) continue;                                // may-contain without a filter: everything may
         if (!__any_sync(0xffffffffu, mask != 0)) continue;
         const ColRef kc = sp.col[st.key_col];
@@ -318,22 +358,20 @@ __global__ void __launch_bounds__(kPipeThreads) pipe_kernel(const PipeParams* __
           for (int j = 0; j < kWarpRows; ++j) found |= ((w[j] >> ((key[j] - st.lk.kmin) & 31)) & 1u) << j;   // NULL keys never match (w = 0)
           mask &= st.kind == DFGPU_STAGE_ANTI ? ~found : found;
         } else {
-          if (s == sp.first_hash) {
-#pragma unroll
-            for (int j = 0; j < kWarpRows; ++j) key0[j] = key[j];
-          }
           if (st.kind != DFGPU_STAGE_ANTI) {
             mask &= kvalid;                      // NULL keys never match
             if (st.lk.bloom) {
-              unsigned long long bw[kWarpRows], bm[kWarpRows];
+              unsigned long long bw[kWarpRows];
+              uint32_t bt[kWarpRows];
 #pragma unroll
               for (int j = 0; j < kWarpRows; ++j) {
-                uint64_t b; bloom_pos(lk_hash(key[j]), st.lk.bloom_blocks, &b, &bm[j]);
-                bw[j] = ((mask >> j) & 1u) ? ld_keep_u64(&st.lk.bloom[b], pol_keep) : 0ull;
+                const BloomPos bp = bloom_pos(key[j], st.lk.bloom_blocks);
+                bt[j] = bp.t;
+                bw[j] = ((mask >> j) & 1u) ? ld_keep_u64(&st.lk.bloom[bp.block], pol_keep) : 0ull;
               }
               uint32_t pass = 0;
 #pragma unroll
-              for (int j = 0; j < kWarpRows; ++j) pass |= (uint32_t)((bw[j] & bm[j]) == bm[j]) << j;
+              for (int j = 0; j < kWarpRows; ++j) pass |= (uint32_t)bloom_test(bw[j], bt[j]) << j;
               mask &= pass;
             }
           }
@@ -347,7 +385,7 @@ __global__ void __launch_bounds__(kPipeThreads) pipe_kernel(const PipeParams* __
       unsigned int pos = qn + incl - cnt;
 #pragma unroll
       for (int j = 0; j < kWarpRows; ++j)
-        if ((mask >> j) & 1u) { q_row[pos] = (uint32_t)(row0 + j); q_key[pos] = key0[j]; ++pos; }
+        if ((mask >> j) & 1u) { q_row[pos] = (uint32_t)(row0 + j); ++pos; }
       qn += __shfl_sync(0xffffffffu, incl, 31);
       __syncwarp();
     }
@@ -378,7 +416,7 @@ __global__ void __launch_bounds__(kPipeThreads) pipe_kernel(const PipeParams* __
         for (int u = 0; u < kPhaseB; ++u) {
           found[u] = false; look[u] = live[u]; key[u] = 0;
           if (look[u]) {
-            key[u] = s == sp.first_hash ? q_key[qbase + u * 32 + lane] : ld_stream_int(kc.ptr, kc.width, kc.sgn, row[u], pol_stream);
+            key[u] = ld_stream_int(kc.ptr, kc.width, kc.sgn, row[u], pol_stream);   // the line was streamed in moments ago: an L2 hit
             if ((kc.valid && !bit_get(kc.valid, kc.voff + row[u])) || key[u] == kEmptyKey) look[u] = false;   // NULL keys never match
           }
           slot[u] = __umul64hi(lk_hash(key[u]), st.lk.cap); ck[u] = kEmptyKey; cp[u] = 0;
@@ -464,8 +502,12 @@ __global__ void __launch_bounds__(kPipeThreads) pipe_kernel(const PipeParams* __
           for (int a = 0; a < sp.n_aggs; ++a) {
             const AggDef ag = sp.agg[a];
             if (ag.func == DFGPU_AGG_COUNT_STAR) continue;   // = the row counter
-            const uint64_t v = pipe_eval(sp.pool + ag.start, ag.n, ag.small, row[u], ext, err_ok);
-            if (!err_ok[1]) continue;                        // NULL inputs are skipped (accumulate.rs:373-470)
+            uint64_t v;
+            if (ag.small == 2) v = eval_int_fast(sp.pool + ag.start, ag.n, row[u], ext);
+            else {
+              v = pipe_eval(sp.pool + ag.start, ag.n, ag.small, row[u], ext, err_ok);
+              if (!err_ok[1]) continue;                      // NULL inputs are skipped (accumulate.rs:373-470)
+            }
             if (ag.nn_word >= 0) red_add_u64(rec + ag.nn_word, 1ull);
             switch (ag.func) {
               case DFGPU_AGG_COUNT: red_add_u64(rec + ag.word, 1ull); break;
@@ -582,7 +624,7 @@ __global__ void __launch_bounds__(kPipeThreads) pipe_output_kernel(const PipePar
         } else if (key != kEmptyKey) {
           const uint64_t h = lk_hash(key);
           bool maybe = true;
-          if (st.lk.bloom) { uint64_t b; unsigned long long m; bloom_pos(h, st.lk.bloom_blocks, &b, &m); maybe = (st.lk.bloom[b] & m) == m; }
+          if (st.lk.bloom) { const BloomPos bp = bloom_pos(key, st.lk.bloom_blocks); maybe = bloom_test(st.lk.bloom[bp.block], bp.t); }
           if (maybe) {
             uint64_t slot = __umul64hi(h, st.lk.cap);
             while (true) {
@@ -658,7 +700,7 @@ __global__ void __launch_bounds__(256) lookup_rehash_kernel(LookupDev old_t, Loo
       if (atomicCAS(q, (unsigned long long)kEmptyKey, key) == kEmptyKey) { for (int w = 1; w < new_t.stride; ++w) q[w] = r[w]; break; }
       if (++d == new_t.cap) d = 0;
     }
-    if (new_t.bloom) { uint64_t b; unsigned long long m; bloom_pos(h, new_t.bloom_blocks, &b, &m); atomicOr(&new_t.bloom[b], m); }
+    if (new_t.bloom) bloom_set(new_t.bloom, new_t.bloom_blocks, key);
   }
 }
 // accumulator identities for MIN / MAX (SUM / COUNT start at the zero the table was initialised with)
@@ -905,6 +947,21 @@ static int plan_depth(const ExprPlan& plan) {
   return mx;
 }
 
+// only integer columns without NULLs (in THIS batch), non-NULL integer literals, payload fields and + - *: eval_int_fast applies
+static bool plan_is_int_arith(const dfgpu_pipeline* p, const ExprPlan& plan, const std::vector<DCol>& cols) {
+  for (size_t i = 0; i < plan.nodes.size(); ++i) {
+    const dfgpu_expr_node& nd = plan.nodes[i];
+    const int t = plan.out_type[i];
+    if (!type_is_int(t)) return false;
+    if (nd.kind == DFGPU_EXPR_COLUMN) { if (nd.a < (int)cols.size() && cols[nd.a].validity) return false; }
+    else if (nd.kind == DFGPU_EXPR_LITERAL) { if (nd.is_null) return false; }
+    else if (nd.kind == DFGPU_EXPR_BINARY) { if (nd.a != DFGPU_OP_PLUS && nd.a != DFGPU_OP_MINUS && nd.a != DFGPU_OP_MULTIPLY) return false; }
+    else return false;
+  }
+  (void)p;
+  return true;
+}
+
 static bool expr_can_be_null(const ExprPlan& plan, const std::vector<DCol>& cols) {
   for (const auto& nd : plan.nodes) {
     if (nd.kind == DFGPU_EXPR_COLUMN && nd.a < (int)cols.size() && cols[nd.a].validity) return true;
@@ -976,6 +1033,7 @@ static void fill_params(dfgpu_pipeline* p, const std::vector<DCol>& cols, PipePa
       if (ag.has_expr) {
         d.start = bind_pool(p, ag.plan, cols, pp, &pool_used); d.n = (int)ag.plan.nodes.size();
         d.small = plan_depth(ag.plan) <= 4 ? 1 : 0;
+        if (d.small && plan_is_int_arith(p, ag.plan, cols)) d.small = 2;
         if (ag.nn_word < 0 && ag.func != DFGPU_AGG_COUNT)
           DF_CHECK(!expr_can_be_null(ag.plan, cols), DFGPU_ERR_UNSUPPORTED, "pipeline: nullable aggregate input needs one more accumulator word in the lookup (n_acc_words)");
       }

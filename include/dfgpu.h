@@ -319,12 +319,17 @@ int dfgpu_agg_create(dfgpu_ctx* ctx, const int32_t* input_types, int32_t n_cols,
                      const int32_t* group_cols, int32_t n_group,
                      const dfgpu_agg_desc* aggs, int32_t n_aggs,
                      int32_t mode, int64_t batch_size, int64_t capacity_hint, dfgpu_agg** out);
+/* skip-partial-aggregation probe (aggregates/skip_partial.rs:69-110; execution.skip_partial_aggregation_probe_rows_threshold = 100000,
+ * ..._ratio_threshold = 0.8, both the defaults here): in Partial mode, once that many rows have been aggregated and groups / rows
+ * exceeds the ratio, the handle emits its groups and converts every later batch row by row into state rows (convert_to_state).
+ * probe_rows_threshold = 0 switches the probe off.  Call before the first push. */
+int dfgpu_agg_set_skip_partial(dfgpu_agg* a, int64_t probe_rows_threshold, double probe_ratio_threshold);
 int dfgpu_agg_push_host(dfgpu_agg* a, const dfgpu_column* cols, int32_t n_cols);
 int dfgpu_agg_push_device(dfgpu_agg* a, const dfgpu_column* cols, int32_t n_cols);
 int dfgpu_agg_push_arrow(dfgpu_agg* a, const struct ArrowArray* batch, const struct ArrowSchema* schema);
 int dfgpu_agg_finish(dfgpu_agg* a);
 int dfgpu_agg_next(dfgpu_agg* a, int host, dfgpu_batch** out);
-int64_t dfgpu_agg_metric(dfgpu_agg* a, const char* name); /* "num_groups","input_rows","output_rows","table_capacity","rehashes" */
+int64_t dfgpu_agg_metric(dfgpu_agg* a, const char* name); /* "num_groups","input_rows","output_rows","table_capacity","rehashes","skipped_aggregation_rows" */
 void dfgpu_agg_destroy(dfgpu_agg* a);
 
 /* ===================================================================================== */

@@ -101,9 +101,11 @@ def gpu_hash_join(ctx, build, probe, on_build, on_probe, out_side, out_index, jo
     return cols
 
 
-def gpu_group_by(ctx, cols, group_cols, aggs, mode=D.AGG_SINGLE, batch_rows=None, device=False, types=None, capacity_hint=0, return_handle=False):
+def gpu_group_by(ctx, cols, group_cols, aggs, mode=D.AGG_SINGLE, batch_rows=None, device=False, types=None, capacity_hint=0, return_handle=False, skip_partial=None):
     t = type_ids(cols, types)
     a = D.AggHandle(ctx, t, group_cols, aggs, mode, 8192, capacity_hint)
+    if skip_partial is not None:
+        a.set_skip_partial(*skip_partial)
     n = len(cols[0][0])
     keep = []
     for s, e in split_points(n, batch_rows):

@@ -234,3 +234,43 @@ def test_gpu_aggregate_without_group_by(gpu_ctx, n, batch_rows):
         assert gvalid == evalid
         if evalid:
             assert np.isclose(float(g[0][0]), float(e[0][0]), rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("name,threshold,n_agg", [("skip_aggregation_after_first_batch", 2, 3), ("skip_aggregation_after_threshold", 5, 4)])
+def test_gpu_skip_partial_reproduces_the_references_partial_output(gpu_ctx, name, threshold, n_agg):
+    """aggregates/mod.rs:5431-5603 with the reference's settings (probe_rows_threshold 2 / 5, ratio 0.1): the GPU Partial emits the
+    aggregated groups, then every later batch row by row (convert_to_state) in input order — the reference's snapshot."""
+    m = MISC[name]
+    key = np.concatenate([np.array(b["key"], np.int32) for b in m["batches"]]); val = np.concatenate([np.array(b["val"], np.int32) for b in m["batches"]])
+    got, h = gpu_group_by(gpu_ctx, [(key, None), (val, None)], [0], [(D.AGG_COUNT, 1, -1)], mode=D.AGG_PARTIAL, batch_rows=3, skip_partial=(threshold, 0.1), return_handle=True)
+    rp = m["reference_partial"]
+    assert h.metric("skipped_aggregation_rows") == len(rp["key"]) - n_agg
+    h.close()
+    assert sorted(zip(got[0][0][:n_agg].tolist(), got[1][0][:n_agg].tolist())) == sorted(zip(rp["key"][:n_agg], rp["count"][:n_agg]))
+    assert got[0][0][n_agg:].tolist() == rp["key"][n_agg:] and got[1][0][n_agg:].tolist() == rp["count"][n_agg:]
+    # the probe is off with threshold 0, and the default thresholds (100 000 rows, 0.8) never trigger here
+    for sp in ((0, 0.1), None):
+        got = gpu_group_by(gpu_ctx, [(key, None), (val, None)], [0], [(D.AGG_COUNT, 1, -1)], mode=D.AGG_PARTIAL, batch_rows=3, skip_partial=sp)
+        assert sorted(zip(got[0][0].tolist(), got[1][0].tolist())) == sorted(zip(m["final"]["key"], m["final"]["count"]))
+
+
+def test_gpu_skip_partial_high_cardinality_final_equals_single(gpu_ctx):
+    """default thresholds: 300 000 rows with ~all-distinct keys -> after the first 120 000-row batch groups / rows > 0.8 and the rest
+    passes through as state rows (SUM / COUNT / MIN / AVG / COUNT(*), NULL values, a FILTER, NULL keys); Final over that == Single"""
+    rng = np.random.default_rng(101)
+    n = 300_000
+    k = rng.permutation(10 * n)[:n].astype(np.int64); kv = rng.random(n) > 0.01
+    v = rng.integers(-10**9, 10**9, n).astype(np.int64); vv = rng.random(n) > 0.1
+    f = rng.normal(size=n); flt = rng.random(n) > 0.3
+    cols = [(k, kv), (v, vv), (f, None), (flt, None)]
+    aggs = [(D.AGG_SUM, 1, -1), (D.AGG_COUNT, 1, 3), (D.AGG_MIN, 1, -1), (D.AGG_AVG, 2, -1), (D.AGG_COUNT_STAR, -1, -1), (D.AGG_MAX, 2, 3)]
+    part, h = gpu_group_by(gpu_ctx, cols, [0], aggs, mode=D.AGG_PARTIAL, batch_rows=120_000, device=True, return_handle=True)
+    assert h.metric("skipped_aggregation_rows") == n - 120_000 and len(part[0][0]) > 0.95 * n
+    h.close()
+    types = [D.INT64, D.INT64, D.INT64, D.INT64, D.UINT64, D.FLOAT64, D.INT64, D.FLOAT64]
+    fin = gpu_group_by(gpu_ctx, part, [0], [(a[0], -1, -1) for a in aggs], mode=D.AGG_FINAL, types=types)
+    single = gpu_group_by(gpu_ctx, cols, [0], aggs, batch_rows=120_000)
+    close_cols(fin, single, float_cols={4, 6})
+    oaggs = [(O.A_SUM, cols[1], None), (O.A_COUNT, cols[1], cols[3]), (O.A_MIN, cols[1], None), (O.A_AVG, cols[2], None), (O.A_COUNT_STAR, None, None), (O.A_MAX, cols[2], cols[3])]
+    exp = oracle_table([cols[0]], oaggs, [np.int64, np.int64, np.int64, np.float64, np.int64, np.float64])
+    close_cols(single, exp, float_cols={4, 6})
