@@ -38,7 +38,8 @@ constexpr uint64_t kEmptyKey = ~0ull;
 constexpr int kMaxPipeCols = 16, kMaxStages = 3, kMaxPipeAggs = 4, kMaxExt = 8, kMaxTerms = 4, kPoolNodes = 56, kMaxBuildPay = 8;
 constexpr int kPipeThreads = 256, kPipeItems = 4, kPipeTile = kPipeThreads * kPipeItems;
 enum LookupMode : int { LK_HASH = 0, LK_BITMAP = 1 };
-enum SinkKind : int { SINK_NONE = 0, SINK_COUNT = 1, SINK_BUILD = 2, SINK_AGG = 3, SINK_OUTPUT = 4, SINK_OUTPUT_ANY = 5 /* row order unspecified */ };
+enum SinkKind : int { SINK_NONE = 0, SINK_COUNT = 1, SINK_BUILD = 2, SINK_AGG = 3, SINK_OUTPUT = 4, SINK_OUTPUT_ANY = 5 /* row order unspecified */,
+                      SINK_PACK = 6 /* build sink, table size unknown: {key, payload} records to a staging buffer, inserted afterwards */ };
 constexpr int kStageMaybe = 3;   // DFGPU_STAGE_MAYBE
 
 struct LookupDev {
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
         for (int s = 0; s < kMaxStages; ++s) ext[s] = pay[s][u];
         if (!live[u]) continue;
         alive_cnt++;
-        if (SINK == SINK_BUILD) {
+        if (SINK == SINK_BUILD || SINK == SINK_PACK) {
           const ColRef kc = sp.col[sp.bkey_col];
           if (kc.valid && !bit_get(kc.valid, kc.voff + row[u])) continue;   // NULL build keys are not inserted (utils.rs:2146-2155)
           const uint64_t key = ld_stream_int(kc.ptr, kc.width, kc.sgn, row[u], pol_stream);
@@ -493,9 +494,19 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
             if (sp.bpay_width[c] < 8) v &= (1ull << (8 * sp.bpay_width[c])) - 1ull;
             p |= v << sp.bpay_shift[c];
           }
-          const int rc = lk_insert(sp.target, key, p);
-          if (rc == 0) ins_cnt++;
-          else if (rc == 2 || sp.target_unique) fail |= rc;
+          if (SINK == SINK_PACK) {   // one reservation per warp and round (the lanes still active here), coalesced 16-byte stores
+            const unsigned am = __activemask();
+            const int leader = __ffs(am) - 1;
+            unsigned long long o = 0;
+            if (lane == leader) o = atomicAdd(sp.out_counter, (unsigned long long)__popc(am));
+            o = __shfl_sync(am, o, leader) + __popc(am & ((1u << lane) - 1u));
+            ((ulonglong2*)sp.out_dst[0])[o] = make_ulonglong2(key, p);
+            ins_cnt++;
+          } else {
+            const int rc = lk_insert(sp.target, key, p);
+            if (rc == 0) ins_cnt++;
+            else if (rc == 2 || sp.target_unique) fail |= rc;
+          }
         } else if (SINK == SINK_AGG) {
           unsigned long long* rec = arec[u];
           red_add_u64(rec + sp.rows_word, 1ull);
@@ -702,6 +713,20 @@ __global__ void __launch_bounds__(256) lookup_rehash_kernel(LookupDev old_t, Loo
     }
     if (new_t.bloom) bloom_set(new_t.bloom, new_t.bloom_blocks, key);
   }
+}
+// second half of a build whose size was unknown: the packed {key, payload} records of the survivors go into the (now sized) table
+__global__ void __launch_bounds__(256) lookup_insert_records_kernel(LookupDev t, const ulonglong2* __restrict__ recs, int64_t n, int unique, unsigned long long* __restrict__ counters /* [_, inserted, fail] */) {
+  unsigned int ins = 0; int fail = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const ulonglong2 r = recs[i];
+    const int rc = lk_insert(t, r.x, r.y);
+    if (rc == 0) ins++;
+    else if (rc == 2 || unique) fail |= rc;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) ins += __shfl_xor_sync(0xffffffffu, ins, d);
+  fail = __any_sync(0xffffffffu, fail & 1) | (__any_sync(0xffffffffu, fail & 2) << 1);
+  if ((threadIdx.x & 31) == 0) { if (ins) atomicAdd(&counters[1], (unsigned long long)ins); if (fail) atomicOr(&counters[2], (unsigned long long)fail); }
 }
 // accumulator identities for MIN / MAX (SUM / COUNT start at the zero the table was initialised with)
 __global__ void __launch_bounds__(256) lookup_init_acc_kernel(LookupDev t, int word, unsigned long long value) {
@@ -1111,21 +1136,39 @@ static void pipeline_push(dfgpu_pipeline* p, const std::vector<DCol>& cols) {
   if (p->sink == SINK_BUILD) {
     dfgpu_lookup* t = p->target;
     if (t->mode == LK_HASH && !t->filter_only && (uint64_t)(t->rows + n) * 2 > t->cap) {
-      // the batch may not fit at load factor 0.5: count its survivors first (same kernel, counting sink), then size the table
+      // the batch may not fit at load factor 0.5 and nobody knows how many rows survive: ONE pass evaluates the pipeline and leaves
+      // the survivors as packed {key, payload} records; the table is sized for exactly that many and the records are inserted by a
+      // dense kernel (no second scan of the input).
+      fill_params(p, cols, &pp);
+      DevBuf recs(ctx, (size_t)n * 16);
+      p->counters.zero();
+      pp.out_dst[0] = recs.ptr;
+      pp.out_counter = p->counters.as<unsigned long long>() + 4;
+      upload_params(p, pp);
+      launch_pipe<SINK_PACK>(p, n, "pipeline_build");
+      unsigned long long h8[8];
+      DF_CUDA(cudaMemcpyAsync(h8, p->counters.ptr, 64, cudaMemcpyDeviceToHost, ctx->stream));
+      DF_CUDA(cudaStreamSynchronize(ctx->stream));
+      check_errors(h8[3]);
+      const int64_t packed = (int64_t)h8[4];
+      lookup_reserve(t, t->rows + packed);
+      p->counters.zero();
+      if (packed > 0) {
+        KernelTimer kt(ctx, "lookup_insert");
+        lookup_insert_records_kernel<<<grid_for(packed, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(lookup_dev(t), (const ulonglong2*)recs.ptr, packed,
+                                                                                                   (t->has_payload || t->opt.n_acc_words > 0) ? 1 : 0, p->counters.as<unsigned long long>());
+        DF_LAUNCH_CHECK(ctx);
+      }
+      read_counters(p, h);
+      h[0] = h8[0];
+    } else {
       fill_params(p, cols, &pp);
       upload_params(p, pp);
       p->counters.zero();
-      launch_pipe<SINK_COUNT>(p, n, "pipeline_count");
+      launch_pipe<SINK_BUILD>(p, n, "pipeline_build");
       read_counters(p, h);
       check_errors(h[3]);
-      lookup_reserve(t, t->rows + (int64_t)h[0]);
     }
-    fill_params(p, cols, &pp);
-    upload_params(p, pp);
-    p->counters.zero();
-    launch_pipe<SINK_BUILD>(p, n, "pipeline_build");
-    read_counters(p, h);
-    check_errors(h[3]);
     if (h[2] & 2) throw Error(DFGPU_ERR_INVALID, "lookup build: a key lies outside the declared key range (or is the reserved all-ones value)");
     if (h[2] & 1) throw Error(DFGPU_ERR_UNSUPPORTED, "lookup build: duplicate build keys — the fused lookup needs unique keys, use dfgpu_hashjoin");
     t->rows += (int64_t)h[1];
