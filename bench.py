@@ -394,7 +394,8 @@ def main():
     barrier()
     clk = clocks.stop() if rank == 0 else None
     launches = ctx.launches + (runner.extra_launches() if world > 1 else 0) - launches0
-    ktimes = {k: ctx.kernel_time(k) for k in ("pipeline_agg", "pipeline_build", "pipeline_count")}
+    ktimes = {k: ctx.kernel_time(k) for k in ("pipe:lineitem", "pipe:orders", "pipe:owner_probe_agg", "pipeline_build", "pipeline_output", "lookup_insert", "filter_allreduce",
+                                              "partition")}
     ctx.set_kernel_timing(False)
     # ---- the timed output, verified at the timed size ----
     if world > 1:
@@ -423,7 +424,7 @@ def main():
     line = None
     if rank == 0:
         peak, peak_src = peaks()
-        a_ms, a_n = ktimes["pipeline_agg"]
+        a_ms, a_n = ktimes["pipe:lineitem"]      # the lineitem scan: N = 1 filter -> Bloom -> probe -> SUM; N > 1 filter -> membership filter -> output
         k_ms = a_ms / max(a_n, 1)
         algo_bytes = 28.0 * nl                 # lineitem: 8 + 8 + 8 + 4 B per row, every column once
         achieved = algo_bytes / (k_ms / 1000.0) / 1e9 if k_ms > 0 else 0.0
@@ -433,19 +434,21 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_pipeline_traffic.json")))["pipe_kernel_agg_sf100_dram_bytes"]
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": "pipe_kernel<aggregate> (lineitem: filter -> Bloom -> probe -> SUM into the matched record)", "achieved": achieved, "peak": peak,
+        roofline = {"bound": "hbm", "kernel": "pipe_kernel<aggregate> (lineitem: filter -> Bloom -> probe -> SUM into the matched record)" if world == 1 else
+                    "pipe_kernel<output> (lineitem: filter -> pushed-down membership filter -> survivors to the exchange)", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write at SF100, profiles/r2_pipeline_traffic.json)",
                     "peak_source": peak_src, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step, "algorithmic_bytes_per_launch": algo_bytes,
                     "launches_per_step": a_n / args.steps,
                     "whole_pipeline_achieved_gbs": q_bytes / (ms_per_step / 1000.0) / 1e9 if world == 1 else None,
                     "whole_pipeline_frac": q_bytes / (ms_per_step / 1000.0) / 1e9 / peak if world == 1 else None,
-                    "other_kernels_ms": {k: v[0] / max(v[1], 1) for k, v in ktimes.items() if v[1] and k != "pipeline_agg"}}
+                    "other_kernels_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1] and k != "pipe:lineitem"}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic (generated in HBM, counter-based)",
                 "config": {"workload": WORKLOAD.format(sf=sf, nc=nc, no=no, nl=nl), "rows_per_step": in_rows, "stages": st, "fingerprint": fp,
                            "fingerprint_verified": "asserted against the CPU restatement's fingerprint of the same tables" if world == 1 else f"sum over ranks asserted against oracle_q3_stream_fingerprint of the SF{sf * world:g} database",
                            "l2": "inputs (20.6 GB/GPU) exceed L2; no flush",
-                           "plan": "3 fused pipelines (dfgpu_pipeline): customer -> key bitmap; orders -> filter + semi probe -> build {o_orderkey -> (o_orderdate, o_shippriority)} + Bloom filter; lineitem -> filter + Bloom + probe + SUM into the matched record",
+                           "plan": "3 fused pipelines (dfgpu_pipeline): customer -> key bitmap; orders -> filter + semi probe -> build {o_orderkey -> (o_orderdate, o_shippriority)} + Bloom filter; lineitem -> filter + Bloom + probe + SUM into the matched record" if world == 1 else
+                                   "per rank: customer keys all-gathered -> global bitmap; orders -> filter + semi -> membership filter (OR-all-reduced over NVLink) + exchange -> owner builds the join table; lineitem -> filter + membership filter -> exchange -> owner probes + SUMs into the matched record (scripts/q3_multi_gpu.py)",
                            "exchange": "none (single GPU)" if world == 1 else runner.exchange_description()},
                 "clocks": clk, "gpu_launches": int(launches), "roofline": roofline}
 

@@ -120,7 +120,7 @@ EXPORTS = [
     "dfgpu_partition_plan_scatter_peer_chunk", "dfgpu_partition_plan_destroy",
     "dfgpu_ipc_export", "dfgpu_ipc_import", "dfgpu_ipc_close",
     "dfgpu_lookup_default_options", "dfgpu_lookup_create", "dfgpu_lookup_metric", "dfgpu_lookup_destroy", "dfgpu_lookup_clear",
-    "dfgpu_lookup_filter_buffer", "dfgpu_lookup_filter_allreduce_peer", "dfgpu_pipeline_sink_output_unordered", "dfgpu_column_minmax_device", "dfgpu_column_sum_device",
+    "dfgpu_lookup_filter_buffer", "dfgpu_lookup_filter_allreduce_peer", "dfgpu_pipeline_sink_output_unordered", "dfgpu_pipeline_set_name", "dfgpu_column_minmax_device", "dfgpu_column_sum_device",
     "dfgpu_pipeline_create", "dfgpu_pipeline_sink_build", "dfgpu_pipeline_sink_aggregate", "dfgpu_pipeline_sink_output",
     "dfgpu_pipeline_push_host", "dfgpu_pipeline_push_device", "dfgpu_pipeline_push_arrow", "dfgpu_pipeline_finish",
     "dfgpu_pipeline_next", "dfgpu_pipeline_metric", "dfgpu_pipeline_destroy",
@@ -223,6 +223,7 @@ def load_library() -> C.CDLL:
     sig("dfgpu_pipeline_sink_build", C.c_int, [vp, vp, i32, P(i32), i32])
     sig("dfgpu_pipeline_sink_aggregate", C.c_int, [vp, P(i32), i32, P(PipelineAgg), i32, i32, i64])
     sig("dfgpu_pipeline_sink_output", C.c_int, [vp, P(i32), i32, i64])
+    sig("dfgpu_pipeline_set_name", C.c_int, [vp, C.c_char_p])
     sig("dfgpu_pipeline_push_host", C.c_int, [vp, P(Column), i32])
     sig("dfgpu_pipeline_push_device", C.c_int, [vp, P(Column), i32])
     sig("dfgpu_pipeline_push_arrow", C.c_int, [vp, vp, vp])
@@ -729,8 +730,9 @@ class Pipeline(_Operator):
     """dfgpu_pipeline: predicate -> probe stage(s) -> sink, one pass.  stages: [(kind, key_col, Lookup)]"""
     _next_fn, _destroy_fn, _metric_fn = "dfgpu_pipeline_next", "dfgpu_pipeline_destroy", "dfgpu_pipeline_metric"
 
-    def __init__(self, ctx, input_types, predicate=None, stages=()):
+    def __init__(self, ctx, input_types, predicate=None, stages=(), name=None):
         super().__init__(ctx)
+        self._name = name
         self._keep = [st[2] for st in stages]
         na = expr_nodes(predicate) if predicate else None
         sa = (PipelineStage * max(len(stages), 1))()
@@ -738,6 +740,8 @@ class Pipeline(_Operator):
             sa[i].kind, sa[i].key_col, sa[i].lookup = kind, key_col, lk.h
         ctx.check(ctx.lib.dfgpu_pipeline_create(ctx.h, _i32arr(input_types), len(input_types), na, len(predicate) if predicate else 0,
                                                 sa, len(stages), C.byref(self.h)))
+        if name:
+            ctx.check(ctx.lib.dfgpu_pipeline_set_name(self.h, name.encode()))
 
     def sink_build(self, target: Lookup, key_col: int, payload_cols=()):
         self._keep.append(target)

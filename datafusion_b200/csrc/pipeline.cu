@@ -881,6 +881,7 @@ struct dfgpu_pipeline {
   DevBuf params_dev, counters;
   std::deque<BatchPtr> outq;
   int64_t m_input_rows = 0, m_sink_rows = 0, m_output_rows = 0, m_groups = 0;
+  std::string name;   // optional label: the kernel-timing family becomes "pipe:<name>" (dfgpu_kernel_time)
 };
 
 namespace dfgpu {
@@ -1083,7 +1084,8 @@ static void launch_pipe(dfgpu_pipeline* p, int64_t n, const char* timer_name) {
     blocks_per_sm = std::max(1, blocks_per_sm);
   }
   const int grid = (int)std::min<int64_t>(ntiles, (int64_t)kNumSMs * blocks_per_sm);
-  KernelTimer kt(ctx, timer_name);
+  const std::string tname = p->name.empty() ? std::string(timer_name) : "pipe:" + p->name;
+  KernelTimer kt(ctx, tname.c_str());
   pipe_kernel<SINK><<<grid, kPipeThreads, 0, ctx->stream>>>((const PipeParams*)p->params_dev.ptr, n, p->counters.as<unsigned long long>());
   DF_LAUNCH_CHECK(ctx);
 }
@@ -1615,6 +1617,12 @@ int dfgpu_pipeline_sink_output_unordered(dfgpu_pipeline* p, const int32_t* out_c
   const int rc = dfgpu_pipeline_sink_output(p, out_cols, n_out, batch_size);
   if (rc == DFGPU_OK) p->out_ordered = false;
   return rc;
+}
+
+int dfgpu_pipeline_set_name(dfgpu_pipeline* p, const char* name) {
+  if (!p || !name) return DFGPU_ERR_INVALID;
+  p->name = name;
+  return DFGPU_OK;
 }
 
 int dfgpu_pipeline_push_device(dfgpu_pipeline* p, const dfgpu_column* cols, int32_t n_cols) {

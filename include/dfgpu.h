@@ -423,6 +423,9 @@ int dfgpu_pipeline_sink_output(dfgpu_pipeline* p, const int32_t* out_cols, int32
 /* the same, row order unspecified (what a RepartitionExec consumer sees anyway, repartition/mod.rs:1320-1400): runs on the two-phase
  * kernel and is several times faster than the ordered sink on selective pipelines */
 int dfgpu_pipeline_sink_output_unordered(dfgpu_pipeline* p, const int32_t* out_cols, int32_t n_out, int64_t batch_size);
+/* optional label: this pipeline's kernel is timed under the family "pipe:<name>" (dfgpu_set_kernel_timing / dfgpu_kernel_time) —
+ * the per-operator metrics set of a plan node (metrics(), execution_plan.rs:713) */
+int dfgpu_pipeline_set_name(dfgpu_pipeline* p, const char* name);
 int dfgpu_pipeline_push_host(dfgpu_pipeline* p, const dfgpu_column* cols, int32_t n_cols);    /* H2D inside, overlapped with the kernel in row chunks */
 int dfgpu_pipeline_push_device(dfgpu_pipeline* p, const dfgpu_column* cols, int32_t n_cols);
 int dfgpu_pipeline_push_arrow(dfgpu_pipeline* p, const struct ArrowArray* batch, const struct ArrowSchema* schema);

@@ -141,12 +141,12 @@ def run_q3_fused(ctx, customer, orders, lineitem):
     stages["customer_building"] = p1.metric("sink_rows")
     p1.close()
     l2 = D.Lookup(ctx, D.INT64, [D.INT32, D.INT32], n_acc_words=2, membership_filter=-1)
-    p2 = D.Pipeline(ctx, orders.types, B(D.OP_LT, C(2), L(CUT, D.INT32)), [(D.STAGE_SEMI, 1, l1)])
+    p2 = D.Pipeline(ctx, orders.types, B(D.OP_LT, C(2), L(CUT, D.INT32)), [(D.STAGE_SEMI, 1, l1)], name="orders")
     p2.sink_build(l2, 0, [2, 3])
     p2.push_device(orders.cols); p2.finish()
     stages["orders_of_building_customers"] = p2.metric("sink_rows")
     p2.close()
-    p3 = D.Pipeline(ctx, lineitem.types, B(D.OP_GT, C(3), L(CUT, D.INT32)), [(D.STAGE_INNER, 0, l2)])
+    p3 = D.Pipeline(ctx, lineitem.types, B(D.OP_GT, C(3), L(CUT, D.INT32)), [(D.STAGE_INNER, 0, l2)], name="lineitem")
     p3.sink_aggregate([0, 4, 5], [(D.AGG_SUM, B(D.OP_MULTIPLY, C(1), B(D.OP_MINUS, L(100), C(2))))], D.AGG_SINGLE_PARTITIONED)
     p3.push_device(lineitem.cols); p3.finish()
     res = p3.drain(host=False)
@@ -169,12 +169,12 @@ def run_q3_fused_host(ctx, c_host, o_host, l_host, c_types, o_types, l_types):
     p1.sink_build(l1, 0, [])
     p1.push_device(c_dev); p1.finish(); p1.close()
     l2 = D.Lookup(ctx, D.INT64, [D.INT32, D.INT32], n_acc_words=2, membership_filter=-1)
-    p2 = D.Pipeline(ctx, o_types, B(D.OP_LT, C(2), L(CUT, D.INT32)), [(D.STAGE_SEMI, 1, l1)])
+    p2 = D.Pipeline(ctx, o_types, B(D.OP_LT, C(2), L(CUT, D.INT32)), [(D.STAGE_SEMI, 1, l1)], name="orders")
     p2.sink_build(l2, 0, [2, 3])
     p2.push_host(o_host); p2.finish()
     stages["orders_of_building_customers"] = p2.metric("sink_rows")
     p2.close()
-    p3 = D.Pipeline(ctx, l_types, B(D.OP_GT, C(3), L(CUT, D.INT32)), [(D.STAGE_INNER, 0, l2)])
+    p3 = D.Pipeline(ctx, l_types, B(D.OP_GT, C(3), L(CUT, D.INT32)), [(D.STAGE_INNER, 0, l2)], name="lineitem")
     p3.sink_aggregate([0, 4, 5], [(D.AGG_SUM, B(D.OP_MULTIPLY, C(1), B(D.OP_MINUS, L(100), C(2))))], D.AGG_SINGLE_PARTITIONED)
     p3.push_host(l_host); p3.finish()
     res = p3.drain(host=True)

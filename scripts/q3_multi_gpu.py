@@ -93,7 +93,7 @@ class PartitionedQ3:
         for b in ck:
             b.release()
         # ---- orders: filter + semi probe -> qualified orders; their keys -> membership filter F ----
-        p = D.Pipeline(ctx, orr.types, B(D.OP_LT, Cc(2), L(Q.CUT, D.INT32)), [(D.STAGE_SEMI, 1, l1)])
+        p = D.Pipeline(ctx, orr.types, B(D.OP_LT, Cc(2), L(Q.CUT, D.INT32)), [(D.STAGE_SEMI, 1, l1)], name="orders")
         p.sink_output([0, 2, 3], ordered=False)
         p.push_device(orr.cols); p.finish()
         qo = p.drain(host=False)
@@ -114,7 +114,7 @@ class PartitionedQ3:
         p.push_device(xo.columns()); p.finish(); p.close()
         st["orders_owned"] = xo.rows
         # ---- lineitem: filter + pushed-down membership filter -> exchange -> owner probes + aggregates ----
-        p = D.Pipeline(ctx, li.types, B(D.OP_GT, Cc(3), L(Q.CUT, D.INT32)), [(D.STAGE_MAYBE, 0, self.F)])
+        p = D.Pipeline(ctx, li.types, B(D.OP_GT, Cc(3), L(Q.CUT, D.INT32)), [(D.STAGE_MAYBE, 0, self.F)], name="lineitem")
         p.sink_output([0, 1, 2], ordered=False)
         p.push_device(li.cols); p.finish()
         ql = p.drain(host=False)
@@ -124,7 +124,7 @@ class PartitionedQ3:
         xl = self.px_l.exchange(lcols, [0])               # RepartitionExec Hash(l_orderkey)
         for b in ql:
             b.release()
-        p = D.Pipeline(ctx, [D.INT64, D.INT64, D.INT64], None, [(D.STAGE_INNER, 0, l2)])
+        p = D.Pipeline(ctx, [D.INT64, D.INT64, D.INT64], None, [(D.STAGE_INNER, 0, l2)], name="owner_probe_agg")
         p.sink_aggregate([0, 3, 4], [(D.AGG_SUM, B(D.OP_MULTIPLY, Cc(1), B(D.OP_MINUS, L(100), Cc(2))))], D.AGG_SINGLE_PARTITIONED)
         p.push_device(xl.columns()); p.finish()
         self.last_res = p.drain(host=False)
