@@ -67,6 +67,26 @@ def usable_threads():
     return n
 
 
+def gpu_local_cpus(device):
+    """CPUs on the GPU's NUMA node (nvidia-smi topo -m "CPU Affinity" column), or None.  Pinned host buffers are allocated on the node of
+    the allocating thread: a staging buffer on the far socket costs PCIe H2D bandwidth."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        for line in out.splitlines():
+            parts = line.split()
+            if parts and parts[0] == f"GPU{device}":
+                for tok in parts[1:]:
+                    if tok[0].isdigit() and ("-" in tok or "," in tok) and not tok.startswith("NV"):
+                        cpus = set()
+                        for rng in tok.split(","):
+                            lo, _, hi = rng.partition("-")
+                            cpus.update(range(int(lo), int(hi or lo) + 1))
+                        return cpus & set(os.sched_getaffinity(0)) or None
+    except Exception:
+        pass
+    return None
+
+
 def mem_available_gb():
     try:
         for line in open("/proc/meminfo"):
@@ -455,6 +475,10 @@ def main():
     # ---- e2e through the C ABI with host (pinned) buffers ----
     if world == 1:
         import ctypes as C
+        old_aff = os.sched_getaffinity(0)
+        local_cpus = gpu_local_cpus(local)
+        if local_cpus:
+            os.sched_setaffinity(0, local_cpus)     # allocate (first-touch) the pinned staging buffers on the GPU's NUMA node
         hcols = {}
         for tname, t in (("c", cu), ("o", orr), ("l", li)):
             hs = []
@@ -482,8 +506,9 @@ def main():
         args.e2e_steps = max(args.e2e_steps, 1)
         line["e2e"] = {"value": in_rows * args.e2e_steps / (t1 - t0), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
                        "ms_per_step": 1000 * (t1 - t0) / args.e2e_steps, "timer": "host wall clock around the C-ABI calls (H2D of the three tables from pinned memory, kernels, D2H of the result rows)",
-                       "pcie_gbs": (h2d + d2h) * args.e2e_steps / (t1 - t0) / 1e9}
+                       "pcie_gbs": (h2d + d2h) * args.e2e_steps / (t1 - t0) / 1e9, "host_thread_pinned_to_gpu_numa_node": bool(local_cpus)}
         del hcols
+        os.sched_setaffinity(0, old_aff)
     elif rank == 0 or world > 1:
         e2e = runner.e2e(args.e2e_steps, barrier)
         if rank == 0:
