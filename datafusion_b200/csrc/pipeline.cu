@@ -29,6 +29,7 @@
 #include "expr_dev.cuh"
 #include <climits>
 #include <array>
+#include <algorithm>
 
 namespace dfgpu {
 
@@ -62,6 +63,8 @@ struct PipeParams {
   LookupDev target; int bkey_col, target_unique, n_bpay, bpay_src[kMaxBuildPay], bpay_shift[kMaxBuildPay], bpay_width[kMaxBuildPay];
   // aggregate sink (group id == record of stage `agg_stage`)
   int agg_stage, rows_word, n_aggs; AggDef agg[kMaxPipeAggs];
+  // input columns the sink reads per survivor (aggregate arguments, build key / payload, output columns): prefetched to L2 at enqueue time
+  int n_sinkcols, sinkcol[8];
   // unordered output sink
   int n_out, out_src[kMaxPipeCols], out_width[kMaxPipeCols]; void* out_dst[kMaxPipeCols]; unsigned long long* out_counter;
   ENode pool[kPoolNodes];
@@ -393,6 +396,11 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
 #pragma unroll
               for (int j = 0; j < kWarpRows; ++j) pass |= (uint32_t)bloom_test(bw[j], bt[j]) << j;
               mask &= pass;
+              if ((sp.hints & 8) && st.kind != kStageMaybe && st.lk.cap) {   // the rare rows that pass: fetch their table record towards L2 now
+#pragma unroll
+                for (int j = 0; j < kWarpRows; ++j)
+                  if ((mask >> j) & 1u) asm volatile("prefetch.global.L2 [%0];" :: "l"(st.lk.recs + __umul64hi(lk_hash(key[j]), st.lk.cap) * (uint64_t)st.lk.stride));
+              }
             }
           }
         }
@@ -405,7 +413,12 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
       unsigned int pos = qn + incl - cnt;
 #pragma unroll
       for (int j = 0; j < kWarpRows; ++j)
-        if ((mask >> j) & 1u) { q_row[pos] = (uint32_t)(row0 + j); ++pos; }
+        if ((mask >> j) & 1u) {
+          q_row[pos] = (uint32_t)(row0 + j); ++pos;
+          if (sp.hints & 8) {   // the survivor waits in the queue for a few tiles: start its DRAM fetches now, phase B then hits L2
+            for (int c = 0; c < sp.n_sinkcols; ++c) { const ColRef& sc = sp.col[sp.sinkcol[c]]; asm volatile("prefetch.global.L2 [%0];" :: "l"((const char*)sc.ptr + (row0 + j) * sc.width)); }
+          }
+        }
       qn += __shfl_sync(0xffffffffu, incl, 31);
       __syncwarp();
     }
@@ -1018,7 +1031,7 @@ static bool expr_can_be_null(const ExprPlan& plan, const std::vector<DCol>& cols
 static void fill_params(dfgpu_pipeline* p, const std::vector<DCol>& cols, PipeParams* pp) {
   memset(pp, 0, sizeof(*pp));
   pp->n_cols = (int)cols.size();
-  static const int hints_env = getenv("DFGPU_PIPE_HINTS") ? atoi(getenv("DFGPU_PIPE_HINTS")) : 7;   // 1 stream evict-first, 2 filter evict-last, 4 L2 prefetch one tile ahead
+  static const int hints_env = getenv("DFGPU_PIPE_HINTS") ? atoi(getenv("DFGPU_PIPE_HINTS")) : 15;  // 1 stream evict-first, 2 filter evict-last, 4 L2 prefetch one tile ahead, 8 survivor prefetch
   pp->hints = hints_env;
   for (size_t c = 0; c < cols.size(); ++c) pp->col[c] = col_ref(cols[c]);
   int pool_used = 0;
@@ -1056,6 +1069,15 @@ static void fill_params(dfgpu_pipeline* p, const std::vector<DCol>& cols, PipePa
   for (size_t s = 0; s < p->stages.size(); ++s) if (p->stages[s].lookup->mode == LK_HASH && p->stages[s].kind != DFGPU_STAGE_MAYBE && pp->first_hash < 0) pp->first_hash = (int)s;
   for (size_t s = 0; s < p->stages.size(); ++s) {
     pp->stage[s].kind = p->stages[s].kind; pp->stage[s].key_col = p->stages[s].key_col; pp->stage[s].lk = lookup_dev(p->stages[s].lookup);
+  }
+  {   // input columns read per survivor by the sink
+    std::vector<int> sc;
+    auto add = [&](int c) { if (c >= 0 && c < (int)cols.size() && std::find(sc.begin(), sc.end(), c) == sc.end() && sc.size() < 8) sc.push_back(c); };
+    if (p->sink == SINK_BUILD) { add(p->bkey_col); for (int c : p->bpay_cols) add(c); }
+    else if (p->sink == SINK_AGG) { for (const PipeAgg& ag : p->aggs) if (ag.has_expr) for (const auto& nd : ag.plan.nodes) if (nd.kind == DFGPU_EXPR_COLUMN) add(nd.a); }
+    else if (p->sink == SINK_OUTPUT) { for (int c : p->out_cols) add(c); }
+    pp->n_sinkcols = (int)sc.size();
+    for (size_t i = 0; i < sc.size(); ++i) pp->sinkcol[i] = sc[i];
   }
   pp->n_ext = (int)p->exts.size();
   for (size_t e = 0; e < p->exts.size(); ++e) pp->ext[e] = p->exts[e];
