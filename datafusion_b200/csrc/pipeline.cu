@@ -29,7 +29,6 @@
 #include "expr_dev.cuh"
 #include <climits>
 #include <array>
-#include <algorithm>
 
 namespace dfgpu {
 
@@ -63,8 +62,6 @@ struct PipeParams {
   LookupDev target; int bkey_col, target_unique, n_bpay, bpay_src[kMaxBuildPay], bpay_shift[kMaxBuildPay], bpay_width[kMaxBuildPay];
   // aggregate sink (group id == record of stage `agg_stage`)
   int agg_stage, rows_word, n_aggs; AggDef agg[kMaxPipeAggs];
-  // input columns the sink reads per survivor (aggregate arguments, build key / payload, output columns): prefetched to L2 at enqueue time
-  int n_sinkcols, sinkcol[8];
   // unordered output sink
   int n_out, out_src[kMaxPipeCols], out_width[kMaxPipeCols]; void* out_dst[kMaxPipeCols]; unsigned long long* out_counter;
   ENode pool[kPoolNodes];
@@ -270,14 +267,6 @@ __device__ __forceinline__ void load8(const ColRef& c, int64_t row0, int64_t n, 
     }
   }
 }
-// L2 prefetch of the 8 rows a lane will read from column c one tile ahead: the next iteration's 128-bit loads then hit L2 instead of
-// waiting a full DRAM round trip (the kernel is latency-bound at 37 % occupancy: issue slots are 70 % idle, long-scoreboard stalls lead)
-__device__ __forceinline__ void prefetch8(const ColRef& c, int64_t row0, int64_t n) {
-  if (row0 + kWarpRows > n) return;
-  const char* p = (const char*)c.ptr + row0 * c.width;
-  asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
-  if (c.width == 8) asm volatile("prefetch.global.L2 [%0];" :: "l"(p + 32));
-}
 // validity bits of the same 8 rows (bit j = row0 + j is non-NULL)
 __device__ __forceinline__ uint32_t valid8(const ColRef& c, int64_t row0, int64_t n) {
   if (!c.valid) return 0xFFu;
@@ -306,11 +295,6 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
     if (!draining) {
       // =============================== phase A ===============================
       const int64_t row0 = tile * kWarpTile + (int64_t)lane * kWarpRows;
-      if (sp.hints & 4) {   // one tile ahead: the predicate's columns and every stage's key column
-        const int64_t nrow0 = row0 + nwarps * kWarpTile;
-        if (sp.pred_mode == 1) for (int t = 0; t < sp.n_terms; ++t) prefetch8(sp.col[sp.term_col[t]], nrow0, n);
-        for (int s = 0; s < sp.n_stages; ++s) prefetch8(sp.col[sp.stage[s].key_col], nrow0, n);
-      }
       uint32_t mask = row0 + kWarpRows <= n ? 0xFFu : (row0 < n ? (1u << (int)(n - row0)) - 1u : 0u);
       if (sp.pred_mode == 1) {   // FilterExec, conjunction of `column <cmp> literal`
 #pragma unroll 1
@@ -321,29 +305,23 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
           mask &= valid8(c, row0, n);            // a NULL predicate drops the row
           const int op = sp.term_op[t];
           const long long lit = sp.term_lit[t];
-          uint32_t r = 0;
-#define DF_CMP8(EXPR) do { _Pragma("unroll") for (int j = 0; j < kWarpRows; ++j) r |= (uint32_t)(EXPR) << j; } while (0)
+          uint32_t lt = 0, eq = 0;
           if (sp.term_uns[t]) {
-            const uint64_t ul = (uint64_t)lit;
-            switch (op) {
-              case DFGPU_OP_EQ: DF_CMP8(v[j] == ul); break;
-              case DFGPU_OP_NEQ: DF_CMP8(v[j] != ul); break;
-              case DFGPU_OP_LT: DF_CMP8(v[j] < ul); break;
-              case DFGPU_OP_LTEQ: DF_CMP8(v[j] <= ul); break;
-              case DFGPU_OP_GT: DF_CMP8(v[j] > ul); break;
-              default: DF_CMP8(v[j] >= ul); break;
-            }
+#pragma unroll
+            for (int j = 0; j < kWarpRows; ++j) { lt |= (uint32_t)(v[j] < (uint64_t)lit) << j; eq |= (uint32_t)(v[j] == (uint64_t)lit) << j; }
           } else {
-            switch (op) {
-              case DFGPU_OP_EQ: DF_CMP8((long long)v[j] == lit); break;
-              case DFGPU_OP_NEQ: DF_CMP8((long long)v[j] != lit); break;
-              case DFGPU_OP_LT: DF_CMP8((long long)v[j] < lit); break;
-              case DFGPU_OP_LTEQ: DF_CMP8((long long)v[j] <= lit); break;
-              case DFGPU_OP_GT: DF_CMP8((long long)v[j] > lit); break;
-              default: DF_CMP8((long long)v[j] >= lit); break;
-            }
+#pragma unroll
+            for (int j = 0; j < kWarpRows; ++j) { lt |= (uint32_t)((long long)v[j] < lit) << j; eq |= (uint32_t)((long long)v[j] == lit) << j; }
           }
-#undef DF_CMP8
+          uint32_t r;
+          switch (op) {
+            case DFGPU_OP_EQ: r = eq; break;
+            case DFGPU_OP_NEQ: r = ~eq; break;
+            case DFGPU_OP_LT: r = lt; break;
+            case DFGPU_OP_LTEQ: r = lt | eq; break;
+            case DFGPU_OP_GT: r = ~(lt | eq); break;
+            default: r = ~lt; break;
+          }
           mask &= r;
         }
       } else if (sp.pred_mode == 2) {   // FilterExec, general expression
@@ -396,11 +374,6 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
 #pragma unroll
               for (int j = 0; j < kWarpRows; ++j) pass |= (uint32_t)bloom_test(bw[j], bt[j]) << j;
               mask &= pass;
-              if ((sp.hints & 8) && st.kind != kStageMaybe && st.lk.cap) {   // the rare rows that pass: fetch their table record towards L2 now
-#pragma unroll
-                for (int j = 0; j < kWarpRows; ++j)
-                  if ((mask >> j) & 1u) asm volatile("prefetch.global.L2 [%0];" :: "l"(st.lk.recs + __umul64hi(lk_hash(key[j]), st.lk.cap) * (uint64_t)st.lk.stride));
-              }
             }
           }
         }
@@ -413,12 +386,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
       unsigned int pos = qn + incl - cnt;
 #pragma unroll
       for (int j = 0; j < kWarpRows; ++j)
-        if ((mask >> j) & 1u) {
-          q_row[pos] = (uint32_t)(row0 + j); ++pos;
-          if (sp.hints & 8) {   // the survivor waits in the queue for a few tiles: start its DRAM fetches now, phase B then hits L2
-            for (int c = 0; c < sp.n_sinkcols; ++c) { const ColRef& sc = sp.col[sp.sinkcol[c]]; asm volatile("prefetch.global.L2 [%0];" :: "l"((const char*)sc.ptr + (row0 + j) * sc.width)); }
-          }
-        }
+        if ((mask >> j) & 1u) { q_row[pos] = (uint32_t)(row0 + j); ++pos; }
       qn += __shfl_sync(0xffffffffu, incl, 31);
       __syncwarp();
     }
@@ -1031,7 +999,7 @@ static bool expr_can_be_null(const ExprPlan& plan, const std::vector<DCol>& cols
 static void fill_params(dfgpu_pipeline* p, const std::vector<DCol>& cols, PipeParams* pp) {
   memset(pp, 0, sizeof(*pp));
   pp->n_cols = (int)cols.size();
-  static const int hints_env = getenv("DFGPU_PIPE_HINTS") ? atoi(getenv("DFGPU_PIPE_HINTS")) : 15;  // 1 stream evict-first, 2 filter evict-last, 4 L2 prefetch one tile ahead, 8 survivor prefetch
+  static const int hints_env = getenv("DFGPU_PIPE_HINTS") ? atoi(getenv("DFGPU_PIPE_HINTS")) : 3;
   pp->hints = hints_env;
   for (size_t c = 0; c < cols.size(); ++c) pp->col[c] = col_ref(cols[c]);
   int pool_used = 0;
@@ -1069,15 +1037,6 @@ static void fill_params(dfgpu_pipeline* p, const std::vector<DCol>& cols, PipePa
   for (size_t s = 0; s < p->stages.size(); ++s) if (p->stages[s].lookup->mode == LK_HASH && p->stages[s].kind != DFGPU_STAGE_MAYBE && pp->first_hash < 0) pp->first_hash = (int)s;
   for (size_t s = 0; s < p->stages.size(); ++s) {
     pp->stage[s].kind = p->stages[s].kind; pp->stage[s].key_col = p->stages[s].key_col; pp->stage[s].lk = lookup_dev(p->stages[s].lookup);
-  }
-  {   // input columns read per survivor by the sink
-    std::vector<int> sc;
-    auto add = [&](int c) { if (c >= 0 && c < (int)cols.size() && std::find(sc.begin(), sc.end(), c) == sc.end() && sc.size() < 8) sc.push_back(c); };
-    if (p->sink == SINK_BUILD) { add(p->bkey_col); for (int c : p->bpay_cols) add(c); }
-    else if (p->sink == SINK_AGG) { for (const PipeAgg& ag : p->aggs) if (ag.has_expr) for (const auto& nd : ag.plan.nodes) if (nd.kind == DFGPU_EXPR_COLUMN) add(nd.a); }
-    else if (p->sink == SINK_OUTPUT) { for (int c : p->out_cols) add(c); }
-    pp->n_sinkcols = (int)sc.size();
-    for (size_t i = 0; i < sc.size(); ++i) pp->sinkcol[i] = sc[i];
   }
   pp->n_ext = (int)p->exts.size();
   for (size_t e = 0; e < p->exts.size(); ++e) pp->ext[e] = p->exts[e];
