@@ -1615,8 +1615,8 @@ static void push_probe(dfgpu_hashjoin* j, std::vector<DCol>&& cols) {
         }
         {
           KernelTimer kt(ctx, "join_probe");
-          if (j->inline_words == 2) radix_probe_kernel<2><<<kNumSMs * 6, 256, 0, ctx->stream>>>(recs.as<RadixRec>(), n, j->iref, ro, rtile, rtot);
-          else radix_probe_kernel<1><<<kNumSMs * 6, 256, 0, ctx->stream>>>(recs.as<RadixRec>(), n, j->iref, ro, rtile, rtot);
+          if (j->inline_words == 2) radix_probe_kernel<2><<<kNumSMs * 8, 256, 0, ctx->stream>>>(recs.as<RadixRec>(), n, j->iref, ro, rtile, rtot);
+          else radix_probe_kernel<1><<<kNumSMs * 8, 256, 0, ctx->stream>>>(recs.as<RadixRec>(), n, j->iref, ro, rtile, rtot);
           DF_LAUNCH_CHECK(ctx);
         }
         unsigned long long hrows = 0;
