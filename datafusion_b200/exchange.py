@@ -291,6 +291,21 @@ def peer_chunk_layout(m, rank: int):
     return dst_row, chunk_start[:, rank].copy(), per_chunk[:, rank].copy(), int(per_chunk.sum(axis=0).max())
 
 
+def allgather_wrapping_sum(dist, values: Sequence[int], device) -> List[int]:
+    """element-wise sum mod 2^64 of one vector of unsigned 64-bit values per rank (order-independent result fingerprints: every group /
+    row is owned by exactly one rank).  Exact on the host from an all-gather — NCCL / gloo reductions have no wrapping uint64 sum."""
+    import torch
+    m64 = (1 << 64) - 1
+    t = torch.tensor([int(v) - (1 << 64) if int(v) >= (1 << 63) else int(v) for v in values], dtype=torch.int64, device=device)
+    allt = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(allt, t)
+    tot = [0] * len(values)
+    for a in allt:
+        for i, v in enumerate(a.cpu().tolist()):
+            tot[i] = (tot[i] + (v & m64)) & m64
+    return tot
+
+
 def _check_distributed_join(join_kwargs, supported, who):
     jt = join_kwargs.get("join_type", D.JOIN_INNER)
     if jt not in supported:

@@ -139,16 +139,8 @@ class PartitionedQ3:
         return fp + [self.last_stages.get("joined_rows_owned", 0), self.last_stages.get("orders_owned", 0)]
 
     def all_reduce_fingerprint(self, fp_local):
-        """wrapping sum over ranks (every group is owned by exactly one rank), computed exactly on the host from an all-gather"""
-        torch = self.torch
-        t = torch.tensor([int(x) - (1 << 64) if int(x) >= (1 << 63) else int(x) for x in fp_local], dtype=torch.int64, device=self.dev)
-        allt = [torch.zeros_like(t) for _ in range(self.world)]
-        self.dist.all_gather(allt, t)
-        tot = [0] * len(fp_local)
-        for a in allt:
-            for i, v in enumerate(a.cpu().tolist()):
-                tot[i] = (tot[i] + (v & M64)) & M64
-        return tot
+        """wrapping sum over ranks (every group is owned by exactly one rank)"""
+        return exchange.allgather_wrapping_sum(self.dist, fp_local, self.dev)
 
     def e2e(self, steps, barrier):
         """host leg: every rank uploads its shard from pinned host memory each step (H2D inside the timed region), runs the step and

@@ -117,3 +117,68 @@ def test_peer_chunk_layout_is_a_disjoint_cover():
                 assert rows[c] == m[:, c, dst].sum()
                 assert start[c] == m[:, :c, dst].sum()
             assert mx == m.sum(axis=(0, 1)).max()
+
+
+def _q3_worker(rank, world, port, out_q):
+    """the partitioned multi-GPU Q3 plan (scripts/q3_multi_gpu.py) with the oracle's CPU operators in place of the kernels: same sharding,
+    same exchanges (customer keys all-gathered; qualified orders and filtered lineitems hash-exchanged to their owners; groups owned by
+    the owner of their order key), same fingerprint reduction"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from datafusion_b200 import exchange
+    from oracle import oracle as O
+    sf = 0.02
+    t = O.q3_generate(sf * world, threads=1)                                   # the global database; this rank owns a contiguous row range of each table
+    sl = lambda a, n: a[rank * n:(rank + 1) * n]
+    nc, no, nl = len(t["c_custkey"]) // world, len(t["o_orderkey"]) // world, len(t["l_orderkey"]) // world
+    dev = torch.device("cpu")
+
+    def a2a(cols, key):
+        pid = _partition_ids(cols[key], world)
+        order = np.argsort(pid, kind="stable")
+        sc_ = np.bincount(pid, minlength=world).tolist()
+        rc_ = exchange.exchange_counts(dist, sc_, dev)
+        sc, rc, so, ro = exchange.plan_all_to_all(sc_, rc_)
+        got = exchange.all_to_all_columns(dist, [torch.from_numpy(np.ascontiguousarray(c[order])) for c in cols], sc, rc)
+        return [g.numpy() for g in got]
+    # customer: filter -> keys -> all-gather (CollectLeft)
+    ck = sl(t["c_custkey"], nc)[sl(t["c_mktsegment"], nc) == 1]
+    cnt = torch.tensor([len(ck)]); allc = [torch.zeros_like(cnt) for _ in range(world)]; dist.all_gather(allc, cnt)
+    mx = max(int(c.item()) for c in allc)
+    pad = torch.zeros(mx, dtype=torch.int64); pad[:len(ck)] = torch.from_numpy(ck)
+    allk = [torch.zeros_like(pad) for _ in range(world)]; dist.all_gather(allk, pad)
+    cust = np.concatenate([k.numpy()[:int(c.item())] for k, c in zip(allk, allc)])
+    # orders: filter + semi -> exchange by o_orderkey
+    ok, oc, od, op_ = sl(t["o_orderkey"], no), sl(t["o_custkey"], no), sl(t["o_orderdate"], no), sl(t["o_shippriority"], no)
+    m = (od < O.Q3_CUT) & np.isin(oc, cust)
+    qo = a2a([ok[m], od[m].astype(np.int64), op_[m].astype(np.int64)], 0)
+    # lineitem: filter -> exchange by l_orderkey (the membership filter only removes rows without a partner: same result)
+    lk, lp, ld, ls = sl(t["l_orderkey"], nl), sl(t["l_extendedprice"], nl), sl(t["l_discount"], nl), sl(t["l_shipdate"], nl)
+    m = ls > O.Q3_CUT
+    ql = a2a([lk[m], lp[m], ld[m]], 0)
+    # owner: Inner join + group-by (the oracle's operators)
+    j = O.hash_join([(qo[0], None), (qo[1], None), (qo[2], None)], [(ql[0], None), (ql[1], None), (ql[2], None)], [0], [0], [1, 0, 0, 1, 1], [0, 1, 2, 1, 2])
+    rev = (j[3][0].astype(np.uint64) * (100 - j[4][0]).astype(np.uint64)).view(np.int64)
+    keys, res = O.group_by([j[0], j[1], j[2]], [(O.A_SUM, (rev, None), None)]) if len(rev) else ([(np.zeros(0, np.int64), None)] * 3, [{"i": np.zeros(0, np.int64)}])
+    usum = lambda a: int(np.asarray(a).astype(np.int64).view(np.uint64).sum(dtype=np.uint64))
+    fp_local = [len(keys[0][0]), usum(keys[0][0]), usum(keys[1][0]), usum(keys[2][0]), usum(res[0]["i"]), len(rev), len(qo[0])]
+    fp = exchange.allgather_wrapping_sum(dist, fp_local, dev)
+    if rank == 0:
+        efp, ejoined, eorders = O.q3_stream_fingerprint(sf * world, threads=2)
+        out_q.put((fp, efp + [ejoined, eorders]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_partitioned_q3_plan_world_size_2_matches_the_global_evaluation():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_q3_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, exp = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert got == exp and got[0] > 100
