@@ -16,8 +16,7 @@ sys.path.insert(0, ROOT)
 
 def _bench(monkeypatch):
     b = importlib.import_module("bench")
-    monkeypatch.setattr(b, "NB_PER_GPU", 200_000)
-    monkeypatch.setattr(b, "NP_PER_GPU", 2_000_000)
+    monkeypatch.setenv("DFGPU_Q3_SF", "0.2")          # a small instance of the same Q3 workload keeps the CPU arm to seconds here
     return b
 
 
@@ -35,6 +34,15 @@ def test_reference_arm_prints_the_contract_line(monkeypatch, capsys):
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["metric"] == b.METRIC
+    assert d["config"]["workload"].startswith("C4 TPC-H Q3-shaped pipeline, SF0.2") and d["config"]["fingerprint"][0] > 1000
+    assert d["cpu_baseline"]["runs"] == 2 and d["cpu_baseline"]["best_rows_per_s"] >= d["cpu_baseline"]["median_rows_per_s"] * 0.999
+
+
+def test_usable_threads_respects_affinity_and_quota(monkeypatch):
+    b = importlib.import_module("bench")
+    n = b.usable_threads()
+    assert 1 <= n <= len(os.sched_getaffinity(0))
+    assert b.cpu_sample_sf(100.0) in (100.0, 50.0, 25.0, 12.5, 6.25, 3.125, 1.5625, 0.78125)
 
 
 def test_reference_arm_is_rank0_only(monkeypatch, capsys):
