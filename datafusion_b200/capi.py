@@ -119,6 +119,8 @@ EXPORTS = [
     "dfgpu_partition_plan_create", "dfgpu_partition_plan_scatter_peer", "dfgpu_partition_plan_create_chunked",
     "dfgpu_partition_plan_scatter_peer_chunk", "dfgpu_partition_plan_destroy",
     "dfgpu_ipc_export", "dfgpu_ipc_import", "dfgpu_ipc_close",
+    "dfgpu_comm_unique_id", "dfgpu_comm_init", "dfgpu_comm_rank", "dfgpu_comm_size", "dfgpu_comm_barrier", "dfgpu_comm_allgather_i64", "dfgpu_comm_share",
+    "dfgpu_comm_destroy", "dfgpu_exchange_create", "dfgpu_exchange_run", "dfgpu_exchange_columns", "dfgpu_exchange_destroy",
     "dfgpu_lookup_default_options", "dfgpu_lookup_create", "dfgpu_lookup_metric", "dfgpu_lookup_destroy", "dfgpu_lookup_clear",
     "dfgpu_lookup_filter_buffer", "dfgpu_lookup_filter_allreduce_peer", "dfgpu_pipeline_sink_output_unordered", "dfgpu_pipeline_set_name", "dfgpu_column_minmax_device", "dfgpu_column_sum_device",
     "dfgpu_pipeline_create", "dfgpu_pipeline_sink_build", "dfgpu_pipeline_sink_aggregate", "dfgpu_pipeline_sink_output",
@@ -209,6 +211,18 @@ def load_library() -> C.CDLL:
     sig("dfgpu_ipc_export", C.c_int, [vp, vp, C.c_char_p])
     sig("dfgpu_ipc_import", C.c_int, [vp, C.c_char_p, P(vp)])
     sig("dfgpu_ipc_close", C.c_int, [vp, vp])
+    sig("dfgpu_comm_unique_id", C.c_int, [C.c_char_p])
+    sig("dfgpu_comm_init", C.c_int, [vp, i32, i32, C.c_char_p, P(vp)])
+    sig("dfgpu_comm_rank", i32, [vp])
+    sig("dfgpu_comm_size", i32, [vp])
+    sig("dfgpu_comm_barrier", C.c_int, [vp])
+    sig("dfgpu_comm_allgather_i64", C.c_int, [vp, P(i64), i32, P(i64)])
+    sig("dfgpu_comm_share", C.c_int, [vp, vp, P(vp)])
+    sig("dfgpu_comm_destroy", None, [vp])
+    sig("dfgpu_exchange_create", C.c_int, [vp, P(i32), i32, i64, P(vp)])
+    sig("dfgpu_exchange_run", C.c_int, [vp, P(Column), i32, P(i32), i32, P(i64)])
+    sig("dfgpu_exchange_columns", C.c_int, [vp, P(Column), i32])
+    sig("dfgpu_exchange_destroy", None, [vp])
     sig("dfgpu_lookup_default_options", None, [P(LookupOptions)])
     sig("dfgpu_lookup_create", C.c_int, [vp, i32, P(i32), i32, P(LookupOptions), P(vp)])
     sig("dfgpu_lookup_metric", i64, [vp, C.c_char_p])
@@ -769,3 +783,55 @@ class Pipeline(_Operator):
     def push_device(self, cols): self._push("dfgpu_pipeline_push_device", cols)
     def push_arrow(self, rb): self._push_arrow("dfgpu_pipeline_push_arrow", rb)
     def finish(self): self.ctx.check(self.ctx.lib.dfgpu_pipeline_finish(self.h))
+
+
+def comm_unique_id() -> bytes:
+    """128-byte rendezvous id (the role of ncclUniqueId): create on one rank, hand to every rank by any means"""
+    buf = C.create_string_buffer(128)
+    if load_library().dfgpu_comm_unique_id(buf) != OK:
+        raise DfgpuError(-1, "cannot create a communicator id")
+    return buf.raw
+
+
+class Comm:
+    """dfgpu_comm: the ranks (one process per GPU) of one box — barrier, count all-gather, buffer sharing over CUDA IPC; no NCCL"""
+
+    def __init__(self, ctx: Context, n_ranks: int, rank: int, unique_id: bytes):
+        self.ctx, self.h = ctx, C.c_void_p()
+        ctx.check(ctx.lib.dfgpu_comm_init(ctx.h, n_ranks, rank, unique_id, C.byref(self.h)))
+        self.rank, self.size = rank, n_ranks
+
+    def barrier(self):
+        self.ctx.check(self.ctx.lib.dfgpu_comm_barrier(self.h))
+
+    def allgather_i64(self, mine: Sequence[int]) -> List[List[int]]:
+        n = len(mine)
+        a = (C.c_int64 * n)(*mine); out = (C.c_int64 * (n * self.size))()
+        self.ctx.check(self.ctx.lib.dfgpu_comm_allgather_i64(self.h, a, n, out))
+        return [list(out[r * n:(r + 1) * n]) for r in range(self.size)]
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.dfgpu_comm_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class Exchange:
+    """dfgpu_exchange: RepartitionExec Hash across the ranks of a Comm, entirely inside the library"""
+
+    def __init__(self, comm: Comm, col_types: Sequence[int], cap_rows: int):
+        self.comm, self.ctx, self.types, self.h = comm, comm.ctx, list(col_types), C.c_void_p()
+        self.ctx.check(self.ctx.lib.dfgpu_exchange_create(comm.h, _i32arr(self.types), len(self.types), int(cap_rows), C.byref(self.h)))
+
+    def run(self, cols, key_cols: Sequence[int]) -> List[Column]:
+        rows = C.c_int64()
+        self.ctx.check(self.ctx.lib.dfgpu_exchange_run(self.h, _cols(cols), len(cols), _i32arr(list(key_cols)), len(key_cols), C.byref(rows)))
+        out = (Column * len(self.types))()
+        self.ctx.check(self.ctx.lib.dfgpu_exchange_columns(self.h, out, len(self.types)))
+        self.rows = rows.value
+        return [out[i] for i in range(len(self.types))]
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.dfgpu_exchange_destroy(self.h)
+            self.h = C.c_void_p()

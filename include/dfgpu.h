@@ -480,6 +480,34 @@ int dfgpu_ipc_export(dfgpu_ctx* ctx, void* dev_ptr, uint8_t* handle_out);
 int dfgpu_ipc_import(dfgpu_ctx* ctx, const uint8_t* handle, void** peer_ptr_out);
 int dfgpu_ipc_close(dfgpu_ctx* ctx, void* peer_ptr);
 
+/* ===================================================================================== */
+/* multi-GPU control inside the ABI (one process or thread per GPU of ONE box): what a Rust host needs to drive the partition
+ * exchange without NCCL / torch.distributed.  Control plane: a POSIX shared-memory segment named after a 128-byte unique id the
+ * application hands to every rank (the role of ncclUniqueId); data plane: CUDA IPC — every rank maps every peer's receive buffers
+ * and the scatter kernel stores rows straight into the owner's HBM over NVLink.  Reference analogue: the channels of RepartitionExec
+ * (physical-plan/src/repartition/mod.rs:618-648, 1320-1400).                              */
+/* ===================================================================================== */
+typedef struct dfgpu_comm dfgpu_comm;
+typedef struct dfgpu_exchange dfgpu_exchange;
+int dfgpu_comm_unique_id(uint8_t* id_out /* 128 bytes */);      /* call once, broadcast to every rank by any means */
+int dfgpu_comm_init(dfgpu_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t* id /* 128 bytes */, dfgpu_comm** out); /* collective */
+int32_t dfgpu_comm_rank(dfgpu_comm* c);
+int32_t dfgpu_comm_size(dfgpu_comm* c);
+/* collective: returns once every rank's ctx stream has drained and every rank has arrived */
+int dfgpu_comm_barrier(dfgpu_comm* c);
+/* collective: all[r][0..n) = rank r's `mine` (n <= 64): the count matrix of an exchange */
+int dfgpu_comm_allgather_i64(dfgpu_comm* c, const int64_t* mine, int32_t n, int64_t* all);
+/* collective: share a device allocation made with dfgpu_malloc; peer_ptrs_out[r] = rank r's buffer mapped here (own pointer for r == rank) */
+int dfgpu_comm_share(dfgpu_comm* c, void* dev_ptr, void** peer_ptrs_out);
+void dfgpu_comm_destroy(dfgpu_comm* c);
+/* RepartitionExec Hash(key columns) across the ranks (repartition/mod.rs:1097-1145): persistent receive buffers of cap_rows rows per
+ * column, shared once; one run = histogram -> count all-gather -> fused partition + peer-memory scatter -> barrier.  Rows arrive grouped
+ * by source rank, in source order.  All three calls are collective; columns must be free of NULLs. */
+int dfgpu_exchange_create(dfgpu_comm* c, const int32_t* col_types, int32_t n_cols, int64_t cap_rows, dfgpu_exchange** out);
+int dfgpu_exchange_run(dfgpu_exchange* x, const dfgpu_column* cols, int32_t n_cols, const int32_t* key_cols, int32_t n_keys, int64_t* recv_rows_out);
+int dfgpu_exchange_columns(dfgpu_exchange* x, dfgpu_column* out, int32_t n_cols);   /* device views of the received rows (valid until the next run) */
+void dfgpu_exchange_destroy(dfgpu_exchange* x);
+
 #ifdef __cplusplus
 }
 #endif

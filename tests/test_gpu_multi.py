@@ -27,3 +27,11 @@ def test_two_rank_paths_match_the_oracle(script, args, marker):
         pytest.skip("needs >= 2 GPUs on the box")
     r = _torchrun(script, 2, *args)
     assert r.returncode == 0 and marker in r.stdout and "=False" not in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+def test_library_communicator_and_exchange_without_nccl():
+    """dfgpu_comm / dfgpu_exchange: rendezvous over POSIX shared memory, rows over CUDA IPC peer stores — no torch.distributed at all"""
+    if _gpus() < 2:
+        pytest.skip("needs >= 2 GPUs on the box")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "verify_comm_exchange.py"), "2"], cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "VERIFY_COMM_EXCHANGE OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
