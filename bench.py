@@ -212,6 +212,44 @@ def gen_sum(kind, seed, a, b, n, chunk=1 << 24):
     return tot
 
 
+def boundary_costs(ctx, D):
+    """what the reference-facing boundary costs when the caller does NOT hand over pinned, large batches: FilterExec (x > c, 20 % selected) fed
+    (a) one 64M-row batch from pinned / pageable / page-locked-in-place (dfgpu_host_register) host memory, (b) the same rows as 8192-row batches"""
+    import ctypes as C
+    n = 1 << 26
+    nodes = [(D.EXPR_COLUMN, 0, 0, 0, 0, 0.0), (D.EXPR_LITERAL, 0, D.INT64, 0, int((1 << 32) * 0.8), 0.0), (D.EXPR_BINARY, D.OP_GT, 0, 0, 0, 0.0)]
+    dx = ctx.generate_i64(D.GEN_UNIFORM, 1, 0, 1 << 32, 0, n)
+    pinned = ctx.pinned_empty(n, np.int64)
+    ctx.check(ctx.lib.dfgpu_memcpy_d2h(ctx.h, pinned.ctypes.data_as(C.c_void_p), C.c_void_p(dx.ptr), n * 8)); ctx.sync()
+    pageable = np.array(pinned, copy=True)
+    registered = np.array(pinned, copy=True)
+    ctx.check(ctx.lib.dfgpu_host_register(ctx.h, registered.ctypes.data_as(C.c_void_p), registered.nbytes))
+
+    def run(host, batch_rows):
+        f = D.FilterHandle(ctx, [D.INT64], nodes, batch_size=8192)
+        kept = 0
+        for s in range(0, n, batch_rows):
+            f.push_host([D.HostColumn(host[s:s + batch_rows])])
+            for o in f.drain(host=True):
+                kept += o.num_rows; o.release()
+        f.finish()
+        for o in f.drain(host=True):
+            kept += o.num_rows; o.release()
+        f.close()
+        return kept
+    out = {}
+    for name, host, br, rows in (("pinned_one_batch", pinned, n, n), ("pageable_one_batch", pageable, n, n), ("registered_in_place_one_batch", registered, n, n),
+                                 ("pinned_8192_row_batches", pinned, 8192, 1 << 22)):
+        sub = host[:rows]
+        run(sub, br)
+        t0 = time.perf_counter(); kept = run(sub, br); dt = time.perf_counter() - t0
+        out[name] = {"rows_per_s": rows / dt, "h2d_gbs": rows * 8 / dt / 1e9, "rows": rows, "kept": int(kept)}
+    ctx.check(ctx.lib.dfgpu_host_unregister(ctx.h, registered.ctypes.data_as(C.c_void_p)))
+    dx.free()
+    out["note"] = "FilterExec x:int64 > c through dfgpu_filter_push_host + next(host=1), wall clock; 8192-row batches are launch / synchronisation bound (INTEGRATION.md §4: coalesce batches in front of a GPU operator)"
+    return out
+
+
 def secondary_configs(ctx, D, peak):
     out = {}
     col = lambda buf, n: D.DeviceColumn(ctx, D.INT64, n, buf)
@@ -519,6 +557,10 @@ def main():
             b.release()
         last.clear()
         del cu, orr, li          # 20.6 GB of tables: make room for the 16 GB group-by input
+        try:
+            line["e2e"]["boundary_costs"] = boundary_costs(ctx, D)
+        except Exception as exc:
+            line["e2e"]["boundary_costs"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         try:
             line["roofline"]["secondary"] = secondary_configs(ctx, D, peak)
         except AssertionError:

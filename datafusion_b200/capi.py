@@ -101,7 +101,7 @@ ArrowArray._fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offse
 # every symbol include/dfgpu.h declares (tests check the library exports all of them)
 EXPORTS = [
     "dfgpu_ctx_create", "dfgpu_ctx_destroy", "dfgpu_last_error", "dfgpu_version", "dfgpu_device_count", "dfgpu_sync",
-    "dfgpu_ctx_stream", "dfgpu_poll_ready", "dfgpu_malloc", "dfgpu_free", "dfgpu_host_alloc", "dfgpu_host_free", "dfgpu_memcpy_h2d",
+    "dfgpu_ctx_stream", "dfgpu_poll_ready", "dfgpu_malloc", "dfgpu_free", "dfgpu_host_alloc", "dfgpu_host_free", "dfgpu_host_register", "dfgpu_host_unregister", "dfgpu_memcpy_h2d",
     "dfgpu_memcpy_d2h", "dfgpu_memset", "dfgpu_flush_l2", "dfgpu_event_create", "dfgpu_event_record",
     "dfgpu_event_elapsed_ms", "dfgpu_event_destroy", "dfgpu_launch_count", "dfgpu_generate_i64",
     "dfgpu_set_kernel_timing", "dfgpu_kernel_time", "dfgpu_kernel_time_reset",
@@ -160,6 +160,8 @@ def load_library() -> C.CDLL:
     sig("dfgpu_free", C.c_int, [vp, vp])
     sig("dfgpu_host_alloc", C.c_int, [vp, C.c_size_t, P(vp)])
     sig("dfgpu_host_free", C.c_int, [vp, vp])
+    sig("dfgpu_host_register", C.c_int, [vp, vp, C.c_size_t])
+    sig("dfgpu_host_unregister", C.c_int, [vp, vp])
     sig("dfgpu_memcpy_h2d", C.c_int, [vp, vp, vp, C.c_size_t])
     sig("dfgpu_memcpy_d2h", C.c_int, [vp, vp, vp, C.c_size_t])
     sig("dfgpu_memset", C.c_int, [vp, vp, C.c_int, C.c_size_t])

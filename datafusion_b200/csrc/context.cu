@@ -180,6 +180,20 @@ int dfgpu_host_free(dfgpu_ctx* ctx, void* p) {
   if (p) DF_CUDA(cudaFreeHost(p));
   DF_API_END
 }
+// Page-lock caller-owned host memory in place (an Arrow buffer the Rust side already holds): later `*_push_host` / `*_push_arrow`
+// calls over it copy at the pinned PCIe rate instead of through the driver's pageable staging path.
+int dfgpu_host_register(dfgpu_ctx* ctx, void* p, size_t bytes) {
+  DF_API_BEGIN(ctx)
+  DF_CHECK(p && bytes, DFGPU_ERR_INVALID, "null argument");
+  set_device(ctx);
+  DF_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+  DF_API_END
+}
+int dfgpu_host_unregister(dfgpu_ctx* ctx, void* p) {
+  DF_API_BEGIN(ctx)
+  if (p) DF_CUDA(cudaHostUnregister(p));
+  DF_API_END
+}
 int dfgpu_memcpy_h2d(dfgpu_ctx* ctx, void* dst, const void* src, size_t bytes) {
   DF_API_BEGIN(ctx)
   set_device(ctx);

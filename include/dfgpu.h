@@ -134,6 +134,10 @@ int dfgpu_malloc(dfgpu_ctx* ctx, size_t bytes, void** out);     /* stream-ordere
 int dfgpu_free(dfgpu_ctx* ctx, void* p);
 int dfgpu_host_alloc(dfgpu_ctx* ctx, size_t bytes, void** out); /* pinned host memory */
 int dfgpu_host_free(dfgpu_ctx* ctx, void* p);
+/* page-lock / release caller-owned host memory in place (e.g. the Arrow buffers of a batch that will be pushed repeatedly or is large):
+ * H2D copies from pageable memory run at roughly a third of the pinned PCIe rate (bench.py `boundary_costs`) */
+int dfgpu_host_register(dfgpu_ctx* ctx, void* p, size_t bytes);
+int dfgpu_host_unregister(dfgpu_ctx* ctx, void* p);
 int dfgpu_memcpy_h2d(dfgpu_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on ctx stream */
 int dfgpu_memcpy_d2h(dfgpu_ctx* ctx, void* dst, const void* src, size_t bytes);
 int dfgpu_memset(dfgpu_ctx* ctx, void* dst, int value, size_t bytes);
