@@ -1299,9 +1299,8 @@ static void finish_build(dfgpu_hashjoin* j) {
       const uint64_t cap = j->use_array_map ? j->table.asize : ((std::max<uint64_t>(1024, (uint64_t)n * cap_pct / 100) + 3) & ~3ull);
       j->inline_slots.alloc(ctx, (size_t)cap * 8 * W);
       j->inline_slots.fill(0xFF);
-      static const int bucket_env = getenv("DFGPU_JOIN_BUCKET") ? atoi(getenv("DFGPU_JOIN_BUCKET")) : 0;
       j->iref.slots = j->inline_slots.ptr; j->iref.cap = cap; j->iref.dense = j->use_array_map ? 1 : 0; j->iref.amin = j->table.amin;
-      j->iref.bucket = (bucket_env && !j->use_array_map) ? 1 : 0;
+      j->iref.bucket = 0;   // bucket-aligned start slots were a round-1 experiment that only the v0 probe kernel honoured: retired
       DF_CUDA(cudaMemsetAsync(j->counters.ptr, 0, 64, ctx->stream));
       {
         KernelTimer kt(ctx, "join_build");

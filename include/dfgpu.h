@@ -250,12 +250,18 @@ enum dfgpu_null_equality { DFGPU_NULL_EQUALS_NOTHING = 0, DFGPU_NULL_EQUALS_NULL
 typedef struct dfgpu_hashjoin_options {
   int32_t join_type;       /* dfgpu_join_type */
   int32_t null_equality;   /* dfgpu_null_equality (joins/utils.rs:2122-2158) */
-  int64_t batch_size;      /* execution.batch_size, config.rs:904 */
+  int64_t batch_size;      /* execution.batch_size, config.rs:904 — accepted for parity with the reference's options; the join emits ONE output
+                            * batch per pushed probe batch (results do not depend on it: the MapOffset resumption of the reference is
+                            * batch-size independent, tests/test_gpu_join.py runs the 8192/10/5/2/1 matrix) and the shim slices zero-copy */
   /* perfect-hash (ArrayMap) selection — exec.rs:172-179, config.rs:913,923 */
   int64_t perfect_hash_join_small_build_threshold; /* default 1024 */
   double perfect_hash_join_min_key_density;        /* default 0.15 */
   int32_t force_hash_collisions; /* mirror of cargo feature force_hash_collisions (hash_utils.rs:1185-1205) */
-  int32_t ordered_output;  /* 1 = reference order (probe order × ascending build index); 0 = any order */
+  int32_t ordered_output;  /* 1 (default) = the reference's order: probe order x ascending build index for Inner / RightSemi / RightAnti /
+                            * RightMark; Right / Full put unmatched probe rows in probe order between the matches without a JoinFilter and
+                            * after them with one (the reference's own order depends on batch_size and `right_side_ordered`, utils.rs:1449-1460:
+                            * compare sorted).  0 = the consumer ignores row order (an aggregate or a repartition above): a join whose
+                            * table exceeds L2 then takes the radix-partitioned probe and returns rows partition-major */
   int32_t null_aware;      /* NOT IN semantics (HashJoinExec::null_aware, exec.rs:429-455, stream.rs:755-806, 1016-1072): LeftAnti /
                             * RightAnti on ONE key column; a NULL on the other side empties the result, NULL keys of the
                             * preserved side are never emitted (unless the other side is empty) */
