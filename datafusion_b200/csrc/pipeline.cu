@@ -46,6 +46,7 @@ struct LookupDev {
   int mode, stride /* 8-byte words per record */, has_payload, pad;
   unsigned long long* recs; uint64_t cap;
   unsigned long long* bloom; uint64_t bloom_blocks;
+  uint32_t* coarse; uint64_t coarse_words;   // optional first level (4 bits per key, L2-resident) in front of a filter that exceeds L2
   uint32_t* bits; uint64_t kmin, ksize;
 };
 struct ColRef { const void* ptr; const uint8_t* valid; int64_t voff; int width, sgn, vec /* base pointer 16-byte aligned: 128-bit loads allowed */, pad; };
@@ -112,6 +113,23 @@ __device__ __forceinline__ void bloom_set(unsigned long long* bloom, uint64_t bl
   const BloomPos p = bloom_pos(key, blocks);
   atomicOr(&bloom[p.block], bloom_mask(p.t));
 }
+// Coarse first level for filters that do not fit L2 (a join's filter shared by 4-8 GPUs is hundreds of MB): 4 bits per key, two probe
+// bits in one 32-bit word.  It stays L2-resident and rejects ~85 % of the keys without a partner, so only ~1 probe in 4 pays the DRAM
+// access of the exact (16 bits per key) level behind it.
+struct CoarsePos { uint32_t word, mask; };
+__device__ __forceinline__ CoarsePos coarse_pos(uint64_t key, uint64_t words) {
+  uint32_t h = ((uint32_t)key * 0x27D4EB2Fu) ^ ((uint32_t)(key >> 32) * 0x165667B1u);
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13;
+  CoarsePos p;
+  p.word = __umulhi(h, (uint32_t)words);
+  const uint32_t t = h * 0xC2B2AE35u;
+  p.mask = (1u << (t >> 27)) | (1u << ((t >> 22) & 31));
+  return p;
+}
+__device__ __forceinline__ void filter_set(const LookupDev& t, uint64_t key) {
+  bloom_set(t.bloom, t.bloom_blocks, key);
+  if (t.coarse) { const CoarsePos c = coarse_pos(key, t.coarse_words); atomicOr(&t.coarse[c.word], c.mask); }
+}
 __device__ __forceinline__ bool bloom_test(unsigned long long w, uint32_t t) {
   const uint32_t m0 = (1u << (t & 31)) | (1u << ((t >> 5) & 31)), m1 = (1u << ((t >> 10) & 31)) | (1u << ((t >> 15) & 31));
   return ((uint32_t)w & m0) == m0 && ((uint32_t)(w >> 32) & m1) == m1;
@@ -128,7 +146,7 @@ __device__ __forceinline__ int lk_insert(const LookupDev& t, uint64_t key, uint6
   if (key == kEmptyKey) return 2;
   const uint64_t h = lk_hash(key);
   if (t.cap == 0) {   // filter-only lookup: membership bits, no table
-    bloom_set(t.bloom, t.bloom_blocks, key);
+    filter_set(t, key);
     return 0;
   }
   uint64_t s = __umul64hi(h, t.cap);
@@ -142,7 +160,7 @@ __device__ __forceinline__ int lk_insert(const LookupDev& t, uint64_t key, uint6
     if (prev == key) { rc = 1; break; }
     if (++s == t.cap) s = 0;
   }
-  if (rc == 0 && t.bloom) bloom_set(t.bloom, t.bloom_blocks, key);
+  if (rc == 0 && t.bloom) filter_set(t, key);
   return rc;
 }
 
@@ -361,6 +379,19 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
         } else {
           if (st.kind != DFGPU_STAGE_ANTI) {
             mask &= kvalid;                      // NULL keys never match
+            if (st.lk.coarse) {   // first level: L2-resident, removes most rows before the exact level's DRAM access
+              uint32_t cw[kWarpRows], cm[kWarpRows];
+#pragma unroll
+              for (int j = 0; j < kWarpRows; ++j) {
+                const CoarsePos cp = coarse_pos(key[j], st.lk.coarse_words);
+                cm[j] = cp.mask;
+                cw[j] = ((mask >> j) & 1u) ? __ldg(&st.lk.coarse[cp.word]) : 0u;
+              }
+              uint32_t cpass = 0;
+#pragma unroll
+              for (int j = 0; j < kWarpRows; ++j) cpass |= (uint32_t)((cw[j] & cm[j]) == cm[j]) << j;
+              mask &= cpass;
+            }
             if (st.lk.bloom) {
               unsigned long long bw[kWarpRows];
               uint32_t bt[kWarpRows];
@@ -635,7 +666,8 @@ __global__ void __launch_bounds__(kPipeThreads) pipe_output_kernel(const PipePar
         } else if (key != kEmptyKey) {
           const uint64_t h = lk_hash(key);
           bool maybe = true;
-          if (st.lk.bloom) { const BloomPos bp = bloom_pos(key, st.lk.bloom_blocks); maybe = bloom_test(st.lk.bloom[bp.block], bp.t); }
+          if (st.lk.coarse) { const CoarsePos cp = coarse_pos(key, st.lk.coarse_words); maybe = (st.lk.coarse[cp.word] & cp.mask) == cp.mask; }
+          if (maybe && st.lk.bloom) { const BloomPos bp = bloom_pos(key, st.lk.bloom_blocks); maybe = bloom_test(st.lk.bloom[bp.block], bp.t); }
           if (maybe) {
             uint64_t slot = __umul64hi(h, st.lk.cap);
             while (true) {
@@ -711,7 +743,7 @@ __global__ void __launch_bounds__(256) lookup_rehash_kernel(LookupDev old_t, Loo
       if (atomicCAS(q, (unsigned long long)kEmptyKey, key) == kEmptyKey) { for (int w = 1; w < new_t.stride; ++w) q[w] = r[w]; break; }
       if (++d == new_t.cap) d = 0;
     }
-    if (new_t.bloom) bloom_set(new_t.bloom, new_t.bloom_blocks, key);
+    if (new_t.bloom) filter_set(new_t, key);
   }
 }
 // second half of a build whose size was unknown: the packed {key, payload} records of the survivors go into the (now sized) table
@@ -854,7 +886,7 @@ struct dfgpu_lookup {
   int mode = LK_HASH, stride = 1;
   bool has_payload = false;
   DevBuf recs, bloom, bits;
-  uint64_t cap = 0, bloom_blocks = 0, kmin = 0, ksize = 0;
+  uint64_t cap = 0, bloom_blocks = 0, coarse_words = 0, kmin = 0, ksize = 0;   // the coarse level lives behind the exact blocks in `bloom`
   int64_t rows = 0, rehashes = 0;
   bool acc_claimed = false, filter_only = false;
 };
@@ -892,6 +924,7 @@ static LookupDev lookup_dev(const dfgpu_lookup* l) {
   d.mode = l->mode; d.stride = l->stride; d.has_payload = l->has_payload ? 1 : 0;
   d.recs = l->recs.as<unsigned long long>(); d.cap = l->cap;
   d.bloom = l->bloom.ptr ? l->bloom.as<unsigned long long>() : nullptr; d.bloom_blocks = l->bloom_blocks;
+  d.coarse = (l->bloom.ptr && l->coarse_words) ? (uint32_t*)(l->bloom.as<unsigned long long>() + l->bloom_blocks) : nullptr; d.coarse_words = l->coarse_words;
   d.bits = l->bits.ptr ? l->bits.as<uint32_t>() : nullptr; d.kmin = l->kmin; d.ksize = l->ksize;
   return d;
 }
@@ -1379,7 +1412,10 @@ int dfgpu_lookup_create(dfgpu_ctx* ctx, int32_t key_type, const int32_t* payload
     l->filter_only = true;
     l->bloom_blocks = std::max<uint64_t>(1024, (uint64_t)l->opt.expected_rows / 4);   // 16 bits per key
     DF_CHECK(l->bloom_blocks < (1ull << 32), DFGPU_ERR_UNSUPPORTED, "lookup: filter too large");
-    l->bloom.alloc(ctx, (size_t)l->bloom_blocks * 8);
+    // a filter larger than L2 gets the coarse first level (4 bits per key) in the same allocation: one buffer to share and to all-reduce
+    static const int coarse_mb = getenv("DFGPU_FILTER_COARSE_MB") ? atoi(getenv("DFGPU_FILTER_COARSE_MB")) : 48;
+    if (coarse_mb >= 0 && (size_t)l->bloom_blocks * 8 > ((size_t)coarse_mb << 20)) l->coarse_words = (std::max<uint64_t>(4096, (uint64_t)l->opt.expected_rows / 8) + 1) & ~1ull;
+    l->bloom.alloc(ctx, (size_t)l->bloom_blocks * 8 + (size_t)l->coarse_words * 4);
     l->bloom.zero();
   }
   if (l->mode == LK_HASH && !l->filter_only && l->opt.expected_rows > 0) lookup_reserve(l.get(), l->opt.expected_rows);
@@ -1415,7 +1451,7 @@ int dfgpu_lookup_clear(dfgpu_lookup* l) {
 int dfgpu_lookup_filter_buffer(dfgpu_lookup* l, void** words_dev, uint64_t* n_bytes) {
   DF_API_BEGIN(l ? l->ctx : nullptr)
   DF_CHECK(l && words_dev && n_bytes, DFGPU_ERR_INVALID, "null argument");
-  *words_dev = l->bloom.ptr; *n_bytes = (uint64_t)l->bloom_blocks * 8;
+  *words_dev = l->bloom.ptr; *n_bytes = (uint64_t)l->bloom_blocks * 8 + (uint64_t)l->coarse_words * 4;
   DF_API_END
 }
 int dfgpu_lookup_filter_allreduce_peer(dfgpu_lookup* l, void* const* peer_words, int32_t rank, int32_t n_ranks) {
@@ -1429,9 +1465,10 @@ int dfgpu_lookup_filter_allreduce_peer(dfgpu_lookup* l, void* const* peer_words,
   memset(&pw, 0, sizeof(pw));
   for (int q = 0; q < n_ranks; ++q) { DF_CHECK(peer_words[q], DFGPU_ERR_INVALID, "filter all-reduce: null peer pointer"); pw.p[q] = (unsigned long long*)peer_words[q]; }
   DF_CHECK(pw.p[rank] == l->bloom.as<unsigned long long>(), DFGPU_ERR_INVALID, "filter all-reduce: peer_words[rank] must be this lookup's own filter");
-  const uint64_t slice = l->bloom_blocks / (uint64_t)n_ranks + 1;
+  const uint64_t words64 = l->bloom_blocks + l->coarse_words / 2;   // exact blocks + coarse level, merged as one array of 64-bit words
+  const uint64_t slice = words64 / (uint64_t)n_ranks + 1;
   KernelTimer kt(ctx, "filter_allreduce");
-  filter_allreduce_peer_kernel<<<grid_for((int64_t)slice, 256, kNumSMs * 4), 256, 0, ctx->stream>>>(pw, rank, n_ranks, l->bloom_blocks);
+  filter_allreduce_peer_kernel<<<grid_for((int64_t)slice, 256, kNumSMs * 4), 256, 0, ctx->stream>>>(pw, rank, n_ranks, words64);
   DF_LAUNCH_CHECK(ctx);
   DF_API_END
 }

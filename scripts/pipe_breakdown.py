@@ -19,6 +19,9 @@ q = D.Pipeline(ctx, orr.types, B(D.OP_LT, C(2), L(Q.CUT, D.INT32)), [(D.STAGE_SE
 qk = q.drain(host=False); q.close()
 F = D.Lookup(ctx, D.INT64, [], expected_rows=nq, filter_only=True)
 p = D.Pipeline(ctx, [D.INT64]); p.sink_build(F, 0, []); p.push_device([qk[0].column(0)]); p.finish(); p.close()
+F8 = D.Lookup(ctx, D.INT64, [], expected_rows=8 * nq, filter_only=True)      # the geometry of an 8-GPU run's merged filter (8x the keys' bits; only this rank's keys set)
+p = D.Pipeline(ctx, [D.INT64]); p.sink_build(F8, 0, []); p.push_device([qk[0].column(0)]); p.finish(); p.close()
+print("filter bytes: 1-GPU geometry", F.filter_buffer()[1], " 8-GPU geometry", F8.filter_buffer()[1], flush=True)
 l2n = D.Lookup(ctx, D.INT64, [D.INT32, D.INT32], n_acc_words=2, membership_filter=0)        # the same table without a Bloom filter
 p = D.Pipeline(ctx, orr.types, B(D.OP_LT, C(2), L(Q.CUT, D.INT32)), [(D.STAGE_SEMI, 1, l1)]); p.sink_build(l2n, 0, [2, 3]); p.push_device(orr.cols); p.finish(); p.close()
 
@@ -27,6 +30,7 @@ variants = {
     "A0 predicate only, nothing survives (streams l_shipdate)": lambda: (D.Pipeline(ctx, li.types, B(D.OP_GT, C(3), L(2**30, D.INT32)), name="v"), lambda p: p.sink_output([0], ordered=False)),
     "A1 predicate, 54% survive -> output l_orderkey": lambda: (D.Pipeline(ctx, li.types, B(D.OP_GT, C(3), L(Q.CUT, D.INT32)), name="v"), lambda p: p.sink_output([0], ordered=False)),
     "A2 predicate + membership filter (MAYBE) -> output l_orderkey": lambda: (D.Pipeline(ctx, li.types, B(D.OP_GT, C(3), L(Q.CUT, D.INT32)), [(D.STAGE_MAYBE, 0, F)], name="v"), lambda p: p.sink_output([0], ordered=False)),
+    "A2x8 predicate + membership filter of 8-GPU geometry -> output l_orderkey": lambda: (D.Pipeline(ctx, li.types, B(D.OP_GT, C(3), L(Q.CUT, D.INT32)), [(D.STAGE_MAYBE, 0, F8)], name="v"), lambda p: p.sink_output([0], ordered=False)),
     "A3 predicate + membership filter -> output key, price, discount": lambda: (D.Pipeline(ctx, li.types, B(D.OP_GT, C(3), L(Q.CUT, D.INT32)), [(D.STAGE_MAYBE, 0, F)], name="v"), lambda p: p.sink_output([0, 1, 2], ordered=False)),
     "B1 predicate + Bloom + probe (SEMI) -> output l_orderkey": lambda: (D.Pipeline(ctx, li.types, B(D.OP_GT, C(3), L(Q.CUT, D.INT32)), [(D.STAGE_SEMI, 0, l2)], name="v"), lambda p: p.sink_output([0], ordered=False)),
     "B2 full: predicate + Bloom + probe + SUM(price * (100 - disc))": lambda: (D.Pipeline(ctx, li.types, B(D.OP_GT, C(3), L(Q.CUT, D.INT32)), [(D.STAGE_INNER, 0, l2)], name="v"), lambda p: p.sink_aggregate([0, 4, 5], [(D.AGG_SUM, rev)])),
