@@ -310,6 +310,97 @@ def secondary_configs(ctx, D, peak):
     out["C2_join_100Mx10M_sparse_unique_radix_partitioned"] = {"ms_per_step": ms_r, "rows_per_s": (nb + npr) / ms_r * 1e3, "achieved_gbs": algo / ms_r / 1e6, "frac": algo / ms_r / 1e6 / peak,
                                                                "partition_ms": rp_ms / max(rp_n, 1), "probe_kernel_ms": pr_ms / max(pr_n, 1), "fingerprint": fp_r,
                                                                "note": "ordered_output = 0: probe side radix-partitioned on the top hash bits (TMA bulk loads / stores), per-partition probe with the sub-table L2-resident"}
+    # ---- C2(ii) with a 10 % hit rate: probe keys drawn from a key set 10x the build side (ordered probe; the misses cost a lookup, no output) ----
+    pk10 = ctx.generate_i64(D.GEN_SPARSE_OF, 42, 43, 10 * nb, 0, npr)
+    probe10 = [col(pk10, npr), col(pp, npr)]
+
+    def join10(keep=False):
+        j = D.HashJoinHandle(ctx, [D.INT64, D.INT64], [D.INT64, D.INT64], [0], [0], [0, 0, 1], [0, 1, 1])
+        j.push_build_device(build_cols); j.finish_build()
+        j.push_probe_device(probe10); j.finish_probe()
+        rows = j.metric("output_rows")
+        outs = j.drain(host=False)
+        fp = None
+        if keep:
+            s = [0, 0, 0]
+            for b in outs:
+                for c in range(3):
+                    s[c] = (s[c] + D.column_sum_device(ctx, b.column(c))) & M64
+            fp = [rows, (s[0] + 3 * s[1] + 5 * s[2]) & M64]
+        for b in outs:
+            b.release()
+        j.close()
+        return rows, fp
+    join10()
+    ctx.record(e0)
+    for _ in range(3):
+        join10()
+    ctx.record(e1)
+    ms10 = ctx.elapsed_ms(e0, e1) / 3
+    rows10, fp10 = join10(keep=True)
+    with np.errstate(over="ignore"):   # closed form: row i hits iff j_i = splitmix(43, i) % (10 nb) < nb; then k = splitmix(42, j_i), pb = splitmix(7, j_i)
+        er, es = 0, 0
+        for s0 in range(0, npr, 1 << 24):
+            i = np.arange(s0, min(npr, s0 + (1 << 24)), dtype=np.uint64)
+            jx = splitmix64_np(43, i) % np.uint64(10 * nb)
+            hit = jx < np.uint64(nb)
+            er += int(hit.sum())
+            es = (es + int(splitmix64_np(42, jx[hit]).sum(dtype=np.uint64)) + 3 * int(splitmix64_np(7, jx[hit]).sum(dtype=np.uint64)) + 5 * int(splitmix64_np(8, i[hit]).sum(dtype=np.uint64))) & M64
+    assert fp10 == [er, es], f"C2 10%-hit fingerprint {fp10} != closed form {[er, es]}"
+    algo10 = 16.0 * nb + 16.0 * npr + 24.0 * er
+    out["C2_join_100Mx10M_sparse_unique_10pct_hit"] = {"ms_per_step": ms10, "rows_per_s": (nb + npr) / ms10 * 1e3, "output_rows": int(rows10), "achieved_gbs": algo10 / ms10 / 1e6,
+                                                       "frac": algo10 / ms10 / 1e6 / peak, "fingerprint": fp10, "verified": "rows + checksum == closed form over the generators"}
+    pk10.free()
+    # ---- C2(iii): duplicated build keys (the chained table: count -> scan -> emit -> take), ~4 build rows per key, every probe row hits ----
+    nk = nb // 4
+    bkd = ctx.generate_i64(D.GEN_SPARSE_OF, 42, 99, nk, 0, nb)          # build key of row b = splitmix(42, splitmix(99, b) % nk)
+    npd = npr // 4                                                       # 25M probe rows x ~5 matches = ~125M output rows
+    pkd = ctx.generate_i64(D.GEN_SPARSE_OF, 42, 43, nk, 0, npd)
+    build_d, probe_d = [col(bkd, nb), col(bp, nb)], [col(pkd, npd), col(pp, npd)]
+
+    def joind(keep=False):
+        j = D.HashJoinHandle(ctx, [D.INT64, D.INT64], [D.INT64, D.INT64], [0], [0], [0, 0, 1], [0, 1, 1])
+        j.push_build_device(build_d); j.finish_build()
+        j.push_probe_device(probe_d); j.finish_probe()
+        rows = j.metric("output_rows")
+        outs = j.drain(host=False)
+        fp = None
+        if keep:
+            s = [0, 0, 0]
+            for b in outs:
+                for c in range(3):
+                    s[c] = (s[c] + D.column_sum_device(ctx, b.column(c))) & M64
+            fp = [rows, (s[0] + 3 * s[1] + 5 * s[2]) & M64]
+        for b in outs:
+            b.release()
+        j.close()
+        return rows, fp
+    joind()
+    ctx.record(e0)
+    for _ in range(3):
+        joind()
+    ctx.record(e1)
+    msd = ctx.elapsed_ms(e0, e1) / 3
+    rowsd, fpd = joind(keep=True)
+    with np.errstate(over="ignore"):   # closed form: multiplicity and payload sum per key slot, then one pass over the probe rows
+        ib = np.arange(nb, dtype=np.uint64)
+        jb = (splitmix64_np(99, ib) % np.uint64(nk)).astype(np.int64)
+        mult = np.bincount(jb, minlength=nk).astype(np.uint64)
+        pbv = splitmix64_np(7, ib)
+        order = np.argsort(jb, kind="stable"); cs = np.concatenate([[np.uint64(0)], np.cumsum(pbv[order], dtype=np.uint64)])
+        starts = np.concatenate([[0], np.cumsum(mult.astype(np.int64))])
+        spb = cs[starts[1:]] - cs[starts[:-1]]                           # wrapping sum of pb over the build rows of each key slot
+        ip = np.arange(npd, dtype=np.uint64)
+        jp = (splitmix64_np(43, ip) % np.uint64(nk)).astype(np.int64)
+        m = mult[jp]
+        er = int(m.sum())
+        es = (int((splitmix64_np(42, jp.astype(np.uint64)) * m).sum(dtype=np.uint64)) + 3 * int(spb[jp].sum(dtype=np.uint64)) + 5 * int((splitmix64_np(8, ip) * m).sum(dtype=np.uint64))) & M64
+    assert fpd == [er, es], f"C2 duplicated-build fingerprint {fpd} != closed form {[er, es]}"
+    algod = 16.0 * nb + 16.0 * npd + 24.0 * er
+    out["C2_join_25Mx10M_duplicated_build_keys_chained"] = {"ms_per_step": msd, "rows_per_s": (nb + npd) / msd * 1e3, "output_rows": int(rowsd), "achieved_gbs": algod / msd / 1e6,
+                                                             "frac": algod / msd / 1e6 / peak, "fingerprint": fpd, "verified": "rows + checksum == closed form over the generators",
+                                                             "note": "2.5M distinct keys x ~4 build rows each (Poisson), 25M probe rows, every probe row matches its key's whole chain in ascending build row"}
+    bkd.free(); pkd.free()
     for b in (bk, bp, pk, pp):
         b.free()
     # ---- C3: group-by SUM / COUNT, 1B rows -> 1M groups ----
