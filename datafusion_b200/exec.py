@@ -425,8 +425,6 @@ class GpuAggregateExec(ExecutionPlan):
 
     def __init__(self, mode: str, group_by: Sequence[str], aggr_expr: Sequence[AggregateExpr], input: ExecutionPlan,
                  input_schema: Optional[pa.Schema] = None, capacity_hint: int = 0):
-        if not group_by:
-            raise NotImplementedError("This feature is not implemented: aggregation without GROUP BY stays on the CPU AggregateExec")
         self.mode, self.group_by, self.aggr_expr, self.input = mode, list(group_by), list(aggr_expr), input
         self.input_schema = input_schema or input.schema  # schema of the RAW input (needed in Final modes for value types)
         self.capacity_hint = capacity_hint
@@ -472,6 +470,209 @@ class GpuAggregateExec(ExecutionPlan):
             op.close()
 
     def metrics(self): return self._metrics
+
+
+# ---------------------------------------------------------------------------------------------
+# pipeline fusion — the executable twin of the second optimizer rule of INTEGRATION.md §2a
+# ---------------------------------------------------------------------------------------------
+class _Scan:
+    """the probe-side chain of one pipeline: source plan, predicate over the source schema, probe stages, names visible downstream"""
+
+    def __init__(self, source: ExecutionPlan, predicate: Optional[Expr] = None):
+        self.source, self.predicate = source, predicate
+        self.stages: List[Tuple[int, str, "GpuPipelineExec"]] = []     # (stage kind, probe key column, build pipeline)
+        self.visible: List[str] = [f.name for f in source.schema]       # column names the operators above may still reference
+
+    def virtual_schema(self) -> pa.Schema:
+        fields = list(self.source.schema)
+        for kind, _, build in self.stages:
+            if kind == D.STAGE_INNER:
+                fields += [build.scan_field(n) for n in build.payload]
+        return pa.schema(fields)
+
+
+def _as_scan(plan: ExecutionPlan) -> Optional[_Scan]:
+    """[ProjectionExec(columns only)]* over [FilterExec]? over [HashJoinExec(RightSemi / RightAnti / Inner, one key, fusable build)]* over a source"""
+    if isinstance(plan, GpuProjectionExec):
+        if not all(isinstance(e, Column) and e.name == name for e, name in plan.exprs):
+            return None
+        sc = _as_scan(plan.input)
+        if sc is not None:
+            sc.visible = [name for _, name in plan.exprs]
+        return sc
+    if isinstance(plan, GpuFilterExec):
+        if plan.fetch is not None:
+            return None
+        inner = plan.input
+        if isinstance(inner, (GpuFilterExec, GpuHashJoinExec, GpuProjectionExec, GpuAggregateExec)):
+            return None                                   # predicates are fused over the source columns only
+        sc = _Scan(inner, plan.predicate)
+        if plan.projection is not None:
+            sc.visible = [inner.schema.field(i).name for i in plan.projection]
+        return sc
+    if isinstance(plan, GpuHashJoinExec):
+        if plan.join_type not in ("RightSemi", "RightAnti", "Inner") or len(plan.on) != 1 or plan.filter is not None or plan.null_aware or plan.null_equality != "NullEqualsNothing":
+            return None
+        sc = _as_scan(plan.right)
+        if sc is None or plan.on[0][1] not in [f.name for f in sc.source.schema]:
+            return None
+        kind = {"RightSemi": D.STAGE_SEMI, "RightAnti": D.STAGE_ANTI, "Inner": D.STAGE_INNER}[plan.join_type]
+        payload = [f.name for f in plan.left.schema if f.name != plan.on[0][0]] if kind == D.STAGE_INNER else []
+        build = _as_build(plan.left, plan.on[0][0], payload)
+        if build is None:
+            return None
+        sc.stages.append((kind, plan.on[0][1], build))
+        names = [f.name for f in plan.schema]
+        sc.visible = names
+        return sc
+    if isinstance(plan, (GpuAggregateExec,)):
+        return None
+    return _Scan(plan)
+
+
+def _as_build(plan: ExecutionPlan, key: str, payload: List[str]) -> Optional["GpuPipelineExec"]:
+    sc = _as_scan(plan)
+    if sc is None or len(sc.stages) >= 3:
+        return None
+    vs = sc.virtual_schema()
+    if vs.get_field_index(key) < 0 or vs.get_field_index(key) >= len(sc.source.schema) or any(vs.get_field_index(n) < 0 for n in payload):
+        return None
+    bits = sum(D.WIDTH[type_id(vs.field(n).type)] * 8 for n in payload)
+    if bits > 64:
+        return None
+    return GpuPipelineExec(sc, sink="build", key=key, payload=payload)
+
+
+class GpuPipelineExec(ExecutionPlan):
+    """One fused pipeline (dfgpu_pipeline): source -> predicate -> probe stages -> {build | aggregate | output}.  Built by fuse_pipelines()."""
+
+    def __init__(self, scan: _Scan, sink: str, key: Optional[str] = None, payload: Sequence[str] = (), group_by: Sequence[str] = (),
+                 aggs: Sequence[Tuple[str, Optional[Expr], str]] = (), mode: str = "Single", out_schema: Optional[pa.Schema] = None):
+        self.scan, self.sink, self.key, self.payload, self.group_by, self.aggs, self.mode = scan, sink, key, list(payload), list(group_by), list(aggs), mode
+        self.schema = out_schema if out_schema is not None else pa.schema([])
+        self.n_acc_words = 0
+        self._metrics = {}
+
+    def children(self): return [self.scan.source] + [b for _, _, b in self.scan.stages]
+    def scan_field(self, name: str) -> pa.Field: return self.scan.virtual_schema().field(name)
+    def metrics(self): return self._metrics
+
+    # ---- build side: run the pipeline into a dfgpu_lookup ----
+    def build_lookup(self, ctx: TaskContext) -> D.Lookup:
+        vs = self.scan.virtual_schema()
+        batches = list(self.scan.source.execute(ctx))
+        key_range = None
+        ktype = vs.field(self.key).type
+        if not self.payload and self.n_acc_words == 0 and pa.types.is_integer(ktype) and batches:   # statistics: the bounds collect_left_input tracks
+            import pyarrow.compute as pc
+            mm = [pc.min_max(b.column(self.scan.source.schema.get_field_index(self.key))) for b in batches if b.num_rows]
+            lo = [m["min"].as_py() for m in mm if m["min"].is_valid]; hi = [m["max"].as_py() for m in mm if m["max"].is_valid]
+            if lo:
+                key_range = (min(lo), max(hi))
+        look = D.Lookup(ctx.gpu, type_id(ktype), [type_id(vs.field(n).type) for n in self.payload], key_range=key_range, n_acc_words=self.n_acc_words)
+        pipe, keep = self._make_pipeline(ctx)
+        try:
+            pipe.sink_build(look, vs.get_field_index(self.key), [vs.get_field_index(n) for n in self.payload])
+            for rb in batches:
+                pipe.push_arrow(rb)
+            pipe.finish()
+            self._metrics = {"input_rows": pipe.metric("input_rows"), "build_rows": pipe.metric("sink_rows"), "lookup_mode": look.metric("mode")}
+        finally:
+            pipe.close()
+            for l in keep:
+                l.close()
+        return look
+
+    def _make_pipeline(self, ctx: TaskContext):
+        ssch = self.scan.source.schema
+        nodes = None
+        if self.scan.predicate is not None:
+            nodes = []
+            self.scan.predicate.rpn(ssch, nodes)
+        stages, keep = [], []
+        for kind, pkey, build in self.scan.stages:
+            look = build.build_lookup(ctx)                      # the pipeline breaker: WaitBuildSide (hash_join/stream.rs:117-140)
+            keep.append(look)
+            stages.append((kind, ssch.get_field_index(pkey), look))
+        return D.Pipeline(ctx.gpu, [type_id(f.type) for f in ssch], nodes, stages), keep
+
+    def execute(self, ctx):
+        assert self.sink == "aggregate", "build pipelines are driven by their consumer"
+        vs = self.scan.virtual_schema()
+        pipe, keep = self._make_pipeline(ctx)
+        try:
+            aggs = []
+            for func, expr, _ in self.aggs:
+                if expr is None:
+                    aggs.append((_AGG_FUNCS[func], None))
+                else:
+                    nodes: list = []
+                    expr.rpn(vs, nodes)
+                    aggs.append((_AGG_FUNCS[func], nodes))
+            pipe.sink_aggregate([vs.get_field_index(g) for g in self.group_by], aggs, _AGG_MODES[self.mode], 0)
+            for rb in self.scan.source.execute(ctx):
+                pipe.push_arrow(rb)
+            pipe.finish()
+            bs = ctx.config.batch_size
+            for rb in _drain(pipe, self.schema):
+                for s in range(0, rb.num_rows, bs):
+                    yield rb.slice(s, bs)
+            self._metrics = {k: pipe.metric(k) for k in ("input_rows", "sink_rows", "num_groups")}
+        finally:
+            pipe.close()
+            for l in keep:
+                l.close()
+
+
+def fuse_pipelines(plan: ExecutionPlan) -> ExecutionPlan:
+    """PhysicalOptimizerRule twin: AggregateExec(Single / SinglePartitioned / Partial) over [ProjectionExec] over
+    HashJoinExec(Inner) whose GROUP BY is the probe key plus build-side columns becomes ONE GpuPipelineExec; its build side (filters, semi
+    joins, column projections) becomes build pipelines.  Anything else is returned unchanged (the unfused Gpu*Exec operators run)."""
+    if not isinstance(plan, GpuAggregateExec) or plan.mode not in ("Single", "SinglePartitioned", "Partial") or not plan.group_by:
+        return plan
+    below, proj = plan.input, None
+    if isinstance(below, GpuProjectionExec):
+        proj, below = below, below.input
+    if not isinstance(below, GpuHashJoinExec) or below.join_type != "Inner":
+        return plan
+    sc = _as_scan(below)
+    if sc is None or not sc.stages or sc.stages[-1][0] != D.STAGE_INNER:
+        return plan
+    kind, pkey, build = sc.stages[-1]
+    vs = sc.virtual_schema()
+    exprs = {name: e for e, name in proj.exprs} if proj is not None else {f.name: Column(f.name) for f in below.schema}
+    # group keys: the probe key (or the equal build key) and payload fields of the LAST inner stage
+    group = []
+    for g in plan.group_by:
+        e = exprs.get(g)
+        if not isinstance(e, Column):
+            return plan
+        n = pkey if e.name == build.key else e.name
+        if n != pkey and n not in build.payload:
+            return plan
+        group.append(n)
+    if pkey not in group:
+        return plan
+    aggs = []
+    for a in plan.aggr_expr:
+        if a.filter is not None:
+            return plan
+        e = None if a.arg is None else exprs.get(a.arg)
+        if a.arg is not None and e is None:
+            return plan
+        if a.func == "avg" and e is not None and e.data_type(vs) != pa.float64():
+            return plan
+        aggs.append((a.func, e, a.alias))
+    try:
+        for _, e, _ in aggs:
+            if e is not None:
+                e.rpn(vs, [])                              # every referenced name must exist in the virtual schema
+    except KeyError:
+        return plan
+    build.n_acc_words = 1 + sum(2 if f == "avg" else 1 for f, _, _ in aggs) + sum(1 for f, _, _ in aggs if f in ("sum", "min", "max"))
+    if build.n_acc_words > 12:
+        return plan
+    return GpuPipelineExec(sc, sink="aggregate", group_by=group, aggs=aggs, mode=plan.mode, out_schema=plan.schema)
 
 
 def collect(plan: ExecutionPlan, ctx: Optional[TaskContext] = None) -> List[pa.RecordBatch]:

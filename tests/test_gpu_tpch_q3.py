@@ -11,8 +11,8 @@ import numpy as np
 import pyarrow as pa
 import pytest
 
-from datafusion_b200.exec import (AggregateExpr, GpuAggregateExec, GpuFilterExec, GpuHashJoinExec, GpuProjectionExec, MemoryExec, SessionConfig,
-                                  TaskContext, col, collect, lit)
+from datafusion_b200.exec import (AggregateExpr, GpuAggregateExec, GpuFilterExec, GpuHashJoinExec, GpuPipelineExec, GpuProjectionExec, MemoryExec, SessionConfig,
+                                  TaskContext, col, collect, fuse_pipelines, lit)
 
 pytestmark = pytest.mark.gpu
 EPOCH = datetime.date(1970, 1, 1)
@@ -76,3 +76,38 @@ def test_q3_pipeline_matches_independent_evaluation(gpu_ctx, sf, batch_rows):
     exp = q3_expected(customer, orders, lineitem)
     assert len(exp) > 0 and got == exp
     assert inner.metrics()["array_map_created_count"] == 0 or sf < 0.01   # o_orderkey is sparse (8 of 32): hash path at scale
+
+
+def q3_plan(customer, orders, lineitem, batch_rows):
+    mem = lambda t: MemoryExec(t.to_batches(max_chunksize=batch_rows), t.schema)
+    c = GpuFilterExec(col("c_mktsegment") == lit(1, pa.int32()), mem(customer), projection=[0])
+    o = GpuFilterExec(col("o_orderdate") < lit(CUT, pa.date32()), mem(orders))
+    semi = GpuHashJoinExec(c, o, [("c_custkey", "o_custkey")], "RightSemi")
+    semi_p = GpuProjectionExec([(col("o_orderkey"), "o_orderkey"), (col("o_orderdate"), "o_orderdate"), (col("o_shippriority"), "o_shippriority")], semi)
+    l = GpuFilterExec(col("l_shipdate") > lit(CUT, pa.date32()), mem(lineitem), projection=[0, 1, 2])
+    inner = GpuHashJoinExec(semi_p, l, [("o_orderkey", "l_orderkey")], "Inner", projection=[1, 2, 3, 4, 5])
+    rev = GpuProjectionExec([(col("l_orderkey"), "l_orderkey"), (col("o_orderdate"), "o_orderdate"), (col("o_shippriority"), "o_shippriority"),
+                             (col("l_extendedprice") * (lit(100, pa.int64()) - col("l_discount")), "rev")], inner)
+    return rev, GpuAggregateExec("SinglePartitioned", ["l_orderkey", "o_orderdate", "o_shippriority"], [AggregateExpr("sum", "rev", "revenue")], rev)
+
+
+@pytest.mark.parametrize("sf,batch_rows", [(0.002, 1000), (0.05, 8192)])
+def test_fusion_rule_collapses_the_q3_plan_into_pipelines(gpu_ctx, sf, batch_rows):
+    """the executable twin of the fusion rule: the reference-shaped operator tree of Q3 becomes ONE GpuPipelineExec over two
+    build pipelines, fed and drained through the Arrow C Data Interface, and gives the unfused plan's rows"""
+    customer, orders, lineitem = gen_tables(sf)
+    ctx = TaskContext(SessionConfig(), gpu_ctx)
+    rev, agg = q3_plan(customer, orders, lineitem, batch_rows)
+    fused = fuse_pipelines(agg)
+    assert isinstance(fused, GpuPipelineExec) and fused.schema == agg.schema
+    builds = [b for _, _, b in fused.scan.stages]
+    assert len(builds) == 1 and builds[0].key == "o_orderkey" and builds[0].payload == ["o_orderdate", "o_shippriority"] and len(builds[0].scan.stages) == 1
+    out = pa.Table.from_batches(collect(fused, ctx))
+    got = sorted(zip(out["l_orderkey"].to_pylist(), np.asarray(out["o_orderdate"].cast(pa.int32())).tolist(), out["o_shippriority"].to_pylist(), out["revenue"].to_pylist()))
+    exp = q3_expected(customer, orders, lineitem)
+    assert len(exp) > 0 and got == exp
+    assert fused.metrics()["num_groups"] == len(exp) and builds[0].scan.stages[0][2].metrics()["lookup_mode"] == 1     # the customer key set became a bitmap
+    # shapes the rule must leave alone: a GROUP BY that the join key does not determine, a Final aggregate
+    other = GpuAggregateExec("Single", ["o_shippriority"], [AggregateExpr("sum", "rev", "revenue")], rev)
+    assert fuse_pipelines(other) is other
+    assert fuse_pipelines(rev) is rev
