@@ -39,8 +39,49 @@ NP_OF_TYPE = {
 }
 TYPE_OF_NP = {np.dtype(v): k for k, v in NP_OF_TYPE.items() if k not in (DATE32, DATE64, TIMESTAMP)}
 TYPE_OF_NP[np.dtype(np.bool_)] = BOOL
-WIDTH = {BOOL: 0, INT8: 1, UINT8: 1, INT16: 2, UINT16: 2, INT32: 4, UINT32: 4, FLOAT32: 4, DATE32: 4, INT64: 8,
-         UINT64: 8, FLOAT64: 8, DATE64: 8, TIMESTAMP: 8, DECIMAL128: 16}
+_WIDTH = {BOOL: 0, INT8: 1, UINT8: 1, INT16: 2, UINT16: 2, INT32: 4, UINT32: 4, FLOAT32: 4, DATE32: 4, INT64: 8,
+          UINT64: 8, FLOAT64: 8, DATE64: 8, TIMESTAMP: 8, DECIMAL128: 16}
+
+
+def decimal128(precision: int, scale: int) -> int:
+    """DFGPU_DECIMAL128_TYPE(p, s): the type code of Decimal128(precision, scale)"""
+    return DECIMAL128 | (int(precision) << 8) | ((int(scale) & 0xff) << 16)
+
+
+def type_base(t: int) -> int:
+    return t & 0xff
+
+
+def decimal_precision_scale(t: int):
+    sc = (t >> 16) & 0xff
+    return (t >> 8) & 0xff, sc - 256 if sc >= 128 else sc
+
+
+class _Width(dict):
+    def __missing__(self, t):          # Decimal128(p, s) codes carry p and s in the upper bytes
+        return _WIDTH[t & 0xff]
+
+
+WIDTH = _Width(_WIDTH)
+
+
+def decimal_to_words(values) -> np.ndarray:
+    """Python ints -> the Arrow Decimal128 buffer: [n, 2] uint64 (low word, high word), two's complement"""
+    out = np.empty((len(values), 2), np.uint64)
+    for i, v in enumerate(values):
+        u = int(v) % (1 << 128)
+        out[i, 0] = u & 0xFFFFFFFFFFFFFFFF
+        out[i, 1] = u >> 64
+    return out
+
+
+def words_to_decimal(words: np.ndarray) -> list:
+    """[n, 2] uint64 -> signed Python ints"""
+    out = []
+    for lo, hi in np.asarray(words, np.uint64).reshape(-1, 2).tolist():
+        u = (int(hi) << 64) | int(lo)
+        out.append(u - (1 << 128) if u >= (1 << 127) else u)
+    return out
 
 
 class DfgpuError(RuntimeError):
@@ -126,6 +167,8 @@ EXPORTS = [
     "dfgpu_pipeline_create", "dfgpu_pipeline_sink_build", "dfgpu_pipeline_sink_aggregate", "dfgpu_pipeline_sink_output",
     "dfgpu_pipeline_push_host", "dfgpu_pipeline_push_device", "dfgpu_pipeline_push_arrow", "dfgpu_pipeline_finish",
     "dfgpu_pipeline_next", "dfgpu_pipeline_metric", "dfgpu_pipeline_destroy",
+    "dfgpu_dictionary_create", "dfgpu_dictionary_unify", "dfgpu_dictionary_code", "dfgpu_dictionary_size", "dfgpu_dictionary_value",
+    "dfgpu_dictionary_remap", "dfgpu_dictionary_destroy",
 ]
 
 _lib = None
@@ -225,6 +268,13 @@ def load_library() -> C.CDLL:
     sig("dfgpu_exchange_run", C.c_int, [vp, P(Column), i32, P(i32), i32, P(i64)])
     sig("dfgpu_exchange_columns", C.c_int, [vp, P(Column), i32])
     sig("dfgpu_exchange_destroy", None, [vp])
+    sig("dfgpu_dictionary_create", C.c_int, [vp, P(vp)])
+    sig("dfgpu_dictionary_unify", C.c_int, [vp, vp, vp, vp, i64, vp])
+    sig("dfgpu_dictionary_code", i32, [vp, C.c_char_p, i64])
+    sig("dfgpu_dictionary_size", i64, [vp])
+    sig("dfgpu_dictionary_value", C.c_int, [vp, i32, P(vp), P(i64)])
+    sig("dfgpu_dictionary_remap", C.c_int, [vp, P(Column), C.c_int, vp, i64, P(vp)])
+    sig("dfgpu_dictionary_destroy", None, [vp])
     sig("dfgpu_lookup_default_options", None, [P(LookupOptions)])
     sig("dfgpu_lookup_create", C.c_int, [vp, i32, P(i32), i32, P(LookupOptions), P(vp)])
     sig("dfgpu_lookup_metric", i64, [vp, C.c_char_p])
@@ -420,6 +470,9 @@ class HostColumn:
         self.length = len(values)
         if self.type == BOOL:
             self._values = pack_bits(values)
+        elif type_base(self.type) == DECIMAL128:
+            # values: [n, 2] uint64 words (decimal_to_words) or Python ints
+            self._values = np.ascontiguousarray(values if values.dtype == np.uint64 and values.ndim == 2 else decimal_to_words(list(values)))
         else:
             self._values = np.ascontiguousarray(values.astype(NP_OF_TYPE[self.type], copy=False))
         self._validity = None if valid is None else pack_bits(valid)
@@ -491,7 +544,7 @@ class Batch:
             w = WIDTH[c.type]
             off = c.offset if (c.validity and not self.is_host) else 0
             raw = self._read((c.values or 0) + off * w, n * w)
-            if c.type == DECIMAL128:
+            if type_base(c.type) == DECIMAL128:
                 vals = raw.view(np.uint64).reshape(-1, 2)
             else:
                 vals = raw.view(NP_OF_TYPE[c.type]).copy()
@@ -590,6 +643,14 @@ def expr_nodes(nodes: Sequence[tuple]):
     """[(kind, a, type, is_null, lit_i64, lit_f64), ...] -> ExprNode array"""
     arr = (ExprNode * len(nodes))()
     for i, nd in enumerate(nodes):
+        if nd[0] == EXPR_LITERAL and type_base(nd[2]) == DECIMAL128:
+            # Decimal128 literal: lit_i64 = the value as a Python int; the low word goes to lit_i64, the high word into the bytes of lit_f64
+            u = int(nd[4]) % (1 << 128)
+            lo, hi = u & 0xFFFFFFFFFFFFFFFF, u >> 64
+            arr[i].kind, arr[i].a, arr[i].type, arr[i].is_null = nd[0], nd[1], nd[2], nd[3]
+            arr[i].lit_i64 = lo - (1 << 64) if lo >= (1 << 63) else lo
+            C.memmove(C.addressof(arr[i]) + ExprNode.lit_f64.offset, hi.to_bytes(8, "little"), 8)
+            continue
         arr[i].kind, arr[i].a, arr[i].type, arr[i].is_null, arr[i].lit_i64, arr[i].lit_f64 = nd
     return arr
 
@@ -793,6 +854,53 @@ def comm_unique_id() -> bytes:
     if load_library().dfgpu_comm_unique_id(buf) != OK:
         raise DfgpuError(-1, "cannot create a communicator id")
     return buf.raw
+
+
+class Dictionary:
+    """dfgpu_dictionary: one code space for the string keys of every batch (and of both join sides); the operators see INT32 codes"""
+
+    def __init__(self, ctx: Context):
+        self.ctx, self.h = ctx, C.c_void_p()
+        ctx.check(ctx.lib.dfgpu_dictionary_create(ctx.h, C.byref(self.h)))
+
+    def unify(self, offsets: np.ndarray, data: np.ndarray, valid: Optional[np.ndarray] = None) -> np.ndarray:
+        """one batch's dictionary values (Arrow Utf8 layout) -> remap table local code -> unified code (-1 for a NULL value)"""
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        data = np.ascontiguousarray(data, np.uint8)
+        n = len(offsets) - 1
+        vbits = None if valid is None else pack_bits(np.asarray(valid, bool))
+        remap = np.empty(max(n, 1), np.int32)
+        self.ctx.check(self.ctx.lib.dfgpu_dictionary_unify(self.h, offsets.ctypes.data, data.ctypes.data if len(data) else None,
+                                                           vbits.ctypes.data if vbits is not None else None, n, remap.ctypes.data))
+        return remap[:n]
+
+    def code(self, value: bytes) -> int:
+        return int(self.ctx.lib.dfgpu_dictionary_code(self.h, value, len(value)))
+
+    def size(self) -> int:
+        return int(self.ctx.lib.dfgpu_dictionary_size(self.h))
+
+    def value(self, code: int) -> bytes:
+        ptr, ln = C.c_void_p(), C.c_int64()
+        rc = self.ctx.lib.dfgpu_dictionary_value(self.h, int(code), C.byref(ptr), C.byref(ln))
+        if rc != OK:
+            raise DfgpuError(rc, "dictionary: no such code")
+        return C.string_at(ptr.value, ln.value) if ln.value else b""
+
+    def remap(self, codes, remap: np.ndarray, on_host: bool = False) -> "Batch":
+        """device INT32 column of unified codes for one batch's keys column"""
+        remap = np.ascontiguousarray(remap, np.int32)
+        col = codes.c() if not isinstance(codes, Column) else codes
+        out = C.c_void_p()
+        self.ctx.check(self.ctx.lib.dfgpu_dictionary_remap(self.h, C.byref(col), 1 if on_host else 0, remap.ctypes.data if len(remap) else None,
+                                                           len(remap), C.byref(out)))
+        self._keep = codes
+        return Batch(self.ctx, out.value)
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.dfgpu_dictionary_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 class Comm:

@@ -146,7 +146,15 @@ __device__ __forceinline__ void apply_agg(const AggDev& a, int64_t row, uint64_t
       atomicAdd(&a.acc0[slot], a.merge ? (unsigned long long)((const int64_t*)a.in0)[row] : 1ull);
       break;
     case DFGPU_AGG_SUM:
-      if (a.cls == 2) atomicAdd((double*)&a.acc0[slot], load_as_f64(a.in0, a.in0_type, row));
+      if (a.cls == 3) {
+        // Decimal128: i128 add_wrapping (sum.rs:316 on Decimal128Type) as two 64-bit atomics — the carry out of the low word is a
+        // function of this add alone (old + lo overflowed), so the high words sum to the right value in any interleaving
+        const unsigned long long* p = (const unsigned long long*)a.in0 + 2 * row;
+        const unsigned long long lo = p[0], hi = p[1];
+        const unsigned long long old = atomicAdd(&a.acc0[slot], lo);
+        const unsigned long long carry = (old + lo) < old ? 1ull : 0ull;
+        if (hi + carry) atomicAdd(&a.acc1[slot], hi + carry);
+      } else if (a.cls == 2) atomicAdd((double*)&a.acc0[slot], load_as_f64(a.in0, a.in0_type, row));
       else if (a.in0_type == DFGPU_UINT64) atomicAdd(&a.acc0[slot], (unsigned long long)((const uint64_t*)a.in0)[row]);
       else atomicAdd(&a.acc0[slot], (unsigned long long)load_as_i64(a.in0, a.in0_type, row));  // add_wrapping (sum.rs:316)
       if (a.seen) a.seen[slot] = 1;
@@ -434,7 +442,7 @@ __global__ void agg_init_seen_kernel(TableDev t, uint8_t* __restrict__ seen) {
 }
 
 // ---- emit kernels: one per output column, 32 consecutive outputs per warp ----
-enum EmitKind : int { EK_KEY = 0, EK_COPY64 = 1, EK_AVG = 2, EK_MINMAX = 3 };
+enum EmitKind : int { EK_KEY = 0, EK_COPY64 = 1, EK_AVG = 2, EK_MINMAX = 3, EK_DEC128 = 4 };
 struct EmitDesc {
   int kind;
   int out_type;        // output column type
@@ -490,6 +498,11 @@ __global__ void __launch_bounds__(256) agg_emit_kernel(EmitDesc d, const uint32_
           bits = d.acc0[s];
           if (d.seen) ok = d.seen[s] != 0;
           break;
+        case EK_DEC128:
+          if (d.seen) ok = d.seen[s] != 0;
+          ((unsigned long long*)out)[2 * i] = ok ? d.acc0[s] : 0ull;
+          ((unsigned long long*)out)[2 * i + 1] = ok ? d.acc1[s] : 0ull;
+          break;
         case EK_AVG: {
           unsigned long long c = d.acc1[s];
           if (c == 0) { ok = false; break; }
@@ -512,7 +525,7 @@ __global__ void __launch_bounds__(256) agg_emit_kernel(EmitDesc d, const uint32_
       }
       if (!ok) bits = 0;
       if (d.out_type == DFGPU_BOOL) bval = bits & 1;
-      else store_typed(out, d.out_type, i, bits);
+      else if (d.kind != EK_DEC128) store_typed(out, d.out_type, i, bits);
     }
     uint32_t vw = __ballot_sync(0xffffffffu, ok);
     uint32_t bw = __ballot_sync(0xffffffffu, bval);
@@ -544,7 +557,10 @@ __global__ void __launch_bounds__(256) agg_convert_state_kernel(AggSet aggs, Sta
         switch (a.func) {
           case DFGPU_AGG_COUNT: case DFGPU_AGG_COUNT_STAR: ((int64_t*)o.v0)[row] = ok ? 1 : 0; break;
           case DFGPU_AGG_SUM:
-            if (a.cls == 2) ((double*)o.v0)[row] = ok ? load_as_f64(a.in0, a.in0_type, row) : 0.0;
+            if (a.cls == 3) {
+              const unsigned long long* p = (const unsigned long long*)a.in0 + 2 * row;
+              ((unsigned long long*)o.v0)[2 * row] = ok ? p[0] : 0ull; ((unsigned long long*)o.v0)[2 * row + 1] = ok ? p[1] : 0ull;
+            } else if (a.cls == 2) ((double*)o.v0)[row] = ok ? load_as_f64(a.in0, a.in0_type, row) : 0.0;
             else ((uint64_t*)o.v0)[row] = !ok ? 0ull : (a.in0_type == DFGPU_UINT64 ? ((const uint64_t*)a.in0)[row] : (uint64_t)load_as_i64(a.in0, a.in0_type, row));
             break;
           case DFGPU_AGG_MIN: case DFGPU_AGG_MAX: {
@@ -661,7 +677,7 @@ static void alloc_table(dfgpu_agg* a, uint64_t cap, DevBuf* tags, std::vector<De
   for (size_t i = 0; i < a->aggs.size(); ++i) {
     (*acc0)[i].alloc(ctx, (size_t)(cap + 2) * 8);
     fill_u64(ctx, (*acc0)[i].ptr, cap + 2, a->aggs[i].init0);
-    if (a->aggs[i].func == DFGPU_AGG_AVG) { (*acc1)[i].alloc(ctx, (size_t)(cap + 2) * 8); (*acc1)[i].zero(); }
+    if (a->aggs[i].func == DFGPU_AGG_AVG || a->aggs[i].cls == 3) { (*acc1)[i].alloc(ctx, (size_t)(cap + 2) * 8); (*acc1)[i].zero(); }   // AVG: count; Decimal128 SUM: high word
     if (a->aggs[i].track_seen) { (*seen)[i].alloc(ctx, (size_t)(cap + 2)); (*seen)[i].zero(); }
   }
 }
@@ -741,7 +757,7 @@ static void agg_convert_batch_to_state(dfgpu_agg* a, const std::vector<DCol>& co
         break;
       }
       default: {   // SUM / MIN / MAX
-        const int t = st.func == DFGPU_AGG_SUM ? (st.cls == 2 ? DFGPU_FLOAT64 : (st.cls == 1 ? DFGPU_UINT64 : DFGPU_INT64)) : st.out_type;
+        const int t = st.func == DFGPU_AGG_SUM ? (st.cls == 3 ? st.out_type : (st.cls == 2 ? DFGPU_FLOAT64 : (st.cls == 1 ? DFGPU_UINT64 : DFGPU_INT64))) : st.out_type;
         DCol c = alloc_col(ctx, t, n, true);
         so.o[i].v0 = c.own_values->ptr; so.o[i].valid0 = c.own_validity->as<uint32_t>(); so.o[i].t0 = t;
         c.null_count = -1;
@@ -1022,8 +1038,8 @@ static void agg_emit_table(dfgpu_agg* a) {
     d.null_bit = -1;
     switch (s.func) {
       case DFGPU_AGG_SUM: {
-        d.kind = EK_COPY64;
-        int t2 = s.cls == 2 ? DFGPU_FLOAT64 : (s.cls == 1 ? DFGPU_UINT64 : DFGPU_INT64);  // Sum::return_type, sum.rs:232-261
+        d.kind = s.cls == 3 ? EK_DEC128 : EK_COPY64;
+        int t2 = s.cls == 3 ? s.out_type : (s.cls == 2 ? DFGPU_FLOAT64 : (s.cls == 1 ? DFGPU_UINT64 : DFGPU_INT64));  // Sum::return_type, sum.rs:232-261
         out->cols.push_back(run_emit(d, t2, s.track_seen));
         break;
       }
@@ -1154,7 +1170,12 @@ int dfgpu_agg_create(dfgpu_ctx* ctx, const int32_t* input_types, int32_t n_cols,
     s.cls = type_is_float(vt) ? 2 : (type_is_unsigned_int(vt) ? 1 : 0);
     switch (s.func) {
       case DFGPU_AGG_SUM:
-        DF_CHECK(type_is_int(vt) || type_is_float(vt), DFGPU_ERR_UNSUPPORTED, "SUM: numeric argument required (Decimal128 not supported yet)");
+        if (type_is_decimal(vt)) {
+          // Sum::return_type (sum.rs:247-249): Decimal128(min(38, precision + 10), scale); the state column already carries that type
+          DF_CHECK(dec_precision(vt) >= 1, DFGPU_ERR_UNSUPPORTED, "SUM: Decimal128 argument needs its precision and scale (DFGPU_DECIMAL128_TYPE)");
+          s.cls = 3;
+          s.out_type = a->state_input ? vt : dec_type(std::min(38, dec_precision(vt) + 10), dec_scale(vt));
+        } else DF_CHECK(type_is_int(vt) || type_is_float(vt), DFGPU_ERR_UNSUPPORTED, "SUM: numeric argument required");
         s.init0 = 0; break;
       case DFGPU_AGG_COUNT: case DFGPU_AGG_COUNT_STAR: s.init0 = 0; break;
       case DFGPU_AGG_AVG:

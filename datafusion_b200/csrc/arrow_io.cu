@@ -27,7 +27,11 @@ static int arrow_type(const char* fmt) {
     // decimal128 only ("d:p,s" or "d:p,s,128")
     int commas = 0;
     for (char ch : f) commas += ch == ',';
-    if (commas == 1 || f.size() >= 4 && f.substr(f.size() - 4) == ",128") return DFGPU_DECIMAL128;
+    if (commas == 1 || f.size() >= 4 && f.substr(f.size() - 4) == ",128") {
+      int p = 0, sc = 0;
+      if (sscanf(f.c_str(), "d:%d,%d", &p, &sc) == 2 && p >= 1 && p <= 38 && sc >= 0 && sc <= p) return dec_type(p, sc);
+      return DFGPU_DECIMAL128;  // negative scale: carried as an opaque 16-byte value
+    }
     return -1;
   }
   return -1;

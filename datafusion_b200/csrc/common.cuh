@@ -44,8 +44,13 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 // ------------------------------------------------------------------------------------------
 // type helpers
 // ------------------------------------------------------------------------------------------
+// Decimal128(p, s): the ABI's type code carries precision and scale in its upper bytes (DFGPU_DECIMAL128_TYPE)
+__host__ __device__ inline bool type_is_decimal(int t) { return (t & 0xff) == DFGPU_DECIMAL128; }
+__host__ __device__ inline int dec_precision(int t) { return (t >> 8) & 0xff; }
+__host__ __device__ inline int dec_scale(int t) { return (int)(int8_t)((t >> 16) & 0xff); }
+__host__ __device__ inline int dec_type(int p, int s) { return DFGPU_DECIMAL128 | (p << 8) | ((s & 0xff) << 16); }
 __host__ __device__ inline int type_width(int t) {
-  switch (t) {
+  switch (t & 0xff) {
     case DFGPU_BOOL: return 0;  // bit-packed
     case DFGPU_INT8: case DFGPU_UINT8: return 1;
     case DFGPU_INT16: case DFGPU_UINT16: return 2;

@@ -299,7 +299,7 @@ void dfgpu_batch_release(dfgpu_batch* b) {
 // ---- Arrow C Data export of a host batch (struct array, one child per column) ----
 namespace {
 const char* arrow_format(int type) {
-  switch (type) {
+  switch (type & 0xff) {
     case DFGPU_BOOL: return "b";
     case DFGPU_INT8: return "c"; case DFGPU_UINT8: return "C";
     case DFGPU_INT16: return "s"; case DFGPU_UINT16: return "S";
@@ -322,7 +322,7 @@ struct ExportPrivate {
 struct SchemaPrivate {
   std::vector<ArrowSchema> children;
   std::vector<ArrowSchema*> child_ptrs;
-  std::vector<std::string> names;
+  std::vector<std::string> names, formats;
 };
 void release_child_array(ArrowArray* a) { a->release = nullptr; }
 void release_top_array(ArrowArray* a) {
@@ -361,12 +361,17 @@ int dfgpu_batch_export_arrow(dfgpu_batch* b, struct ArrowArray* out_array, struc
   out_array->release = release_top_array; out_array->private_data = p;
 
   auto* sp = new SchemaPrivate();
-  sp->children.resize(n); sp->child_ptrs.resize(n); sp->names.resize(n);
+  sp->children.resize(n); sp->child_ptrs.resize(n); sp->names.resize(n); sp->formats.resize(n);
   for (size_t i = 0; i < n; ++i) {
     sp->names[i] = "c" + std::to_string(i);
     ArrowSchema& s = sp->children[i];
     memset(&s, 0, sizeof(s));
-    s.format = arrow_format(p->cols[i].type); s.name = sp->names[i].c_str(); s.flags = ARROW_FLAG_NULLABLE;
+    s.format = arrow_format(p->cols[i].type);
+    if (type_is_decimal(p->cols[i].type) && dec_precision(p->cols[i].type) > 0) {   // "d:precision,scale"
+      sp->formats[i] = "d:" + std::to_string(dec_precision(p->cols[i].type)) + "," + std::to_string(dec_scale(p->cols[i].type));
+      s.format = sp->formats[i].c_str();
+    }
+    s.name = sp->names[i].c_str(); s.flags = ARROW_FLAG_NULLABLE;
     s.release = release_child_schema;
     sp->child_ptrs[i] = &s;
   }

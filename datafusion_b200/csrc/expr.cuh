@@ -11,6 +11,8 @@ struct ExprPlan {
   std::vector<int> in_type, out_type;
   int root_type = 0;
   std::vector<ExprGuard> guards;
+  bool has_decimal = false;        // some node reads or produces a Decimal128: evaluated on the 128-bit stack (expr_dec.cuh)
+  std::vector<int64_t> aux;        // per node: power-of-ten rescale exponents of decimal BINARY / CAST nodes
 };
 // type inference + validation of a post-order program against a schema
 ExprPlan plan_expr(const int32_t* schema_types, int n_cols, const dfgpu_expr_node* nodes, int n_nodes);

@@ -27,9 +27,10 @@ struct ENode {
 };
 struct EProgram { int n; ENode node[kMaxNodes]; };
 
-enum Cls : int { C_I64 = 0, C_U64 = 1, C_F64 = 2, C_BOOL = 3 };
+enum Cls : int { C_I64 = 0, C_U64 = 1, C_F64 = 2, C_BOOL = 3, C_DEC = 4 /* Decimal128: 128-bit stack, expr_dec.cuh */ };
 __host__ __device__ inline int cls_of(int t) {
   if (t == DFGPU_BOOL) return C_BOOL;
+  if (type_is_decimal(t)) return C_DEC;
   if (type_is_float(t)) return C_F64;
   if (type_is_unsigned_int(t)) return C_U64;
   return C_I64;

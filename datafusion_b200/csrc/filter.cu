@@ -18,6 +18,7 @@
 #include "scan.cuh"
 #include "expr.cuh"
 #include "expr_dev.cuh"
+#include "expr_dec.cuh"
 
 namespace dfgpu {
 
@@ -52,6 +53,43 @@ __global__ void __launch_bounds__(256) expr_eval_kernel(EProgram p, int64_t n, v
     if (lane == 0) {
       if (out_valid) out_valid[wi] = vw;
       if (out_boolwords) out_boolwords[wi] = bw;  // NULL slots hold 0
+      if (out_select) out_select[wi] = bw;
+    }
+  }
+  if (err) atomicOr(err_flag, err);
+}
+
+// the same for programs that touch Decimal128 values: 128-bit evaluation stack (expr_dec.cuh)
+__global__ void __launch_bounds__(256) expr_eval_dec_kernel(EProgram p, int64_t n, void* __restrict__ out_values, uint32_t* __restrict__ out_boolwords,
+                                                         uint32_t* __restrict__ out_valid, uint32_t* __restrict__ out_select, int* __restrict__ err_flag) {
+  const int64_t nw = (n + 31) / 32;
+  const int lane = threadIdx.x & 31;
+  const int root_type = p.node[p.n - 1].out_type;
+  int err = 0;
+  for (int64_t wi = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; wi < nw; wi += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int64_t row = wi * 32 + lane;
+    i128 rv = 0;
+    bool rok = false;
+    if (row < n) {
+      rv = eval_nodes_dec(p.node, p.n, row, &rok, &err);
+      if (!rok) rv = 0;
+      if (out_values) {
+        const uint64_t lo = (uint64_t)rv;
+        if (type_is_decimal(root_type)) { ((unsigned long long*)out_values)[2 * row] = lo; ((unsigned long long*)out_values)[2 * row + 1] = (uint64_t)((u128)rv >> 64); }
+        else switch (root_type) {
+          case DFGPU_INT8: case DFGPU_UINT8: ((uint8_t*)out_values)[row] = (uint8_t)lo; break;
+          case DFGPU_INT16: case DFGPU_UINT16: ((uint16_t*)out_values)[row] = (uint16_t)lo; break;
+          case DFGPU_INT32: case DFGPU_UINT32: case DFGPU_DATE32: ((uint32_t*)out_values)[row] = (uint32_t)lo; break;
+          case DFGPU_FLOAT32: ((float*)out_values)[row] = (float)__longlong_as_double((long long)lo); break;
+          default: ((uint64_t*)out_values)[row] = lo; break;
+        }
+      }
+    }
+    uint32_t vw = __ballot_sync(0xffffffffu, rok);
+    uint32_t bw = __ballot_sync(0xffffffffu, rok && ((uint64_t)rv & 1));
+    if (lane == 0) {
+      if (out_valid) out_valid[wi] = vw;
+      if (out_boolwords) out_boolwords[wi] = bw;
       if (out_select) out_select[wi] = bw;
     }
   }
@@ -142,7 +180,7 @@ __global__ void __launch_bounds__(kFiltThreads) filter_fused_kernel(const EProgr
   bool keep[kFiltItems];
   uint32_t m = 0;
   int err = 0;
-  if (FAST) {
+  if (FAST == 1) {
     int64_t v[kFiltItems];
 #pragma unroll
     for (int k = 0; k < kFiltItems; ++k) v[k] = row0 + k < n ? fast_col[row0 + k] : 0;
@@ -166,7 +204,9 @@ __global__ void __launch_bounds__(kFiltThreads) filter_fused_kernel(const EProgr
       keep[k] = false;
       if (row0 + k < n) {
         bool ok;
-        uint64_t val = eval_row(*prog, row0 + k, &ok, &err);
+        uint64_t val;
+        if (FAST == 2) val = (uint64_t)eval_nodes_dec(prog->node, prog->n, row0 + k, &ok, &err);   // the predicate touches Decimal128 values
+        else val = eval_row(*prog, row0 + k, &ok, &err);
         keep[k] = ok && (val & 1);   // NULL predicate rows are dropped (filter_record_batch)
       }
       m += keep[k] ? 1u : 0u;
@@ -210,6 +250,7 @@ static bool is_cmp_op(int op) { return (op >= DFGPU_OP_EQ && op <= DFGPU_OP_GTEQ
 static bool is_arith_op(int op) { return op >= DFGPU_OP_PLUS && op <= DFGPU_OP_MODULO; }
 static bool is_bit_op(int op) { return op >= DFGPU_OP_BITAND && op <= DFGPU_OP_SHIFT_RIGHT; }
 static bool expr_type_ok(int t) {
+  if (type_is_decimal(t)) return dec_precision(t) >= 1 && dec_precision(t) <= 38 && dec_scale(t) >= 0 && dec_scale(t) <= dec_precision(t);
   return t == DFGPU_BOOL || type_is_int(t) || type_is_float(t);
 }
 
@@ -219,6 +260,7 @@ ExprPlan plan_expr(const int32_t* schema_types, int n_cols, const dfgpu_expr_nod
   p.nodes.assign(nodes, nodes + n_nodes);
   p.in_type.assign(n_nodes, 0);
   p.out_type.assign(n_nodes, 0);
+  p.aux.assign(n_nodes, 0);
   std::vector<int> stack;       // node index of each stack entry
   for (int i = 0; i < n_nodes; ++i) {
     const dfgpu_expr_node& nd = nodes[i];
@@ -239,6 +281,41 @@ ExprPlan plan_expr(const int32_t* schema_types, int n_cols, const dfgpu_expr_nod
         int r = stack.back(); stack.pop_back();
         int l = stack.back(); stack.pop_back();
         int lt = p.out_type[l], rt = p.out_type[r];
+        if (type_is_decimal(lt) || type_is_decimal(rt)) {
+          // arrow-arith decimal_op (arithmetic.rs): result precision / scale and the rescale multipliers per operator
+          DF_CHECK(type_is_decimal(lt) && type_is_decimal(rt), DFGPU_ERR_INVALID, "expression: a Decimal128 operand needs a Decimal128 partner (the planner's coercion casts the other side)");
+          const int p1 = dec_precision(lt), s1 = dec_scale(lt), p2 = dec_precision(rt), s2 = dec_scale(rt);
+          p.in_type[i] = lt;
+          p.has_decimal = true;
+          if (is_cmp_op(nd.a)) {
+            DF_CHECK(lt == rt, DFGPU_ERR_INVALID, "expression: Decimal128 comparison needs equal precision and scale on both sides");
+            p.out_type[i] = DFGPU_BOOL;
+          } else if (is_arith_op(nd.a)) {
+            int rp, rs, le = 0, re = 0;
+            switch (nd.a) {
+              case DFGPU_OP_PLUS: case DFGPU_OP_MINUS:
+                rs = std::max(s1, s2); rp = std::min(38, rs + std::max(p1 - s1, p2 - s2) + 1); le = rs - s1; re = rs - s2; break;
+              case DFGPU_OP_MULTIPLY:
+                rp = std::min(38, p1 + p2 + 1); rs = s1 + s2;
+                DF_CHECK(rs <= 38, DFGPU_ERR_INVALID, "expression: Decimal128 multiply: output scale exceeds 38");
+                break;
+              case DFGPU_OP_DIVIDE: {
+                rs = std::min(38, s1 + 4);                 // "a fixed scale increment of 4" (postgres / MySQL)
+                const int mul_pow = rs - s1 + s2;
+                rp = std::min(38, mul_pow + p1);
+                if (mul_pow >= 0) le = mul_pow; else re = -mul_pow;
+                break;
+              }
+              default:  // MODULO
+                rs = std::max(s1, s2); rp = std::min(38, rs + std::min(p1 - s1, p2 - s2)); le = rs - s1; re = rs - s2; break;
+            }
+            DF_CHECK(le <= 38 && re <= 38, DFGPU_ERR_INVALID, "expression: Decimal128 rescale exceeds 10^38");
+            p.out_type[i] = dec_type(rp, rs);
+            p.aux[i] = (int64_t)le | ((int64_t)re << 8);
+          } else throw Error(DFGPU_ERR_UNSUPPORTED, "expression: operator not supported on Decimal128");
+          stack.push_back(i);
+          break;
+        }
         // the planner coerces both sides to one type (expr-common type_coercion); we insist on it
         DF_CHECK(lt == rt || (cls_of(lt) == cls_of(rt) && type_width(lt) == type_width(rt)), DFGPU_ERR_INVALID,
                  "expression: binary operands must already be coerced to a common type");
@@ -273,6 +350,18 @@ ExprPlan plan_expr(const int32_t* schema_types, int n_cols, const dfgpu_expr_nod
       case DFGPU_EXPR_CAST:
         DF_CHECK(!stack.empty() && expr_type_ok(nd.type), DFGPU_ERR_UNSUPPORTED, "expression: cast target not supported");
         p.in_type[i] = p.out_type[stack.back()]; p.out_type[i] = nd.type; stack.back() = i;
+        if (type_is_decimal(p.in_type[i]) || type_is_decimal(nd.type)) {
+          const int from = p.in_type[i], to = nd.type;
+          p.has_decimal = true;
+          DF_CHECK(from != DFGPU_BOOL && to != DFGPU_BOOL, DFGPU_ERR_UNSUPPORTED, "expression: Boolean <-> Decimal128 cast is not supported");
+          int e;
+          if (type_is_decimal(from) && type_is_decimal(to)) e = std::abs(dec_scale(to) - dec_scale(from));
+          else if (type_is_decimal(to)) e = dec_scale(to);
+          else e = dec_scale(from);
+          // float <-> decimal goes through 10^scale as an f64, exact up to 10^22 (beyond that the reference's powi rounding would have to be reproduced)
+          if (type_is_float(from) || type_is_float(to)) DF_CHECK(e <= 22, DFGPU_ERR_UNSUPPORTED, "expression: float <-> Decimal128 cast with scale > 22 stays on the CPU operator");
+          p.aux[i] = e;
+        }
         break;
       default: throw Error(DFGPU_ERR_INVALID, "expression: unknown node kind");
     }
@@ -280,6 +369,7 @@ ExprPlan plan_expr(const int32_t* schema_types, int n_cols, const dfgpu_expr_nod
   }
   DF_CHECK(stack.size() == 1, DFGPU_ERR_INVALID, "expression: malformed program (stack must end with one value)");
   p.root_type = p.out_type[n_nodes - 1];
+  for (int i = 0; i < n_nodes; ++i) if (type_is_decimal(p.out_type[i]) || type_is_decimal(p.in_type[i])) p.has_decimal = true;
   // ---- short-circuit guards: AND / OR nodes whose RHS can raise an error ----
   {
     std::vector<int> start(n_nodes), depth_before(n_nodes);
@@ -298,6 +388,7 @@ ExprPlan plan_expr(const int32_t* schema_types, int n_cols, const dfgpu_expr_nod
       for (int j = rhs_start; j < i; ++j) {
         if (nodes[j].kind == DFGPU_EXPR_CAST) can_error = true;
         if (nodes[j].kind == DFGPU_EXPR_BINARY && (nodes[j].a == DFGPU_OP_DIVIDE || nodes[j].a == DFGPU_OP_MODULO) && !type_is_float(p.in_type[j])) can_error = true;
+        if (nodes[j].kind == DFGPU_EXPR_BINARY && is_arith_op(nodes[j].a) && type_is_decimal(p.in_type[j])) can_error = true;   // checked 128-bit arithmetic
       }
       if (!can_error) continue;
       ExprGuard g;
@@ -349,6 +440,7 @@ uint64_t literal_bits(const dfgpu_expr_node& nd) {
     uint64_t b; memcpy(&b, &d, 8); return b;
   }
   if (nd.type == DFGPU_BOOL) return nd.lit_i64 ? 1 : 0;
+  if (type_is_decimal(nd.type)) return (uint64_t)nd.lit_i64;   // low half; the high half rides in the bytes of lit_f64 (bind_program)
   switch (nd.type) {
     case DFGPU_INT8: return (uint64_t)(int64_t)(int8_t)nd.lit_i64;
     case DFGPU_INT16: return (uint64_t)(int64_t)(int16_t)nd.lit_i64;
@@ -373,6 +465,9 @@ void bind_program(const ExprPlan& plan, const std::vector<DCol>& cols, EProgram*
       e.col = c.values; e.valid = c.validity; e.voff = c.offset;
     } else if (nd.kind == DFGPU_EXPR_LITERAL) {
       e.lit = literal_bits(nd); e.lit_null = nd.is_null;
+      if (type_is_decimal(nd.type)) memcpy(&e.voff, &nd.lit_f64, 8);
+    } else if ((nd.kind == DFGPU_EXPR_BINARY || nd.kind == DFGPU_EXPR_CAST) && plan.has_decimal) {
+      e.voff = plan.aux[i];   // power-of-ten rescale exponents (expr_dec.cuh)
     }
     if (gmasks) { e.g_and = (*gmasks)[i].first; e.g_or = (*gmasks)[i].second; }
   }
@@ -417,7 +512,8 @@ EvalResult evaluate_expr(dfgpu_ctx* ctx, const ExprPlan& plan, const std::vector
   DevBuf err(ctx, 4);
   err.zero();
   if (n > 0) {
-    expr_eval_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(
+    auto kern = plan.has_decimal ? expr_eval_dec_kernel : expr_eval_kernel;
+    kern<<<grid_for(n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(
         prog, n, (want_column && rt != DFGPU_BOOL) ? res.column.own_values->ptr : nullptr,
         (want_column && rt == DFGPU_BOOL) ? res.column.own_values->as<uint32_t>() : nullptr,
         want_column ? res.column.own_validity->as<uint32_t>() : nullptr, want_select ? res.select_words.as<uint32_t>() : nullptr, err.as<int>());
@@ -425,7 +521,7 @@ EvalResult evaluate_expr(dfgpu_ctx* ctx, const ExprPlan& plan, const std::vector
     int e = read_scalar<int>(ctx, err.as<int>());
     if (e & ERR_DIV_ZERO) throw Error(DFGPU_ERR_ARITH, "Arrow error: Divide by zero error");
     if (e & ERR_OVERFLOW) throw Error(DFGPU_ERR_ARITH, "Arrow error: Arithmetic overflow");
-    if (e & ERR_CAST) throw Error(DFGPU_ERR_ARITH, "Arrow error: Cast error: Can't cast value to the target type (out of range)");
+    if (e & ERR_CAST) throw Error(DFGPU_ERR_ARITH, "Arrow error: Cast error: Can't cast value to the target type (out of range or beyond the Decimal128 precision)");
   }
   if (want_column) {
     // an expression over columns that carry no validity bitmap in THIS batch and without NULL literals cannot produce a NULL
@@ -552,7 +648,8 @@ static void filter_push(dfgpu_filter* f, const std::vector<DCol>& cols) {
         progbuf.alloc(ctx, sizeof(EProgram));
         DF_CUDA(cudaMemcpyAsync(progbuf.ptr, &prog, sizeof(EProgram), cudaMemcpyHostToDevice, ctx->stream));
         DF_CUDA(cudaStreamSynchronize(ctx->stream));  // `prog` lives on this stack frame
-        filter_fused_kernel<0><<<(int)nt, kFiltThreads, 0, ctx->stream>>>((const EProgram*)progbuf.ptr, nullptr, 0, 0, n, fc, desc.as<unsigned long long>(), counter, totals, err.as<int>());
+        if (plan.has_decimal) filter_fused_kernel<2><<<(int)nt, kFiltThreads, 0, ctx->stream>>>((const EProgram*)progbuf.ptr, nullptr, 0, 0, n, fc, desc.as<unsigned long long>(), counter, totals, err.as<int>());
+        else filter_fused_kernel<0><<<(int)nt, kFiltThreads, 0, ctx->stream>>>((const EProgram*)progbuf.ptr, nullptr, 0, 0, n, fc, desc.as<unsigned long long>(), counter, totals, err.as<int>());
       }
       DF_LAUNCH_CHECK(ctx);
     }

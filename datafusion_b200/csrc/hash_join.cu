@@ -1614,8 +1614,15 @@ static void push_probe(dfgpu_hashjoin* j, std::vector<DCol>&& cols) {
         }
         {
           KernelTimer kt(ctx, "join_probe");
-          if (j->inline_words == 2) radix_probe_kernel<2><<<kNumSMs * 8, 256, 0, ctx->stream>>>(recs.as<RadixRec>(), n, j->iref, ro, rtile, rtot);
-          else radix_probe_kernel<1><<<kNumSMs * 8, 256, 0, ctx->stream>>>(recs.as<RadixRec>(), n, j->iref, ro, rtile, rtot);
+          bool all8 = true;
+          for (int c = 0; c < ro.n; ++c) all8 = all8 && ro.width[c] == 8;
+          if (j->inline_words == 2) {
+            if (all8) radix_probe_kernel<2, true><<<kNumSMs * 8, 256, 0, ctx->stream>>>(recs.as<RadixRec>(), n, j->iref, ro, rtile, rtot);
+            else radix_probe_kernel<2, false><<<kNumSMs * 8, 256, 0, ctx->stream>>>(recs.as<RadixRec>(), n, j->iref, ro, rtile, rtot);
+          } else {
+            if (all8) radix_probe_kernel<1, true><<<kNumSMs * 8, 256, 0, ctx->stream>>>(recs.as<RadixRec>(), n, j->iref, ro, rtile, rtot);
+            else radix_probe_kernel<1, false><<<kNumSMs * 8, 256, 0, ctx->stream>>>(recs.as<RadixRec>(), n, j->iref, ro, rtile, rtot);
+          }
           DF_LAUNCH_CHECK(ctx);
         }
         unsigned long long hrows = 0;

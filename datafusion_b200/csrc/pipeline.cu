@@ -27,6 +27,7 @@
 #include "scan.cuh"
 #include "expr.cuh"
 #include "expr_dev.cuh"
+#include "expr_dec.cuh"
 #include <climits>
 #include <array>
 
@@ -224,13 +225,35 @@ __device__ __forceinline__ uint64_t eval_int_fast(const ENode* __restrict__ node
   return s0;
 }
 
+// programs that touch Decimal128 values (small == 3): the 128-bit interpreter; returns the low word, *hi the high word
+__device__ __noinline__ uint64_t pipe_eval_dec(const ENode* nodes, int n, int64_t row, const uint64_t* ext, int* err_ok, unsigned long long* hi) {
+  bool ok;
+  int err = 0;
+  const i128 v = eval_nodes_dec(nodes, n, row, &ok, &err, ext);
+  err_ok[0] |= err; err_ok[1] = ok ? 1 : 0;
+  *hi = (unsigned long long)((u128)v >> 64);
+  return (uint64_t)v;
+}
 // one out-of-line copy of each interpreter: the kernel stays small enough for the instruction cache
+template <bool DEC>
 __device__ __noinline__ uint64_t pipe_eval(const ENode* nodes, int n, int small, int64_t row, const uint64_t* ext, int* err_ok /* [0]=err bits (or-ed), [1]=valid */) {
+  if (DEC && small == 3) { unsigned long long hi; return pipe_eval_dec(nodes, n, row, ext, err_ok, &hi); }
   bool ok;
   int err = 0;
   const uint64_t v = small ? eval_nodes_reg<4>(nodes, n, row, &ok, &err, ext) : eval_nodes(nodes, n, row, &ok, &err, ext);
   err_ok[0] |= err; err_ok[1] = ok ? 1 : 0;
   return v;
+}
+// SUM over a Decimal128 argument, evaluated and accumulated out of line (the hot integer path of the aggregate sink stays as it was):
+// i128 add_wrapping over two accumulator words — the carry out of the low word is decided by this add alone
+__device__ __noinline__ void pipe_sum_dec(const ENode* nodes, int n, int64_t row, const uint64_t* ext, int* err_ok, unsigned long long* acc, unsigned long long* nn) {
+  unsigned long long hi;
+  const unsigned long long lo = pipe_eval_dec(nodes, n, row, ext, err_ok, &hi);
+  if (!err_ok[1]) return;                                  // NULL inputs are skipped (accumulate.rs:373-470)
+  if (nn) atomicAdd(nn, 1ull);
+  const unsigned long long old = atomicAdd(acc, lo);
+  const unsigned long long add_hi = hi + ((old + lo) < old ? 1ull : 0ull);
+  if (add_hi) atomicAdd(acc + 1, add_hi);
 }
 
 __device__ __forceinline__ uint4 ld_stream_v4(const void* p, uint64_t pol) {
@@ -292,7 +315,7 @@ __device__ __forceinline__ uint32_t valid8(const ColRef& c, int64_t row0, int64_
   return nb > 0 ? load_bits32(c.valid, c.voff + row0, nb) : 0u;
 }
 
-template <int SINK>
+template <int SINK, bool DEC>
 __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams* __restrict__ gp, int64_t n, unsigned long long* __restrict__ counters /* [alive, inserted, fail, err] */) {
   __shared__ PipeParams sp;
   __shared__ uint32_t q_rows[kPipeWarps][kQueueCap];
@@ -346,7 +369,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
 #pragma unroll 1
         for (int j = 0; j < kWarpRows; ++j) {
           if (!((mask >> j) & 1u)) continue;
-          const uint64_t val = pipe_eval(sp.pool + sp.pred_start, sp.pred_n, sp.pred_small, row0 + j, nullptr, err_ok);
+          const uint64_t val = pipe_eval<DEC>(sp.pool + sp.pred_start, sp.pred_n, sp.pred_small, row0 + j, nullptr, err_ok);
           if (!(err_ok[1] && (val & 1))) mask &= ~(1u << j);
         }
       }
@@ -546,8 +569,11 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
             if (ag.func == DFGPU_AGG_COUNT_STAR) continue;   // = the row counter
             uint64_t v;
             if (ag.small == 2) v = eval_int_fast(sp.pool + ag.start, ag.n, row[u], ext);
-            else {
-              v = pipe_eval(sp.pool + ag.start, ag.n, ag.small, row[u], ext, err_ok);
+            else if (DEC && ag.cls == C_DEC && ag.func == DFGPU_AGG_SUM) {
+              pipe_sum_dec(sp.pool + ag.start, ag.n, row[u], ext, err_ok, rec + ag.word, ag.nn_word >= 0 ? rec + ag.nn_word : nullptr);
+              continue;
+            } else {
+              v = pipe_eval<DEC>(sp.pool + ag.start, ag.n, ag.small, row[u], ext, err_ok);
               if (!err_ok[1]) continue;                      // NULL inputs are skipped (accumulate.rs:373-470)
             }
             if (ag.nn_word >= 0) red_add_u64(rec + ag.nn_word, 1ull);
@@ -775,7 +801,7 @@ __global__ void __launch_bounds__(256) lookup_groups_kernel(LookupDev t, int row
     if (lane == 0) words[w] = b;
   }
 }
-struct EmitCol { int kind /* 0 key, 1 payload field, 2 accumulator word, 3 AVG value, 4 count as u64 */, width, shift, word, nn_word, cnt_word, f64; void* dst; uint32_t* valid; };
+struct EmitCol { int kind /* 0 key, 1 payload field, 2 accumulator word, 3 AVG value, 4 count as u64, 5 Decimal128 sum (two words) */, width, shift, word, nn_word, cnt_word, f64; void* dst; uint32_t* valid; };
 struct EmitCols { int n; EmitCol c[kMaxPipeCols]; };
 __global__ void __launch_bounds__(256) lookup_emit_kernel(LookupDev t, const uint32_t* __restrict__ slots, int64_t n, int rows_word, EmitCols ec) {
   const int lane = threadIdx.x & 31;
@@ -794,6 +820,11 @@ __global__ void __launch_bounds__(256) lookup_emit_kernel(LookupDev t, const uin
           case 1: v = r[1] >> e.shift; break;
           case 2: v = r[e.word]; ok = e.nn_word >= 0 ? r[e.nn_word] != 0ull : true; break;
           case 4: v = r[e.word]; break;
+          case 5:
+            ok = e.nn_word >= 0 ? r[e.nn_word] != 0ull : true;
+            ((unsigned long long*)e.dst)[2 * i] = ok ? r[e.word] : 0ull;
+            ((unsigned long long*)e.dst)[2 * i + 1] = ok ? r[e.word + 1] : 0ull;
+            break;
           default: {   // AVG = sum / count over Float64 (functions-aggregate/src/average.rs)
             const unsigned long long cnt = r[e.cnt_word];
             ok = cnt != 0ull;
@@ -802,7 +833,7 @@ __global__ void __launch_bounds__(256) lookup_emit_kernel(LookupDev t, const uin
           }
         }
         if (!ok) v = 0;
-        switch (e.width) {
+        if (e.kind != 5) switch (e.width) {
           case 1: ((uint8_t*)e.dst)[i] = (uint8_t)v; break;
           case 2: ((uint16_t*)e.dst)[i] = (uint16_t)v; break;
           case 4: ((uint32_t*)e.dst)[i] = (uint32_t)v; break;
@@ -988,6 +1019,9 @@ static int bind_pool(const dfgpu_pipeline* p, const ExprPlan& plan, const std::v
       }
     } else if (nd.kind == DFGPU_EXPR_LITERAL) {
       e.lit = literal_bits(nd); e.lit_null = nd.is_null;
+      if (type_is_decimal(nd.type)) memcpy(&e.voff, &nd.lit_f64, 8);
+    } else if ((nd.kind == DFGPU_EXPR_BINARY || nd.kind == DFGPU_EXPR_CAST) && plan.has_decimal) {
+      e.voff = plan.aux[i];   // power-of-ten rescale exponents (expr_dec.cuh)
     }
     e.g_and = gmasks[i].first; e.g_or = gmasks[i].second;
   }
@@ -1049,7 +1083,7 @@ static void fill_params(dfgpu_pipeline* p, const std::vector<DCol>& cols, PipePa
           nd[i + 2].a >= DFGPU_OP_EQ && nd[i + 2].a <= DFGPU_OP_GTEQ && !nd[i + 1].is_null) {
         const int ct = p->in_types[nd[i].a];
         const int cls = cls_of(ct);
-        if ((cls != C_I64 && cls != C_U64) || (int)terms.size() >= kMaxTerms) { fast = false; break; }
+        if ((cls != C_I64 && cls != C_U64) || p->pred.has_decimal || (int)terms.size() >= kMaxTerms) { fast = false; break; }
         terms.push_back({(long long)nd[i].a, (long long)nd[i + 2].a, (long long)(cls == C_U64), (long long)literal_bits(nd[i + 1])});
         depth++; i += 3;
       } else if (nd[i].kind == DFGPU_EXPR_BINARY && nd[i].a == DFGPU_OP_AND && depth >= 2) { depth--; i++; }
@@ -1062,7 +1096,7 @@ static void fill_params(dfgpu_pipeline* p, const std::vector<DCol>& cols, PipePa
       pp->pred_mode = 2;
       pp->pred_start = bind_pool(p, p->pred, cols, pp, &pool_used);
       pp->pred_n = (int)p->pred.nodes.size();
-      pp->pred_small = plan_depth(p->pred) <= 4 ? 1 : 0;
+      pp->pred_small = p->pred.has_decimal ? 3 : (plan_depth(p->pred) <= 4 ? 1 : 0);
     }
   }
   pp->n_stages = (int)p->stages.size();
@@ -1093,6 +1127,7 @@ static void fill_params(dfgpu_pipeline* p, const std::vector<DCol>& cols, PipePa
         d.start = bind_pool(p, ag.plan, cols, pp, &pool_used); d.n = (int)ag.plan.nodes.size();
         d.small = plan_depth(ag.plan) <= 4 ? 1 : 0;
         if (d.small && plan_is_int_arith(p, ag.plan, cols)) d.small = 2;
+        if (ag.plan.has_decimal) d.small = 3;
         if (ag.nn_word < 0 && ag.func != DFGPU_AGG_COUNT)
           DF_CHECK(!expr_can_be_null(ag.plan, cols), DFGPU_ERR_UNSUPPORTED, "pipeline: nullable aggregate input needs one more accumulator word in the lookup (n_acc_words)");
       }
@@ -1110,16 +1145,22 @@ template <int SINK>
 static void launch_pipe(dfgpu_pipeline* p, int64_t n, const char* timer_name) {
   dfgpu_ctx* ctx = p->ctx;
   const int64_t ntiles = (n + kPipeTile - 1) / kPipeTile;
+  // programs that touch Decimal128 values run a second instantiation of the kernel (128-bit interpreter linked in): the integer
+  // instantiation stays byte for byte what it was
+  bool dec = p->has_pred && p->pred.has_decimal;
+  for (const auto& ag : p->aggs) dec = dec || (ag.has_expr && ag.plan.has_decimal);
   static const int blocks_env = getenv("DFGPU_PIPE_BLOCKS_PER_SM") ? atoi(getenv("DFGPU_PIPE_BLOCKS_PER_SM")) : 0;
   int blocks_per_sm = blocks_env;
   if (blocks_per_sm <= 0) {   // persistent blocks: exactly one resident wave (a second wave would start after the first finished)
-    DF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, pipe_kernel<SINK>, kPipeThreads, 0));
+    if (dec) DF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, pipe_kernel<SINK, true>, kPipeThreads, 0));
+    else DF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, pipe_kernel<SINK, false>, kPipeThreads, 0));
     blocks_per_sm = std::max(1, blocks_per_sm);
   }
   const int grid = (int)std::min<int64_t>(ntiles, (int64_t)kNumSMs * blocks_per_sm);
   const std::string tname = p->name.empty() ? std::string(timer_name) : "pipe:" + p->name;
   KernelTimer kt(ctx, tname.c_str());
-  pipe_kernel<SINK><<<grid, kPipeThreads, 0, ctx->stream>>>((const PipeParams*)p->params_dev.ptr, n, p->counters.as<unsigned long long>());
+  if (dec) pipe_kernel<SINK, true><<<grid, kPipeThreads, 0, ctx->stream>>>((const PipeParams*)p->params_dev.ptr, n, p->counters.as<unsigned long long>());
+  else pipe_kernel<SINK, false><<<grid, kPipeThreads, 0, ctx->stream>>>((const PipeParams*)p->params_dev.ptr, n, p->counters.as<unsigned long long>());
   DF_LAUNCH_CHECK(ctx);
 }
 
@@ -1161,7 +1202,8 @@ static void pipeline_push(dfgpu_pipeline* p, const std::vector<DCol>& cols) {
   for (size_t c = 0; c < cols.size(); ++c) {
     DF_CHECK(cols[c].type == p->in_types[c], DFGPU_ERR_INVALID, "pipeline input column type mismatch");
     DF_CHECK(cols[c].length == n, DFGPU_ERR_INVALID, "pipeline input ragged columns");
-    DF_CHECK(cols[c].type != DFGPU_BOOL && type_width(cols[c].type) <= 8, DFGPU_ERR_UNSUPPORTED, "pipeline: fixed-width columns of <= 8 bytes only");
+    DF_CHECK(cols[c].type != DFGPU_BOOL && (type_width(cols[c].type) <= 8 || type_is_decimal(cols[c].type)), DFGPU_ERR_UNSUPPORTED,
+             "pipeline: fixed-width columns of <= 8 bytes (and Decimal128 inside expressions) only");
   }
   p->m_input_rows += n;
   if (n == 0) return;
@@ -1351,7 +1393,12 @@ static void pipeline_finish(dfgpu_pipeline* p) {
     switch (ag.func) {
       case DFGPU_AGG_COUNT_STAR: e.kind = 4; e.word = p->rows_word; add(DFGPU_INT64, false, e); break;
       case DFGPU_AGG_COUNT: e.kind = 4; e.word = ag.word; add(DFGPU_INT64, false, e); break;
-      case DFGPU_AGG_SUM: e.kind = 2; e.word = ag.word; e.nn_word = ag.nn_word; add(sum_type, ag.nn_word >= 0, e); break;
+      case DFGPU_AGG_SUM:
+        if (ag.cls == C_DEC) {   // Sum::return_type: Decimal128(min(38, p + 10), s) (sum.rs:247-249); the Partial state has the same type
+          e.kind = 5; e.word = ag.word; e.nn_word = ag.nn_word;
+          add(dec_type(std::min(38, dec_precision(ag.arg_type) + 10), dec_scale(ag.arg_type)), ag.nn_word >= 0, e);
+        } else { e.kind = 2; e.word = ag.word; e.nn_word = ag.nn_word; add(sum_type, ag.nn_word >= 0, e); }
+        break;
       case DFGPU_AGG_MIN: case DFGPU_AGG_MAX: e.kind = 2; e.word = ag.word; e.nn_word = ag.nn_word; add(ag.arg_type, ag.nn_word >= 0, e); break;
       case DFGPU_AGG_AVG:
         if (partial) {   // state = [count: UInt64, sum: Float64] (aggregates/mod.rs:3591-3700)
@@ -1621,8 +1668,10 @@ int dfgpu_pipeline_sink_aggregate(dfgpu_pipeline* p, const int32_t* group_cols, 
       DF_CHECK(ag.cls != C_BOOL || ag.func == DFGPU_AGG_COUNT, DFGPU_ERR_UNSUPPORTED, "pipeline aggregate: Boolean arguments only for COUNT");
       if (ag.func == DFGPU_AGG_AVG) DF_CHECK(ag.arg_type == DFGPU_FLOAT64, DFGPU_ERR_UNSUPPORTED, "pipeline aggregate: AVG takes a Float64 argument (the planner casts)");
       if ((ag.func == DFGPU_AGG_MIN || ag.func == DFGPU_AGG_MAX)) DF_CHECK(ag.arg_type != DFGPU_FLOAT32, DFGPU_ERR_UNSUPPORTED, "pipeline aggregate: MIN/MAX over Float32 stays on dfgpu_agg");
+      if (ag.cls == C_DEC) DF_CHECK(ag.func == DFGPU_AGG_SUM || ag.func == DFGPU_AGG_COUNT, DFGPU_ERR_UNSUPPORTED, "pipeline aggregate: SUM / COUNT over Decimal128 (MIN / MAX / AVG stay on the CPU operator)");
       DF_CHECK(next < budget, DFGPU_ERR_UNSUPPORTED, "pipeline aggregate: not enough accumulator words in the lookup (n_acc_words)");
       ag.word = next++;
+      if (ag.cls == C_DEC && ag.func == DFGPU_AGG_SUM) { DF_CHECK(next < budget, DFGPU_ERR_UNSUPPORTED, "pipeline aggregate: a Decimal128 SUM takes two accumulator words (n_acc_words)"); next++; }
       if (ag.func == DFGPU_AGG_AVG) { DF_CHECK(next < budget, DFGPU_ERR_UNSUPPORTED, "pipeline aggregate: not enough accumulator words in the lookup (n_acc_words)"); ag.cnt_word = next++; ag.nn_word = ag.cnt_word; }
     }
     new_aggs.push_back(std::move(ag));
@@ -1644,6 +1693,7 @@ int dfgpu_pipeline_sink_output(dfgpu_pipeline* p, const int32_t* out_cols, int32
   DF_CHECK(p->sink == SINK_NONE && p->m_input_rows == 0, DFGPU_ERR_STATE, "pipeline: the sink is chosen once, before the first push");
   for (int c = 0; c < n_out; ++c) {
     DF_CHECK(out_cols[c] >= 0 && out_cols[c] < (int)p->vtypes.size(), DFGPU_ERR_INVALID, "pipeline output: column out of range");
+    DF_CHECK(type_width(p->vtypes[out_cols[c]]) <= 8, DFGPU_ERR_UNSUPPORTED, "pipeline output: 16-byte columns leave through dfgpu_filter / dfgpu_hashjoin");
     p->out_cols.push_back(out_cols[c]);
   }
   p->batch_size = batch_size; p->sink = SINK_OUTPUT;

@@ -164,7 +164,7 @@ struct RadixOut {
   void* dst[kMaxFusedCols];
 };
 
-template <int W>
+template <int W, bool ALL8>
 __global__ void __launch_bounds__(256) radix_probe_kernel(const RadixRec* __restrict__ recs, int64_t n, InlineRef t, RadixOut oc, unsigned int* __restrict__ tile_counter,
                                                          unsigned long long* __restrict__ totals /* [out rows] */) {
   constexpr int ITEMS = 4, TILE = 256 * ITEMS;
@@ -195,17 +195,25 @@ __global__ void __launch_bounds__(256) radix_probe_kernel(const RadixRec* __rest
         else cur[k] = __ldcg((const unsigned long long*)t.slots + slot[k]);
       }
     }
+    // lockstep linear probing: each round advances every unresolved row of the lane by one slot, so the (rare) second and third
+    // probes of the lane's rows overlap instead of running one dependent chain after the other
+    unsigned pend = 0;
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-      if (!live[k]) continue;
-      while (true) {
-        if (cur[k] == key[k]) { hit[k] = true; pay[k] = curp[k]; break; }
-        if (cur[k] == kEmpty64) break;
-        if (++slot[k] == t.cap) slot[k] = 0;
-        if (W == 2) { const uint4 x = __ldcg((const uint4*)t.slots + slot[k]); cur[k] = (uint64_t)x.x | ((uint64_t)x.y << 32); curp[k] = (uint64_t)x.z | ((uint64_t)x.w << 32); }
-        else cur[k] = __ldcg((const unsigned long long*)t.slots + slot[k]);
+    for (int k = 0; k < ITEMS; ++k) if (live[k]) pend |= 1u << k;
+    while (pend) {
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k) {
+        if (!((pend >> k) & 1u)) continue;
+        if (cur[k] == key[k]) { hit[k] = true; pay[k] = curp[k]; pend &= ~(1u << k); }
+        else if (cur[k] == kEmpty64) pend &= ~(1u << k);
+        else {
+          if (++slot[k] == t.cap) slot[k] = 0;
+          if (W == 2) { const uint4 x = __ldcg((const uint4*)t.slots + slot[k]); cur[k] = (uint64_t)x.x | ((uint64_t)x.y << 32); curp[k] = (uint64_t)x.z | ((uint64_t)x.w << 32); }
+          else cur[k] = __ldcg((const unsigned long long*)t.slots + slot[k]);
+        }
       }
     }
+    __syncwarp();
     // warp-aggregated reservation of output rows, coalesced column writes
     unsigned int tot = 0, mypos[ITEMS];
 #pragma unroll
@@ -217,8 +225,11 @@ __global__ void __launch_bounds__(256) radix_probe_kernel(const RadixRec* __rest
     for (int k = 0; k < ITEMS; ++k) {
       if (!hit[k]) continue;
       const unsigned long long o = obase + mypos[k];
-      for (int c = 0; c < oc.n; ++c) {
+#pragma unroll
+      for (int c = 0; c < kMaxFusedCols; ++c) {
+        if (c >= oc.n) break;
         const unsigned long long x = oc.kind[c] == 0 ? key[k] : (oc.kind[c] == 1 ? val[k] : (pay[k] >> oc.shift[c]));
+        if (ALL8) { ((uint64_t*)oc.dst[c])[o] = x; continue; }
         switch (oc.width[c]) {
           case 8: ((uint64_t*)oc.dst[c])[o] = x; break;
           case 4: ((uint32_t*)oc.dst[c])[o] = (uint32_t)x; break;

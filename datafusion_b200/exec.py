@@ -31,11 +31,14 @@ def type_id(t: pa.DataType) -> int:
     if pa.types.is_timestamp(t):
         return D.TIMESTAMP
     if pa.types.is_decimal128(t):
-        return D.DECIMAL128
+        return D.decimal128(t.precision, t.scale) if 0 <= t.scale <= t.precision else D.DECIMAL128
     raise NotImplementedError(f"This feature is not implemented: GPU operators do not support Arrow type {t}")
 
 
 def arrow_type(tid: int) -> pa.DataType:
+    if D.type_base(tid) == D.DECIMAL128:
+        p, sc = D.decimal_precision_scale(tid)
+        return pa.decimal128(p or 38, sc)
     return {D.BOOL: pa.bool_(), D.INT8: pa.int8(), D.INT16: pa.int16(), D.INT32: pa.int32(), D.INT64: pa.int64(), D.UINT8: pa.uint8(),
             D.UINT16: pa.uint16(), D.UINT32: pa.uint32(), D.UINT64: pa.uint64(), D.FLOAT32: pa.float32(), D.FLOAT64: pa.float64(),
             D.DATE32: pa.date32(), D.DATE64: pa.date64(), D.TIMESTAMP: pa.timestamp("ns")}[tid]
@@ -108,6 +111,12 @@ class Literal(Expr):
         v = 0 if self.value is None else self.value
         if tid in (D.FLOAT32, D.FLOAT64):
             out.append((D.EXPR_LITERAL, 0, tid, isnull, 0, float(v)))
+        elif D.type_base(tid) == D.DECIMAL128:
+            import decimal
+            with decimal.localcontext() as dctx:
+                dctx.prec = 80
+                unscaled = int(decimal.Decimal(str(v)).scaleb(self.type.scale).to_integral_value(rounding=decimal.ROUND_HALF_UP))
+            out.append((D.EXPR_LITERAL, 0, tid, isnull, unscaled, 0.0))   # capi.expr_nodes splits the 128-bit value
         else:
             if hasattr(v, "toordinal") and tid == D.DATE32:
                 import datetime
@@ -127,18 +136,36 @@ class BinaryExpr(Expr):
         if isinstance(r, Literal) and not isinstance(l, Literal):
             lt = l.data_type(schema)
             if r.type != lt and (pa.types.is_integer(r.type) or pa.types.is_floating(r.type)) and not pa.types.is_boolean(lt):
-                r = Literal(r.value, lt)
+                if pa.types.is_decimal128(lt) and self.op in (D.OP_PLUS, D.OP_MINUS, D.OP_MULTIPLY, D.OP_DIVIDE, D.OP_MODULO) and pa.types.is_integer(r.type):
+                    r = Literal(r.value, pa.decimal128(20, 0))    # Int64 -> Decimal128(20, 0) (type_coercion/binary.rs:1265)
+                else:
+                    r = Literal(r.value, lt)
         elif isinstance(l, Literal) and not isinstance(r, Literal):
             rt = r.data_type(schema)
             if l.type != rt and (pa.types.is_integer(l.type) or pa.types.is_floating(l.type)) and not pa.types.is_boolean(rt):
-                l = Literal(l.value, rt)
+                if pa.types.is_decimal128(rt) and self.op in (D.OP_PLUS, D.OP_MINUS, D.OP_MULTIPLY, D.OP_DIVIDE, D.OP_MODULO) and pa.types.is_integer(l.type):
+                    l = Literal(l.value, pa.decimal128(20, 0))
+                else:
+                    l = Literal(l.value, rt)
         return l, r
 
     def data_type(self, schema):
         if self.op in (D.OP_EQ, D.OP_NEQ, D.OP_LT, D.OP_LTEQ, D.OP_GT, D.OP_GTEQ, D.OP_AND, D.OP_OR, D.OP_IS_DISTINCT_FROM,
                        D.OP_IS_NOT_DISTINCT_FROM):
             return pa.bool_()
-        return self._coerced(schema)[0].data_type(schema)
+        l, r = self._coerced(schema)
+        lt, rt = l.data_type(schema), r.data_type(schema)
+        if pa.types.is_decimal128(lt) and pa.types.is_decimal128(rt):   # arrow-arith decimal_op result types (include/dfgpu.h)
+            p1, s1, p2, s2 = lt.precision, lt.scale, rt.precision, rt.scale
+            if self.op in (D.OP_PLUS, D.OP_MINUS):
+                sc = max(s1, s2); return pa.decimal128(min(38, sc + max(p1 - s1, p2 - s2) + 1), sc)
+            if self.op == D.OP_MULTIPLY:
+                return pa.decimal128(min(38, p1 + p2 + 1), s1 + s2)
+            if self.op == D.OP_DIVIDE:
+                sc = min(38, s1 + 4); return pa.decimal128(min(38, sc - s1 + s2 + p1), sc)
+            if self.op == D.OP_MODULO:
+                sc = max(s1, s2); return pa.decimal128(min(38, sc + min(p1 - s1, p2 - s2)), sc)
+        return lt
 
     def rpn(self, schema, out):
         l, r = self._coerced(schema)

@@ -96,6 +96,15 @@ enum dfgpu_type {
   DFGPU_TIMESTAMP = 14,  /* int64, unit carried by the Arrow schema only */
   DFGPU_DECIMAL128 = 15  /* 16-byte little-endian two's complement (TPC-H money)           */
 };
+/* Decimal128(precision, scale) (arrow DataType::Decimal128; the TPC-H money columns are Decimal128(15, 2),
+ * benchmarks/src/tpch/mod.rs:52-122): wherever a type code is passed or returned, the precision and the scale ride in the
+ * upper bytes — DFGPU_DECIMAL128_TYPE(15, 2).  Arithmetic, comparison, CAST and SUM need them (result types follow
+ * arrow-arith's decimal rules, see dfgpu_expr_node); the bare DFGPU_DECIMAL128 code (precision 0) is an opaque 16-byte value
+ * that can only be carried, compared for equality as a key, and counted. */
+#define DFGPU_DECIMAL128_TYPE(p, s) ((int32_t)(DFGPU_DECIMAL128 | ((int32_t)(p) << 8) | (((int32_t)(s) & 0xff) << 16)))
+#define DFGPU_TYPE_BASE(t) ((int32_t)(t) & 0xff)
+#define DFGPU_DECIMAL_PRECISION(t) (((int32_t)(t) >> 8) & 0xff)
+#define DFGPU_DECIMAL_SCALE(t) ((int32_t)(int8_t)(((int32_t)(t) >> 16) & 0xff))
 
 typedef struct dfgpu_column {
   int32_t type;            /* enum dfgpu_type */
@@ -204,9 +213,21 @@ typedef struct dfgpu_expr_node {
   int32_t a;        /* column index or dfgpu_op */
   int32_t type;     /* literal type / cast target */
   int32_t is_null;  /* literal is NULL */
-  int64_t lit_i64;  /* integer / date / bool literal */
-  double lit_f64;   /* float literal */
+  int64_t lit_i64;  /* integer / date / bool literal; Decimal128 literal: the low 64 bits */
+  double lit_f64;   /* float literal; Decimal128 literal: these 8 bytes hold the HIGH 64 bits (two's complement) */
 } dfgpu_expr_node;
+/* Decimal128 in expressions (arrow-arith 59.2 arithmetic.rs `decimal_op`, arrow-cast 59.2 cast/decimal.rs — third-party crates
+ * pinned by the reference's Cargo.lock and absent from its tree; anchored on the reference's own vectors
+ * binary.rs:4355-5000 comparison_decimal_expr_test / arithmetic_decimal_expr_test / arithmetic_divide_zero):
+ *   - both operands of a binary node are Decimal128 (the planner's coercion inserted the CASTs, type_coercion/binary.rs:1257);
+ *     comparisons need equal (precision, scale);
+ *   - PLUS / MINUS : scale max(s1, s2), precision min(38, scale + max(p1 - s1, p2 - s2) + 1); operands rescaled by 10^(scale - s_i)
+ *   - MULTIPLY     : precision min(38, p1 + p2 + 1), scale s1 + s2
+ *   - DIVIDE       : scale min(38, s1 + 4), precision min(38, p1 + scale - s1 + s2); (l * 10^(scale - s1 + s2)) / r, truncating
+ *   - MODULO       : scale max(s1, s2), precision min(38, scale + min(p1 - s1, p2 - s2))
+ *   every step is checked on the 128-bit value: overflow = "Arithmetic overflow", zero divisor = "Divide by zero" (DFGPU_ERR_ARITH);
+ *   - CAST int -> decimal, decimal -> decimal (rescale, round half away from zero, precision checked), decimal -> int
+ *     (truncating), decimal <-> float64 (scale <= 22). */
 
 /* ===================================================================================== */
 /* FilterExec (physical-plan/src/filter.rs:85; hot loop poll_next :1364-1445)             */
@@ -489,6 +510,29 @@ void dfgpu_partition_plan_destroy(dfgpu_partition_plan* plan);
 int dfgpu_ipc_export(dfgpu_ctx* ctx, void* dev_ptr, uint8_t* handle_out);
 int dfgpu_ipc_import(dfgpu_ctx* ctx, const uint8_t* handle, void** peer_ptr_out);
 int dfgpu_ipc_close(dfgpu_ctx* ctx, void* peer_ptr);
+
+/* ===================================================================================== */
+/* dictionary-coded string keys.  The reference joins / groups on Utf8, Utf8View and Dictionary(_, Utf8) columns by hashing and
+ * comparing bytes (common/src/hash_utils.rs create_hashes; aggregates/group_values/mod.rs:139-217 GroupValuesBytes /
+ * GroupValuesBytesView; the TPC-H string columns, benchmarks/src/tpch/mod.rs:52-122).  On the GPU path a string key is an INT32
+ * code — every integer-key operator applies — provided all batches (and both join sides) share ONE code space.  Arrow
+ * dictionaries are per batch: a dfgpu_dictionary unifies them on the host (the distinct values are few next to the rows),
+ * dfgpu_dictionary_remap rewrites a batch's codes on the device.  A literal (`c_mktsegment = 'BUILDING'`) becomes
+ * `codes = dfgpu_dictionary_code(...)`; a string never seen matches nothing (-1).               */
+/* ===================================================================================== */
+typedef struct dfgpu_dictionary dfgpu_dictionary;
+int dfgpu_dictionary_create(dfgpu_ctx* ctx, dfgpu_dictionary** out);
+/* merge one batch's dictionary values (Arrow Utf8 layout: offsets[n_values + 1], data; validity = LSB bitmap or NULL) into the
+ * unified dictionary; remap_out[i] = unified code of local value i, -1 for a NULL value.  Host-side. */
+int dfgpu_dictionary_unify(dfgpu_dictionary* d, const int32_t* offsets, const uint8_t* data, const uint8_t* validity, int64_t n_values, int32_t* remap_out);
+int32_t dfgpu_dictionary_code(dfgpu_dictionary* d, const uint8_t* bytes, int64_t len);   /* -1 = not present */
+int64_t dfgpu_dictionary_size(dfgpu_dictionary* d);
+int dfgpu_dictionary_value(dfgpu_dictionary* d, int32_t code, const uint8_t** bytes, int64_t* len);   /* valid until the next unify */
+/* codes: the batch's keys column (any integer type; host buffers when codes_on_host != 0, else device pointers); out: one INT32
+ * device column with out[i] = remap[codes[i]], NULL where the input is NULL or the dictionary value is NULL.  A code outside
+ * [0, n_remap) is DFGPU_ERR_INVALID. */
+int dfgpu_dictionary_remap(dfgpu_dictionary* d, const dfgpu_column* codes, int codes_on_host, const int32_t* remap, int64_t n_remap, dfgpu_batch** out);
+void dfgpu_dictionary_destroy(dfgpu_dictionary* d);
 
 /* ===================================================================================== */
 /* multi-GPU control inside the ABI (one process or thread per GPU of ONE box): what a Rust host needs to drive the partition

@@ -223,7 +223,43 @@ def hash_join(build: Sequence[Col], probe: Sequence[Col], on_build: Sequence[int
 def group_by(keys: Sequence[Col], aggs: Sequence[tuple], merge: bool = False, batch_size: int = 8192, force_collisions: bool = False):
     """aggs: [(func, arg: Col | None, filter: Col | None)]   (merge: [(func, state_col(s)...)] with arg = count/sum state;
     AVG merge passes arg=(count col) and a 4th element (sum col)).
-    Returns (group key columns in FIRST-SEEN order, [per aggregate dict(i=, f=, c=, valid=)])."""
+    Returns (group key columns in FIRST-SEEN order, [per aggregate dict(i=, f=, c=, valid=)]).
+    A SUM over a Decimal128 column (`Dec`) is i128 add_wrapping (sum.rs:316 with Decimal128Type): restated as three 64-bit wrapping sums over
+    the limbs lo & 0xffffffff, lo >> 32 and hi, recombined mod 2^128; its result dict carries dec=Dec(..., min(38, p + 10), s)
+    (Sum::return_type, sum.rs:247-249; merge keeps the state's own type)."""
+    if any(len(ag) > 1 and ag[1] is not None and isinstance(ag[1][0], Dec) for ag in aggs):
+        flat, where = [], []
+        for ag in aggs:
+            arg = ag[1] if len(ag) > 1 else None
+            if arg is not None and isinstance(arg[0], Dec):
+                d, val = arg
+                filt = ag[2] if len(ag) > 2 else None
+                if ag[0] == A_SUM:
+                    u = [int(x) % (1 << 128) for x in d]
+                    limbs = [np.array([x & 0xffffffff for x in u], np.int64), np.array([(x >> 32) & 0xffffffff for x in u], np.int64),
+                             np.array([x >> 64 for x in u], np.uint64).view(np.int64)]
+                    where.append(("dec", len(flat), d.p if merge else min(38, d.p + 10), d.s))
+                    flat += [(A_SUM, (l, val), filt) for l in limbs]
+                elif ag[0] in (A_COUNT, A_COUNT_STAR):
+                    where.append(("one", len(flat)))
+                    flat.append((ag[0], (np.zeros(len(d), np.int64), val), filt))
+                else:
+                    raise NotImplementedError("oracle: only SUM / COUNT over Decimal128")
+            else:
+                where.append(("one", len(flat)))
+                flat.append(ag)
+        out_keys, res = group_by(keys, flat, merge=merge, batch_size=batch_size, force_collisions=force_collisions)
+        out = []
+        for w in where:
+            if w[0] == "one":
+                out.append(res[w[1]])
+            else:
+                _, at, pp, ss = w
+                l0, l1, hi = res[at]["i"], res[at + 1]["i"], res[at + 2]["i"].view(np.uint64)
+                tot = [(int(a) + (int(b) << 32) + (int(c) << 64)) % (1 << 128) for a, b, c in zip(l0, l1, hi)]
+                tot = [x - (1 << 128) if x >= (1 << 127) else x for x in tot]
+                out.append(dict(dec=Dec(tot, pp, ss), valid=res[at]["valid"], i=None, f=None, c=None))
+        return out_keys, out
     L = lib()
     nk = len(keys)
     n = len(keys[0][0]) if nk else 0
@@ -291,6 +327,8 @@ def agg_output_columns(func: int, r: dict, arg_dtype, state: bool) -> List[Col]:
     """Shape one aggregate's oracle result like AggregateExec's output (state() or evaluate())."""
     def nv(v):
         return None if v.all() else v
+    if func == A_SUM and r.get("dec") is not None:
+        return [(r["dec"], nv(r["valid"]))]
     if func == A_SUM:
         if np.dtype(arg_dtype).kind == "f":
             return [(r["f"], nv(r["valid"]))]
@@ -391,6 +429,147 @@ def partial_aggregate_with_skip(key_batches: Sequence[Sequence[Col]], arg_batche
  OP_IS_DISTINCT_FROM, OP_IS_NOT_DISTINCT_FROM, OP_BITAND, OP_BITOR, OP_BITXOR, OP_SHIFT_LEFT, OP_SHIFT_RIGHT) = range(1, 21)
 
 
+class ArrowArithmeticOverflow(ArithmeticError):
+    """ArrowError::ArithmeticOverflow (checked i128 arithmetic of Decimal128 operands)"""
+
+
+# ---------------------------------------------------------------------------------------------
+# Decimal128 (arrow-arith 59.2.0 arithmetic.rs `decimal_op`, arrow-cast 59.2.0 cast/decimal.rs — third-party crates pinned by the
+# reference's Cargo.lock and absent from /root/reference: their published algorithm is restated here; pinned by the reference's own
+# vectors binary.rs:4355-5000 in tests/test_oracle_decimal.py)
+# ---------------------------------------------------------------------------------------------
+class Dec(np.ndarray):
+    """Decimal128Array values: unscaled Python ints in an object ndarray + (precision p, scale s)"""
+
+    def __new__(cls, values, precision: int, scale: int):
+        vals = list(values)
+        obj = np.empty(len(vals), dtype=object)
+        obj[:] = [int(x) for x in vals]
+        obj = obj.view(cls)
+        obj.p, obj.s = int(precision), int(scale)
+        return obj
+
+    def __array_finalize__(self, obj):
+        self.p = getattr(obj, "p", None)
+        self.s = getattr(obj, "s", None)
+
+
+def _arr(v):
+    return v if isinstance(v, Dec) else np.asarray(v)
+
+
+def decimal_dtype(p: int, s: int):
+    """the `dt` of a Decimal128 literal / cast target node"""
+    return ("decimal128", int(p), int(s))
+
+
+_I128_MIN, _I128_MAX = -(1 << 127), (1 << 127) - 1
+
+
+def _chk128(x: int) -> int:
+    if not (_I128_MIN <= x <= _I128_MAX):
+        raise ArrowArithmeticOverflow("Arithmetic overflow")
+    return x
+
+
+def _tdiv(a: int, b: int) -> int:      # Rust's `/` on integers truncates toward zero
+    q = abs(a) // abs(b)
+    return q if (a < 0) == (b < 0) else -q
+
+
+def decimal_result_type(op: int, p1: int, s1: int, p2: int, s2: int):
+    """(precision, scale, l_exp, r_exp) of `decimal_op`: operands are multiplied by 10^l_exp / 10^r_exp before the operation"""
+    if op in (OP_PLUS, OP_MINUS):
+        rs = max(s1, s2)
+        return min(38, rs + max(p1 - s1, p2 - s2) + 1), rs, rs - s1, rs - s2
+    if op == OP_MULTIPLY:
+        return min(38, p1 + p2 + 1), s1 + s2, 0, 0
+    if op == OP_DIVIDE:
+        rs = min(38, s1 + 4)                       # "a fixed scale increment of 4"
+        mul_pow = rs - s1 + s2
+        return min(38, mul_pow + p1), rs, max(mul_pow, 0), max(-mul_pow, 0)
+    if op == OP_MODULO:
+        rs = max(s1, s2)
+        return min(38, rs + min(p1 - s1, p2 - s2)), rs, rs - s1, rs - s2
+    raise ValueError(op)
+
+
+def _dec_binary(op: int, l: "Dec", r: "Dec", act: np.ndarray):
+    n = len(l)
+    if op in (OP_EQ, OP_NEQ, OP_LT, OP_LTEQ, OP_GT, OP_GTEQ):
+        assert (l.p, l.s) == (r.p, r.s), "Decimal128 comparison needs equal precision and scale (the planner coerces)"
+        f = {OP_EQ: int.__eq__, OP_NEQ: int.__ne__, OP_LT: int.__lt__, OP_LTEQ: int.__le__, OP_GT: int.__gt__, OP_GTEQ: int.__ge__}[op]
+        return np.array([bool(f(int(a), int(b))) for a, b in zip(l, r)], bool) if n else np.zeros(0, bool)
+    rp, rs, le, re = decimal_result_type(op, l.p, l.s, r.p, r.s)
+    lm, rm = 10 ** le, 10 ** re
+    out = []
+    for i in range(n):
+        if not act[i]:
+            out.append(0); continue
+        x, y = _chk128(int(l[i]) * lm), _chk128(int(r[i]) * rm)
+        if op == OP_PLUS: z = x + y
+        elif op == OP_MINUS: z = x - y
+        elif op == OP_MULTIPLY: z = x * y
+        else:
+            if y == 0:
+                raise ArrowDivideByZero("Divide by zero error")
+            q = _tdiv(x, y)
+            z = q if op == OP_DIVIDE else x - q * y
+        out.append(_chk128(z))
+    return Dec(out, rp, rs)
+
+
+def _dec_fits(x: int, precision: int) -> bool:
+    return abs(x) < 10 ** precision
+
+
+def _dec_cast(v, val, n, tgt):
+    """CastExpr with a Decimal128 on either side (CastOptions safe = false: failures are errors)"""
+    act = np.ones(n, bool) if val is None else np.asarray(val, bool)
+    if isinstance(tgt, tuple):
+        _, p, sc = tgt
+        out = []
+        for i in range(n):
+            if not act[i]:
+                out.append(0); continue
+            if isinstance(v, Dec):
+                x = int(v[i])
+                if sc >= v.s:
+                    x = x * 10 ** (sc - v.s)
+                else:                                   # convert_to_smaller_scale_decimal: round half away from zero
+                    div = 10 ** (v.s - sc); half = div // 2
+                    d = _tdiv(x, div); rem = x - d * div
+                    x = (d + 1 if rem >= half else d) if x >= 0 else (d - 1 if rem <= -half else d)
+            elif np.asarray(v).dtype.kind == "f":
+                prod = np.float64(v[i]) * np.float64(10.0 ** sc) if sc <= 22 else None
+                if prod is None or not np.isfinite(prod):
+                    raise ArrowCastError("Cannot cast to Decimal128")
+                t = np.trunc(prod)                            # f64::round: half away from zero (np.round would round half to even)
+                m = float(t + np.copysign(1.0, prod)) if abs(prod - t) >= 0.5 else float(t)
+                x = int(abs(m)); x = -x if m < 0 else x
+            else:
+                x = int(v[i]) * 10 ** sc
+            if not _dec_fits(x, p) or not (_I128_MIN <= x <= _I128_MAX):
+                raise ArrowCastError(f"{x} is too large to store in a Decimal128 of precision {p}")
+            out.append(x)
+        return Dec(out, p, sc), val
+    tgt = np.dtype(tgt)
+    assert isinstance(v, Dec)
+    if tgt.kind == "f":
+        with np.errstate(all="ignore"):
+            r = np.array([float(np.float64(int(x)) / np.float64(10.0 ** v.s)) for x in v], np.float64).astype(tgt)   # `x as f64 / 10f64.powi(s)`
+        return np.where(act, r, 0).astype(tgt), val
+    info = np.iinfo(tgt)
+    out = np.zeros(n, tgt)
+    for i in range(n):
+        if act[i]:
+            q = _tdiv(int(v[i]), 10 ** v.s)
+            if not (info.min <= q <= info.max):
+                raise ArrowCastError("Can't cast value to the target type")
+            out[i] = q
+    return out, val
+
+
 class ArrowDivideByZero(ArithmeticError):
     pass
 
@@ -454,7 +633,7 @@ def eval_expr(cols: Sequence[Col], nodes: Sequence[tuple], col_dtypes: Optional[
             rare = tc if is_and else n - tc
             if np.float32(rare) / np.float32(n) <= PRE_SELECTION_THRESHOLD:
                 mask = np.asarray(lv, bool) if is_and else ~np.asarray(lv, bool)
-                sel = [(np.asarray(v)[mask], None if val is None else np.asarray(val, bool)[mask]) for v, val in cs]
+                sel = [(_arr(v)[mask], None if val is None else np.asarray(val, bool)[mask]) for v, val in cs]
                 rv, rval = ev(rlo, hi - 1, sel)
                 out = np.full(n, not is_and, bool)                           # fill_value: false for AND, true for OR
                 out[mask] = np.asarray(rv, bool)
@@ -486,9 +665,12 @@ def _eval_flat(cols: Sequence[Col], nodes: Sequence[tuple]) -> Col:
     for kind, a, dt, is_null, lit in nodes:
         if kind == E_COLUMN:
             v, val = cols[a]
-            st.append((np.asarray(v), None if val is None else np.asarray(val, bool)))
+            st.append((_arr(v), None if val is None else np.asarray(val, bool)))
         elif kind == E_LITERAL:
-            arr = np.full(n, 0 if is_null else lit, dtype=dt)
+            if isinstance(dt, tuple):
+                arr = Dec([0 if is_null else int(lit)] * n, dt[1], dt[2])
+            else:
+                arr = np.full(n, 0 if is_null else lit, dtype=dt)
             st.append((arr, np.zeros(n, bool) if is_null else None))
         elif kind == E_BINARY:
             (rv, rval), (lv, lval) = st.pop(), st.pop()
@@ -506,6 +688,20 @@ def _eval_flat(cols: Sequence[Col], nodes: Sequence[tuple]) -> Col:
                     res_t, res_f = lt | rt, lf & rf
                 valid = res_t | res_f
                 st.append((res_t, None if valid.all() else valid))
+            elif isinstance(lv, Dec) or isinstance(rv, Dec):
+                assert isinstance(lv, Dec) and isinstance(rv, Dec), "a Decimal128 operand needs a Decimal128 partner (the planner's coercion casts the other side)"
+                act = np.ones(n, bool) if both is None else both
+                if a in (OP_IS_DISTINCT_FROM, OP_IS_NOT_DISTINCT_FROM):
+                    lvv = np.ones(n, bool) if lval is None else lval
+                    rvv = np.ones(n, bool) if rval is None else rval
+                    ne = _dec_binary(OP_NEQ, lv, rv, act)
+                    distinct = (lvv != rvv) | (lvv & rvv & ne)
+                    st.append((distinct if a == OP_IS_DISTINCT_FROM else ~distinct, None))
+                else:
+                    r = _dec_binary(a, lv, rv, act)
+                    if not isinstance(r, Dec) and both is not None:
+                        r = r & both
+                    st.append((r, both))
             elif a in (OP_EQ, OP_NEQ, OP_LT, OP_LTEQ, OP_GT, OP_GTEQ, OP_IS_DISTINCT_FROM, OP_IS_NOT_DISTINCT_FROM):
                 if lv.dtype.kind == "f":
                     x, y = _total_order_key(lv), _total_order_key(rv)
@@ -570,10 +766,16 @@ def _eval_flat(cols: Sequence[Col], nodes: Sequence[tuple]) -> Col:
             st.append((np.ones(n, bool) if val is None else val.copy(), None))
         elif kind == E_NEGATIVE:
             v, val = st.pop()
+            if isinstance(v, Dec):       # neg_wrapping
+                st.append((Dec([((-int(x) + (1 << 127)) % (1 << 128)) - (1 << 127) for x in v], v.p, v.s), val))
+                continue
             with np.errstate(all="ignore"):
                 st.append((-v, val))
         elif kind == E_CAST:
             v, val = st.pop()
+            if isinstance(v, Dec) or isinstance(dt, tuple):
+                st.append(_dec_cast(v, val, n, dt))
+                continue
             tgt = np.dtype(dt)
             act = np.ones(n, bool) if val is None else np.asarray(val, bool)
             if tgt.kind in "iu" and v.dtype.kind in "iuf":
@@ -628,7 +830,7 @@ def filter_batch(cols: Sequence[Col], pred: Col, projection: Optional[Sequence[i
     for i in proj:
         v, val = cols[i]
         nv = None if val is None else np.asarray(val, bool)[keep]
-        out.append((np.asarray(v)[keep], None if nv is None or nv.all() else nv))
+        out.append((_arr(v)[keep], None if nv is None or nv.all() else nv))
     return out
 
 
