@@ -250,6 +250,47 @@ def boundary_costs(ctx, D):
     return out
 
 
+def q3_decimal_money(ctx, D, Q, cu, orr, li, sf, peak):
+    """the headline plan over the reference's real money types (benchmarks/src/tpch/mod.rs:52-122): l_extendedprice, l_discount as
+    Decimal128(15,2), sum(l_extendedprice * (1 - l_discount)) as Decimal128(38,4) — 128-bit checked arithmetic per row, two accumulator
+    words per group.  The unscaled sums equal the int64 variant's, so the same fingerprint pins it at the timed size."""
+    dl = Q.decimal_money(ctx, li)
+    e0, e1 = ctx.event(), ctx.event()
+
+    def step(keep=False):
+        res, st = Q.run_q3_fused(ctx, cu, orr, dl)
+        if keep:
+            return res, st
+        for b in res:
+            b.release()
+        return None, st
+    for _ in range(2):
+        step()
+    ctx.set_kernel_timing(True); ctx.kernel_time_reset()
+    ctx.record(e0)
+    for _ in range(5):
+        step()
+    ctx.record(e1)
+    ms = ctx.elapsed_ms(e0, e1) / 5
+    kms, kn = ctx.kernel_time("pipe:lineitem")
+    ctx.set_kernel_timing(False)
+    res, st = step(keep=True)
+    assert res[0].column(3).type == D.decimal128(38, 4), "SUM over Decimal128(38,4) keeps (38,4)"
+    fp = Q.result_fingerprint(ctx, res)
+    for b in res:
+        b.release()
+    if sf == 100:
+        assert fp == Q3_FINGERPRINT_SF100, f"Q3 SF100 (Decimal128 money) fingerprint {fp} != {Q3_FINGERPRINT_SF100}"
+    nl = dl.rows
+    algo = 44.0 * nl                      # lineitem: 8 + 16 + 16 + 4 B per row
+    k = kms / max(kn, 1)
+    rows = cu.rows + orr.rows + nl
+    return {"ms_per_step": ms, "rows_per_s": rows / (ms / 1000.0), "lineitem_kernel_ms": k, "achieved_gbs": algo / (k / 1000.0) / 1e9 if k > 0 else None,
+            "frac": algo / (k / 1000.0) / 1e9 / peak if k > 0 else None, "fingerprint": fp, "groups": st["groups"],
+            "verified": "group count + wrapping sums of every result column (Decimal128: low word + 3 x high word) == the CPU restatement's fingerprint of the same tables" if sf == 100 else "type check only (fingerprint pinned at SF100)",
+            "note": "l_extendedprice, l_discount Decimal128(15,2); sum(l_extendedprice * (Some(1),20,0 - l_discount)) -> Decimal128(38,4): checked i128 arithmetic on the 128-bit interpreter (expr_dec.cuh), i128 add_wrapping as two 64-bit atomics"}
+
+
 def secondary_configs(ctx, D, peak):
     out = {}
     col = lambda buf, n: D.DeviceColumn(ctx, D.INT64, n, buf)
@@ -647,6 +688,13 @@ def main():
         for b in last.get("res", []):
             b.release()
         last.clear()
+        dec_block = None
+        try:
+            dec_block = q3_decimal_money(ctx, D, Q, cu, orr, li, sf, peak)
+        except AssertionError:
+            raise
+        except Exception as exc:
+            dec_block = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         del cu, orr, li          # 20.6 GB of tables: make room for the 16 GB group-by input
         try:
             line["e2e"]["boundary_costs"] = boundary_costs(ctx, D)
@@ -658,6 +706,7 @@ def main():
             raise
         except Exception as exc:
             line["roofline"]["secondary"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        line["roofline"]["secondary"]["C4_q3_decimal128_money"] = dec_block
 
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -69,6 +69,7 @@ __device__ __forceinline__ bool load_group_key(const GroupCols& g, int64_t row, 
         case 1: v = ((const uint8_t*)g.ptr[c])[row]; break;
         case 2: v = ((const uint16_t*)g.ptr[c])[row]; break;
         case 4: v = ((const uint32_t*)g.ptr[c])[row]; if (g.is_float[c] && (v & 0x7FFFFFFFull) == 0) v = 0; break;  // f32 -0.0 -> +0.0
+        case 16: k.lo |= ((const uint64_t*)g.ptr[c])[2 * row]; k.hi |= ((const uint64_t*)g.ptr[c])[2 * row + 1]; continue;   // Decimal128: the whole 128-bit key (single group column)
         default: v = ((const uint64_t*)g.ptr[c])[row]; if (g.is_float[c] && (v << 1) == 0) v = 0; break;     // f64 -0.0 -> +0.0
       }
       key_or(k, v, g.shift[c]);
@@ -487,6 +488,7 @@ __global__ void __launch_bounds__(256) agg_emit_kernel(EmitDesc d, const uint32_
             bool isnull = d.null_bit < 64 ? ((lo >> d.null_bit) & 1) : ((hi >> (d.null_bit - 64)) & 1);
             if (isnull) { ok = false; break; }
           }
+          if (d.width_bits == 128) { ((unsigned long long*)out)[2 * i] = lo; ((unsigned long long*)out)[2 * i + 1] = hi; break; }   // Decimal128 key
           if (d.shift < 64) {
             bits = lo >> d.shift;
             if (d.shift > 0 && d.shift + d.width_bits > 64) bits |= hi << (64 - d.shift);
@@ -525,7 +527,8 @@ __global__ void __launch_bounds__(256) agg_emit_kernel(EmitDesc d, const uint32_
       }
       if (!ok) bits = 0;
       if (d.out_type == DFGPU_BOOL) bval = bits & 1;
-      else if (d.kind != EK_DEC128) store_typed(out, d.out_type, i, bits);
+      else if (type_width(d.out_type) == 16) { if (!ok) { ((unsigned long long*)out)[2 * i] = 0ull; ((unsigned long long*)out)[2 * i + 1] = 0ull; } }   // 16-byte values were stored above
+      else store_typed(out, d.out_type, i, bits);
     }
     uint32_t vw = __ballot_sync(0xffffffffu, ok);
     uint32_t bw = __ballot_sync(0xffffffffu, bval);
@@ -1127,7 +1130,7 @@ int dfgpu_agg_create(dfgpu_ctx* ctx, const int32_t* input_types, int32_t n_cols,
     DF_CHECK(group_cols[c] >= 0 && group_cols[c] < n_cols, DFGPU_ERR_INVALID, "group column index out of range");
     int t = input_types[group_cols[c]];
     int w = type_width(t);
-    DF_CHECK(w >= 0 && w <= 8, DFGPU_ERR_UNSUPPORTED, "aggregate: group column type not supported");
+    DF_CHECK((w >= 0 && w <= 8) || (w == 16 && n_group == 1), DFGPU_ERR_UNSUPPORTED, "aggregate: group column type not supported (a 16-byte Decimal128 key must be the only group column)");
     int wb = (t == DFGPU_BOOL) ? 1 : 8 * w;
     a->g_shift.push_back(bits);
     a->g_width_bits.push_back(wb);

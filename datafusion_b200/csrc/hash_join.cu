@@ -1136,11 +1136,79 @@ struct dfgpu_hashjoin {
   // metrics (BuildProbeJoinMetrics, joins/utils.rs:1756-1778)
   int64_t m_build_rows = 0, m_build_batches = 0, m_input_rows = 0, m_input_batches = 0, m_output_rows = 0, m_output_batches = 0,
           m_array_map = 0, m_probe_hits = 0, m_radix_probes = 0;
+  // wide keys (> 64 bits together, or a 16-byte Decimal128 key): the table is keyed by a 64-bit hash of the key columns (a hidden INT64
+  // column appended to both sides) and key equality becomes a conjunct of the JoinFilter — the reference's own scheme: lookup by hash,
+  // then equal_rows_arr on the candidate pairs (joins/utils.rs:2191-2257, hash_join/stream.rs lookup_join_hashmap)
+  bool wide = false;
+  std::vector<int> wide_on_build, wide_on_probe;
+  std::vector<dfgpu_expr_node> wide_expr;   // (kb0 = kp0) AND (kb1 = kp1) ... over intermediate columns 0 .. 2 n_keys - 1
   bool probe_side_non_empty = false;
   bool probe_has_null = false;   // null-aware LeftAnti: a NULL probe key was seen (JoinLeftData::probe_side_has_null)
 };
 
 namespace dfgpu {
+
+// ---- wide keys: one 64-bit hash per row over all key columns -------------------------------------------------------------------
+constexpr int kMaxWideKeys = 8;
+struct WideKeyCols { int n; const void* ptr[kMaxWideKeys]; const uint8_t* valid[kMaxWideKeys]; int64_t voff[kMaxWideKeys]; int width[kMaxWideKeys], is_float[kMaxWideKeys]; };
+__global__ void __launch_bounds__(256) wide_key_kernel(WideKeyCols kc, int64_t n, int null_equals_null, unsigned long long* __restrict__ out, uint32_t* __restrict__ out_valid) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = (n + 31) / 32;
+  for (int64_t wi = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; wi < nw; wi += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int64_t row = wi * 32 + lane;
+    bool ok = row < n;
+    if (row < n) {
+      uint64_t h = kSeedJoin;
+#pragma unroll 1
+      for (int c = 0; c < kc.n; ++c) {
+        if (kc.valid[c] && !bit_get(kc.valid[c], kc.voff[c] + row)) {
+          if (null_equals_null) { h = hash_combine(h, 0x6E756C6Cull); continue; }   // NULL joins NULL: one fixed token per NULL key
+          ok = false; break;                                                          // a NULL key never matches (utils.rs:2146-2155)
+        }
+        uint64_t v, v2 = 0;
+        switch (kc.width[c]) {
+          case 0: v = bit_get((const uint8_t*)kc.ptr[c], kc.voff[c] + row) ? 1ull : 0ull; break;
+          case 1: v = ((const uint8_t*)kc.ptr[c])[row]; break;
+          case 2: v = ((const uint16_t*)kc.ptr[c])[row]; break;
+          case 4: v = ((const uint32_t*)kc.ptr[c])[row]; if (kc.is_float[c] && (v & 0x7FFFFFFFull) == 0) v = 0; break;   // -0.0 = +0.0
+          case 16: v = ((const uint64_t*)kc.ptr[c])[2 * row]; v2 = ((const uint64_t*)kc.ptr[c])[2 * row + 1]; break;
+          default: v = ((const uint64_t*)kc.ptr[c])[row]; if (kc.is_float[c] && (v << 1) == 0) v = 0; break;
+        }
+        h = hash_combine(h, v);
+        if (kc.width[c] == 16) h = hash_combine(h, v2);
+      }
+      if (h == kEmpty64) h = 0x5bd1e995ull;      // the table's empty marker is not a key
+      out[row] = ok ? h : 0ull;
+    }
+    const uint32_t b = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0 && out_valid) out_valid[wi] = b;
+  }
+}
+
+// the hidden key column of one batch
+static DCol wide_key_column(dfgpu_hashjoin* j, const std::vector<DCol>& cols, const std::vector<int>& on) {
+  dfgpu_ctx* ctx = j->ctx;
+  set_device(ctx);
+  const int64_t n = cols.empty() ? 0 : cols[0].length;
+  WideKeyCols kc;
+  memset(&kc, 0, sizeof(kc));
+  kc.n = (int)on.size();
+  bool any_valid = false;
+  for (int c = 0; c < kc.n; ++c) {
+    const DCol& col = cols[on[c]];
+    kc.ptr[c] = col.values; kc.valid[c] = col.validity; kc.voff[c] = col.offset; kc.width[c] = type_width(col.type); kc.is_float[c] = type_is_float(col.type) ? 1 : 0;
+    any_valid = any_valid || col.validity != nullptr;
+  }
+  const bool nen = j->opt.null_equality == DFGPU_NULL_EQUALS_NULL;
+  DCol out = alloc_col(ctx, DFGPU_INT64, n, any_valid && !nen);
+  if (n > 0) {
+    wide_key_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(kc, n, nen ? 1 : 0, (unsigned long long*)out.own_values->ptr,
+                                                                         out.own_validity ? out.own_validity->as<uint32_t>() : nullptr);
+    DF_LAUNCH_CHECK(ctx);
+  }
+  out.null_count = (any_valid && !nen) ? -1 : 0;
+  return out;
+}
 
 static void make_keycols(const std::vector<DCol>& cols, const std::vector<int>& on, KeyCols* kc) {
   memset(kc, 0, sizeof(*kc));
@@ -1160,23 +1228,54 @@ static void make_keycols(const std::vector<DCol>& cols, const std::vector<int>& 
 
 static void check_join_keys(dfgpu_hashjoin* j) {
   int bits = 0;
-  DF_CHECK(!j->on_build.empty() && j->on_build.size() <= kMaxKeys, DFGPU_ERR_UNSUPPORTED, "hash join: 1..4 key columns supported");
+  bool wide = false;
+  DF_CHECK(!j->on_build.empty(), DFGPU_ERR_INVALID, "hash join: at least one key column");
   for (size_t c = 0; c < j->on_build.size(); ++c) {
     int bt = j->build_types[j->on_build[c]], pt = j->probe_types[j->on_probe[c]];
     DF_CHECK(type_width(bt) == type_width(pt) && type_is_float(bt) == type_is_float(pt) &&
                  type_is_signed_int(bt) == type_is_signed_int(pt),
              DFGPU_ERR_INVALID, "hash join: key types differ between build and probe side");
+    if (type_is_decimal(bt)) DF_CHECK(bt == pt, DFGPU_ERR_INVALID, "hash join: Decimal128 key columns need equal precision and scale on both sides");
     int w = type_width(bt);
-    DF_CHECK(w >= 1 && w <= 8, DFGPU_ERR_UNSUPPORTED, "hash join: key type must be a fixed-width type of <= 64 bits");
+    DF_CHECK(w >= 0 && w <= 16, DFGPU_ERR_UNSUPPORTED, "hash join: key type must be a fixed-width type");
+    if (w == 16 || w == 0) wide = true;
     bits += 8 * w;
   }
-  DF_CHECK(bits <= 64, DFGPU_ERR_UNSUPPORTED, "hash join: key columns wider than 64 bits together are not supported yet");
+  if (bits > 64 || j->on_build.size() > (size_t)kMaxKeys) wide = true;
+  if (wide) {
+    // keys that do not fit the exact 64-bit tag: hash + equality conjunct (see dfgpu_hashjoin::wide)
+    DF_CHECK(j->on_build.size() <= (size_t)kMaxWideKeys, DFGPU_ERR_UNSUPPORTED, "hash join: at most 8 key columns");
+    DF_CHECK(!j->opt.null_aware, DFGPU_ERR_UNSUPPORTED, "hash join: null-aware anti join on a key wider than 64 bits stays on the CPU operator");
+    j->wide = true;
+    j->wide_on_build = j->on_build; j->wide_on_probe = j->on_probe;
+    const int nk = (int)j->on_build.size();
+    std::vector<int32_t> types;
+    for (int c = 0; c < nk; ++c) {
+      j->filt_side.push_back(0); j->filt_index.push_back(j->wide_on_build[c]); types.push_back(j->build_types[j->wide_on_build[c]]);
+      j->filt_side.push_back(1); j->filt_index.push_back(j->wide_on_probe[c]); types.push_back(j->probe_types[j->wide_on_probe[c]]);
+    }
+    const int eq = j->opt.null_equality == DFGPU_NULL_EQUALS_NULL ? DFGPU_OP_IS_NOT_DISTINCT_FROM : DFGPU_OP_EQ;
+    auto node = [](int kind, int a) { dfgpu_expr_node nd; memset(&nd, 0, sizeof(nd)); nd.kind = kind; nd.a = a; return nd; };
+    for (int c = 0; c < nk; ++c) {
+      j->wide_expr.push_back(node(DFGPU_EXPR_COLUMN, 2 * c));
+      j->wide_expr.push_back(node(DFGPU_EXPR_COLUMN, 2 * c + 1));
+      j->wide_expr.push_back(node(DFGPU_EXPR_BINARY, eq));
+      if (c > 0) j->wide_expr.push_back(node(DFGPU_EXPR_BINARY, DFGPU_OP_AND));
+    }
+    j->filt_plan = plan_expr(types.data(), (int)types.size(), j->wide_expr.data(), (int)j->wide_expr.size());
+    j->has_filter = true;
+    // the hidden hash-key column goes last on both sides and becomes the only `on` column
+    j->on_build.assign(1, (int)j->build_types.size()); j->on_probe.assign(1, (int)j->probe_types.size());
+    j->build_types.push_back(DFGPU_INT64); j->probe_types.push_back(DFGPU_INT64);
+    return;
+  }
   if (j->opt.null_equality == DFGPU_NULL_EQUALS_NULL)
-    DF_CHECK(j->on_build.size() == 1, DFGPU_ERR_UNSUPPORTED, "hash join: NullEqualsNull supported for single-column keys only");
+    DF_CHECK(j->on_build.size() == 1, DFGPU_ERR_UNSUPPORTED, "hash join: NullEqualsNull on several key columns takes the wide-key path (pass keys wider than 64 bits) or a single column");
 }
 
 static void push_build(dfgpu_hashjoin* j, std::vector<DCol>&& cols) {
   DF_CHECK(!j->built, DFGPU_ERR_STATE, "push_build after finish_build");
+  if (j->wide && cols.size() + 1 == j->build_types.size()) cols.push_back(wide_key_column(j, cols, j->wide_on_build));
   DF_CHECK(cols.size() == j->build_types.size(), DFGPU_ERR_INVALID, "build batch column count mismatch");
   int64_t rows = cols.empty() ? 0 : cols[0].length;
   for (size_t c = 0; c < cols.size(); ++c) {
@@ -1501,6 +1600,7 @@ static void push_probe_filtered(dfgpu_hashjoin* j, const std::vector<DCol>& cols
 static void push_probe(dfgpu_hashjoin* j, std::vector<DCol>&& cols) {
   DF_CHECK(j->built, DFGPU_ERR_STATE, "push_probe before finish_build");
   DF_CHECK(!j->probe_done, DFGPU_ERR_STATE, "push_probe after finish_probe");
+  if (j->wide && cols.size() + 1 == j->probe_types.size()) cols.push_back(wide_key_column(j, cols, j->wide_on_probe));
   DF_CHECK(cols.size() == j->probe_types.size(), DFGPU_ERR_INVALID, "probe batch column count mismatch");
   dfgpu_ctx* ctx = j->ctx;
   set_device(ctx);
@@ -2040,16 +2140,39 @@ int dfgpu_hashjoin_set_filter(dfgpu_hashjoin* j, const int32_t* col_side, const 
   DF_CHECK(!j->built && j->build_parts.empty(), DFGPU_ERR_STATE, "set_filter must be called before any batch is pushed");
   DF_CHECK(!(j->opt.null_aware && j->opt.join_type == DFGPU_JOIN_RIGHT_ANTI), DFGPU_ERR_INVALID, "null_aware RightAnti join does not support a join filter");
   std::vector<int32_t> types;
+  std::vector<int> fside, findex;
+  std::vector<dfgpu_expr_node> nodes;
+  int shift = 0;
+  if (j->wide) {   // key equality stays the first conjunct; the user's column references move behind the key columns
+    DF_CHECK(j->filt_side.size() == 2 * j->wide_on_build.size(), DFGPU_ERR_STATE, "set_filter called twice");
+    fside = j->filt_side; findex = j->filt_index;
+    for (size_t c = 0; c < fside.size(); ++c) types.push_back((fside[c] == 0 ? j->build_types : j->probe_types)[findex[c]]);
+    nodes = j->wide_expr;
+    shift = (int)fside.size();
+  }
   for (int c = 0; c < n_cols; ++c) {
     DF_CHECK(col_side[c] == 0 || col_side[c] == 1, DFGPU_ERR_INVALID, "join filter column side must be 0 (build) or 1 (probe)");
     const auto& tv = col_side[c] == 0 ? j->build_types : j->probe_types;
-    DF_CHECK(col_index[c] >= 0 && col_index[c] < (int)tv.size(), DFGPU_ERR_INVALID, "join filter column index out of range");
+    const int limit = (int)tv.size() - (j->wide ? 1 : 0);   // the hidden hash-key column is not addressable
+    DF_CHECK(col_index[c] >= 0 && col_index[c] < limit, DFGPU_ERR_INVALID, "join filter column index out of range");
     types.push_back(tv[col_index[c]]);
+    fside.push_back(col_side[c]); findex.push_back(col_index[c]);
   }
-  j->filt_plan = plan_expr(types.data(), n_cols, expr, n_nodes);
+  for (int i = 0; i < n_nodes; ++i) {
+    dfgpu_expr_node nd = expr[i];
+    if (nd.kind == DFGPU_EXPR_COLUMN) { DF_CHECK(nd.a >= 0 && nd.a < n_cols, DFGPU_ERR_INVALID, "join filter: column index out of range"); nd.a += shift; }
+    nodes.push_back(nd);
+  }
+  if (j->wide) { dfgpu_expr_node a; memset(&a, 0, sizeof(a)); a.kind = DFGPU_EXPR_BINARY; a.a = DFGPU_OP_AND; nodes.push_back(a); }
+  {
+    // the user's expression must be Boolean on its own
+    ExprPlan user = plan_expr(types.data() + shift, n_cols, expr, n_nodes);
+    DF_CHECK(user.root_type == DFGPU_BOOL, DFGPU_ERR_INVALID, "join filter expression must return Boolean");
+  }
+  j->filt_plan = plan_expr(types.data(), (int)types.size(), nodes.data(), (int)nodes.size());
   DF_CHECK(j->filt_plan.root_type == DFGPU_BOOL, DFGPU_ERR_INVALID, "join filter expression must return Boolean");
-  j->filt_side.assign(col_side, col_side + n_cols);
-  j->filt_index.assign(col_index, col_index + n_cols);
+  j->filt_side = fside;
+  j->filt_index = findex;
   j->has_filter = true;
   DF_API_END
 }

@@ -893,6 +893,7 @@ __global__ void __launch_bounds__(256) col_sum_kernel(ColRef c, int64_t n, unsig
       case 1: s += c.sgn ? (uint64_t)(int64_t)((const int8_t*)c.ptr)[i] : ((const uint8_t*)c.ptr)[i]; break;
       case 2: s += c.sgn ? (uint64_t)(int64_t)((const int16_t*)c.ptr)[i] : ((const uint16_t*)c.ptr)[i]; break;
       case 4: s += c.sgn ? (uint64_t)(int64_t)((const int32_t*)c.ptr)[i] : ((const uint32_t*)c.ptr)[i]; break;
+      case 16: s += ((const uint64_t*)c.ptr)[2 * i] + 3ull * ((const uint64_t*)c.ptr)[2 * i + 1]; break;   // Decimal128: low word + 3 x high word
       default: s += ((const uint64_t*)c.ptr)[i]; break;
     }
     cnt++;
@@ -1552,7 +1553,7 @@ int dfgpu_column_minmax_device(dfgpu_ctx* ctx, const dfgpu_column* col, int64_t*
 int dfgpu_column_sum_device(dfgpu_ctx* ctx, const dfgpu_column* col, uint64_t* sum_out, int64_t* valid_out) {
   DF_API_BEGIN(ctx)
   DF_CHECK(ctx && col && sum_out, DFGPU_ERR_INVALID, "null argument");
-  DF_CHECK(key_type_ok(col->type), DFGPU_ERR_UNSUPPORTED, "column sum: integer-like columns only");
+  DF_CHECK(key_type_ok(col->type) || type_is_decimal(col->type), DFGPU_ERR_UNSUPPORTED, "column sum: integer-like and Decimal128 columns only");
   set_device(ctx);
   DCol c = device_view(*col);
   DevBuf acc(ctx, 16);

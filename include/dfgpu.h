@@ -417,7 +417,8 @@ void dfgpu_lookup_destroy(dfgpu_lookup* l);
 /* min / max / non-null count of one integer column (device resident): feeds dfgpu_lookup_options.key_min/key_max */
 int dfgpu_column_minmax_device(dfgpu_ctx* ctx, const dfgpu_column* col, int64_t* min_out, int64_t* max_out, int64_t* valid_out);
 /* wrapping (mod 2^64) sum of the non-NULL values of an integer column, device resident: order-independent fingerprints of
- * results too large to compare row by row (SURVEY.md §8d "Large-config verification") */
+ * results too large to compare row by row (SURVEY.md §8d "Large-config verification"); a Decimal128 column contributes
+ * low word + 3 x high word per value */
 int dfgpu_column_sum_device(dfgpu_ctx* ctx, const dfgpu_column* col, uint64_t* sum_out, int64_t* valid_out);
 
 enum dfgpu_stage_kind {

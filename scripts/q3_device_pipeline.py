@@ -124,6 +124,30 @@ def run_q3(ctx, customer, orders, lineitem):
     return res, stages
 
 
+DEC_MONEY = D.decimal128(15, 2)     # l_extendedprice, l_discount in the TPC-H schema (benchmarks/src/tpch/mod.rs:52-122)
+
+
+def decimal_money(ctx, lineitem):
+    """the lineitem table with its money columns as Decimal128(15,2) — the reference's TPC-H schema — instead of int64 cents /
+    percent: CAST(int64 AS Decimal128(15,0)) on the device, relabelled at scale 2 (same unscaled integers)"""
+    cols, types, keep = list(lineitem.cols), list(lineitem.types), list(lineitem._keep)
+    for i in (1, 2):
+        b = D.evaluate_device(ctx, [lineitem.cols[i]], lineitem.rows, CAST(C(0), D.decimal128(15, 0)))
+        c = b.column(0)
+        c.type = DEC_MONEY
+        cols[i], types[i] = c, DEC_MONEY
+        keep.append(b)
+    return Table(lineitem.names, types, cols, lineitem.rows, keep)
+
+
+def revenue_expr(l_types):
+    """sum argument of q3.slt.part:62: l_extendedprice * (1 - l_discount); int64 money: price_cents * (100 - discount_percent)"""
+    if D.type_base(l_types[1]) == D.DECIMAL128:
+        one = [(D.EXPR_LITERAL, 0, D.decimal128(20, 0), 0, 1, 0.0)]          # Int64 literal coerced to Decimal128(20,0)
+        return B(D.OP_MULTIPLY, C(1), B(D.OP_MINUS, one, C(2)))             # -> Decimal128(38,4)
+    return B(D.OP_MULTIPLY, C(1), B(D.OP_MINUS, L(100), C(2)))
+
+
 def run_q3_fused(ctx, customer, orders, lineitem):
     """the same plan as three fused pipelines (dfgpu_pipeline): every table is read once, no intermediate batch touches HBM
 
@@ -140,14 +164,15 @@ def run_q3_fused(ctx, customer, orders, lineitem):
     p1.push_device(customer.cols); p1.finish()
     stages["customer_building"] = p1.metric("sink_rows")
     p1.close()
-    l2 = D.Lookup(ctx, D.INT64, [D.INT32, D.INT32], n_acc_words=2, membership_filter=-1)
+    dec = D.type_base(lineitem.types[1]) == D.DECIMAL128                 # a Decimal128 SUM takes two accumulator words
+    l2 = D.Lookup(ctx, D.INT64, [D.INT32, D.INT32], n_acc_words=3 if dec else 2, membership_filter=-1)
     p2 = D.Pipeline(ctx, orders.types, B(D.OP_LT, C(2), L(CUT, D.INT32)), [(D.STAGE_SEMI, 1, l1)], name="orders")
     p2.sink_build(l2, 0, [2, 3])
     p2.push_device(orders.cols); p2.finish()
     stages["orders_of_building_customers"] = p2.metric("sink_rows")
     p2.close()
     p3 = D.Pipeline(ctx, lineitem.types, B(D.OP_GT, C(3), L(CUT, D.INT32)), [(D.STAGE_INNER, 0, l2)], name="lineitem")
-    p3.sink_aggregate([0, 4, 5], [(D.AGG_SUM, B(D.OP_MULTIPLY, C(1), B(D.OP_MINUS, L(100), C(2))))], D.AGG_SINGLE_PARTITIONED)
+    p3.sink_aggregate([0, 4, 5], [(D.AGG_SUM, revenue_expr(lineitem.types))], D.AGG_SINGLE_PARTITIONED)
     p3.push_device(lineitem.cols); p3.finish()
     res = p3.drain(host=False)
     stages["joined_rows"] = p3.metric("sink_rows")

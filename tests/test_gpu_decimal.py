@@ -323,3 +323,32 @@ def test_fused_q3_with_decimal_money(gpu_ctx, nulls, mode):
     assert len(want) > 500
     assert got == want
     p.close(); l2.close(); l1.close()
+
+
+def test_gpu_group_by_decimal_key(gpu_ctx):
+    """GROUP BY one Decimal128 column: the 128-bit value is the key (incl. -1 = all ones, 0, wide values, one NULL group)"""
+    r = random.Random(16)
+    n = 30000
+    pool = [-1, 0, 1, 10 ** 30, -(10 ** 30), 12345, (1 << 100) + 7, -(1 << 100)] + [r.randint(-10 ** 37, 10 ** 37) for _ in range(40)]
+    keys = [pool[r.randrange(len(pool))] for _ in range(n)]
+    kvalid = np.array([r.random() > 0.03 for _ in range(n)], bool)
+    v = np.array([r.randint(-1000, 1000) for _ in range(n)], np.int64)
+    want = {}
+    for i in range(n):
+        k = keys[i] if kvalid[i] else None
+        s, c = want.get(k, (0, 0))
+        want[k] = (s + int(v[i]), c + 1)
+    h = D.AggHandle(gpu_ctx, [D.decimal128(38, 0), D.INT64], [0], [(D.AGG_SUM, 1, -1), (D.AGG_COUNT_STAR, -1, -1)], D.AGG_SINGLE)
+    for s in range(0, n, 8000):
+        e = min(n, s + 8000)
+        h.push_host([gpu_host_col(D, (O.Dec(keys[s:e], 38, 0), kvalid[s:e])), D.HostColumn(v[s:e])])
+    h.finish()
+    got = {}
+    for b in h.drain(host=True):
+        assert b.column(0).type == D.decimal128(38, 0)
+        k, s1, c1 = gpu_col_as_py(D, b, 0)[0], gpu_col_as_py(D, b, 1)[0], gpu_col_as_py(D, b, 2)[0]
+        for i in range(len(k)):
+            assert k[i] not in got
+            got[k[i]] = (s1[i], c1[i])
+    assert got == want and None in want and -1 in want
+    h.close()
