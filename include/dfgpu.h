@@ -292,7 +292,10 @@ void dfgpu_hashjoin_default_options(dfgpu_hashjoin_options* o);
 
 /* build = left child, probe = right child (exec.rs:768-776).  on_build/on_probe: key column indices.
  * out_side[j]/out_index[j]: output column j is column out_index[j] of side out_side[j]
- * (0 = build/left, 1 = probe/right, 2 = mark column) — ColumnIndex of joins/utils.rs:1332-1387. */
+ * (0 = build/left, 1 = probe/right, 2 = mark column) — ColumnIndex of joins/utils.rs:1332-1387.
+ * Keys: up to 4 columns of <= 64 bits together are stored exactly in the table (one probe = one compare); anything else — up to 8
+ * columns, wider together, a Decimal128 / Boolean key — is looked up by a hash of the key columns and verified on the candidate
+ * pairs like the reference's equal_rows_arr (joins/utils.rs:2191-2257): same results, generic probe path. */
 int dfgpu_hashjoin_create(dfgpu_ctx* ctx,
                           const int32_t* build_types, int32_t n_build_cols,
                           const int32_t* probe_types, int32_t n_probe_cols,
