@@ -254,6 +254,7 @@ def q3_decimal_money(ctx, D, Q, cu, orr, li, sf, peak):
     """the headline plan over the reference's real money types (benchmarks/src/tpch/mod.rs:52-122): l_extendedprice, l_discount as
     Decimal128(15,2), sum(l_extendedprice * (1 - l_discount)) as Decimal128(38,4) — 128-bit checked arithmetic per row, two accumulator
     words per group.  The unscaled sums equal the int64 variant's, so the same fingerprint pins it at the timed size."""
+    ctx.trim_device_cache()
     dl = Q.decimal_money(ctx, li)
     e0, e1 = ctx.event(), ctx.event()
 
@@ -293,6 +294,7 @@ def q3_decimal_money(ctx, D, Q, cu, orr, li, sf, peak):
 
 def secondary_configs(ctx, D, peak):
     out = {}
+    ctx.trim_device_cache()
     col = lambda buf, n: D.DeviceColumn(ctx, D.INT64, n, buf)
     e0, e1 = ctx.event(), ctx.event()
     # ---- C2: HashJoinExec inner 100M x 10M, sparse unique keys (hashbrown path of the reference), 100 % hit ----
@@ -351,6 +353,7 @@ def secondary_configs(ctx, D, peak):
     out["C2_join_100Mx10M_sparse_unique_radix_partitioned"] = {"ms_per_step": ms_r, "rows_per_s": (nb + npr) / ms_r * 1e3, "achieved_gbs": algo / ms_r / 1e6, "frac": algo / ms_r / 1e6 / peak,
                                                                "partition_ms": rp_ms / max(rp_n, 1), "probe_kernel_ms": pr_ms / max(pr_n, 1), "fingerprint": fp_r,
                                                                "note": "ordered_output = 0: probe side radix-partitioned on the top hash bits (TMA bulk loads / stores), per-partition probe with the sub-table L2-resident"}
+    ctx.trim_device_cache()   # every block starts from the same allocator state (its warm-up steps refill the cache)
     # ---- C2(ii) with a 10 % hit rate: probe keys drawn from a key set 10x the build side (ordered probe; the misses cost a lookup, no output) ----
     pk10 = ctx.generate_i64(D.GEN_SPARSE_OF, 42, 43, 10 * nb, 0, npr)
     probe10 = [col(pk10, npr), col(pp, npr)]
@@ -372,12 +375,13 @@ def secondary_configs(ctx, D, peak):
             b.release()
         j.close()
         return rows, fp
-    join10()
+    for _ in range(2):
+        join10()
     ctx.record(e0)
-    for _ in range(3):
+    for _ in range(5):
         join10()
     ctx.record(e1)
-    ms10 = ctx.elapsed_ms(e0, e1) / 3
+    ms10 = ctx.elapsed_ms(e0, e1) / 5
     rows10, fp10 = join10(keep=True)
     with np.errstate(over="ignore"):   # closed form: row i hits iff j_i = splitmix(43, i) % (10 nb) < nb; then k = splitmix(42, j_i), pb = splitmix(7, j_i)
         er, es = 0, 0
@@ -392,6 +396,7 @@ def secondary_configs(ctx, D, peak):
     out["C2_join_100Mx10M_sparse_unique_10pct_hit"] = {"ms_per_step": ms10, "rows_per_s": (nb + npr) / ms10 * 1e3, "output_rows": int(rows10), "achieved_gbs": algo10 / ms10 / 1e6,
                                                        "frac": algo10 / ms10 / 1e6 / peak, "fingerprint": fp10, "verified": "rows + checksum == closed form over the generators"}
     pk10.free()
+    ctx.trim_device_cache()   # every block starts from the same allocator state (its warm-up steps refill the cache)
     # ---- C2(iii): duplicated build keys (the chained table: count -> scan -> emit -> take), ~4 build rows per key, every probe row hits ----
     nk = nb // 4
     bkd = ctx.generate_i64(D.GEN_SPARSE_OF, 42, 99, nk, 0, nb)          # build key of row b = splitmix(42, splitmix(99, b) % nk)
@@ -416,12 +421,13 @@ def secondary_configs(ctx, D, peak):
             b.release()
         j.close()
         return rows, fp
-    joind()
+    for _ in range(2):
+        joind()
     ctx.record(e0)
-    for _ in range(3):
+    for _ in range(5):
         joind()
     ctx.record(e1)
-    msd = ctx.elapsed_ms(e0, e1) / 3
+    msd = ctx.elapsed_ms(e0, e1) / 5
     rowsd, fpd = joind(keep=True)
     with np.errstate(over="ignore"):   # closed form: multiplicity and payload sum per key slot, then one pass over the probe rows
         ib = np.arange(nb, dtype=np.uint64)
@@ -444,6 +450,7 @@ def secondary_configs(ctx, D, peak):
     bkd.free(); pkd.free()
     for b in (bk, bp, pk, pp):
         b.free()
+    ctx.trim_device_cache()   # every block starts from the same allocator state (its warm-up steps refill the cache)
     # ---- C3: group-by SUM / COUNT, 1B rows -> 1M groups ----
     ng, gn = 1_000_000, 1_000_000_000
     gk = ctx.generate_i64(D.GEN_UNIFORM, 5, 0, ng, 0, gn); gv = ctx.generate_i64(D.GEN_UNIFORM, 6, -2**31, 2**32, 0, gn)
@@ -478,6 +485,7 @@ def secondary_configs(ctx, D, peak):
     out["C3_groupby_sum_count_1B_rows_1M_groups"] = {"ms_per_step": ms, "rows_per_s": gn / ms * 1e3, "groups": int(g), "achieved_gbs": algo / ms / 1e6, "frac": algo / ms / 1e6 / peak,
                                                     "fingerprint": fp, "verified": "groups + (3 sum key + 5 sum sum + 7 sum count) mod 2^64 == closed form over the generators"}
     gk.free(); gv.free()
+    ctx.trim_device_cache()   # every block starts from the same allocator state (its warm-up steps refill the cache)
     # ---- C1 shape: FilterExec x:int64 > c over 100M rows x 2 columns, selectivity 20 % ----
     fn = 100_000_000
     fx = ctx.generate_i64(D.GEN_UNIFORM, 1, 0, 1 << 32, 0, fn); fy = ctx.generate_i64(D.GEN_SPLITMIX, 2, 0, 0, 0, fn)

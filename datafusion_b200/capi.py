@@ -143,7 +143,7 @@ ArrowArray._fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offse
 EXPORTS = [
     "dfgpu_ctx_create", "dfgpu_ctx_destroy", "dfgpu_last_error", "dfgpu_version", "dfgpu_device_count", "dfgpu_sync",
     "dfgpu_ctx_stream", "dfgpu_poll_ready", "dfgpu_malloc", "dfgpu_free", "dfgpu_host_alloc", "dfgpu_host_free", "dfgpu_host_register", "dfgpu_host_unregister", "dfgpu_memcpy_h2d",
-    "dfgpu_memcpy_d2h", "dfgpu_memset", "dfgpu_flush_l2", "dfgpu_event_create", "dfgpu_event_record",
+    "dfgpu_memcpy_d2h", "dfgpu_memset", "dfgpu_flush_l2", "dfgpu_trim_device_cache", "dfgpu_event_create", "dfgpu_event_record",
     "dfgpu_event_elapsed_ms", "dfgpu_event_destroy", "dfgpu_launch_count", "dfgpu_generate_i64",
     "dfgpu_set_kernel_timing", "dfgpu_kernel_time", "dfgpu_kernel_time_reset",
     "dfgpu_filter_create", "dfgpu_filter_push_host", "dfgpu_filter_push_device", "dfgpu_filter_push_arrow",
@@ -209,6 +209,7 @@ def load_library() -> C.CDLL:
     sig("dfgpu_memcpy_d2h", C.c_int, [vp, vp, vp, C.c_size_t])
     sig("dfgpu_memset", C.c_int, [vp, vp, C.c_int, C.c_size_t])
     sig("dfgpu_flush_l2", C.c_int, [vp])
+    sig("dfgpu_trim_device_cache", C.c_int, [vp])
     sig("dfgpu_event_create", C.c_int, [vp, P(vp)])
     sig("dfgpu_event_record", C.c_int, [vp, vp])
     sig("dfgpu_event_elapsed_ms", C.c_int, [vp, vp, vp, P(C.c_float)])
@@ -353,6 +354,10 @@ class Context:
 
     def flush_l2(self):
         self.check(self.lib.dfgpu_flush_l2(self.h))
+
+    def trim_device_cache(self):
+        """hand the allocator's idle device blocks back to the driver (dfgpu_trim_device_cache)"""
+        self.check(self.lib.dfgpu_trim_device_cache(self.h))
 
     # memory
     def malloc(self, nbytes: int) -> int:

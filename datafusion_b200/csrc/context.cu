@@ -212,6 +212,14 @@ int dfgpu_memset(dfgpu_ctx* ctx, void* dst, int value, size_t bytes) {
   if (bytes) DF_CUDA(cudaMemsetAsync(dst, value, bytes, ctx->stream));
   DF_API_END
 }
+int dfgpu_trim_device_cache(dfgpu_ctx* ctx) {
+  DF_API_BEGIN(ctx)
+  DF_CHECK(ctx, DFGPU_ERR_INVALID, "null ctx");
+  set_device(ctx);
+  dev_cache_trim(ctx);
+  DF_API_END
+}
+
 int dfgpu_flush_l2(dfgpu_ctx* ctx) {
   DF_API_BEGIN(ctx)
   set_device(ctx);

@@ -151,6 +151,10 @@ int dfgpu_memcpy_h2d(dfgpu_ctx* ctx, void* dst, const void* src, size_t bytes); 
 int dfgpu_memcpy_d2h(dfgpu_ctx* ctx, void* dst, const void* src, size_t bytes);
 int dfgpu_memset(dfgpu_ctx* ctx, void* dst, int value, size_t bytes);
 int dfgpu_flush_l2(dfgpu_ctx* ctx);  /* writes a >L2 scratch buffer (bench hygiene) */
+/* return the idle blocks of the context's caching device allocator to the driver (synchronises the stream); the cache otherwise
+ * keeps freed blocks for reuse up to half of the device memory (DFGPU_DEV_CACHE_GB).  What a MemoryPool adapter calls under
+ * memory pressure (execution/src/memory_pool). */
+int dfgpu_trim_device_cache(dfgpu_ctx* ctx);
 
 /* CUDA-event timing on the ctx stream (torch.cuda.Event only sees torch's stream). */
 int dfgpu_event_create(dfgpu_ctx* ctx, void** out);
