@@ -49,8 +49,9 @@ __host__ __device__ inline bool type_is_decimal(int t) { return (t & 0xff) == DF
 __host__ __device__ inline int dec_precision(int t) { return (t >> 8) & 0xff; }
 __host__ __device__ inline int dec_scale(int t) { return (int)(int8_t)((t >> 16) & 0xff); }
 __host__ __device__ inline int dec_type(int p, int s) { return DFGPU_DECIMAL128 | (p << 8) | ((s & 0xff) << 16); }
-__host__ __device__ inline int type_width(int t) {
-  switch (t & 0xff) {
+// width of a primitive (non-decimal) type code: the device interpreters' fast path (a Decimal128(p, s) code never reaches them)
+__host__ __device__ inline int type_width_prim(int t) {
+  switch (t) {
     case DFGPU_BOOL: return 0;  // bit-packed
     case DFGPU_INT8: case DFGPU_UINT8: return 1;
     case DFGPU_INT16: case DFGPU_UINT16: return 2;
@@ -58,6 +59,17 @@ __host__ __device__ inline int type_width(int t) {
     case DFGPU_INT64: case DFGPU_UINT64: case DFGPU_FLOAT64: case DFGPU_DATE64: case DFGPU_TIMESTAMP: return 8;
     case DFGPU_DECIMAL128: return 16;
     default: return -1;
+  }
+}
+__host__ __device__ inline int type_width(int t) {
+  switch (t) {
+    case DFGPU_BOOL: return 0;  // bit-packed
+    case DFGPU_INT8: case DFGPU_UINT8: return 1;
+    case DFGPU_INT16: case DFGPU_UINT16: return 2;
+    case DFGPU_INT32: case DFGPU_UINT32: case DFGPU_FLOAT32: case DFGPU_DATE32: return 4;
+    case DFGPU_INT64: case DFGPU_UINT64: case DFGPU_FLOAT64: case DFGPU_DATE64: case DFGPU_TIMESTAMP: return 8;
+    case DFGPU_DECIMAL128: return 16;
+    default: return type_is_decimal(t) ? 16 : -1;   // Decimal128(p, s): precision and scale in the upper bytes
   }
 }
 __host__ __device__ inline bool type_is_signed_int(int t) {

@@ -28,13 +28,14 @@ struct ENode {
 struct EProgram { int n; ENode node[kMaxNodes]; };
 
 enum Cls : int { C_I64 = 0, C_U64 = 1, C_F64 = 2, C_BOOL = 3, C_DEC = 4 /* Decimal128: 128-bit stack, expr_dec.cuh */ };
-__host__ __device__ inline int cls_of(int t) {
+// class of a primitive (non-decimal) type: what the 64-bit interpreter dispatches on
+__host__ __device__ inline int cls_of_prim(int t) {
   if (t == DFGPU_BOOL) return C_BOOL;
-  if (type_is_decimal(t)) return C_DEC;
   if (type_is_float(t)) return C_F64;
   if (type_is_unsigned_int(t)) return C_U64;
   return C_I64;
 }
+__host__ __device__ inline int cls_of(int t) { return type_is_decimal(t) ? C_DEC : cls_of_prim(t); }
 
 // values travel on the evaluation stack as 64-bit payloads: ints sign/zero-extended, floats as
 // f64 bits (f32 widened exactly), bools as 0/1.
@@ -80,7 +81,7 @@ enum ErrBits : int { ERR_DIV_ZERO = 1, ERR_OVERFLOW = 2, ERR_CAST = 4 };
 
 __device__ __forceinline__ void eval_binary(const ENode& nd, uint64_t a, bool av, uint64_t b, bool bv, uint64_t* r, bool* rv, int* err) {
   const int op = nd.op;
-  const int c = cls_of(nd.in_type);
+  const int c = cls_of_prim(nd.in_type);
   // ---- Kleene logic (and_kleene / or_kleene) ----
   if (op == DFGPU_OP_AND) {
     bool at = av && a, af = av && !a, bt = bv && b, bf = bv && !b;
@@ -166,9 +167,9 @@ __device__ __forceinline__ void eval_binary(const ENode& nd, uint64_t a, bool av
     case DFGPU_OP_BITXOR: z = a ^ b; break;
     // arrow's bitwise_shift_left / _right are `wrapping_shl` / `wrapping_shr`: the shift amount is taken modulo the bit width
     // (binary.rs bitwise_shift_array_overflow_test: 2 << 100 = 32 for Int32), sign-propagating for signed types
-    case DFGPU_OP_SHIFT_LEFT: { const int w = type_width(nd.out_type) * 8; z = a << (b & (uint64_t)(w - 1)); break; }
+    case DFGPU_OP_SHIFT_LEFT: { const int w = type_width_prim(nd.out_type) * 8; z = a << (b & (uint64_t)(w - 1)); break; }
     case DFGPU_OP_SHIFT_RIGHT: {
-      const int w = type_width(nd.out_type) * 8;
+      const int w = type_width_prim(nd.out_type) * 8;
       const uint64_t sh = b & (uint64_t)(w - 1);
       if (c == C_I64) z = (uint64_t)((long long)a >> sh);
       else z = a >> sh;
@@ -181,14 +182,14 @@ __device__ __forceinline__ void eval_binary(const ENode& nd, uint64_t a, bool av
 // CastExpr with the default CastOptions { safe: false } (expressions/cast.rs:37-40): a value that does not fit the integer target is
 // an error ("Can't cast value ..."), not a wrapped or NULL result; NULL slots never raise.  Float -> int truncates toward zero.
 __device__ __forceinline__ uint64_t cast_value(uint64_t v, int from, int to, bool valid, int* err) {
-  int cf = cls_of(from), ct = cls_of(to);
+  int cf = cls_of_prim(from), ct = cls_of_prim(to);
   if (ct == C_F64) {
     double d = cf == C_F64 ? __longlong_as_double((long long)v) : (cf == C_U64 || cf == C_BOOL ? (double)v : (double)(long long)v);
     if (to == DFGPU_FLOAT32) d = (double)(float)d;
     return (uint64_t)__double_as_longlong(d);
   }
   if (ct == C_BOOL) return cf == C_F64 ? (__longlong_as_double((long long)v) != 0.0) : (v != 0);
-  const int w = type_width(to) * 8;
+  const int w = type_width_prim(to) * 8;
   uint64_t iv = v;
   bool fits = true;
   if (cf == C_F64) {
@@ -225,7 +226,7 @@ __device__ __forceinline__ uint64_t eval_nodes(const ENode* __restrict__ nodes, 
     break;
       case kExprExt: {
     uint64_t v = ext[nd.voff] >> (int)nd.lit;
-    const int w = type_width(nd.out_type);
+    const int w = type_width_prim(nd.out_type);
     if (w < 8) { v &= (1ull << (8 * w)) - 1ull; if (type_is_signed_int(nd.out_type)) v = (uint64_t)(((int64_t)(v << (64 - 8 * w))) >> (64 - 8 * w)); }
     if (nd.out_type == DFGPU_FLOAT32) { float f = __uint_as_float((uint32_t)v); v = (uint64_t)__double_as_longlong((double)f); }
     sk[sp] = true; sv[sp] = v; ++sp;
@@ -250,7 +251,7 @@ __device__ __forceinline__ uint64_t eval_nodes(const ENode* __restrict__ nodes, 
       case DFGPU_EXPR_IS_NULL: sv[sp - 1] = sk[sp - 1] ? 0 : 1; sk[sp - 1] = true; break;
       case DFGPU_EXPR_IS_NOT_NULL: sv[sp - 1] = sk[sp - 1] ? 1 : 0; sk[sp - 1] = true; break;
       case DFGPU_EXPR_NEGATIVE:
-    if (cls_of(nd.out_type) == C_F64) sv[sp - 1] ^= 0x8000000000000000ull;
+    if (cls_of_prim(nd.out_type) == C_F64) sv[sp - 1] ^= 0x8000000000000000ull;
     else sv[sp - 1] = wrap_to_type(0ull - sv[sp - 1], nd.out_type);  // neg_wrapping
     break;
       case DFGPU_EXPR_CAST: {
@@ -293,7 +294,7 @@ __device__ __forceinline__ uint64_t eval_nodes_reg(const ENode* __restrict__ nod
       DF_PUSH(nd.lit, !nd.lit_null);
     } else if (nd.kind == kExprExt) {
       uint64_t v = ext[nd.voff] >> (int)nd.lit;
-      const int w = type_width(nd.out_type);
+      const int w = type_width_prim(nd.out_type);
       if (w < 8) { v &= (1ull << (8 * w)) - 1ull; if (type_is_signed_int(nd.out_type)) v = (uint64_t)(((int64_t)(v << (64 - 8 * w))) >> (64 - 8 * w)); }
       if (nd.out_type == DFGPU_FLOAT32) { float f = __uint_as_float((uint32_t)v); v = (uint64_t)__double_as_longlong((double)f); }
       DF_PUSH(v, true);
@@ -321,7 +322,7 @@ __device__ __forceinline__ uint64_t eval_nodes_reg(const ENode* __restrict__ nod
         case DFGPU_EXPR_IS_NULL: a = ak ? 0 : 1; ak = true; break;
         case DFGPU_EXPR_IS_NOT_NULL: a = ak ? 1 : 0; ak = true; break;
         case DFGPU_EXPR_NEGATIVE:
-          if (cls_of(nd.out_type) == C_F64) a ^= 0x8000000000000000ull;
+          if (cls_of_prim(nd.out_type) == C_F64) a ^= 0x8000000000000000ull;
           else a = wrap_to_type(0ull - a, nd.out_type);  // neg_wrapping
           break;
         case DFGPU_EXPR_CAST: {

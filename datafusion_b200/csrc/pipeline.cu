@@ -212,13 +212,13 @@ __device__ __forceinline__ uint64_t eval_int_fast(const ENode* __restrict__ node
     const ENode& nd = nodes[i];
     if (nd.kind == DFGPU_EXPR_BINARY) {
       uint64_t r = nd.op == DFGPU_OP_PLUS ? s1 + s0 : (nd.op == DFGPU_OP_MINUS ? s1 - s0 : s1 * s0);
-      if (type_width(nd.out_type) < 8) r = wrap_to_type(r, nd.out_type);
+      if (type_width_prim(nd.out_type) < 8) r = wrap_to_type(r, nd.out_type);
       s0 = r; s1 = s2; s2 = s3;
     } else {
       uint64_t v;
       if (nd.kind == DFGPU_EXPR_COLUMN) v = load_col_value(nd, row);
       else if (nd.kind == DFGPU_EXPR_LITERAL) v = nd.lit;
-      else { v = ext[nd.voff] >> (int)nd.lit; const int w = type_width(nd.out_type); if (w < 8) { v &= (1ull << (8 * w)) - 1ull; if (type_is_signed_int(nd.out_type)) v = (uint64_t)(((int64_t)(v << (64 - 8 * w))) >> (64 - 8 * w)); } }
+      else { v = ext[nd.voff] >> (int)nd.lit; const int w = type_width_prim(nd.out_type); if (w < 8) { v &= (1ull << (8 * w)) - 1ull; if (type_is_signed_int(nd.out_type)) v = (uint64_t)(((int64_t)(v << (64 - 8 * w))) >> (64 - 8 * w)); } }
       s3 = s2; s2 = s1; s1 = s0; s0 = v;
     }
   }
