@@ -103,7 +103,7 @@ class ExprNode(C.Structure):
 class HashJoinOptions(C.Structure):
     _fields_ = [("join_type", C.c_int32), ("null_equality", C.c_int32), ("batch_size", C.c_int64),
                 ("perfect_hash_join_small_build_threshold", C.c_int64), ("perfect_hash_join_min_key_density", C.c_double),
-                ("force_hash_collisions", C.c_int32), ("ordered_output", C.c_int32), ("null_aware", C.c_int32), ("reserved0", C.c_int32)]
+                ("force_hash_collisions", C.c_int32), ("ordered_output", C.c_int32), ("null_aware", C.c_int32), ("membership_filter", C.c_int32)]
 
 
 class AggDesc(C.Structure):
@@ -681,7 +681,7 @@ class HashJoinHandle(_Operator):
 
     def __init__(self, ctx, build_types, probe_types, on_build, on_probe, out_side, out_index, join_type=JOIN_INNER,
                  null_equality=NULL_EQUALS_NOTHING, batch_size=8192, phj_threshold=None, phj_density=None, force_hash_collisions=False,
-                 null_aware=False, ordered_output=True):
+                 null_aware=False, ordered_output=True, membership_filter=False):
         super().__init__(ctx)
         opt = HashJoinOptions()
         ctx.lib.dfgpu_hashjoin_default_options(C.byref(opt))
@@ -692,6 +692,7 @@ class HashJoinHandle(_Operator):
             opt.perfect_hash_join_min_key_density = phj_density
         opt.force_hash_collisions = 1 if force_hash_collisions else 0
         opt.null_aware = 1 if null_aware else 0
+        opt.membership_filter = 1 if membership_filter else 0   # Bloom filter over the build keys, tested before the table (low hit rates)
         opt.ordered_output = 1 if ordered_output else 0   # 0: the consumer ignores row order (aggregate / repartition above) -> the radix-partitioned probe may run
         ctx.check(ctx.lib.dfgpu_hashjoin_create(ctx.h, _i32arr(build_types), len(build_types), _i32arr(probe_types), len(probe_types),
                                                 _i32arr(on_build), _i32arr(on_probe), len(on_build), _i32arr(out_side), _i32arr(out_index),

@@ -26,6 +26,7 @@
 #include "batch.cuh"
 #include "scan.cuh"
 #include "expr.cuh"
+#include "bloom.cuh"
 
 namespace dfgpu {
 
@@ -471,7 +472,8 @@ __global__ void __launch_bounds__(kFusedThreads) join_probe_fused_kernel(KeyCols
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxPayloadCols = 8;
 struct PayloadCols { int n; const void* ptr[kMaxPayloadCols]; int width[kMaxPayloadCols]; int shift[kMaxPayloadCols]; };
-struct InlineRef { void* slots; uint64_t cap; int dense; uint64_t amin; int bucket; /* probe sequences start on a 4-slot boundary (one 64 B line for 16 B slots) */ };
+struct InlineRef { void* slots; uint64_t cap; int dense; uint64_t amin; int bucket; /* probe sequences start on a 4-slot boundary (one 64 B line for 16 B slots) */
+                   const unsigned long long* bloom; uint64_t bloom_blocks; /* optional membership filter over the build keys (dfgpu_hashjoin_options.membership_filter) */ };
 struct InlineOut {
   int n;
   int kind[kMaxFusedCols];   // 0: gather from a probe-side column by probe row; 1: extract from the payload word
@@ -497,6 +499,15 @@ __device__ __forceinline__ uint64_t load_payload(const PayloadCols& pc, int64_t 
     p |= v << pc.shift[c];
   }
   return p;
+}
+
+// membership filter over the (non-NULL) build keys: the stand-alone join's form of dynamic filter pushdown (a27; the fused pipeline
+// carries the same filter in dfgpu_lookup) — a probe row whose key is not in the filter skips the table access, which is a DRAM miss
+__global__ void __launch_bounds__(256) join_bloom_build_kernel(KeyCols kc, int64_t n, unsigned long long* __restrict__ bloom, uint64_t blocks) {
+  for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t tag;
+    if (load_tag(kc, row, &tag)) bloom_set(bloom, blocks, tag);
+  }
 }
 
 template <int W>
@@ -528,7 +539,7 @@ __global__ void __launch_bounds__(256) join_build_inline_kernel(KeyCols kc, Payl
   }
 }
 
-template <int W>
+template <int W, bool BLOOM>
 __global__ void __launch_bounds__(kFusedThreads) join_probe_inline_v0_kernel(KeyCols kc, int64_t n, InlineRef t, InlineOut oc,
                                                                        unsigned long long* __restrict__ tile_desc, unsigned int* __restrict__ tile_counter,
                                                                        unsigned long long* __restrict__ totals) {
@@ -554,6 +565,13 @@ __global__ void __launch_bounds__(kFusedThreads) join_probe_inline_v0_kernel(Key
       if (t.dense) { slot[k] = tags[k] - t.amin; if (slot[k] >= t.cap) live[k] = false; }
       else slot[k] = t.bucket ? (__umul64hi(hash_u64(tags[k], kSeedJoin), t.cap >> 2) << 2) : __umul64hi(hash_u64(tags[k], kSeedJoin), t.cap);
     }
+  }
+  if (BLOOM) {   // the filter words of the 4 rows are fetched back to back (L2-resident), then the rows without a partner drop out
+    unsigned long long bw[kFusedItems]; uint32_t bt[kFusedItems];
+#pragma unroll
+    for (int k = 0; k < kFusedItems; ++k) { bw[k] = ~0ull; bt[k] = 0; if (live[k]) { const BloomPos bp = bloom_pos(tags[k], t.bloom_blocks); bt[k] = bp.t; bw[k] = __ldg(t.bloom + bp.block); } }
+#pragma unroll
+    for (int k = 0; k < kFusedItems; ++k) if (live[k] && !bloom_test(bw[k], bt[k])) live[k] = false;
   }
   uint64_t cur[kFusedItems], curp[kFusedItems];
 #pragma unroll
@@ -1128,7 +1146,7 @@ struct dfgpu_hashjoin {
   // inline-payload table (unique keys, Inner, narrow build side)
   bool inline_ok = false;
   int inline_words = 0;
-  DevBuf inline_slots;
+  DevBuf inline_slots, bloom;
   InlineRef iref{};
   std::vector<int> out_kind, out_src, out_shift;  // per output column: kind (0 probe gather / 1 payload), probe column index, payload shift
   // output
@@ -1411,6 +1429,16 @@ static void finish_build(dfgpu_hashjoin* j) {
       DF_CUDA(cudaMemcpyAsync(hc, j->counters.ptr, 24, cudaMemcpyDeviceToHost, ctx->stream));
       DF_CUDA(cudaStreamSynchronize(ctx->stream));
       if (hc[2] == 0) {
+        if (j->opt.membership_filter && !j->use_array_map && n > 0) {
+          // 16 bits per build key, one 64-bit block per 4 keys; probed before the table by the ordered probe kernel
+          const uint64_t blocks = std::max<uint64_t>(1024, ((uint64_t)n + 3) / 4);
+          j->bloom.alloc(ctx, (size_t)blocks * 8);
+          j->bloom.zero();
+          KernelTimer kt(ctx, "join_build");
+          join_bloom_build_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(j->build_keys, n, j->bloom.as<unsigned long long>(), blocks);
+          DF_LAUNCH_CHECK(ctx);
+          j->iref.bloom = j->bloom.as<unsigned long long>(); j->iref.bloom_blocks = blocks;
+        }
         j->inline_ok = true; j->inline_words = W;
         j->distinct = j->valid_rows = (int64_t)hc[0]; j->null_rows = (int64_t)hc[1];
         j->unique = true;
@@ -1773,8 +1801,13 @@ static void push_probe(dfgpu_hashjoin* j, std::vector<DCol>&& cols) {
         if (j->inline_words == 2) join_probe_inline_v2_kernel<2><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
         else join_probe_inline_v2_kernel<1><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
       } else if (variant == 0) {
-        if (j->inline_words == 2) join_probe_inline_v0_kernel<2><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
-        else join_probe_inline_v0_kernel<1><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
+        if (j->iref.bloom) {
+          if (j->inline_words == 2) join_probe_inline_v0_kernel<2, true><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
+          else join_probe_inline_v0_kernel<1, true><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
+        } else {
+          if (j->inline_words == 2) join_probe_inline_v0_kernel<2, false><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
+          else join_probe_inline_v0_kernel<1, false><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
+        }
       } else {
         if (j->inline_words == 2) join_probe_inline_kernel<2><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
         else join_probe_inline_kernel<1><<<(int)nt, kFusedThreads, 0, ctx->stream>>>(pk, n, j->iref, oc, desc.as<unsigned long long>(), counter, totals);
@@ -2238,6 +2271,7 @@ int64_t dfgpu_hashjoin_metric(dfgpu_hashjoin* j, const char* name) {
   if (s == "array_map_created_count") return j->m_array_map;
   if (s == "probe_hits") return j->m_probe_hits;
   if (s == "radix_partitioned_probes") return j->m_radix_probes;
+  if (s == "membership_filter_bytes") return (int64_t)j->bloom.bytes;
   if (s == "build_distinct_keys") return j->distinct;
   if (s == "build_unique") return j->unique ? 1 : 0;
   if (s == "build_null_key_rows") return j->null_rows;

@@ -28,6 +28,7 @@
 #include "expr.cuh"
 #include "expr_dev.cuh"
 #include "expr_dec.cuh"
+#include "bloom.cuh"
 #include <climits>
 #include <array>
 
@@ -94,26 +95,6 @@ __device__ __forceinline__ Rec128 rec_cas128(void* addr, Rec128 cmp, Rec128 val)
 }
 
 __device__ __forceinline__ uint64_t lk_hash(uint64_t key) { return hash_u64(key, kSeedJoin); }
-// Membership filter = split-block Bloom filter: one 64-bit block per key (two 32-bit words, two probe bits in each), 16 bits per key.
-// Block and bit positions come from a 32-bit multiplicative hash of both key halves — the filter is probed for EVERY scanned row, so
-// its cost is counted in instructions: ~12 integer ops here against ~45 for mix64 + a 64-bit fastrange + four 64-bit shifts.
-struct BloomPos { uint32_t block, t; };   // t: 20 hash bits = four 5-bit probe positions (two per 32-bit word)
-__device__ __forceinline__ BloomPos bloom_pos(uint64_t key, uint64_t blocks) {
-  uint32_t h1 = ((uint32_t)key ^ ((uint32_t)(key >> 32) * 0x85EBCA6Bu)) * 0x9E3779B1u;
-  h1 ^= h1 >> 15;
-  BloomPos p;
-  p.block = __umulhi(h1, (uint32_t)blocks);
-  p.t = (h1 * 0xC2B2AE35u) >> 12;                           // the well-mixed upper 20 bits of a second multiply
-  return p;
-}
-__device__ __forceinline__ unsigned long long bloom_mask(uint32_t t) {
-  const uint32_t m0 = (1u << (t & 31)) | (1u << ((t >> 5) & 31)), m1 = (1u << ((t >> 10) & 31)) | (1u << ((t >> 15) & 31));
-  return ((unsigned long long)m1 << 32) | m0;
-}
-__device__ __forceinline__ void bloom_set(unsigned long long* bloom, uint64_t blocks, uint64_t key) {
-  const BloomPos p = bloom_pos(key, blocks);
-  atomicOr(&bloom[p.block], bloom_mask(p.t));
-}
 // Coarse first level for filters that do not fit L2 (a join's filter shared by 4-8 GPUs is hundreds of MB): 4 bits per key, two probe
 // bits in one 32-bit word.  It stays L2-resident and rejects ~85 % of the keys without a partner, so only ~1 probe in 4 pays the DRAM
 // access of the exact (16 bits per key) level behind it.
@@ -130,10 +111,6 @@ __device__ __forceinline__ CoarsePos coarse_pos(uint64_t key, uint64_t words) {
 __device__ __forceinline__ void filter_set(const LookupDev& t, uint64_t key) {
   bloom_set(t.bloom, t.bloom_blocks, key);
   if (t.coarse) { const CoarsePos c = coarse_pos(key, t.coarse_words); atomicOr(&t.coarse[c.word], c.mask); }
-}
-__device__ __forceinline__ bool bloom_test(unsigned long long w, uint32_t t) {
-  const uint32_t m0 = (1u << (t & 31)) | (1u << ((t >> 5) & 31)), m1 = (1u << ((t >> 10) & 31)) | (1u << ((t >> 15) & 31));
-  return ((uint32_t)w & m0) == m0 && ((uint32_t)(w >> 32) & m1) == m1;
 }
 
 // insert one record; returns 0 inserted, 1 duplicate key, 2 cannot store this key

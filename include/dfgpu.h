@@ -290,7 +290,11 @@ typedef struct dfgpu_hashjoin_options {
   int32_t null_aware;      /* NOT IN semantics (HashJoinExec::null_aware, exec.rs:429-455, stream.rs:755-806, 1016-1072): LeftAnti /
                             * RightAnti on ONE key column; a NULL on the other side empties the result, NULL keys of the
                             * preserved side are never emitted (unless the other side is empty) */
-  int32_t reserved0;
+  int32_t membership_filter; /* 1 = also build a split-block Bloom filter over the build keys (16 bits per key) and test it before the table
+                            * in the ordered probe of the inline (unique-key Inner) path: the stand-alone join's dynamic filter pushdown
+                            * (hash_join/shared_bounds.rs, partitioned_hash_eval.rs).  Pays when most probe rows have no partner — a miss
+                            * then costs an L2-resident filter probe instead of a DRAM table access; with every row matching it only adds
+                            * the filter probe.  0 (default) = off; ignored by the other probe paths */
 } dfgpu_hashjoin_options;
 void dfgpu_hashjoin_default_options(dfgpu_hashjoin_options* o);
 

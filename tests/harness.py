@@ -66,9 +66,9 @@ def split_points(n: int, batch_rows: Optional[int]):
 
 def gpu_hash_join(ctx, build, probe, on_build, on_probe, out_side, out_index, join_type=D.JOIN_INNER, null_equality=D.NULL_EQUALS_NOTHING,
                   batch_size=8192, phj=(1024, 0.15), force_collisions=False, build_batch_rows=None, probe_batch_rows=None, device=False,
-                  build_types=None, probe_types=None, return_handle=False, filter=None, null_aware=False, ordered_output=True):
+                  build_types=None, probe_types=None, return_handle=False, filter=None, null_aware=False, ordered_output=True, membership_filter=False):
     bt, pt = type_ids(build, build_types), type_ids(probe, probe_types)
-    j = D.HashJoinHandle(ctx, bt, pt, on_build, on_probe, out_side, out_index, join_type, null_equality, batch_size, phj[0], phj[1], force_collisions, null_aware, ordered_output)
+    j = D.HashJoinHandle(ctx, bt, pt, on_build, on_probe, out_side, out_index, join_type, null_equality, batch_size, phj[0], phj[1], force_collisions, null_aware, ordered_output, membership_filter)
     if filter is not None:
         j.set_filter(*filter)
     nb, npr = len(build[0][0]), len(probe[0][0])

@@ -275,3 +275,27 @@ def test_gpu_radix_partitioned_probe_gives_the_same_rows(gpu_ctx, monkeypatch, p
     assert h.metric("radix_partitioned_probes") == 0
     h.close()
     assert_cols_equal(got, exp, ordered=True, what="ordered path untouched")
+
+
+@pytest.mark.parametrize("hit_pct,with_payload,device", [(10, True, True), (100, True, False), (10, False, True), (0, True, True)])
+def test_gpu_membership_filter_keeps_rows_and_order(gpu_ctx, hit_pct, with_payload, device):
+    """dfgpu_hashjoin_options.membership_filter: a Bloom filter over the build keys tested before the table (the stand-alone join's dynamic
+    filter pushdown, shared_bounds.rs) must change nothing but the number of table accesses — same rows, same (reference) order, with NULL
+    probe keys, misses and several probe batches"""
+    rng = np.random.default_rng(300 + hit_pct)
+    nb, npr = 40_000, 150_123
+    universe = rng.permutation(1_000_000)[:nb * 10].astype(np.int64) * 1_000_003 - 7
+    bk = universe[:nb]
+    build = [(bk, None), (rng.integers(-2**62, 2**62, nb).astype(np.int64), None)]
+    hit = rng.random(npr) < hit_pct / 100.0
+    pk = np.where(hit, bk[rng.integers(0, nb, npr)], universe[nb + rng.integers(0, nb * 9, npr)])
+    probe = [(pk, rng.random(npr) > 0.03), (np.arange(npr, dtype=np.int64), None)]
+    side, idx = ([0, 0, 1, 1], [0, 1, 0, 1]) if with_payload else ([0, 1, 1], [0, 0, 1])
+    exp = O.hash_join(build, probe, [0], [0], side, idx, phj_threshold=0, phj_density=float("inf"))
+    got, h = gpu_hash_join(gpu_ctx, build, probe, [0], [0], side, idx, phj=(0, float("inf")), probe_batch_rows=60_001, device=device, return_handle=True,
+                           membership_filter=True)
+    assert h.metric("membership_filter_bytes") >= nb * 2 and h.metric("array_map_created_count") == 0
+    h.close()
+    assert_cols_equal(got, exp, ordered=True, what=f"membership filter hit={hit_pct}% payload={with_payload}")
+    if hit_pct in (10, 100):
+        assert len(exp[0][0]) > npr * hit_pct // 100 * 0.9
