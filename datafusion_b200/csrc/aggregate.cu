@@ -42,7 +42,64 @@ struct GroupCols {
   int shift[kMaxGroupCols];     // bit position of the value inside the 128-bit key
   int null_bit[kMaxGroupCols];  // bit position of the null flag or -1
   int is_float[kMaxGroupCols];  // canonicalise -0.0 -> +0.0 (primitive.rs:75-98)
+  // wide keys (> 128 bits together): the table tag is a 64-bit hash of the key tuple, the tuple itself is stored per slot by the thread
+  // that claims it (two 64-bit words per column + a NULL mask) and every row of the batch is compared against it afterwards
+  // (GroupValuesColumn: hash, then vectorized_equal_to against the stored group values, group_values/multi_group_by/mod.rs:628)
+  int wide;
+  unsigned long long* kstore[kMaxGroupCols * 2];
+  uint8_t* knull;
 };
+
+// one group column's value as stored / hashed in the wide-key path: raw bits widened to 64 (+ a second word for 16-byte types), floats
+// with -0.0 folded into +0.0
+__device__ __forceinline__ bool load_group_col(const GroupCols& g, int c, int64_t row, uint64_t* v, uint64_t* v2) {
+  *v = 0; *v2 = 0;
+  if (g.valid[c] && !bit_get(g.valid[c], g.voff[c] + row)) return false;
+  switch (g.width[c]) {
+    case 0: *v = bit_get((const uint8_t*)g.ptr[c], g.boff[c] + row) ? 1ull : 0ull; break;
+    case 1: *v = ((const uint8_t*)g.ptr[c])[row]; break;
+    case 2: *v = ((const uint16_t*)g.ptr[c])[row]; break;
+    case 4: *v = ((const uint32_t*)g.ptr[c])[row]; if (g.is_float[c] && (*v & 0x7FFFFFFFull) == 0) *v = 0; break;
+    case 16: *v = ((const uint64_t*)g.ptr[c])[2 * row]; *v2 = ((const uint64_t*)g.ptr[c])[2 * row + 1]; break;
+    default: *v = ((const uint64_t*)g.ptr[c])[row]; if (g.is_float[c] && (*v << 1) == 0) *v = 0; break;
+  }
+  return true;
+}
+__device__ __forceinline__ uint64_t wide_group_hash(const GroupCols& g, int64_t row) {
+  uint64_t h = kSeedAgg;
+#pragma unroll 1
+  for (int c = 0; c < g.n; ++c) {
+    uint64_t v, v2;
+    if (!load_group_col(g, c, row, &v, &v2)) { h = hash_combine(h, 0x6E756C6Cull + (uint64_t)c); continue; }   // NULL is a group value
+    h = hash_combine(h, v);
+    if (g.width[c] == 16) h = hash_combine(h, v2);
+  }
+  return h == kEmptyKey ? 0x5bd1e995ull : h;
+}
+__device__ __forceinline__ void store_group_key(const GroupCols& g, int64_t row, uint64_t slot) {
+  unsigned int nullmask = 0;
+#pragma unroll 1
+  for (int c = 0; c < g.n; ++c) {
+    uint64_t v, v2;
+    if (!load_group_col(g, c, row, &v, &v2)) nullmask |= 1u << c;
+    g.kstore[2 * c][slot] = v;
+    if (g.width[c] == 16) g.kstore[2 * c + 1][slot] = v2;
+  }
+  g.knull[slot] = (uint8_t)nullmask;
+}
+__device__ __forceinline__ bool equal_group_key(const GroupCols& g, int64_t row, uint64_t slot) {
+  const unsigned int nullmask = g.knull[slot];
+#pragma unroll 1
+  for (int c = 0; c < g.n; ++c) {
+    uint64_t v, v2;
+    const bool ok = load_group_col(g, c, row, &v, &v2);
+    if (ok == (((nullmask >> c) & 1u) != 0)) return false;
+    if (!ok) continue;
+    if (g.kstore[2 * c][slot] != v) return false;
+    if (g.width[c] == 16 && g.kstore[2 * c + 1][slot] != v2) return false;
+  }
+  return true;
+}
 
 __device__ __forceinline__ void key_or(Key2& k, uint64_t v, int shift) {
   // v < 2^width and shift + width <= 128, so nothing is lost
@@ -56,6 +113,7 @@ __device__ __forceinline__ void key_or(Key2& k, uint64_t v, int shift) {
 
 // returns true when the row belongs to the single-column NULL group
 __device__ __forceinline__ bool load_group_key(const GroupCols& g, int64_t row, Key2* out) {
+  if (g.wide) { *out = Key2{wide_group_hash(g, row), 0ull}; return false; }
   Key2 k{0ull, 0ull};
   bool null_group = false;
 #pragma unroll
@@ -301,11 +359,30 @@ __global__ void __launch_bounds__(256) agg_update_kernel(GroupCols g, AggSet agg
         overflow[pos] = (uint32_t)(row[r] - row0);
         continue;
       }
+      if (KW == 1 && claimed && g.wide) store_group_key(g, row[r], slot);   // read back only by later kernels (verify, rehash, emit)
 #pragma unroll 1
       for (int a = 0; a < aggs.n; ++a) apply_agg(aggs.a[a], row[r], slot);
     }
   }
 }
+// wide keys: every row of the chunk against the key tuple stored in its slot.  Runs after the update kernel (and its replays) finished, so
+// every claim and its stored tuple is visible; a mismatch means two distinct tuples share a 64-bit hash.
+__global__ void __launch_bounds__(256) agg_verify_wide_kernel(GroupCols g, TableDev t, int64_t row0, int64_t n, int* __restrict__ mismatch) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = row0 + i;
+    const uint64_t h = wide_group_hash(g, row);
+    uint64_t s = start_slot<1>(t, Key2{h, 0ull});
+    bool found = false;
+    for (int probe = 0; probe < kMaxProbe; ++probe) {
+      const unsigned long long tag = ((const unsigned long long*)t.tags)[s];
+      if (tag == h) { found = true; break; }
+      if (tag == kEmptyKey) break;
+      if (++s == t.cap) s = 0;
+    }
+    if (!found || !equal_group_key(g, row, s)) *mismatch = 1;
+  }
+}
+
 // ---- fast path: one non-null 8-byte key, every aggregate of the form acc[slot] += (column ? column[row] : 1) ----
 // (SUM over a non-null 8-byte integer column, COUNT / COUNT(*) without NULLs or FILTER, and their Final-mode
 // merges) — the C3 shape.  No type switches, no validity reads; 4 rows per thread with the loads hoisted.
@@ -384,7 +461,7 @@ __global__ void __launch_bounds__(256) agg_update_fast_kernel(const unsigned lon
   }
 }
 
-struct AccArrays { int n; void* ptr[kMaxAggs * 3]; void* new_ptr[kMaxAggs * 3]; int elem[kMaxAggs * 3]; };
+struct AccArrays { int n; void* ptr[kMaxAggs * 3 + kMaxGroupCols * 2 + 1]; void* new_ptr[kMaxAggs * 3 + kMaxGroupCols * 2 + 1]; int elem[kMaxAggs * 3 + kMaxGroupCols * 2 + 1]; };
 
 // grow: re-insert every occupied slot of the old table into the new one and move its accumulators
 template <int KW>
@@ -443,7 +520,7 @@ __global__ void agg_init_seen_kernel(TableDev t, uint8_t* __restrict__ seen) {
 }
 
 // ---- emit kernels: one per output column, 32 consecutive outputs per warp ----
-enum EmitKind : int { EK_KEY = 0, EK_COPY64 = 1, EK_AVG = 2, EK_MINMAX = 3, EK_DEC128 = 4 };
+enum EmitKind : int { EK_KEY = 0, EK_COPY64 = 1, EK_AVG = 2, EK_MINMAX = 3, EK_DEC128 = 4, EK_WIDEKEY = 5 };
 struct EmitDesc {
   int kind;
   int out_type;        // output column type
@@ -500,6 +577,11 @@ __global__ void __launch_bounds__(256) agg_emit_kernel(EmitDesc d, const uint32_
           bits = d.acc0[s];
           if (d.seen) ok = d.seen[s] != 0;
           break;
+        case EK_WIDEKEY:   // acc0 / acc1: the column's stored words, seen: the slots' NULL masks, null_bit: this column's bit
+          ok = ((d.seen[s] >> d.null_bit) & 1) == 0;
+          bits = d.acc0[s];
+          if (type_width(d.out_type) == 16) { ((unsigned long long*)out)[2 * i] = ok ? d.acc0[s] : 0ull; ((unsigned long long*)out)[2 * i + 1] = ok ? d.acc1[s] : 0ull; }
+          break;
         case EK_DEC128:
           if (d.seen) ok = d.seen[s] != 0;
           ((unsigned long long*)out)[2 * i] = ok ? d.acc0[s] : 0ull;
@@ -527,7 +609,7 @@ __global__ void __launch_bounds__(256) agg_emit_kernel(EmitDesc d, const uint32_
       }
       if (!ok) bits = 0;
       if (d.out_type == DFGPU_BOOL) bval = bits & 1;
-      else if (type_width(d.out_type) == 16) { if (!ok) { ((unsigned long long*)out)[2 * i] = 0ull; ((unsigned long long*)out)[2 * i + 1] = 0ull; } }   // 16-byte values were stored above
+      else if (type_width(d.out_type) == 16) { if (!ok && d.kind != EK_WIDEKEY) { ((unsigned long long*)out)[2 * i] = 0ull; ((unsigned long long*)out)[2 * i + 1] = 0ull; } }   // 16-byte values were stored above
       else store_typed(out, d.out_type, i, bits);
     }
     uint32_t vw = __ballot_sync(0xffffffffu, ok);
@@ -635,6 +717,10 @@ struct dfgpu_agg {
   // key packing
   std::vector<int> g_shift, g_width_bits, g_null_bit;
   bool single_null_slot = false;
+  // wide keys (> 128 bits together): hash tag + stored key tuples (GroupCols::wide)
+  bool wide = false;
+  std::vector<DevBuf> kstore;   // 2 per group column (second word only for 16-byte types)
+  DevBuf knull;
   // table
   DevBuf tags, counters /* [ngroups, overflow_count] */, special_used;
   uint64_t cap = 0;
@@ -672,10 +758,20 @@ static void fill_u64(dfgpu_ctx* ctx, void* p, uint64_t n, unsigned long long v) 
   DF_LAUNCH_CHECK(ctx);
 }
 
-static void alloc_table(dfgpu_agg* a, uint64_t cap, DevBuf* tags, std::vector<DevBuf>* acc0, std::vector<DevBuf>* acc1, std::vector<DevBuf>* seen) {
+static void alloc_table(dfgpu_agg* a, uint64_t cap, DevBuf* tags, std::vector<DevBuf>* acc0, std::vector<DevBuf>* acc1, std::vector<DevBuf>* seen,
+                        std::vector<DevBuf>* kstore = nullptr, DevBuf* knull = nullptr) {
   dfgpu_ctx* ctx = a->ctx;
   tags->alloc(ctx, (size_t)(cap + 2) * 8 * a->kw);
   tags->fill(0xFF);
+  if (a->wide && kstore && knull) {
+    kstore->resize(a->group_cols.size() * 2);
+    for (size_t c = 0; c < a->group_cols.size(); ++c) {
+      (*kstore)[2 * c].alloc(ctx, (size_t)(cap + 2) * 8);
+      if (type_width(a->input_types[a->group_cols[c]]) == 16) (*kstore)[2 * c + 1].alloc(ctx, (size_t)(cap + 2) * 8);
+    }
+    knull->alloc(ctx, (size_t)(cap + 2));
+    knull->zero();
+  }
   acc0->resize(a->aggs.size()); acc1->resize(a->aggs.size()); seen->resize(a->aggs.size());
   for (size_t i = 0; i < a->aggs.size(); ++i) {
     (*acc0)[i].alloc(ctx, (size_t)(cap + 2) * 8);
@@ -688,8 +784,9 @@ static void alloc_table(dfgpu_agg* a, uint64_t cap, DevBuf* tags, std::vector<De
 static void grow_table(dfgpu_agg* a, uint64_t new_cap) {
   dfgpu_ctx* ctx = a->ctx;
   DevBuf ntags, ncounters(ctx, 16), nspecial(ctx, 8);
-  std::vector<DevBuf> nacc0, nacc1, nseen;
-  alloc_table(a, new_cap, &ntags, &nacc0, &nacc1, &nseen);
+  std::vector<DevBuf> nacc0, nacc1, nseen, nkstore;
+  DevBuf nknull;
+  alloc_table(a, new_cap, &ntags, &nacc0, &nacc1, &nseen, &nkstore, &nknull);
   ncounters.zero();
   nspecial.zero();
   TableDev old_t = table_dev(a, a->tags, a->cap, a->counters, a->special_used);
@@ -701,6 +798,11 @@ static void grow_table(dfgpu_agg* a, uint64_t new_cap) {
     arr.ptr[arr.n] = a->aggs[i].acc0.ptr; arr.new_ptr[arr.n] = nacc0[i].ptr; arr.elem[arr.n++] = 8;
     if (a->aggs[i].acc1.ptr) { arr.ptr[arr.n] = a->aggs[i].acc1.ptr; arr.new_ptr[arr.n] = nacc1[i].ptr; arr.elem[arr.n++] = 8; }
     if (a->aggs[i].seen.ptr) { arr.ptr[arr.n] = a->aggs[i].seen.ptr; arr.new_ptr[arr.n] = nseen[i].ptr; arr.elem[arr.n++] = 1; }
+  }
+  if (a->wide) {
+    for (size_t k = 0; k < a->kstore.size(); ++k)
+      if (a->kstore[k].ptr) { arr.ptr[arr.n] = a->kstore[k].ptr; arr.new_ptr[arr.n] = nkstore[k].ptr; arr.elem[arr.n++] = 8; }
+    arr.ptr[arr.n] = a->knull.ptr; arr.new_ptr[arr.n] = nknull.ptr; arr.elem[arr.n++] = 1;
   }
   int grid = grid_for((int64_t)a->cap + 2, 256, kNumSMs * 8);
   if (a->kw == 1) agg_rehash_kernel<1><<<grid, 256, 0, ctx->stream>>>(old_t, new_t, arr);
@@ -715,6 +817,7 @@ static void grow_table(dfgpu_agg* a, uint64_t new_cap) {
     a->aggs[i].acc1 = std::move(nacc1[i]);
     a->aggs[i].seen = std::move(nseen[i]);
   }
+  if (a->wide) { a->kstore = std::move(nkstore); a->knull = std::move(nknull); }
   a->cap = new_cap;
   a->m_rehashes++;
 }
@@ -816,8 +919,9 @@ static void agg_push(dfgpu_agg* a, const std::vector<DCol>& cols) {
     g.width[c] = type_width(col.type); g.boff[c] = col.offset;
     g.shift[c] = a->g_shift[c]; g.null_bit[c] = a->g_null_bit[c];
     g.is_float[c] = type_is_float(col.type) ? 1 : 0;
-    DF_CHECK(!(col.validity && a->g_null_bit[c] < 0 && !a->single_null_slot), DFGPU_ERR_INVALID, "group column declared non-nullable has a validity bitmap");
+    DF_CHECK(a->wide || !(col.validity && a->g_null_bit[c] < 0 && !a->single_null_slot), DFGPU_ERR_INVALID, "group column declared non-nullable has a validity bitmap");
   }
+  g.wide = a->wide ? 1 : 0;
   // aggregates
   AggSet set;
   memset(&set, 0, sizeof(set));
@@ -860,6 +964,10 @@ static void agg_push(dfgpu_agg* a, const std::vector<DCol>& cols) {
       set.a[i].acc1 = a->aggs[i].acc1.as<unsigned long long>();
       set.a[i].seen = a->aggs[i].seen.as<uint8_t>();
       if (i < kMaxFastAggs) fa.acc[i] = a->aggs[i].acc0.as<unsigned long long>();
+    }
+    if (a->wide) {
+      for (size_t k = 0; k < a->kstore.size(); ++k) g.kstore[k] = a->kstore[k].as<unsigned long long>();
+      g.knull = a->knull.as<uint8_t>();
     }
   };
   // chunked processing with ramp-up so an undersized table is discovered cheaply
@@ -924,6 +1032,17 @@ static void agg_push(dfgpu_agg* a, const std::vector<DCol>& cols) {
       work = (int64_t)hc[1];
       uint64_t want = std::max<uint64_t>(a->cap * 4, (hc[0] + hc[1]) * 2);
       grow_table(a, (want + 3) & ~3ull);
+    }
+    if (a->wide) {
+      // vectorized_equal_to: every row of the chunk against its group's stored tuple (all claims of the chunk are complete by now)
+      refresh_ptrs();
+      TableDev t = table_dev(a, a->tags, a->cap, a->counters, a->special_used);
+      DevBuf mism(ctx, 4);
+      mism.zero();
+      agg_verify_wide_kernel<<<grid_for(m, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(g, t, done, m, mism.as<int>());
+      DF_LAUNCH_CHECK(ctx);
+      const int bad = read_scalar<int>(ctx, mism.as<int>());
+      DF_CHECK(!bad, DFGPU_ERR_UNSUPPORTED, "aggregate: two distinct wide group keys share a 64-bit hash (expected once in ~2^64 / groups^2 runs): keep the CPU operator for this input");
     }
     done += m;
     chunk = std::min<int64_t>(chunk * 4, kMaxChunk);
@@ -1029,6 +1148,12 @@ static void agg_emit_table(dfgpu_agg* a) {
   for (size_t c = 0; c < a->group_cols.size(); ++c) {
     EmitDesc d;
     memset(&d, 0, sizeof(d));
+    if (a->wide) {   // the stored tuple: column c's words + bit c of the NULL mask
+      d.kind = EK_WIDEKEY; d.acc0 = a->kstore[2 * c].as<unsigned long long>(); d.acc1 = a->kstore[2 * c + 1].as<unsigned long long>();
+      d.seen = a->knull.as<uint8_t>(); d.null_bit = (int)c;
+      out->cols.push_back(run_emit(d, a->input_types[a->group_cols[c]], true));
+      continue;
+    }
     d.kind = EK_KEY; d.shift = a->g_shift[c]; d.width_bits = a->g_width_bits[c]; d.null_bit = a->g_null_bit[c];
     d.single_null_slot = a->single_null_slot;
     bool nullable = a->g_null_bit[c] >= 0 || a->single_null_slot;
@@ -1126,11 +1251,13 @@ int dfgpu_agg_create(dfgpu_ctx* ctx, const int32_t* input_types, int32_t n_cols,
   // key packing: values first, then one null flag per (multi-column) group column.  All group
   // columns are treated as nullable: the schema-level nullability is not part of this ABI.
   int bits = 0;
+  bool wide = false;
   for (int c = 0; c < n_group; ++c) {
     DF_CHECK(group_cols[c] >= 0 && group_cols[c] < n_cols, DFGPU_ERR_INVALID, "group column index out of range");
     int t = input_types[group_cols[c]];
     int w = type_width(t);
-    DF_CHECK((w >= 0 && w <= 8) || (w == 16 && n_group == 1), DFGPU_ERR_UNSUPPORTED, "aggregate: group column type not supported (a 16-byte Decimal128 key must be the only group column)");
+    DF_CHECK(w >= 0 && w <= 16, DFGPU_ERR_UNSUPPORTED, "aggregate: group column type not supported");
+    if (w == 16 && n_group > 1) wide = true;   // a 16-byte Decimal128 key next to other group columns
     int wb = (t == DFGPU_BOOL) ? 1 : 8 * w;
     a->g_shift.push_back(bits);
     a->g_width_bits.push_back(wb);
@@ -1147,7 +1274,13 @@ int dfgpu_agg_create(dfgpu_ctx* ctx, const int32_t* input_types, int32_t n_cols,
     bits -= n_group;
     for (int c = 0; c < n_group; ++c) a->g_null_bit[c] = -1;
   }
-  DF_CHECK(bits <= 128, DFGPU_ERR_UNSUPPORTED, "aggregate: group key wider than 128 bits is not supported yet");
+  if (bits > 128 || wide) {
+    // keys beyond the exact 128-bit tag: hash tag + stored tuples + a verification pass per batch (GroupCols::wide)
+    a->wide = true;
+    a->single_null_slot = false;
+    for (int c = 0; c < n_group; ++c) { a->g_shift[c] = 0; a->g_null_bit[c] = c; }   // NULL is part of the tuple: bit c of the slot's NULL mask
+    bits = 64;
+  }
   a->key_bits = bits;
   a->kw = bits <= 64 ? 1 : 2;
   int next_state_col = n_group;
@@ -1209,7 +1342,7 @@ int dfgpu_agg_create(dfgpu_ctx* ctx, const int32_t* input_types, int32_t n_cols,
   a->special_used.alloc(ctx, 8); a->special_used.zero();
   {
     std::vector<DevBuf> acc0, acc1, seen;
-    alloc_table(a.get(), cap, &a->tags, &acc0, &acc1, &seen);
+    alloc_table(a.get(), cap, &a->tags, &acc0, &acc1, &seen, &a->kstore, &a->knull);
     for (size_t i = 0; i < a->aggs.size(); ++i) { a->aggs[i].acc0 = std::move(acc0[i]); a->aggs[i].acc1 = std::move(acc1[i]); a->aggs[i].seen = std::move(seen[i]); }
   }
   *out = a.release();
