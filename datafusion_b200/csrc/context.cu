@@ -320,28 +320,35 @@ const char* arrow_format(int type) {
     default: return "n";
   }
 }
-struct ExportPrivate {
-  std::vector<HCol> cols;  // keeps the pinned buffers alive
-  std::vector<ArrowArray> child_arrays;
-  std::vector<ArrowArray*> child_ptrs;
-  std::vector<std::vector<const void*>> child_buffers;
-  const void* top_buffers[1] = {nullptr};
-};
-struct SchemaPrivate {
-  std::vector<ArrowSchema> children;
-  std::vector<ArrowSchema*> child_ptrs;
-  std::vector<std::string> names, formats;
-};
-void release_child_array(ArrowArray* a) { a->release = nullptr; }
-void release_top_array(ArrowArray* a) {
+// Arrow C Data Interface ownership: every child is an independently released structure (a consumer may MOVE a child out of the
+// parent — copy the struct, null the original's release — and keep it after the parent is released), the parent owns the child
+// struct memory and releases the children that were not moved.
+struct ChildPrivate { HCol col; const void* buffers[2]; };          // keeps this column's pinned buffers alive
+struct ExportPrivate { std::vector<ArrowArray*> children; const void* top_buffers[1] = {nullptr}; };
+struct ChildSchemaPrivate { std::string name, format; };
+struct SchemaPrivate { std::vector<ArrowSchema*> children; };
+void release_child_array(ArrowArray* a) {
   if (!a || !a->release) return;
-  delete (ExportPrivate*)a->private_data;
+  delete (ChildPrivate*)a->private_data;
   a->release = nullptr;
 }
-void release_child_schema(ArrowSchema* s) { s->release = nullptr; }
+void release_top_array(ArrowArray* a) {
+  if (!a || !a->release) return;
+  auto* p = (ExportPrivate*)a->private_data;
+  for (ArrowArray* c : p->children) { if (c->release) c->release(c); delete c; }
+  delete p;
+  a->release = nullptr;
+}
+void release_child_schema(ArrowSchema* s) {
+  if (!s || !s->release) return;
+  delete (ChildSchemaPrivate*)s->private_data;
+  s->release = nullptr;
+}
 void release_top_schema(ArrowSchema* s) {
   if (!s || !s->release) return;
-  delete (SchemaPrivate*)s->private_data;
+  auto* p = (SchemaPrivate*)s->private_data;
+  for (ArrowSchema* c : p->children) { if (c->release) c->release(c); delete c; }
+  delete p;
   s->release = nullptr;
 }
 }  // namespace
@@ -349,43 +356,41 @@ void release_top_schema(ArrowSchema* s) {
 int dfgpu_batch_export_arrow(dfgpu_batch* b, struct ArrowArray* out_array, struct ArrowSchema* out_schema) {
   if (!b || !b->host || !out_array || !out_schema) return DFGPU_ERR_INVALID;
   auto* p = new ExportPrivate();
-  p->cols = b->hcols;  // shared_ptr copies: the buffers outlive the dfgpu_batch
-  size_t n = p->cols.size();
-  p->child_arrays.resize(n); p->child_ptrs.resize(n); p->child_buffers.resize(n);
+  const size_t n = b->hcols.size();
   for (size_t i = 0; i < n; ++i) {
-    HCol& h = p->cols[i];
-    p->child_buffers[i] = {h.validity ? h.validity->ptr : nullptr, h.values ? h.values->ptr : nullptr};
-    ArrowArray& a = p->child_arrays[i];
-    memset(&a, 0, sizeof(a));
-    a.length = h.length; a.null_count = h.validity ? h.null_count : 0; a.offset = 0;
-    a.n_buffers = 2; a.buffers = p->child_buffers[i].data();
-    a.release = release_child_array;
-    p->child_ptrs[i] = &a;
+    auto* cp = new ChildPrivate();
+    cp->col = b->hcols[i];  // shared_ptr copies: the buffers outlive the dfgpu_batch and the parent array
+    cp->buffers[0] = cp->col.validity ? cp->col.validity->ptr : nullptr;
+    cp->buffers[1] = cp->col.values ? cp->col.values->ptr : nullptr;
+    auto* a = new ArrowArray();
+    memset(a, 0, sizeof(*a));
+    a->length = cp->col.length; a->null_count = cp->col.validity ? cp->col.null_count : 0; a->offset = 0;
+    a->n_buffers = 2; a->buffers = cp->buffers;
+    a->release = release_child_array; a->private_data = cp;
+    p->children.push_back(a);
   }
   memset(out_array, 0, sizeof(*out_array));
   out_array->length = b->rows; out_array->null_count = 0; out_array->offset = 0;
   out_array->n_buffers = 1; out_array->buffers = p->top_buffers;
-  out_array->n_children = (int64_t)n; out_array->children = p->child_ptrs.data();
+  out_array->n_children = (int64_t)n; out_array->children = p->children.data();
   out_array->release = release_top_array; out_array->private_data = p;
 
   auto* sp = new SchemaPrivate();
-  sp->children.resize(n); sp->child_ptrs.resize(n); sp->names.resize(n); sp->formats.resize(n);
   for (size_t i = 0; i < n; ++i) {
-    sp->names[i] = "c" + std::to_string(i);
-    ArrowSchema& s = sp->children[i];
-    memset(&s, 0, sizeof(s));
-    s.format = arrow_format(p->cols[i].type);
-    if (type_is_decimal(p->cols[i].type) && dec_precision(p->cols[i].type) > 0) {   // "d:precision,scale"
-      sp->formats[i] = "d:" + std::to_string(dec_precision(p->cols[i].type)) + "," + std::to_string(dec_scale(p->cols[i].type));
-      s.format = sp->formats[i].c_str();
-    }
-    s.name = sp->names[i].c_str(); s.flags = ARROW_FLAG_NULLABLE;
-    s.release = release_child_schema;
-    sp->child_ptrs[i] = &s;
+    auto* csp = new ChildSchemaPrivate();
+    csp->name = "c" + std::to_string(i);
+    const int t = b->hcols[i].type;
+    csp->format = arrow_format(t);
+    if (type_is_decimal(t) && dec_precision(t) > 0) csp->format = "d:" + std::to_string(dec_precision(t)) + "," + std::to_string(dec_scale(t));   // "d:precision,scale"
+    auto* cs = new ArrowSchema();
+    memset(cs, 0, sizeof(*cs));
+    cs->format = csp->format.c_str(); cs->name = csp->name.c_str(); cs->flags = ARROW_FLAG_NULLABLE;
+    cs->release = release_child_schema; cs->private_data = csp;
+    sp->children.push_back(cs);
   }
   memset(out_schema, 0, sizeof(*out_schema));
   out_schema->format = "+s"; out_schema->name = ""; out_schema->n_children = (int64_t)n;
-  out_schema->children = sp->child_ptrs.data(); out_schema->release = release_top_schema; out_schema->private_data = sp;
+  out_schema->children = sp->children.data(); out_schema->release = release_top_schema; out_schema->private_data = sp;
   return DFGPU_OK;
 }
 

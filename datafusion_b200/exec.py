@@ -438,6 +438,8 @@ class AggregateExpr:
         if self.func == "avg":
             return pa.float64()
         if self.func == "sum":  # Sum::return_type, functions-aggregate/src/sum.rs:232-261
+            if pa.types.is_decimal128(t):
+                return pa.decimal128(min(38, t.precision + 10), t.scale)
             return pa.float64() if pa.types.is_floating(t) else pa.uint64() if pa.types.is_unsigned_integer(t) else pa.int64()
         return t
 

@@ -93,7 +93,9 @@ enum dfgpu_type {
   DFGPU_FLOAT64 = 11,
   DFGPU_DATE32 = 12,     /* int32 days  (TPC-H dates, benchmarks/src/tpch/mod.rs:52-122) */
   DFGPU_DATE64 = 13,     /* int64 ms    */
-  DFGPU_TIMESTAMP = 14,  /* int64, unit carried by the Arrow schema only */
+  DFGPU_TIMESTAMP = 14,  /* int64; unit and time zone live in the caller's schema only: any "ts?:tz" is accepted on import and
+                          * dfgpu_batch_export_arrow writes "tsn:" — the shim builds its arrays with the DataType of the operator's own
+                          * output schema (known at plan time) instead of trusting the exported format string */
   DFGPU_DECIMAL128 = 15  /* 16-byte little-endian two's complement (TPC-H money)           */
 };
 /* Decimal128(precision, scale) (arrow DataType::Decimal128; the TPC-H money columns are Decimal128(15, 2),

@@ -109,3 +109,47 @@ def test_poll_ready_is_non_blocking_and_becomes_true(gpu_ctx):
         time.sleep(0.0005)
     assert gpu_ctx.poll_ready() is True and first in (True, False)
     buf.free()
+
+
+def test_decimal_money_through_the_exec_twin(gpu_ctx, task_ctx):
+    """Decimal128(15,2) columns through the Arrow boundary: FilterExec on a decimal predicate, the revenue expression's type, SUM's
+    Decimal128(25,2) result — against pyarrow on the same record batches"""
+    import decimal
+    import pyarrow.compute as pc
+    rng = np.random.default_rng(3)
+    n = 50_000
+    price = pa.array([decimal.Decimal(int(v)).scaleb(-2) for v in rng.integers(90_000, 10_500_000, n)], pa.decimal128(15, 2))
+    disc = pa.array([None if rng.random() < 0.05 else decimal.Decimal(int(v)).scaleb(-2) for v in rng.integers(0, 11, n)], pa.decimal128(15, 2))
+    flag = pa.array(rng.integers(0, 7, n), pa.int32())
+    rb = pa.record_batch([price, disc, flag], names=["p", "d", "k"])
+    src = MemoryExec([rb.slice(0, 20_000), rb.slice(20_000)])
+    f = GpuFilterExec(col("d") >= lit(decimal.Decimal("0.05"), pa.decimal128(15, 2)), src)
+    assert (col("p") * (lit(1) - col("d"))).data_type(rb.schema) == pa.decimal128(38, 4)
+    agg = GpuAggregateExec("Single", ["k"], [AggregateExpr("sum", "p"), AggregateExpr("count", "d")], f)
+    assert agg.schema.field(1).type == pa.decimal128(25, 2)
+    got = pa.Table.from_batches(list(agg.execute(task_ctx)), schema=agg.schema).sort_by("k")
+    keep = pc.fill_null(pc.greater_equal(disc, pa.scalar(decimal.Decimal("0.05"), pa.decimal128(15, 2))), False)
+    ref = pa.table({"k": flag, "p": price, "d": disc}).filter(keep).group_by("k").aggregate([("p", "sum"), ("d", "count")]).sort_by("k")
+    assert got.column(0).to_pylist() == ref["k"].to_pylist()
+    assert got.column(1).to_pylist() == ref["p_sum"].to_pylist() and got.column(2).to_pylist() == ref["d_count"].to_pylist()
+
+
+def test_exported_arrow_children_outlive_the_parent(gpu_ctx):
+    """Arrow C Data Interface: a child moved out of the exported struct array stays valid after the parent (and the dfgpu batch) are
+    released — pyarrow's import does exactly that per column"""
+    import gc
+    from datafusion_b200 import capi as D
+    x = np.arange(100_000, dtype=np.int64)
+    f = D.FilterHandle(gpu_ctx, [D.INT64], [(D.EXPR_COLUMN, 0, 0, 0, 0, 0.0), (D.EXPR_LITERAL, 0, D.INT64, 0, 49_999, 0.0), (D.EXPR_BINARY, D.OP_GT, 0, 0, 0, 0.0)], None, 1 << 20, -1)
+    f.push_host([D.HostColumn(x)]); f.finish()
+    outs = f.drain(host=True)
+    rbs = [b.to_arrow() for b in outs]
+    cols = [rb.column(0) for rb in rbs]          # the children alone
+    for b in outs:
+        b.release()
+    del outs, rbs
+    f.close()
+    gc.collect()
+    junk = [np.ones(1 << 20, np.int64) for _ in range(8)]     # churn the host allocator
+    assert pa.concat_arrays(cols).to_numpy().tolist() == list(range(50_000, 100_000))
+    del junk
