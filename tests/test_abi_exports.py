@@ -85,3 +85,22 @@ def test_struct_layouts_match_the_header(tmp_path):
         for item in parts[2:]:
             fname, off = item.split("=")
             assert getattr(st, fname).offset == int(off), (parts[0], fname)
+
+
+def test_decimal_type_codes_match_the_header_macros(tmp_path):
+    """capi.decimal128(p, s) / decimal_precision_scale must encode exactly like DFGPU_DECIMAL128_TYPE / DFGPU_DECIMAL_PRECISION / _SCALE"""
+    cases = [(15, 2), (38, 4), (20, 0), (1, 1), (38, 38), (10, -2)]
+    lines = ['#include <stdio.h>', '#include "dfgpu.h"', 'int main(void) {']
+    for p, s in cases:
+        lines.append(f'  printf("%d %d %d %d\\n", DFGPU_DECIMAL128_TYPE({p}, {s}), DFGPU_TYPE_BASE(DFGPU_DECIMAL128_TYPE({p}, {s})), '
+                     f'DFGPU_DECIMAL_PRECISION(DFGPU_DECIMAL128_TYPE({p}, {s})), DFGPU_DECIMAL_SCALE(DFGPU_DECIMAL128_TYPE({p}, {s})));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "dec.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "dec"
+    subprocess.run(["gcc", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    for (p, s), line in zip(cases, out):
+        code, base, cp, cs = (int(x) for x in line.split())
+        assert code == capi.decimal128(p, s) and base == capi.DECIMAL128 == capi.type_base(code)
+        assert (cp, cs) == (p, s) == capi.decimal_precision_scale(code)
