@@ -259,6 +259,102 @@ def _drain(op, schema) -> Iterator[pa.RecordBatch]:
         yield _rename(b.to_arrow(), schema)
 
 
+# ---------------------------------------------------------------------------------------------
+# string keys — Utf8 / Utf8View / Dictionary(_, Utf8) columns as INT32 codes in ONE code space (dfgpu_dictionary)
+# ---------------------------------------------------------------------------------------------
+def _is_string_like(t: pa.DataType) -> bool:
+    if pa.types.is_dictionary(t):
+        t = t.value_type
+    return pa.types.is_string(t) or pa.types.is_large_string(t) or (hasattr(pa.types, "is_string_view") and pa.types.is_string_view(t))
+
+
+class StringDictionary:
+    """the plan-wide code space: equal strings <=> equal codes in every column, every batch and on both sides of a join"""
+
+    def __init__(self, ctx: TaskContext):
+        self.ctx = ctx
+        self.dic = D.Dictionary(ctx.gpu)
+
+    def encode(self, arr: pa.Array) -> pa.Array:
+        """string-like array -> int32 codes (NULL stays NULL): the batch's own dictionary is unified on the host (distinct values only),
+        the row codes are rewritten on the device (dfgpu_dictionary_remap)"""
+        import numpy as np
+        if isinstance(arr, pa.ChunkedArray):
+            arr = arr.combine_chunks()
+        d = arr if pa.types.is_dictionary(arr.type) else arr.dictionary_encode()
+        values = d.dictionary.cast(pa.string())
+        bufs = values.buffers()
+        offsets = np.frombuffer(bufs[1], np.int32, len(values) + 1, values.offset * 4) if len(values) else np.zeros(1, np.int32)
+        data = np.frombuffer(bufs[2], np.uint8) if bufs[2] is not None else np.zeros(0, np.uint8)
+        vvalid = None if values.null_count == 0 else np.asarray(values.is_valid())
+        remap = self.dic.unify(offsets, data, vvalid)
+        idx = d.indices.cast(pa.int32())
+        codes = D.HostColumn(np.asarray(idx.fill_null(0)), None if idx.null_count == 0 else np.asarray(idx.is_valid()))
+        b = self.dic.remap(codes, remap, on_host=True)
+        v, valid = b.column_numpy(0)
+        b.release()
+        return pa.array(v, pa.int32(), mask=None if valid is None else ~valid)
+
+    def decode(self, codes: pa.Array, to: pa.DataType) -> pa.Array:
+        n = self.dic.size()
+        values = pa.array([self.dic.value(i).decode() for i in range(n)], pa.string())
+        if isinstance(codes, pa.ChunkedArray):
+            codes = codes.combine_chunks()
+        out = pa.DictionaryArray.from_arrays(codes.cast(pa.int32()), values)
+        return out if pa.types.is_dictionary(to) else out.cast(to)
+
+    def code(self, s: str) -> int:
+        """the literal of `col = 'text'`: -1 when the string was never seen (matches nothing)"""
+        return self.dic.code(s.encode())
+
+    def close(self):
+        self.dic.close()
+
+
+class DictionaryEncodeExec(ExecutionPlan):
+    """string-like columns of the input -> INT32 code columns (same names); everything else passes through"""
+
+    def __init__(self, input: ExecutionPlan, dictionary_of: "callable"):
+        self.input, self.dictionary_of = input, dictionary_of
+        self.string_cols = [i for i, f in enumerate(input.schema) if _is_string_like(f.type)]
+        self.schema = pa.schema([pa.field(f.name, pa.int32(), True) if i in self.string_cols else f for i, f in enumerate(input.schema)])
+
+    def children(self): return [self.input]
+
+    def execute(self, ctx):
+        sd = self.dictionary_of(ctx)
+        for rb in self.input.execute(ctx):
+            cols = [sd.encode(rb.column(i)) if i in self.string_cols else rb.column(i) for i in range(rb.num_columns)]
+            yield pa.RecordBatch.from_arrays(cols, schema=self.schema)
+
+
+class DictionaryDecodeExec(ExecutionPlan):
+    """INT32 code columns `names` of the input -> strings of type `to` (after the GPU operators)"""
+
+    def __init__(self, input: ExecutionPlan, names: Sequence[str], dictionary_of: "callable", to: pa.DataType = pa.string()):
+        self.input, self.names, self.dictionary_of, self.to = input, list(names), dictionary_of, to
+        self.schema = pa.schema([pa.field(f.name, to, True) if f.name in self.names else f for f in input.schema])
+
+    def children(self): return [self.input]
+
+    def execute(self, ctx):
+        sd = self.dictionary_of(ctx)
+        for rb in self.input.execute(ctx):
+            cols = [sd.decode(rb.column(i), self.to) if f.name in self.names else rb.column(i) for i, f in enumerate(rb.schema)]
+            yield pa.RecordBatch.from_arrays(cols, schema=self.schema)
+
+
+def plan_string_dictionary():
+    """a factory for the `dictionary_of` argument: one StringDictionary per TaskContext, created on first use"""
+    cache = {}
+
+    def get(ctx: TaskContext) -> StringDictionary:
+        if id(ctx) not in cache:
+            cache[id(ctx)] = StringDictionary(ctx)
+        return cache[id(ctx)]
+    return get
+
+
 class GpuFilterExec(ExecutionPlan):
     """FilterExec (physical-plan/src/filter.rs:85): FilterExecBuilder::new(predicate, input).with_projection(..).with_fetch(..)"""
 

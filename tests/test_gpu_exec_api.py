@@ -5,7 +5,7 @@ import numpy as np
 import pyarrow as pa
 import pytest
 
-from datafusion_b200.exec import (AggregateExpr, GpuAggregateExec, GpuFilterExec, GpuHashJoinExec, JoinFilter, MemoryExec, SessionConfig, TaskContext,
+from datafusion_b200.exec import (AggregateExpr, DictionaryDecodeExec, DictionaryEncodeExec, GpuAggregateExec, GpuFilterExec, GpuHashJoinExec, JoinFilter, MemoryExec, SessionConfig, TaskContext, plan_string_dictionary,
                                   col, collect, lit)
 from harness import load_golden
 
@@ -153,3 +153,35 @@ def test_exported_arrow_children_outlive_the_parent(gpu_ctx):
     junk = [np.ones(1 << 20, np.int64) for _ in range(8)]     # churn the host allocator
     assert pa.concat_arrays(cols).to_numpy().tolist() == list(range(50_000, 100_000))
     del junk
+
+
+def test_string_keys_through_the_exec_twin(gpu_ctx, task_ctx):
+    """Utf8 and Dictionary(Int32, Utf8) key columns: DictionaryEncodeExec -> GpuHashJoinExec -> GpuAggregateExec -> DictionaryDecodeExec,
+    one plan-wide code space; against pyarrow joining and grouping on the strings themselves"""
+    rng = np.random.default_rng(12)
+    words = ["AUTOMOBILE", "BUILDING", "FURNITURE", "MACHINERY", "HOUSEHOLD", "", "büilding", "x" * 200]
+    nl, nr = 400, 9000
+    lseg = [None if rng.random() < 0.05 else words[int(rng.integers(0, 6))] for _ in range(nl)]            # plain Utf8, 6 of the 8 words
+    left = pa.record_batch([pa.array(lseg, pa.string()), pa.array(np.arange(nl), pa.int64())], names=["seg", "lid"])
+    rbatches, rseg_all, rv_all = [], [], []
+    for part in range(3):                                                                                   # dictionary arrays, another dictionary per batch
+        local = [words[i] for i in rng.permutation(len(words))[: int(rng.integers(2, 9))]]
+        idx = rng.integers(0, len(local), nr // 3)
+        mask = rng.random(nr // 3) < 0.04
+        seg = pa.DictionaryArray.from_arrays(pa.array(idx.astype(np.int32), mask=mask), pa.array(local, pa.string()))
+        v = rng.integers(-100, 100, nr // 3).astype(np.int64)
+        rbatches.append(pa.record_batch([seg, pa.array(v)], names=["seg_r", "v"]))
+        rseg_all += seg.to_pylist(); rv_all += v.tolist()
+    dictionary_of = plan_string_dictionary()
+    join = GpuHashJoinExec(DictionaryEncodeExec(MemoryExec([left]), dictionary_of), DictionaryEncodeExec(MemoryExec(rbatches), dictionary_of), [("seg", "seg_r")], "Inner")
+    agg = GpuAggregateExec("Single", ["seg"], [AggregateExpr("sum", "v"), AggregateExpr("count_star", None), AggregateExpr("sum", "lid")], join)
+    out = DictionaryDecodeExec(agg, ["seg"], dictionary_of)
+    assert out.schema.field(0).type == pa.string()
+    got = pa.Table.from_batches(list(out.execute(task_ctx)), schema=out.schema).sort_by("seg")
+    lt = pa.table({"seg": pa.array(lseg, pa.string()), "lid": np.arange(nl)})
+    rt = pa.table({"seg_r": pa.array(rseg_all, pa.string()), "v": rv_all})
+    ref = lt.join(rt, keys="seg", right_keys="seg_r", join_type="inner").group_by("seg").aggregate([("v", "sum"), ([], "count_all"), ("lid", "sum")]).sort_by("seg")
+    assert got.column(0).to_pylist() == ref["seg"].to_pylist() and len(ref) >= 5
+    assert got.column(1).to_pylist() == ref["v_sum"].to_pylist()
+    assert got.column(2).to_pylist() == ref["count_all"].to_pylist() and got.column(3).to_pylist() == ref["lid_sum"].to_pylist()
+    dictionary_of(task_ctx).close()
