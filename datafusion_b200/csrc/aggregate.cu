@@ -387,6 +387,7 @@ __global__ void __launch_bounds__(256) agg_verify_wide_kernel(GroupCols g, Table
 // (SUM over a non-null 8-byte integer column, COUNT / COUNT(*) without NULLs or FILTER, and their Final-mode
 // merges) — the C3 shape.  No type switches, no validity reads; 4 rows per thread with the loads hoisted.
 constexpr int kMaxFastAggs = 4;
+constexpr int kAggPairedDefault = 0;
 struct FastAggs { int n; const unsigned long long* col[kMaxFastAggs]; unsigned long long* acc[kMaxFastAggs]; };
 
 template <int R, int NA, int B>
@@ -458,6 +459,96 @@ __global__ void __launch_bounds__(256) agg_update_fast_kernel(const unsigned lon
 #pragma unroll
       for (int a = 0; a < NA; ++a) atomicAdd(&fa.acc[a][slot], v[r][a]);
     }
+  }
+}
+
+// ---- paired accumulators: the two-aggregate fast path (SUM + COUNT, the C3 shape) with ONE L2 reduction request per row ----
+// The kernel above is bound by the number of L2 atomic requests (two RED instructions per row, 32 distinct sectors each).  Here the
+// slot's two accumulators are adjacent — pairs[slot] = {acc of aggregate 0, acc of aggregate 1}, one 16-byte half-sector — and a lane
+// PAIR updates one slot with one RED instruction: in the first instruction the even lane adds its row's first value while its odd
+// neighbour adds the same row's second value (same sector, same instruction: the LSU hands L2 one sector request with two active
+// words); the second instruction does the odd lanes' rows.  A warp's RED instruction touches 16 sectors instead of 32.
+// `pairs` holds additive deltas only; agg_fold_pairs_kernel adds them into the per-aggregate arrays before anything else reads those.
+__device__ __forceinline__ void red_add_u64_pred(unsigned long long* p, unsigned long long v, bool on) {
+  if (on) asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+template <int R>
+__global__ void __launch_bounds__(256) agg_update_pair_kernel(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ col0,
+                                                           const unsigned long long* __restrict__ col1, ulonglong2* __restrict__ pairs, TableDev t,
+                                                           int64_t row0, int64_t n, const uint32_t* __restrict__ row_list, uint32_t* __restrict__ overflow,
+                                                           unsigned long long* __restrict__ overflow_count) {
+  const int lane = threadIdx.x & 31;
+  const bool even = !(lane & 1);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // the trip count is warp-uniform (lanes past the end stay in the loop, dead): the lane pairs exchange values with full-mask shuffles
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 - lane < n; i0 += stride * R) {
+    int64_t row[R];
+    unsigned long long k[R], cur[R], v0[R], v1[R];
+    uint4 bk0[R], bk1[R];
+    uint64_t s[R];
+    bool live[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t i = i0 + r * stride;
+      live[r] = i < n;
+      row[r] = live[r] ? row0 + (row_list ? (int64_t)row_list[i] : i) : row0;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) k[r] = live[r] ? keys[row[r]] : 0ull;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      v0[r] = (col0 && live[r]) ? col0[row[r]] : 1ull;
+      v1[r] = (col1 && live[r]) ? col1[row[r]] : 1ull;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) { s[r] = start_slot<1>(t, Key2{k[r], 0ull}); cur[r] = 0; }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      bk0[r] = make_uint4(0, 0, 0, 0); bk1[r] = bk0[r];
+      if (live[r] && k[r] != kEmptyKey) { const uint4* bp = (const uint4*)((const unsigned long long*)t.tags + s[r]); bk0[r] = __ldcg(bp); bk1[r] = __ldcg(bp + 1); }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (!(live[r] && k[r] != kEmptyKey)) continue;
+      const unsigned long long t0 = (unsigned long long)bk0[r].x | ((unsigned long long)bk0[r].y << 32), t1 = (unsigned long long)bk0[r].z | ((unsigned long long)bk0[r].w << 32);
+      const unsigned long long t2 = (unsigned long long)bk1[r].x | ((unsigned long long)bk1[r].y << 32), t3 = (unsigned long long)bk1[r].z | ((unsigned long long)bk1[r].w << 32);
+      if (t0 == k[r] || t0 == kEmptyKey) { cur[r] = t0; }
+      else if (t1 == k[r] || t1 == kEmptyKey) { cur[r] = t1; s[r] += 1; }
+      else if (t2 == k[r] || t2 == kEmptyKey) { cur[r] = t2; s[r] += 2; }
+      else { cur[r] = t3; s[r] += 3; }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      bool claimed = false;
+      uint64_t slot = ~0ull;
+      if (live[r]) {
+        if (k[r] == kEmptyKey) slot = find_or_claim<1>(t, Key2{k[r], 0ull}, false, true, &claimed);
+        else slot = find_or_claim_from<1>(t, Key2{k[r], 0ull}, s[r], Key2{cur[r], 0ull}, &claimed);
+      }
+      __syncwarp();
+      const unsigned m = __ballot_sync(0xffffffffu, claimed);
+      if (m && lane == __ffs(m) - 1) atomicAdd(t.ngroups, (unsigned long long)__popc(m));
+      const bool ok = live[r] && slot != ~0ull;
+      if (live[r] && !ok) {   // table budget exhausted: the host grows the table and replays the row
+        const unsigned long long pos = atomicAdd(overflow_count, 1ull);
+        overflow[pos] = (uint32_t)(row[r] - row0);
+      }
+      __syncwarp();
+      const uint32_t ms = (uint32_t)slot;                                       // the launcher guarantees cap + 2 < 2^32
+      const uint32_t ps = __shfl_xor_sync(0xffffffffu, ms, 1);                  // the neighbour's slot, second value, row state
+      const unsigned long long pv1 = __shfl_xor_sync(0xffffffffu, v1[r], 1);
+      const bool pok = __shfl_xor_sync(0xffffffffu, ok ? 1 : 0, 1) != 0;
+      unsigned long long* const mine = &pairs[ok ? ms : 0u].x;                  // this lane's row, first accumulator
+      unsigned long long* const theirs = &pairs[pok ? ps : 0u].y;               // the neighbour's row, second accumulator
+      red_add_u64_pred(even ? mine : theirs, even ? v0[r] : pv1, even ? ok : pok);    // rows of the even lanes
+      red_add_u64_pred(even ? theirs : mine, even ? pv1 : v0[r], even ? pok : ok);    // rows of the odd lanes
+    }
+  }
+}
+__global__ void __launch_bounds__(256) agg_fold_pairs_kernel(ulonglong2* __restrict__ pairs, unsigned long long* __restrict__ acc_a, unsigned long long* __restrict__ acc_b, uint64_t n) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const ulonglong2 p = pairs[i];
+    if (p.x | p.y) { acc_a[i] += p.x; acc_b[i] += p.y; pairs[i] = make_ulonglong2(0ull, 0ull); }
   }
 }
 
@@ -724,6 +815,11 @@ struct dfgpu_agg {
   // table
   DevBuf tags, counters /* [ngroups, overflow_count] */, special_used;
   uint64_t cap = 0;
+  // paired accumulators of the two-aggregate fast path (agg_update_pair_kernel): additive deltas, folded into aggs[0/1].acc0 before those are read
+  DevBuf pairs;
+  uint64_t pairs_cap = 0;
+  bool pairs_dirty = false;
+  int paired_mode = 0;   // DFGPU_AGG_PAIRED at create: 0 = one RED per aggregate and row; 1 / 2 = agg_update_pair_kernel with 2 / 4 rows in flight per thread
   std::deque<BatchPtr> outq;
   int64_t m_input_rows = 0, m_output_rows = 0, m_rehashes = 0, m_num_groups = 0, m_input_batches = 0;
   // skip-partial-aggregation probe (aggregates/skip_partial.rs:69-110; config.rs skip_partial_aggregation_probe_*)
@@ -781,8 +877,20 @@ static void alloc_table(dfgpu_agg* a, uint64_t cap, DevBuf* tags, std::vector<De
   }
 }
 
+// add the paired fast path's deltas into the per-aggregate accumulator arrays (every reader of those arrays calls this first)
+static void fold_pairs(dfgpu_agg* a) {
+  if (!a->pairs_dirty) return;
+  dfgpu_ctx* ctx = a->ctx;
+  const uint64_t total = a->pairs_cap + 2;
+  agg_fold_pairs_kernel<<<grid_for((int64_t)total, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(a->pairs.as<ulonglong2>(), a->aggs[0].acc0.as<unsigned long long>(),
+                                                                                          a->aggs[1].acc0.as<unsigned long long>(), total);
+  DF_LAUNCH_CHECK(ctx);
+  a->pairs_dirty = false;
+}
+
 static void grow_table(dfgpu_agg* a, uint64_t new_cap) {
   dfgpu_ctx* ctx = a->ctx;
+  fold_pairs(a);
   DevBuf ntags, ncounters(ctx, 16), nspecial(ctx, 8);
   std::vector<DevBuf> nacc0, nacc1, nseen, nkstore;
   DevBuf nknull;
@@ -958,6 +1066,10 @@ static void agg_push(dfgpu_agg* a, const std::vector<DCol>& cols) {
     fa.col[i] = sum_like ? (const unsigned long long*)d.in0 : nullptr;
   }
   fa.n = set.n;
+  const int paired_env = a->paired_mode;
+  static const int fast_r4 = getenv("DFGPU_AGG_R4") ? atoi(getenv("DFGPU_AGG_R4")) : 0;
+  const bool use_pair = fast && paired_env > 0 && fa.n == 2 && a->bucketed;
+  if (!use_pair) fold_pairs(a);   // the kernels below update the per-aggregate arrays directly
   auto refresh_ptrs = [&]() {
     for (int i = 0; i < set.n; ++i) {
       set.a[i].acc0 = a->aggs[i].acc0.as<unsigned long long>();
@@ -994,11 +1106,24 @@ static void agg_push(dfgpu_agg* a, const std::vector<DCol>& cols) {
           const unsigned long long* kp = (const unsigned long long*)g.ptr[0];
           uint32_t* ov = overflow.as<uint32_t>();
           unsigned long long* oc = a->counters.as<unsigned long long>() + 1;
-          if (a->bucketed) {
+          if (use_pair && a->cap + 2 < (1ull << 32)) {
+            if (a->pairs_cap != a->cap || !a->pairs.ptr) {   // first use, or the table grew (grow_table folded the old deltas)
+              a->pairs.alloc(ctx, (size_t)(a->cap + 2) * 16);
+              a->pairs.zero();
+              a->pairs_cap = a->cap;
+            }
+            a->pairs_dirty = true;
+            if (paired_env >= 2) agg_update_pair_kernel<4><<<grid, 256, 0, ctx->stream>>>(kp, fa.col[0], fa.col[1], a->pairs.as<ulonglong2>(), t, done, work, list, ov, oc);
+            else agg_update_pair_kernel<2><<<grid_for((work + 1) / 2, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(kp, fa.col[0], fa.col[1], a->pairs.as<ulonglong2>(), t, done, work, list, ov, oc);
+          } else if (a->bucketed) {
+            if (use_pair) fold_pairs(a);
             const int grid2 = grid_for((work + 1) / 2, 256, kNumSMs * 8);
             switch (fa.n) {
               case 1: agg_update_fast_kernel<2, 1, 1><<<grid2, 256, 0, ctx->stream>>>(kp, fa, t, done, work, list, ov, oc); break;
-              case 2: agg_update_fast_kernel<2, 2, 1><<<grid2, 256, 0, ctx->stream>>>(kp, fa, t, done, work, list, ov, oc); break;
+              case 2:
+                if (fast_r4) agg_update_fast_kernel<4, 2, 1><<<grid, 256, 0, ctx->stream>>>(kp, fa, t, done, work, list, ov, oc);   // A/B switch: 4 rows in flight per thread
+                else agg_update_fast_kernel<2, 2, 1><<<grid2, 256, 0, ctx->stream>>>(kp, fa, t, done, work, list, ov, oc);
+                break;
               case 3: agg_update_fast_kernel<2, 3, 1><<<grid2, 256, 0, ctx->stream>>>(kp, fa, t, done, work, list, ov, oc); break;
               default: agg_update_fast_kernel<2, 4, 1><<<grid2, 256, 0, ctx->stream>>>(kp, fa, t, done, work, list, ov, oc); break;
             }
@@ -1119,6 +1244,7 @@ static void agg_finish(dfgpu_agg* a) {
 
 static void agg_emit_table(dfgpu_agg* a) {
   dfgpu_ctx* ctx = a->ctx;
+  fold_pairs(a);
   // emit = group_values.emit(EmitTo::All) ++ acc.state()/evaluate() (common.rs:247-297)
   TableDev t = table_dev(a, a->tags, a->cap, a->counters, a->special_used);
   const uint64_t total = a->cap + 2;
@@ -1335,6 +1461,7 @@ int dfgpu_agg_create(dfgpu_ctx* ctx, const int32_t* input_types, int32_t n_cols,
   static const int cap_mult = getenv("DFGPU_AGG_CAPMULT") ? atoi(getenv("DFGPU_AGG_CAPMULT")) : 3;
   static const int bucket_env = getenv("DFGPU_AGG_BUCKET") ? atoi(getenv("DFGPU_AGG_BUCKET")) : 1;
   a->bucketed = bucket_env != 0;
+  a->paired_mode = getenv("DFGPU_AGG_PAIRED") ? atoi(getenv("DFGPU_AGG_PAIRED")) : kAggPairedDefault;
   if (capacity_hint > 0) { cap = std::max<uint64_t>(cap, (uint64_t)capacity_hint * cap_mult); a->hinted = true; }
   cap = (cap + 3) & ~3ull;
   a->cap = cap;
