@@ -43,6 +43,7 @@ enum LookupMode : int { LK_HASH = 0, LK_BITMAP = 1 };
 enum SinkKind : int { SINK_NONE = 0, SINK_COUNT = 1, SINK_BUILD = 2, SINK_AGG = 3, SINK_OUTPUT = 4, SINK_OUTPUT_ANY = 5 /* row order unspecified */,
                       SINK_PACK = 6 /* build sink, table size unknown: {key, payload} records to a staging buffer, inserted afterwards */ };
 constexpr int kStageMaybe = 3;   // DFGPU_STAGE_MAYBE
+constexpr int kPipeVarDefault = 0;   // pipe_kernel's VAR when DFGPU_PIPE_VAR is not set
 
 struct LookupDev {
   int mode, stride /* 8-byte words per record */, has_payload, pad;
@@ -292,7 +293,12 @@ __device__ __forceinline__ uint32_t valid8(const ColRef& c, int64_t row0, int64_
   return nb > 0 ? load_bits32(c.valid, c.voff + row0, nb) : 0u;
 }
 
-template <int SINK, bool DEC>
+// VAR (compile-time, so the default instantiation's code stays what was measured): bit 0 = at the start of phase B, prefetch the argument
+// columns' sectors of the survivors into L2 (the interpreter reads them one dependent DRAM access after the other otherwise);
+// bit 1 = at the start of phase A, prefetch this tile's key column of the first stage (its load is issued only after the predicate's
+// column has arrived and been compared).  DFGPU_PIPE_VAR selects the instantiation (aggregate sink only).
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+template <int SINK, bool DEC, int VAR = 0>
 __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams* __restrict__ gp, int64_t n, unsigned long long* __restrict__ counters /* [alive, inserted, fail, err] */) {
   __shared__ PipeParams sp;
   __shared__ uint32_t q_rows[kPipeWarps][kQueueCap];
@@ -314,6 +320,10 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
       // =============================== phase A ===============================
       const int64_t row0 = tile * kWarpTile + (int64_t)lane * kWarpRows;
       uint32_t mask = row0 + kWarpRows <= n ? 0xFFu : (row0 < n ? (1u << (int)(n - row0)) - 1u : 0u);
+      if ((VAR & 2) && sp.n_stages > 0 && row0 < n) {
+        const ColRef& kc0 = sp.col[sp.stage[0].key_col];
+        prefetch_l2((const char*)kc0.ptr + row0 * kc0.width);
+      }
       if (sp.pred_mode == 1) {   // FilterExec, conjunction of `column <cmp> literal`
 #pragma unroll 1
         for (int t = 0; t < sp.n_terms; ++t) {
@@ -433,6 +443,21 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
       for (int u = 0; u < kPhaseB; ++u) {
         const unsigned int e = u * 32 + lane;
         live[u] = e < take; row[u] = live[u] ? (int64_t)q_row[qbase + e] : 0; arec[u] = nullptr;
+      }
+      if ((VAR & 1) && SINK == SINK_AGG) {
+#pragma unroll 1
+        for (int a = 0; a < sp.n_aggs; ++a) {
+          const AggDef& ag = sp.agg[a];
+          if (ag.small != 2) continue;
+#pragma unroll 1
+          for (int i = 0; i < ag.n; ++i) {
+            const ENode& nd = sp.pool[ag.start + i];
+            if (nd.kind != DFGPU_EXPR_COLUMN) continue;
+            const int w = type_width_prim(nd.out_type);
+#pragma unroll
+            for (int u = 0; u < kPhaseB; ++u) if (live[u]) prefetch_l2((const char*)nd.col + row[u] * w);
+          }
+        }
       }
 #pragma unroll
       for (int s = 0; s < kMaxStages; ++s) {
@@ -1137,8 +1162,14 @@ static void launch_pipe(dfgpu_pipeline* p, int64_t n, const char* timer_name) {
   const int grid = (int)std::min<int64_t>(ntiles, (int64_t)kNumSMs * blocks_per_sm);
   const std::string tname = p->name.empty() ? std::string(timer_name) : "pipe:" + p->name;
   KernelTimer kt(ctx, tname.c_str());
-  if (dec) pipe_kernel<SINK, true><<<grid, kPipeThreads, 0, ctx->stream>>>((const PipeParams*)p->params_dev.ptr, n, p->counters.as<unsigned long long>());
-  else pipe_kernel<SINK, false><<<grid, kPipeThreads, 0, ctx->stream>>>((const PipeParams*)p->params_dev.ptr, n, p->counters.as<unsigned long long>());
+  const int var_env = getenv("DFGPU_PIPE_VAR") ? atoi(getenv("DFGPU_PIPE_VAR")) : kPipeVarDefault;
+  const PipeParams* gp = (const PipeParams*)p->params_dev.ptr;
+  unsigned long long* cnt = p->counters.as<unsigned long long>();
+  if (dec) pipe_kernel<SINK, true><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
+  else if (SINK == SINK_AGG && var_env == 1) pipe_kernel<SINK_AGG, false, 1><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
+  else if (SINK == SINK_AGG && var_env == 2) pipe_kernel<SINK_AGG, false, 2><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
+  else if (SINK == SINK_AGG && var_env == 3) pipe_kernel<SINK_AGG, false, 3><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
+  else pipe_kernel<SINK, false><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   DF_LAUNCH_CHECK(ctx);
 }
 
