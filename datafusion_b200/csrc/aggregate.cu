@@ -819,6 +819,7 @@ struct dfgpu_agg {
   DevBuf pairs;
   uint64_t pairs_cap = 0;
   bool pairs_dirty = false;
+  int fast_r4 = 0;       // DFGPU_AGG_R4 at create (A/B switch): the two-aggregate fast kernel with 4 instead of 2 rows in flight per thread
   int paired_mode = 0;   // DFGPU_AGG_PAIRED at create: 0 = one RED per aggregate and row; 1 / 2 = agg_update_pair_kernel with 2 / 4 rows in flight per thread
   std::deque<BatchPtr> outq;
   int64_t m_input_rows = 0, m_output_rows = 0, m_rehashes = 0, m_num_groups = 0, m_input_batches = 0;
@@ -1067,7 +1068,7 @@ static void agg_push(dfgpu_agg* a, const std::vector<DCol>& cols) {
   }
   fa.n = set.n;
   const int paired_env = a->paired_mode;
-  static const int fast_r4 = getenv("DFGPU_AGG_R4") ? atoi(getenv("DFGPU_AGG_R4")) : 0;
+  const int fast_r4 = a->fast_r4;
   const bool use_pair = fast && paired_env > 0 && fa.n == 2 && a->bucketed;
   if (!use_pair) fold_pairs(a);   // the kernels below update the per-aggregate arrays directly
   auto refresh_ptrs = [&]() {
@@ -1461,6 +1462,7 @@ int dfgpu_agg_create(dfgpu_ctx* ctx, const int32_t* input_types, int32_t n_cols,
   static const int cap_mult = getenv("DFGPU_AGG_CAPMULT") ? atoi(getenv("DFGPU_AGG_CAPMULT")) : 3;
   static const int bucket_env = getenv("DFGPU_AGG_BUCKET") ? atoi(getenv("DFGPU_AGG_BUCKET")) : 1;
   a->bucketed = bucket_env != 0;
+  a->fast_r4 = getenv("DFGPU_AGG_R4") ? atoi(getenv("DFGPU_AGG_R4")) : 0;
   a->paired_mode = getenv("DFGPU_AGG_PAIRED") ? atoi(getenv("DFGPU_AGG_PAIRED")) : kAggPairedDefault;
   if (capacity_hint > 0) { cap = std::max<uint64_t>(cap, (uint64_t)capacity_hint * cap_mult); a->hinted = true; }
   cap = (cap + 3) & ~3ull;

@@ -300,8 +300,9 @@ __device__ __forceinline__ uint32_t valid8(const ColRef& c, int64_t row0, int64_
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 template <int SINK, bool DEC, int VAR = 0>
 __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams* __restrict__ gp, int64_t n, unsigned long long* __restrict__ counters /* [alive, inserted, fail, err] */) {
+  constexpr int PB = (VAR & 4) ? 4 : kPhaseB, PBG = 32 * PB, QC = PBG + kWarpTile;   // bit 2: four instead of two survivors per lane and phase-B round
   __shared__ PipeParams sp;
-  __shared__ uint32_t q_rows[kPipeWarps][kQueueCap];
+  __shared__ uint32_t q_rows[kPipeWarps][QC];
   for (int i = threadIdx.x; i < (int)(sizeof(PipeParams) / 4); i += kPipeThreads) ((uint32_t*)&sp)[i] = ((const uint32_t*)gp)[i];
   __syncthreads();
   const uint64_t pol_stream = (sp.hints & 1) ? policy_evict_first() : policy_normal();
@@ -432,15 +433,15 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
       __syncwarp();
     }
     // =============================== phase B ===============================
-    while (qn >= (unsigned)kPhaseBGroup || (draining && qn > 0)) {
-      const unsigned int take = qn >= (unsigned)kPhaseBGroup ? (unsigned)kPhaseBGroup : qn;
+    while (qn >= (unsigned)PBG || (draining && qn > 0)) {
+      const unsigned int take = qn >= (unsigned)PBG ? (unsigned)PBG : qn;
       const unsigned int qbase = qn - take;   // consume from the tail: nothing has to move
-      bool live[kPhaseB];
-      int64_t row[kPhaseB];
-      uint64_t pay[kMaxStages][kPhaseB];
-      unsigned long long* arec[kPhaseB];
+      bool live[PB];
+      int64_t row[PB];
+      uint64_t pay[kMaxStages][PB];
+      unsigned long long* arec[PB];
 #pragma unroll
-      for (int u = 0; u < kPhaseB; ++u) {
+      for (int u = 0; u < PB; ++u) {
         const unsigned int e = u * 32 + lane;
         live[u] = e < take; row[u] = live[u] ? (int64_t)q_row[qbase + e] : 0; arec[u] = nullptr;
       }
@@ -455,22 +456,22 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
             if (nd.kind != DFGPU_EXPR_COLUMN) continue;
             const int w = type_width_prim(nd.out_type);
 #pragma unroll
-            for (int u = 0; u < kPhaseB; ++u) if (live[u]) prefetch_l2((const char*)nd.col + row[u] * w);
+            for (int u = 0; u < PB; ++u) if (live[u]) prefetch_l2((const char*)nd.col + row[u] * w);
           }
         }
       }
 #pragma unroll
       for (int s = 0; s < kMaxStages; ++s) {
 #pragma unroll
-        for (int u = 0; u < kPhaseB; ++u) pay[s][u] = 0;
+        for (int u = 0; u < PB; ++u) pay[s][u] = 0;
         if (s >= sp.n_stages) continue;
         const StageDev& st = sp.stage[s];
         if (st.lk.mode == LK_BITMAP || st.kind == kStageMaybe) continue;   // decided in phase A
         const ColRef kc = sp.col[st.key_col];
-        uint64_t key[kPhaseB], slot[kPhaseB], ck[kPhaseB], cp[kPhaseB];
-        bool look[kPhaseB], found[kPhaseB];
+        uint64_t key[PB], slot[PB], ck[PB], cp[PB];
+        bool look[PB], found[PB];
 #pragma unroll
-        for (int u = 0; u < kPhaseB; ++u) {
+        for (int u = 0; u < PB; ++u) {
           found[u] = false; look[u] = live[u]; key[u] = 0;
           if (look[u]) {
             key[u] = ld_stream_int(kc.ptr, kc.width, kc.sgn, row[u], pol_stream);   // the line was streamed in moments ago: an L2 hit
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
           }
         }
 #pragma unroll
-        for (int u = 0; u < kPhaseB; ++u) {
+        for (int u = 0; u < PB; ++u) {
           if (look[u]) {
             while (true) {   // linear probing continues only past a foreign key (load factor <= 0.5)
               if (ck[u] == key[u]) { found[u] = true; break; }
@@ -501,14 +502,14 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
       }
       // ---- sink ----
       if (SINK == SINK_OUTPUT_ANY) {   // rows leave in arrival order: one global reservation per 128-row group, coalesced column writes
-        unsigned int tot = 0, mypos[kPhaseB];
+        unsigned int tot = 0, mypos[PB];
 #pragma unroll
-        for (int u = 0; u < kPhaseB; ++u) { const unsigned m = __ballot_sync(0xffffffffu, live[u]); mypos[u] = tot + __popc(m & ((1u << lane) - 1u)); tot += __popc(m); }
+        for (int u = 0; u < PB; ++u) { const unsigned m = __ballot_sync(0xffffffffu, live[u]); mypos[u] = tot + __popc(m & ((1u << lane) - 1u)); tot += __popc(m); }
         unsigned long long obase = 0;
         if (lane == 0 && tot) obase = atomicAdd(sp.out_counter, (unsigned long long)tot);
         obase = __shfl_sync(0xffffffffu, obase, 0);
 #pragma unroll
-        for (int u = 0; u < kPhaseB; ++u) {
+        for (int u = 0; u < PB; ++u) {
           if (!live[u]) continue;
           alive_cnt++;
           for (int c = 0; c < sp.n_out; ++c) {
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
         }
       }
 #pragma unroll
-      for (int u = 0; u < kPhaseB; ++u) {
+      for (int u = 0; u < PB; ++u) {
         if (SINK == SINK_OUTPUT_ANY) break;
         uint64_t ext[kMaxStages];
 #pragma unroll
@@ -1169,6 +1170,9 @@ static void launch_pipe(dfgpu_pipeline* p, int64_t n, const char* timer_name) {
   else if (SINK == SINK_AGG && var_env == 1) pipe_kernel<SINK_AGG, false, 1><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else if (SINK == SINK_AGG && var_env == 2) pipe_kernel<SINK_AGG, false, 2><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else if (SINK == SINK_AGG && var_env == 3) pipe_kernel<SINK_AGG, false, 3><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
+  else if (SINK == SINK_AGG && var_env == 4) pipe_kernel<SINK_AGG, false, 4><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
+  else if (SINK == SINK_AGG && var_env == 5) pipe_kernel<SINK_AGG, false, 5><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
+  else if (SINK == SINK_AGG && var_env == 7) pipe_kernel<SINK_AGG, false, 7><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else pipe_kernel<SINK, false><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   DF_LAUNCH_CHECK(ctx);
 }

@@ -1,0 +1,85 @@
+"""One process, many answers (GPU minutes are scarce): event-timed A/B of the opt-in kernel variants at the bench sizes.
+  * Q3 SF100 fused plan with pipe_kernel's prefetch instantiations (DFGPU_PIPE_VAR: bit 0 / 1 prefetches, bit 2 four survivors per lane and phase-B round; read per launch)
+  * C3 group-by (1B rows -> 1M groups, SUM + COUNT) with the paired-accumulator kernel (DFGPU_AGG_PAIRED = 0, 1, 2) and the
+    4-rows-in-flight fast kernel (DFGPU_AGG_R4 = 1), read when the handle is created
+Every variant's result fingerprint must equal the default's.  Prints one JSON object; `winner` = the fastest variant if it beats the
+default by >= 3 %, else the default."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from datafusion_b200 import capi as D
+import q3_device_pipeline as Q
+
+sf = float(sys.argv[1]) if len(sys.argv) > 1 else 100
+rows = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000_000
+ctx = D.Context(0)
+out = {"sf": sf, "agg_rows": rows}
+
+
+def q3(var, steps=6):
+    os.environ["DFGPU_PIPE_VAR"] = str(var)
+    for _ in range(2):
+        res, st = Q.run_q3_fused(ctx, cu, orr, li)
+        fp = Q.result_fingerprint(ctx, res)
+        for b in res: b.release()
+    ctx.set_kernel_timing(True); ctx.kernel_time_reset()
+    e0, e1 = ctx.event(), ctx.event()
+    ctx.record(e0)
+    for _ in range(steps):
+        res, st = Q.run_q3_fused(ctx, cu, orr, li)
+        for b in res: b.release()
+    ctx.record(e1)
+    ms = ctx.elapsed_ms(e0, e1) / steps
+    kt = ctx.kernel_time("pipe:lineitem")
+    ctx.set_kernel_timing(False)
+    return {"var": var, "step_ms": round(ms, 3), "lineitem_kernel_ms": round(kt[0] / max(kt[1], 1), 3), "fingerprint": fp}
+
+
+cu, orr, li = Q.gen_tables(ctx, sf)
+runs = [q3(v) for v in (0, 1, 2, 3, 4, 5, 7, 0)]
+del cu, orr, li
+ctx.trim_device_cache()
+base = min(r["lineitem_kernel_ms"] for r in runs if r["var"] == 0)
+assert all(r["fingerprint"] == runs[0]["fingerprint"] for r in runs), "a prefetch variant changed the result"
+best = min(runs, key=lambda r: r["lineitem_kernel_ms"])
+out["q3"] = {"runs": runs, "baseline_kernel_ms": base, "winner": best["var"] if best["lineitem_kernel_ms"] < 0.97 * base else 0}
+os.environ["DFGPU_PIPE_VAR"] = "0"
+
+g = 1_000_000
+k = ctx.generate_i64(D.GEN_UNIFORM, 5, 0, g, 0, rows); v = ctx.generate_i64(D.GEN_UNIFORM, 6, -2**31, 2**32, 0, rows)
+
+
+def c3(paired, r4=0, iters=3):
+    os.environ["DFGPU_AGG_PAIRED"] = str(paired); os.environ["DFGPU_AGG_R4"] = str(r4)
+    times, fp = [], None
+    ctx.set_kernel_timing(True); ctx.kernel_time_reset()
+    for it in range(iters + 1):
+        e0, e1 = ctx.event(), ctx.event()
+        a = D.AggHandle(ctx, [D.INT64, D.INT64], [0], [(D.AGG_SUM, 1, -1), (D.AGG_COUNT, 1, -1)], capacity_hint=g)
+        ctx.record(e0)
+        a.push_device([D.DeviceColumn(ctx, D.INT64, rows, k), D.DeviceColumn(ctx, D.INT64, rows, v)]); a.finish()
+        ctx.record(e1)
+        if it: times.append(round(ctx.elapsed_ms(e0, e1), 3))
+        res = a.drain(host=False)
+        if fp is None:
+            ng = sum(b.num_rows for b in res)
+            sums = [0, 0, 0]
+            for b in res:
+                for c in range(3):
+                    sums[c] = (sums[c] + D.column_sum_device(ctx, b.column(c))) % (1 << 64)
+            fp = [ng] + sums
+        for b in res: b.release()
+        a.close()
+    kt = ctx.kernel_time("agg_update")
+    ctx.set_kernel_timing(False)
+    return {"paired": paired, "r4": r4, "step_ms": times, "kernel_ms": round(kt[0] / max(kt[1], 1), 3), "fingerprint": fp}
+
+
+aruns = [c3(0), c3(1), c3(2), c3(0, 1), c3(0)]
+abase = min(min(r["step_ms"]) for r in aruns if r["paired"] == 0 and r["r4"] == 0)
+assert all(r["fingerprint"] == aruns[0]["fingerprint"] for r in aruns), "a group-by variant changed the result"
+abest = min(aruns, key=lambda r: min(r["step_ms"]))
+out["c3"] = {"runs": aruns, "baseline_step_ms": abase,
+             "winner_paired": abest["paired"] if min(abest["step_ms"]) < 0.97 * abase else 0,
+             "winner_r4": abest["r4"] if min(abest["step_ms"]) < 0.97 * abase else 0}
+print(json.dumps(out))
