@@ -296,7 +296,8 @@ __device__ __forceinline__ uint32_t valid8(const ColRef& c, int64_t row0, int64_
 // VAR (compile-time, so the default instantiation's code stays what was measured): bit 0 = at the start of phase B, prefetch the argument
 // columns' sectors of the survivors into L2 (the interpreter reads them one dependent DRAM access after the other otherwise);
 // bit 1 = at the start of phase A, prefetch this tile's key column of the first stage (its load is issued only after the predicate's
-// column has arrived and been compared).  DFGPU_PIPE_VAR selects the instantiation (aggregate sink only).
+// column has arrived and been compared); bit 2 = four instead of two survivors per lane and phase-B round; bit 3 = lane-paired REDs in
+// the aggregate sink.  DFGPU_PIPE_VAR selects the instantiation (aggregate sink; bit 1 also for the pack sink).
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 template <int SINK, bool DEC, int VAR = 0>
 __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams* __restrict__ gp, int64_t n, unsigned long long* __restrict__ counters /* [alive, inserted, fail, err] */) {
@@ -530,9 +531,36 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
           }
         }
       }
+      bool sunk = false;
+      if ((VAR & 8) && SINK == SINK_AGG) {
+        // one RED instruction per lane PAIR and row: the row counter and the sum word of a record share a sector, so the even lane adds
+        // its row's count while the odd neighbour adds the same row's value (then the roles swap) — half the L2 reduction requests
+        const AggDef& ag0 = sp.agg[0];
+        if (sp.n_aggs == 1 && ag0.small == 2 && ag0.func == DFGPU_AGG_SUM && ag0.cls != C_F64 && ag0.cls != C_DEC && ag0.nn_word < 0) {
+          sunk = true;
+          const bool even = !(lane & 1);
+#pragma unroll
+          for (int u = 0; u < PB; ++u) {
+            uint64_t ext[kMaxStages];
+#pragma unroll
+            for (int s = 0; s < kMaxStages; ++s) ext[s] = pay[s][u];
+            unsigned long long v = 0;
+            if (live[u]) { alive_cnt++; v = eval_int_fast(sp.pool + ag0.start, ag0.n, row[u], ext); }
+            __syncwarp();
+            const unsigned long long rp = (unsigned long long)arec[u];
+            const unsigned long long prp = __shfl_xor_sync(0xffffffffu, rp, 1);
+            const unsigned long long pv = __shfl_xor_sync(0xffffffffu, v, 1);
+            const bool pl = __shfl_xor_sync(0xffffffffu, live[u] ? 1 : 0, 1) != 0;
+            unsigned long long* const mine = (unsigned long long*)rp + sp.rows_word;    // this lane's row: the row counter
+            unsigned long long* const theirs = (unsigned long long*)prp + ag0.word;     // the neighbour's row: the sum
+            if (even ? live[u] : pl) red_add_u64(even ? mine : theirs, even ? 1ull : pv);     // rows of the even lanes
+            if (even ? pl : live[u]) red_add_u64(even ? theirs : mine, even ? pv : 1ull);     // rows of the odd lanes
+          }
+        }
+      }
 #pragma unroll
       for (int u = 0; u < PB; ++u) {
-        if (SINK == SINK_OUTPUT_ANY) break;
+        if (SINK == SINK_OUTPUT_ANY || sunk) break;
         uint64_t ext[kMaxStages];
 #pragma unroll
         for (int s = 0; s < kMaxStages; ++s) ext[s] = pay[s][u];
@@ -1173,6 +1201,10 @@ static void launch_pipe(dfgpu_pipeline* p, int64_t n, const char* timer_name) {
   else if (SINK == SINK_AGG && var_env == 4) pipe_kernel<SINK_AGG, false, 4><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else if (SINK == SINK_AGG && var_env == 5) pipe_kernel<SINK_AGG, false, 5><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else if (SINK == SINK_AGG && var_env == 7) pipe_kernel<SINK_AGG, false, 7><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
+  else if (SINK == SINK_AGG && var_env == 8) pipe_kernel<SINK_AGG, false, 8><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
+  else if (SINK == SINK_AGG && var_env == 9) pipe_kernel<SINK_AGG, false, 9><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
+  else if (SINK == SINK_AGG && var_env == 11) pipe_kernel<SINK_AGG, false, 11><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
+  else if (SINK == SINK_PACK && (var_env & 2)) pipe_kernel<SINK_PACK, false, 2><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else pipe_kernel<SINK, false><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   DF_LAUNCH_CHECK(ctx);
 }

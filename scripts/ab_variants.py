@@ -30,13 +30,13 @@ def q3(var, steps=6):
         for b in res: b.release()
     ctx.record(e1)
     ms = ctx.elapsed_ms(e0, e1) / steps
-    kt = ctx.kernel_time("pipe:lineitem")
+    kt = ctx.kernel_time("pipe:lineitem"); ko = ctx.kernel_time("pipe:orders")
     ctx.set_kernel_timing(False)
-    return {"var": var, "step_ms": round(ms, 3), "lineitem_kernel_ms": round(kt[0] / max(kt[1], 1), 3), "fingerprint": fp}
+    return {"var": var, "step_ms": round(ms, 3), "lineitem_kernel_ms": round(kt[0] / max(kt[1], 1), 3), "orders_kernel_ms": round(ko[0] / max(ko[1], 1), 3), "fingerprint": fp}
 
 
 cu, orr, li = Q.gen_tables(ctx, sf)
-runs = [q3(v) for v in (0, 1, 2, 3, 4, 5, 7, 0)]
+runs = [q3(v) for v in (0, 1, 2, 3, 4, 5, 7, 8, 9, 11, 0)]
 del cu, orr, li
 ctx.trim_device_cache()
 base = min(r["lineitem_kernel_ms"] for r in runs if r["var"] == 0)
