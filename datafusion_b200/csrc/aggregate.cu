@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(256) agg_verify_wide_kernel(GroupCols g, Table
 // (SUM over a non-null 8-byte integer column, COUNT / COUNT(*) without NULLs or FILTER, and their Final-mode
 // merges) — the C3 shape.  No type switches, no validity reads; 4 rows per thread with the loads hoisted.
 constexpr int kMaxFastAggs = 4;
-constexpr int kAggPairedDefault = 0;
+constexpr int kAggPairedDefault = 1;   // measured: C3 16.36 -> 13.37 ms (profiles/README.md)
 struct FastAggs { int n; const unsigned long long* col[kMaxFastAggs]; unsigned long long* acc[kMaxFastAggs]; };
 
 template <int R, int NA, int B>
@@ -472,7 +472,11 @@ __global__ void __launch_bounds__(256) agg_update_fast_kernel(const unsigned lon
 __device__ __forceinline__ void red_add_u64_pred(unsigned long long* p, unsigned long long v, bool on) {
   if (on) asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
-template <int R>
+// the 32-byte sector of a bucket (four tags) in ONE request: LDG.E.ENL2.256 (sm_100); two 128-bit loads are two L2 requests
+__device__ __forceinline__ void ld_bucket_256(const unsigned long long* p, unsigned long long t[4]) {
+  asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(t[0]), "=l"(t[1]), "=l"(t[2]), "=l"(t[3]) : "l"(p));
+}
+template <int R, bool WIDE>
 __global__ void __launch_bounds__(256) agg_update_pair_kernel(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ col0,
                                                            const unsigned long long* __restrict__ col1, ulonglong2* __restrict__ pairs, TableDev t,
                                                            int64_t row0, int64_t n, const uint32_t* __restrict__ row_list, uint32_t* __restrict__ overflow,
@@ -483,8 +487,7 @@ __global__ void __launch_bounds__(256) agg_update_pair_kernel(const unsigned lon
   // the trip count is warp-uniform (lanes past the end stay in the loop, dead): the lane pairs exchange values with full-mask shuffles
   for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 - lane < n; i0 += stride * R) {
     int64_t row[R];
-    unsigned long long k[R], cur[R], v0[R], v1[R];
-    uint4 bk0[R], bk1[R];
+    unsigned long long k[R], cur[R], v0[R], v1[R], tg[R][4];
     uint64_t s[R];
     bool live[R];
 #pragma unroll
@@ -504,14 +507,21 @@ __global__ void __launch_bounds__(256) agg_update_pair_kernel(const unsigned lon
     for (int r = 0; r < R; ++r) { s[r] = start_slot<1>(t, Key2{k[r], 0ull}); cur[r] = 0; }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      bk0[r] = make_uint4(0, 0, 0, 0); bk1[r] = bk0[r];
-      if (live[r] && k[r] != kEmptyKey) { const uint4* bp = (const uint4*)((const unsigned long long*)t.tags + s[r]); bk0[r] = __ldcg(bp); bk1[r] = __ldcg(bp + 1); }
+      tg[r][0] = tg[r][1] = tg[r][2] = tg[r][3] = 0ull;
+      if (live[r] && k[r] != kEmptyKey) {
+        const unsigned long long* bp = (const unsigned long long*)t.tags + s[r];   // start slots are multiples of four: 32-byte aligned
+        if (WIDE) ld_bucket_256(bp, tg[r]);
+        else {
+          const uint4 b0 = __ldcg((const uint4*)bp), b1 = __ldcg((const uint4*)bp + 1);
+          tg[r][0] = (unsigned long long)b0.x | ((unsigned long long)b0.y << 32); tg[r][1] = (unsigned long long)b0.z | ((unsigned long long)b0.w << 32);
+          tg[r][2] = (unsigned long long)b1.x | ((unsigned long long)b1.y << 32); tg[r][3] = (unsigned long long)b1.z | ((unsigned long long)b1.w << 32);
+        }
+      }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       if (!(live[r] && k[r] != kEmptyKey)) continue;
-      const unsigned long long t0 = (unsigned long long)bk0[r].x | ((unsigned long long)bk0[r].y << 32), t1 = (unsigned long long)bk0[r].z | ((unsigned long long)bk0[r].w << 32);
-      const unsigned long long t2 = (unsigned long long)bk1[r].x | ((unsigned long long)bk1[r].y << 32), t3 = (unsigned long long)bk1[r].z | ((unsigned long long)bk1[r].w << 32);
+      const unsigned long long t0 = tg[r][0], t1 = tg[r][1], t2 = tg[r][2], t3 = tg[r][3];
       if (t0 == k[r] || t0 == kEmptyKey) { cur[r] = t0; }
       else if (t1 == k[r] || t1 == kEmptyKey) { cur[r] = t1; s[r] += 1; }
       else if (t2 == k[r] || t2 == kEmptyKey) { cur[r] = t2; s[r] += 2; }
@@ -820,7 +830,7 @@ struct dfgpu_agg {
   uint64_t pairs_cap = 0;
   bool pairs_dirty = false;
   int fast_r4 = 0;       // DFGPU_AGG_R4 at create (A/B switch): the two-aggregate fast kernel with 4 instead of 2 rows in flight per thread
-  int paired_mode = 0;   // DFGPU_AGG_PAIRED at create: 0 = one RED per aggregate and row; 1 / 2 = agg_update_pair_kernel with 2 / 4 rows in flight per thread
+  int paired_mode = 0;   // DFGPU_AGG_PAIRED at create: 0 = one RED per aggregate and row; agg_update_pair_kernel: 1 = 2 rows in flight per thread (default), 2 = 4 rows, 3 / 4 = 2 / 3 rows + 256-bit bucket load
   std::deque<BatchPtr> outq;
   int64_t m_input_rows = 0, m_output_rows = 0, m_rehashes = 0, m_num_groups = 0, m_input_batches = 0;
   // skip-partial-aggregation probe (aggregates/skip_partial.rs:69-110; config.rs skip_partial_aggregation_probe_*)
@@ -1114,8 +1124,12 @@ static void agg_push(dfgpu_agg* a, const std::vector<DCol>& cols) {
               a->pairs_cap = a->cap;
             }
             a->pairs_dirty = true;
-            if (paired_env >= 2) agg_update_pair_kernel<4><<<grid, 256, 0, ctx->stream>>>(kp, fa.col[0], fa.col[1], a->pairs.as<ulonglong2>(), t, done, work, list, ov, oc);
-            else agg_update_pair_kernel<2><<<grid_for((work + 1) / 2, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(kp, fa.col[0], fa.col[1], a->pairs.as<ulonglong2>(), t, done, work, list, ov, oc);
+            const int grid2 = grid_for((work + 1) / 2, 256, kNumSMs * 8);
+            ulonglong2* pr = a->pairs.as<ulonglong2>();
+            if (paired_env == 2) agg_update_pair_kernel<4, false><<<grid, 256, 0, ctx->stream>>>(kp, fa.col[0], fa.col[1], pr, t, done, work, list, ov, oc);
+            else if (paired_env == 3) agg_update_pair_kernel<2, true><<<grid2, 256, 0, ctx->stream>>>(kp, fa.col[0], fa.col[1], pr, t, done, work, list, ov, oc);
+            else if (paired_env == 4) agg_update_pair_kernel<3, true><<<grid_for((work + 2) / 3, 256, kNumSMs * 8), 256, 0, ctx->stream>>>(kp, fa.col[0], fa.col[1], pr, t, done, work, list, ov, oc);
+            else agg_update_pair_kernel<2, false><<<grid2, 256, 0, ctx->stream>>>(kp, fa.col[0], fa.col[1], pr, t, done, work, list, ov, oc);
           } else if (a->bucketed) {
             if (use_pair) fold_pairs(a);
             const int grid2 = grid_for((work + 1) / 2, 256, kNumSMs * 8);

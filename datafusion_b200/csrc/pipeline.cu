@@ -43,7 +43,7 @@ enum LookupMode : int { LK_HASH = 0, LK_BITMAP = 1 };
 enum SinkKind : int { SINK_NONE = 0, SINK_COUNT = 1, SINK_BUILD = 2, SINK_AGG = 3, SINK_OUTPUT = 4, SINK_OUTPUT_ANY = 5 /* row order unspecified */,
                       SINK_PACK = 6 /* build sink, table size unknown: {key, payload} records to a staging buffer, inserted afterwards */ };
 constexpr int kStageMaybe = 3;   // DFGPU_STAGE_MAYBE
-constexpr int kPipeVarDefault = 0;   // pipe_kernel's VAR when DFGPU_PIPE_VAR is not set
+constexpr int kPipeVarDefault = 11;   // pipe_kernel's VAR when DFGPU_PIPE_VAR is not set
 
 struct LookupDev {
   int mode, stride /* 8-byte words per record */, has_payload, pad;
@@ -248,7 +248,26 @@ __device__ __forceinline__ uint64_t ext32(uint32_t x, int sgn) { return sgn ? (u
 __device__ __forceinline__ uint64_t ext16(uint32_t x, int sgn) { return sgn ? (uint64_t)(int64_t)(int16_t)x : (uint64_t)(x & 0xFFFFu); }
 __device__ __forceinline__ uint64_t ext8(uint32_t x, int sgn) { return sgn ? (uint64_t)(int64_t)(int8_t)x : (uint64_t)(x & 0xFFu); }
 // 8 consecutive elements starting at row0 (a multiple of 8), sign / zero extended to 64 bits
+// 256-bit loads (LDG.E.ENL2.256, sm_100): a lane's 8 rows of a 4-byte column are ONE 32-byte sector, of an 8-byte column two — with
+// 128-bit loads every instruction of the warp asks L2 for 32 HALF sectors (twice the requests for the same bytes)
+__device__ __forceinline__ void ld_stream_v4x64(const void* p, uint64_t pol, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d) {
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p), "l"(pol));
+}
+template <bool WIDE = false>
 __device__ __forceinline__ void load8(const ColRef& c, int64_t row0, int64_t n, uint64_t v[kWarpRows], uint64_t pol) {
+  if (WIDE && c.vec == 2 && row0 + kWarpRows <= n && (c.width == 8 || c.width == 4)) {   // vec == 2: base pointer 32-byte aligned
+    if (c.width == 8) {
+      const char* p = (const char*)c.ptr + row0 * 8;
+      ld_stream_v4x64(p, pol, v[0], v[1], v[2], v[3]);
+      ld_stream_v4x64(p + 32, pol, v[4], v[5], v[6], v[7]);
+    } else {
+      uint64_t a, b, cc, d;
+      ld_stream_v4x64((const char*)c.ptr + row0 * 4, pol, a, b, cc, d);
+      v[0] = ext32((uint32_t)a, c.sgn); v[1] = ext32((uint32_t)(a >> 32), c.sgn); v[2] = ext32((uint32_t)b, c.sgn); v[3] = ext32((uint32_t)(b >> 32), c.sgn);
+      v[4] = ext32((uint32_t)cc, c.sgn); v[5] = ext32((uint32_t)(cc >> 32), c.sgn); v[6] = ext32((uint32_t)d, c.sgn); v[7] = ext32((uint32_t)(d >> 32), c.sgn);
+    }
+    return;
+  }
   if (c.vec && row0 + kWarpRows <= n) {
     switch (c.width) {
       case 8: {
@@ -296,12 +315,14 @@ __device__ __forceinline__ uint32_t valid8(const ColRef& c, int64_t row0, int64_
 // VAR (compile-time, so the default instantiation's code stays what was measured): bit 0 = at the start of phase B, prefetch the argument
 // columns' sectors of the survivors into L2 (the interpreter reads them one dependent DRAM access after the other otherwise);
 // bit 1 = at the start of phase A, prefetch this tile's key column of the first stage (its load is issued only after the predicate's
-// column has arrived and been compared); bit 2 = four instead of two survivors per lane and phase-B round; bit 3 = lane-paired REDs in
-// the aggregate sink.  DFGPU_PIPE_VAR selects the instantiation (aggregate sink; bit 1 also for the pack sink).
+// column has arrived and been compared); bit 3 (8) = lane-paired REDs in the aggregate sink; bit 4 (16) = prefetch the table record and the
+// argument sectors already when a row passes the membership filter in phase A; bit 5 (32) = 256-bit column loads in phase A.  DFGPU_PIPE_VAR selects the instantiation (aggregate sink;
+// bit 1 also for the pack sink); 0 is the round-2 kernel as first measured, 11 the default (profiles/README.md: 8.09 -> 7.50 ms).
+// (Four instead of two survivors per lane and phase-B round was measured too: 13.9 ms, removed.)
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 template <int SINK, bool DEC, int VAR = 0>
 __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams* __restrict__ gp, int64_t n, unsigned long long* __restrict__ counters /* [alive, inserted, fail, err] */) {
-  constexpr int PB = (VAR & 4) ? 4 : kPhaseB, PBG = 32 * PB, QC = PBG + kWarpTile;   // bit 2: four instead of two survivors per lane and phase-B round
+  constexpr int PB = kPhaseB, PBG = kPhaseBGroup, QC = kQueueCap;
   __shared__ PipeParams sp;
   __shared__ uint32_t q_rows[kPipeWarps][QC];
   for (int i = threadIdx.x; i < (int)(sizeof(PipeParams) / 4); i += kPipeThreads) ((uint32_t*)&sp)[i] = ((const uint32_t*)gp)[i];
@@ -331,7 +352,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
         for (int t = 0; t < sp.n_terms; ++t) {
           const ColRef c = sp.col[sp.term_col[t]];
           uint64_t v[kWarpRows];
-          load8(c, row0, n, v, pol_stream);
+          load8<(VAR & 32) != 0>(c, row0, n, v, pol_stream);
           mask &= valid8(c, row0, n);            // a NULL predicate drops the row
           const int op = sp.term_op[t];
           const long long lit = sp.term_lit[t];
@@ -375,7 +396,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
         if (!__any_sync(0xffffffffu, mask != 0)) continue;
         const ColRef kc = sp.col[st.key_col];
         uint64_t key[kWarpRows];
-        load8(kc, row0, n, key, pol_stream);
+        load8<(VAR & 32) != 0>(kc, row0, n, key, pol_stream);
         const uint32_t kvalid = valid8(kc, row0, n);
         if (bitmap) {
           uint32_t w[kWarpRows];
@@ -417,6 +438,27 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
 #pragma unroll
               for (int j = 0; j < kWarpRows; ++j) pass |= (uint32_t)bloom_test(bw[j], bt[j]) << j;
               mask &= pass;
+              if ((VAR & 16) && SINK == SINK_AGG && s == sp.agg_stage && st.lk.cap && st.kind != kStageMaybe) {
+                // the rows that passed the filter reach phase B some tiles later: start their DRAM accesses now (table record, argument sectors)
+#pragma unroll
+                for (int j = 0; j < kWarpRows; ++j)
+                  if ((mask >> j) & 1u) prefetch_l2(st.lk.recs + __umul64hi(lk_hash(key[j]), st.lk.cap) * (uint64_t)st.lk.stride);
+                uint32_t m = mask;
+                while (m) {
+                  const int j = __ffs(m) - 1;
+                  m &= m - 1;
+#pragma unroll 1
+                  for (int a = 0; a < sp.n_aggs; ++a) {
+                    const AggDef& ag = sp.agg[a];
+                    if (ag.small != 2) continue;
+#pragma unroll 1
+                    for (int i = 0; i < ag.n; ++i) {
+                      const ENode& nd = sp.pool[ag.start + i];
+                      if (nd.kind == DFGPU_EXPR_COLUMN) prefetch_l2((const char*)nd.col + (row0 + j) * type_width_prim(nd.out_type));
+                    }
+                  }
+                }
+              }
             }
           }
         }
@@ -1026,7 +1068,7 @@ static void lookup_reserve(dfgpu_lookup* l, int64_t rows) {
 static ColRef col_ref(const DCol& c) {
   ColRef r;
   r.ptr = c.values; r.valid = c.validity; r.voff = c.offset; r.width = type_width(c.type); r.sgn = type_is_signed_int(c.type) ? 1 : 0;
-  r.vec = ((uintptr_t)c.values % 16 == 0) ? 1 : 0; r.pad = 0;
+  r.vec = ((uintptr_t)c.values % 32 == 0) ? 2 : (((uintptr_t)c.values % 16 == 0) ? 1 : 0); r.pad = 0;   // 2: 256-bit loads allowed too
   return r;
 }
 
@@ -1198,13 +1240,17 @@ static void launch_pipe(dfgpu_pipeline* p, int64_t n, const char* timer_name) {
   else if (SINK == SINK_AGG && var_env == 1) pipe_kernel<SINK_AGG, false, 1><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else if (SINK == SINK_AGG && var_env == 2) pipe_kernel<SINK_AGG, false, 2><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else if (SINK == SINK_AGG && var_env == 3) pipe_kernel<SINK_AGG, false, 3><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
-  else if (SINK == SINK_AGG && var_env == 4) pipe_kernel<SINK_AGG, false, 4><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
-  else if (SINK == SINK_AGG && var_env == 5) pipe_kernel<SINK_AGG, false, 5><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
-  else if (SINK == SINK_AGG && var_env == 7) pipe_kernel<SINK_AGG, false, 7><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else if (SINK == SINK_AGG && var_env == 8) pipe_kernel<SINK_AGG, false, 8><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else if (SINK == SINK_AGG && var_env == 9) pipe_kernel<SINK_AGG, false, 9><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else if (SINK == SINK_AGG && var_env == 11) pipe_kernel<SINK_AGG, false, 11><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
+  else if (SINK == SINK_AGG && var_env == 26) pipe_kernel<SINK_AGG, false, 26><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
+  else if (SINK == SINK_AGG && var_env == 27) pipe_kernel<SINK_AGG, false, 27><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
+  else if (SINK == SINK_AGG && var_env == 43) pipe_kernel<SINK_AGG, false, 43><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
+  else if (SINK == SINK_AGG && var_env == 59) pipe_kernel<SINK_AGG, false, 59><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
+  else if (SINK == SINK_PACK && (var_env & 32)) pipe_kernel<SINK_PACK, false, 34><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else if (SINK == SINK_PACK && (var_env & 2)) pipe_kernel<SINK_PACK, false, 2><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
+  else if (SINK == SINK_OUTPUT_ANY && (var_env & 32)) pipe_kernel<SINK_OUTPUT_ANY, false, 34><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);   // the multi-GPU plan's scans
+  else if (SINK == SINK_OUTPUT_ANY && (var_env & 2)) pipe_kernel<SINK_OUTPUT_ANY, false, 2><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else pipe_kernel<SINK, false><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   DF_LAUNCH_CHECK(ctx);
 }

@@ -1,15 +1,17 @@
 """One process, many answers (GPU minutes are scarce): event-timed A/B of the opt-in kernel variants at the bench sizes.
-  * Q3 SF100 fused plan with pipe_kernel's prefetch instantiations (DFGPU_PIPE_VAR: bit 0 / 1 prefetches, bit 2 four survivors per lane and phase-B round; read per launch)
-  * C3 group-by (1B rows -> 1M groups, SUM + COUNT) with the paired-accumulator kernel (DFGPU_AGG_PAIRED = 0, 1, 2) and the
-    4-rows-in-flight fast kernel (DFGPU_AGG_R4 = 1), read when the handle is created
+  * Q3 SF100 fused plan with pipe_kernel's instantiations (DFGPU_PIPE_VAR bits: 1 / 2 prefetches, 8 lane-paired REDs, 16 prefetch at
+    filter-pass time, 32 256-bit column loads; read per launch) against the default instantiation and the round-start kernel (0)
+  * C3 group-by (1B rows -> 1M groups, SUM + COUNT) with the paired-accumulator kernel's modes (DFGPU_AGG_PAIRED = 1 default, 3 / 4 with the
+    256-bit bucket load, 0 = one RED per aggregate and row), read when the handle is created
 Every variant's result fingerprint must equal the default's.  Prints one JSON object; `winner` = the fastest variant if it beats the
-default by >= 3 %, else the default."""
+default by >= 2 %, else the default.  (The first round of this A/B — variants 1, 2, 3, 4, 5, 7, 8, 9, 11 against 0 — is in profiles/README.md.)"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from datafusion_b200 import capi as D
 import q3_device_pipeline as Q
 
+Q3_DEFAULT, C3_DEFAULT = 11, 1   # kPipeVarDefault (pipeline.cu), kAggPairedDefault (aggregate.cu)
 sf = float(sys.argv[1]) if len(sys.argv) > 1 else 100
 rows = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000_000
 ctx = D.Context(0)
@@ -36,14 +38,13 @@ def q3(var, steps=6):
 
 
 cu, orr, li = Q.gen_tables(ctx, sf)
-runs = [q3(v) for v in (0, 1, 2, 3, 4, 5, 7, 8, 9, 11, 0)]
+runs = [q3(v) for v in (Q3_DEFAULT, 27, 26, 43, 59, 0, Q3_DEFAULT)]
 del cu, orr, li
 ctx.trim_device_cache()
-base = min(r["lineitem_kernel_ms"] for r in runs if r["var"] == 0)
+base = min(r["step_ms"] for r in runs if r["var"] == Q3_DEFAULT)
 assert all(r["fingerprint"] == runs[0]["fingerprint"] for r in runs), "a prefetch variant changed the result"
-best = min(runs, key=lambda r: r["lineitem_kernel_ms"])
-out["q3"] = {"runs": runs, "baseline_kernel_ms": base, "winner": best["var"] if best["lineitem_kernel_ms"] < 0.97 * base else 0}
-os.environ["DFGPU_PIPE_VAR"] = "0"
+best = min(runs, key=lambda r: r["step_ms"])
+XX
 
 g = 1_000_000
 k = ctx.generate_i64(D.GEN_UNIFORM, 5, 0, g, 0, rows); v = ctx.generate_i64(D.GEN_UNIFORM, 6, -2**31, 2**32, 0, rows)
@@ -75,11 +76,10 @@ def c3(paired, r4=0, iters=3):
     return {"paired": paired, "r4": r4, "step_ms": times, "kernel_ms": round(kt[0] / max(kt[1], 1), 3), "fingerprint": fp}
 
 
-aruns = [c3(0), c3(1), c3(2), c3(0, 1), c3(0)]
-abase = min(min(r["step_ms"]) for r in aruns if r["paired"] == 0 and r["r4"] == 0)
+aruns = [c3(C3_DEFAULT), c3(3), c3(4), c3(0), c3(C3_DEFAULT)]
+abase = min(min(r["step_ms"]) for r in aruns if r["paired"] == C3_DEFAULT and r["r4"] == 0)
 assert all(r["fingerprint"] == aruns[0]["fingerprint"] for r in aruns), "a group-by variant changed the result"
 abest = min(aruns, key=lambda r: min(r["step_ms"]))
 out["c3"] = {"runs": aruns, "baseline_step_ms": abase,
-             "winner_paired": abest["paired"] if min(abest["step_ms"]) < 0.97 * abase else 0,
-             "winner_r4": abest["r4"] if min(abest["step_ms"]) < 0.97 * abase else 0}
+             "winner_paired": abest["paired"] if min(abest["step_ms"]) < 0.98 * abase else C3_DEFAULT, "winner_r4": 0}
 print(json.dumps(out))

@@ -1,4 +1,5 @@
-"""The paired-accumulator group-by kernel (agg_update_pair_kernel, DFGPU_AGG_PAIRED=1|2): the two-aggregate fast path
+"""The paired-accumulator group-by kernel (agg_update_pair_kernel; DFGPU_AGG_PAIRED = 1 (default) | 2 | 3 | 4, 0 = the kernel with one RED
+per aggregate and row): the two-aggregate fast path
 (SUM + COUNT over a non-null int64 column, the C3 shape; Final-mode merges of two states) with one L2 reduction request
 per row.  Same outputs as the default kernel and as the oracle: bit-exact, rows compared sorted (aggregation_fuzzer/mod.rs:59-86).
 The mode is read when the handle is created, so the tests switch it per handle."""
@@ -17,7 +18,7 @@ def oracle_sum_count(g, v, vv=None):
     return [keys[0]] + O.agg_output_columns(O.A_SUM, res[0], np.int64, False) + O.agg_output_columns(O.A_COUNT, res[1], np.int64, False)
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("mode", ["0", "1", "2", "3", "4"])
 @pytest.mark.parametrize("n,groups,batch_rows,hint", [(100_003, 700, None, 0), (1_000_001, 300_000, 250_000, 0), (2_000_000, 50_000, 999_983, 50_000), (37, 5, 7, 0)])
 def test_paired_sum_count_equals_oracle(gpu_ctx, monkeypatch, mode, n, groups, batch_rows, hint):
     monkeypatch.setenv("DFGPU_AGG_PAIRED", mode)
@@ -29,7 +30,7 @@ def test_paired_sum_count_equals_oracle(gpu_ctx, monkeypatch, mode, n, groups, b
     assert_cols_equal(got, oracle_sum_count(g, v), ordered=False, what=f"paired mode {mode}")
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("mode", ["1", "2", "3", "4"])
 def test_paired_then_generic_batches_fold_correctly(gpu_ctx, monkeypatch, mode):
     """batches without NULLs take the paired kernel, a batch with NULLs takes the generic kernel on the per-aggregate arrays,
     then paired again: the deltas must be folded at every switch, at table growth and before the emit"""
@@ -54,7 +55,7 @@ def test_paired_then_generic_batches_fold_correctly(gpu_ctx, monkeypatch, mode):
     assert_cols_equal(got, oracle_sum_count(g, v, vv), ordered=False, what="paired / generic / paired")
 
 
-@pytest.mark.parametrize("mode", ["0", "1"])
+@pytest.mark.parametrize("mode", ["0", "1", "3"])
 def test_paired_partial_then_final_equals_single(gpu_ctx, monkeypatch, mode):
     monkeypatch.setenv("DFGPU_AGG_PAIRED", mode)
     rng = np.random.default_rng(11)
