@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(256) agg_verify_wide_kernel(GroupCols g, Table
 // (SUM over a non-null 8-byte integer column, COUNT / COUNT(*) without NULLs or FILTER, and their Final-mode
 // merges) — the C3 shape.  No type switches, no validity reads; 4 rows per thread with the loads hoisted.
 constexpr int kMaxFastAggs = 4;
-constexpr int kAggPairedDefault = 1;   // measured: C3 16.36 -> 13.37 ms (profiles/README.md)
+constexpr int kAggPairedDefault = 4;   // measured on C3 (1B rows -> 1M groups): mode 0 16.38 ms, 1 13.4-14.0, 3 11.09, 4 10.69 (profiles/README.md)
 struct FastAggs { int n; const unsigned long long* col[kMaxFastAggs]; unsigned long long* acc[kMaxFastAggs]; };
 
 template <int R, int NA, int B>
@@ -830,7 +830,7 @@ struct dfgpu_agg {
   uint64_t pairs_cap = 0;
   bool pairs_dirty = false;
   int fast_r4 = 0;       // DFGPU_AGG_R4 at create (A/B switch): the two-aggregate fast kernel with 4 instead of 2 rows in flight per thread
-  int paired_mode = 0;   // DFGPU_AGG_PAIRED at create: 0 = one RED per aggregate and row; agg_update_pair_kernel: 1 = 2 rows in flight per thread (default), 2 = 4 rows, 3 / 4 = 2 / 3 rows + 256-bit bucket load
+  int paired_mode = 0;   // DFGPU_AGG_PAIRED at create: 0 = one RED per aggregate and row; agg_update_pair_kernel: 1 = 2 rows in flight per thread, 2 = 4 rows, 3 / 4 = 2 / 3 rows + 256-bit bucket load (4 is the default)
   std::deque<BatchPtr> outq;
   int64_t m_input_rows = 0, m_output_rows = 0, m_rehashes = 0, m_num_groups = 0, m_input_batches = 0;
   // skip-partial-aggregation probe (aggregates/skip_partial.rs:69-110; config.rs skip_partial_aggregation_probe_*)

@@ -43,7 +43,7 @@ enum LookupMode : int { LK_HASH = 0, LK_BITMAP = 1 };
 enum SinkKind : int { SINK_NONE = 0, SINK_COUNT = 1, SINK_BUILD = 2, SINK_AGG = 3, SINK_OUTPUT = 4, SINK_OUTPUT_ANY = 5 /* row order unspecified */,
                       SINK_PACK = 6 /* build sink, table size unknown: {key, payload} records to a staging buffer, inserted afterwards */ };
 constexpr int kStageMaybe = 3;   // DFGPU_STAGE_MAYBE
-constexpr int kPipeVarDefault = 11;   // pipe_kernel's VAR when DFGPU_PIPE_VAR is not set
+constexpr int kPipeVarDefault = 43;   // pipe_kernel's VAR when DFGPU_PIPE_VAR is not set
 
 struct LookupDev {
   int mode, stride /* 8-byte words per record */, has_payload, pad;
@@ -312,13 +312,19 @@ __device__ __forceinline__ uint32_t valid8(const ColRef& c, int64_t row0, int64_
   return nb > 0 ? load_bits32(c.valid, c.voff + row0, nb) : 0u;
 }
 
-// VAR (compile-time, so the default instantiation's code stays what was measured): bit 0 = at the start of phase B, prefetch the argument
-// columns' sectors of the survivors into L2 (the interpreter reads them one dependent DRAM access after the other otherwise);
-// bit 1 = at the start of phase A, prefetch this tile's key column of the first stage (its load is issued only after the predicate's
-// column has arrived and been compared); bit 3 (8) = lane-paired REDs in the aggregate sink; bit 4 (16) = prefetch the table record and the
-// argument sectors already when a row passes the membership filter in phase A; bit 5 (32) = 256-bit column loads in phase A.  DFGPU_PIPE_VAR selects the instantiation (aggregate sink;
-// bit 1 also for the pack sink); 0 is the round-2 kernel as first measured, 11 the default (profiles/README.md: 8.09 -> 7.50 ms).
-// (Four instead of two survivors per lane and phase-B round was measured too: 13.9 ms, removed.)
+// VAR (compile-time, so that an instantiation which has been measured stays byte for byte what it was while others are tried against it):
+//   bit 0 (1)  at the start of phase B, prefetch.global.L2 the survivors' argument sectors (the integer evaluator would read them one
+//              dependent DRAM access after the other);
+//   bit 1 (2)  at the start of phase A, prefetch this tile's key column of the first stage (its load is issued only after the predicate's
+//              column has arrived and been compared);
+//   bit 3 (8)  lane-paired REDs in the aggregate sink: a record's row counter and sum share a sector, so the even lane adds its row's count
+//              while its odd neighbour adds the same row's value (then the roles swap) — one reduction request per row instead of two;
+//   bit 5 (32) 256-bit column loads in phase A (LDG.E.ENL2.256): a lane's 8 rows are one or two whole sectors; with 128-bit loads every
+//              instruction of the warp asks L2 for 32 half sectors.
+// DFGPU_PIPE_VAR selects the instantiation (aggregate sink; bits 1 and 5 also for the pack / unordered-output sinks).  0 is the round-2 kernel as
+// first measured (lineitem pass of Q3 at SF100: 8.1 ms), 11 = 7.5 ms, 43 the default = 7.1 ms (profiles/README.md "L2 request count").  Measured
+// and removed: four instead of two survivors per lane and phase-B round (13.9 ms); prefetching the table record and the argument sectors
+// already when a row passes the membership filter in phase A (10.4 ms: the prefetches of five tiles queue up in front of the column stream).
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 template <int SINK, bool DEC, int VAR = 0>
 __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams* __restrict__ gp, int64_t n, unsigned long long* __restrict__ counters /* [alive, inserted, fail, err] */) {
@@ -438,27 +444,6 @@ __global__ void __launch_bounds__(kPipeThreads, 3) pipe_kernel(const PipeParams*
 #pragma unroll
               for (int j = 0; j < kWarpRows; ++j) pass |= (uint32_t)bloom_test(bw[j], bt[j]) << j;
               mask &= pass;
-              if ((VAR & 16) && SINK == SINK_AGG && s == sp.agg_stage && st.lk.cap && st.kind != kStageMaybe) {
-                // the rows that passed the filter reach phase B some tiles later: start their DRAM accesses now (table record, argument sectors)
-#pragma unroll
-                for (int j = 0; j < kWarpRows; ++j)
-                  if ((mask >> j) & 1u) prefetch_l2(st.lk.recs + __umul64hi(lk_hash(key[j]), st.lk.cap) * (uint64_t)st.lk.stride);
-                uint32_t m = mask;
-                while (m) {
-                  const int j = __ffs(m) - 1;
-                  m &= m - 1;
-#pragma unroll 1
-                  for (int a = 0; a < sp.n_aggs; ++a) {
-                    const AggDef& ag = sp.agg[a];
-                    if (ag.small != 2) continue;
-#pragma unroll 1
-                    for (int i = 0; i < ag.n; ++i) {
-                      const ENode& nd = sp.pool[ag.start + i];
-                      if (nd.kind == DFGPU_EXPR_COLUMN) prefetch_l2((const char*)nd.col + (row0 + j) * type_width_prim(nd.out_type));
-                    }
-                  }
-                }
-              }
             }
           }
         }
@@ -1243,10 +1228,7 @@ static void launch_pipe(dfgpu_pipeline* p, int64_t n, const char* timer_name) {
   else if (SINK == SINK_AGG && var_env == 8) pipe_kernel<SINK_AGG, false, 8><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else if (SINK == SINK_AGG && var_env == 9) pipe_kernel<SINK_AGG, false, 9><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else if (SINK == SINK_AGG && var_env == 11) pipe_kernel<SINK_AGG, false, 11><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
-  else if (SINK == SINK_AGG && var_env == 26) pipe_kernel<SINK_AGG, false, 26><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
-  else if (SINK == SINK_AGG && var_env == 27) pipe_kernel<SINK_AGG, false, 27><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else if (SINK == SINK_AGG && var_env == 43) pipe_kernel<SINK_AGG, false, 43><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
-  else if (SINK == SINK_AGG && var_env == 59) pipe_kernel<SINK_AGG, false, 59><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else if (SINK == SINK_PACK && (var_env & 32)) pipe_kernel<SINK_PACK, false, 34><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else if (SINK == SINK_PACK && (var_env & 2)) pipe_kernel<SINK_PACK, false, 2><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else if (SINK == SINK_OUTPUT_ANY && (var_env & 32)) pipe_kernel<SINK_OUTPUT_ANY, false, 34><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);   // the multi-GPU plan's scans

@@ -1,17 +1,17 @@
 """One process, many answers (GPU minutes are scarce): event-timed A/B of the opt-in kernel variants at the bench sizes.
-  * Q3 SF100 fused plan with pipe_kernel's instantiations (DFGPU_PIPE_VAR bits: 1 / 2 prefetches, 8 lane-paired REDs, 16 prefetch at
-    filter-pass time, 32 256-bit column loads; read per launch) against the default instantiation and the round-start kernel (0)
-  * C3 group-by (1B rows -> 1M groups, SUM + COUNT) with the paired-accumulator kernel's modes (DFGPU_AGG_PAIRED = 1 default, 3 / 4 with the
+  * Q3 SF100 fused plan with pipe_kernel's instantiations (DFGPU_PIPE_VAR bits: 1 / 2 prefetches, 8 lane-paired REDs, 32 256-bit column
+    loads; read per launch) against the default instantiation (43) and the round-start kernel (0)
+  * C3 group-by (1B rows -> 1M groups, SUM + COUNT) with the paired-accumulator kernel's modes (DFGPU_AGG_PAIRED: 4 default, 3 / 4 with the
     256-bit bucket load, 0 = one RED per aggregate and row), read when the handle is created
 Every variant's result fingerprint must equal the default's.  Prints one JSON object; `winner` = the fastest variant if it beats the
-default by >= 2 %, else the default.  (The first round of this A/B — variants 1, 2, 3, 4, 5, 7, 8, 9, 11 against 0 — is in profiles/README.md.)"""
+default by >= 2 %, else the default.  (The two passes of round 2 — profiles/r2c_ab_variants_pass{1,2}.json — are tabulated in profiles/README.md.)"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from datafusion_b200 import capi as D
 import q3_device_pipeline as Q
 
-Q3_DEFAULT, C3_DEFAULT = 11, 1   # kPipeVarDefault (pipeline.cu), kAggPairedDefault (aggregate.cu)
+Q3_DEFAULT, C3_DEFAULT = 43, 4   # kPipeVarDefault (pipeline.cu), kAggPairedDefault (aggregate.cu)
 sf = float(sys.argv[1]) if len(sys.argv) > 1 else 100
 rows = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000_000
 ctx = D.Context(0)
@@ -38,7 +38,7 @@ def q3(var, steps=6):
 
 
 cu, orr, li = Q.gen_tables(ctx, sf)
-runs = [q3(v) for v in (Q3_DEFAULT, 27, 26, 43, 59, 0, Q3_DEFAULT)]
+runs = [q3(v) for v in (Q3_DEFAULT, 11, 9, 3, 0, Q3_DEFAULT)]
 del cu, orr, li
 ctx.trim_device_cache()
 base = min(r["step_ms"] for r in runs if r["var"] == Q3_DEFAULT)
@@ -78,7 +78,7 @@ def c3(paired, r4=0, iters=3):
     return {"paired": paired, "r4": r4, "step_ms": times, "kernel_ms": round(kt[0] / max(kt[1], 1), 3), "fingerprint": fp}
 
 
-aruns = [c3(C3_DEFAULT), c3(3), c3(4), c3(0), c3(C3_DEFAULT)]
+aruns = [c3(C3_DEFAULT), c3(3), c3(1), c3(0), c3(C3_DEFAULT)]
 abase = min(min(r["step_ms"]) for r in aruns if r["paired"] == C3_DEFAULT and r["r4"] == 0)
 assert all(r["fingerprint"] == aruns[0]["fingerprint"] for r in aruns), "a group-by variant changed the result"
 abest = min(aruns, key=lambda r: min(r["step_ms"]))
