@@ -644,12 +644,12 @@ def main():
         q_bytes = 16.0 * nc + 24.0 * no + 28.0 * nl   # whole pipeline: every input column once (this generator's widths)
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_pipeline_traffic.json")))["pipe_kernel_agg_sf100_dram_bytes"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r2c_pipeline_traffic.json")))["pipe_kernel_agg_sf100_dram_bytes"]
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": "pipe_kernel<aggregate> (lineitem: filter -> Bloom -> probe -> SUM into the matched record)" if world == 1 else
                     "pipe_kernel<output> (lineitem: filter -> pushed-down membership filter -> survivors to the exchange)", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write at SF100, profiles/r2_pipeline_traffic.json)",
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write at SF100, profiles/r2c_pipeline_traffic.json)",
                     "peak_source": peak_src, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step, "algorithmic_bytes_per_launch": algo_bytes,
                     "launches_per_step": a_n / args.steps,
                     "whole_pipeline_achieved_gbs": q_bytes / (ms_per_step / 1000.0) / 1e9 if world == 1 else None,
