@@ -321,7 +321,7 @@ __device__ __forceinline__ uint32_t valid8(const ColRef& c, int64_t row0, int64_
 //              while its odd neighbour adds the same row's value (then the roles swap) — one reduction request per row instead of two;
 //   bit 5 (32) 256-bit column loads in phase A (LDG.E.ENL2.256): a lane's 8 rows are one or two whole sectors; with 128-bit loads every
 //              instruction of the warp asks L2 for 32 half sectors.
-// DFGPU_PIPE_VAR selects the instantiation (aggregate sink; bits 1 and 5 also for the pack / unordered-output sinks).  0 is the round-2 kernel as
+// DFGPU_PIPE_VAR selects the instantiation (aggregate sink; bits 1 and 5 also for the pack sink, bit 1 for the unordered-output sink).  0 is the round-2 kernel as
 // first measured (lineitem pass of Q3 at SF100: 8.1 ms), 11 = 7.5 ms, 43 the default = 7.1 ms (profiles/README.md "L2 request count").  Measured
 // and removed: four instead of two survivors per lane and phase-B round (13.9 ms); prefetching the table record and the argument sectors
 // already when a row passes the membership filter in phase A (10.4 ms: the prefetches of five tiles queue up in front of the column stream).
@@ -1231,8 +1231,7 @@ static void launch_pipe(dfgpu_pipeline* p, int64_t n, const char* timer_name) {
   else if (SINK == SINK_AGG && var_env == 43) pipe_kernel<SINK_AGG, false, 43><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else if (SINK == SINK_PACK && (var_env & 32)) pipe_kernel<SINK_PACK, false, 34><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   else if (SINK == SINK_PACK && (var_env & 2)) pipe_kernel<SINK_PACK, false, 2><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
-  else if (SINK == SINK_OUTPUT_ANY && (var_env & 32)) pipe_kernel<SINK_OUTPUT_ANY, false, 34><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);   // the multi-GPU plan's scans
-  else if (SINK == SINK_OUTPUT_ANY && (var_env & 2)) pipe_kernel<SINK_OUTPUT_ANY, false, 2><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
+  else if (SINK == SINK_OUTPUT_ANY && (var_env & 2)) pipe_kernel<SINK_OUTPUT_ANY, false, 2><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);   // the multi-GPU plan's scans (the 256-bit loads were not measured on this sink)
   else pipe_kernel<SINK, false><<<grid, kPipeThreads, 0, ctx->stream>>>(gp, n, cnt);
   DF_LAUNCH_CHECK(ctx);
 }
