@@ -60,3 +60,49 @@ def test_partial_state_schema_and_final_output_schema():
     fin = GpuAggregateExec("Final", ["a"], [AggregateExpr("avg", "b", "AVG(b)"), AggregateExpr("sum", "b", "s"), AggregateExpr("count", "b", "n")], part, input_schema=t.schema)
     assert [(f.name, f.type) for f in fin.schema] == [("a", pa.uint32()), ("AVG(b)", pa.float64()), ("s", pa.float64()), ("n", pa.int64())]
     assert fin.state_input and not fin.state_output and part.state_output and not part.state_input
+
+
+# ---- result types of decimal expressions: the twin's BinaryExpr.data_type against the types the reference's own decimal tests assert
+# (binary.rs:4355-5000, transcribed in tests/golden/decimal_kat.json; arrow-arith's decimal_op rules) ----
+import json
+import os
+import re
+
+from datafusion_b200 import capi as D
+from datafusion_b200.exec import BinaryExpr, CastExpr, Column, Literal
+
+_OPS = {"plus": D.OP_PLUS, "minus": D.OP_MINUS, "multiply": D.OP_MULTIPLY, "divide": D.OP_DIVIDE, "modulo": D.OP_MODULO, "eq": D.OP_EQ, "neq": D.OP_NEQ,
+        "lt": D.OP_LT, "lteq": D.OP_LTEQ, "gt": D.OP_GT, "gteq": D.OP_GTEQ, "is_distinct_from": D.OP_IS_DISTINCT_FROM, "is_not_distinct_from": D.OP_IS_NOT_DISTINCT_FROM}
+
+
+def _pa_type(s):
+    m = re.fullmatch(r"decimal128\((\d+),(-?\d+)\)", s)
+    if m:
+        return pa.decimal128(int(m.group(1)), int(m.group(2)))
+    return {"bool": pa.bool_(), "int32": pa.int32(), "int64": pa.int64(), "float64": pa.float64(), "float32": pa.float32()}[s]
+
+
+def _decimal_cases():
+    d = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "decimal_kat.json")))
+    return [c for c in d["cases"] if "expected" in c and all(it[0] in ("col", "lit", "cast", "op") for it in c["rpn"]) and all(it[0] != "op" or it[1] in _OPS for it in c["rpn"])]
+
+
+@pytest.mark.parametrize("case", _decimal_cases(), ids=lambda c: c["name"])
+def test_decimal_expression_result_types_match_the_reference_vectors(case):
+    schema = pa.schema([pa.field(f"c{i}", _pa_type(c["type"])) for i, c in enumerate(case["cols"])])
+    st = []
+    for it in case["rpn"]:
+        if it[0] == "col":
+            st.append(Column(f"c{it[1]}"))
+        elif it[0] == "lit":
+            st.append(Literal(it[2], _pa_type(it[1])))
+        elif it[0] == "cast":
+            st.append(CastExpr(st.pop(), _pa_type(it[1])))
+        else:
+            r, l = st.pop(), st.pop()
+            st.append(BinaryExpr(l, _OPS[it[1]], r))
+    assert len(st) == 1
+    assert st[0].data_type(schema) == _pa_type(case["expected"]["type"]), case["name"]
+    out = []
+    st[0].rpn(schema, out)                                  # lowers without error, one node per RPN item
+    assert len(out) == len(case["rpn"])
