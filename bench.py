@@ -498,7 +498,8 @@ def secondary_configs(ctx, D, peak):
     assert fp == exp, f"C3 group-by fingerprint {fp} != closed form {exp}"
     algo = 16.0 * gn + 24.0 * ng
     out["C3_groupby_sum_count_1B_rows_1M_groups"] = {"ms_per_step": ms, "rows_per_s": gn / ms * 1e3, "groups": int(g), "achieved_gbs": algo / ms / 1e6, "frac": algo / ms / 1e6 / peak,
-                                                    "fingerprint": fp, "verified": "groups + (3 sum key + 5 sum sum + 7 sum count) mod 2^64 == closed form over the generators"}
+                                                    "fingerprint": fp, "verified": "groups + (3 sum key + 5 sum sum + 7 sum count) mod 2^64 == closed form over the generators",
+                                                    "note": "agg_update_pair_kernel: {sum, count} of a slot share a sector and a lane pair updates them with one RED; the tag bucket is one 256-bit load (DFGPU_AGG_PAIRED=0 for the kernel with one RED per aggregate and row)"}
     gk.free(); gv.free()
     ctx.trim_device_cache()   # every block starts from the same allocator state (its warm-up steps refill the cache)
     # ---- C1 shape: FilterExec x:int64 > c over 100M rows x 2 columns, selectivity 20 % ----
